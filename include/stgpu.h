@@ -1,0 +1,212 @@
+/* stgpu.h — C ABI of libstgpu, the B200 (sm_100a) engine that stands in for StringTie's per-bundle
+ * assembly hot path.
+ *
+ * Drop-in boundary: the reference host calls
+ *     int infer_transcripts(BundleData* bundle);          // rlink.h:380, call site stringtie.cpp:1477
+ * one bundle at a time from a worker thread.  A host that links libstgpu flattens each BundleData
+ * (bundle.h:314-424) into an `stg_bundle_view`, packs thousands of them into an `stg_batch`, and submits
+ * the batch; the library returns what infer_transcripts() would have written back into BundleData.
+ *
+ * Everything here is plain C: pointers + sizes, no C++/torch types.  All functions return 0 on success or
+ * a negative STG_E* code; stg_last_error() gives the message (the reference has no error returns: every
+ * failure is GError()->exit(1), gclib/GBase.cpp:31-53 — the adaptor maps a non-zero return to GError).
+ *
+ * Stage coverage in this build (rows of SURVEY.md §8a):
+ *   a1  boundary data model                      -> stg_bundle_view / stg_packed_batch
+ *   a2  cov_edge_add / add_read_to_cov           -> stg_run(), kernels cov_expand_* / cov_tile
+ *   a3  junction support loop                    -> stg_run(), kernel junc_support
+ *   a4  clamped + BSIZE-blocked prefix scan      -> stg_run(), kernel cov_tile
+ *   a5  get_cov / get_cov_sign                   -> stg_query_cov()
+ */
+#ifndef STGPU_H_
+#define STGPU_H_
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STG_ABI_VERSION 1
+#define STG_BSIZE 10000 /* rlink.cpp:11 — block size of the blocked prefix sums in bpcov */
+
+enum {
+  STG_OK = 0,
+  STG_EINVAL = -1,   /* malformed view / batch */
+  STG_ECUDA = -2,    /* CUDA runtime error (message in stg_last_error) */
+  STG_ENOMEM = -3,
+  STG_ENODEV = -4,   /* no CUDA device: the library never falls back to the CPU */
+  STG_EIO = -5,
+  STG_ERANGE = -6,   /* batch exceeds a 32-bit index space: split it */
+  STG_EUNSUPPORTED = -7
+};
+
+/* read flag bits (CReadAln bit-fields, bundle.h:176-177) */
+#define STG_RF_UNITIG 1u
+#define STG_RF_LONGREAD 2u
+
+/* ---- options: snapshot of the globals rlink.cpp imports (rlink.cpp:16-55; defaults stringtie.cpp:122-190) */
+typedef struct stg_params {
+  uint32_t struct_size; /* = sizeof(stg_params), for forward compatibility */
+  uint32_t junctionsupport; /* 10  anchor length (stringtie.cpp:140) */
+  uint32_t sserror;         /* 25  (stringtie.cpp:141) */
+  int32_t junctionthr;      /* 1   (stringtie.cpp:142) */
+  uint32_t bundledist;      /* 50  (stringtie.cpp:145); -L/--mix force 0 (stringtie.cpp:1014-1023) */
+  int32_t mintranscriptlen; /* 200 */
+  int32_t allowed_nodes;    /* 1000 */
+  float readthr;            /* 1 */
+  float singlethr;          /* 4.75 */
+  float isofrac;            /* 0.01 */
+  float mcov;               /* 1 */
+  uint8_t trim;             /* 1 */
+  uint8_t eonly, nomulti, viral, mixedMode, isnascent, printNascent, guided;
+  uint8_t isunitig;         /* 1 */
+  uint8_t longreads, rawreads;
+  uint8_t includesource;    /* 1 */
+  uint8_t geneabundance, havePtFeatures;
+  uint8_t reserved[18];
+} stg_params;
+
+/* Fill *p with the reference defaults. */
+void stg_params_default(stg_params* p);
+
+/* ---- one bundle, as the host sees it (mirror of BundleData's inputs, bundle.h:314-333) --------------
+ * Coordinates are 1-based inclusive genomic positions exactly as in CReadAln::segs / CJunction.
+ * Junction row 0 is the reference's null sentinel (rlink.cpp:821-824) when n_juncs > 0.              */
+typedef struct stg_bundle_view {
+  int32_t start, end;           /* BundleData::start / end */
+  int32_t n_reads, n_juncs;
+  /* reads, in readlist order (CReadAln, bundle.h:169-230) */
+  const uint32_t* r_start;      /* GSeg::start */
+  const uint32_t* r_end;        /* GSeg::end */
+  const uint32_t* r_len;        /* CReadAln::len */
+  const float* r_count;         /* CReadAln::read_count */
+  const int16_t* r_nh;          /* CReadAln::nh */
+  const int8_t* r_strand;       /* -1, 0, +1 */
+  const uint8_t* r_flags;       /* STG_RF_* */
+  const uint32_t* r_seg_off;    /* [n_reads+1] CSR into seg_* (CReadAln::segs) */
+  const uint32_t* seg_start;
+  const uint32_t* seg_end;
+  const int32_t* rjunc_idx;     /* [n_segs - n_reads] row in j_* of CReadAln::juncs[i]; intron i of read n is
+                                   entry r_seg_off[n] - n + i */
+  const uint32_t* r_pair_off;   /* [n_reads+1] CSR into pair_* (CReadAln::pair_idx / pair_count) */
+  const int32_t* pair_idx;      /* bundle-local read index of the mate (may be -1) */
+  const float* pair_cnt;
+  /* junction table, in BundleData::junction order (CJunction, bundle.h:141-166) */
+  const uint32_t* j_start;
+  const uint32_t* j_end;
+  const int8_t* j_strand;
+  const int8_t* j_guide_match;
+  const double* j_nreads;
+  const double* j_nm;
+  const double* j_mm;
+} stg_bundle_view;
+
+/* ---- a batch of bundles, concatenated SoA (what the bundle batcher produces and the GPU consumes) ----
+ * Same fields as stg_bundle_view with every array concatenated over bundles; offsets (r_seg_off, r_pair_off)
+ * are GLOBAL into the concatenated arrays; pair_idx and rjunc_idx stay bundle-local.                   */
+typedef struct stg_packed_batch {
+  int64_t n_bundles, n_reads, n_segs, n_pairs, n_juncs;
+  const int32_t* b_start;       /* [n_bundles] */
+  const int32_t* b_end;         /* [n_bundles] */
+  const uint32_t* b_read_off;   /* [n_bundles+1] */
+  const uint32_t* b_junc_off;   /* [n_bundles+1] */
+  const uint32_t* r_start;
+  const uint32_t* r_end;
+  const uint32_t* r_len;
+  const float* r_count;
+  const int16_t* r_nh;
+  const int8_t* r_strand;
+  const uint8_t* r_flags;
+  const uint32_t* r_seg_off;    /* [n_reads+1] */
+  const uint32_t* r_pair_off;   /* [n_reads+1] */
+  const uint32_t* seg_start;
+  const uint32_t* seg_end;
+  const int32_t* rjunc_idx;     /* [n_segs - n_reads] */
+  const int32_t* pair_idx;
+  const float* pair_cnt;
+  const uint32_t* j_start;
+  const uint32_t* j_end;
+  const int8_t* j_strand;
+  const int8_t* j_guide_match;
+  const double* j_nreads;
+  const double* j_nm;
+  const double* j_mm;
+} stg_packed_batch;
+
+typedef struct stg_ctx stg_ctx;         /* one per (host process, GPU) */
+typedef struct stg_builder stg_builder; /* host-side bundle batcher (pinned staging) */
+typedef struct stg_dbatch stg_dbatch;   /* a batch resident in HBM + its outputs */
+
+/* ---- lifecycle ------------------------------------------------------------------------------------- */
+int stg_init(const stg_params* params, int device, stg_ctx** out);
+int stg_shutdown(stg_ctx* ctx);
+const char* stg_last_error(const stg_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
+int stg_abi_version(void);
+
+/* ---- bundle batcher: BundleData-shaped views -> one packed batch in pinned host memory ------------- */
+int stg_builder_create(stg_ctx* ctx, stg_builder** out);
+int stg_builder_add(stg_builder* b, const stg_bundle_view* view); /* copies; the view may be freed after */
+int stg_builder_packed(stg_builder* b, stg_packed_batch* out);    /* borrow; valid until reset/destroy */
+int stg_builder_reset(stg_builder* b);
+int stg_builder_destroy(stg_builder* b);
+
+/* ---- device batches --------------------------------------------------------------------------------
+ * stg_upload: validate, plan the HBM layout (bpcov offsets, tiles), allocate, enqueue H2D copies on the
+ *             context stream.  `host` may be pageable or pinned (pinned makes the copies asynchronous).
+ * stg_run:    enqueue every kernel of the stages listed at the top of this file. Asynchronous.
+ * stg_sync:   wait for the context stream.                                                            */
+int stg_upload(stg_ctx* ctx, const stg_packed_batch* host, stg_dbatch** out);
+int stg_run(stg_ctx* ctx, stg_dbatch* batch);
+int stg_sync(stg_ctx* ctx);
+int stg_free_batch(stg_ctx* ctx, stg_dbatch* batch);
+
+/* Outputs of the coverage / junction-support stage (count_good_junctions, rlink.cpp:16656-17136).
+ * bpcov layout in HBM: for bundle b, lane s in {0:-, 1:all, 2:+}, index i in [0, len_b) with
+ * len_b = end-start+3 (rlink.cpp:16875): element cov_off[b] + s*stride[b] + i  (float32).             */
+int stg_cov_layout(const stg_dbatch* batch, int64_t* cov_off /*[n_bundles]*/, int64_t* stride /*[n_bundles]*/,
+                   int64_t* total_floats);
+int stg_fetch_bpcov(stg_ctx* ctx, const stg_dbatch* batch, int64_t bundle, float* out /*[3*len_b], lane-major*/);
+int stg_fetch_bpcov_all(stg_ctx* ctx, const stg_dbatch* batch, float* out /*[total_floats]*/);
+const float* stg_device_bpcov(const stg_dbatch* batch); /* device pointer (for consumers that stay on the GPU) */
+/* CJunction::nreads_good / leftsupport / rightsupport after the stage; each [n_juncs] */
+int stg_fetch_junction_support(stg_ctx* ctx, const stg_dbatch* batch, double* nreads_good, double* leftsupport,
+                               double* rightsupport);
+/* per bundle: sum over the bundle of clamped coverage per lane, get_cov(s, 0, len_b-2) — [n_bundles*3] f64 */
+int stg_fetch_cov_totals(stg_ctx* ctx, const stg_dbatch* batch, double* totals);
+
+/* a5: batched get_cov (sign=0, rlink.cpp:1830) / get_cov_sign (sign=1, rlink.cpp:1842).
+ * start/end are bundle-relative (pos - refstart), lane is the reference's `s` argument. Host arrays. */
+int stg_query_cov(stg_ctx* ctx, const stg_dbatch* batch, int64_t n, const int32_t* bundle, const int8_t* lane,
+                  const uint32_t* start, const uint32_t* end, int sign, double* out);
+
+/* Convenience drop-in for ONE bundle, synchronous (upload + run + fetch), the shape of the reference call. */
+typedef struct stg_bundle_result {
+  float* bpcov;            /* caller-allocated [3*(end-start+3)] or NULL */
+  double* j_nreads_good;   /* caller-allocated [n_juncs] or NULL */
+  double* j_leftsupport;
+  double* j_rightsupport;
+} stg_bundle_result;
+int stg_infer_transcripts(stg_ctx* ctx, const stg_bundle_view* view, stg_bundle_result* result);
+
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------------
+ * With profiling on, stg_run brackets every kernel with CUDA events on the context stream.            */
+int stg_set_profiling(stg_ctx* ctx, int enabled);
+int stg_kernel_count(const stg_ctx* ctx);                       /* kernels launched by the last stg_run */
+int stg_kernel_time(stg_ctx* ctx, int i, const char** name, float* ms); /* after stg_sync */
+int64_t stg_launch_counter(const stg_ctx* ctx);                 /* total kernel launches since init */
+/* algorithmic work of the coverage stage for this batch:
+ * L = sum of bundle lengths (end-start+3), S = mate-merged coverage intervals, J = junction-support updates */
+int stg_batch_stats(stg_ctx* ctx, const stg_dbatch* batch, int64_t* L, int64_t* S, int64_t* J);
+void* stg_stream(stg_ctx* ctx);                                 /* cudaStream_t of the context */
+
+/* ---- packed-batch files (.stgb): named little-endian arrays; used by tests, bench and the oracle tools
+ * file := "STGB" u32 version u32 n_arrays { char name[24]; u32 dtype; u32 pad; u64 count; bytes (padded to 8) } */
+enum { STG_DT_I8 = 1, STG_DT_U8 = 2, STG_DT_I16 = 3, STG_DT_I32 = 4, STG_DT_U32 = 5, STG_DT_F32 = 6,
+       STG_DT_F64 = 7, STG_DT_I64 = 8 };
+#define STG_FILE_MAGIC 0x42475453u /* "STGB" */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STGPU_H_ */
