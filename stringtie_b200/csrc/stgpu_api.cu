@@ -1,0 +1,518 @@
+// stgpu_api.cu — host side of libstgpu: the C ABI of include/stgpu.h, the bundle batcher, HBM layout planning,
+// kernel sequencing and result fetch.  No CPU compute path exists here: without a CUDA device stg_init fails.
+#include "stgpu_internal.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace {
+
+thread_local std::string tl_error;
+
+struct Timed { const char* name; cudaEvent_t e0, e1; };
+
+}  // namespace
+
+struct stg_ctx {
+  int device = 0;
+  int num_sms = 0;
+  stg_params params;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  bool profiling = false;
+  std::vector<Timed> timed;      // events of the last stg_run
+  std::vector<cudaEvent_t> event_pool;
+  size_t event_used = 0;
+  int64_t launches = 0;
+  std::mutex mu;
+};
+
+struct stg_builder {
+  stg_ctx* ctx;
+  std::vector<int32_t> b_start, b_end;
+  std::vector<uint32_t> b_read_off{0}, b_junc_off{0};
+  std::vector<uint32_t> r_start, r_end, r_len;
+  std::vector<float> r_count;
+  std::vector<int16_t> r_nh;
+  std::vector<int8_t> r_strand;
+  std::vector<uint8_t> r_flags;
+  std::vector<uint32_t> r_seg_off{0}, r_pair_off{0}, seg_start, seg_end;
+  std::vector<int32_t> rjunc_idx, pair_idx;
+  std::vector<float> pair_cnt;
+  std::vector<uint32_t> j_start, j_end;
+  std::vector<int8_t> j_strand, j_guide_match;
+  std::vector<double> j_nreads, j_nm, j_mm;
+};
+
+struct stg_dbatch {
+  DevBatchView v;
+  std::vector<void*> allocs;       // everything cudaMalloc'ed for this batch
+  std::vector<int64_t> h_cov_off;  // [n_bundles] float offset of lane 0 of bundle b (= 3*gbase)
+  std::vector<int64_t> h_stride;   // [n_bundles]
+  std::vector<uint32_t> h_len;
+  int64_t ivl_capacity = 0;
+  int64_t sum_len = 0;
+  bool ran = false;
+};
+
+namespace {
+
+int fail(stg_ctx* ctx, int code, const std::string& msg) {
+  tl_error = msg;
+  if (ctx) ctx->error = msg;
+  return code;
+}
+
+#define CK(ctx, call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(ctx, STG_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));            \
+  } while (0)
+
+template <class T>
+int dev_alloc(stg_ctx* ctx, stg_dbatch* d, T** out, int64_t count) {
+  void* p = nullptr;
+  size_t bytes = (size_t)std::max<int64_t>(count, 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail(ctx, STG_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  d->allocs.push_back(p);
+  *out = (T*)p;
+  return STG_OK;
+}
+
+template <class T>
+int dev_upload(stg_ctx* ctx, stg_dbatch* d, const T** out, const T* host, int64_t count) {
+  T* p = nullptr;
+  int rc = dev_alloc(ctx, d, &p, count);
+  if (rc) return rc;
+  if (count > 0) CK(ctx, cudaMemcpyAsync(p, host, (size_t)count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  *out = p;
+  return STG_OK;
+}
+
+void free_batch_allocs(stg_dbatch* d) {
+  for (void* p : d->allocs) cudaFree(p);
+  d->allocs.clear();
+}
+
+cudaEvent_t take_event(stg_ctx* ctx) {
+  if (ctx->event_used == ctx->event_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->event_pool.push_back(e);
+  }
+  return ctx->event_pool[ctx->event_used++];
+}
+
+struct Scope {  // brackets a group of launches with events when profiling is on
+  stg_ctx* ctx; Timed t; bool on;
+  Scope(stg_ctx* c, const char* name, int nlaunch) : ctx(c), on(c->profiling) {
+    ctx->launches += nlaunch;
+    t.name = name;
+    if (on) { t.e0 = take_event(ctx); t.e1 = take_event(ctx); cudaEventRecord(t.e0, ctx->stream); }
+  }
+  ~Scope() { if (on) { cudaEventRecord(t.e1, ctx->stream); ctx->timed.push_back(t); } }
+};
+
+int validate(stg_ctx* ctx, const stg_packed_batch* h) {
+  if (!h) return fail(ctx, STG_EINVAL, "null batch");
+  if (h->n_bundles < 0 || h->n_reads < 0 || h->n_segs < h->n_reads || h->n_pairs < 0 || h->n_juncs < 0)
+    return fail(ctx, STG_EINVAL, "negative or inconsistent counts");
+  if (h->n_reads >= (int64_t)0x7fffffff || h->n_segs >= (int64_t)0xffffffffLL || h->n_pairs >= (int64_t)0xffffffffLL ||
+      h->n_juncs >= (int64_t)0x7fffffff)
+    return fail(ctx, STG_ERANGE, "batch exceeds 32-bit index space; split it");
+  if (h->n_bundles == 0) return STG_OK;
+  if (h->b_read_off[0] != 0 || h->b_read_off[h->n_bundles] != (uint32_t)h->n_reads)
+    return fail(ctx, STG_EINVAL, "b_read_off does not span the reads");
+  if (h->b_junc_off[0] != 0 || h->b_junc_off[h->n_bundles] != (uint32_t)h->n_juncs)
+    return fail(ctx, STG_EINVAL, "b_junc_off does not span the junctions");
+  if (h->n_reads && (h->r_seg_off[0] != 0 || h->r_seg_off[h->n_reads] != (uint32_t)h->n_segs))
+    return fail(ctx, STG_EINVAL, "r_seg_off does not span the segments");
+  if (h->n_reads && (h->r_pair_off[0] != 0 || h->r_pair_off[h->n_reads] != (uint32_t)h->n_pairs))
+    return fail(ctx, STG_EINVAL, "r_pair_off does not span the pair links");
+  for (int64_t b = 0; b < h->n_bundles; b++) {
+    if (h->b_end[b] < h->b_start[b]) return fail(ctx, STG_EINVAL, "bundle with end < start");
+    if (h->b_read_off[b + 1] < h->b_read_off[b] || h->b_junc_off[b + 1] < h->b_junc_off[b])
+      return fail(ctx, STG_EINVAL, "bundle offsets not monotone");
+  }
+  return STG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void stg_params_default(stg_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->struct_size = sizeof(stg_params);
+  p->junctionsupport = 10; p->sserror = 25; p->junctionthr = 1; p->bundledist = 50;
+  p->mintranscriptlen = 200; p->allowed_nodes = 1000;
+  p->readthr = 1.f; p->singlethr = 4.75f; p->isofrac = 0.01f; p->mcov = 1.f;
+  p->trim = 1; p->isunitig = 1; p->includesource = 1;
+}
+
+int stg_abi_version(void) { return STG_ABI_VERSION; }
+
+const char* stg_last_error(const stg_ctx* ctx) { return ctx ? ctx->error.c_str() : tl_error.c_str(); }
+
+int stg_init(const stg_params* params, int device, stg_ctx** out) {
+  if (!out) return fail(nullptr, STG_EINVAL, "stg_init: out is null");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, STG_ENODEV, std::string("no CUDA device (libstgpu has no CPU path): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, STG_EINVAL, "stg_init: bad device index");
+  stg_ctx* ctx = new stg_ctx();
+  ctx->device = device;
+  if (params) {
+    if (params->struct_size != sizeof(stg_params)) { delete ctx; return fail(nullptr, STG_EINVAL, "stg_params.struct_size mismatch"); }
+    ctx->params = *params;
+  } else stg_params_default(&ctx->params);
+  if (ctx->params.longreads || ctx->params.mixedMode) {
+    delete ctx;
+    return fail(nullptr, STG_EUNSUPPORTED, "long-read / mixed mode junction correction (rlink.cpp:16668-16975) is not built yet");
+  }
+  CK(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(nullptr, cudaGetDeviceProperties(&prop, device));
+  ctx->num_sms = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    delete ctx;
+    return fail(nullptr, STG_ENODEV, "libstgpu is built for sm_100a (B200) only");
+  }
+  CK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  *out = ctx;
+  return STG_OK;
+}
+
+int stg_shutdown(stg_ctx* ctx) {
+  if (!ctx) return STG_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return STG_OK;
+}
+
+void* stg_stream(stg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// ---- bundle batcher -----------------------------------------------------------------------------------------
+int stg_builder_create(stg_ctx* ctx, stg_builder** out) {
+  if (!out) return fail(ctx, STG_EINVAL, "stg_builder_create: out is null");
+  stg_builder* b = new stg_builder();
+  b->ctx = ctx;
+  *out = b;
+  return STG_OK;
+}
+
+int stg_builder_add(stg_builder* b, const stg_bundle_view* v) {
+  if (!b || !v) return fail(nullptr, STG_EINVAL, "stg_builder_add: null argument");
+  if (v->n_reads < 0 || v->n_juncs < 0 || v->end < v->start) return fail(b->ctx, STG_EINVAL, "stg_builder_add: bad view");
+  const int32_t nr = v->n_reads;
+  const uint32_t nseg = nr ? v->r_seg_off[nr] - v->r_seg_off[0] : 0;
+  const uint32_t npair = nr ? v->r_pair_off[nr] - v->r_pair_off[0] : 0;
+  const uint32_t seg_base = (uint32_t)b->seg_start.size(), pair_base = (uint32_t)b->pair_idx.size();
+  b->b_start.push_back(v->start); b->b_end.push_back(v->end);
+  for (int32_t n = 0; n < nr; n++) {
+    const uint32_t ns = v->r_seg_off[n + 1] - v->r_seg_off[n];
+    if (ns < 1) return fail(b->ctx, STG_EINVAL, "stg_builder_add: read without segments");
+    b->r_start.push_back(v->r_start[n]); b->r_end.push_back(v->r_end[n]); b->r_len.push_back(v->r_len[n]);
+    b->r_count.push_back(v->r_count[n]); b->r_nh.push_back(v->r_nh[n]); b->r_strand.push_back(v->r_strand[n]);
+    b->r_flags.push_back(v->r_flags[n]);
+    b->r_seg_off.push_back(seg_base + (v->r_seg_off[n + 1] - v->r_seg_off[0]));
+    b->r_pair_off.push_back(pair_base + (v->r_pair_off[n + 1] - v->r_pair_off[0]));
+  }
+  const uint32_t s0 = nr ? v->r_seg_off[0] : 0, p0 = nr ? v->r_pair_off[0] : 0;
+  b->seg_start.insert(b->seg_start.end(), v->seg_start + s0, v->seg_start + s0 + nseg);
+  b->seg_end.insert(b->seg_end.end(), v->seg_end + s0, v->seg_end + s0 + nseg);
+  b->rjunc_idx.insert(b->rjunc_idx.end(), v->rjunc_idx, v->rjunc_idx + (nseg - (uint32_t)nr));
+  b->pair_idx.insert(b->pair_idx.end(), v->pair_idx + p0, v->pair_idx + p0 + npair);
+  b->pair_cnt.insert(b->pair_cnt.end(), v->pair_cnt + p0, v->pair_cnt + p0 + npair);
+  b->j_start.insert(b->j_start.end(), v->j_start, v->j_start + v->n_juncs);
+  b->j_end.insert(b->j_end.end(), v->j_end, v->j_end + v->n_juncs);
+  b->j_strand.insert(b->j_strand.end(), v->j_strand, v->j_strand + v->n_juncs);
+  b->j_guide_match.insert(b->j_guide_match.end(), v->j_guide_match, v->j_guide_match + v->n_juncs);
+  b->j_nreads.insert(b->j_nreads.end(), v->j_nreads, v->j_nreads + v->n_juncs);
+  b->j_nm.insert(b->j_nm.end(), v->j_nm, v->j_nm + v->n_juncs);
+  b->j_mm.insert(b->j_mm.end(), v->j_mm, v->j_mm + v->n_juncs);
+  b->b_read_off.push_back((uint32_t)b->r_start.size());
+  b->b_junc_off.push_back((uint32_t)b->j_start.size());
+  return STG_OK;
+}
+
+int stg_builder_packed(stg_builder* b, stg_packed_batch* o) {
+  if (!b || !o) return fail(nullptr, STG_EINVAL, "stg_builder_packed: null argument");
+  o->n_bundles = (int64_t)b->b_start.size(); o->n_reads = (int64_t)b->r_start.size();
+  o->n_segs = (int64_t)b->seg_start.size(); o->n_pairs = (int64_t)b->pair_idx.size(); o->n_juncs = (int64_t)b->j_start.size();
+  o->b_start = b->b_start.data(); o->b_end = b->b_end.data(); o->b_read_off = b->b_read_off.data();
+  o->b_junc_off = b->b_junc_off.data(); o->r_start = b->r_start.data(); o->r_end = b->r_end.data();
+  o->r_len = b->r_len.data(); o->r_count = b->r_count.data(); o->r_nh = b->r_nh.data(); o->r_strand = b->r_strand.data();
+  o->r_flags = b->r_flags.data(); o->r_seg_off = b->r_seg_off.data(); o->r_pair_off = b->r_pair_off.data();
+  o->seg_start = b->seg_start.data(); o->seg_end = b->seg_end.data(); o->rjunc_idx = b->rjunc_idx.data();
+  o->pair_idx = b->pair_idx.data(); o->pair_cnt = b->pair_cnt.data(); o->j_start = b->j_start.data();
+  o->j_end = b->j_end.data(); o->j_strand = b->j_strand.data(); o->j_guide_match = b->j_guide_match.data();
+  o->j_nreads = b->j_nreads.data(); o->j_nm = b->j_nm.data(); o->j_mm = b->j_mm.data();
+  return STG_OK;
+}
+
+int stg_builder_reset(stg_builder* b) {
+  if (!b) return STG_OK;
+  stg_ctx* ctx = b->ctx;
+  *b = stg_builder();
+  b->ctx = ctx;
+  return STG_OK;
+}
+
+int stg_builder_destroy(stg_builder* b) { delete b; return STG_OK; }
+
+// ---- upload: validate, plan the layout, copy ----------------------------------------------------------------
+int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
+  if (!ctx || !out) return fail(ctx, STG_EINVAL, "stg_upload: null argument");
+  *out = nullptr;
+  int rc = validate(ctx, h);
+  if (rc) return rc;
+  CK(ctx, cudaSetDevice(ctx->device));
+  stg_dbatch* d = new stg_dbatch();
+  DevBatchView& v = d->v;
+  memset(&v, 0, sizeof(v));
+  v.n_bundles = h->n_bundles; v.n_reads = h->n_reads; v.n_segs = h->n_segs; v.n_pairs = h->n_pairs; v.n_juncs = h->n_juncs;
+  const int64_t nb = h->n_bundles;
+  // layout
+  std::vector<uint32_t> len(nb), stride(nb), gbase(nb + 1), tile_off(nb + 1);
+  d->h_cov_off.resize(nb); d->h_stride.resize(nb); d->h_len.resize(nb);
+  uint64_t g = 0, t = 0;
+  for (int64_t b = 0; b < nb; b++) {
+    const uint64_t l = (uint64_t)((int64_t)h->b_end[b] - (int64_t)h->b_start[b] + 3);
+    const uint64_t s = (l + STG_LANE_ALIGN - 1) / STG_LANE_ALIGN * STG_LANE_ALIGN;
+    if (l >= 0x7fffffffull) { delete d; return fail(ctx, STG_ERANGE, "bundle span too large"); }
+    len[b] = (uint32_t)l; stride[b] = (uint32_t)s; gbase[b] = (uint32_t)g; tile_off[b] = (uint32_t)t;
+    d->h_cov_off[b] = (int64_t)(3 * g); d->h_stride[b] = (int64_t)s; d->h_len[b] = (uint32_t)l;
+    d->sum_len += (int64_t)l;
+    g += s; t += (l + STG_TILE_W - 1) / STG_TILE_W;
+    if (g >= 0xffffffffull || t >= 0xffffffffull) { delete d; return fail(ctx, STG_ERANGE, "batch spans more than 2^32 positions; split it"); }
+  }
+  gbase[nb] = (uint32_t)g; tile_off[nb] = (uint32_t)t;
+  v.total_pos = (int64_t)g; v.n_tiles = (int64_t)t;
+
+#define UP(field, count) do { rc = dev_upload(ctx, d, &v.field, h->field, (int64_t)(count)); if (rc) { free_batch_allocs(d); delete d; return rc; } } while (0)
+  UP(b_start, nb); UP(b_end, nb); UP(b_read_off, nb + 1); UP(b_junc_off, nb + 1);
+  UP(r_start, h->n_reads); UP(r_end, h->n_reads); UP(r_len, h->n_reads); UP(r_count, h->n_reads); UP(r_nh, h->n_reads);
+  UP(r_strand, h->n_reads); UP(r_flags, h->n_reads); UP(r_seg_off, h->n_reads + 1); UP(r_pair_off, h->n_reads + 1);
+  UP(seg_start, h->n_segs); UP(seg_end, h->n_segs); UP(rjunc_idx, h->n_segs - h->n_reads);
+  UP(pair_idx, h->n_pairs); UP(pair_cnt, h->n_pairs);
+  UP(j_start, h->n_juncs); UP(j_end, h->n_juncs); UP(j_strand, h->n_juncs); UP(j_guide_match, h->n_juncs);
+  UP(j_nreads, h->n_juncs); UP(j_nm, h->n_juncs); UP(j_mm, h->n_juncs);
+#undef UP
+#define UPV(field, vec) do { rc = dev_upload(ctx, d, &v.field, vec.data(), (int64_t)vec.size()); if (rc) { free_batch_allocs(d); delete d; return rc; } } while (0)
+  UPV(b_len, len); UPV(b_stride, stride); UPV(b_gbase, gbase); UPV(b_tile_off, tile_off);
+#undef UPV
+  // the layout vectors are pageable locals: make sure their copies have left the host before they die
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+#define AL(field, count) do { rc = dev_alloc(ctx, d, &v.field, (int64_t)(count)); if (rc) { free_batch_allocs(d); delete d; return rc; } } while (0)
+  AL(r_ivl_cnt, h->n_reads + 1);
+  AL(scan_partials, scan_partials_needed(std::max<int64_t>(h->n_reads + 1, h->n_segs * 2 + h->n_pairs * 4 + 16)));
+  AL(tile_carry, v.n_tiles * 8); AL(tile_flag, v.n_tiles); AL(tile_ticket, 1);
+  AL(bpcov, 3 * v.total_pos);
+  AL(j_nreads_good, h->n_juncs); AL(j_leftsupport, h->n_juncs); AL(j_rightsupport, h->n_juncs);
+  AL(b_cov_total, nb * 3);
+#undef AL
+  // the padding between a lane's length and its stride is written by the tile kernel; nothing else to clear
+  *out = d;
+  return STG_OK;
+}
+
+int stg_free_batch(stg_ctx* ctx, stg_dbatch* d) {
+  if (!d) return STG_OK;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  free_batch_allocs(d);
+  delete d;
+  return STG_OK;
+}
+
+// ---- run: the kernel sequence of the stage -----------------------------------------------------------------
+int stg_run(stg_ctx* ctx, stg_dbatch* d) {
+  if (!ctx || !d) return fail(ctx, STG_EINVAL, "stg_run: null argument");
+  CK(ctx, cudaSetDevice(ctx->device));
+  DevBatchView& v = d->v;
+  cudaStream_t st = ctx->stream;
+  ctx->timed.clear();
+  ctx->event_used = 0;
+  KernelParams kp{ctx->params.junctionsupport, ctx->params.junctionthr, ctx->params.longreads};
+  if (v.n_juncs) {
+    CK(ctx, cudaMemsetAsync(v.j_nreads_good, 0, sizeof(double) * v.n_juncs, st));
+    CK(ctx, cudaMemsetAsync(v.j_leftsupport, 0, sizeof(double) * v.n_juncs, st));
+    CK(ctx, cudaMemsetAsync(v.j_rightsupport, 0, sizeof(double) * v.n_juncs, st));
+  }
+  if (v.n_tiles) CK(ctx, cudaMemsetAsync(v.tile_flag, 0, sizeof(uint32_t) * v.n_tiles, st));
+  CK(ctx, cudaMemsetAsync(v.tile_ticket, 0, sizeof(uint32_t), st));
+  { Scope s(ctx, "expand_count+junction_support", 1); CK(ctx, launch_expand_count(v, kp, st)); }
+  { Scope s(ctx, "scan_interval_offsets", 3); CK(ctx, launch_scan_exclusive_add(v.r_ivl_cnt, v.n_reads + 1, v.scan_partials, st)); }
+  // the interval count sizes the next buffers: one 4-byte read-back (the only host sync inside the stage)
+  uint32_t n_ivl = 0;
+  if (v.n_reads) {
+    CK(ctx, cudaMemcpyAsync(&n_ivl, v.r_ivl_cnt + v.n_reads, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+  }
+  v.n_ivl = n_ivl;
+  if ((int64_t)n_ivl > d->ivl_capacity) {
+    const int64_t cap = (int64_t)n_ivl + (int64_t)n_ivl / 16 + 1024;
+    int rc;
+    if ((rc = dev_alloc(ctx, d, &v.ivl_a, cap)) || (rc = dev_alloc(ctx, d, &v.ivl_b, cap)) ||
+        (rc = dev_alloc(ctx, d, &v.ivl_w, cap)) || (rc = dev_alloc(ctx, d, &v.ivl_lane, cap)) ||
+        (rc = dev_alloc(ctx, d, &v.ivl_pmax_b, cap)) || (rc = dev_alloc(ctx, d, &v.ivl_smin_a, cap)))
+      return rc;
+    // scan scratch must cover the interval arrays too
+    uint32_t* sp = nullptr;
+    if ((rc = dev_alloc(ctx, d, &sp, scan_partials_needed(std::max<int64_t>(cap, v.n_reads + 1))))) return rc;
+    v.scan_partials = sp;
+    d->ivl_capacity = cap;
+  }
+  { Scope s(ctx, "expand_write", 1); CK(ctx, launch_expand_write(v, st)); }
+  { Scope s(ctx, "window_scans", 6); CK(ctx, launch_window_scans(v, st)); }
+  { Scope s(ctx, "cov_tile", 1); CK(ctx, launch_cov_tiles(v, ctx->num_sms, st)); }
+  { Scope s(ctx, "cov_totals", 1); CK(ctx, launch_cov_totals(v, st)); }
+  d->ran = true;
+  return STG_OK;
+}
+
+int stg_sync(stg_ctx* ctx) {
+  if (!ctx) return fail(nullptr, STG_EINVAL, "stg_sync: null ctx");
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return STG_OK;
+}
+
+// ---- results ------------------------------------------------------------------------------------------------
+int stg_cov_layout(const stg_dbatch* d, int64_t* cov_off, int64_t* stride, int64_t* total_floats) {
+  if (!d) return fail(nullptr, STG_EINVAL, "stg_cov_layout: null batch");
+  for (int64_t b = 0; b < d->v.n_bundles; b++) {
+    if (cov_off) cov_off[b] = d->h_cov_off[b];
+    if (stride) stride[b] = d->h_stride[b];
+  }
+  if (total_floats) *total_floats = 3 * d->v.total_pos;
+  return STG_OK;
+}
+
+const float* stg_device_bpcov(const stg_dbatch* d) { return d ? d->v.bpcov : nullptr; }
+
+int stg_fetch_bpcov(stg_ctx* ctx, const stg_dbatch* d, int64_t b, float* out) {
+  if (!ctx || !d || !out || b < 0 || b >= d->v.n_bundles) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov: bad argument");
+  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov: batch has not been run");
+  CK(ctx, cudaSetDevice(ctx->device));
+  const size_t len = d->h_len[b];
+  CK(ctx, cudaMemcpy2DAsync(out, len * sizeof(float), d->v.bpcov + d->h_cov_off[b], (size_t)d->h_stride[b] * sizeof(float),
+                            len * sizeof(float), 3, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return STG_OK;
+}
+
+int stg_fetch_bpcov_all(stg_ctx* ctx, const stg_dbatch* d, float* out) {
+  if (!ctx || !d || !out) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_all: bad argument");
+  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_all: batch has not been run");
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaMemcpyAsync(out, d->v.bpcov, sizeof(float) * 3 * (size_t)d->v.total_pos, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return STG_OK;
+}
+
+int stg_fetch_junction_support(stg_ctx* ctx, const stg_dbatch* d, double* good, double* left, double* right) {
+  if (!ctx || !d) return fail(ctx, STG_EINVAL, "stg_fetch_junction_support: bad argument");
+  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_fetch_junction_support: batch has not been run");
+  CK(ctx, cudaSetDevice(ctx->device));
+  const size_t nb = sizeof(double) * (size_t)d->v.n_juncs;
+  if (nb) {
+    if (good) CK(ctx, cudaMemcpyAsync(good, d->v.j_nreads_good, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (left) CK(ctx, cudaMemcpyAsync(left, d->v.j_leftsupport, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (right) CK(ctx, cudaMemcpyAsync(right, d->v.j_rightsupport, nb, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return STG_OK;
+}
+
+int stg_fetch_cov_totals(stg_ctx* ctx, const stg_dbatch* d, double* totals) {
+  if (!ctx || !d || !totals) return fail(ctx, STG_EINVAL, "stg_fetch_cov_totals: bad argument");
+  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_fetch_cov_totals: batch has not been run");
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (d->v.n_bundles)
+    CK(ctx, cudaMemcpyAsync(totals, d->v.b_cov_total, sizeof(double) * 3 * (size_t)d->v.n_bundles, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return STG_OK;
+}
+
+int stg_query_cov(stg_ctx* ctx, const stg_dbatch* d, int64_t n, const int32_t* bundle, const int8_t* lane,
+                  const uint32_t* start, const uint32_t* end, int sign, double* out) {
+  if (!ctx || !d || n < 0 || (n && (!bundle || !lane || !start || !end || !out)))
+    return fail(ctx, STG_EINVAL, "stg_query_cov: bad argument");
+  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_query_cov: batch has not been run");
+  if (n == 0) return STG_OK;
+  for (int64_t i = 0; i < n; i++) {
+    if (bundle[i] < 0 || bundle[i] >= d->v.n_bundles || lane[i] < 0 || lane[i] > 2 || end[i] < start[i] ||
+        (uint64_t)end[i] + 1 >= d->h_len[bundle[i]])
+      return fail(ctx, STG_EINVAL, "stg_query_cov: query outside its bundle");
+  }
+  CK(ctx, cudaSetDevice(ctx->device));
+  int32_t* db = nullptr; int8_t* dl = nullptr; uint32_t *ds = nullptr, *de = nullptr; double* dout = nullptr;
+  CK(ctx, cudaMalloc(&db, n * sizeof(int32_t))); CK(ctx, cudaMalloc(&dl, n)); CK(ctx, cudaMalloc(&ds, n * 4));
+  CK(ctx, cudaMalloc(&de, n * 4)); CK(ctx, cudaMalloc(&dout, n * 8));
+  cudaStream_t st = ctx->stream;
+  CK(ctx, cudaMemcpyAsync(db, bundle, n * 4, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(dl, lane, n, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(ds, start, n * 4, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(de, end, n * 4, cudaMemcpyHostToDevice, st));
+  ctx->launches++;
+  CK(ctx, launch_query_cov(d->v, n, db, dl, ds, de, sign, dout, st));
+  CK(ctx, cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  cudaFree(db); cudaFree(dl); cudaFree(ds); cudaFree(de); cudaFree(dout);
+  return STG_OK;
+}
+
+int stg_infer_transcripts(stg_ctx* ctx, const stg_bundle_view* view, stg_bundle_result* result) {
+  if (!ctx || !view || !result) return fail(ctx, STG_EINVAL, "stg_infer_transcripts: null argument");
+  stg_builder* b = nullptr;
+  int rc = stg_builder_create(ctx, &b);
+  if (rc) return rc;
+  stg_dbatch* d = nullptr;
+  stg_packed_batch pb;
+  if (!(rc = stg_builder_add(b, view)) && !(rc = stg_builder_packed(b, &pb)) && !(rc = stg_upload(ctx, &pb, &d)) &&
+      !(rc = stg_run(ctx, d))) {
+    if (result->bpcov) rc = stg_fetch_bpcov(ctx, d, 0, result->bpcov);
+    if (!rc) rc = stg_fetch_junction_support(ctx, d, result->j_nreads_good, result->j_leftsupport, result->j_rightsupport);
+  }
+  stg_free_batch(ctx, d);
+  stg_builder_destroy(b);
+  return rc;
+}
+
+// ---- measurement hooks ------------------------------------------------------------------------------------------
+int stg_set_profiling(stg_ctx* ctx, int enabled) {
+  if (!ctx) return fail(nullptr, STG_EINVAL, "stg_set_profiling: null ctx");
+  ctx->profiling = enabled != 0;
+  return STG_OK;
+}
+
+int stg_kernel_count(const stg_ctx* ctx) { return ctx ? (int)ctx->timed.size() : 0; }
+
+int stg_kernel_time(stg_ctx* ctx, int i, const char** name, float* ms) {
+  if (!ctx || i < 0 || i >= (int)ctx->timed.size()) return fail(ctx, STG_EINVAL, "stg_kernel_time: bad index");
+  if (name) *name = ctx->timed[i].name;
+  if (ms) CK(ctx, cudaEventElapsedTime(ms, ctx->timed[i].e0, ctx->timed[i].e1));
+  return STG_OK;
+}
+
+int64_t stg_launch_counter(const stg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int stg_batch_stats(stg_ctx* ctx, const stg_dbatch* d, int64_t* L, int64_t* S, int64_t* J) {
+  if (!d) return fail(ctx, STG_EINVAL, "stg_batch_stats: null batch");
+  if (L) *L = d->sum_len;
+  if (S) *S = d->v.n_ivl;           // valid after stg_run
+  if (J) *J = d->v.n_segs - d->v.n_reads;
+  return STG_OK;
+}
+
+}  // extern "C"

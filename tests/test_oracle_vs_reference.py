@@ -1,0 +1,80 @@
+"""Pins the CPU restatement (oracle/stg_oracle.c) to the reference: golden vectors dumped from the reference binary
+itself (tests/golden/make_golden.py) and, where oracle/_ref/ref_hot is present, live runs of the reference's own
+count_good_junctions() on generated packed batches.  Bar: bit-exact float32 bpcov, exact f64 junction support."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from stringtie_b200 import synth
+from stringtie_b200.stgb import read_stgb, write_stgb
+from tests import orc
+from tests.conftest import ROOT
+
+REF_HOT = os.path.join(ROOT, "oracle", "_ref", "ref_hot")
+
+
+def _check(arrays, ref):
+    cov, off, good, left, right = orc.run(arrays)
+    assert cov.size == ref["s1_cov"].size
+    assert np.array_equal(cov.view(np.uint32), ref["s1_cov"].view(np.uint32)), "bpcov differs from the reference"
+    assert np.array_equal(good, ref["s1_j_nreads_good"])
+    assert np.array_equal(left, ref["s1_j_leftsupport"])
+    assert np.array_equal(right, ref["s1_j_rightsupport"])
+
+
+def test_oracle_matches_golden(golden):
+    assert golden["b_cov_stage"].min() == 1  # dumped right after count_good_junctions
+    assert golden["b_cov_final_same"].all()  # build_graphs never modifies bpcov
+    _check(golden, golden)
+
+
+def test_golden_has_inexact_weights(golden):
+    # the fixtures must exercise order-dependent float accumulation (NH=3,5,6 -> 1/3, 1/5, 1/6)
+    assert np.isin(golden["r_nh"], [3, 5, 6]).any()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_HOT), reason="reference harness not built (oracle/_ref is built from /root/reference)")
+@pytest.mark.parametrize("case", ["synth", "adv1", "adv2"])
+def test_oracle_matches_live_reference(tmp_path, case):
+    if case == "synth":
+        a = synth.make_batch(n_bundles=40, reads_per_bundle=800, seed=3)
+    else:
+        a = synth.make_adversarial(seed=int(case[-1]) + 10, n_bundles=14)
+    src, dst = str(tmp_path / "in.stgb"), str(tmp_path / "out.stgb")
+    write_stgb(src, a)
+    subprocess.check_call([REF_HOT, src, "--dump", dst], stdout=subprocess.DEVNULL)
+    _check(a, read_stgb(dst))
+
+
+def test_get_cov_against_bruteforce(golden):
+    """get_cov on the blocked prefix layout == plain sum of the clamped coverage, across BSIZE block borders."""
+    a = golden
+    cov, off, *_ = orc.run(a)
+    lens = a["b_end"].astype(np.int64) - a["b_start"] + 3
+    b = int(np.argmax(lens))
+    L = int(lens[b])
+    assert L > 20000
+    c = cov[off[b]:off[b + 1]].copy()
+    lane1 = c[L:2 * L].astype(np.float64)
+    # undo the blocked prefix sums to per-base coverage
+    per = np.empty(L)
+    for i in range(L):
+        per[i] = lane1[i] - (lane1[i - 1] if i % 10000 else 0.0)
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        s = int(rng.integers(0, L - 3))
+        e = int(rng.integers(s, L - 2))
+        got = orc.get_cov(c, L, 1, s, e)
+        want = per[s + 1:e + 2].sum()
+        # the stored prefix sums are float32: differences carry ~ulp(prefix) absolute error
+        assert abs(got - want) <= 1e-3 * max(1.0, want) + 4 * np.finfo(np.float32).eps * lane1.max()
+
+
+def test_stats_counts(golden):
+    L, S, J = orc.stats(golden)
+    lens = golden["b_end"].astype(np.int64) - golden["b_start"] + 3
+    assert L == int(lens.sum())
+    assert J == golden["seg_start"].size - golden["r_start"].size
+    assert S > 0
