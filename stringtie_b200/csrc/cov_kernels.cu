@@ -8,6 +8,7 @@
 //   get_cov / get_cov_sign           rlink.cpp:1830-1853
 //
 // Design: thousands of bundles are processed at once.
+//   K0  junc_anchor    one thread per junction row: the anchor length it demands (10 or 25).
 //   K1  expand_count   one thread per read: counts the coverage intervals the read deposits (mate merge walk)
 //                      and adds its junction support with f64 atomics (exact, hence order-free: DESIGN.md §3.4).
 //   K2  scan           exclusive prefix sum of the counts (3-phase block scan).
@@ -15,7 +16,10 @@
 //                      in reference order, so "index order" == the order the reference applies deposits in.
 //   K4  window scans   prefix max of the -w positions, suffix min of the +w positions: both are monotone, so
 //                      a sub-tile finds the contiguous slice of intervals that can touch it by two searches.
-//   K5  cov_tile       one WARP per sub-tile of 1024 positions x 3 strand lanes held in shared memory:
+//   K4b tile_plan      one thread per sub-tile: the two searches + everything else the tile kernel needs, as one
+//                      32-byte record, in column-major ticket order (all first sub-tiles of all bundles, then
+//                      all second ones ...) so that resident warps work on ~3500 different bundles at once.
+//   K5  cov_tile       one WARP per sub-tile of 512 positions x 3 strand lanes held in shared memory:
 //                      ordered deposit of the slice (float32 adds land on every address in reference order —
 //                      bit-exact for any weights), then the two sequential recurrences over the sub-tile with
 //                      the (c, b) state handed from the previous sub-tile of the bundle through global memory,
@@ -38,6 +42,21 @@ __device__ __forceinline__ uint32_t find_bundle_of_read(const uint32_t* __restri
     if (__ldg(b_read_off + mid) <= n) lo = mid; else hi = mid;
   }
   return lo;
+}
+
+// same, but the warp first tries the bundle of its first lane (reads of a warp almost always share a bundle)
+__device__ __forceinline__ uint32_t find_bundle_of_read_warp(const uint32_t* __restrict__ b_read_off, int64_t nb,
+                                                             uint32_t n, bool active) {
+  const uint32_t mask = __activemask();
+  const int leader = __ffs(mask) - 1;
+  uint32_t b = 0;
+  if ((int)(threadIdx.x & 31) == leader) b = find_bundle_of_read(b_read_off, nb, n);
+  b = __shfl_sync(mask, b, leader);
+  if (active) {
+    // lanes beyond the leader's bundle walk forward (bundles may be empty: skip while the next one starts <= n)
+    while (b + 1 < (uint32_t)nb && __ldg(b_read_off + b + 1) <= n) b++;
+  }
+  return b;
 }
 
 // Walk the coverage intervals read n deposits, in the reference's order (rlink.cpp:144-219):
@@ -96,13 +115,35 @@ __device__ __forceinline__ void walk_read_intervals(const DevBatchView& v, uint3
 }
 
 // --------------------------------------------------------------------------------------------------------------
+// K0: per-junction anchor requirement (rlink.cpp:16991-16997): junctionsupport, raised to longintronanchor for
+// introns longer than longintron or (short reads) junctions whose non-mismatch support is below junctionthr
+// --------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) junc_anchor_kernel(DevBatchView v, KernelParams prm) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= v.n_juncs) return;
+  uint32_t anchor = prm.junctionsupport;
+  const uint32_t jlen = v.j_end[j] - v.j_start[j] + 1;
+  if (jlen > 100000u /*longintron, rlink.h:31*/ ||
+      (!prm.longreads && v.j_nreads[j] - v.j_nm[j] < (double)prm.junctionthr && v.j_mm[j] == 0.0)) {
+    if (anchor < 25u /*longintronanchor, rlink.h:32*/) anchor = 25u;
+  }
+  v.junc_anchor[j] = (uint8_t)(anchor > 255u ? 255u : anchor);
+}
+
+cudaError_t launch_junc_anchor(const DevBatchView& v, const KernelParams& p, cudaStream_t st) {
+  if (v.n_juncs == 0) return cudaSuccess;
+  junc_anchor_kernel<<<(unsigned)((v.n_juncs + 255) / 256), 256, 0, st>>>(v, p);
+  return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------------------------------
 // K1: count intervals per read + junction support
 // --------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) expand_count_kernel(DevBatchView v, KernelParams prm) {
   const int64_t n64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n64 >= v.n_reads) return;
   const uint32_t n = (uint32_t)n64;
-  const uint32_t b = find_bundle_of_read(v.b_read_off, v.n_bundles, n);
+  const uint32_t b = find_bundle_of_read_warp(v.b_read_off, v.n_bundles, n, true);
   const uint32_t r0 = v.b_read_off[b];
   uint32_t cnt = 0;
   walk_read_intervals(v, r0, n, [&](uint32_t, uint32_t, float, int) { cnt++; });
@@ -110,7 +151,7 @@ __global__ void __launch_bounds__(256) expand_count_kernel(DevBatchView v, Kerne
   if (n64 == v.n_reads - 1) v.r_ivl_cnt[v.n_reads] = 0;
 
   // junction support (rlink.cpp:16890-17016): left anchor = longest exon at or before the intron,
-  // right anchor = longest exon after it; the anchor threshold is raised for long / weak introns.
+  // right anchor = longest exon after it.
   const uint32_t s0 = v.r_seg_off[n], s1 = v.r_seg_off[n + 1];
   const uint32_t nex = s1 - s0;
   if (nex < 2) return;
@@ -128,6 +169,7 @@ __global__ void __launch_bounds__(256) expand_count_kernel(DevBatchView v, Kerne
       if (i < kLocal) rsup[i] = m;
     }
   }
+  const double w = (double)rdcount;
   uint32_t lmax = 0;
   for (uint32_t i = 1; i < nex; i++) {
     const uint32_t l = v.seg_end[s0 + i - 1] - v.seg_start[s0 + i - 1] + 1;
@@ -144,13 +186,7 @@ __global__ void __launch_bounds__(256) expand_count_kernel(DevBatchView v, Kerne
       }
     }
     const uint32_t j = j0 + (uint32_t)jl;
-    uint32_t anchor = prm.junctionsupport;
-    const uint32_t jlen = v.j_end[j] - v.j_start[j] + 1;
-    if (jlen > 100000u /*longintron, rlink.h:31*/ ||
-        (!prm.longreads && v.j_nreads[j] - v.j_nm[j] < (double)prm.junctionthr && v.j_mm[j] == 0.0)) {
-      if (anchor < 25u /*longintronanchor, rlink.h:32*/) anchor = 25u;
-    }
-    const double w = (double)rdcount;
+    const uint32_t anchor = v.junc_anchor[j];
     if (lmax >= anchor) {
       atomicAdd(v.j_leftsupport + j, w);
       if (rmax >= anchor) { atomicAdd(v.j_rightsupport + j, w); atomicAdd(v.j_nreads_good + j, w); }
@@ -168,8 +204,9 @@ __global__ void __launch_bounds__(256) expand_write_kernel(DevBatchView v) {
   if (n64 >= v.n_reads) return;
   const uint32_t n = (uint32_t)n64;
   uint32_t k = v.r_ivl_cnt[n];
-  if (k == v.r_ivl_cnt[n + 1]) return;
-  const uint32_t b = find_bundle_of_read(v.b_read_off, v.n_bundles, n);
+  const bool any = k != v.r_ivl_cnt[n + 1];
+  const uint32_t b = find_bundle_of_read_warp(v.b_read_off, v.n_bundles, n, any);
+  if (!any) return;
   const uint32_t r0 = v.b_read_off[b];
   const uint32_t gb = v.b_gbase[b];
   const uint32_t refstart = (uint32_t)v.b_start[b];
@@ -179,10 +216,9 @@ __global__ void __launch_bounds__(256) expand_write_kernel(DevBatchView v) {
     uint32_t ia = start - refstart + 1, ib = end - refstart + 2;
     if (start < refstart || ib >= len) { ia = 0; ib = 0; w = 0.f; }  // read outside its bundle: dropped (the
                                                                     // reference would write out of bounds)
-    v.ivl_a[k] = gb + ia;
-    v.ivl_b[k] = gb + ib;
-    v.ivl_w[k] = w;
-    v.ivl_lane[k] = (uint8_t)lane;
+    v.ivl[k] = make_uint4(gb + ia, gb + ib, __float_as_uint(w), (uint32_t)lane);
+    v.ivl_smin_a[k] = gb + ia;
+    v.ivl_pmax_b[k] = gb + ib;
     k++;
   });
 }
@@ -305,9 +341,9 @@ cudaError_t launch_scan_exclusive_add(uint32_t* data, int64_t n_plus_1, uint32_t
 }
 
 cudaError_t launch_window_scans(const DevBatchView& v, cudaStream_t st) {
-  cudaError_t e = run_scan<OP_MAX, false, false>(v.ivl_b, v.ivl_pmax_b, v.n_ivl, v.scan_partials, st);
+  cudaError_t e = run_scan<OP_MAX, false, false>(v.ivl_pmax_b, v.ivl_pmax_b, v.n_ivl, v.scan_partials, st);
   if (e != cudaSuccess) return e;
-  return run_scan<OP_MIN, true, false>(v.ivl_a, v.ivl_smin_a, v.n_ivl, v.scan_partials, st);
+  return run_scan<OP_MIN, true, false>(v.ivl_smin_a, v.ivl_smin_a, v.n_ivl, v.scan_partials, st);
 }
 
 cudaError_t launch_expand_count(const DevBatchView& v, const KernelParams& p, cudaStream_t st) {
@@ -323,83 +359,135 @@ cudaError_t launch_expand_write(const DevBatchView& v, cudaStream_t st) {
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// K5: the tile kernel
+// K4b: per-tile plan records, in ticket (column-major) order
 // --------------------------------------------------------------------------------------------------------------
-// first index in [lo, hi) with arr[idx] >= key (arr non-decreasing); whole warp cooperates (32-ary search)
-__device__ __forceinline__ uint32_t warp_lower_bound(const uint32_t* __restrict__ arr, uint32_t lo, uint32_t hi,
-                                                     uint32_t key, int lane) {
-  while (hi - lo > 32) {
-    const uint32_t step = (hi - lo + 31) / 32;
-    uint32_t p = lo + (uint32_t)(lane + 1) * step - 1;  // last index of my slice
-    if (p >= hi) p = hi - 1;
-    const bool ge = __ldg(arr + p) >= key;
-    const uint32_t m = __ballot_sync(FULL, ge);
-    if (m == 0) return hi;
-    const int f = __ffs(m) - 1;
-    const uint32_t nlo = lo + (uint32_t)f * step;
-    uint32_t nhi = nlo + step;
-    if (nhi > hi) nhi = hi;
-    lo = nlo; hi = nhi;  // arr[hi-1] >= key, so the answer is inside
+// first index in [lo, hi) with arr[idx] >= key (arr non-decreasing)
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ arr, uint32_t lo, uint32_t hi,
+                                                    uint32_t key) {
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(arr + mid) >= key) hi = mid; else lo = mid + 1;
   }
-  const uint32_t idx = lo + lane;
-  const bool ge = idx < hi && __ldg(arr + idx) >= key;
-  const uint32_t m = __ballot_sync(FULL, ge);
-  return m ? lo + (__ffs(m) - 1) : hi;
+  return lo;
 }
 
-int cov_tile_smem_bytes() { return STG_TILE_WARPS * (4 * STG_TILE_W) * 4; }
+__global__ void __launch_bounds__(256) tile_plan_kernel(DevBatchView v) {
+  const int64_t t64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t64 >= v.n_tiles) return;
+  const uint32_t t = (uint32_t)t64;
+  // column j = last j with col_off[j] <= t; rank within the column -> bundle
+  uint32_t lo = 0, hi = (uint32_t)v.n_cols;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(v.col_off + mid) <= t) lo = mid; else hi = mid;
+  }
+  const uint32_t jt = lo;
+  const uint32_t b = v.b_order[t - v.col_off[jt]];
+  const uint32_t len = v.b_len[b];
+  const uint32_t i0 = jt * STG_TILE_W;
+  TileRec r;
+  r.gbase = v.b_gbase[b];
+  r.g0 = r.gbase + i0;
+  r.npos = min((uint32_t)STG_TILE_W, len - i0);
+  r.stride = v.b_stride[b];
+  r.tile_id = v.b_tile_off[b] + jt;
+  r.pad = 0;
+  const uint32_t K0 = v.r_ivl_cnt[v.b_read_off[b]], K1 = v.r_ivl_cnt[v.b_read_off[b + 1]];
+  r.k0 = lower_bound_u32(v.ivl_pmax_b, K0, K1, r.g0);             // first interval whose -w lands at or after g0
+  r.k1 = lower_bound_u32(v.ivl_smin_a, K0, K1, r.g0 + r.npos);    // first interval from which every +w is past the tile
+  if (r.k1 < r.k0) r.k1 = r.k0;
+  v.tile_plan[t] = r;
+}
+
+cudaError_t launch_tile_plan(const DevBatchView& v, cudaStream_t st) {
+  if (v.n_tiles == 0) return cudaSuccess;
+  tile_plan_kernel<<<(unsigned)((v.n_tiles + 255) / 256), 256, 0, st>>>(v);
+  return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K5: the tile kernel
+// --------------------------------------------------------------------------------------------------------------
+constexpr int TW = STG_TILE_W;          // positions per sub-tile
+constexpr int TWS = TW + 4;             // lane stride in shared memory (+4 floats: the three chain threads hit
+                                        // different banks with their 128-bit accesses)
+constexpr int TNW = TW / 32;            // 32-position words per sub-tile
+constexpr int TILE_SMEM_WORDS = 3 * TWS + TW + 3 * TNW + 3 * TNW;  // d, stamp, masks, fills
+
+int cov_tile_smem_bytes() { return STG_TILE_WARPS * TILE_SMEM_WORDS * 4; }
+
+__device__ __forceinline__ void deposit_one(float* d, uint32_t sl, uint32_t p, float w, bool add) {
+  float* q = d + sl * TWS + p;
+  *q = add ? __fadd_rn(*q, w) : __fsub_rn(*q, w);
+  if (sl != 1) {
+    float* q1 = d + TWS + p;
+    *q1 = add ? __fadd_rn(*q1, w) : __fsub_rn(*q1, w);
+  }
+}
 
 __global__ void __launch_bounds__(STG_TILE_WARPS * 32, 1) cov_tile_kernel(DevBatchView v) {
-  constexpr int W = STG_TILE_W;
   extern __shared__ __align__(16) uint32_t smem_raw[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float* d = reinterpret_cast<float*>(smem_raw) + (size_t)wid * 4 * W;   // d[3][W]
-  uint32_t* stamp = reinterpret_cast<uint32_t*>(d + 3 * W);              // stamp[W]
+  float* d = reinterpret_cast<float*>(smem_raw) + (size_t)wid * TILE_SMEM_WORDS;  // d[3][TWS]
+  uint32_t* stamp = reinterpret_cast<uint32_t*>(d + 3 * TWS);                     // stamp[TW]
+  uint32_t* masks = stamp + TW;                                                   // masks[3][TNW]
+  float* fills = reinterpret_cast<float*>(masks + 3 * TNW);                       // fills[3][TNW]
+
+  // stamps persist across the sub-tiles of this warp: keys only ever decrease, so stale ones never match
+  for (int q = lane; q < TW; q += 32) stamp[q] = FULL;
+  uint32_t epoch = 0x03ffffffu;
+  __syncwarp();
 
   for (;;) {
     uint32_t t = 0;
     if (lane == 0) t = atomicAdd(v.tile_ticket, 1u);
     t = __shfl_sync(FULL, t, 0);
     if ((int64_t)t >= v.n_tiles) break;
+    // one 32-byte record per sub-tile
+    uint32_t recw = 0;
+    if (lane < 8) recw = __ldg(reinterpret_cast<const uint32_t*>(v.tile_plan + t) + lane);
+    const uint32_t g0 = __shfl_sync(FULL, recw, 0), gbase = __shfl_sync(FULL, recw, 1);
+    const uint32_t k0 = __shfl_sync(FULL, recw, 2), k1 = __shfl_sync(FULL, recw, 3);
+    const uint32_t stride = __shfl_sync(FULL, recw, 4), npos = __shfl_sync(FULL, recw, 5);
+    const uint32_t tile_id = __shfl_sync(FULL, recw, 6);
+    const uint32_t i0 = g0 - gbase;
 
-    // which bundle: last b with b_tile_off[b] <= t
-    uint32_t lo = 0, hi = (uint32_t)v.n_bundles;
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (__ldg(v.b_tile_off + mid) <= t) lo = mid; else hi = mid;
+    // state handed over by the previous sub-tile of this bundle: issue the loads now, consume them after the deposit
+    float c = 0.f, bs = 0.f;
+    bool have_carry = (i0 == 0);
+    if (!have_carry) {
+      uint32_t f = 0;
+      if (lane == 0) f = atomicAdd(v.tile_flag + (tile_id - 1), 0u);
+      f = __shfl_sync(FULL, f, 0);
+      if (f) {
+        __threadfence();
+        if (lane < 3) { c = __ldcg(v.tile_carry + (size_t)(tile_id - 1) * 8 + lane); bs = __ldcg(v.tile_carry + (size_t)(tile_id - 1) * 8 + 4 + lane); }
+        have_carry = true;
+      }
     }
-    const uint32_t b = lo;
-    const uint32_t jt = t - v.b_tile_off[b];
-    const uint32_t len = v.b_len[b];
-    const uint32_t i0 = jt * W;
-    const uint32_t npos = min((uint32_t)W, len - i0);
-    const uint32_t g0 = v.b_gbase[b] + i0, g1 = g0 + npos;
 
+    if (epoch < 0x10000u) {  // (practically never) restart the key space
+      for (int q = lane; q < TW; q += 32) stamp[q] = FULL;
+      epoch = 0x03ffffffu;
+    }
     // clear the sub-tile
     {
       float4* d4 = reinterpret_cast<float4*>(d);
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int q = lane; q < 3 * W / 4; q += 32) d4[q] = z;
-      uint4* s4 = reinterpret_cast<uint4*>(stamp);
-      const uint4 o = make_uint4(FULL, FULL, FULL, FULL);
-      for (int q = lane; q < W / 4; q += 32) s4[q] = o;
+      for (int q = lane; q < 3 * TWS / 4; q += 32) d4[q] = z;
     }
     __syncwarp();
 
-    // the slice of intervals that can deposit into [g0, g1)
-    const uint32_t K0 = v.r_ivl_cnt[v.b_read_off[b]], K1 = v.r_ivl_cnt[v.b_read_off[b + 1]];
-    const uint32_t k0 = warp_lower_bound(v.ivl_pmax_b, K0, K1, g0, lane);
-    const uint32_t k1 = warp_lower_bound(v.ivl_smin_a, K0, K1, g1, lane);
-
-    // ordered deposit. `epoch` decreases, so keys of later rounds are smaller than any stale stamp.
-    uint32_t epoch = 0x03ffffffu;
+    // ordered deposit of intervals [k0, k1). `epoch` decreases, so keys of later rounds are smaller than stale stamps.
+    uint4 cur = make_uint4(FULL, FULL, 0u, 1u);
+    if (k0 + lane < k1) cur = __ldcs(v.ivl + k0 + lane);
     for (uint32_t kb = k0; kb < k1; kb += 32) {
-      const uint32_t k = kb + lane;
-      uint32_t a = 0, z = 0; float w = 0.f; int sl = 1;
-      if (k < k1) { a = v.ivl_a[k]; z = v.ivl_b[k]; w = v.ivl_w[k]; sl = v.ivl_lane[k]; }
-      const bool ina = k < k1 && a >= g0 && a < g1;
-      const bool inz = k < k1 && z >= g0 && z < g1;
-      const uint32_t pa = a - g0, pz = z - g0;
+      uint4 nxt = make_uint4(FULL, FULL, 0u, 1u);
+      if (kb + 32 + lane < k1) nxt = __ldcs(v.ivl + kb + 32 + lane);
+      const uint32_t pa = cur.x - g0, pz = cur.y - g0;   // unsigned: out-of-tile positions become >= npos
+      const bool ina = pa < npos, inz = pz < npos;
+      const float w = __uint_as_float(cur.z);
+      const uint32_t sl = cur.w;
       // round 0: plain stores detect whether any two lanes share a position
       uint32_t key = (epoch << 5) | (uint32_t)lane; epoch--;
       if (ina) stamp[pa] = key;
@@ -407,11 +495,11 @@ __global__ void __launch_bounds__(STG_TILE_WARPS * 32, 1) cov_tile_kernel(DevBat
       __syncwarp();
       const bool mine = (!ina || stamp[pa] == key) && (!inz || stamp[pz] == key);
       if (__all_sync(FULL, mine)) {
-        if (ina) { d[sl * W + pa] = __fadd_rn(d[sl * W + pa], w); if (sl != 1) d[W + pa] = __fadd_rn(d[W + pa], w); }
-        if (inz) { d[sl * W + pz] = __fsub_rn(d[sl * W + pz], w); if (sl != 1) d[W + pz] = __fsub_rn(d[W + pz], w); }
+        if (ina) deposit_one(d, sl, pa, w, true);
+        if (inz) deposit_one(d, sl, pz, w, false);
         __syncwarp();
       } else {
-        // some position is hit by several intervals of this group: apply in lane (= reference) order.
+        // some position is hit by several intervals of this group: apply in lane (= reference) order
         bool pending = ina || inz;
         while (__any_sync(FULL, pending)) {
           key = (epoch << 5) | (uint32_t)lane; epoch--;
@@ -419,51 +507,101 @@ __global__ void __launch_bounds__(STG_TILE_WARPS * 32, 1) cov_tile_kernel(DevBat
           __syncwarp();
           const bool win = pending && (!ina || stamp[pa] == key) && (!inz || stamp[pz] == key);
           if (win) {
-            if (ina) { d[sl * W + pa] = __fadd_rn(d[sl * W + pa], w); if (sl != 1) d[W + pa] = __fadd_rn(d[W + pa], w); }
-            if (inz) { d[sl * W + pz] = __fsub_rn(d[sl * W + pz], w); if (sl != 1) d[W + pz] = __fsub_rn(d[W + pz], w); }
+            if (ina) deposit_one(d, sl, pa, w, true);
+            if (inz) deposit_one(d, sl, pz, w, false);
             pending = false;
           }
           __syncwarp();
         }
       }
+      cur = nxt;
     }
     __syncwarp();
 
-    // state handed over from the previous sub-tile of this bundle
-    float c = 0.f, bs = 0.f;
-    if (jt > 0) {
-      if (lane == 0) { while (atomicAdd(v.tile_flag + (t - 1), 0u) == 0u) __nanosleep(64); }
+    // which 32-position words received any deposit, per strand lane
+    const int nwords = (int)((npos + 31) / 32);
+    for (int q = 0; q < nwords; q++) {
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        const uint32_t m = __ballot_sync(FULL, d[s * TWS + q * 32 + lane] != 0.f);
+        if (lane == 0) masks[s * TNW + q] = m;
+      }
+    }
+    __syncwarp();
+
+    if (!have_carry) {
+      if (lane == 0) { while (atomicAdd(v.tile_flag + (tile_id - 1), 0u) == 0u) __nanosleep(40); }
       __syncwarp();
       __threadfence();
-      if (lane < 3) { c = __ldcg(v.tile_carry + (size_t)(t - 1) * 8 + lane); bs = __ldcg(v.tile_carry + (size_t)(t - 1) * 8 + 4 + lane); }
+      if (lane < 3) { c = __ldcg(v.tile_carry + (size_t)(tile_id - 1) * 8 + lane); bs = __ldcg(v.tile_carry + (size_t)(tile_id - 1) * 8 + 4 + lane); }
     }
-    // the two recurrences (rlink.cpp:17037-17063), one strand lane per thread
+
+    // the two recurrences (rlink.cpp:17037-17063), one strand lane per thread:
+    //   c = max(0, c + d[i]);  bs = (i % BSIZE == 0 ? 0 : bs) + c;  out[i] = bs
+    uint32_t fillmask = 0;
     if (lane < 3) {
-      float* dl = d + lane * W;
-      uint32_t to_reset = (STG_BSIZE - i0 % STG_BSIZE) % STG_BSIZE;  // first position of this sub-tile where idx % BSIZE == 0
-      for (uint32_t i = 0; i < npos; i++) {
-        if (i == to_reset) { bs = 0.f; to_reset += STG_BSIZE; }
-        float x = __fadd_rn(dl[i], c);
-        if (x < 0.f) x = 0.f;
-        c = x;
-        x = __fadd_rn(x, bs);
-        bs = x;
-        dl[i] = x;
+      float* dl = d + lane * TWS;
+      const uint32_t* ml = masks + lane * TNW;
+      float* fl = fills + lane * TNW;
+      const uint32_t to_reset = (STG_BSIZE - i0 % STG_BSIZE) % STG_BSIZE;  // in-tile position where idx % BSIZE == 0
+      for (int q = 0; q < nwords; q++) {
+        const uint32_t base = (uint32_t)q * 32;
+        const bool full = base + 32 <= npos;
+        const bool has_reset = to_reset >= base && to_reset < base + 32;
+        if (full && !has_reset) {
+          if (ml[q] == 0 && __fadd_rn(bs, c) == bs) {  // nothing deposited and c too small to move bs: constant word
+            fl[q] = bs;
+            fillmask |= 1u << q;
+            continue;
+          }
+          float4 x[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) x[u] = *reinterpret_cast<const float4*>(dl + base + u * 4);
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            c = fmaxf(__fadd_rn(x[u].x, c), 0.f); bs = __fadd_rn(c, bs); x[u].x = bs;
+            c = fmaxf(__fadd_rn(x[u].y, c), 0.f); bs = __fadd_rn(c, bs); x[u].y = bs;
+            c = fmaxf(__fadd_rn(x[u].z, c), 0.f); bs = __fadd_rn(c, bs); x[u].z = bs;
+            c = fmaxf(__fadd_rn(x[u].w, c), 0.f); bs = __fadd_rn(c, bs); x[u].w = bs;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) *reinterpret_cast<float4*>(dl + base + u * 4) = x[u];
+        } else {
+          const uint32_t lim = min(base + 32, npos);
+          for (uint32_t i = base; i < lim; i++) {
+            if (i == to_reset) bs = 0.f;
+            c = fmaxf(__fadd_rn(dl[i], c), 0.f);
+            bs = __fadd_rn(c, bs);
+            dl[i] = bs;
+          }
+        }
       }
-      __stcg(v.tile_carry + (size_t)t * 8 + lane, c);
-      __stcg(v.tile_carry + (size_t)t * 8 + 4 + lane, bs);
+      __stcg(v.tile_carry + (size_t)tile_id * 8 + lane, c);
+      __stcg(v.tile_carry + (size_t)tile_id * 8 + 4 + lane, bs);
       __threadfence();
     }
     __syncwarp();
-    if (lane == 0) { __threadfence(); atomicExch(v.tile_flag + t, 1u); }
+    if (lane == 0) { __threadfence(); atomicExch(v.tile_flag + tile_id, 1u); }
 
-    // finished bpcov of the sub-tile: one streaming, coalesced write per strand lane
+    // constant words
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+      uint32_t fm = __shfl_sync(FULL, fillmask, s);
+      while (fm) {
+        const int q = __ffs(fm) - 1;
+        fm &= fm - 1;
+        d[s * TWS + q * 32 + lane] = fills[s * TNW + q];
+      }
+    }
+    __syncwarp();
+
+    // finished bpcov of the sub-tile: one streaming, coalesced write per strand lane (incl. the zero padding)
     {
-      const uint32_t stride = v.b_stride[b];
-      float* out = v.bpcov + 3 * (size_t)v.b_gbase[b] + i0;
-      const uint32_t n4 = min((uint32_t)W, stride - i0) / 4;  // includes the zero padding up to the lane stride
+      float* out = v.bpcov + 3 * (size_t)gbase + i0;
+      const uint32_t n4 = min((uint32_t)TW, stride - i0) / 4;
+#pragma unroll
       for (int s = 0; s < 3; s++) {
-        const float4* src = reinterpret_cast<const float4*>(d + s * W);
+        const float4* src = reinterpret_cast<const float4*>(d + s * TWS);
         float4* dst = reinterpret_cast<float4*>(out + (size_t)s * stride);
         for (uint32_t q = lane; q < n4; q += 32) __stcs(dst + q, src[q]);
       }

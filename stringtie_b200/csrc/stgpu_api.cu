@@ -298,6 +298,28 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
   }
   gbase[nb] = (uint32_t)g; tile_off[nb] = (uint32_t)t;
   v.total_pos = (int64_t)g; v.n_tiles = (int64_t)t;
+  // ticket order of the tile kernel: column-major over (bundle, sub-tile index) — bundles sorted by their number
+  // of sub-tiles (descending), col_off[j] = tickets before column j.
+  std::vector<uint32_t> order(nb), col_off;
+  {
+    uint32_t max_nt = 0;
+    for (int64_t b = 0; b < nb; b++) max_nt = std::max(max_nt, tile_off[b + 1] - tile_off[b]);
+    std::vector<uint32_t> hist(max_nt + 2, 0);            // counting sort by tile count, descending, stable
+    for (int64_t b = 0; b < nb; b++) hist[tile_off[b + 1] - tile_off[b]]++;
+    std::vector<uint32_t> first(max_nt + 2, 0);
+    uint32_t acc = 0;
+    for (uint32_t nt = max_nt + 1; nt-- > 0;) { first[nt] = acc; acc += hist[nt]; }
+    for (int64_t b = 0; b < nb; b++) order[first[tile_off[b + 1] - tile_off[b]]++] = (uint32_t)b;
+    col_off.assign(max_nt + 1, 0);
+    uint32_t alive = (uint32_t)nb, run = 0;               // bundles with more than j sub-tiles
+    for (uint32_t j = 0; j < max_nt; j++) {
+      col_off[j] = run;
+      alive -= hist[j];                                   // bundles with exactly j sub-tiles are not in column j
+      run += alive;
+    }
+    col_off[max_nt] = run;
+    v.n_cols = max_nt;
+  }
 
 #define UP(field, count) do { rc = dev_upload(ctx, d, &v.field, h->field, (int64_t)(count)); if (rc) { free_batch_allocs(d); delete d; return rc; } } while (0)
   UP(b_start, nb); UP(b_end, nb); UP(b_read_off, nb + 1); UP(b_junc_off, nb + 1);
@@ -310,6 +332,7 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
 #undef UP
 #define UPV(field, vec) do { rc = dev_upload(ctx, d, &v.field, vec.data(), (int64_t)vec.size()); if (rc) { free_batch_allocs(d); delete d; return rc; } } while (0)
   UPV(b_len, len); UPV(b_stride, stride); UPV(b_gbase, gbase); UPV(b_tile_off, tile_off);
+  UPV(b_order, order); UPV(col_off, col_off);
 #undef UPV
   // the layout vectors are pageable locals: make sure their copies have left the host before they die
   CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -317,6 +340,7 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
   AL(r_ivl_cnt, h->n_reads + 1);
   AL(scan_partials, scan_partials_needed(std::max<int64_t>(h->n_reads + 1, h->n_segs * 2 + h->n_pairs * 4 + 16)));
   AL(tile_carry, v.n_tiles * 8); AL(tile_flag, v.n_tiles); AL(tile_ticket, 1);
+  AL(tile_plan, v.n_tiles); AL(junc_anchor, h->n_juncs);
   AL(bpcov, 3 * v.total_pos);
   AL(j_nreads_good, h->n_juncs); AL(j_leftsupport, h->n_juncs); AL(j_rightsupport, h->n_juncs);
   AL(b_cov_total, nb * 3);
@@ -350,6 +374,7 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   }
   if (v.n_tiles) CK(ctx, cudaMemsetAsync(v.tile_flag, 0, sizeof(uint32_t) * v.n_tiles, st));
   CK(ctx, cudaMemsetAsync(v.tile_ticket, 0, sizeof(uint32_t), st));
+  { Scope s(ctx, "junc_anchor", 1); CK(ctx, launch_junc_anchor(v, kp, st)); }
   { Scope s(ctx, "expand_count+junction_support", 1); CK(ctx, launch_expand_count(v, kp, st)); }
   { Scope s(ctx, "scan_interval_offsets", 3); CK(ctx, launch_scan_exclusive_add(v.r_ivl_cnt, v.n_reads + 1, v.scan_partials, st)); }
   // the interval count sizes the next buffers: one 4-byte read-back (the only host sync inside the stage)
@@ -362,9 +387,8 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   if ((int64_t)n_ivl > d->ivl_capacity) {
     const int64_t cap = (int64_t)n_ivl + (int64_t)n_ivl / 16 + 1024;
     int rc;
-    if ((rc = dev_alloc(ctx, d, &v.ivl_a, cap)) || (rc = dev_alloc(ctx, d, &v.ivl_b, cap)) ||
-        (rc = dev_alloc(ctx, d, &v.ivl_w, cap)) || (rc = dev_alloc(ctx, d, &v.ivl_lane, cap)) ||
-        (rc = dev_alloc(ctx, d, &v.ivl_pmax_b, cap)) || (rc = dev_alloc(ctx, d, &v.ivl_smin_a, cap)))
+    if ((rc = dev_alloc(ctx, d, &v.ivl, cap)) || (rc = dev_alloc(ctx, d, &v.ivl_pmax_b, cap)) ||
+        (rc = dev_alloc(ctx, d, &v.ivl_smin_a, cap)))
       return rc;
     // scan scratch must cover the interval arrays too
     uint32_t* sp = nullptr;
@@ -374,6 +398,7 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   }
   { Scope s(ctx, "expand_write", 1); CK(ctx, launch_expand_write(v, st)); }
   { Scope s(ctx, "window_scans", 6); CK(ctx, launch_window_scans(v, st)); }
+  { Scope s(ctx, "tile_plan", 1); CK(ctx, launch_tile_plan(v, st)); }
   { Scope s(ctx, "cov_tile", 1); CK(ctx, launch_cov_tiles(v, ctx->num_sms, st)); }
   { Scope s(ctx, "cov_totals", 1); CK(ctx, launch_cov_totals(v, st)); }
   d->ran = true;

@@ -6,9 +6,20 @@
 #include <vector>
 #include "../../include/stgpu.h"
 
-#define STG_TILE_W 1024          // positions per sub-tile (one warp owns one sub-tile of all three strand lanes)
-#define STG_TILE_WARPS 12        // warps per CTA of the tile kernel: 12 * 16 KB = 192 KB dynamic shared memory
+#define STG_TILE_W 512           // positions per sub-tile (one warp owns one sub-tile of all three strand lanes)
+#define STG_TILE_WARPS 24        // warps per CTA of the tile kernel (one CTA per SM; ~8.6 KB shared memory per warp)
 #define STG_LANE_ALIGN 32        // every strand lane of every bundle starts on a 128-byte boundary
+
+// Everything a warp needs to process one sub-tile, prepared by tile_plan_kernel (one 32-byte load).
+struct __align__(32) TileRec {
+  uint32_t g0;        // global position of the first index of the sub-tile
+  uint32_t gbase;     // global position of index 0 of its bundle (i0 = g0 - gbase)
+  uint32_t k0, k1;    // slice of the interval array that can deposit into the sub-tile
+  uint32_t stride;    // lane stride of the bundle
+  uint32_t npos;      // valid positions (<= STG_TILE_W)
+  uint32_t tile_id;   // bundle-major tile id (index of its carry / flag)
+  uint32_t pad;
+};
 
 // Device view of one batch: inputs (copies of stg_packed_batch arrays), the planned layout, scratch and outputs.
 struct DevBatchView {
@@ -32,21 +43,24 @@ struct DevBatchView {
   const uint32_t* b_len;       // [n_bundles]   end-start+3
   const uint32_t* b_stride;    // [n_bundles]   len rounded up to STG_LANE_ALIGN
   const uint32_t* b_gbase;     // [n_bundles+1] prefix sum of b_stride: "global position" of index 0 of bundle b
-  const uint32_t* b_tile_off;  // [n_bundles+1] prefix sum of ceil(len/STG_TILE_W)
+  const uint32_t* b_tile_off;  // [n_bundles+1] prefix sum of ceil(len/STG_TILE_W): bundle-major tile ids
+  const uint32_t* b_order;     // [n_bundles]   bundles sorted by tile count, descending
+  const uint32_t* col_off;     // [n_cols+1]    col_off[j] = number of tiles with in-bundle index < j; tickets are
+                               //               handed out column-major: all first sub-tiles, all second ones, ...
+  int64_t n_cols;
   int64_t n_tiles;
   int64_t total_pos;           // b_gbase[n_bundles]
   // scratch
   uint32_t* r_ivl_cnt;         // [n_reads+1] per-read interval count, then exclusive prefix (in place)
   int64_t n_ivl;               // filled after the count pass (host reads it back)
-  uint32_t* ivl_a;             // [n_ivl] global position of the +w deposit
-  uint32_t* ivl_b;             // [n_ivl] global position of the -w deposit
-  float* ivl_w;                // [n_ivl]
-  uint8_t* ivl_lane;           // [n_ivl] 0,1,2
-  uint32_t* ivl_pmax_b;        // [n_ivl] inclusive prefix max of ivl_b
-  uint32_t* ivl_smin_a;        // [n_ivl] inclusive suffix min of ivl_a
+  uint4* ivl;                  // [n_ivl] {global position of the +w deposit, of the -w deposit, w bits, lane}
+  uint32_t* ivl_pmax_b;        // [n_ivl] -w positions, then (in place) their inclusive prefix max
+  uint32_t* ivl_smin_a;        // [n_ivl] +w positions, then (in place) their inclusive suffix min
   uint32_t* scan_partials;     // scratch for the 3-phase scans
-  float* tile_carry;           // [n_tiles*8] c[3], bsum[3] handed from sub-tile t to t+1 of the same bundle
-  uint32_t* tile_flag;         // [n_tiles]   1 when tile_carry[t] is published
+  uint8_t* junc_anchor;        // [n_juncs] anchor length each junction demands (10 or 25, rlink.cpp:16991-16997)
+  TileRec* tile_plan;          // [n_tiles] indexed by ticket
+  float* tile_carry;           // [n_tiles*8] c[3], bsum[3] handed from sub-tile j to j+1 of the same bundle
+  uint32_t* tile_flag;         // [n_tiles]   1 when tile_carry[tile] is published (bundle-major tile id)
   uint32_t* tile_ticket;       // [1]
   // outputs
   float* bpcov;                // [3*total_pos]: bundle b lane s index i at 3*b_gbase[b] + s*b_stride[b] + i
@@ -65,6 +79,8 @@ cudaError_t launch_expand_count(const DevBatchView& v, const KernelParams& p, cu
 cudaError_t launch_scan_exclusive_add(uint32_t* data, int64_t n_plus_1, uint32_t* partials, cudaStream_t st);
 cudaError_t launch_expand_write(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_window_scans(const DevBatchView& v, cudaStream_t st);
+cudaError_t launch_junc_anchor(const DevBatchView& v, const KernelParams& p, cudaStream_t st);
+cudaError_t launch_tile_plan(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_cov_tiles(const DevBatchView& v, int num_sms, cudaStream_t st);
 cudaError_t launch_cov_totals(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_query_cov(const DevBatchView& v, int64_t n, const int32_t* bundle, const int8_t* lane,

@@ -338,3 +338,40 @@ def make_adversarial(seed: int = 1, n_bundles: int = 12, max_reads: int = 400,
     res["r_seg_off"] = np.asarray(r_seg_off, dtype=np.uint32)
     res["r_pair_off"] = np.asarray(r_pair_off, dtype=np.uint32)
     return res
+
+
+def replicate(a: Dict[str, np.ndarray], k: int, gap: int = 100000) -> Dict[str, np.ndarray]:
+    """k coordinate-shifted copies of a packed batch, concatenated: a cheap way to reach 10^8 alignments.
+    Every copy is a distinct set of bundles in distinct memory; only the gene models repeat."""
+    if k <= 1:
+        return a
+    nb, nr = a["b_start"].size, a["r_start"].size
+    ns, npair, nj = a["seg_start"].size, a["pair_idx"].size, a["j_start"].size
+    width = int(a["b_end"].max()) + gap
+    if width * k >= 2 ** 31:
+        raise ValueError("replicated coordinates overflow int32")
+    out = {}
+    sh = (np.arange(k, dtype=np.int64) * width)
+    for key in ("b_start", "b_end"):
+        out[key] = (a[key].astype(np.int64)[None, :] + sh[:, None]).reshape(-1).astype(np.int32)
+    for key in ("r_start", "r_end", "seg_start", "seg_end"):
+        out[key] = (a[key].astype(np.int64)[None, :] + sh[:, None]).reshape(-1).astype(np.uint32)
+    js = a["j_start"].astype(np.int64)[None, :] + sh[:, None]
+    je = a["j_end"].astype(np.int64)[None, :] + sh[:, None]
+    sentinel = (a["j_start"] == 0) & (a["j_end"] == 0)
+    js[:, sentinel] = 0
+    je[:, sentinel] = 0
+    out["j_start"] = js.reshape(-1).astype(np.uint32)
+    out["j_end"] = je.reshape(-1).astype(np.uint32)
+    for key in ("r_len", "r_count", "r_nh", "r_strand", "r_flags", "rjunc_idx", "pair_idx", "pair_cnt", "j_strand",
+                "j_guide_match", "j_nreads", "j_nm", "j_mm"):
+        out[key] = np.tile(a[key], k)
+    for key, n in (("b_read_off", nr), ("b_junc_off", nj), ("r_seg_off", ns), ("r_pair_off", npair)):
+        body = a[key].astype(np.int64)[None, :-1] + (np.arange(k, dtype=np.int64) * n)[:, None]
+        out[key] = np.concatenate([body.reshape(-1), [k * n]]).astype(np.uint32)
+    return out
+
+
+def total_input_bytes(a: Dict[str, np.ndarray]) -> int:
+    from .stgb import INPUT_FIELDS
+    return int(sum(a[k].nbytes for k in INPUT_FIELDS))
