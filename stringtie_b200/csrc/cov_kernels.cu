@@ -7,24 +7,28 @@
 //                                                          b restarted every BSIZE = 10000 entries
 //   get_cov / get_cov_sign           rlink.cpp:1830-1853
 //
-// Design: thousands of bundles are processed at once.
+// Design: thousands of bundles are processed at once; float32 deposits must land on every address in
+// the reference's order (read order), so the events are BINNED, not scattered with atomics:
 //   K0  junc_anchor    one thread per junction row: the anchor length it demands (10 or 25).
 //   K1  expand_count   one thread per read: counts the coverage intervals the read deposits (mate merge walk)
 //                      and adds its junction support with f64 atomics (exact, hence order-free: DESIGN.md §3.4).
 //   K2  scan           exclusive prefix sum of the counts (3-phase block scan).
-//   K3  expand_write   one thread per read: writes its intervals (global position of +w, of -w, w, lane)
+//   K3  expand_write   one thread per read: writes its intervals {tile(+w), tile(-w), positions, lane, w}
 //                      in reference order, so "index order" == the order the reference applies deposits in.
-//   K4  window scans   prefix max of the -w positions, suffix min of the +w positions: both are monotone, so
-//                      a sub-tile finds the contiguous slice of intervals that can touch it by two searches.
-//   K4b tile_plan      one thread per sub-tile: the two searches + everything else the tile kernel needs, as one
-//                      32-byte record, in column-major ticket order (all first sub-tiles of all bundles, then
-//                      all second ones ...) so that resident warps work on ~3500 different bundles at once.
-//   K5  cov_tile       one WARP per sub-tile of 512 positions x 3 strand lanes held in shared memory:
-//                      ordered deposit of the slice (float32 adds land on every address in reference order —
-//                      bit-exact for any weights), then the two sequential recurrences over the sub-tile with
-//                      the (c, b) state handed from the previous sub-tile of the bundle through global memory,
-//                      then one coalesced streaming write of the finished bpcov.  The difference array never
-//                      exists in HBM.
+//   K4  chunk_hull     one warp per chunk of 512 intervals: the range of tiles its events land in; scans give
+//                      each chunk a row of per-tile counters and make the ranges searchable.
+//   K5  bin_count      one warp per chunk: events per (chunk, tile).
+//   K6  bin_columns    one thread per tile: exclusive prefix down the chunks that reach it -> every chunk's first
+//                      slot in the tile's event list; per-tile totals -> scan -> list offsets.
+//   K7  bin_scatter    one warp per chunk, walking its intervals in order: a STABLE counting sort of the events by
+//                      tile (rank = slot of chunk + rank inside the warp by ballot) -> tight per-tile event lists.
+//   K8  tile_plan      one thread per sub-tile: one 32-byte record, in column-major ticket order (all first
+//                      sub-tiles of all bundles, then all second ones ...).
+//   K9  cov_tile       one WARP per sub-tile of 512 positions x 3 strand lanes held in shared memory:
+//                      ordered deposit of its event list (same-position events of a 32-group are chained in lane
+//                      order inside one thread: bit-exact for any weights), then the two sequential recurrences
+//                      with the (c, b) state taken from the nearest earlier sub-tile that had events, then one
+//                      coalesced streaming write of the finished bpcov.  The difference array never exists in HBM.
 // All float arithmetic is compiled without FMA contraction (-fmad=false): the reference is plain x86-64 SSE.
 #include "stgpu_internal.h"
 
@@ -33,29 +37,12 @@
 // --------------------------------------------------------------------------------------------------------------
 // small helpers
 // --------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t find_bundle_of_read(const uint32_t* __restrict__ b_read_off, int64_t nb,
-                                                        uint32_t n) {
-  // last b with b_read_off[b] <= n
-  uint32_t lo = 0, hi = (uint32_t)nb;  // answer in [lo, hi)
-  while (hi - lo > 1) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(b_read_off + mid) <= n) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
-// same, but the warp first tries the bundle of its first lane (reads of a warp almost always share a bundle)
-__device__ __forceinline__ uint32_t find_bundle_of_read_warp(const uint32_t* __restrict__ b_read_off, int64_t nb,
-                                                             uint32_t n, bool active) {
-  const uint32_t mask = __activemask();
-  const int leader = __ffs(mask) - 1;
-  uint32_t b = 0;
-  if ((int)(threadIdx.x & 31) == leader) b = find_bundle_of_read(b_read_off, nb, n);
-  b = __shfl_sync(mask, b, leader);
-  if (active) {
-    // lanes beyond the leader's bundle walk forward (bundles may be empty: skip while the next one starts <= n)
-    while (b + 1 < (uint32_t)nb && __ldg(b_read_off + b + 1) <= n) b++;
-  }
+// bundle of read n: start from the bundle of the first read of this CTA (planned on the host) and walk forward;
+// empty bundles are skipped (the answer is the LAST b with b_read_off[b] <= n)
+__device__ __forceinline__ uint32_t bundle_of_read(const DevBatchView& v, uint32_t n) {
+  uint32_t b = __ldg(v.cta_bundle + blockIdx.x);
+  const uint32_t nb = (uint32_t)v.n_bundles;
+  while (b + 1 < nb && __ldg(v.b_read_off + b + 1) <= n) b++;
   return b;
 }
 
@@ -139,11 +126,21 @@ cudaError_t launch_junc_anchor(const DevBatchView& v, const KernelParams& p, cud
 // --------------------------------------------------------------------------------------------------------------
 // K1: count intervals per read + junction support
 // --------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) expand_count_kernel(DevBatchView v, KernelParams prm) {
+__device__ __forceinline__ void add_support(const DevBatchView& v, uint32_t j, uint32_t lmax, uint32_t rmax, double w) {
+  const uint32_t anchor = v.junc_anchor[j];
+  if (lmax >= anchor) {
+    atomicAdd(v.j_leftsupport + j, w);
+    if (rmax >= anchor) { atomicAdd(v.j_rightsupport + j, w); atomicAdd(v.j_nreads_good + j, w); }
+  } else if (rmax >= anchor) {
+    atomicAdd(v.j_rightsupport + j, w);
+  }
+}
+
+__global__ void __launch_bounds__(STG_READ_BLOCK) expand_count_kernel(DevBatchView v, KernelParams prm) {
   const int64_t n64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n64 >= v.n_reads) return;
   const uint32_t n = (uint32_t)n64;
-  const uint32_t b = find_bundle_of_read_warp(v.b_read_off, v.n_bundles, n, true);
+  const uint32_t b = bundle_of_read(v, n);
   const uint32_t r0 = v.b_read_off[b];
   uint32_t cnt = 0;
   walk_read_intervals(v, r0, n, [&](uint32_t, uint32_t, float, int) { cnt++; });
@@ -157,41 +154,40 @@ __global__ void __launch_bounds__(256) expand_count_kernel(DevBatchView v, Kerne
   if (nex < 2) return;
   float rdcount = v.r_count[n];
   if ((v.r_flags[n] & STG_RF_UNITIG) && rdcount > 1.f) rdcount = 1.f;
+  const double w = (double)rdcount;
   const int32_t* __restrict__ rj = v.rjunc_idx + (s0 - n);
   const uint32_t j0 = v.b_junc_off[b];
-  constexpr uint32_t kLocal = 24;
-  uint32_t rsup[kLocal];  // rsup[i] = longest exon among segs[i..nex-1], for i < kLocal
-  {
-    uint32_t m = 0;
-    for (uint32_t i = nex; i-- > 0;) {
-      const uint32_t l = v.seg_end[s0 + i] - v.seg_start[s0 + i] + 1;
-      if (l > m) m = l;
-      if (i < kLocal) rsup[i] = m;
-    }
-  }
-  const double w = (double)rdcount;
-  uint32_t lmax = 0;
-  for (uint32_t i = 1; i < nex; i++) {
-    const uint32_t l = v.seg_end[s0 + i - 1] - v.seg_start[s0 + i - 1] + 1;
-    if (l > lmax) lmax = l;
-    const int32_t jl = rj[i - 1];
-    if (jl < 0) continue;
-    uint32_t rmax;
-    if (i < kLocal) rmax = rsup[i];
-    else {  // very long reads: recompute the suffix maximum
-      rmax = 0;
-      for (uint32_t q = i; q < nex; q++) {
-        const uint32_t lq = v.seg_end[s0 + q] - v.seg_start[s0 + q] + 1;
-        if (lq > rmax) rmax = lq;
+  constexpr int kReg = 8;
+  if (nex <= kReg) {  // the usual case: exon lengths and their suffix maxima stay in registers
+    uint32_t len[kReg], rs[kReg];
+#pragma unroll
+    for (int q = 0; q < kReg; q++) len[q] = (uint32_t)q < nex ? v.seg_end[s0 + q] - v.seg_start[s0 + q] + 1 : 0u;
+    rs[kReg - 1] = len[kReg - 1];
+#pragma unroll
+    for (int q = kReg - 2; q >= 0; q--) rs[q] = len[q] > rs[q + 1] ? len[q] : rs[q + 1];
+    uint32_t lmax = 0;
+#pragma unroll
+    for (int i = 1; i < kReg; i++) {
+      if ((uint32_t)i < nex) {
+        if (len[i - 1] > lmax) lmax = len[i - 1];
+        const int32_t jl = rj[i - 1];
+        if (jl >= 0) add_support(v, j0 + (uint32_t)jl, lmax, rs[i], w);
       }
     }
-    const uint32_t j = j0 + (uint32_t)jl;
-    const uint32_t anchor = v.junc_anchor[j];
-    if (lmax >= anchor) {
-      atomicAdd(v.j_leftsupport + j, w);
-      if (rmax >= anchor) { atomicAdd(v.j_rightsupport + j, w); atomicAdd(v.j_nreads_good + j, w); }
-    } else if (rmax >= anchor) {
-      atomicAdd(v.j_rightsupport + j, w);
+  } else {  // many exons (long reads): suffix maximum recomputed only when the running one expires
+    uint32_t lmax = 0, rmax = 0, rmax_at = 0;  // rmax = max len[i..nex-1], attained (last) at rmax_at
+    for (uint32_t i = 1; i < nex; i++) {
+      const uint32_t l = v.seg_end[s0 + i - 1] - v.seg_start[s0 + i - 1] + 1;
+      if (l > lmax) lmax = l;
+      if (i == 1 || rmax_at < i) {
+        rmax = 0;
+        for (uint32_t q = i; q < nex; q++) {
+          const uint32_t lq = v.seg_end[s0 + q] - v.seg_start[s0 + q] + 1;
+          if (lq >= rmax) { rmax = lq; rmax_at = q; }
+        }
+      }
+      const int32_t jl = rj[i - 1];
+      if (jl >= 0) add_support(v, j0 + (uint32_t)jl, lmax, rmax, w);
     }
   }
 }
@@ -199,16 +195,15 @@ __global__ void __launch_bounds__(256) expand_count_kernel(DevBatchView v, Kerne
 // --------------------------------------------------------------------------------------------------------------
 // K3: write intervals
 // --------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) expand_write_kernel(DevBatchView v) {
+__global__ void __launch_bounds__(STG_READ_BLOCK) expand_write_kernel(DevBatchView v) {
   const int64_t n64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n64 >= v.n_reads) return;
   const uint32_t n = (uint32_t)n64;
   uint32_t k = v.r_ivl_cnt[n];
-  const bool any = k != v.r_ivl_cnt[n + 1];
-  const uint32_t b = find_bundle_of_read_warp(v.b_read_off, v.n_bundles, n, any);
-  if (!any) return;
+  if (k == v.r_ivl_cnt[n + 1]) return;
+  const uint32_t b = bundle_of_read(v, n);
   const uint32_t r0 = v.b_read_off[b];
-  const uint32_t gb = v.b_gbase[b];
+  const uint32_t toff = v.b_tile_off[b];
   const uint32_t refstart = (uint32_t)v.b_start[b];
   const uint32_t len = v.b_len[b];
   walk_read_intervals(v, r0, n, [&](uint32_t start, uint32_t end, float w, int lane) {
@@ -216,9 +211,9 @@ __global__ void __launch_bounds__(256) expand_write_kernel(DevBatchView v) {
     uint32_t ia = start - refstart + 1, ib = end - refstart + 2;
     if (start < refstart || ib >= len) { ia = 0; ib = 0; w = 0.f; }  // read outside its bundle: dropped (the
                                                                     // reference would write out of bounds)
-    v.ivl[k] = make_uint4(gb + ia, gb + ib, __float_as_uint(w), (uint32_t)lane);
-    v.ivl_smin_a[k] = gb + ia;
-    v.ivl_pmax_b[k] = gb + ib;
+    v.ivl[k] = make_uint4(toff + (ia >> STG_TILE_SHIFT), toff + (ib >> STG_TILE_SHIFT),
+                          (ia & (STG_TILE_W - 1)) | ((ib & (STG_TILE_W - 1)) << 9) | ((uint32_t)lane << 18),
+                          __float_as_uint(w));
     k++;
   });
 }
@@ -340,27 +335,119 @@ cudaError_t launch_scan_exclusive_add(uint32_t* data, int64_t n_plus_1, uint32_t
   return run_scan<OP_ADD, false, true>(data, data, n_plus_1, partials, st);
 }
 
-cudaError_t launch_window_scans(const DevBatchView& v, cudaStream_t st) {
-  cudaError_t e = run_scan<OP_MAX, false, false>(v.ivl_pmax_b, v.ivl_pmax_b, v.n_ivl, v.scan_partials, st);
-  if (e != cudaSuccess) return e;
-  return run_scan<OP_MIN, true, false>(v.ivl_smin_a, v.ivl_smin_a, v.n_ivl, v.scan_partials, st);
-}
 
 cudaError_t launch_expand_count(const DevBatchView& v, const KernelParams& p, cudaStream_t st) {
   if (v.n_reads == 0) return cudaSuccess;
-  expand_count_kernel<<<(unsigned)((v.n_reads + 255) / 256), 256, 0, st>>>(v, p);
+  expand_count_kernel<<<(unsigned)((v.n_reads + STG_READ_BLOCK - 1) / STG_READ_BLOCK), STG_READ_BLOCK, 0, st>>>(v, p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_expand_write(const DevBatchView& v, cudaStream_t st) {
   if (v.n_reads == 0) return cudaSuccess;
-  expand_write_kernel<<<(unsigned)((v.n_reads + 255) / 256), 256, 0, st>>>(v);
+  expand_write_kernel<<<(unsigned)((v.n_reads + STG_READ_BLOCK - 1) / STG_READ_BLOCK), STG_READ_BLOCK, 0, st>>>(v);
   return cudaGetLastError();
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// K4b: per-tile plan records, in ticket (column-major) order
+// K4..K7: stable binning of the deposit events by sub-tile
+//
+// Interval k contributes two events: +w at (ta, pa) and -w at (tb, pb); events are ordered by (k, endpoint).
+// A chunk is STG_CHUNK consecutive intervals, owned by one warp.  For every chunk c and every tile t in the
+// chunk's hull [ch_tlo[c], ch_thi[c]] there is one counter cell.  After bin_count a cell holds the number of
+// events of chunk c in tile t; bin_columns turns every column into its exclusive prefix over chunks, so that
+// bin_scatter can place event e of chunk c at  tile_evoff[t] + cell(c, t) + (rank of e among the events of c in t),
+// which is exactly the position of e in the reference-ordered event list of tile t.
 // --------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chunk_hull_kernel(DevBatchView v) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= v.n_chunks) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t k0 = c * STG_CHUNK;
+  const int64_t k1 = k0 + STG_CHUNK < v.n_ivl ? k0 + STG_CHUNK : v.n_ivl;
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  for (int64_t k = k0 + lane; k < k1; k += 32) {
+    const uint4 iv = __ldg(v.ivl + k);
+    lo = min(lo, iv.x);  // ta <= tb always (the -w deposit lies to the right of the +w one)
+    hi = max(hi, iv.y);
+  }
+  lo = __reduce_min_sync(FULL, lo);
+  hi = __reduce_max_sync(FULL, hi);
+  if (lane == 0) {
+    v.ch_tlo[c] = lo; v.ch_thi[c] = hi;
+    v.ch_smin_tlo[c] = lo; v.ch_pmax_thi[c] = hi;
+    v.ch_row_off[c] = hi - lo + 1;
+    if (c == v.n_chunks - 1) v.ch_row_off[v.n_chunks] = 0;
+  }
+}
+
+cudaError_t launch_chunk_hull(const DevBatchView& v, cudaStream_t st) {
+  if (v.n_chunks == 0) return cudaSuccess;
+  chunk_hull_kernel<<<(unsigned)((v.n_chunks * 32 + 255) / 256), 256, 0, st>>>(v);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if ((e = run_scan<OP_ADD, false, true>(v.ch_row_off, v.ch_row_off, v.n_chunks + 1, v.scan_partials, st)) != cudaSuccess) return e;
+  if ((e = run_scan<OP_MAX, false, false>(v.ch_pmax_thi, v.ch_pmax_thi, v.n_chunks, v.scan_partials, st)) != cudaSuccess) return e;
+  return run_scan<OP_MIN, true, false>(v.ch_smin_tlo, v.ch_smin_tlo, v.n_chunks, v.scan_partials, st);
+}
+
+// One warp walks its chunk in order, 32 intervals (64 events) per step; inside a step the events of one tile are
+// ranked by (lane, endpoint) with two ballots.  SCATTER = false: count only.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) bin_kernel(DevBatchView v) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= v.n_chunks) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int64_t k0 = c * STG_CHUNK;
+  const int64_t k1 = k0 + STG_CHUNK < v.n_ivl ? k0 + STG_CHUNK : v.n_ivl;
+  const uint32_t tlo = __ldg(v.ch_tlo + c);
+  uint32_t* __restrict__ row = v.cells + __ldg(v.ch_row_off + c);
+  uint4 cur = make_uint4(0u, 0u, 0u, 0u);
+  if (k0 + lane < k1) cur = __ldcs(v.ivl + k0 + lane);
+  for (int64_t kb = k0; kb < k1; kb += 32) {
+    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+    if (kb + 32 + lane < k1) nxt = __ldcs(v.ivl + kb + 32 + lane);
+    const bool valid = kb + lane < k1;
+    const uint32_t ta = cur.x, tb = cur.y;
+    bool todo_a = valid, todo_b = valid;
+    for (;;) {
+      const uint32_t pending = __ballot_sync(FULL, todo_a || todo_b);
+      if (!pending) break;
+      const int src = __ffs(pending) - 1;
+      const uint32_t T = __shfl_sync(FULL, todo_a ? ta : tb, src);
+      const bool ina = todo_a && ta == T, inb = todo_b && tb == T;
+      const uint32_t ba = __ballot_sync(FULL, ina), bb = __ballot_sync(FULL, inb);
+      const uint32_t cntT = __popc(ba) + __popc(bb);
+      if (!SCATTER) {
+        if (lane == src) atomicAdd(row + (T - tlo), cntT);   // the row is private to this warp: no contention
+      } else {
+        uint32_t base = 0;
+        if (lane == src) base = atomicAdd(row + (T - tlo), cntT) + __ldg(v.tile_evoff + T);
+        base = __shfl_sync(FULL, base, src);
+        const uint32_t before = base + __popc(ba & lt) + __popc(bb & lt);
+        const uint32_t lane_bits = (cur.z >> 18) << 9;
+        if (ina) v.events[before] = make_uint2((cur.z & 511u) | lane_bits, cur.w);
+        if (inb) v.events[before + (ina ? 1u : 0u)] = make_uint2(((cur.z >> 9) & 511u) | lane_bits, cur.w ^ 0x80000000u);
+      }
+      todo_a = todo_a && !ina;
+      todo_b = todo_b && !inb;
+    }
+    cur = nxt;
+  }
+}
+
+cudaError_t launch_bin_count(const DevBatchView& v, cudaStream_t st) {
+  if (v.n_chunks == 0) return cudaSuccess;
+  bin_kernel<false><<<(unsigned)((v.n_chunks * 32 + 255) / 256), 256, 0, st>>>(v);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bin_scatter(const DevBatchView& v, cudaStream_t st) {
+  if (v.n_chunks == 0) return cudaSuccess;
+  bin_kernel<true><<<(unsigned)((v.n_chunks * 32 + 255) / 256), 256, 0, st>>>(v);
+  return cudaGetLastError();
+}
+
 // first index in [lo, hi) with arr[idx] >= key (arr non-decreasing)
 __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ arr, uint32_t lo, uint32_t hi,
                                                     uint32_t key) {
@@ -371,6 +458,42 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__
   return lo;
 }
 
+// One thread per tile: exclusive prefix of its column over the chunks whose hull contains it.
+__global__ void __launch_bounds__(256) bin_columns_kernel(DevBatchView v) {
+  const int64_t t64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t64 >= v.n_tiles) return;
+  const uint32_t t = (uint32_t)t64;
+  uint32_t run = 0;
+  if (v.n_chunks > 0) {
+    const uint32_t nc = (uint32_t)v.n_chunks;
+    const uint32_t c0 = lower_bound_u32(v.ch_pmax_thi, 0, nc, t);       // first chunk reaching up to t
+    const uint32_t c1 = lower_bound_u32(v.ch_smin_tlo, 0, nc, t + 1);   // from here on every chunk starts past t
+    for (uint32_t c = c0; c < c1; c++) {
+      const uint32_t lo = __ldg(v.ch_tlo + c);
+      if (t < lo || t > __ldg(v.ch_thi + c)) continue;
+      uint32_t* cell = v.cells + __ldg(v.ch_row_off + c) + (t - lo);
+      const uint32_t x = *cell;
+      *cell = run;
+      run += x;
+    }
+  }
+  v.tile_evoff[t] = run;
+  v.tile_lastne[t] = run ? t + 1 : 0u;
+  if (t64 == v.n_tiles - 1) v.tile_evoff[v.n_tiles] = 0;
+}
+
+cudaError_t launch_bin_columns(const DevBatchView& v, cudaStream_t st) {
+  if (v.n_tiles == 0) return cudaSuccess;
+  bin_columns_kernel<<<(unsigned)((v.n_tiles + 255) / 256), 256, 0, st>>>(v);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if ((e = run_scan<OP_ADD, false, true>(v.tile_evoff, v.tile_evoff, v.n_tiles + 1, v.scan_partials, st)) != cudaSuccess) return e;
+  return run_scan<OP_MAX, false, false>(v.tile_lastne, v.tile_lastne, v.n_tiles, v.scan_partials, st);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K8: per-tile plan records, in ticket (column-major) order
+// --------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tile_plan_kernel(DevBatchView v) {
   const int64_t t64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t64 >= v.n_tiles) return;
@@ -384,18 +507,20 @@ __global__ void __launch_bounds__(256) tile_plan_kernel(DevBatchView v) {
   const uint32_t jt = lo;
   const uint32_t b = v.b_order[t - v.col_off[jt]];
   const uint32_t len = v.b_len[b];
-  const uint32_t i0 = jt * STG_TILE_W;
   TileRec r;
   r.gbase = v.b_gbase[b];
-  r.g0 = r.gbase + i0;
-  r.npos = min((uint32_t)STG_TILE_W, len - i0);
+  r.i0 = jt * STG_TILE_W;
+  r.npos = min((uint32_t)STG_TILE_W, len - r.i0);
   r.stride = v.b_stride[b];
-  r.tile_id = v.b_tile_off[b] + jt;
-  r.pad = 0;
-  const uint32_t K0 = v.r_ivl_cnt[v.b_read_off[b]], K1 = v.r_ivl_cnt[v.b_read_off[b + 1]];
-  r.k0 = lower_bound_u32(v.ivl_pmax_b, K0, K1, r.g0);             // first interval whose -w lands at or after g0
-  r.k1 = lower_bound_u32(v.ivl_smin_a, K0, K1, r.g0 + r.npos);    // first interval from which every +w is past the tile
-  if (r.k1 < r.k0) r.k1 = r.k0;
+  const uint32_t first = v.b_tile_off[b];
+  r.tile_id = first + jt;
+  r.e0 = v.tile_evoff[r.tile_id];
+  r.nev = v.tile_evoff[r.tile_id + 1] - r.e0;
+  r.wait_tile = STG_NO_TILE;
+  if (jt > 0) {
+    const uint32_t last = v.tile_lastne[r.tile_id - 1];   // 1 + last tile at or before tile_id-1 that has events
+    if (last > first) r.wait_tile = last - 1;
+  }
   v.tile_plan[t] = r;
 }
 
@@ -406,22 +531,34 @@ cudaError_t launch_tile_plan(const DevBatchView& v, cudaStream_t st) {
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// K5: the tile kernel
+// K9: the tile kernel
 // --------------------------------------------------------------------------------------------------------------
 constexpr int TW = STG_TILE_W;          // positions per sub-tile
 constexpr int TWS = TW + 4;             // lane stride in shared memory (+4 floats: the three chain threads hit
                                         // different banks with their 128-bit accesses)
 constexpr int TNW = TW / 32;            // 32-position words per sub-tile
-constexpr int TILE_SMEM_WORDS = 3 * TWS + TW + 3 * TNW + 3 * TNW;  // d, stamp, masks, fills
+constexpr int TILE_SMEM_WORDS = 3 * TWS + 3 * TNW + 3 * TNW;  // d, masks, fills
 
 int cov_tile_smem_bytes() { return STG_TILE_WARPS * TILE_SMEM_WORDS * 4; }
 
-__device__ __forceinline__ void deposit_one(float* d, uint32_t sl, uint32_t p, float w, bool add) {
-  float* q = d + sl * TWS + p;
-  *q = add ? __fadd_rn(*q, w) : __fsub_rn(*q, w);
-  if (sl != 1) {
-    float* q1 = d + TWS + p;
-    *q1 = add ? __fadd_rn(*q1, w) : __fsub_rn(*q1, w);
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t x;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(x) : "l"(p) : "memory");
+  return x;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t x) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(x) : "memory");
+}
+
+// wait until sub-tile `tile` has published its carry, then load it: lanes 0..2 get (c, bs) of their strand lane
+__device__ __forceinline__ void take_carry(const DevBatchView& v, uint32_t tile, int lane, float& c, float& bs) {
+  if (lane == 0) {
+    while (ld_acquire_u32(v.tile_flag + tile) == 0u) __nanosleep(32);
+  }
+  __syncwarp();
+  if (lane < 3) {
+    c = __ldcg(v.tile_carry + (size_t)tile * 8 + lane);
+    bs = __ldcg(v.tile_carry + (size_t)tile * 8 + 4 + lane);
   }
 }
 
@@ -429,14 +566,9 @@ __global__ void __launch_bounds__(STG_TILE_WARPS * 32, 1) cov_tile_kernel(DevBat
   extern __shared__ __align__(16) uint32_t smem_raw[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float* d = reinterpret_cast<float*>(smem_raw) + (size_t)wid * TILE_SMEM_WORDS;  // d[3][TWS]
-  uint32_t* stamp = reinterpret_cast<uint32_t*>(d + 3 * TWS);                     // stamp[TW]
-  uint32_t* masks = stamp + TW;                                                   // masks[3][TNW]
+  uint32_t* masks = reinterpret_cast<uint32_t*>(d + 3 * TWS);                     // masks[3][TNW]
   float* fills = reinterpret_cast<float*>(masks + 3 * TNW);                       // fills[3][TNW]
-
-  // stamps persist across the sub-tiles of this warp: keys only ever decrease, so stale ones never match
-  for (int q = lane; q < TW; q += 32) stamp[q] = FULL;
-  uint32_t epoch = 0x03ffffffu;
-  __syncwarp();
+  const uint2 no_event = make_uint2(0u, 0u);
 
   for (;;) {
     uint32_t t = 0;
@@ -446,104 +578,124 @@ __global__ void __launch_bounds__(STG_TILE_WARPS * 32, 1) cov_tile_kernel(DevBat
     // one 32-byte record per sub-tile
     uint32_t recw = 0;
     if (lane < 8) recw = __ldg(reinterpret_cast<const uint32_t*>(v.tile_plan + t) + lane);
-    const uint32_t g0 = __shfl_sync(FULL, recw, 0), gbase = __shfl_sync(FULL, recw, 1);
-    const uint32_t k0 = __shfl_sync(FULL, recw, 2), k1 = __shfl_sync(FULL, recw, 3);
+    const uint32_t gbase = __shfl_sync(FULL, recw, 0), i0 = __shfl_sync(FULL, recw, 1);
+    const uint32_t e0 = __shfl_sync(FULL, recw, 2), nev = __shfl_sync(FULL, recw, 3);
     const uint32_t stride = __shfl_sync(FULL, recw, 4), npos = __shfl_sync(FULL, recw, 5);
-    const uint32_t tile_id = __shfl_sync(FULL, recw, 6);
-    const uint32_t i0 = g0 - gbase;
+    const uint32_t tile_id = __shfl_sync(FULL, recw, 6), wait_tile = __shfl_sync(FULL, recw, 7);
+    const uint32_t to_reset = (STG_BSIZE - i0 % STG_BSIZE) % STG_BSIZE;  // in-tile position where idx % BSIZE == 0
+    float* out = v.bpcov + 3 * (size_t)gbase + i0;
+    const uint32_t n4 = min((uint32_t)TW, stride - i0) / 4;              // float4 per lane incl. the zero padding
 
-    // state handed over by the previous sub-tile of this bundle: issue the loads now, consume them after the deposit
+    uint2 cur = no_event;
+    if (lane < nev) cur = __ldcs(v.events + e0 + lane);
+
+    // state at the end of the previous position (rlink.cpp:17037-17063): c = clamped coverage, bs = running block sum
     float c = 0.f, bs = 0.f;
-    bool have_carry = (i0 == 0);
-    if (!have_carry) {
-      uint32_t f = 0;
-      if (lane == 0) f = atomicAdd(v.tile_flag + (tile_id - 1), 0u);
-      f = __shfl_sync(FULL, f, 0);
-      if (f) {
+    auto fetch_state = [&]() {
+      if (wait_tile == STG_NO_TILE) return;            // nothing deposited before this sub-tile: c = bs = 0
+      take_carry(v, wait_tile, lane, c, bs);
+      if (wait_tile == tile_id - 1) return;
+      // the sub-tiles in between had no events.  With c == 0 they only carry bs along (reset to 0 by a block start)
+      const bool nz = __any_sync(FULL, lane < 3 && c != 0.f);
+      if (!nz) {
+        const uint32_t first = tile_id - i0 / TW;                        // first sub-tile of the bundle
+        const uint32_t wlast = (wait_tile - first) * TW + TW - 1;        // last index of the sub-tile waited on
+        if ((i0 - 1) / STG_BSIZE != wlast / STG_BSIZE) bs = 0.f;
+      } else {
+        take_carry(v, tile_id - 1, lane, c, bs);                         // a residue travels: take the slow chain
+      }
+    };
+    auto publish = [&]() {
+      if (lane < 3) {
+        __stcg(v.tile_carry + (size_t)tile_id * 8 + lane, c);
+        __stcg(v.tile_carry + (size_t)tile_id * 8 + 4 + lane, bs);
         __threadfence();
-        if (lane < 3) { c = __ldcg(v.tile_carry + (size_t)(tile_id - 1) * 8 + lane); bs = __ldcg(v.tile_carry + (size_t)(tile_id - 1) * 8 + 4 + lane); }
-        have_carry = true;
+      }
+      __syncwarp();
+      if (lane == 0) st_release_u32(v.tile_flag + tile_id, 1u);
+    };
+
+    if (nev == 0) {
+      fetch_state();
+      if (!__any_sync(FULL, lane < 3 && c != 0.f)) {
+        // no events and no coverage entering: every position repeats bs (0 from a block start on)
+        float b0 = __shfl_sync(FULL, bs, 0), b1 = __shfl_sync(FULL, bs, 1), b2 = __shfl_sync(FULL, bs, 2);
+        if (to_reset < npos) bs = 0.f;
+        publish();
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+          const float bv = s == 0 ? b0 : (s == 1 ? b1 : b2);
+          float4* dst = reinterpret_cast<float4*>(out + (size_t)s * stride);
+          for (uint32_t q = lane; q < n4; q += 32) {
+            const uint32_t p = q * 4;
+            float4 x;
+            x.x = (p + 0 < to_reset && p + 0 < npos) ? bv : 0.f;
+            x.y = (p + 1 < to_reset && p + 1 < npos) ? bv : 0.f;
+            x.z = (p + 2 < to_reset && p + 2 < npos) ? bv : 0.f;
+            x.w = (p + 3 < to_reset && p + 3 < npos) ? bv : 0.f;
+            __stcs(dst + q, x);
+          }
+        }
+        continue;
       }
     }
 
-    if (epoch < 0x10000u) {  // (practically never) restart the key space
-      for (int q = lane; q < TW; q += 32) stamp[q] = FULL;
-      epoch = 0x03ffffffu;
-    }
     // clear the sub-tile
     {
       float4* d4 = reinterpret_cast<float4*>(d);
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int q = lane; q < 3 * TWS / 4; q += 32) d4[q] = z;
+      for (int q = lane; q < 3 * TNW; q += 32) masks[q] = 0u;
     }
     __syncwarp();
 
-    // ordered deposit of intervals [k0, k1). `epoch` decreases, so keys of later rounds are smaller than stale stamps.
-    uint4 cur = make_uint4(FULL, FULL, 0u, 1u);
-    if (k0 + lane < k1) cur = __ldcs(v.ivl + k0 + lane);
-    for (uint32_t kb = k0; kb < k1; kb += 32) {
-      uint4 nxt = make_uint4(FULL, FULL, 0u, 1u);
-      if (kb + 32 + lane < k1) nxt = __ldcs(v.ivl + kb + 32 + lane);
-      const uint32_t pa = cur.x - g0, pz = cur.y - g0;   // unsigned: out-of-tile positions become >= npos
-      const bool ina = pa < npos, inz = pz < npos;
-      const float w = __uint_as_float(cur.z);
-      const uint32_t sl = cur.w;
-      // round 0: plain stores detect whether any two lanes share a position
-      uint32_t key = (epoch << 5) | (uint32_t)lane; epoch--;
-      if (ina) stamp[pa] = key;
-      if (inz) stamp[pz] = key;
-      __syncwarp();
-      const bool mine = (!ina || stamp[pa] == key) && (!inz || stamp[pz] == key);
-      if (__all_sync(FULL, mine)) {
-        if (ina) deposit_one(d, sl, pa, w, true);
-        if (inz) deposit_one(d, sl, pz, w, false);
-        __syncwarp();
-      } else {
-        // some position is hit by several intervals of this group: apply in lane (= reference) order
-        bool pending = ina || inz;
-        while (__any_sync(FULL, pending)) {
-          key = (epoch << 5) | (uint32_t)lane; epoch--;
-          if (pending) { if (ina) atomicMin(stamp + pa, key); if (inz) atomicMin(stamp + pz, key); }
-          __syncwarp();
-          const bool win = pending && (!ina || stamp[pa] == key) && (!inz || stamp[pz] == key);
-          if (win) {
-            if (ina) deposit_one(d, sl, pa, w, true);
-            if (inz) deposit_one(d, sl, pz, w, false);
-            pending = false;
-          }
-          __syncwarp();
+    // ordered deposit of the event list.  Events of one 32-group that share a position are chained, in lane
+    // (= reference) order, in the registers of the first of them; groups are applied one after the other.
+    for (uint32_t eb = 0; eb < nev; eb += 32) {
+      uint2 nxt = no_event;
+      if (eb + 32 + lane < nev) nxt = __ldcs(v.events + e0 + eb + 32 + lane);
+      const bool valid = eb + lane < nev;
+      const uint32_t pos = cur.x & 511u, sl = cur.x >> 9;
+      const float val = __uint_as_float(cur.y);
+      const uint32_t grp = __match_any_sync(FULL, valid ? pos : (0x8000u | (uint32_t)lane));
+      const bool leader = valid && (__ffs(grp) - 1 == lane);
+      const int maxn = __reduce_max_sync(FULL, valid ? __popc(grp) : 0);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      if (leader) { a0 = d[pos]; a1 = d[TWS + pos]; a2 = d[2 * TWS + pos]; }
+      uint32_t rem = leader ? grp : 0u;
+      uint32_t touched = 0;
+      for (int r = 0; r < maxn; r++) {
+        const int src = rem ? __ffs(rem) - 1 : lane;
+        const float vv = __shfl_sync(FULL, val, src);
+        const uint32_t ss = __shfl_sync(FULL, sl, src);
+        if (rem) {
+          // cov_edge_add (rlink.cpp:133-142): the strand's own lane, and lane 1 as well when the strand is known
+          if (ss == 0) { a0 = __fadd_rn(a0, vv); a1 = __fadd_rn(a1, vv); touched |= 3u; }
+          else if (ss == 1) { a1 = __fadd_rn(a1, vv); touched |= 2u; }
+          else { a2 = __fadd_rn(a2, vv); a1 = __fadd_rn(a1, vv); touched |= 6u; }
+          rem &= rem - 1;
         }
       }
+      if (leader) {
+        const uint32_t bit = 1u << (pos & 31u), wq = pos >> 5;
+        if (touched & 1u) { d[pos] = a0; atomicOr(masks + wq, bit); }
+        if (touched & 2u) { d[TWS + pos] = a1; atomicOr(masks + TNW + wq, bit); }
+        if (touched & 4u) { d[2 * TWS + pos] = a2; atomicOr(masks + 2 * TNW + wq, bit); }
+      }
+      __syncwarp();
       cur = nxt;
     }
-    __syncwarp();
 
-    // which 32-position words received any deposit, per strand lane
-    const int nwords = (int)((npos + 31) / 32);
-    for (int q = 0; q < nwords; q++) {
-#pragma unroll
-      for (int s = 0; s < 3; s++) {
-        const uint32_t m = __ballot_sync(FULL, d[s * TWS + q * 32 + lane] != 0.f);
-        if (lane == 0) masks[s * TNW + q] = m;
-      }
-    }
-    __syncwarp();
-
-    if (!have_carry) {
-      if (lane == 0) { while (atomicAdd(v.tile_flag + (tile_id - 1), 0u) == 0u) __nanosleep(40); }
-      __syncwarp();
-      __threadfence();
-      if (lane < 3) { c = __ldcg(v.tile_carry + (size_t)(tile_id - 1) * 8 + lane); bs = __ldcg(v.tile_carry + (size_t)(tile_id - 1) * 8 + 4 + lane); }
-    }
+    if (nev != 0) fetch_state();
 
     // the two recurrences (rlink.cpp:17037-17063), one strand lane per thread:
     //   c = max(0, c + d[i]);  bs = (i % BSIZE == 0 ? 0 : bs) + c;  out[i] = bs
+    const int nwords = (int)((npos + 31) / 32);
     uint32_t fillmask = 0;
     if (lane < 3) {
       float* dl = d + lane * TWS;
       const uint32_t* ml = masks + lane * TNW;
       float* fl = fills + lane * TNW;
-      const uint32_t to_reset = (STG_BSIZE - i0 % STG_BSIZE) % STG_BSIZE;  // in-tile position where idx % BSIZE == 0
       for (int q = 0; q < nwords; q++) {
         const uint32_t base = (uint32_t)q * 32;
         const bool full = base + 32 <= npos;
@@ -576,12 +728,8 @@ __global__ void __launch_bounds__(STG_TILE_WARPS * 32, 1) cov_tile_kernel(DevBat
           }
         }
       }
-      __stcg(v.tile_carry + (size_t)tile_id * 8 + lane, c);
-      __stcg(v.tile_carry + (size_t)tile_id * 8 + 4 + lane, bs);
-      __threadfence();
     }
-    __syncwarp();
-    if (lane == 0) { __threadfence(); atomicExch(v.tile_flag + tile_id, 1u); }
+    publish();
 
     // constant words
 #pragma unroll
@@ -596,15 +744,11 @@ __global__ void __launch_bounds__(STG_TILE_WARPS * 32, 1) cov_tile_kernel(DevBat
     __syncwarp();
 
     // finished bpcov of the sub-tile: one streaming, coalesced write per strand lane (incl. the zero padding)
-    {
-      float* out = v.bpcov + 3 * (size_t)gbase + i0;
-      const uint32_t n4 = min((uint32_t)TW, stride - i0) / 4;
 #pragma unroll
-      for (int s = 0; s < 3; s++) {
-        const float4* src = reinterpret_cast<const float4*>(d + s * TWS);
-        float4* dst = reinterpret_cast<float4*>(out + (size_t)s * stride);
-        for (uint32_t q = lane; q < n4; q += 32) __stcs(dst + q, src[q]);
-      }
+    for (int s = 0; s < 3; s++) {
+      const float4* src = reinterpret_cast<const float4*>(d + s * TWS);
+      float4* dst = reinterpret_cast<float4*>(out + (size_t)s * stride);
+      for (uint32_t q = lane; q < n4; q += 32) __stcs(dst + q, src[q]);
     }
     __syncwarp();
   }

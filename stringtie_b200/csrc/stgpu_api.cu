@@ -52,7 +52,9 @@ struct stg_dbatch {
   std::vector<int64_t> h_cov_off;  // [n_bundles] float offset of lane 0 of bundle b (= 3*gbase)
   std::vector<int64_t> h_stride;   // [n_bundles]
   std::vector<uint32_t> h_len;
-  int64_t ivl_capacity = 0;
+  int64_t ivl_capacity = 0;     // intervals the interval / event / chunk arrays can hold
+  int64_t cell_capacity = 0;    // counter cells of the binning matrix
+  int64_t scan_capacity = 0;    // elements the scan scratch covers
   int64_t sum_len = 0;
   bool ran = false;
 };
@@ -330,17 +332,28 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
   UP(j_start, h->n_juncs); UP(j_end, h->n_juncs); UP(j_strand, h->n_juncs); UP(j_guide_match, h->n_juncs);
   UP(j_nreads, h->n_juncs); UP(j_nm, h->n_juncs); UP(j_mm, h->n_juncs);
 #undef UP
+  // bundle of the first read of every block of STG_READ_BLOCK reads (the per-read kernels start their search there)
+  std::vector<uint32_t> cta_bundle((size_t)((h->n_reads + STG_READ_BLOCK - 1) / STG_READ_BLOCK) + 1, 0);
+  {
+    int64_t b = 0;
+    for (size_t i = 0; i + 1 < cta_bundle.size(); i++) {
+      const uint32_t n = (uint32_t)(i * STG_READ_BLOCK);
+      while (b + 1 < nb && h->b_read_off[b + 1] <= n) b++;
+      cta_bundle[i] = (uint32_t)b;
+    }
+  }
 #define UPV(field, vec) do { rc = dev_upload(ctx, d, &v.field, vec.data(), (int64_t)vec.size()); if (rc) { free_batch_allocs(d); delete d; return rc; } } while (0)
   UPV(b_len, len); UPV(b_stride, stride); UPV(b_gbase, gbase); UPV(b_tile_off, tile_off);
-  UPV(b_order, order); UPV(col_off, col_off);
+  UPV(b_order, order); UPV(col_off, col_off); UPV(cta_bundle, cta_bundle);
 #undef UPV
   // the layout vectors are pageable locals: make sure their copies have left the host before they die
   CK(ctx, cudaStreamSynchronize(ctx->stream));
 #define AL(field, count) do { rc = dev_alloc(ctx, d, &v.field, (int64_t)(count)); if (rc) { free_batch_allocs(d); delete d; return rc; } } while (0)
   AL(r_ivl_cnt, h->n_reads + 1);
-  AL(scan_partials, scan_partials_needed(std::max<int64_t>(h->n_reads + 1, h->n_segs * 2 + h->n_pairs * 4 + 16)));
+  d->scan_capacity = std::max<int64_t>(h->n_reads + 1, v.n_tiles + 1);
+  AL(scan_partials, scan_partials_needed(d->scan_capacity));
   AL(tile_carry, v.n_tiles * 8); AL(tile_flag, v.n_tiles); AL(tile_ticket, 1);
-  AL(tile_plan, v.n_tiles); AL(junc_anchor, h->n_juncs);
+  AL(tile_plan, v.n_tiles); AL(tile_evoff, v.n_tiles + 1); AL(tile_lastne, v.n_tiles); AL(junc_anchor, h->n_juncs);
   AL(bpcov, 3 * v.total_pos);
   AL(j_nreads_good, h->n_juncs); AL(j_leftsupport, h->n_juncs); AL(j_rightsupport, h->n_juncs);
   AL(b_cov_total, nb * 3);
@@ -377,27 +390,51 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   { Scope s(ctx, "junc_anchor", 1); CK(ctx, launch_junc_anchor(v, kp, st)); }
   { Scope s(ctx, "expand_count+junction_support", 1); CK(ctx, launch_expand_count(v, kp, st)); }
   { Scope s(ctx, "scan_interval_offsets", 3); CK(ctx, launch_scan_exclusive_add(v.r_ivl_cnt, v.n_reads + 1, v.scan_partials, st)); }
-  // the interval count sizes the next buffers: one 4-byte read-back (the only host sync inside the stage)
+  // the interval count sizes the next buffers: a 4-byte read-back (one of the two host syncs inside the stage)
   uint32_t n_ivl = 0;
   if (v.n_reads) {
     CK(ctx, cudaMemcpyAsync(&n_ivl, v.r_ivl_cnt + v.n_reads, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(ctx, cudaStreamSynchronize(st));
   }
+  if (n_ivl >= 0x7fffffffu) return fail(ctx, STG_ERANGE, "batch deposits more than 2^31 coverage intervals; split it");
   v.n_ivl = n_ivl;
+  v.n_chunks = ((int64_t)n_ivl + STG_CHUNK - 1) / STG_CHUNK;
   if ((int64_t)n_ivl > d->ivl_capacity) {
     const int64_t cap = (int64_t)n_ivl + (int64_t)n_ivl / 16 + 1024;
+    const int64_t ccap = (cap + STG_CHUNK - 1) / STG_CHUNK + 1;
     int rc;
-    if ((rc = dev_alloc(ctx, d, &v.ivl, cap)) || (rc = dev_alloc(ctx, d, &v.ivl_pmax_b, cap)) ||
-        (rc = dev_alloc(ctx, d, &v.ivl_smin_a, cap)))
+    if ((rc = dev_alloc(ctx, d, &v.ivl, cap)) || (rc = dev_alloc(ctx, d, &v.events, 2 * cap)) ||
+        (rc = dev_alloc(ctx, d, &v.ch_tlo, ccap)) || (rc = dev_alloc(ctx, d, &v.ch_thi, ccap)) ||
+        (rc = dev_alloc(ctx, d, &v.ch_pmax_thi, ccap)) || (rc = dev_alloc(ctx, d, &v.ch_smin_tlo, ccap)) ||
+        (rc = dev_alloc(ctx, d, &v.ch_row_off, ccap + 1)))
       return rc;
-    // scan scratch must cover the interval arrays too
-    uint32_t* sp = nullptr;
-    if ((rc = dev_alloc(ctx, d, &sp, scan_partials_needed(std::max<int64_t>(cap, v.n_reads + 1))))) return rc;
-    v.scan_partials = sp;
+    if (ccap + 1 > d->scan_capacity) {  // scan scratch must cover the chunk arrays too
+      uint32_t* sp = nullptr;
+      if ((rc = dev_alloc(ctx, d, &sp, scan_partials_needed(ccap + 1)))) return rc;
+      v.scan_partials = sp;
+      d->scan_capacity = ccap + 1;
+    }
     d->ivl_capacity = cap;
   }
   { Scope s(ctx, "expand_write", 1); CK(ctx, launch_expand_write(v, st)); }
-  { Scope s(ctx, "window_scans", 6); CK(ctx, launch_window_scans(v, st)); }
+  { Scope s(ctx, "chunk_hull+scans", 10); CK(ctx, launch_chunk_hull(v, st)); }
+  // second read-back: the size of the (chunk x tile) counter matrix
+  uint32_t n_cells = 0;
+  if (v.n_chunks) {
+    CK(ctx, cudaMemcpyAsync(&n_cells, v.ch_row_off + v.n_chunks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+  }
+  v.n_cells = n_cells;
+  if ((int64_t)n_cells > d->cell_capacity) {
+    const int64_t cap = (int64_t)n_cells + (int64_t)n_cells / 16 + 1024;
+    int rc;
+    if ((rc = dev_alloc(ctx, d, &v.cells, cap))) return rc;
+    d->cell_capacity = cap;
+  }
+  if (n_cells) CK(ctx, cudaMemsetAsync(v.cells, 0, sizeof(uint32_t) * (size_t)n_cells, st));
+  { Scope s(ctx, "bin_count", 1); CK(ctx, launch_bin_count(v, st)); }
+  { Scope s(ctx, "bin_columns+scans", 7); CK(ctx, launch_bin_columns(v, st)); }
+  { Scope s(ctx, "bin_scatter", 1); CK(ctx, launch_bin_scatter(v, st)); }
   { Scope s(ctx, "tile_plan", 1); CK(ctx, launch_tile_plan(v, st)); }
   { Scope s(ctx, "cov_tile", 1); CK(ctx, launch_cov_tiles(v, ctx->num_sms, st)); }
   { Scope s(ctx, "cov_totals", 1); CK(ctx, launch_cov_totals(v, st)); }

@@ -7,18 +7,23 @@
 #include "../../include/stgpu.h"
 
 #define STG_TILE_W 512           // positions per sub-tile (one warp owns one sub-tile of all three strand lanes)
-#define STG_TILE_WARPS 24        // warps per CTA of the tile kernel (one CTA per SM; ~8.6 KB shared memory per warp)
+#define STG_TILE_SHIFT 9
+#define STG_TILE_WARPS 24        // warps per CTA of the tile kernel (one CTA per SM; ~6.6 KB shared memory per warp)
 #define STG_LANE_ALIGN 32        // every strand lane of every bundle starts on a 128-byte boundary
+#define STG_CHUNK 512            // coverage intervals per binning chunk (one warp walks one chunk in order)
+#define STG_READ_BLOCK 256       // reads per CTA of the per-read kernels (cta_bundle is sampled at this step)
+#define STG_NO_TILE 0xffffffffu
 
 // Everything a warp needs to process one sub-tile, prepared by tile_plan_kernel (one 32-byte load).
 struct __align__(32) TileRec {
-  uint32_t g0;        // global position of the first index of the sub-tile
-  uint32_t gbase;     // global position of index 0 of its bundle (i0 = g0 - gbase)
-  uint32_t k0, k1;    // slice of the interval array that can deposit into the sub-tile
+  uint32_t gbase;     // global position of index 0 of its bundle
+  uint32_t i0;        // in-bundle index of the first position of the sub-tile
+  uint32_t e0;        // first event of the sub-tile in the binned event array
+  uint32_t nev;       // number of events
   uint32_t stride;    // lane stride of the bundle
   uint32_t npos;      // valid positions (<= STG_TILE_W)
   uint32_t tile_id;   // bundle-major tile id (index of its carry / flag)
-  uint32_t pad;
+  uint32_t wait_tile; // nearest earlier sub-tile of the bundle that has events (STG_NO_TILE: none)
 };
 
 // Device view of one batch: inputs (copies of stg_packed_batch arrays), the planned layout, scratch and outputs.
@@ -47,19 +52,31 @@ struct DevBatchView {
   const uint32_t* b_order;     // [n_bundles]   bundles sorted by tile count, descending
   const uint32_t* col_off;     // [n_cols+1]    col_off[j] = number of tiles with in-bundle index < j; tickets are
                                //               handed out column-major: all first sub-tiles, all second ones, ...
+  const uint32_t* cta_bundle;  // [ceil(n_reads/STG_READ_BLOCK)] bundle of read STG_READ_BLOCK*i
   int64_t n_cols;
   int64_t n_tiles;
   int64_t total_pos;           // b_gbase[n_bundles]
   // scratch
   uint32_t* r_ivl_cnt;         // [n_reads+1] per-read interval count, then exclusive prefix (in place)
   int64_t n_ivl;               // filled after the count pass (host reads it back)
-  uint4* ivl;                  // [n_ivl] {global position of the +w deposit, of the -w deposit, w bits, lane}
-  uint32_t* ivl_pmax_b;        // [n_ivl] -w positions, then (in place) their inclusive prefix max
-  uint32_t* ivl_smin_a;        // [n_ivl] +w positions, then (in place) their inclusive suffix min
+  uint4* ivl;                  // [n_ivl] {tile of the +w deposit, tile of the -w deposit,
+                               //          pos(+w) | pos(-w) << 9 | lane << 18, w bits}, in reference order
+  int64_t n_chunks;            // ceil(n_ivl / STG_CHUNK)
+  uint32_t* ch_tlo;            // [n_chunks] lowest tile any event of the chunk lands in
+  uint32_t* ch_thi;            // [n_chunks] highest
+  uint32_t* ch_pmax_thi;       // [n_chunks] inclusive prefix max of ch_thi  (monotone: searchable)
+  uint32_t* ch_smin_tlo;       // [n_chunks] inclusive suffix min of ch_tlo  (monotone: searchable)
+  uint32_t* ch_row_off;        // [n_chunks+1] first cell of the chunk's row of per-tile event counts
+  int64_t n_cells;             // ch_row_off[n_chunks] (host reads it back)
+  uint32_t* cells;             // [n_cells] row c, column t-ch_tlo[c]: events of chunk c in tile t; after the column
+                               //           scan: events of earlier chunks in tile t (the chunk's first slot)
+  uint32_t* tile_evoff;        // [n_tiles+1] event count per tile, then exclusive prefix (in place)
+  uint32_t* tile_lastne;       // [n_tiles]   (t+1 if tile t has events else 0), then inclusive prefix max
+  uint2* events;               // [2*n_ivl]   {pos | lane << 9, signed weight bits}, tile-major, reference order
   uint32_t* scan_partials;     // scratch for the 3-phase scans
   uint8_t* junc_anchor;        // [n_juncs] anchor length each junction demands (10 or 25, rlink.cpp:16991-16997)
   TileRec* tile_plan;          // [n_tiles] indexed by ticket
-  float* tile_carry;           // [n_tiles*8] c[3], bsum[3] handed from sub-tile j to j+1 of the same bundle
+  float* tile_carry;           // [n_tiles*8] c[3], bsum[3] after the last position of the sub-tile
   uint32_t* tile_flag;         // [n_tiles]   1 when tile_carry[tile] is published (bundle-major tile id)
   uint32_t* tile_ticket;       // [1]
   // outputs
@@ -78,7 +95,10 @@ struct KernelParams {
 cudaError_t launch_expand_count(const DevBatchView& v, const KernelParams& p, cudaStream_t st);
 cudaError_t launch_scan_exclusive_add(uint32_t* data, int64_t n_plus_1, uint32_t* partials, cudaStream_t st);
 cudaError_t launch_expand_write(const DevBatchView& v, cudaStream_t st);
-cudaError_t launch_window_scans(const DevBatchView& v, cudaStream_t st);
+cudaError_t launch_chunk_hull(const DevBatchView& v, cudaStream_t st);      // + the three chunk-level scans
+cudaError_t launch_bin_count(const DevBatchView& v, cudaStream_t st);
+cudaError_t launch_bin_columns(const DevBatchView& v, cudaStream_t st);     // + the two tile-level scans
+cudaError_t launch_bin_scatter(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_junc_anchor(const DevBatchView& v, const KernelParams& p, cudaStream_t st);
 cudaError_t launch_tile_plan(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_cov_tiles(const DevBatchView& v, int num_sms, cudaStream_t st);
