@@ -280,11 +280,11 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    t_tile = kmean.get("cov_tile", float("nan"))
+    t_tile = sum(kmean.get(k, 0.0) for k in ("deep_deposit", "cov_tile", "cov_fill")) or float("nan")
     alg_tile = 24.0 * L + 13.0 * S          # bytes the dominant kernel's work amounts to
     alg_stage = alg_tile + 8.0 * J
     t_stage = sum(kmean.values())
-    roofline = {"bound": "hbm", "kernel": "cov_tile", "achieved": alg_tile / (t_tile * 1e-3) / 1e9, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "deep_deposit + cov_tile + cov_fill (ordered deposit, recurrences and the bpcov write)", "achieved": alg_tile / (t_tile * 1e-3) / 1e9, "peak": peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 (B200_PROFILING.md)",
                 "unit": "GB/s", "frac": alg_tile / (t_tile * 1e-3) / 1e9 / peak, "traffic": None,
                 "algorithmic_bytes": alg_tile, "formula": "24*L + 13*S (SURVEY.md §8d; the 8*J term belongs to expand_count)",

@@ -124,19 +124,9 @@ cudaError_t launch_junc_anchor(const DevBatchView& v, const KernelParams& p, cud
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// K1: count intervals per read + junction support
+// K1: count intervals per read
 // --------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void add_support(const DevBatchView& v, uint32_t j, uint32_t lmax, uint32_t rmax, double w) {
-  const uint32_t anchor = v.junc_anchor[j];
-  if (lmax >= anchor) {
-    atomicAdd(v.j_leftsupport + j, w);
-    if (rmax >= anchor) { atomicAdd(v.j_rightsupport + j, w); atomicAdd(v.j_nreads_good + j, w); }
-  } else if (rmax >= anchor) {
-    atomicAdd(v.j_rightsupport + j, w);
-  }
-}
-
-__global__ void __launch_bounds__(STG_READ_BLOCK) expand_count_kernel(DevBatchView v, KernelParams prm) {
+__global__ void __launch_bounds__(STG_READ_BLOCK) expand_count_kernel(DevBatchView v) {
   const int64_t n64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n64 >= v.n_reads) return;
   const uint32_t n = (uint32_t)n64;
@@ -146,37 +136,37 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) expand_count_kernel(DevBatchVi
   walk_read_intervals(v, r0, n, [&](uint32_t, uint32_t, float, int) { cnt++; });
   v.r_ivl_cnt[n] = cnt;
   if (n64 == v.n_reads - 1) v.r_ivl_cnt[v.n_reads] = 0;
+}
 
-  // junction support (rlink.cpp:16890-17016): left anchor = longest exon at or before the intron,
-  // right anchor = longest exon after it.
-  const uint32_t s0 = v.r_seg_off[n], s1 = v.r_seg_off[n + 1];
-  const uint32_t nex = s1 - s0;
-  if (nex < 2) return;
-  float rdcount = v.r_count[n];
-  if ((v.r_flags[n] & STG_RF_UNITIG) && rdcount > 1.f) rdcount = 1.f;
-  const double w = (double)rdcount;
+// --------------------------------------------------------------------------------------------------------------
+// K1b: junction support (rlink.cpp:16890-17016): for intron i of a read, left anchor = longest exon at or before
+// it, right anchor = longest exon after it; the junction row gets leftsupport / rightsupport / nreads_good += w.
+// The sums are float weights accumulated in f64: every partial sum is exactly representable, so the order of the
+// additions is free.  One thread per read; the 32 reads of a warp usually cross the same few junctions, so each
+// round the warp groups its updates by junction row (match) and issues ONE f64 atomic per row and counter.
+// --------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(STG_READ_BLOCK) junc_support_kernel(DevBatchView v) {
+  const int64_t n64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool live = n64 < v.n_reads;
+  const uint32_t n = live ? (uint32_t)n64 : 0u;
+  uint32_t s0 = 0, nex = 0;
+  if (live) { s0 = v.r_seg_off[n]; nex = v.r_seg_off[n + 1] - s0; }
+  const uint32_t max_nex = __reduce_max_sync(FULL, nex);
+  if (max_nex < 2) return;
+  uint32_t j0 = 0;
+  float w = 0.f;
   const int32_t* __restrict__ rj = v.rjunc_idx + (s0 - n);
-  const uint32_t j0 = v.b_junc_off[b];
-  constexpr int kReg = 8;
-  if (nex <= kReg) {  // the usual case: exon lengths and their suffix maxima stay in registers
-    uint32_t len[kReg], rs[kReg];
-#pragma unroll
-    for (int q = 0; q < kReg; q++) len[q] = (uint32_t)q < nex ? v.seg_end[s0 + q] - v.seg_start[s0 + q] + 1 : 0u;
-    rs[kReg - 1] = len[kReg - 1];
-#pragma unroll
-    for (int q = kReg - 2; q >= 0; q--) rs[q] = len[q] > rs[q + 1] ? len[q] : rs[q + 1];
-    uint32_t lmax = 0;
-#pragma unroll
-    for (int i = 1; i < kReg; i++) {
-      if ((uint32_t)i < nex) {
-        if (len[i - 1] > lmax) lmax = len[i - 1];
-        const int32_t jl = rj[i - 1];
-        if (jl >= 0) add_support(v, j0 + (uint32_t)jl, lmax, rs[i], w);
-      }
-    }
-  } else {  // many exons (long reads): suffix maximum recomputed only when the running one expires
-    uint32_t lmax = 0, rmax = 0, rmax_at = 0;  // rmax = max len[i..nex-1], attained (last) at rmax_at
-    for (uint32_t i = 1; i < nex; i++) {
+  if (nex >= 2) {
+    j0 = v.b_junc_off[bundle_of_read(v, n)];
+    w = v.r_count[n];
+    if ((v.r_flags[n] & STG_RF_UNITIG) && w > 1.f) w = 1.f;
+  }
+  uint32_t lmax = 0, rmax = 0, rmax_at = 0;  // rmax = max len[i..nex-1], attained (last) at rmax_at
+  for (uint32_t i = 1; i < max_nex; i++) {
+    uint32_t key = 0x80000000u | (uint32_t)lane;  // lanes without an update this round never match anyone
+    bool fl = false, fr = false;
+    if (i < nex) {
       const uint32_t l = v.seg_end[s0 + i - 1] - v.seg_start[s0 + i - 1] + 1;
       if (l > lmax) lmax = l;
       if (i == 1 || rmax_at < i) {
@@ -187,7 +177,34 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) expand_count_kernel(DevBatchVi
         }
       }
       const int32_t jl = rj[i - 1];
-      if (jl >= 0) add_support(v, j0 + (uint32_t)jl, lmax, rmax, w);
+      if (jl >= 0) {
+        const uint32_t j = j0 + (uint32_t)jl;
+        const uint32_t anchor = v.junc_anchor[j];
+        fl = lmax >= anchor; fr = rmax >= anchor;
+        if (fl || fr) key = j;
+      }
+    }
+    const uint32_t grp = __match_any_sync(FULL, key);
+    const uint32_t bl = __ballot_sync(FULL, fl), br = __ballot_sync(FULL, fr);
+    const bool leader = (fl || fr) && (__ffs(grp) - 1 == lane);
+    const int maxn = __reduce_max_sync(FULL, (fl || fr) ? __popc(grp) : 0);
+    double dl = 0.0, dr = 0.0, dg = 0.0;
+    uint32_t rem = leader ? grp : 0u;
+    for (int r = 0; r < maxn; r++) {
+      const int src = __ffs(rem) - 1;                      // -1 for idle lanes: the shuffle wraps, value unused
+      const double wv = (double)__shfl_sync(FULL, w, src);
+      if (rem) {
+        const bool ml = (bl >> src) & 1u, mr = (br >> src) & 1u;
+        if (ml) dl += wv;
+        if (mr) dr += wv;
+        if (ml && mr) dg += wv;
+        rem &= rem - 1;
+      }
+    }
+    if (leader) {
+      if (grp & bl) atomicAdd(v.j_leftsupport + key, dl);
+      if (grp & br) atomicAdd(v.j_rightsupport + key, dr);
+      if (grp & bl & br) atomicAdd(v.j_nreads_good + key, dg);
     }
   }
 }
@@ -336,9 +353,15 @@ cudaError_t launch_scan_exclusive_add(uint32_t* data, int64_t n_plus_1, uint32_t
 }
 
 
-cudaError_t launch_expand_count(const DevBatchView& v, const KernelParams& p, cudaStream_t st) {
+cudaError_t launch_expand_count(const DevBatchView& v, cudaStream_t st) {
   if (v.n_reads == 0) return cudaSuccess;
-  expand_count_kernel<<<(unsigned)((v.n_reads + STG_READ_BLOCK - 1) / STG_READ_BLOCK), STG_READ_BLOCK, 0, st>>>(v, p);
+  expand_count_kernel<<<(unsigned)((v.n_reads + STG_READ_BLOCK - 1) / STG_READ_BLOCK), STG_READ_BLOCK, 0, st>>>(v);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_junc_support(const DevBatchView& v, cudaStream_t st) {
+  if (v.n_reads == 0 || v.n_juncs == 0) return cudaSuccess;
+  junc_support_kernel<<<(unsigned)((v.n_reads + STG_READ_BLOCK - 1) / STG_READ_BLOCK), STG_READ_BLOCK, 0, st>>>(v);
   return cudaGetLastError();
 }
 
@@ -492,41 +515,228 @@ cudaError_t launch_bin_columns(const DevBatchView& v, cudaStream_t st) {
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// K8: per-tile plan records, in ticket (column-major) order
+// K8: per-tile plan records in ticket order.
+// Schedule: sub-tile j of a bundle with nt sub-tiles runs in round floor(j * n_rounds / nt), n_rounds >= max nt.
+// Every bundle then advances at the same relative pace from the first ticket to the last (long bundles are not
+// left over at the end), a bundle has at most one sub-tile per round, and sub-tile j-1 always holds an earlier
+// ticket than sub-tile j — which is what makes waiting on a predecessor's carry deadlock-free.
 // --------------------------------------------------------------------------------------------------------------
+template <bool WRITE>
 __global__ void __launch_bounds__(256) tile_plan_kernel(DevBatchView v) {
   const int64_t t64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t64 >= v.n_tiles) return;
-  const uint32_t t = (uint32_t)t64;
-  // column j = last j with col_off[j] <= t; rank within the column -> bundle
-  uint32_t lo = 0, hi = (uint32_t)v.n_cols;
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(v.col_off + mid) <= t) lo = mid; else hi = mid;
+  const int lane = threadIdx.x & 31;
+  const bool live = t64 < v.n_tiles;
+  const uint32_t tid = live ? (uint32_t)t64 : 0u;   // bundle-major tile id
+  // key: the round of a sub-tile with events; one common key for all event-free sub-tiles; none for dead lanes
+  uint32_t key = 0x80000000u | (uint32_t)lane, b = 0, jt = 0, e0 = 0, nev = 0;
+  if (live) {
+    e0 = v.tile_evoff[tid];
+    nev = v.tile_evoff[tid + 1] - e0;
+    uint32_t lo = 0, hi = (uint32_t)v.n_bundles;     // bundle = last b with b_tile_off[b] <= tid
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(v.b_tile_off + mid) <= tid) lo = mid; else hi = mid;
+    }
+    b = lo;
+    const uint32_t first = __ldg(v.b_tile_off + b);
+    jt = tid - first;
+    const uint32_t nt = __ldg(v.b_tile_off + b + 1) - first;
+    key = nev ? (uint32_t)(((uint64_t)jt * (uint64_t)v.n_rounds) / nt) : 0x40000000u;
   }
-  const uint32_t jt = lo;
-  const uint32_t b = v.b_order[t - v.col_off[jt]];
+  // one atomic per distinct key in the warp
+  const uint32_t grp = __match_any_sync(FULL, key);
+  const int leader = __ffs(grp) - 1;
+  uint32_t base = 0;
+  if (live && lane == leader) {
+    uint32_t* ctr;
+    if (key == 0x40000000u) ctr = v.round_cur + v.n_rounds;          // the fill list has its own cursor
+    else ctr = (WRITE ? v.round_cur : v.round_off) + key;
+    if (WRITE || key != 0x40000000u) base = atomicAdd(ctr, (uint32_t)__popc(grp));
+  }
+  base = __shfl_sync(FULL, base, leader);
+  if (!WRITE || !live) return;
+  // tickets of the main kernel: [0, n_main) by round; the event-free sub-tiles follow in any order
+  const uint32_t n_main = __ldg(v.round_off + v.n_rounds);
+  const uint32_t slot = (nev ? __ldg(v.round_off + key) : n_main) + base + __popc(grp & ((1u << lane) - 1u));
   const uint32_t len = v.b_len[b];
   TileRec r;
   r.gbase = v.b_gbase[b];
   r.i0 = jt * STG_TILE_W;
   r.npos = min((uint32_t)STG_TILE_W, len - r.i0);
   r.stride = v.b_stride[b];
-  const uint32_t first = v.b_tile_off[b];
-  r.tile_id = first + jt;
-  r.e0 = v.tile_evoff[r.tile_id];
-  r.nev = v.tile_evoff[r.tile_id + 1] - r.e0;
+  r.tile_id = tid;
+  r.e0 = e0;
+  r.nev = nev;
+  if (nev >= STG_DEEP_EVENTS) {
+    // deep sub-tile: its difference array is prepared by deep_deposit_kernel; the tile kernel loads slot e0
+    const uint32_t ds = atomicAdd(v.deep_count, 1u);
+    v.deep_list[ds] = make_uint4(tid, e0, nev, 0u);
+    r.e0 = ds;
+    r.nev = nev | 0x80000000u;
+  }
   r.wait_tile = STG_NO_TILE;
   if (jt > 0) {
-    const uint32_t last = v.tile_lastne[r.tile_id - 1];   // 1 + last tile at or before tile_id-1 that has events
-    if (last > first) r.wait_tile = last - 1;
+    const uint32_t last = v.tile_lastne[tid - 1];   // 1 + last tile at or before tid-1 that has events
+    if (last > tid - jt) r.wait_tile = last - 1;
   }
-  v.tile_plan[t] = r;
+  v.tile_plan[slot] = r;
 }
 
 cudaError_t launch_tile_plan(const DevBatchView& v, cudaStream_t st) {
   if (v.n_tiles == 0) return cudaSuccess;
-  tile_plan_kernel<<<(unsigned)((v.n_tiles + 255) / 256), 256, 0, st>>>(v);
+  cudaError_t e = cudaMemsetAsync(v.round_off, 0, sizeof(uint32_t) * (size_t)(v.n_rounds + 1), st);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(v.round_cur, 0, sizeof(uint32_t) * (size_t)(v.n_rounds + 1), st)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(v.deep_count, 0, sizeof(uint32_t), st)) != cudaSuccess) return e;
+  tile_plan_kernel<false><<<(unsigned)((v.n_tiles + 255) / 256), 256, 0, st>>>(v);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if ((e = run_scan<OP_ADD, false, true>(v.round_off, v.round_off, v.n_rounds + 1, v.scan_partials, st)) != cudaSuccess) return e;
+  tile_plan_kernel<true><<<(unsigned)((v.n_tiles + 255) / 256), 256, 0, st>>>(v);
+  return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K8b: deep sub-tiles (>= STG_DEEP_EVENTS events; in RNA-seq a third of all events sit in a fraction of a percent
+// of the sub-tiles, and a single position — a splice site of a highly expressed gene — can receive 10^5 of them).
+// Chaining such a position through warp shuffles costs ~12 instructions per event on one warp: milliseconds.
+// Instead one CTA sorts the sub-tile's event list by position (stable: 16 warps x 512 positions counting sort in
+// shared memory, each warp owning a contiguous slice of the list), and then every position's events are summed in
+// a register by one thread reading them in reference order — the bare dependent-add chain the arithmetic needs.
+// Output: the finished difference array d[3][512] of the sub-tile (deep_d), consumed by cov_tile_kernel.
+// --------------------------------------------------------------------------------------------------------------
+constexpr int DEEP_WARPS = 16;
+static_assert(DEEP_WARPS * 32 == STG_TILE_W, "phase 2 of deep_deposit_kernel maps one thread to one position");
+
+__global__ void __launch_bounds__(DEEP_WARPS * 32) deep_deposit_kernel(DevBatchView v) {
+  __shared__ uint32_t cnt[DEEP_WARPS][STG_TILE_W];       // per warp slice: events per position, then first slot
+  __shared__ uint32_t poff[STG_TILE_W + 1];              // first slot of every position in the sorted list
+  __shared__ __align__(16) float stage[DEEP_WARPS][3][32];
+  __shared__ uint32_t wtot[DEEP_WARPS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t ndeep = *v.deep_count;
+  for (uint32_t di = blockIdx.x; di < ndeep; di += gridDim.x) {
+    const uint4 rec = v.deep_list[di];
+    const uint32_t e0 = rec.y, nev = rec.z;
+    const uint2* __restrict__ ev = v.events + e0;
+    uint2* __restrict__ sorted = v.events2 + e0;
+    const uint32_t steps = (nev + 31) / 32, per = (steps + DEEP_WARPS - 1) / DEEP_WARPS;
+    const uint32_t s_lo = min(steps, (uint32_t)wid * per), s_hi = min(steps, s_lo + per);
+    // phase 1: per-slice histogram
+    for (int q = lane; q < STG_TILE_W; q += 32) cnt[wid][q] = 0u;
+    __syncwarp();
+    for (uint32_t st = s_lo; st < s_hi; st += 4) {
+      uint32_t px[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t e = (st + u) * 32 + lane;
+        px[u] = (st + u < s_hi && e < nev) ? (__ldg(&ev[e].x) & 511u) : 0xffffffffu;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (px[u] != 0xffffffffu) atomicAdd(&cnt[wid][px[u]], 1u);
+    }
+    __syncthreads();
+    // phase 2: thread p owns position p: exclusive prefix down the slices, then across positions
+    {
+      const int p = threadIdx.x;
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < DEEP_WARPS; w++) { const uint32_t x = cnt[w][p]; cnt[w][p] = run; run += x; }
+      uint32_t incl = run;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
+      if (lane == 31) wtot[wid] = incl;
+      __syncthreads();
+      uint32_t wbase = 0;
+      for (int w = 0; w < wid; w++) wbase += wtot[w];
+      const uint32_t excl = wbase + incl - run;
+      poff[p] = excl;
+      if (p == STG_TILE_W - 1) poff[STG_TILE_W] = excl + run;
+#pragma unroll
+      for (int w = 0; w < DEEP_WARPS; w++) cnt[w][p] += excl;
+    }
+    __syncthreads();
+    // phase 3: stable scatter of this warp's slice, 32 events per step in order
+    {
+      uint2 x = make_uint2(0u, 0u);
+      if (s_lo < s_hi && s_lo * 32 + lane < nev) x = __ldg(&ev[s_lo * 32 + lane]);
+      for (uint32_t st = s_lo; st < s_hi; st++) {
+        const bool valid = st * 32 + lane < nev;
+        uint2 xn = make_uint2(0u, 0u);
+        if (st + 1 < s_hi && (st + 1) * 32 + lane < nev) xn = __ldg(&ev[(st + 1) * 32 + lane]);
+        const uint32_t pos = x.x & 511u;
+        const uint32_t grp = __match_any_sync(FULL, valid ? pos : (0x8000u | (uint32_t)lane));
+        const int leader = __ffs(grp) - 1;
+        uint32_t base = 0;
+        if (valid && lane == leader) { base = cnt[wid][pos]; cnt[wid][pos] = base + __popc(grp); }
+        base = __shfl_sync(FULL, base, leader);
+        if (valid) sorted[base + __popc(grp & lt)] = make_uint2(x.x >> 9, x.y);
+        __syncwarp();
+        x = xn;
+      }
+    }
+    __syncthreads();   // also orders the global writes of `sorted` before the reads below (same CTA)
+    // phase 4: every position's events summed in reference order (cov_edge_add, rlink.cpp:133-142: the strand's own
+    // lane, and lane 1 as well).  Short lists: one thread per position walks its list.  Long lists (a splice site of
+    // a deep locus): the warp loads 32 events at a time and lanes 0..2 run the bare chain of dependent adds.
+    float* dd = v.deep_d + (size_t)di * (3 * STG_TILE_W);
+    {
+      const int p = threadIdx.x;
+      const uint32_t l0 = poff[p], n = poff[p + 1] - l0;
+      const bool is_long = n > 64u;
+      if (!is_long) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (uint32_t i = 0; i < n; i++) {
+          const uint2 x = sorted[l0 + i];
+          const float val = __uint_as_float(x.y);
+          if (x.x == 0u) a0 = __fadd_rn(a0, val);
+          if (x.x == 2u) a2 = __fadd_rn(a2, val);
+          a1 = __fadd_rn(a1, val);
+        }
+        dd[p] = a0; dd[STG_TILE_W + p] = a1; dd[2 * STG_TILE_W + p] = a2;
+      }
+      uint32_t todo = __ballot_sync(FULL, is_long);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int q = wid * 32 + src;
+        const uint32_t q0 = __shfl_sync(FULL, l0, src), qn = __shfl_sync(FULL, n, src);
+        float acc = 0.f;   // lane s < 3 accumulates strand lane s
+        uint2 cur = make_uint2(1u, 0u);
+        if ((uint32_t)lane < qn) cur = __ldcg(&sorted[q0 + lane]);
+        for (uint32_t off = 0; off < qn; off += 32) {
+          uint2 nxt = make_uint2(1u, 0u);      // padding: +0.0 on lane 1, a no-op (no accumulator is ever -0)
+          if (off + 32 + lane < qn) nxt = __ldcg(&sorted[q0 + off + 32 + lane]);
+          const float val = __uint_as_float(cur.y);
+          stage[wid][0][lane] = cur.x == 0u ? val : 0.f;
+          stage[wid][1][lane] = val;
+          stage[wid][2][lane] = cur.x == 2u ? val : 0.f;
+          __syncwarp();
+          if (lane < 3) {
+            const float4* sv = reinterpret_cast<const float4*>(stage[wid][lane]);
+            const uint32_t m = min(32u, qn - off);
+            if (m == 32u) {
+#pragma unroll
+              for (int u = 0; u < 8; u++) {
+                const float4 y = sv[u];
+                acc = __fadd_rn(acc, y.x); acc = __fadd_rn(acc, y.y); acc = __fadd_rn(acc, y.z); acc = __fadd_rn(acc, y.w);
+              }
+            } else {
+              for (uint32_t u = 0; u < m; u++) acc = __fadd_rn(acc, stage[wid][lane][u]);
+            }
+          }
+          __syncwarp();
+          cur = nxt;
+        }
+        if (lane < 3) dd[lane * STG_TILE_W + q] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_deep_deposit(const DevBatchView& v, int num_sms, cudaStream_t st) {
+  if (v.n_tiles == 0 || v.n_ivl == 0) return cudaSuccess;
+  deep_deposit_kernel<<<num_sms * 5, DEEP_WARPS * 32, 0, st>>>(v);
   return cudaGetLastError();
 }
 
@@ -541,24 +751,61 @@ constexpr int TILE_SMEM_WORDS = 3 * TWS + 3 * TNW + 3 * TNW;  // d, masks, fills
 
 int cov_tile_smem_bytes() { return STG_TILE_WARPS * TILE_SMEM_WORDS * 4; }
 
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t x;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(x) : "l"(p) : "memory");
+constexpr unsigned long long CARRY_EMPTY = 0xffffffffffffffffull;  // never a valid (c, bs) pair: both are >= 0
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long x;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(x) : "l"(p) : "memory");
   return x;
 }
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t x) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(x) : "memory");
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long x) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(x) : "memory");
 }
 
-// wait until sub-tile `tile` has published its carry, then load it: lanes 0..2 get (c, bs) of their strand lane
-__device__ __forceinline__ void take_carry(const DevBatchView& v, uint32_t tile, int lane, float& c, float& bs) {
-  if (lane == 0) {
-    while (ld_acquire_u32(v.tile_flag + tile) == 0u) __nanosleep(32);
+// m repeated additions bs = fl(bs + c), c >= 0, in O(binades crossed) instead of O(m).
+// Inside one binade a float's bit pattern is linear in its value, and from the second addition inside the binade
+// on, every addition of the same c moves the pattern by the same integer (round-to-nearest-even settles after one
+// step: the tie case leaves an even mantissa behind).  So: step explicitly until three consecutive sums share a
+// binade, then jump to the last sum that still does.  Checked against the plain loop on 3*10^7 random cases
+// (tests/test_advance.c) including ties, subnormals and binade crossings.
+__device__ __forceinline__ float advance_bs(float bs, float c, uint32_t m) {
+  while (m) {
+    const float y1 = __fadd_rn(bs, c); m--; if (!m) return y1;
+    const float y2 = __fadd_rn(y1, c); m--; if (!m) return y2;
+    const uint32_t b1 = __float_as_uint(y1), b2 = __float_as_uint(y2);
+    if ((b1 ^ b2) & 0xff800000u) { bs = y2; continue; }
+    const float y3 = __fadd_rn(y2, c); m--;
+    const uint32_t b3 = __float_as_uint(y3);
+    if ((b3 ^ b2) & 0xff800000u) { bs = y3; continue; }
+    const uint32_t inc = b3 - b2;
+    if (inc == 0) return y3;
+    const uint32_t top = (b3 & 0xff800000u) + 0x00800000u;
+    uint32_t t = (top - b3) / inc;
+    if (t > m) t = m;
+    bs = __uint_as_float(b3 + t * inc); m -= t;
   }
-  __syncwarp();
-  if (lane < 3) {
-    c = __ldcg(v.tile_carry + (size_t)tile * 8 + lane);
-    bs = __ldcg(v.tile_carry + (size_t)tile * 8 + 4 + lane);
+  return bs;
+}
+
+// The same, writing every intermediate sum: dl[k] for k in [k, k1) with the whole warp (arguments warp-uniform).
+__device__ __forceinline__ void fill_run(float* dl, uint32_t k, uint32_t k1, float c, float& bs, int lane) {
+  while (k < k1) {
+    const float y1 = __fadd_rn(bs, c); if (lane == 0) dl[k] = y1; k++; bs = y1; if (k == k1) break;
+    const float y2 = __fadd_rn(y1, c); if (lane == 0) dl[k] = y2; k++; bs = y2; if (k == k1) break;
+    const uint32_t b1 = __float_as_uint(y1), b2 = __float_as_uint(y2);
+    if ((b1 ^ b2) & 0xff800000u) continue;
+    const float y3 = __fadd_rn(y2, c); if (lane == 0) dl[k] = y3; k++; bs = y3;
+    const uint32_t b3 = __float_as_uint(y3);
+    if ((b3 ^ b2) & 0xff800000u) continue;
+    const uint32_t inc = b3 - b2;
+    uint32_t t = k1 - k;
+    if (inc) {
+      const uint32_t top = (b3 & 0xff800000u) + 0x00800000u;
+      const uint32_t tm = (top - b3) / inc;
+      if (tm < t) t = tm;
+    }
+    for (uint32_t j = lane + 1; j <= t; j += 32) dl[k + j - 1] = __uint_as_float(b3 + j * inc);
+    bs = __uint_as_float(b3 + t * inc); k += t;
   }
 }
 
@@ -569,188 +816,262 @@ __global__ void __launch_bounds__(STG_TILE_WARPS * 32, 1) cov_tile_kernel(DevBat
   uint32_t* masks = reinterpret_cast<uint32_t*>(d + 3 * TWS);                     // masks[3][TNW]
   float* fills = reinterpret_cast<float*>(masks + 3 * TNW);                       // fills[3][TNW]
   const uint2 no_event = make_uint2(0u, 0u);
+  const uint32_t n_main = __ldg(v.round_off + v.n_rounds);   // sub-tiles with events: tickets [0, n_main)
 
+  // A warp takes a ticket only when it is free to work on it at once: a sub-tile queued behind unrelated work would
+  // hold up every later sub-tile of its bundle (measured: taking tickets ahead doubled the kernel time).
   for (;;) {
-    uint32_t t = 0;
-    if (lane == 0) t = atomicAdd(v.tile_ticket, 1u);
-    t = __shfl_sync(FULL, t, 0);
-    if ((int64_t)t >= v.n_tiles) break;
-    // one 32-byte record per sub-tile
+    uint32_t t_cur = 0;
+    if (lane == 0) t_cur = atomicAdd(v.tile_ticket, 1u);
+    t_cur = __shfl_sync(FULL, t_cur, 0);
+    if (t_cur >= n_main) break;
     uint32_t recw = 0;
-    if (lane < 8) recw = __ldg(reinterpret_cast<const uint32_t*>(v.tile_plan + t) + lane);
+    if (lane < 8) recw = __ldg(reinterpret_cast<const uint32_t*>(v.tile_plan + t_cur) + lane);
+
     const uint32_t gbase = __shfl_sync(FULL, recw, 0), i0 = __shfl_sync(FULL, recw, 1);
-    const uint32_t e0 = __shfl_sync(FULL, recw, 2), nev = __shfl_sync(FULL, recw, 3);
+    const uint32_t e0 = __shfl_sync(FULL, recw, 2), nev_raw = __shfl_sync(FULL, recw, 3);
     const uint32_t stride = __shfl_sync(FULL, recw, 4), npos = __shfl_sync(FULL, recw, 5);
     const uint32_t tile_id = __shfl_sync(FULL, recw, 6), wait_tile = __shfl_sync(FULL, recw, 7);
     const uint32_t to_reset = (STG_BSIZE - i0 % STG_BSIZE) % STG_BSIZE;  // in-tile position where idx % BSIZE == 0
     float* out = v.bpcov + 3 * (size_t)gbase + i0;
     const uint32_t n4 = min((uint32_t)TW, stride - i0) / 4;              // float4 per lane incl. the zero padding
 
+    const bool deep = (nev_raw & 0x80000000u) != 0u;     // difference array precomputed by deep_deposit_kernel
+    const uint32_t nev = deep ? 0u : nev_raw;
     uint2 cur = no_event;
     if (lane < nev) cur = __ldcs(v.events + e0 + lane);
 
-    // state at the end of the previous position (rlink.cpp:17037-17063): c = clamped coverage, bs = running block sum
+    // state at the end of the previous position (rlink.cpp:17037-17063): c = clamped coverage, bs = running block sum.
+    // It is published by the nearest earlier sub-tile that had events; over the event-free positions in between c
+    // stays put and bs is c added once per position (restarting from 0 at a block start): advance_bs.
     float c = 0.f, bs = 0.f;
     auto fetch_state = [&]() {
       if (wait_tile == STG_NO_TILE) return;            // nothing deposited before this sub-tile: c = bs = 0
-      take_carry(v, wait_tile, lane, c, bs);
-      if (wait_tile == tile_id - 1) return;
-      // the sub-tiles in between had no events.  With c == 0 they only carry bs along (reset to 0 by a block start)
-      const bool nz = __any_sync(FULL, lane < 3 && c != 0.f);
-      if (!nz) {
+      if (lane < 3) {
+        const unsigned long long* p = v.tile_carry + (size_t)wait_tile * 4 + lane;
+        unsigned long long x = ld_relaxed_u64(p);
+        uint32_t ns = 32;
+        while (x == CARRY_EMPTY) { __nanosleep(ns); if (ns < 256u) ns <<= 1; x = ld_relaxed_u64(p); }
+        c = __uint_as_float((uint32_t)x); bs = __uint_as_float((uint32_t)(x >> 32));
         const uint32_t first = tile_id - i0 / TW;                        // first sub-tile of the bundle
         const uint32_t wlast = (wait_tile - first) * TW + TW - 1;        // last index of the sub-tile waited on
-        if ((i0 - 1) / STG_BSIZE != wlast / STG_BSIZE) bs = 0.f;
-      } else {
-        take_carry(v, tile_id - 1, lane, c, bs);                         // a residue travels: take the slow chain
-      }
-    };
-    auto publish = [&]() {
-      if (lane < 3) {
-        __stcg(v.tile_carry + (size_t)tile_id * 8 + lane, c);
-        __stcg(v.tile_carry + (size_t)tile_id * 8 + 4 + lane, bs);
-        __threadfence();
+        const uint32_t gap = i0 - 1 - wlast;
+        if (gap) {
+          const uint32_t rst = (i0 - 1) / STG_BSIZE * STG_BSIZE;         // last block start at or before i0-1
+          bs = rst > wlast ? advance_bs(0.f, c, i0 - rst) : advance_bs(bs, c, gap);
+        }
       }
       __syncwarp();
-      if (lane == 0) st_release_u32(v.tile_flag + tile_id, 1u);
+    };
+    auto write_out = [&](uint32_t fillmask) {
+      // finished bpcov of the sub-tile: one streaming, coalesced write per strand lane (incl. the zero padding);
+      // constant words are taken from `fills` instead of shared memory
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        const uint32_t fm = __shfl_sync(FULL, fillmask, s);
+        const float4* src = reinterpret_cast<const float4*>(d + s * TWS);
+        float4* dst = reinterpret_cast<float4*>(out + (size_t)s * stride);
+        for (uint32_t q = lane; q < n4; q += 32) {
+          float4 x;
+          if ((fm >> (q >> 3)) & 1u) { const float f = fills[s * TNW + (q >> 3)]; x = make_float4(f, f, f, f); }
+          else x = src[q];
+          __stcs(dst + q, x);
+        }
+      }
+      __syncwarp();
     };
 
-    if (nev == 0) {
-      fetch_state();
-      if (!__any_sync(FULL, lane < 3 && c != 0.f)) {
-        // no events and no coverage entering: every position repeats bs (0 from a block start on)
-        float b0 = __shfl_sync(FULL, bs, 0), b1 = __shfl_sync(FULL, bs, 1), b2 = __shfl_sync(FULL, bs, 2);
-        if (to_reset < npos) bs = 0.f;
-        publish();
-#pragma unroll
-        for (int s = 0; s < 3; s++) {
-          const float bv = s == 0 ? b0 : (s == 1 ? b1 : b2);
-          float4* dst = reinterpret_cast<float4*>(out + (size_t)s * stride);
-          for (uint32_t q = lane; q < n4; q += 32) {
-            const uint32_t p = q * 4;
-            float4 x;
-            x.x = (p + 0 < to_reset && p + 0 < npos) ? bv : 0.f;
-            x.y = (p + 1 < to_reset && p + 1 < npos) ? bv : 0.f;
-            x.z = (p + 2 < to_reset && p + 2 < npos) ? bv : 0.f;
-            x.w = (p + 3 < to_reset && p + 3 < npos) ? bv : 0.f;
-            __stcs(dst + q, x);
-          }
-        }
-        continue;
-      }
-    }
-
-    // clear the sub-tile
     {
-      float4* d4 = reinterpret_cast<float4*>(d);
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int q = lane; q < 3 * TWS / 4; q += 32) d4[q] = z;
-      for (int q = lane; q < 3 * TNW; q += 32) masks[q] = 0u;
-    }
-    __syncwarp();
-
-    // ordered deposit of the event list.  Events of one 32-group that share a position are chained, in lane
-    // (= reference) order, in the registers of the first of them; groups are applied one after the other.
-    for (uint32_t eb = 0; eb < nev; eb += 32) {
-      uint2 nxt = no_event;
-      if (eb + 32 + lane < nev) nxt = __ldcs(v.events + e0 + eb + 32 + lane);
-      const bool valid = eb + lane < nev;
-      const uint32_t pos = cur.x & 511u, sl = cur.x >> 9;
-      const float val = __uint_as_float(cur.y);
-      const uint32_t grp = __match_any_sync(FULL, valid ? pos : (0x8000u | (uint32_t)lane));
-      const bool leader = valid && (__ffs(grp) - 1 == lane);
-      const int maxn = __reduce_max_sync(FULL, valid ? __popc(grp) : 0);
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-      if (leader) { a0 = d[pos]; a1 = d[TWS + pos]; a2 = d[2 * TWS + pos]; }
-      uint32_t rem = leader ? grp : 0u;
-      uint32_t touched = 0;
-      for (int r = 0; r < maxn; r++) {
-        const int src = rem ? __ffs(rem) - 1 : lane;
-        const float vv = __shfl_sync(FULL, val, src);
-        const uint32_t ss = __shfl_sync(FULL, sl, src);
-        if (rem) {
-          // cov_edge_add (rlink.cpp:133-142): the strand's own lane, and lane 1 as well when the strand is known
-          if (ss == 0) { a0 = __fadd_rn(a0, vv); a1 = __fadd_rn(a1, vv); touched |= 3u; }
-          else if (ss == 1) { a1 = __fadd_rn(a1, vv); touched |= 2u; }
-          else { a2 = __fadd_rn(a2, vv); a1 = __fadd_rn(a1, vv); touched |= 6u; }
-          rem &= rem - 1;
+      // ---- sub-tile with events ----
+      if (deep) {
+        const float4* src = reinterpret_cast<const float4*>(v.deep_d + (size_t)e0 * (3 * TW));
+        float4* d4 = reinterpret_cast<float4*>(d);
+        for (int q = lane; q < 3 * TW / 4; q += 32) d4[(q / (TW / 4)) * (TWS / 4) + (q % (TW / 4))] = __ldcs(src + q);
+        __syncwarp();
+        for (int q = 0; q < TNW; q++) {
+#pragma unroll
+          for (int s = 0; s < 3; s++) {
+            const uint32_t m = __ballot_sync(FULL, d[s * TWS + q * 32 + lane] != 0.f);
+            if (lane == 0) masks[s * TNW + q] = m;
+          }
         }
-      }
-      if (leader) {
-        const uint32_t bit = 1u << (pos & 31u), wq = pos >> 5;
-        if (touched & 1u) { d[pos] = a0; atomicOr(masks + wq, bit); }
-        if (touched & 2u) { d[TWS + pos] = a1; atomicOr(masks + TNW + wq, bit); }
-        if (touched & 4u) { d[2 * TWS + pos] = a2; atomicOr(masks + 2 * TNW + wq, bit); }
+      } else {
+        float4* d4 = reinterpret_cast<float4*>(d);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = lane; q < 3 * TWS / 4; q += 32) d4[q] = z;
+        for (int q = lane; q < 3 * TNW; q += 32) masks[q] = 0u;
       }
       __syncwarp();
-      cur = nxt;
-    }
 
-    if (nev != 0) fetch_state();
-
-    // the two recurrences (rlink.cpp:17037-17063), one strand lane per thread:
-    //   c = max(0, c + d[i]);  bs = (i % BSIZE == 0 ? 0 : bs) + c;  out[i] = bs
-    const int nwords = (int)((npos + 31) / 32);
-    uint32_t fillmask = 0;
-    if (lane < 3) {
-      float* dl = d + lane * TWS;
-      const uint32_t* ml = masks + lane * TNW;
-      float* fl = fills + lane * TNW;
-      for (int q = 0; q < nwords; q++) {
-        const uint32_t base = (uint32_t)q * 32;
-        const bool full = base + 32 <= npos;
-        const bool has_reset = to_reset >= base && to_reset < base + 32;
-        if (full && !has_reset) {
-          if (ml[q] == 0 && __fadd_rn(bs, c) == bs) {  // nothing deposited and c too small to move bs: constant word
-            fl[q] = bs;
-            fillmask |= 1u << q;
-            continue;
-          }
-          float4 x[8];
-#pragma unroll
-          for (int u = 0; u < 8; u++) x[u] = *reinterpret_cast<const float4*>(dl + base + u * 4);
-#pragma unroll
-          for (int u = 0; u < 8; u++) {
-            c = fmaxf(__fadd_rn(x[u].x, c), 0.f); bs = __fadd_rn(c, bs); x[u].x = bs;
-            c = fmaxf(__fadd_rn(x[u].y, c), 0.f); bs = __fadd_rn(c, bs); x[u].y = bs;
-            c = fmaxf(__fadd_rn(x[u].z, c), 0.f); bs = __fadd_rn(c, bs); x[u].z = bs;
-            c = fmaxf(__fadd_rn(x[u].w, c), 0.f); bs = __fadd_rn(c, bs); x[u].w = bs;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; u++) *reinterpret_cast<float4*>(dl + base + u * 4) = x[u];
-        } else {
-          const uint32_t lim = min(base + 32, npos);
-          for (uint32_t i = base; i < lim; i++) {
-            if (i == to_reset) bs = 0.f;
-            c = fmaxf(__fadd_rn(dl[i], c), 0.f);
-            bs = __fadd_rn(c, bs);
-            dl[i] = bs;
+      // ordered deposit of the event list.  Events of one 32-group that share a position are chained, in lane
+      // (= reference) order, in the registers of the first of them; groups are applied one after the other.
+      for (uint32_t eb = 0; eb < nev; eb += 32) {
+        uint2 nxt = no_event;
+        if (eb + 32 + lane < nev) nxt = __ldcs(v.events + e0 + eb + 32 + lane);
+        const bool valid = eb + lane < nev;
+        const uint32_t pos = cur.x & 511u, sl = cur.x >> 9;
+        const float val = __uint_as_float(cur.y);
+        const uint32_t grp = __match_any_sync(FULL, valid ? pos : (0x8000u | (uint32_t)lane));
+        const uint32_t is0 = __ballot_sync(FULL, valid && sl == 0u), is2 = __ballot_sync(FULL, valid && sl == 2u);
+        const bool leader = valid && (__ffs(grp) - 1 == lane);
+        const int maxn = __reduce_max_sync(FULL, valid ? __popc(grp) : 0);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        if (leader) { a0 = d[pos]; a1 = d[TWS + pos]; a2 = d[2 * TWS + pos]; }
+        uint32_t rem = leader ? grp : 0u;
+        for (int r = 0; r < maxn; r++) {
+          const int src = __ffs(rem) - 1;                 // -1 for idle lanes: the shuffle wraps, value unused
+          const float vv = __shfl_sync(FULL, val, src);
+          if (rem) {
+            // cov_edge_add (rlink.cpp:133-142): the strand's own lane, and lane 1 as well when the strand is known
+            if ((is0 >> src) & 1u) a0 = __fadd_rn(a0, vv);
+            if ((is2 >> src) & 1u) a2 = __fadd_rn(a2, vv);
+            a1 = __fadd_rn(a1, vv);
+            rem &= rem - 1;
           }
         }
+        if (leader) {
+          const uint32_t bit = 1u << (pos & 31u), wq = pos >> 5;
+          if (grp & is0) { d[pos] = a0; atomicOr(masks + wq, bit); }
+          d[TWS + pos] = a1; atomicOr(masks + TNW + wq, bit);
+          if (grp & is2) { d[2 * TWS + pos] = a2; atomicOr(masks + 2 * TNW + wq, bit); }
+        }
+        __syncwarp();
+        cur = nxt;
+      }
+
+      fetch_state();
+
+      // the two recurrences (rlink.cpp:17037-17063), one strand lane per thread:
+      //   c = max(0, c + d[i]);  bs = (i % BSIZE == 0 ? 0 : bs) + c;  out[i] = bs
+      const int nwords = (int)((npos + 31) / 32);
+      uint32_t fillmask = 0;
+      if (lane < 3) {
+        float* dl = d + lane * TWS;
+        const uint32_t* ml = masks + lane * TNW;
+        float* fl = fills + lane * TNW;
+        for (int q = 0; q < nwords; q++) {
+          const uint32_t base = (uint32_t)q * 32;
+          const bool full = base + 32 <= npos;
+          const bool has_reset = to_reset >= base && to_reset < base + 32;
+          if (full && !has_reset) {
+            if (ml[q] == 0) {
+              if (__fadd_rn(bs, c) == bs) {  // nothing deposited and c too small to move bs: constant word
+                fl[q] = bs;
+                fillmask |= 1u << q;
+                continue;
+              }
+              // nothing deposited: c = max(0, c + 0) stays put (c >= 0, never -0), only the block sum runs
+              float4 y[8];
+#pragma unroll
+              for (int u = 0; u < 8; u++) {
+                bs = __fadd_rn(c, bs); y[u].x = bs;
+                bs = __fadd_rn(c, bs); y[u].y = bs;
+                bs = __fadd_rn(c, bs); y[u].z = bs;
+                bs = __fadd_rn(c, bs); y[u].w = bs;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; u++) *reinterpret_cast<float4*>(dl + base + u * 4) = y[u];
+              continue;
+            }
+            float4 x[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) x[u] = *reinterpret_cast<const float4*>(dl + base + u * 4);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              c = fmaxf(__fadd_rn(x[u].x, c), 0.f); bs = __fadd_rn(c, bs); x[u].x = bs;
+              c = fmaxf(__fadd_rn(x[u].y, c), 0.f); bs = __fadd_rn(c, bs); x[u].y = bs;
+              c = fmaxf(__fadd_rn(x[u].z, c), 0.f); bs = __fadd_rn(c, bs); x[u].z = bs;
+              c = fmaxf(__fadd_rn(x[u].w, c), 0.f); bs = __fadd_rn(c, bs); x[u].w = bs;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) *reinterpret_cast<float4*>(dl + base + u * 4) = x[u];
+          } else {
+            const uint32_t lim = min(base + 32, npos);
+            for (uint32_t i = base; i < lim; i++) {
+              if (i == to_reset) bs = 0.f;
+              c = fmaxf(__fadd_rn(dl[i], c), 0.f);
+              bs = __fadd_rn(c, bs);
+              dl[i] = bs;
+            }
+          }
+        }
+        // publish (c, bs) after the last position: one 64-bit store, data and "ready" in the same word
+        st_relaxed_u64(v.tile_carry + (size_t)tile_id * 4 + lane,
+                       ((unsigned long long)__float_as_uint(bs) << 32) | (unsigned long long)__float_as_uint(c));
+      }
+      __syncwarp();
+      write_out(fillmask);
+    }
+
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K10: event-free sub-tiles.  Runs after cov_tile_kernel, so every carry it needs is final: no waiting, no shared
+// memory, full occupancy — a streaming fill.  One warp per sub-tile.
+// --------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cov_fill_kernel(DevBatchView v) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_main = __ldg(v.round_off + v.n_rounds);
+  const uint32_t n_tiles = (uint32_t)v.n_tiles;
+  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t t = n_main + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += warps) {
+    uint32_t recw = 0;
+    if (lane < 8) recw = __ldg(reinterpret_cast<const uint32_t*>(v.tile_plan + t) + lane);
+    const uint32_t gbase = __shfl_sync(FULL, recw, 0), i0 = __shfl_sync(FULL, recw, 1);
+    const uint32_t stride = __shfl_sync(FULL, recw, 4), npos = __shfl_sync(FULL, recw, 5);
+    const uint32_t tile_id = __shfl_sync(FULL, recw, 6), wait_tile = __shfl_sync(FULL, recw, 7);
+    const uint32_t to_reset = (STG_BSIZE - i0 % STG_BSIZE) % STG_BSIZE;  // in-tile position where idx % BSIZE == 0
+    float* out = v.bpcov + 3 * (size_t)gbase + i0;
+    const uint32_t n4 = min((uint32_t)TW, stride - i0) / 4;              // float4 per lane incl. the zero padding
+    // state before the first position: from the nearest earlier sub-tile with events, advanced over the gap
+    float c = 0.f, bs = 0.f;
+    if (wait_tile != STG_NO_TILE && lane < 3) {
+      const unsigned long long x = __ldcg(v.tile_carry + (size_t)wait_tile * 4 + lane);
+      c = __uint_as_float((uint32_t)x); bs = __uint_as_float((uint32_t)(x >> 32));
+      const uint32_t first = tile_id - i0 / TW;
+      const uint32_t wlast = (wait_tile - first) * TW + TW - 1;
+      const uint32_t gap = i0 - 1 - wlast;
+      if (gap) {
+        const uint32_t rst = (i0 - 1) / STG_BSIZE * STG_BSIZE;
+        bs = rst > wlast ? advance_bs(0.f, c, i0 - rst) : advance_bs(bs, c, gap);
       }
     }
-    publish();
-
-    // constant words
+    const bool flat = lane >= 3 || (to_reset < npos ? c == 0.f : __fadd_rn(bs, c) == bs);
+    if (__all_sync(FULL, flat)) {
+      // every position repeats bs (0 from a block start on)
+      const float b0 = __shfl_sync(FULL, bs, 0), b1 = __shfl_sync(FULL, bs, 1), b2 = __shfl_sync(FULL, bs, 2);
 #pragma unroll
-    for (int s = 0; s < 3; s++) {
-      uint32_t fm = __shfl_sync(FULL, fillmask, s);
-      while (fm) {
-        const int q = __ffs(fm) - 1;
-        fm &= fm - 1;
-        d[s * TWS + q * 32 + lane] = fills[s * TNW + q];
+      for (int s = 0; s < 3; s++) {
+        const float bv = s == 0 ? b0 : (s == 1 ? b1 : b2);
+        float4* dst = reinterpret_cast<float4*>(out + (size_t)s * stride);
+        for (uint32_t q = lane; q < n4; q += 32) {
+          const uint32_t p = q * 4;
+          float4 x;
+          x.x = (p + 0 < to_reset && p + 0 < npos) ? bv : 0.f;
+          x.y = (p + 1 < to_reset && p + 1 < npos) ? bv : 0.f;
+          x.z = (p + 2 < to_reset && p + 2 < npos) ? bv : 0.f;
+          x.w = (p + 3 < to_reset && p + 3 < npos) ? bv : 0.f;
+          __stcs(dst + q, x);
+        }
+      }
+    } else {
+      // a coverage residue travels through: bs grows by the same c at every position -> closed-form runs
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        const float cs = __shfl_sync(FULL, c, s);
+        float bss = __shfl_sync(FULL, bs, s);
+        float* dl = out + (size_t)s * stride;
+        if (to_reset < npos) {
+          fill_run(dl, 0, to_reset, cs, bss, lane);
+          bss = 0.f;
+          fill_run(dl, to_reset, npos, cs, bss, lane);
+        } else {
+          fill_run(dl, 0, npos, cs, bss, lane);
+        }
+        for (uint32_t q = npos + lane; q < n4 * 4; q += 32) dl[q] = 0.f;
       }
     }
-    __syncwarp();
-
-    // finished bpcov of the sub-tile: one streaming, coalesced write per strand lane (incl. the zero padding)
-#pragma unroll
-    for (int s = 0; s < 3; s++) {
-      const float4* src = reinterpret_cast<const float4*>(d + s * TWS);
-      float4* dst = reinterpret_cast<float4*>(out + (size_t)s * stride);
-      for (uint32_t q = lane; q < n4; q += 32) __stcs(dst + q, src[q]);
-    }
-    __syncwarp();
   }
 }
 
@@ -766,6 +1087,14 @@ cudaError_t launch_cov_tiles(const DevBatchView& v, int num_sms, cudaStream_t st
   int64_t want = (v.n_tiles + STG_TILE_WARPS - 1) / STG_TILE_WARPS;
   int grid = (int)(want < num_sms ? want : num_sms);
   cov_tile_kernel<<<grid, STG_TILE_WARPS * 32, smem, st>>>(v);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cov_fill(const DevBatchView& v, int num_sms, cudaStream_t st) {
+  if (v.n_tiles == 0) return cudaSuccess;
+  int64_t want = (v.n_tiles + 7) / 8;
+  int grid = (int)(want < (int64_t)num_sms * 8 ? want : (int64_t)num_sms * 8);
+  cov_fill_kernel<<<grid, 256, 0, st>>>(v);
   return cudaGetLastError();
 }
 

@@ -300,27 +300,11 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
   }
   gbase[nb] = (uint32_t)g; tile_off[nb] = (uint32_t)t;
   v.total_pos = (int64_t)g; v.n_tiles = (int64_t)t;
-  // ticket order of the tile kernel: column-major over (bundle, sub-tile index) — bundles sorted by their number
-  // of sub-tiles (descending), col_off[j] = tickets before column j.
-  std::vector<uint32_t> order(nb), col_off;
+  // rounds of the tile schedule (tile_plan_kernel): at least the sub-tile count of the longest bundle
   {
-    uint32_t max_nt = 0;
+    uint32_t max_nt = 1;
     for (int64_t b = 0; b < nb; b++) max_nt = std::max(max_nt, tile_off[b + 1] - tile_off[b]);
-    std::vector<uint32_t> hist(max_nt + 2, 0);            // counting sort by tile count, descending, stable
-    for (int64_t b = 0; b < nb; b++) hist[tile_off[b + 1] - tile_off[b]]++;
-    std::vector<uint32_t> first(max_nt + 2, 0);
-    uint32_t acc = 0;
-    for (uint32_t nt = max_nt + 1; nt-- > 0;) { first[nt] = acc; acc += hist[nt]; }
-    for (int64_t b = 0; b < nb; b++) order[first[tile_off[b + 1] - tile_off[b]]++] = (uint32_t)b;
-    col_off.assign(max_nt + 1, 0);
-    uint32_t alive = (uint32_t)nb, run = 0;               // bundles with more than j sub-tiles
-    for (uint32_t j = 0; j < max_nt; j++) {
-      col_off[j] = run;
-      alive -= hist[j];                                   // bundles with exactly j sub-tiles are not in column j
-      run += alive;
-    }
-    col_off[max_nt] = run;
-    v.n_cols = max_nt;
+    v.n_rounds = std::max<uint32_t>(max_nt, 2048u);
   }
 
 #define UP(field, count) do { rc = dev_upload(ctx, d, &v.field, h->field, (int64_t)(count)); if (rc) { free_batch_allocs(d); delete d; return rc; } } while (0)
@@ -344,21 +328,22 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
   }
 #define UPV(field, vec) do { rc = dev_upload(ctx, d, &v.field, vec.data(), (int64_t)vec.size()); if (rc) { free_batch_allocs(d); delete d; return rc; } } while (0)
   UPV(b_len, len); UPV(b_stride, stride); UPV(b_gbase, gbase); UPV(b_tile_off, tile_off);
-  UPV(b_order, order); UPV(col_off, col_off); UPV(cta_bundle, cta_bundle);
+  UPV(cta_bundle, cta_bundle);
 #undef UPV
   // the layout vectors are pageable locals: make sure their copies have left the host before they die
   CK(ctx, cudaStreamSynchronize(ctx->stream));
 #define AL(field, count) do { rc = dev_alloc(ctx, d, &v.field, (int64_t)(count)); if (rc) { free_batch_allocs(d); delete d; return rc; } } while (0)
   AL(r_ivl_cnt, h->n_reads + 1);
-  d->scan_capacity = std::max<int64_t>(h->n_reads + 1, v.n_tiles + 1);
+  d->scan_capacity = std::max<int64_t>(std::max<int64_t>(h->n_reads + 1, v.n_tiles + 1), v.n_rounds + 1);
   AL(scan_partials, scan_partials_needed(d->scan_capacity));
-  AL(tile_carry, v.n_tiles * 8); AL(tile_flag, v.n_tiles); AL(tile_ticket, 1);
+  AL(tile_carry, v.n_tiles * 4); AL(tile_ticket, 1); AL(deep_count, 1);
+  AL(round_off, v.n_rounds + 1); AL(round_cur, v.n_rounds + 1);
   AL(tile_plan, v.n_tiles); AL(tile_evoff, v.n_tiles + 1); AL(tile_lastne, v.n_tiles); AL(junc_anchor, h->n_juncs);
   AL(bpcov, 3 * v.total_pos);
   AL(j_nreads_good, h->n_juncs); AL(j_leftsupport, h->n_juncs); AL(j_rightsupport, h->n_juncs);
   AL(b_cov_total, nb * 3);
 #undef AL
-  // the padding between a lane's length and its stride is written by the tile kernel; nothing else to clear
+  // the padding between a lane's length and its stride is written by the tile kernels; nothing else to clear
   *out = d;
   return STG_OK;
 }
@@ -385,10 +370,11 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
     CK(ctx, cudaMemsetAsync(v.j_leftsupport, 0, sizeof(double) * v.n_juncs, st));
     CK(ctx, cudaMemsetAsync(v.j_rightsupport, 0, sizeof(double) * v.n_juncs, st));
   }
-  if (v.n_tiles) CK(ctx, cudaMemsetAsync(v.tile_flag, 0, sizeof(uint32_t) * v.n_tiles, st));
+  if (v.n_tiles) CK(ctx, cudaMemsetAsync(v.tile_carry, 0xff, sizeof(unsigned long long) * 4 * (size_t)v.n_tiles, st));
   CK(ctx, cudaMemsetAsync(v.tile_ticket, 0, sizeof(uint32_t), st));
   { Scope s(ctx, "junc_anchor", 1); CK(ctx, launch_junc_anchor(v, kp, st)); }
-  { Scope s(ctx, "expand_count+junction_support", 1); CK(ctx, launch_expand_count(v, kp, st)); }
+  { Scope s(ctx, "junction_support", 1); CK(ctx, launch_junc_support(v, st)); }
+  { Scope s(ctx, "expand_count", 1); CK(ctx, launch_expand_count(v, st)); }
   { Scope s(ctx, "scan_interval_offsets", 3); CK(ctx, launch_scan_exclusive_add(v.r_ivl_cnt, v.n_reads + 1, v.scan_partials, st)); }
   // the interval count sizes the next buffers: a 4-byte read-back (one of the two host syncs inside the stage)
   uint32_t n_ivl = 0;
@@ -403,7 +389,10 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
     const int64_t cap = (int64_t)n_ivl + (int64_t)n_ivl / 16 + 1024;
     const int64_t ccap = (cap + STG_CHUNK - 1) / STG_CHUNK + 1;
     int rc;
+    const int64_t dcap = 2 * cap / STG_DEEP_EVENTS + 1;
     if ((rc = dev_alloc(ctx, d, &v.ivl, cap)) || (rc = dev_alloc(ctx, d, &v.events, 2 * cap)) ||
+        (rc = dev_alloc(ctx, d, &v.events2, 2 * cap)) || (rc = dev_alloc(ctx, d, &v.deep_list, dcap)) ||
+        (rc = dev_alloc(ctx, d, &v.deep_d, dcap * 3 * STG_TILE_W)) ||
         (rc = dev_alloc(ctx, d, &v.ch_tlo, ccap)) || (rc = dev_alloc(ctx, d, &v.ch_thi, ccap)) ||
         (rc = dev_alloc(ctx, d, &v.ch_pmax_thi, ccap)) || (rc = dev_alloc(ctx, d, &v.ch_smin_tlo, ccap)) ||
         (rc = dev_alloc(ctx, d, &v.ch_row_off, ccap + 1)))
@@ -435,8 +424,10 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   { Scope s(ctx, "bin_count", 1); CK(ctx, launch_bin_count(v, st)); }
   { Scope s(ctx, "bin_columns+scans", 7); CK(ctx, launch_bin_columns(v, st)); }
   { Scope s(ctx, "bin_scatter", 1); CK(ctx, launch_bin_scatter(v, st)); }
-  { Scope s(ctx, "tile_plan", 1); CK(ctx, launch_tile_plan(v, st)); }
+  { Scope s(ctx, "tile_plan", 8); CK(ctx, launch_tile_plan(v, st)); }
+  { Scope s(ctx, "deep_deposit", 1); CK(ctx, launch_deep_deposit(v, ctx->num_sms, st)); }
   { Scope s(ctx, "cov_tile", 1); CK(ctx, launch_cov_tiles(v, ctx->num_sms, st)); }
+  { Scope s(ctx, "cov_fill", 1); CK(ctx, launch_cov_fill(v, ctx->num_sms, st)); }
   { Scope s(ctx, "cov_totals", 1); CK(ctx, launch_cov_totals(v, st)); }
   d->ran = true;
   return STG_OK;

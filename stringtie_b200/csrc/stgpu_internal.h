@@ -8,11 +8,12 @@
 
 #define STG_TILE_W 512           // positions per sub-tile (one warp owns one sub-tile of all three strand lanes)
 #define STG_TILE_SHIFT 9
-#define STG_TILE_WARPS 24        // warps per CTA of the tile kernel (one CTA per SM; ~6.6 KB shared memory per warp)
+#define STG_TILE_WARPS 32        // warps per CTA of the tile kernel (one CTA per SM; ~6.6 KB shared memory per warp)
 #define STG_LANE_ALIGN 32        // every strand lane of every bundle starts on a 128-byte boundary
 #define STG_CHUNK 512            // coverage intervals per binning chunk (one warp walks one chunk in order)
 #define STG_READ_BLOCK 256       // reads per CTA of the per-read kernels (cta_bundle is sampled at this step)
 #define STG_NO_TILE 0xffffffffu
+#define STG_DEEP_EVENTS 2048u     // sub-tiles with at least this many events take the sort-by-position path
 
 // Everything a warp needs to process one sub-tile, prepared by tile_plan_kernel (one 32-byte load).
 struct __align__(32) TileRec {
@@ -49,11 +50,8 @@ struct DevBatchView {
   const uint32_t* b_stride;    // [n_bundles]   len rounded up to STG_LANE_ALIGN
   const uint32_t* b_gbase;     // [n_bundles+1] prefix sum of b_stride: "global position" of index 0 of bundle b
   const uint32_t* b_tile_off;  // [n_bundles+1] prefix sum of ceil(len/STG_TILE_W): bundle-major tile ids
-  const uint32_t* b_order;     // [n_bundles]   bundles sorted by tile count, descending
-  const uint32_t* col_off;     // [n_cols+1]    col_off[j] = number of tiles with in-bundle index < j; tickets are
-                               //               handed out column-major: all first sub-tiles, all second ones, ...
   const uint32_t* cta_bundle;  // [ceil(n_reads/STG_READ_BLOCK)] bundle of read STG_READ_BLOCK*i
-  int64_t n_cols;
+  int64_t n_rounds;            // rounds of the tile schedule: max(sub-tiles of the longest bundle, 2048)
   int64_t n_tiles;
   int64_t total_pos;           // b_gbase[n_bundles]
   // scratch
@@ -73,11 +71,18 @@ struct DevBatchView {
   uint32_t* tile_evoff;        // [n_tiles+1] event count per tile, then exclusive prefix (in place)
   uint32_t* tile_lastne;       // [n_tiles]   (t+1 if tile t has events else 0), then inclusive prefix max
   uint2* events;               // [2*n_ivl]   {pos | lane << 9, signed weight bits}, tile-major, reference order
+  uint2* events2;              // [2*n_ivl]   deep sub-tiles only: {lane, signed weight bits} sorted by position (stable)
+  uint4* deep_list;            // [deep_cap]  {tile id, first event, events, -} of every deep sub-tile
+  float* deep_d;               // [deep_cap * 3 * STG_TILE_W] their finished difference arrays
+  uint32_t* deep_count;        // [1]
   uint32_t* scan_partials;     // scratch for the 3-phase scans
   uint8_t* junc_anchor;        // [n_juncs] anchor length each junction demands (10 or 25, rlink.cpp:16991-16997)
-  TileRec* tile_plan;          // [n_tiles] indexed by ticket
-  float* tile_carry;           // [n_tiles*8] c[3], bsum[3] after the last position of the sub-tile
-  uint32_t* tile_flag;         // [n_tiles]   1 when tile_carry[tile] is published (bundle-major tile id)
+  uint32_t* round_off;         // [n_rounds+1] tiles with events per round, then exclusive prefix: first ticket of the
+                               //              round; round_off[n_rounds] = n_main, the number of tiles with events
+  uint32_t* round_cur;         // [n_rounds+1] tickets handed out inside the round; [n_rounds]: event-free tiles placed
+  TileRec* tile_plan;          // [n_tiles] [0, n_main): tiles with events in ticket order; [n_main, n_tiles): the rest
+  unsigned long long* tile_carry;  // [n_tiles*4] per strand lane (c | bs << 32) after the last position of a
+                               //             sub-tile with events; all-ones until published (bundle-major tile id)
   uint32_t* tile_ticket;       // [1]
   // outputs
   float* bpcov;                // [3*total_pos]: bundle b lane s index i at 3*b_gbase[b] + s*b_stride[b] + i
@@ -92,7 +97,8 @@ struct KernelParams {
 };
 
 // kernel launchers (cov_kernels.cu). Each enqueues on `st` and returns the CUDA error of the launch.
-cudaError_t launch_expand_count(const DevBatchView& v, const KernelParams& p, cudaStream_t st);
+cudaError_t launch_expand_count(const DevBatchView& v, cudaStream_t st);
+cudaError_t launch_junc_support(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_scan_exclusive_add(uint32_t* data, int64_t n_plus_1, uint32_t* partials, cudaStream_t st);
 cudaError_t launch_expand_write(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_chunk_hull(const DevBatchView& v, cudaStream_t st);      // + the three chunk-level scans
@@ -101,7 +107,9 @@ cudaError_t launch_bin_columns(const DevBatchView& v, cudaStream_t st);     // +
 cudaError_t launch_bin_scatter(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_junc_anchor(const DevBatchView& v, const KernelParams& p, cudaStream_t st);
 cudaError_t launch_tile_plan(const DevBatchView& v, cudaStream_t st);
+cudaError_t launch_deep_deposit(const DevBatchView& v, int num_sms, cudaStream_t st);
 cudaError_t launch_cov_tiles(const DevBatchView& v, int num_sms, cudaStream_t st);
+cudaError_t launch_cov_fill(const DevBatchView& v, int num_sms, cudaStream_t st);
 cudaError_t launch_cov_totals(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_query_cov(const DevBatchView& v, int64_t n, const int32_t* bundle, const int8_t* lane,
                              const uint32_t* start, const uint32_t* end, int sign, double* out, cudaStream_t st);
