@@ -142,8 +142,9 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) expand_count_kernel(DevBatchVi
 // K1b: junction support (rlink.cpp:16890-17016): for intron i of a read, left anchor = longest exon at or before
 // it, right anchor = longest exon after it; the junction row gets leftsupport / rightsupport / nreads_good += w.
 // The sums are float weights accumulated in f64: every partial sum is exactly representable, so the order of the
-// additions is free.  One thread per read; the 32 reads of a warp usually cross the same few junctions, so each
-// round the warp groups its updates by junction row (match) and issues ONE f64 atomic per row and counter.
+// additions is free.  One thread per read; the 32 reads of a warp usually cross the same few junctions with the
+// same few weights, so each round the warp groups its updates by (junction row, weight) with one 64-bit match and
+// issues ONE f64 atomic of count * w per group and counter (the product is exact: count <= 32, w has 24 bits).
 // --------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(STG_READ_BLOCK) junc_support_kernel(DevBatchView v) {
   const int64_t n64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,33 +185,19 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) junc_support_kernel(DevBatchVi
         if (fl || fr) key = j;
       }
     }
-    const uint32_t grp = __match_any_sync(FULL, key);
+    // updates with the same row AND the same weight: their sum is (count * w), exact in f64
+    const uint32_t grp = __match_any_sync(FULL, ((unsigned long long)key << 32) | (unsigned long long)__float_as_uint(w));
     const uint32_t bl = __ballot_sync(FULL, fl), br = __ballot_sync(FULL, fr);
-    const bool leader = (fl || fr) && (__ffs(grp) - 1 == lane);
-    const int maxn = __reduce_max_sync(FULL, (fl || fr) ? __popc(grp) : 0);
-    double dl = 0.0, dr = 0.0, dg = 0.0;
-    uint32_t rem = leader ? grp : 0u;
-    for (int r = 0; r < maxn; r++) {
-      const int src = __ffs(rem) - 1;                      // -1 for idle lanes: the shuffle wraps, value unused
-      const double wv = (double)__shfl_sync(FULL, w, src);
-      if (rem) {
-        const bool ml = (bl >> src) & 1u, mr = (br >> src) & 1u;
-        if (ml) dl += wv;
-        if (mr) dr += wv;
-        if (ml && mr) dg += wv;
-        rem &= rem - 1;
-      }
-    }
-    if (leader) {
-      if (grp & bl) atomicAdd(v.j_leftsupport + key, dl);
-      if (grp & br) atomicAdd(v.j_rightsupport + key, dr);
-      if (grp & bl & br) atomicAdd(v.j_nreads_good + key, dg);
+    if ((fl || fr) && (__ffs(grp) - 1 == lane)) {
+      const double wd = (double)w;
+      const int nl = __popc(grp & bl), nr = __popc(grp & br), ng = __popc(grp & bl & br);
+      if (nl) atomicAdd(v.j_leftsupport + key, (double)nl * wd);
+      if (nr) atomicAdd(v.j_rightsupport + key, (double)nr * wd);
+      if (ng) atomicAdd(v.j_nreads_good + key, (double)ng * wd);
     }
   }
 }
 
-// --------------------------------------------------------------------------------------------------------------
-// K3: write intervals
 // --------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(STG_READ_BLOCK) expand_write_kernel(DevBatchView v) {
   const int64_t n64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -491,13 +478,25 @@ __global__ void __launch_bounds__(256) bin_columns_kernel(DevBatchView v) {
     const uint32_t nc = (uint32_t)v.n_chunks;
     const uint32_t c0 = lower_bound_u32(v.ch_pmax_thi, 0, nc, t);       // first chunk reaching up to t
     const uint32_t c1 = lower_bound_u32(v.ch_smin_tlo, 0, nc, t + 1);   // from here on every chunk starts past t
-    for (uint32_t c = c0; c < c1; c++) {
-      const uint32_t lo = __ldg(v.ch_tlo + c);
-      if (t < lo || t > __ldg(v.ch_thi + c)) continue;
-      uint32_t* cell = v.cells + __ldg(v.ch_row_off + c) + (t - lo);
-      const uint32_t x = *cell;
-      *cell = run;
-      run += x;
+    // the loads of a batch of chunks are independent of the running prefix: issue them together
+    for (uint32_t cb = c0; cb < c1; cb += 8) {
+      uint32_t* cell[8];
+      uint32_t x[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const uint32_t c = cb + u;
+        cell[u] = nullptr;
+        if (c < c1) {
+          const uint32_t lo = __ldg(v.ch_tlo + c);
+          if (t >= lo && t <= __ldg(v.ch_thi + c)) cell[u] = v.cells + __ldg(v.ch_row_off + c) + (t - lo);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) x[u] = cell[u] ? *cell[u] : 0u;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        if (cell[u]) { *cell[u] = run; run += x[u]; }
+      }
     }
   }
   v.tile_evoff[t] = run;
@@ -614,8 +613,13 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32) deep_deposit_kernel(DevBatchV
   __shared__ uint32_t wtot[DEEP_WARPS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
+  __shared__ uint32_t next_tile;
   const uint32_t ndeep = *v.deep_count;
-  for (uint32_t di = blockIdx.x; di < ndeep; di += gridDim.x) {
+  for (;;) {
+    if (threadIdx.x == 0) next_tile = atomicAdd(v.tile_ticket + 1, 1u);
+    __syncthreads();
+    const uint32_t di = next_tile;
+    if (di >= ndeep) break;
     const uint4 rec = v.deep_list[di];
     const uint32_t e0 = rec.y, nev = rec.z;
     const uint2* __restrict__ ev = v.events + e0;
@@ -685,12 +689,17 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32) deep_deposit_kernel(DevBatchV
       const bool is_long = n > 64u;
       if (!is_long) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        for (uint32_t i = 0; i < n; i++) {
-          const uint2 x = sorted[l0 + i];
-          const float val = __uint_as_float(x.y);
-          if (x.x == 0u) a0 = __fadd_rn(a0, val);
-          if (x.x == 2u) a2 = __fadd_rn(a2, val);
-          a1 = __fadd_rn(a1, val);
+        for (uint32_t i = 0; i < n; i += 8) {   // 8 loads in flight, then the chain
+          uint2 x[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) x[u] = i + u < n ? sorted[l0 + i + u] : make_uint2(1u, 0u);  // pad: +0.0, a no-op
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const float val = __uint_as_float(x[u].y);
+            if (x[u].x == 0u) a0 = __fadd_rn(a0, val);
+            if (x[u].x == 2u) a2 = __fadd_rn(a2, val);
+            a1 = __fadd_rn(a1, val);
+          }
         }
         dd[p] = a0; dd[STG_TILE_W + p] = a1; dd[2 * STG_TILE_W + p] = a2;
       }

@@ -336,7 +336,7 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
   AL(r_ivl_cnt, h->n_reads + 1);
   d->scan_capacity = std::max<int64_t>(std::max<int64_t>(h->n_reads + 1, v.n_tiles + 1), v.n_rounds + 1);
   AL(scan_partials, scan_partials_needed(d->scan_capacity));
-  AL(tile_carry, v.n_tiles * 4); AL(tile_ticket, 1); AL(deep_count, 1);
+  AL(tile_carry, v.n_tiles * 4); AL(tile_ticket, 2); AL(deep_count, 1);
   AL(round_off, v.n_rounds + 1); AL(round_cur, v.n_rounds + 1);
   AL(tile_plan, v.n_tiles); AL(tile_evoff, v.n_tiles + 1); AL(tile_lastne, v.n_tiles); AL(junc_anchor, h->n_juncs);
   AL(bpcov, 3 * v.total_pos);
@@ -371,7 +371,7 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
     CK(ctx, cudaMemsetAsync(v.j_rightsupport, 0, sizeof(double) * v.n_juncs, st));
   }
   if (v.n_tiles) CK(ctx, cudaMemsetAsync(v.tile_carry, 0xff, sizeof(unsigned long long) * 4 * (size_t)v.n_tiles, st));
-  CK(ctx, cudaMemsetAsync(v.tile_ticket, 0, sizeof(uint32_t), st));
+  CK(ctx, cudaMemsetAsync(v.tile_ticket, 0, 2 * sizeof(uint32_t), st));
   { Scope s(ctx, "junc_anchor", 1); CK(ctx, launch_junc_anchor(v, kp, st)); }
   { Scope s(ctx, "junction_support", 1); CK(ctx, launch_junc_support(v, st)); }
   { Scope s(ctx, "expand_count", 1); CK(ctx, launch_expand_count(v, st)); }

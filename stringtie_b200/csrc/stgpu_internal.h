@@ -83,7 +83,7 @@ struct DevBatchView {
   TileRec* tile_plan;          // [n_tiles] [0, n_main): tiles with events in ticket order; [n_main, n_tiles): the rest
   unsigned long long* tile_carry;  // [n_tiles*4] per strand lane (c | bs << 32) after the last position of a
                                //             sub-tile with events; all-ones until published (bundle-major tile id)
-  uint32_t* tile_ticket;       // [1]
+  uint32_t* tile_ticket;       // [2] work counters: [0] cov_tile_kernel, [1] deep_deposit_kernel
   // outputs
   float* bpcov;                // [3*total_pos]: bundle b lane s index i at 3*b_gbase[b] + s*b_stride[b] + i
   double *j_nreads_good, *j_leftsupport, *j_rightsupport;  // [n_juncs]
