@@ -159,7 +159,8 @@ int stg_builder_destroy(stg_builder* b);
 int stg_upload(stg_ctx* ctx, const stg_packed_batch* host, stg_dbatch** out);
 int stg_run(stg_ctx* ctx, stg_dbatch* batch);
 int stg_sync(stg_ctx* ctx);
-int stg_free_batch(stg_ctx* ctx, stg_dbatch* batch);
+int stg_free_batch(stg_ctx* ctx, stg_dbatch* batch);   /* device blocks go back to the context's pool for reuse */
+int stg_trim(stg_ctx* ctx);                            /* release the pooled device memory (cudaFree) */
 
 /* Outputs of the coverage / junction-support stage (count_good_junctions, rlink.cpp:16656-17136).
  * bpcov layout in HBM: for bundle b, lane s in {0:-, 1:all, 2:+}, index i in [0, len_b) with
@@ -188,6 +189,13 @@ typedef struct stg_bundle_result {
   double* j_rightsupport;
 } stg_bundle_result;
 int stg_infer_transcripts(stg_ctx* ctx, const stg_bundle_view* view, stg_bundle_result* result);
+
+/* ---- multi-GPU: bundles shard by genomic locus, one rank per GPU ---------------------------------
+ * Greedy least-loaded assignment on cost = reads + span/64, heaviest bundles first (the reference has one queue
+ * feeding N threads, stringtie.cpp:484-492; here the producer decides the GPU up front).  Host-only, no device
+ * needed.  rank_of[b] in [0, world).  Deterministic: ties go to the lowest rank.                              */
+int stg_shard_assign(int64_t n_bundles, const uint32_t* b_read_off /*[n+1]*/, const int32_t* b_start,
+                     const int32_t* b_end, int world, int32_t* rank_of /*[n]*/, double* rank_cost /*[world] or NULL*/);
 
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------------
  * With profiling on, stg_run brackets every kernel with CUDA events on the context stream.            */

@@ -15,6 +15,11 @@ struct Timed { const char* name; cudaEvent_t e0, e1; };
 
 }  // namespace
 
+// Device memory is recycled through the context: a host that streams batch after batch (the reference's bundle
+// queue does exactly that) must not pay cudaMalloc/cudaFree — tens of milliseconds for the ~25 GB of a C2 batch —
+// on every one.  Blocks are handed back on stg_free_batch and reused best-fit; stg_shutdown / stg_trim release them.
+struct PoolBlock { void* p; size_t bytes; };
+
 struct stg_ctx {
   int device = 0;
   int num_sms = 0;
@@ -27,6 +32,8 @@ struct stg_ctx {
   size_t event_used = 0;
   int64_t launches = 0;
   std::mutex mu;
+  std::vector<PoolBlock> pool_free;
+  size_t pool_bytes = 0;          // bytes currently parked in pool_free
 };
 
 struct stg_builder {
@@ -48,7 +55,7 @@ struct stg_builder {
 
 struct stg_dbatch {
   DevBatchView v;
-  std::vector<void*> allocs;       // everything cudaMalloc'ed for this batch
+  std::vector<PoolBlock> allocs;   // every device block this batch holds (returned to the context pool on free)
   std::vector<int64_t> h_cov_off;  // [n_bundles] float offset of lane 0 of bundle b (= 3*gbase)
   std::vector<int64_t> h_stride;   // [n_bundles]
   std::vector<uint32_t> h_len;
@@ -74,13 +81,44 @@ int fail(stg_ctx* ctx, int code, const std::string& msg) {
       return fail(ctx, STG_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));            \
   } while (0)
 
+void* pool_take(stg_ctx* ctx, size_t bytes, size_t* got) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  int best = -1;
+  for (int i = 0; i < (int)ctx->pool_free.size(); i++) {
+    const size_t b = ctx->pool_free[i].bytes;
+    if (b >= bytes && b <= bytes + bytes / 4 + (1u << 20) && (best < 0 || b < ctx->pool_free[best].bytes)) best = i;
+  }
+  if (best < 0) return nullptr;
+  void* p = ctx->pool_free[best].p;
+  *got = ctx->pool_free[best].bytes;
+  ctx->pool_bytes -= *got;
+  ctx->pool_free.erase(ctx->pool_free.begin() + best);
+  return p;
+}
+
+void pool_release_all(stg_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  for (auto& b : ctx->pool_free) cudaFree(b.p);
+  ctx->pool_free.clear();
+  ctx->pool_bytes = 0;
+}
+
 template <class T>
 int dev_alloc(stg_ctx* ctx, stg_dbatch* d, T** out, int64_t count) {
-  void* p = nullptr;
-  size_t bytes = (size_t)std::max<int64_t>(count, 1) * sizeof(T);
-  cudaError_t e = cudaMalloc(&p, bytes);
-  if (e != cudaSuccess) return fail(ctx, STG_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-  d->allocs.push_back(p);
+  size_t bytes = ((size_t)std::max<int64_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
+  size_t got = 0;
+  void* p = pool_take(ctx, bytes, &got);
+  if (!p) {
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {   // make room: drop everything parked in the pool and retry once
+      cudaGetLastError();
+      pool_release_all(ctx);
+      e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) return fail(ctx, STG_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    got = bytes;
+  }
+  d->allocs.push_back(PoolBlock{p, got});
   *out = (T*)p;
   return STG_OK;
 }
@@ -95,8 +133,16 @@ int dev_upload(stg_ctx* ctx, stg_dbatch* d, const T** out, const T* host, int64_
   return STG_OK;
 }
 
-void free_batch_allocs(stg_dbatch* d) {
-  for (void* p : d->allocs) cudaFree(p);
+void free_batch_allocs(stg_ctx* ctx, stg_dbatch* d) {
+  if (ctx) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (auto& b : d->allocs) {
+      if (ctx->pool_bytes + b.bytes > ((size_t)96 << 30)) { cudaFree(b.p); continue; }   // keep the pool bounded
+      ctx->pool_free.push_back(b); ctx->pool_bytes += b.bytes;
+    }
+  } else {
+    for (auto& b : d->allocs) cudaFree(b.p);
+  }
   d->allocs.clear();
 }
 
@@ -195,6 +241,7 @@ int stg_shutdown(stg_ctx* ctx) {
   if (!ctx) return STG_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  pool_release_all(ctx);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -202,6 +249,14 @@ int stg_shutdown(stg_ctx* ctx) {
 }
 
 void* stg_stream(stg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int stg_trim(stg_ctx* ctx) {
+  if (!ctx) return fail(nullptr, STG_EINVAL, "stg_trim: null ctx");
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  pool_release_all(ctx);
+  return STG_OK;
+}
 
 // ---- bundle batcher -----------------------------------------------------------------------------------------
 int stg_builder_create(stg_ctx* ctx, stg_builder** out) {
@@ -307,7 +362,7 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
     v.n_rounds = std::max<uint32_t>(max_nt, 2048u);
   }
 
-#define UP(field, count) do { rc = dev_upload(ctx, d, &v.field, h->field, (int64_t)(count)); if (rc) { free_batch_allocs(d); delete d; return rc; } } while (0)
+#define UP(field, count) do { rc = dev_upload(ctx, d, &v.field, h->field, (int64_t)(count)); if (rc) { free_batch_allocs(ctx, d); delete d; return rc; } } while (0)
   UP(b_start, nb); UP(b_end, nb); UP(b_read_off, nb + 1); UP(b_junc_off, nb + 1);
   UP(r_start, h->n_reads); UP(r_end, h->n_reads); UP(r_len, h->n_reads); UP(r_count, h->n_reads); UP(r_nh, h->n_reads);
   UP(r_strand, h->n_reads); UP(r_flags, h->n_reads); UP(r_seg_off, h->n_reads + 1); UP(r_pair_off, h->n_reads + 1);
@@ -326,13 +381,13 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
       cta_bundle[i] = (uint32_t)b;
     }
   }
-#define UPV(field, vec) do { rc = dev_upload(ctx, d, &v.field, vec.data(), (int64_t)vec.size()); if (rc) { free_batch_allocs(d); delete d; return rc; } } while (0)
+#define UPV(field, vec) do { rc = dev_upload(ctx, d, &v.field, vec.data(), (int64_t)vec.size()); if (rc) { free_batch_allocs(ctx, d); delete d; return rc; } } while (0)
   UPV(b_len, len); UPV(b_stride, stride); UPV(b_gbase, gbase); UPV(b_tile_off, tile_off);
   UPV(cta_bundle, cta_bundle);
 #undef UPV
   // the layout vectors are pageable locals: make sure their copies have left the host before they die
   CK(ctx, cudaStreamSynchronize(ctx->stream));
-#define AL(field, count) do { rc = dev_alloc(ctx, d, &v.field, (int64_t)(count)); if (rc) { free_batch_allocs(d); delete d; return rc; } } while (0)
+#define AL(field, count) do { rc = dev_alloc(ctx, d, &v.field, (int64_t)(count)); if (rc) { free_batch_allocs(ctx, d); delete d; return rc; } } while (0)
   AL(r_ivl_cnt, h->n_reads + 1);
   d->scan_capacity = std::max<int64_t>(std::max<int64_t>(h->n_reads + 1, v.n_tiles + 1), v.n_rounds + 1);
   AL(scan_partials, scan_partials_needed(d->scan_capacity));
@@ -351,7 +406,7 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
 int stg_free_batch(stg_ctx* ctx, stg_dbatch* d) {
   if (!d) return STG_OK;
   if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-  free_batch_allocs(d);
+  free_batch_allocs(ctx, d);
   delete d;
   return STG_OK;
 }
@@ -540,6 +595,29 @@ int stg_infer_transcripts(stg_ctx* ctx, const stg_bundle_view* view, stg_bundle_
   stg_free_batch(ctx, d);
   stg_builder_destroy(b);
   return rc;
+}
+
+// ---- multi-GPU sharding (host only) -----------------------------------------------------------------------------
+int stg_shard_assign(int64_t nb, const uint32_t* b_read_off, const int32_t* b_start, const int32_t* b_end, int world,
+                     int32_t* rank_of, double* rank_cost) {
+  if (nb < 0 || world < 1 || (nb && (!b_read_off || !b_start || !b_end || !rank_of)))
+    return fail(nullptr, STG_EINVAL, "stg_shard_assign: bad argument");
+  std::vector<double> cost((size_t)nb);
+  std::vector<int64_t> order((size_t)nb);
+  for (int64_t b = 0; b < nb; b++) {
+    cost[b] = (double)(b_read_off[b + 1] - b_read_off[b]) + (double)((int64_t)b_end[b] - (int64_t)b_start[b] + 3) / 64.0;
+    order[b] = b;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return cost[x] > cost[y]; });
+  std::vector<double> load((size_t)world, 0.0);
+  for (int64_t i = 0; i < nb; i++) {
+    int best = 0;
+    for (int r = 1; r < world; r++) if (load[r] < load[best]) best = r;
+    rank_of[order[i]] = best;
+    load[best] += cost[order[i]];
+  }
+  if (rank_cost) for (int r = 0; r < world; r++) rank_cost[r] = load[r];
+  return STG_OK;
 }
 
 // ---- measurement hooks ------------------------------------------------------------------------------------------

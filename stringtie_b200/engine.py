@@ -21,9 +21,9 @@ LIB_PATH = os.path.join(_HERE, "libstgpu.so")
 EXPORTS = [
     "stg_params_default", "stg_init", "stg_shutdown", "stg_last_error", "stg_abi_version", "stg_builder_create",
     "stg_builder_add", "stg_builder_packed", "stg_builder_reset", "stg_builder_destroy", "stg_upload", "stg_run",
-    "stg_sync", "stg_free_batch", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
+    "stg_sync", "stg_free_batch", "stg_trim", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
     "stg_fetch_junction_support", "stg_fetch_cov_totals", "stg_query_cov", "stg_infer_transcripts",
-    "stg_set_profiling", "stg_kernel_count", "stg_kernel_time", "stg_launch_counter", "stg_batch_stats", "stg_stream",
+    "stg_shard_assign", "stg_set_profiling", "stg_kernel_count", "stg_kernel_time", "stg_launch_counter", "stg_batch_stats", "stg_stream",
 ]
 
 
@@ -59,6 +59,7 @@ def load_library() -> C.CDLL:
     L.stg_run.argtypes = [vp, vp]
     L.stg_sync.argtypes = [vp]
     L.stg_free_batch.argtypes = [vp, vp]
+    L.stg_trim.argtypes = [vp]
     L.stg_cov_layout.argtypes = [vp, c_i64p, c_i64p, c_i64p]
     L.stg_fetch_bpcov.argtypes = [vp, vp, C.c_int64, c_f32p]
     L.stg_fetch_bpcov_all.argtypes = [vp, vp, c_f32p]
@@ -69,6 +70,8 @@ def load_library() -> C.CDLL:
     L.stg_query_cov.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int8), C.POINTER(C.c_uint32),
                                 C.POINTER(C.c_uint32), C.c_int, c_f64p]
     L.stg_infer_transcripts.argtypes = [vp, C.POINTER(StgBundleView), C.POINTER(StgBundleResult)]
+    L.stg_shard_assign.argtypes = [C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
+                                   C.POINTER(C.c_int32), c_f64p]
     L.stg_set_profiling.argtypes = [vp, C.c_int]
     L.stg_kernel_count.argtypes = [vp]
     L.stg_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
@@ -126,6 +129,10 @@ class Engine:
     def _ck(self, rc: int):
         if rc != 0:
             raise StgError(f"libstgpu error {rc}: {self.L.stg_last_error(self.ctx).decode()}")
+
+    def trim(self):
+        """Give the pooled device memory back to the driver (stg_trim)."""
+        self._ck(self.L.stg_trim(self.ctx))
 
     def close(self):
         if self.ctx:
