@@ -267,7 +267,9 @@ def main():
             wall = float(t.item())
         e2e = {"value": world * n_reads / wall, "unit": "reads/s", "h2d_bytes_per_step": in_bytes,
                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * wall, "steps": n_e2e,
-               "timing": "host wall clock around upload+run+fetch+free (includes cudaMalloc/cudaFree), max over ranks"}
+               "timing": "host wall clock around stg_upload (H2D of every input array from pinned memory) + stg_run + fetch of "
+                         "junction support and coverage totals + stg_free_batch (device blocks recycled by the context pool), "
+                         "max over ranks"}
 
     if rank != 0:
         if dist is not None:
@@ -282,11 +284,18 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     t_tile = sum(kmean.get(k, 0.0) for k in ("deep_deposit", "cov_tile", "cov_fill")) or float("nan")
     alg_tile = 24.0 * L + 13.0 * S          # bytes the dominant kernel's work amounts to
+    traffic = None
+    try:  # DRAM bytes of the same kernels from the committed ncu --set full capture (only valid for the default workload)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if args.replicas == REPLICAS and args.base_bundles == BASE_BUNDLES:
+            traffic = float(tj["traffic_bytes_per_pass"])
+    except Exception:
+        pass
     alg_stage = alg_tile + 8.0 * J
     t_stage = sum(kmean.values())
     roofline = {"bound": "hbm", "kernel": "deep_deposit + cov_tile + cov_fill (ordered deposit, recurrences and the bpcov write)", "achieved": alg_tile / (t_tile * 1e-3) / 1e9, "peak": peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 (B200_PROFILING.md)",
-                "unit": "GB/s", "frac": alg_tile / (t_tile * 1e-3) / 1e9 / peak, "traffic": None,
+                "unit": "GB/s", "frac": alg_tile / (t_tile * 1e-3) / 1e9 / peak, "traffic": traffic,
                 "algorithmic_bytes": alg_tile, "formula": "24*L + 13*S (SURVEY.md §8d; the 8*J term belongs to expand_count)",
                 "L": L, "S": S, "J": J, "kernel_ms": t_tile,
                 "stage": {"achieved": alg_stage / (t_stage * 1e-3) / 1e9, "frac": alg_stage / (t_stage * 1e-3) / 1e9 / peak,
