@@ -35,6 +35,16 @@ void orc_batch_run(const stg_packed_batch* B, const orc_params* P, const int64_t
 double orc_get_cov(const float* cov, int64_t len, int s, uint32_t start, uint32_t end);
 double orc_get_cov_sign(const float* cov, int64_t len, int s, uint32_t start, uint32_t end);
 
+/* SURVEY.md §8 row a7 — the junction pass that opens build_graphs (rlink.cpp:14385-14809) plus good_junc
+ * (rlink.cpp:13967) on every stranded junction, for one bundle (oracle/stg_oracle_junc.c).
+ * cov: the bundle's finished bpcov [3*len]; good/left/right_in: junction counters after the coverage stage (this
+ * bundle's rows).  Outputs, one per junction row of the bundle: CJunction fields after the pass; o_ej[k] = row of
+ * ejunction[k]; o_good = good_junc verdict on a copy (-1 where strand == 0), o_good_strand = the copy's strand. */
+void orc_junction_pass(const stg_packed_batch* B, const orc_params* P, int64_t b, const float* cov,
+                       const double* good_in, const double* left_in, const double* right_in, int8_t* o_strand,
+                       double* o_nreads, double* o_nreads_good, double* o_left, double* o_right, double* o_mm,
+                       int32_t* o_ej, int8_t* o_good, int8_t* o_good_strand);
+
 /* work counters for the roofline: S = mate-merged coverage intervals emitted, J = junction-support updates */
 void orc_batch_stats(const stg_packed_batch* B, int64_t* L, int64_t* S, int64_t* J);
 

@@ -13,7 +13,7 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run on the GPU box with -m gpu)")
 
 
-GOLDEN = ["short_s11", "short_s12_deep"]
+GOLDEN = ["short_s11", "short_s12_deep", "short_s13_jitter"]
 
 
 def load_golden(name):

@@ -2,7 +2,8 @@
 """Regenerates the committed golden fixtures from the REFERENCE ITSELF (needs /root/reference; run here, not on the
 GPU box):  tools/gen_sam.py (seeded) -> oracle/_ref/ref_tool (unmodified reference main + dump hook, -p 1)
 -> tests/golden/<name>.npz holding the packed-batch inputs that crossed infer_transcripts() and the reference's
-stage outputs (bpcov + junction support after count_good_junctions, predictions at return).
+stage outputs (bpcov + junction support after count_good_junctions, the junction table at the end of the junction
+pass inside build_graphs with good_junc verdicts [a7_*], predictions at return).
 
   make -C oracle ref && python tests/golden/make_golden.py
 """
@@ -22,6 +23,9 @@ CASES = {
     "short_s11": (["--loci", "24", "--pairs", "2500", "--seed", "11", "--long-intron-frac", "0.01"], []),
     "short_s12_deep": (["--loci", "6", "--pairs", "6000", "--seed", "12", "--long-intron-frac", "0.0",
                         "--nh-frac", "0.2"], []),
+    # splice-site jitter + NM tags: junctions supported only by mismatchy reads -> the higherr / demotion pass
+    "short_s13_jitter": (["--loci", "16", "--pairs", "4000", "--seed", "13", "--long-intron-frac", "0.02",
+                          "--nh-frac", "0.1", "--jitter-frac", "0.06"], []),
 }
 
 

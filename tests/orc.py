@@ -80,3 +80,43 @@ def stats(arrays):
     L.orc_batch_stats(C.byref(pb), C.cast(C.byref(a, 0), c_i64p), C.cast(C.byref(a, 8), c_i64p),
                       C.cast(C.byref(a, 16), c_i64p))
     return int(a[0]), int(a[1]), int(a[2])
+
+
+def junction_pass(arrays: Dict[str, np.ndarray], cov: np.ndarray, cov_off: np.ndarray, good: np.ndarray,
+                  left: np.ndarray, right: np.ndarray, junctionsupport: int = 10, junctionthr: int = 1):
+    """SURVEY §8 row a7 on every bundle (oracle/stg_oracle_junc.c).  Returns a dict of per-junction-row arrays:
+    strand, nreads, nreads_good, leftsupport, rightsupport, mm, ej (bundle-local row of ejunction[k]), good,
+    good_strand."""
+    L = lib()
+    if not hasattr(L, "_jp_ready"):
+        i8p, i32p = C.POINTER(C.c_int8), C.POINTER(C.c_int32)
+        L.orc_junction_pass.argtypes = [C.POINTER(StgPackedBatch), C.POINTER(OrcParams), C.c_int64, c_f32p, c_f64p,
+                                        c_f64p, c_f64p, i8p, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, i32p, i8p, i8p]
+        L.orc_junction_pass.restype = None
+        L._jp_ready = True
+    pb, keep = make_packed(arrays)
+    nj = int(pb.n_juncs)
+    out = {"strand": np.zeros(nj, np.int8), "nreads": np.zeros(nj), "nreads_good": np.zeros(nj),
+           "leftsupport": np.zeros(nj), "rightsupport": np.zeros(nj), "mm": np.zeros(nj),
+           "ej": np.zeros(nj, np.int32), "good": np.zeros(nj, np.int8), "good_strand": np.zeros(nj, np.int8)}
+    P = OrcParams(junctionsupport, junctionthr, 0)
+    joff = arrays["b_junc_off"].astype(np.int64)
+    good = np.ascontiguousarray(good, dtype=np.float64)
+    left = np.ascontiguousarray(left, dtype=np.float64)
+    right = np.ascontiguousarray(right, dtype=np.float64)
+    i8p, i32p = C.POINTER(C.c_int8), C.POINTER(C.c_int32)
+
+    def at(a, o, t):
+        return C.cast(a.ctypes.data + o * a.itemsize, t)
+
+    for b in range(int(pb.n_bundles)):
+        j0 = int(joff[b])
+        if joff[b + 1] == j0:
+            continue
+        L.orc_junction_pass(C.byref(pb), C.byref(P), b, at(cov, int(cov_off[b]), c_f32p), at(good, j0, c_f64p),
+                            at(left, j0, c_f64p), at(right, j0, c_f64p), at(out["strand"], j0, i8p),
+                            at(out["nreads"], j0, c_f64p), at(out["nreads_good"], j0, c_f64p),
+                            at(out["leftsupport"], j0, c_f64p), at(out["rightsupport"], j0, c_f64p),
+                            at(out["mm"], j0, c_f64p), at(out["ej"], j0, i32p), at(out["good"], j0, i8p),
+                            at(out["good_strand"], j0, i8p))
+    return out

@@ -30,6 +30,32 @@ def test_oracle_matches_golden(golden):
     _check(golden, golden)
 
 
+A7 = (("strand", "a7_j_strand"), ("nreads", "a7_j_nreads"), ("nreads_good", "a7_j_nreads_good"),
+      ("leftsupport", "a7_j_leftsupport"), ("rightsupport", "a7_j_rightsupport"), ("mm", "a7_j_mm"), ("ej", "a7_ej"),
+      ("good", "a7_j_good"), ("good_strand", "a7_j_good_strand"))
+
+
+def _check_a7(arrays, ref):
+    """the junction table at the end of the junction pass of build_graphs (dumped from inside the
+    reference, before rlink.cpp:14843) and the reference's own good_junc verdicts — exact equality."""
+    cov, off, good, left, right = orc.run(arrays)
+    jp = orc.junction_pass(arrays, cov, off, good, left, right)
+    for k, rk in A7:
+        bad = np.nonzero(jp[k] != ref[rk])[0]
+        assert bad.size == 0, f"a7 {k}: {bad.size} rows differ, first {bad[:5]}: {jp[k][bad[:5]]} vs {ref[rk][bad[:5]]}"
+
+
+def test_oracle_junction_pass_matches_golden(golden):
+    _check_a7(golden, golden)
+
+
+def test_jitter_golden_exercises_the_demotion_pass():
+    from tests.conftest import load_golden
+    g = load_golden("short_s13_jitter")
+    assert (g["a7_j_nreads"] < 0).sum() >= 10 and (g["a7_j_nreads_good"] < 0).sum() >= 10   # demoted left / right
+    assert (g["a7_j_mm"] < 0).sum() >= 10 and (g["a7_j_good"] == 0).sum() >= 10
+
+
 def test_golden_has_inexact_weights(golden):
     # the fixtures must exercise order-dependent float accumulation (NH=3,5,6 -> 1/3, 1/5, 1/6)
     assert np.isin(golden["r_nh"], [3, 5, 6]).any()
@@ -44,8 +70,10 @@ def test_oracle_matches_live_reference(tmp_path, case):
         a = synth.make_adversarial(seed=int(case[-1]) + 10, n_bundles=14)
     src, dst = str(tmp_path / "in.stgb"), str(tmp_path / "out.stgb")
     write_stgb(src, a)
-    subprocess.check_call([REF_HOT, src, "--dump", dst], stdout=subprocess.DEVNULL)
-    _check(a, read_stgb(dst))
+    subprocess.check_call([REF_HOT, src, "--dump", dst, "--a7"], stdout=subprocess.DEVNULL)
+    ref = read_stgb(dst)
+    _check(a, ref)
+    _check_a7(a, ref)
 
 
 def test_get_cov_against_bruteforce(golden):

@@ -36,6 +36,9 @@ def main():
     ap.add_argument("--chroms", type=int, default=2)
     ap.add_argument("--long-intron-frac", type=float, default=0.03)
     ap.add_argument("--nh-frac", type=float, default=0.08, help="fraction of fragments with NH>1")
+    ap.add_argument("--jitter-frac", type=float, default=0.0,
+                    help="fraction of fragments aligned with one splice site shifted by 1-6 bp and an NM tag above "
+                         "mismatchfrac: junctions whose whole support is 'mismatchy' (the higherr pass, rlink.cpp:14538)")
     ap.add_argument("--sam", required=True)
     ap.add_argument("--gtf", default=None)
     a = ap.parse_args()
@@ -87,7 +90,21 @@ def main():
                     gtf.write("%s\tsyn\texon\t%d\t%d\t.\t%s\t.\t%s\n" % (chrom, s, e, strand, attr))
         n = max(1, int(a.pairs * lw / tw))
         for _ in range(n):
-            t = rng.choices(tposs, w)[0]
+            ti = rng.choices(range(len(tposs)), w)[0]
+            t = tposs[ti]
+            nmtag = ""
+            if a.jitter_frac and len(isos[ti]) > 1 and rng.random() < a.jitter_frac:
+                iso = isos[ti]
+                k = rng.randrange(len(iso) - 1)
+                d = rng.choice([-6, -5, -4, -3, -2, -1, 1, 2, 3, 4, 5, 6])
+                ex = [list(exons[i]) for i in iso]
+                if ex[k][1] + d > ex[k][0] + 12 and ex[k + 1][0] + d < ex[k + 1][1] - 12 and ex[k][1] + d < ex[k + 1][0] + d - 20:
+                    ex[k][1] += d
+                    ex[k + 1][0] += d
+                    t = []
+                    for s_, e_ in ex:
+                        t += list(range(s_, e_ + 1))
+                    nmtag = "\tNM:i:%d" % max(3, RL // 25)
             if len(t) < RL + 10:
                 continue
             fl = min(len(t), max(RL, int(rng.gauss(2.2 * RL, 0.4 * RL))))
@@ -100,8 +117,8 @@ def main():
             nh = 1
             if rng.random() < a.nh_frac:
                 nh = rng.choice([2, 2, 3, 3, 4, 5, 6])
-            x1 = "\tXS:A:" + strand if "N" in c1 else ""
-            x2 = "\tXS:A:" + strand if "N" in c2 else ""
+            x1 = ("\tXS:A:" + strand if "N" in c1 else "") + nmtag
+            x2 = ("\tXS:A:" + strand if "N" in c2 else "") + nmtag
             name = "r%d" % rid
             rid += 1
             u = rng.random()
