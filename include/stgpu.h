@@ -17,6 +17,7 @@
  *   a3  junction support loop                    -> stg_run(), kernel junc_support
  *   a4  clamped + BSIZE-blocked prefix scan      -> stg_run(), kernel cov_tile
  *   a5  get_cov / get_cov_sign                   -> stg_query_cov()
+ *   a7  junction pass of build_graphs, good_junc -> stg_run(), kernel junc_pass; stg_fetch_junction_pass()
  */
 #ifndef STGPU_H_
 #define STGPU_H_
@@ -173,6 +174,15 @@ const float* stg_device_bpcov(const stg_dbatch* batch); /* device pointer (for c
 /* CJunction::nreads_good / leftsupport / rightsupport after the stage; each [n_juncs] */
 int stg_fetch_junction_support(stg_ctx* ctx, const stg_dbatch* batch, double* nreads_good, double* leftsupport,
                                double* rightsupport);
+/* Row a7: the junction table at the end of the junction pass that opens build_graphs (rlink.cpp:14385-14809) —
+ * CJunction::strand / nreads / nreads_good / leftsupport / rightsupport / mm (a negative nreads or nreads_good is the
+ * negated row index of the better neighbour the junction was demoted to, rlink.cpp:14644, 14738) — the order of
+ * `ejunction` (junction re-sorted by end, rlink.cpp:14387-14389) as bundle-local row indices, and the verdict of
+ * good_junc (rlink.cpp:13967) on every row that still has a strand (-1 where it has none) together with the strand
+ * good_junc would leave.  Each array [n_juncs]; any pointer may be NULL. */
+int stg_fetch_junction_pass(stg_ctx* ctx, const stg_dbatch* batch, int8_t* strand, double* nreads, double* nreads_good,
+                            double* leftsupport, double* rightsupport, double* mm, int32_t* ej, int8_t* good,
+                            int8_t* good_strand);
 /* per bundle: sum over the bundle of clamped coverage per lane, get_cov(s, 0, len_b-2) — [n_bundles*3] f64 */
 int stg_fetch_cov_totals(stg_ctx* ctx, const stg_dbatch* batch, double* totals);
 

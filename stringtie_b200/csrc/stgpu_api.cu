@@ -224,6 +224,10 @@ int stg_init(const stg_params* params, int device, stg_ctx** out) {
     delete ctx;
     return fail(nullptr, STG_EUNSUPPORTED, "long-read / mixed mode junction correction (rlink.cpp:16668-16975) is not built yet");
   }
+  if (ctx->params.viral || ctx->params.havePtFeatures) {
+    delete ctx;
+    return fail(nullptr, STG_EUNSUPPORTED, "--viral / --ptf branches of the junction pass (rlink.cpp:14189-14202, 14543-14589) are not built yet");
+  }
   CK(nullptr, cudaSetDevice(device));
   cudaDeviceProp prop;
   CK(nullptr, cudaGetDeviceProperties(&prop, device));
@@ -397,6 +401,8 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
   AL(bpcov, 3 * v.total_pos);
   AL(j_nreads_good, h->n_juncs); AL(j_leftsupport, h->n_juncs); AL(j_rightsupport, h->n_juncs);
   AL(b_cov_total, nb * 3);
+  AL(jp_strand, h->n_juncs); AL(jp_nreads, h->n_juncs); AL(jp_nreads_good, h->n_juncs); AL(jp_left, h->n_juncs);
+  AL(jp_right, h->n_juncs); AL(jp_mm, h->n_juncs); AL(jp_ej, h->n_juncs); AL(jp_good, h->n_juncs); AL(jp_good_strand, h->n_juncs);
 #undef AL
   // the padding between a lane's length and its stride is written by the tile kernels; nothing else to clear
   *out = d;
@@ -484,6 +490,11 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   { Scope s(ctx, "cov_tile", 1); CK(ctx, launch_cov_tiles(v, ctx->num_sms, st)); }
   { Scope s(ctx, "cov_fill", 1); CK(ctx, launch_cov_fill(v, ctx->num_sms, st)); }
   { Scope s(ctx, "cov_totals", 1); CK(ctx, launch_cov_totals(v, st)); }
+  {
+    JuncParams jp{ctx->params.junctionsupport, ctx->params.sserror, ctx->params.junctionthr, ctx->params.eonly};
+    Scope s(ctx, "junction_pass", 1);
+    CK(ctx, launch_junc_pass(v, jp, st));
+  }
   d->ran = true;
   return STG_OK;
 }
@@ -537,6 +548,29 @@ int stg_fetch_junction_support(stg_ctx* ctx, const stg_dbatch* d, double* good, 
     if (good) CK(ctx, cudaMemcpyAsync(good, d->v.j_nreads_good, nb, cudaMemcpyDeviceToHost, ctx->stream));
     if (left) CK(ctx, cudaMemcpyAsync(left, d->v.j_leftsupport, nb, cudaMemcpyDeviceToHost, ctx->stream));
     if (right) CK(ctx, cudaMemcpyAsync(right, d->v.j_rightsupport, nb, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return STG_OK;
+}
+
+int stg_fetch_junction_pass(stg_ctx* ctx, const stg_dbatch* d, int8_t* strand, double* nreads, double* nreads_good,
+                            double* leftsupport, double* rightsupport, double* mm, int32_t* ej, int8_t* good,
+                            int8_t* good_strand) {
+  if (!ctx || !d) return fail(ctx, STG_EINVAL, "stg_fetch_junction_pass: bad argument");
+  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_fetch_junction_pass: batch has not been run");
+  CK(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)d->v.n_juncs;
+  if (n) {
+    cudaStream_t st = ctx->stream;
+    if (strand) CK(ctx, cudaMemcpyAsync(strand, d->v.jp_strand, n, cudaMemcpyDeviceToHost, st));
+    if (nreads) CK(ctx, cudaMemcpyAsync(nreads, d->v.jp_nreads, 8 * n, cudaMemcpyDeviceToHost, st));
+    if (nreads_good) CK(ctx, cudaMemcpyAsync(nreads_good, d->v.jp_nreads_good, 8 * n, cudaMemcpyDeviceToHost, st));
+    if (leftsupport) CK(ctx, cudaMemcpyAsync(leftsupport, d->v.jp_left, 8 * n, cudaMemcpyDeviceToHost, st));
+    if (rightsupport) CK(ctx, cudaMemcpyAsync(rightsupport, d->v.jp_right, 8 * n, cudaMemcpyDeviceToHost, st));
+    if (mm) CK(ctx, cudaMemcpyAsync(mm, d->v.jp_mm, 8 * n, cudaMemcpyDeviceToHost, st));
+    if (ej) CK(ctx, cudaMemcpyAsync(ej, d->v.jp_ej, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (good) CK(ctx, cudaMemcpyAsync(good, d->v.jp_good, n, cudaMemcpyDeviceToHost, st));
+    if (good_strand) CK(ctx, cudaMemcpyAsync(good_strand, d->v.jp_good_strand, n, cudaMemcpyDeviceToHost, st));
   }
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   return STG_OK;

@@ -88,6 +88,17 @@ struct DevBatchView {
   float* bpcov;                // [3*total_pos]: bundle b lane s index i at 3*b_gbase[b] + s*b_stride[b] + i
   double *j_nreads_good, *j_leftsupport, *j_rightsupport;  // [n_juncs]
   double* b_cov_total;         // [n_bundles*3]
+  // junction pass of build_graphs (row a7): CJunction fields after rlink.cpp:14385-14809, one per junction row
+  int8_t* jp_strand;
+  double *jp_nreads, *jp_nreads_good, *jp_left, *jp_right, *jp_mm;
+  int32_t* jp_ej;              // bundle-local row of ejunction[k] (junction re-sorted by end)
+  int8_t *jp_good, *jp_good_strand;  // good_junc verdict (-1: row has no strand) and the strand it leaves
+};
+
+struct JuncParams {
+  uint32_t junctionsupport, sserror;
+  int32_t junctionthr;
+  uint32_t eonly;
 };
 
 struct KernelParams {
@@ -113,5 +124,6 @@ cudaError_t launch_cov_fill(const DevBatchView& v, int num_sms, cudaStream_t st)
 cudaError_t launch_cov_totals(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_query_cov(const DevBatchView& v, int64_t n, const int32_t* bundle, const int8_t* lane,
                              const uint32_t* start, const uint32_t* end, int sign, double* out, cudaStream_t st);
+cudaError_t launch_junc_pass(const DevBatchView& v, const JuncParams& p, cudaStream_t st);
 int64_t scan_partials_needed(int64_t n);
 int cov_tile_smem_bytes();

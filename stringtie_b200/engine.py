@@ -22,7 +22,7 @@ EXPORTS = [
     "stg_params_default", "stg_init", "stg_shutdown", "stg_last_error", "stg_abi_version", "stg_builder_create",
     "stg_builder_add", "stg_builder_packed", "stg_builder_reset", "stg_builder_destroy", "stg_upload", "stg_run",
     "stg_sync", "stg_free_batch", "stg_trim", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
-    "stg_fetch_junction_support", "stg_fetch_cov_totals", "stg_query_cov", "stg_infer_transcripts",
+    "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_infer_transcripts",
     "stg_shard_assign", "stg_set_profiling", "stg_kernel_count", "stg_kernel_time", "stg_launch_counter", "stg_batch_stats", "stg_stream",
 ]
 
@@ -66,6 +66,8 @@ def load_library() -> C.CDLL:
     L.stg_device_bpcov.argtypes = [vp]
     L.stg_device_bpcov.restype = vp
     L.stg_fetch_junction_support.argtypes = [vp, vp, c_f64p, c_f64p, c_f64p]
+    i8p, i32p = C.POINTER(C.c_int8), C.POINTER(C.c_int32)
+    L.stg_fetch_junction_pass.argtypes = [vp, vp, i8p, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, i32p, i8p, i8p]
     L.stg_fetch_cov_totals.argtypes = [vp, vp, c_f64p]
     L.stg_query_cov.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int8), C.POINTER(C.c_uint32),
                                 C.POINTER(C.c_uint32), C.c_int, c_f64p]
@@ -182,6 +184,19 @@ class Engine:
         right = np.empty(batch.n_juncs, dtype=np.float64)
         self._ck(self.L.stg_fetch_junction_support(self.ctx, batch.handle, ptr(good), ptr(left), ptr(right)))
         return good, left, right
+
+    def fetch_junction_pass(self, batch: DeviceBatch) -> Dict[str, np.ndarray]:
+        """Row a7: the junction table after the junction pass of build_graphs + good_junc verdicts (stg_fetch_junction_pass)."""
+        n = batch.n_juncs
+        out = {"strand": np.zeros(n, np.int8), "nreads": np.zeros(n), "nreads_good": np.zeros(n),
+               "leftsupport": np.zeros(n), "rightsupport": np.zeros(n), "mm": np.zeros(n),
+               "ej": np.zeros(n, np.int32), "good": np.zeros(n, np.int8), "good_strand": np.zeros(n, np.int8)}
+        i8p, i32p = C.POINTER(C.c_int8), C.POINTER(C.c_int32)
+        self._ck(self.L.stg_fetch_junction_pass(
+            self.ctx, batch.handle, out["strand"].ctypes.data_as(i8p), ptr(out["nreads"]), ptr(out["nreads_good"]),
+            ptr(out["leftsupport"]), ptr(out["rightsupport"]), ptr(out["mm"]), out["ej"].ctypes.data_as(i32p),
+            out["good"].ctypes.data_as(i8p), out["good_strand"].ctypes.data_as(i8p)))
+        return out
 
     def fetch_cov_totals(self, batch: DeviceBatch) -> np.ndarray:
         out = np.empty(batch.n_bundles * 3, dtype=np.float64)

@@ -23,7 +23,16 @@ def gpu_cov_dense(engine, batch, arrays):
     return out
 
 
-def check_batch(engine, arrays, ref_cov=None, ref_support=None):
+A7_KEYS = ("strand", "nreads", "nreads_good", "leftsupport", "rightsupport", "mm", "ej", "good", "good_strand")
+
+
+def golden_a7(g):
+    return {"strand": g["a7_j_strand"], "nreads": g["a7_j_nreads"], "nreads_good": g["a7_j_nreads_good"],
+            "leftsupport": g["a7_j_leftsupport"], "rightsupport": g["a7_j_rightsupport"], "mm": g["a7_j_mm"],
+            "ej": g["a7_ej"], "good": g["a7_j_good"], "good_strand": g["a7_j_good_strand"]}
+
+
+def check_batch(engine, arrays, ref_cov=None, ref_support=None, ref_a7=None):
     batch = engine.upload(arrays)
     try:
         engine.run(batch)
@@ -37,6 +46,14 @@ def check_batch(engine, arrays, ref_cov=None, ref_support=None):
         assert np.array_equal(good, ref_support[0])
         assert np.array_equal(left, ref_support[1])
         assert np.array_equal(right, ref_support[2])
+        # row a7: junction pass of build_graphs + good_junc, against the oracle or the reference's own dump
+        jp = engine.fetch_junction_pass(batch)
+        if ref_a7 is None:
+            lens_, off_ = orc.cov_layout(arrays)
+            ref_a7 = orc.junction_pass(arrays, ref_cov, off_, *ref_support)
+        for k in A7_KEYS:
+            bad = np.nonzero(jp[k] != ref_a7[k])[0]
+            assert bad.size == 0, f"a7 {k}: {bad.size} rows differ, first {bad[:5]}: {jp[k][bad[:5]]} vs {ref_a7[k][bad[:5]]}"
         # second run on the same device batch: identical (idempotent, no leftover state in scratch)
         engine.run(batch)
         got2 = gpu_cov_dense(engine, batch, arrays)
@@ -52,7 +69,8 @@ def check_batch(engine, arrays, ref_cov=None, ref_support=None):
 @pytest.mark.parametrize("name", GOLDEN)
 def test_golden_reference_vectors(engine, name):
     g = load_golden(name)
-    b = check_batch(engine, g, g["s1_cov"], (g["s1_j_nreads_good"], g["s1_j_leftsupport"], g["s1_j_rightsupport"]))
+    b = check_batch(engine, g, g["s1_cov"], (g["s1_j_nreads_good"], g["s1_j_leftsupport"], g["s1_j_rightsupport"]),
+                    golden_a7(g))
     b.free()
 
 
