@@ -124,42 +124,35 @@ cudaError_t launch_junc_anchor(const DevBatchView& v, const KernelParams& p, cud
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// K1: count intervals per read
-// --------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(STG_READ_BLOCK) expand_count_kernel(DevBatchView v) {
-  const int64_t n64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n64 >= v.n_reads) return;
-  const uint32_t n = (uint32_t)n64;
-  const uint32_t b = bundle_of_read(v, n);
-  const uint32_t r0 = v.b_read_off[b];
-  uint32_t cnt = 0;
-  walk_read_intervals(v, r0, n, [&](uint32_t, uint32_t, float, int) { cnt++; });
-  v.r_ivl_cnt[n] = cnt;
-  if (n64 == v.n_reads - 1) v.r_ivl_cnt[v.n_reads] = 0;
-}
-
-// --------------------------------------------------------------------------------------------------------------
-// K1b: junction support (rlink.cpp:16890-17016): for intron i of a read, left anchor = longest exon at or before
+// K1: interval count of every read (the mate-merge walk of add_read_to_cov, rlink.cpp:144-219) and
+// junction support (rlink.cpp:16890-17016): for intron i of a read, left anchor = longest exon at or before
 // it, right anchor = longest exon after it; the junction row gets leftsupport / rightsupport / nreads_good += w.
 // The sums are float weights accumulated in f64: every partial sum is exactly representable, so the order of the
 // additions is free.  One thread per read; the 32 reads of a warp usually cross the same few junctions with the
 // same few weights, so each round the warp groups its updates by (junction row, weight) with one 64-bit match and
 // issues ONE f64 atomic of count * w per group and counter (the product is exact: count <= 32, w has 24 bits).
 // --------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(STG_READ_BLOCK) junc_support_kernel(DevBatchView v) {
+__global__ void __launch_bounds__(STG_READ_BLOCK) expand_count_kernel(DevBatchView v) {
   const int64_t n64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool live = n64 < v.n_reads;
   const uint32_t n = live ? (uint32_t)n64 : 0u;
-  uint32_t s0 = 0, nex = 0;
-  if (live) { s0 = v.r_seg_off[n]; nex = v.r_seg_off[n + 1] - s0; }
+  uint32_t s0 = 0, nex = 0, b = 0;
+  if (live) {
+    b = bundle_of_read(v, n);
+    uint32_t cnt = 0;
+    walk_read_intervals(v, v.b_read_off[b], n, [&](uint32_t, uint32_t, float, int) { cnt++; });
+    v.r_ivl_cnt[n] = cnt;
+    if (n64 == v.n_reads - 1) v.r_ivl_cnt[v.n_reads] = 0;
+    s0 = v.r_seg_off[n]; nex = v.r_seg_off[n + 1] - s0;
+  }
   const uint32_t max_nex = __reduce_max_sync(FULL, nex);
-  if (max_nex < 2) return;
+  if (max_nex < 2 || v.n_juncs == 0) return;
   uint32_t j0 = 0;
   float w = 0.f;
   const int32_t* __restrict__ rj = v.rjunc_idx + (s0 - n);
   if (nex >= 2) {
-    j0 = v.b_junc_off[bundle_of_read(v, n)];
+    j0 = v.b_junc_off[b];
     w = v.r_count[n];
     if ((v.r_flags[n] & STG_RF_UNITIG) && w > 1.f) w = 1.f;
   }
@@ -346,11 +339,7 @@ cudaError_t launch_expand_count(const DevBatchView& v, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_junc_support(const DevBatchView& v, cudaStream_t st) {
-  if (v.n_reads == 0 || v.n_juncs == 0) return cudaSuccess;
-  junc_support_kernel<<<(unsigned)((v.n_reads + STG_READ_BLOCK - 1) / STG_READ_BLOCK), STG_READ_BLOCK, 0, st>>>(v);
-  return cudaGetLastError();
-}
+
 
 cudaError_t launch_expand_write(const DevBatchView& v, cudaStream_t st) {
   if (v.n_reads == 0) return cudaSuccess;
@@ -586,7 +575,7 @@ cudaError_t launch_tile_plan(const DevBatchView& v, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(v.round_off, 0, sizeof(uint32_t) * (size_t)(v.n_rounds + 1), st);
   if (e != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(v.round_cur, 0, sizeof(uint32_t) * (size_t)(v.n_rounds + 1), st)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(v.deep_count, 0, sizeof(uint32_t), st)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(v.deep_count, 0, 2 * sizeof(uint32_t), st)) != cudaSuccess) return e;
   tile_plan_kernel<false><<<(unsigned)((v.n_tiles + 255) / 256), 256, 0, st>>>(v);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if ((e = run_scan<OP_ADD, false, true>(v.round_off, v.round_off, v.n_rounds + 1, v.scan_partials, st)) != cudaSuccess) return e;
@@ -609,7 +598,6 @@ static_assert(DEEP_WARPS * 32 == STG_TILE_W, "phase 2 of deep_deposit_kernel map
 __global__ void __launch_bounds__(DEEP_WARPS * 32) deep_deposit_kernel(DevBatchView v) {
   __shared__ uint32_t cnt[DEEP_WARPS][STG_TILE_W];       // per warp slice: events per position, then first slot
   __shared__ uint32_t poff[STG_TILE_W + 1];              // first slot of every position in the sorted list
-  __shared__ __align__(16) float stage[DEEP_WARPS][3][32];
   __shared__ uint32_t wtot[DEEP_WARPS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -703,49 +691,69 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32) deep_deposit_kernel(DevBatchV
         }
         dd[p] = a0; dd[STG_TILE_W + p] = a1; dd[2 * STG_TILE_W + p] = a2;
       }
-      uint32_t todo = __ballot_sync(FULL, is_long);
-      while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int q = wid * 32 + src;
-        const uint32_t q0 = __shfl_sync(FULL, l0, src), qn = __shfl_sync(FULL, n, src);
-        float acc = 0.f;   // lane s < 3 accumulates strand lane s
-        uint2 cur = make_uint2(1u, 0u);
-        if ((uint32_t)lane < qn) cur = __ldcg(&sorted[q0 + lane]);
-        for (uint32_t off = 0; off < qn; off += 32) {
-          uint2 nxt = make_uint2(1u, 0u);      // padding: +0.0 on lane 1, a no-op (no accumulator is ever -0)
-          if (off + 32 + lane < qn) nxt = __ldcg(&sorted[q0 + off + 32 + lane]);
-          const float val = __uint_as_float(cur.y);
-          stage[wid][0][lane] = cur.x == 0u ? val : 0.f;
-          stage[wid][1][lane] = val;
-          stage[wid][2][lane] = cur.x == 2u ? val : 0.f;
-          __syncwarp();
-          if (lane < 3) {
-            const float4* sv = reinterpret_cast<const float4*>(stage[wid][lane]);
-            const uint32_t m = min(32u, qn - off);
-            if (m == 32u) {
-#pragma unroll
-              for (int u = 0; u < 8; u++) {
-                const float4 y = sv[u];
-                acc = __fadd_rn(acc, y.x); acc = __fadd_rn(acc, y.y); acc = __fadd_rn(acc, y.z); acc = __fadd_rn(acc, y.w);
-              }
-            } else {
-              for (uint32_t u = 0; u < m; u++) acc = __fadd_rn(acc, stage[wid][lane][u]);
-            }
-          }
-          __syncwarp();
-          cur = nxt;
-        }
-        if (lane < 3) dd[lane * STG_TILE_W + q] = acc;
+      else {
+        // handed to deep_long_kernel: the CTA must not idle behind one position's chain of 10^4..10^5 dependent adds
+        const uint32_t slot = atomicAdd(v.deep_count + 1, 1u);
+        v.deep_long[slot] = make_uint4(di, (uint32_t)p, e0 + l0, n);
       }
     }
     __syncthreads();
   }
 }
 
+// Long per-position lists of deep sub-tiles (> 64 events on one position: a splice site of a deep locus), one warp
+// per list: 32 events are loaded at a time (coalesced, next group prefetched) and staged in shared memory per strand
+// lane (cov_edge_add, rlink.cpp:133-142: own lane and lane 1; the other lanes get +0.0, a no-op since no accumulator
+// is ever -0); lanes 0..2 then run the bare chain of dependent adds in reference order.
+__global__ void __launch_bounds__(256) deep_long_kernel(DevBatchView v) {
+  __shared__ __align__(16) float stage[8][3][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t nlong = v.deep_count[1];
+  for (;;) {
+    uint32_t li = 0;
+    if (lane == 0) li = atomicAdd(v.tile_ticket + 2, 1u);
+    li = __shfl_sync(FULL, li, 0);
+    if (li >= nlong) break;
+    const uint4 rec = v.deep_long[li];
+    const uint2* __restrict__ list = v.events2 + rec.z;
+    const uint32_t qn = rec.w;
+    float acc = 0.f;   // lane s < 3 accumulates strand lane s
+    uint2 cur = make_uint2(1u, 0u);
+    if ((uint32_t)lane < qn) cur = __ldcs(&list[lane]);
+    for (uint32_t off = 0; off < qn; off += 32) {
+      uint2 nxt = make_uint2(1u, 0u);
+      if (off + 32 + lane < qn) nxt = __ldcs(&list[off + 32 + lane]);
+      const float val = __uint_as_float(cur.y);
+      stage[wid][0][lane] = cur.x == 0u ? val : 0.f;
+      stage[wid][1][lane] = val;
+      stage[wid][2][lane] = cur.x == 2u ? val : 0.f;
+      __syncwarp();
+      if (lane < 3) {
+        const float4* sv = reinterpret_cast<const float4*>(stage[wid][lane]);
+        const uint32_t m = min(32u, qn - off);
+        if (m == 32u) {
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const float4 y = sv[u];
+            acc = __fadd_rn(acc, y.x); acc = __fadd_rn(acc, y.y); acc = __fadd_rn(acc, y.z); acc = __fadd_rn(acc, y.w);
+          }
+        } else {
+          for (uint32_t u = 0; u < m; u++) acc = __fadd_rn(acc, stage[wid][lane][u]);
+        }
+      }
+      __syncwarp();
+      cur = nxt;
+    }
+    if (lane < 3) v.deep_d[(size_t)rec.x * (3 * STG_TILE_W) + lane * STG_TILE_W + rec.y] = acc;
+  }
+}
+
 cudaError_t launch_deep_deposit(const DevBatchView& v, int num_sms, cudaStream_t st) {
   if (v.n_tiles == 0 || v.n_ivl == 0) return cudaSuccess;
-  deep_deposit_kernel<<<num_sms * 5, DEEP_WARPS * 32, 0, st>>>(v);
+  deep_deposit_kernel<<<num_sms * 4, DEEP_WARPS * 32, 0, st>>>(v);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  deep_long_kernel<<<num_sms * 8, 256, 0, st>>>(v);
   return cudaGetLastError();
 }
 

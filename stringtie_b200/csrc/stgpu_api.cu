@@ -395,7 +395,7 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
   AL(r_ivl_cnt, h->n_reads + 1);
   d->scan_capacity = std::max<int64_t>(std::max<int64_t>(h->n_reads + 1, v.n_tiles + 1), v.n_rounds + 1);
   AL(scan_partials, scan_partials_needed(d->scan_capacity));
-  AL(tile_carry, v.n_tiles * 4); AL(tile_ticket, 2); AL(deep_count, 1);
+  AL(tile_carry, v.n_tiles * 4); AL(tile_ticket, 3); AL(deep_count, 2);
   AL(round_off, v.n_rounds + 1); AL(round_cur, v.n_rounds + 1);
   AL(tile_plan, v.n_tiles); AL(tile_evoff, v.n_tiles + 1); AL(tile_lastne, v.n_tiles); AL(junc_anchor, h->n_juncs);
   AL(bpcov, 3 * v.total_pos);
@@ -432,10 +432,9 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
     CK(ctx, cudaMemsetAsync(v.j_rightsupport, 0, sizeof(double) * v.n_juncs, st));
   }
   if (v.n_tiles) CK(ctx, cudaMemsetAsync(v.tile_carry, 0xff, sizeof(unsigned long long) * 4 * (size_t)v.n_tiles, st));
-  CK(ctx, cudaMemsetAsync(v.tile_ticket, 0, 2 * sizeof(uint32_t), st));
+  CK(ctx, cudaMemsetAsync(v.tile_ticket, 0, 3 * sizeof(uint32_t), st));
   { Scope s(ctx, "junc_anchor", 1); CK(ctx, launch_junc_anchor(v, kp, st)); }
-  { Scope s(ctx, "junction_support", 1); CK(ctx, launch_junc_support(v, st)); }
-  { Scope s(ctx, "expand_count", 1); CK(ctx, launch_expand_count(v, st)); }
+  { Scope s(ctx, "expand_count+junction_support", 1); CK(ctx, launch_expand_count(v, st)); }
   { Scope s(ctx, "scan_interval_offsets", 3); CK(ctx, launch_scan_exclusive_add(v.r_ivl_cnt, v.n_reads + 1, v.scan_partials, st)); }
   // the interval count sizes the next buffers: a 4-byte read-back (one of the two host syncs inside the stage)
   uint32_t n_ivl = 0;
@@ -453,7 +452,7 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
     const int64_t dcap = 2 * cap / STG_DEEP_EVENTS + 1;
     if ((rc = dev_alloc(ctx, d, &v.ivl, cap)) || (rc = dev_alloc(ctx, d, &v.events, 2 * cap)) ||
         (rc = dev_alloc(ctx, d, &v.events2, 2 * cap)) || (rc = dev_alloc(ctx, d, &v.deep_list, dcap)) ||
-        (rc = dev_alloc(ctx, d, &v.deep_d, dcap * 3 * STG_TILE_W)) ||
+        (rc = dev_alloc(ctx, d, &v.deep_d, dcap * 3 * STG_TILE_W)) || (rc = dev_alloc(ctx, d, &v.deep_long, 2 * cap / 64 + 1)) ||
         (rc = dev_alloc(ctx, d, &v.ch_tlo, ccap)) || (rc = dev_alloc(ctx, d, &v.ch_thi, ccap)) ||
         (rc = dev_alloc(ctx, d, &v.ch_pmax_thi, ccap)) || (rc = dev_alloc(ctx, d, &v.ch_smin_tlo, ccap)) ||
         (rc = dev_alloc(ctx, d, &v.ch_row_off, ccap + 1)))
@@ -486,7 +485,7 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   { Scope s(ctx, "bin_columns+scans", 7); CK(ctx, launch_bin_columns(v, st)); }
   { Scope s(ctx, "bin_scatter", 1); CK(ctx, launch_bin_scatter(v, st)); }
   { Scope s(ctx, "tile_plan", 8); CK(ctx, launch_tile_plan(v, st)); }
-  { Scope s(ctx, "deep_deposit", 1); CK(ctx, launch_deep_deposit(v, ctx->num_sms, st)); }
+  { Scope s(ctx, "deep_deposit", 2); CK(ctx, launch_deep_deposit(v, ctx->num_sms, st)); }
   { Scope s(ctx, "cov_tile", 1); CK(ctx, launch_cov_tiles(v, ctx->num_sms, st)); }
   { Scope s(ctx, "cov_fill", 1); CK(ctx, launch_cov_fill(v, ctx->num_sms, st)); }
   { Scope s(ctx, "cov_totals", 1); CK(ctx, launch_cov_totals(v, st)); }

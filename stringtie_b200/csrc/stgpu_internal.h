@@ -74,7 +74,8 @@ struct DevBatchView {
   uint2* events2;              // [2*n_ivl]   deep sub-tiles only: {lane, signed weight bits} sorted by position (stable)
   uint4* deep_list;            // [deep_cap]  {tile id, first event, events, -} of every deep sub-tile
   float* deep_d;               // [deep_cap * 3 * STG_TILE_W] their finished difference arrays
-  uint32_t* deep_count;        // [1]
+  uint4* deep_long;            // [long_cap]  {deep slot, position, first event in events2, events} of every long list
+  uint32_t* deep_count;        // [2] deep sub-tiles, long lists
   uint32_t* scan_partials;     // scratch for the 3-phase scans
   uint8_t* junc_anchor;        // [n_juncs] anchor length each junction demands (10 or 25, rlink.cpp:16991-16997)
   uint32_t* round_off;         // [n_rounds+1] tiles with events per round, then exclusive prefix: first ticket of the
@@ -83,7 +84,7 @@ struct DevBatchView {
   TileRec* tile_plan;          // [n_tiles] [0, n_main): tiles with events in ticket order; [n_main, n_tiles): the rest
   unsigned long long* tile_carry;  // [n_tiles*4] per strand lane (c | bs << 32) after the last position of a
                                //             sub-tile with events; all-ones until published (bundle-major tile id)
-  uint32_t* tile_ticket;       // [2] work counters: [0] cov_tile_kernel, [1] deep_deposit_kernel
+  uint32_t* tile_ticket;       // [3] work counters: cov_tile_kernel, deep_deposit_kernel, deep_long_kernel
   // outputs
   float* bpcov;                // [3*total_pos]: bundle b lane s index i at 3*b_gbase[b] + s*b_stride[b] + i
   double *j_nreads_good, *j_leftsupport, *j_rightsupport;  // [n_juncs]
@@ -109,7 +110,6 @@ struct KernelParams {
 
 // kernel launchers (cov_kernels.cu). Each enqueues on `st` and returns the CUDA error of the launch.
 cudaError_t launch_expand_count(const DevBatchView& v, cudaStream_t st);
-cudaError_t launch_junc_support(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_scan_exclusive_add(uint32_t* data, int64_t n_plus_1, uint32_t* partials, cudaStream_t st);
 cudaError_t launch_expand_write(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_chunk_hull(const DevBatchView& v, cudaStream_t st);      // + the three chunk-level scans
