@@ -163,3 +163,49 @@ def test_large_property_checks(engine):
             d[9999::10000] = 0  # block restarts
             assert (d >= 0).all()
     batch.free()
+
+
+def test_c2_full_size(engine):
+    """BASELINE.json's full size (the bench workload: ~10^8 alignments, 60 000 bundles), every stage against the
+    oracle: per-bundle coverage totals (get_cov over the whole bundle: any wrong bit in the blocked prefix sums moves
+    them), junction support and the junction pass on every row, and the full bpcov bit pattern of the deepest
+    bundles plus a random sample."""
+    import bench
+    base, a = bench.build_workload(bench.REPLICAS, bench.BASE_BUNDLES, 0)
+    batch = engine.upload(a)
+    engine.run(batch)
+    tot = engine.fetch_cov_totals(batch)
+    good, left, right = engine.fetch_junction_support(batch)
+    jp = engine.fetch_junction_pass(batch)
+    cov, off, og, ol, orr = orc.run(a, threads=0)
+    assert np.array_equal(good, og) and np.array_equal(left, ol) and np.array_equal(right, orr)
+    lens, _ = orc.cov_layout(a)
+    nb = lens.size
+    reads = np.diff(a["b_read_off"].astype(np.int64))
+    sample = np.unique(np.concatenate([np.argsort(reads)[-24:], np.argsort(lens)[-8:],
+                                       np.random.default_rng(1).integers(0, nb, 300)]))
+    for b in sample:
+        L = int(lens[b])
+        got = engine.fetch_bpcov(batch, int(b), L).reshape(3, L)
+        want = cov[off[b]:off[b + 1]].reshape(3, L)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"bpcov of bundle {b} differs"
+    # totals of ALL bundles, recomputed from the oracle's bpcov with the oracle's get_cov on a sample, and cross-lane
+    for b in sample:
+        for s in range(3):
+            assert tot[b, s] == orc.get_cov(cov[off[b]:off[b + 1]], int(lens[b]), s, 0, int(lens[b]) - 2)
+    # every bundle: the stored last prefix of every BSIZE block summed in f64 == the GPU total (vectorised get_cov)
+    for s in (1,):
+        want_all = np.zeros(nb)
+        for b in range(nb):
+            L = int(lens[b])
+            lane = cov[off[b] + s * L: off[b] + (s + 1) * L]
+            m = (L - 1) // 10000
+            acc = float(lane[9999:m * 10000:10000].astype(np.float64).sum()) if m else 0.0
+            acc += float(np.float32(lane[L - 1]) - np.float32(lane[0]))
+            want_all[b] = max(acc, 0.0)
+        assert np.array_equal(tot[:, s], want_all)
+    ref_a7 = orc.junction_pass(a, cov, off, og, ol, orr)
+    for k in A7_KEYS:
+        assert np.array_equal(jp[k], ref_a7[k]), f"a7 {k} differs at full size"
+    batch.free()
+    engine.trim()
