@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""bench.py — throughput of the per-bundle assembly hot path (the stages built so far: coverage + junction support,
-i.e. the reference's count_good_junctions) on the C2 workload of BASELINE.json:
+"""bench.py — throughput of the per-bundle assembly hot path (the stages built so far: the reference's
+count_good_junctions = coverage + junction support, and the junction pass that opens build_graphs) on the C2 workload
+of BASELINE.json:
 synthetic 100 M 2x150 paired-end spliced alignments over ~60 k loci.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one rank per GPU under torchrun for N>1)
@@ -28,7 +29,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "aligned reads/sec through assembly (stages built: coverage + junction support = count_good_junctions)"
+METRIC = ("aligned reads/sec through assembly (stages built: count_good_junctions = coverage + junction support, "
+          "and the junction pass of build_graphs)")
 BASE_BUNDLES = 6000          # one seeded base of ~9.7 M alignments ...
 BASE_READS_PER_BUNDLE = 1667
 REPLICAS = 10                # ... x 10 coordinate-shifted replicas = ~97 M alignments over 60 000 loci
@@ -104,10 +106,11 @@ def reference_hot(arrays, nbundles: int, threads: int, reps: int):
         with tempfile.TemporaryDirectory() as td:
             path = os.path.join(td, "sample.stgb")
             write_stgb(path, sample)
-            out = subprocess.check_output([tool, path, "--threads", str(threads), "--reps", str(reps)], text=True)
+            out = subprocess.check_output([tool, path, "--threads", str(threads), "--reps", str(reps), "--a7"], text=True)
         j = json.loads(out.strip().splitlines()[-1])
         return {"value": j["reads_per_s"], "unit": "reads/s", "cores": threads, "kind": "reference",
-                "sample": desc + "; reference count_good_junctions (rlink.cpp:16656) on rebuilt BundleData, "
+                "sample": desc + "; reference count_good_junctions (rlink.cpp:16656) + build_graphs up to the end of its "
+                          "junction pass (rlink.cpp:14165-14842) on rebuilt BundleData, "
                           "aggregate of per-thread reads / per-thread compute time",
                 "bundles_per_s": j["reads_per_s"] * nb / max(nreads, 1), "compute_s": j["compute_s_max"]}
     from tests import orc
@@ -138,7 +141,8 @@ def main():
                      f"(~{args.replicas * args.base_bundles * BASE_READS_PER_BUNDLE / 1e6:.0f} M alignments, 2x150 PE, de novo)")
     config = {"workload": workload_name, "per_gpu": "one full copy of the workload per rank (weak scaling)",
               "l2": "inputs_larger_than_L2", "stages": ["cov_edge_add/add_read_to_cov", "junction support",
-                                                         "blocked clamped scan", "get_cov totals"]}
+                                                         "blocked clamped scan", "get_cov totals",
+                                                         "build_graphs junction pass + good_junc"]}
 
     # ---------------- reference arm: the reference's own CPU code, all host threads, bounded sample ----------
     if args.impl == "reference":
