@@ -1032,9 +1032,24 @@ __global__ void __launch_bounds__(256) cov_fill_kernel(DevBatchView v) {
   const uint32_t n_main = __ldg(v.round_off + v.n_rounds);
   const uint32_t n_tiles = (uint32_t)v.n_tiles;
   const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t t = n_main + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += warps) {
-    uint32_t recw = 0;
-    if (lane < 8) recw = __ldg(reinterpret_cast<const uint32_t*>(v.tile_plan + t) + lane);
+  // software pipeline, two deep: while sub-tile t is written, the plan record of t + 2*warps and the carry of
+  // t + warps (whose record arrived during the previous iteration) are in flight
+  auto load_rec = [&](uint32_t tt) -> uint32_t {
+    return (tt < n_tiles && lane < 8) ? __ldg(reinterpret_cast<const uint32_t*>(v.tile_plan + tt) + lane) : 0u;
+  };
+  auto load_carry = [&](uint32_t rec) -> unsigned long long {
+    const uint32_t wt = __shfl_sync(FULL, rec, 7);
+    return (wt != STG_NO_TILE && lane < 3) ? __ldcg(v.tile_carry + (size_t)wt * 4 + lane) : 0ull;
+  };
+  uint32_t t = n_main + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  uint32_t rec_a = load_rec(t), rec_b = load_rec(t + warps);
+  unsigned long long cw_a = t < n_tiles ? load_carry(rec_a) : 0ull;
+  for (; t < n_tiles; t += warps) {
+    const uint32_t rec_c = load_rec(t + 2 * warps);
+    const unsigned long long cw_b = t + warps < n_tiles ? load_carry(rec_b) : 0ull;
+    const uint32_t recw = rec_a;
+    const unsigned long long x = cw_a;
+    rec_a = rec_b; rec_b = rec_c; cw_a = cw_b;
     const uint32_t gbase = __shfl_sync(FULL, recw, 0), i0 = __shfl_sync(FULL, recw, 1);
     const uint32_t stride = __shfl_sync(FULL, recw, 4), npos = __shfl_sync(FULL, recw, 5);
     const uint32_t tile_id = __shfl_sync(FULL, recw, 6), wait_tile = __shfl_sync(FULL, recw, 7);
@@ -1044,7 +1059,6 @@ __global__ void __launch_bounds__(256) cov_fill_kernel(DevBatchView v) {
     // state before the first position: from the nearest earlier sub-tile with events, advanced over the gap
     float c = 0.f, bs = 0.f;
     if (wait_tile != STG_NO_TILE && lane < 3) {
-      const unsigned long long x = __ldcg(v.tile_carry + (size_t)wait_tile * 4 + lane);
       c = __uint_as_float((uint32_t)x); bs = __uint_as_float((uint32_t)(x >> 32));
       const uint32_t first = tile_id - i0 / TW;
       const uint32_t wlast = (wait_tile - first) * TW + TW - 1;
