@@ -49,23 +49,37 @@ __device__ __forceinline__ uint32_t bundle_of_read(const DevBatchView& v, uint32
 // Walk the coverage intervals read n deposits, in the reference's order (rlink.cpp:144-219):
 // for every mate link i with pair_idx[i] <= n the union of both mates' segments with weight pair_count[i],
 // then the unpaired remainder on the read's own segments.
-template <class Emit>
-__device__ __forceinline__ void walk_read_intervals(const DevBatchView& v, uint32_t r0, uint32_t n, Emit&& emit) {
+// Malformed input (offsets that run backwards or past their arrays, a mate index outside the bundle) must not turn
+// into wild reads on the device: such reads / links are skipped — identically in the count and in the write pass —
+// and reported through v.err_flag; stg_run then fails with STG_EINVAL.  (The reference has no such checks: it would
+// index out of bounds.)
+#define STG_ERR_SEG_OFF 1u
+#define STG_ERR_PAIR_OFF 2u
+#define STG_ERR_PAIR_IDX 4u
+#define STG_ERR_JUNC_IDX 8u
+
+// CHECK = true in the count pass only: stg_run aborts on a raised flag before the write pass is launched.
+template <bool CHECK, class Emit>
+__device__ __forceinline__ void walk_read_intervals(const DevBatchView& v, uint32_t r0, uint32_t r1, uint32_t n, Emit&& emit) {
   if (v.r_flags[n] & STG_RF_UNITIG) return;  // super-read alignments add no coverage (rlink.cpp:16887)
   const uint32_t* __restrict__ ss = v.seg_start;
   const uint32_t* __restrict__ se = v.seg_end;
   const uint32_t rs0 = v.r_seg_off[n], rs1 = v.r_seg_off[n + 1];
+  if (CHECK && (rs1 < rs0 || (int64_t)rs1 > v.n_segs)) { atomicOr(v.err_flag, STG_ERR_SEG_OFF); return; }
   const int sno = (int)v.r_strand[n] + 1;
   float single_count = v.r_count[n];
   const uint32_t p0 = v.r_pair_off[n], p1 = v.r_pair_off[n + 1];
+  if (CHECK && (p1 < p0 || (int64_t)p1 > v.n_pairs)) { atomicOr(v.err_flag, STG_ERR_PAIR_OFF); return; }
   for (uint32_t k = p0; k < p1; k++) {
     const float pc = v.pair_cnt[k];
     single_count = __fsub_rn(single_count, pc);
     const int32_t pl = v.pair_idx[k];
     if (pl < 0) continue;
     const uint32_t np = r0 + (uint32_t)pl;
+    if (CHECK && np >= r1) { atomicOr(v.err_flag, STG_ERR_PAIR_IDX); continue; }
     if (np > n) continue;
     const uint32_t ps0 = v.r_seg_off[np], ps1 = v.r_seg_off[np + 1];
+    if (CHECK && (ps1 < ps0 || (int64_t)ps1 > v.n_segs)) { atomicOr(v.err_flag, STG_ERR_SEG_OFF); continue; }
     const int snop = (int)v.r_strand[np] + 1;
     int lane = sno;
     if (sno != snop) {
@@ -132,7 +146,7 @@ cudaError_t launch_junc_anchor(const DevBatchView& v, const KernelParams& p, cud
 // same few weights, so each round the warp groups its updates by (junction row, weight) with one 64-bit match and
 // issues ONE f64 atomic of count * w per group and counter (the product is exact: count <= 32, w has 24 bits).
 // --------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(STG_READ_BLOCK) expand_count_kernel(DevBatchView v) {
+__global__ void __launch_bounds__(STG_READ_BLOCK, 8) expand_count_kernel(DevBatchView v) {
   const int64_t n64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool live = n64 < v.n_reads;
@@ -141,18 +155,19 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) expand_count_kernel(DevBatchVi
   if (live) {
     b = bundle_of_read(v, n);
     uint32_t cnt = 0;
-    walk_read_intervals(v, v.b_read_off[b], n, [&](uint32_t, uint32_t, float, int) { cnt++; });
+    walk_read_intervals<true>(v, v.b_read_off[b], v.b_read_off[b + 1], n, [&](uint32_t, uint32_t, float, int) { cnt++; });
     v.r_ivl_cnt[n] = cnt;
     if (n64 == v.n_reads - 1) v.r_ivl_cnt[v.n_reads] = 0;
     s0 = v.r_seg_off[n]; nex = v.r_seg_off[n + 1] - s0;
+    if (v.r_seg_off[n + 1] < s0 || (int64_t)v.r_seg_off[n + 1] > v.n_segs) nex = 0;   // flagged by the walk above
   }
   const uint32_t max_nex = __reduce_max_sync(FULL, nex);
   if (max_nex < 2 || v.n_juncs == 0) return;
-  uint32_t j0 = 0;
+  uint32_t j0 = 0, nj = 0;
   float w = 0.f;
   const int32_t* __restrict__ rj = v.rjunc_idx + (s0 - n);
   if (nex >= 2) {
-    j0 = v.b_junc_off[b];
+    j0 = v.b_junc_off[b]; nj = v.b_junc_off[b + 1] - j0;
     w = v.r_count[n];
     if ((v.r_flags[n] & STG_RF_UNITIG) && w > 1.f) w = 1.f;
   }
@@ -171,7 +186,8 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) expand_count_kernel(DevBatchVi
         }
       }
       const int32_t jl = rj[i - 1];
-      if (jl >= 0) {
+      if (jl >= 0 && (uint32_t)jl >= nj) atomicOr(v.err_flag, STG_ERR_JUNC_IDX);
+      else if (jl >= 0) {
         const uint32_t j = j0 + (uint32_t)jl;
         const uint32_t anchor = v.junc_anchor[j];
         fl = lmax >= anchor; fr = rmax >= anchor;
@@ -203,7 +219,7 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) expand_write_kernel(DevBatchVi
   const uint32_t toff = v.b_tile_off[b];
   const uint32_t refstart = (uint32_t)v.b_start[b];
   const uint32_t len = v.b_len[b];
-  walk_read_intervals(v, r0, n, [&](uint32_t start, uint32_t end, float w, int lane) {
+  walk_read_intervals<false>(v, r0, 0u, n, [&](uint32_t start, uint32_t end, float w, int lane) {
     // cov_edge_add(lane, start-refstart, end-refstart+1, w): +w at index start-refstart+1, -w at end-refstart+2
     uint32_t ia = start - refstart + 1, ib = end - refstart + 2;
     if (start < refstart || ib >= len) { ia = 0; ib = 0; w = 0.f; }  // read outside its bundle: dropped (the

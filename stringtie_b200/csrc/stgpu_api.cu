@@ -395,7 +395,7 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
   AL(r_ivl_cnt, h->n_reads + 1);
   d->scan_capacity = std::max<int64_t>(std::max<int64_t>(h->n_reads + 1, v.n_tiles + 1), v.n_rounds + 1);
   AL(scan_partials, scan_partials_needed(d->scan_capacity));
-  AL(tile_carry, v.n_tiles * 4); AL(tile_ticket, 3); AL(deep_count, 2);
+  AL(tile_carry, v.n_tiles * 4); AL(tile_ticket, 3); AL(deep_count, 2); AL(err_flag, 1);
   AL(round_off, v.n_rounds + 1); AL(round_cur, v.n_rounds + 1);
   AL(tile_plan, v.n_tiles); AL(tile_evoff, v.n_tiles + 1); AL(tile_lastne, v.n_tiles); AL(junc_anchor, h->n_juncs);
   AL(bpcov, 3 * v.total_pos);
@@ -433,14 +433,25 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   }
   if (v.n_tiles) CK(ctx, cudaMemsetAsync(v.tile_carry, 0xff, sizeof(unsigned long long) * 4 * (size_t)v.n_tiles, st));
   CK(ctx, cudaMemsetAsync(v.tile_ticket, 0, 3 * sizeof(uint32_t), st));
+  CK(ctx, cudaMemsetAsync(v.err_flag, 0, sizeof(uint32_t), st));
   { Scope s(ctx, "junc_anchor", 1); CK(ctx, launch_junc_anchor(v, kp, st)); }
   { Scope s(ctx, "expand_count+junction_support", 1); CK(ctx, launch_expand_count(v, st)); }
   { Scope s(ctx, "scan_interval_offsets", 3); CK(ctx, launch_scan_exclusive_add(v.r_ivl_cnt, v.n_reads + 1, v.scan_partials, st)); }
   // the interval count sizes the next buffers: a 4-byte read-back (one of the two host syncs inside the stage)
   uint32_t n_ivl = 0;
   if (v.n_reads) {
+    uint32_t err = 0;
     CK(ctx, cudaMemcpyAsync(&n_ivl, v.r_ivl_cnt + v.n_reads, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemcpyAsync(&err, v.err_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(ctx, cudaStreamSynchronize(st));
+    if (err) {
+      std::string what;
+      if (err & 1u) what += " r_seg_off runs backwards or past n_segs;";
+      if (err & 2u) what += " r_pair_off runs backwards or past n_pairs;";
+      if (err & 4u) what += " pair_idx points outside its bundle;";
+      if (err & 8u) what += " rjunc_idx points outside its bundle's junction rows;";
+      return fail(ctx, STG_EINVAL, "malformed batch:" + what);
+    }
   }
   if (n_ivl >= 0x7fffffffu) return fail(ctx, STG_ERANGE, "batch deposits more than 2^31 coverage intervals; split it");
   v.n_ivl = n_ivl;

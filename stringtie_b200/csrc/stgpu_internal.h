@@ -55,6 +55,7 @@ struct DevBatchView {
   int64_t n_tiles;
   int64_t total_pos;           // b_gbase[n_bundles]
   // scratch
+  uint32_t* err_flag;          // [1] STG_ERR_* bits raised by the kernels on malformed input
   uint32_t* r_ivl_cnt;         // [n_reads+1] per-read interval count, then exclusive prefix (in place)
   int64_t n_ivl;               // filled after the count pass (host reads it back)
   uint4* ivl;                  // [n_ivl] {tile of the +w deposit, tile of the -w deposit,

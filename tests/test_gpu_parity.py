@@ -209,3 +209,25 @@ def test_c2_full_size(engine):
         assert np.array_equal(jp[k], ref_a7[k]), f"a7 {k} differs at full size"
     batch.free()
     engine.trim()
+
+
+def test_malformed_batches_are_rejected_not_executed(engine):
+    """Indices that point outside their bundle must come back as STG_EINVAL from stg_run (the kernels skip them instead
+    of reading out of bounds), and the context must stay usable."""
+    from stringtie_b200.engine import StgError
+    good = synth.make_batch(n_bundles=6, reads_per_bundle=300, seed=21)
+    for field, value, msg in (("pair_idx", 10 ** 6, "pair_idx"), ("rjunc_idx", 10 ** 6, "rjunc_idx")):
+        a = {k: v.copy() for k, v in good.items()}
+        assert a[field].size > 10
+        a[field][a[field].size // 2] = value
+        batch = engine.upload(a)
+        with pytest.raises(StgError, match=msg):
+            engine.run(batch)
+        batch.free()
+    a = {k: v.copy() for k, v in good.items()}
+    a["r_seg_off"][5] = a["r_seg_off"][4] - 1 if a["r_seg_off"][4] > 0 else a["r_seg_off"][6] + 7
+    batch = engine.upload(a)
+    with pytest.raises(StgError):
+        engine.run(batch)
+    batch.free()
+    check_batch(engine, good).free()   # the context still works
