@@ -734,31 +734,41 @@ __global__ void __launch_bounds__(256) deep_long_kernel(DevBatchView v) {
     const uint2* __restrict__ list = v.events2 + rec.z;
     const uint32_t qn = rec.w;
     float acc = 0.f;   // lane s < 3 accumulates strand lane s
-    uint2 cur = make_uint2(1u, 0u);
-    if ((uint32_t)lane < qn) cur = __ldcs(&list[lane]);
-    for (uint32_t off = 0; off < qn; off += 32) {
-      uint2 nxt = make_uint2(1u, 0u);
-      if (off + 32 + lane < qn) nxt = __ldcs(&list[off + 32 + lane]);
-      const float val = __uint_as_float(cur.y);
-      stage[wid][0][lane] = cur.x == 0u ? val : 0.f;
-      stage[wid][1][lane] = val;
-      stage[wid][2][lane] = cur.x == 2u ? val : 0.f;
-      __syncwarp();
-      if (lane < 3) {
-        const float4* sv = reinterpret_cast<const float4*>(stage[wid][lane]);
-        const uint32_t m = min(32u, qn - off);
-        if (m == 32u) {
+    // 4 groups of 32 events (1 KB) are in flight ahead of the chain: the list streams from HBM at ~1 us latency
+    // while one group costs the chain only ~150 cycles
+    constexpr int DEPTH = 4;
+    const uint2 pad = make_uint2(1u, 0u);      // +0.0 on lane 1: a no-op (no accumulator is ever -0)
+    uint2 cur[DEPTH];
+#pragma unroll
+    for (int g = 0; g < DEPTH; g++) cur[g] = (uint32_t)(g * 32 + lane) < qn ? __ldcs(&list[g * 32 + lane]) : pad;
+    for (uint32_t off = 0; off < qn; off += 32 * DEPTH) {
+      uint2 nxt[DEPTH];
+#pragma unroll
+      for (int g = 0; g < DEPTH; g++) {
+        const uint32_t e = off + 32 * DEPTH + g * 32 + lane;
+        nxt[g] = e < qn ? __ldcs(&list[e]) : pad;
+      }
+#pragma unroll
+      for (int g = 0; g < DEPTH; g++) {
+        if (off + g * 32 >= qn) break;
+        const float val = __uint_as_float(cur[g].y);
+        stage[wid][0][lane] = cur[g].x == 0u ? val : 0.f;
+        stage[wid][1][lane] = val;
+        stage[wid][2][lane] = cur[g].x == 2u ? val : 0.f;
+        __syncwarp();
+        if (lane < 3) {
+          // the padding of a partial group adds +0.0: harmless, so the chain is always the unrolled one
+          const float4* sv = reinterpret_cast<const float4*>(stage[wid][lane]);
 #pragma unroll
           for (int u = 0; u < 8; u++) {
             const float4 y = sv[u];
             acc = __fadd_rn(acc, y.x); acc = __fadd_rn(acc, y.y); acc = __fadd_rn(acc, y.z); acc = __fadd_rn(acc, y.w);
           }
-        } else {
-          for (uint32_t u = 0; u < m; u++) acc = __fadd_rn(acc, stage[wid][lane][u]);
         }
+        __syncwarp();
       }
-      __syncwarp();
-      cur = nxt;
+#pragma unroll
+      for (int g = 0; g < DEPTH; g++) cur[g] = nxt[g];
     }
     if (lane < 3) v.deep_d[(size_t)rec.x * (3 * STG_TILE_W) + lane * STG_TILE_W + rec.y] = acc;
   }
