@@ -45,6 +45,29 @@ void orc_junction_pass(const stg_packed_batch* B, const orc_params* P, int64_t b
                        double* o_nreads, double* o_nreads_good, double* o_left, double* o_right, double* o_mm,
                        int32_t* o_ej, int8_t* o_good, int8_t* o_good_strand);
 
+/* SURVEY.md §8 rows a8 + a9 (first half) — the read loop of build_graphs (rlink.cpp:14845-15127: per-read junction
+ * repair, un-pairing, add_read_to_group, fragment counting) and the merging of neighbouring groups (:15134-15164),
+ * for one bundle (oracle/stg_oracle_groups.c).  Inputs as for orc_junction_pass.  Everything in the result is
+ * malloc'ed by the callee; release with orc_groups_free. */
+typedef struct orc_groups_out {
+  int32_t n_reads, n_segs, n_pairs, n_juncs, n_groups, n_colors, color;
+  int32_t startgroup[3];          /* first group of every strand lane (-1: none) */
+  double num_fragments, frag_len; /* BundleData::num_fragments / frag_len */
+  /* reads after the loop: strand, pair links (CSR of the input), segments (CSR of the input), junction rows */
+  int8_t* r_strand; int32_t* pair_idx; uint32_t *seg_start, *seg_end; int32_t* rjunc;
+  /* junction table after the loop (appended rows included, re-sorted as the reference does) */
+  uint32_t *j_start, *j_end; int8_t* j_strand; double *j_nreads, *j_nreads_good, *j_left, *j_right, *j_nm, *j_mm;
+  /* groups: slot g == CGroup::grid; dead slots (merged away) have g_alive == 0 */
+  uint32_t *g_start, *g_end; int32_t *g_color, *g_next; float *g_cov_sum, *g_multi; int8_t* g_alive;
+  int32_t* merge;                 /* [n_groups] */
+  int32_t* eqcol;                 /* [n_colors] */
+  uint32_t* rg_off; int32_t* rg;  /* readgroup[n] = rg[rg_off[n] .. rg_off[n+1]) */
+} orc_groups_out;
+void orc_groups_bundle(const stg_packed_batch* B, const orc_params* P, int64_t b, const float* cov,
+                       const double* good_in, const double* left_in, const double* right_in, uint32_t bundledist,
+                       orc_groups_out* out);
+void orc_groups_free(orc_groups_out* out);
+
 /* work counters for the roofline: S = mate-merged coverage intervals emitted, J = junction-support updates */
 void orc_batch_stats(const stg_packed_batch* B, int64_t* L, int64_t* S, int64_t* J);
 

@@ -16,6 +16,7 @@
  * (hook inserted before rlink.cpp:14843 by oracle/Makefile) on generated batches and on the golden fixtures.
  */
 #include "stg_oracle.h"
+#include "stg_oracle_internal.h"
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -24,12 +25,6 @@
 #define ERROR_PERC 0.1    /* rlink.h:14 */
 #define CHI_WIN 100       /* rlink.h:17 */
 #define LONGINTRON 100000u /* rlink.h:31 */
-
-typedef struct {
-  uint32_t start, end;
-  int8_t strand, guide_match, consleft, consright;
-  double nreads, nreads_good, leftsupport, rightsupport, nm, mm;
-} junc_t;
 
 static int junc_cmp_end(const junc_t* a, const junc_t* b) { /* rlink.cpp:1236-1244 */
   if (a->end < b->end) return -1;
@@ -40,20 +35,20 @@ static int junc_cmp_end(const junc_t* a, const junc_t* b) { /* rlink.cpp:1236-12
 }
 
 /* gclib/GVec.hh:896-920 on an index array */
-static void qsort_ref(int32_t* list, const junc_t* J, int L, int R) {
+void orc_qsort_ref(int32_t* list, const junc_t* J, int L, int R, int (*cmp)(const junc_t*, const junc_t*)) {
   int I, Jx;
   do {
     I = L; Jx = R;
     const junc_t* P = &J[list[L + ((R - L) >> 1)]];
     do {
-      while (junc_cmp_end(&J[list[I]], P) < 0) I++;
-      while (junc_cmp_end(&J[list[Jx]], P) > 0) Jx--;
+      while (cmp(&J[list[I]], P) < 0) I++;
+      while (cmp(&J[list[Jx]], P) > 0) Jx--;
       if (I <= Jx) {
         int32_t t = list[I]; list[I] = list[Jx]; list[Jx] = t;
         I++; Jx--;
       }
     } while (I <= Jx);
-    if (L < Jx) qsort_ref(list, J, L, Jx);
+    if (L < Jx) orc_qsort_ref(list, J, L, Jx, cmp);
     L = I;
   } while (I < R);
 }
@@ -74,8 +69,8 @@ static int ok_to_demote(const junc_t* cur, const junc_t* better) { /* rlink.cpp:
 }
 
 /* rlink.cpp:13967-14070 for !eonly, !longreads; returns the verdict, *strand_out = jd.strand afterwards */
-static int good_junc(const junc_t* jd_in, int64_t refstart, const float* cov, int64_t len, int junctionthr,
-                     int8_t* strand_out) {
+int orc_good_junc(const junc_t* jd_in, int64_t refstart, const float* cov, int64_t len, int junctionthr,
+                  int8_t* strand_out) {
   junc_t jd = *jd_in;
   int res = 1;
   if (jd.guide_match) goto done;
@@ -113,19 +108,20 @@ done:
   return res;
 }
 
-void orc_junction_pass(const stg_packed_batch* B, const orc_params* P, int64_t b, const float* cov,
-                       const double* good_in, const double* left_in, const double* right_in, int8_t* o_strand,
-                       double* o_nreads, double* o_nreads_good, double* o_left, double* o_right, double* o_mm,
-                       int32_t* o_ej, int8_t* o_good, int8_t* o_good_strand) {
+/* the pass itself: returns the junction rows (malloc'ed, n of them, with `extra` spare slots) and the ejunction order */
+void orc_junction_state(const stg_packed_batch* B, const orc_params* P, int64_t b, const float* cov,
+                        const double* good_in, const double* left_in, const double* right_in, int extra,
+                        junc_t** J_out, int32_t** ej_out, int* n_out) {
   const uint32_t j0 = B->b_junc_off[b];
   const int n = (int)(B->b_junc_off[b + 1] - j0);
+  *J_out = NULL; *ej_out = NULL; *n_out = n;
   if (n == 0) return;
   const int64_t refstart = B->b_start[b];
   const int64_t len = orc_bundle_len(B, b);
   const uint32_t junctionsupport = P->junctionsupport, sserror = 25; /* stringtie.cpp:141 */
   const int junctionthr = P->junctionthr;
-  junc_t* J = (junc_t*)malloc(sizeof(junc_t) * (size_t)n);
-  int32_t* ej = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+  junc_t* J = (junc_t*)malloc(sizeof(junc_t) * (size_t)(n + extra));
+  int32_t* ej = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n + extra));
   for (int i = 0; i < n; i++) {
     J[i].start = B->j_start[j0 + i]; J[i].end = B->j_end[j0 + i];
     J[i].strand = B->j_strand[j0 + i]; J[i].guide_match = B->j_guide_match[j0 + i];
@@ -134,7 +130,7 @@ void orc_junction_pass(const stg_packed_batch* B, const orc_params* P, int64_t b
     J[i].nreads_good = good_in[i]; J[i].leftsupport = left_in[i]; J[i].rightsupport = right_in[i];
     ej[i] = i;
   }
-  qsort_ref(ej, J, 0, n - 1); /* GList(junction) copy, then setSorted(juncCmpEnd): rlink.cpp:14387-14389 */
+  orc_qsort_ref(ej, J, 0, n - 1, junc_cmp_end); /* GList(junction) copy, then setSorted(juncCmpEnd): rlink.cpp:14387-14389 */
 #define EJ(k) J[ej[k]]
 
   /* ---- per-start / per-end support: rlink.cpp:14391-14531 (gseq == NULL, checkfeat == false, !mixedMode) ---- */
@@ -299,13 +295,26 @@ void orc_junction_pass(const stg_packed_batch* B, const orc_params* P, int64_t b
     }
   }
 
+#undef EJ
+  *J_out = J; *ej_out = ej;
+}
+
+void orc_junction_pass(const stg_packed_batch* B, const orc_params* P, int64_t b, const float* cov,
+                       const double* good_in, const double* left_in, const double* right_in, int8_t* o_strand,
+                       double* o_nreads, double* o_nreads_good, double* o_left, double* o_right, double* o_mm,
+                       int32_t* o_ej, int8_t* o_good, int8_t* o_good_strand) {
+  junc_t* J; int32_t* ej; int n;
+  orc_junction_state(B, P, b, cov, good_in, left_in, right_in, 0, &J, &ej, &n);
+  if (n == 0) return;
+  const int64_t refstart = B->b_start[b];
+  const int64_t len = orc_bundle_len(B, b);
+  const int junctionthr = P->junctionthr;
   for (int i = 0; i < n; i++) {
     o_strand[i] = J[i].strand; o_nreads[i] = J[i].nreads; o_nreads_good[i] = J[i].nreads_good;
     o_left[i] = J[i].leftsupport; o_right[i] = J[i].rightsupport; o_mm[i] = J[i].mm;
     o_ej[i] = ej[i];
     o_good[i] = -1; o_good_strand[i] = J[i].strand;
-    if (J[i].strand) o_good[i] = (int8_t)good_junc(&J[i], refstart, cov, len, junctionthr, &o_good_strand[i]);
+    if (J[i].strand) o_good[i] = (int8_t)orc_good_junc(&J[i], refstart, cov, len, junctionthr, &o_good_strand[i]);
   }
-#undef EJ
   free(J); free(ej);
 }

@@ -120,3 +120,72 @@ def junction_pass(arrays: Dict[str, np.ndarray], cov: np.ndarray, cov_off: np.nd
                             at(out["mm"], j0, c_f64p), at(out["ej"], j0, i32p), at(out["good"], j0, i8p),
                             at(out["good_strand"], j0, i8p))
     return out
+
+
+class OrcGroupsOut(C.Structure):
+    _fields_ = ([(k, C.c_int32) for k in ("n_reads", "n_segs", "n_pairs", "n_juncs", "n_groups", "n_colors", "color")] +
+                [("startgroup", C.c_int32 * 3), ("num_fragments", C.c_double), ("frag_len", C.c_double)] +
+                [("r_strand", C.POINTER(C.c_int8)), ("pair_idx", C.POINTER(C.c_int32)),
+                 ("seg_start", C.POINTER(C.c_uint32)), ("seg_end", C.POINTER(C.c_uint32)), ("rjunc", C.POINTER(C.c_int32)),
+                 ("j_start", C.POINTER(C.c_uint32)), ("j_end", C.POINTER(C.c_uint32)), ("j_strand", C.POINTER(C.c_int8)),
+                 ("j_nreads", c_f64p), ("j_nreads_good", c_f64p), ("j_left", c_f64p), ("j_right", c_f64p),
+                 ("j_nm", c_f64p), ("j_mm", c_f64p),
+                 ("g_start", C.POINTER(C.c_uint32)), ("g_end", C.POINTER(C.c_uint32)), ("g_color", C.POINTER(C.c_int32)),
+                 ("g_next", C.POINTER(C.c_int32)), ("g_cov_sum", c_f32p), ("g_multi", c_f32p),
+                 ("g_alive", C.POINTER(C.c_int8)), ("merge", C.POINTER(C.c_int32)), ("eqcol", C.POINTER(C.c_int32)),
+                 ("rg_off", C.POINTER(C.c_uint32)), ("rg", C.POINTER(C.c_int32))])
+
+
+def _np(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+def groups(arrays: Dict[str, np.ndarray], cov: np.ndarray, cov_off: np.ndarray, good: np.ndarray, left: np.ndarray,
+           right: np.ndarray, bundles=None, junctionsupport: int = 10, junctionthr: int = 1, bundledist: int = 50):
+    """SURVEY §8 rows a8 + a9 (first half) per bundle (oracle/stg_oracle_groups.c): list of dicts, one per bundle."""
+    L = lib()
+    if not hasattr(L, "_gr_ready"):
+        L.orc_groups_bundle.argtypes = [C.POINTER(StgPackedBatch), C.POINTER(OrcParams), C.c_int64, c_f32p, c_f64p, c_f64p,
+                                        c_f64p, C.c_uint32, C.POINTER(OrcGroupsOut)]
+        L.orc_groups_bundle.restype = None
+        L.orc_groups_free.argtypes = [C.POINTER(OrcGroupsOut)]
+        L.orc_groups_free.restype = None
+        L._gr_ready = True
+    pb, keep = make_packed(arrays)
+    P = OrcParams(junctionsupport, junctionthr, 0)
+    joff = arrays["b_junc_off"].astype(np.int64)
+    good = np.ascontiguousarray(good, dtype=np.float64)
+    left = np.ascontiguousarray(left, dtype=np.float64)
+    right = np.ascontiguousarray(right, dtype=np.float64)
+
+    def at(a, o, t):
+        return C.cast(a.ctypes.data + o * a.itemsize, t)
+
+    res = []
+    for b in (range(int(pb.n_bundles)) if bundles is None else bundles):
+        o = OrcGroupsOut()
+        j0 = int(joff[b])
+        L.orc_groups_bundle(C.byref(pb), C.byref(P), b, at(cov, int(cov_off[b]), c_f32p), at(good, j0, c_f64p),
+                            at(left, j0, c_f64p), at(right, j0, c_f64p), bundledist, C.byref(o))
+        nintr = o.n_segs - o.n_reads
+        d = {"startgroup": np.array(list(o.startgroup), dtype=np.int32), "num_fragments": o.num_fragments,
+             "frag_len": o.frag_len, "color": o.color,
+             "r_strand": _np(o.r_strand, o.n_reads, np.int8), "pair_idx": _np(o.pair_idx, o.n_pairs, np.int32),
+             "seg_start": _np(o.seg_start, o.n_segs, np.uint32), "seg_end": _np(o.seg_end, o.n_segs, np.uint32),
+             "rjunc": _np(o.rjunc, nintr, np.int32),
+             "j_start": _np(o.j_start, o.n_juncs, np.uint32), "j_end": _np(o.j_end, o.n_juncs, np.uint32),
+             "j_strand": _np(o.j_strand, o.n_juncs, np.int8), "j_nreads": _np(o.j_nreads, o.n_juncs, np.float64),
+             "j_nreads_good": _np(o.j_nreads_good, o.n_juncs, np.float64), "j_left": _np(o.j_left, o.n_juncs, np.float64),
+             "j_right": _np(o.j_right, o.n_juncs, np.float64), "j_nm": _np(o.j_nm, o.n_juncs, np.float64),
+             "j_mm": _np(o.j_mm, o.n_juncs, np.float64),
+             "g_alive": _np(o.g_alive, o.n_groups, np.int8), "g_start": _np(o.g_start, o.n_groups, np.uint32),
+             "g_end": _np(o.g_end, o.n_groups, np.uint32), "g_color": _np(o.g_color, o.n_groups, np.int32),
+             "g_next": _np(o.g_next, o.n_groups, np.int32), "g_cov": _np(o.g_cov_sum, o.n_groups, np.float32),
+             "g_multi": _np(o.g_multi, o.n_groups, np.float32), "merge": _np(o.merge, o.n_groups, np.int32),
+             "eqcol": _np(o.eqcol, o.n_colors, np.int32), "rg_off": _np(o.rg_off, o.n_reads + 1, np.uint32),
+             "rg": _np(o.rg, int(o.rg_off[o.n_reads]) if o.n_reads else 0, np.int32)}
+        L.orc_groups_free(C.byref(o))
+        res.append(d)
+    return res

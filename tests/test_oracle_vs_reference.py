@@ -56,6 +56,20 @@ def test_jitter_golden_exercises_the_demotion_pass():
     assert (g["a7_j_mm"] < 0).sum() >= 10 and (g["a7_j_good"] == 0).sum() >= 10
 
 
+def _check_a9(arrays, ref):
+    """Rows a8 + a9 (first half): state after the read loop of build_graphs and the merging of neighbouring groups
+    (dumped from inside the reference, before rlink.cpp:15194): reads, junction table, groups, colours, readgroup,
+    fragment counters — exact equality."""
+    from tests import a9_util
+    cov, off, good, left, right = orc.run(arrays)
+    a9_util.assert_same(orc.groups(arrays, cov, off, good, left, right), a9_util.split_reference_dump(ref, arrays))
+
+
+def test_oracle_read_loop_and_groups_match_golden(golden):
+    from stringtie_b200.stgb import input_view
+    _check_a9(input_view(golden), golden)
+
+
 def test_golden_has_inexact_weights(golden):
     # the fixtures must exercise order-dependent float accumulation (NH=3,5,6 -> 1/3, 1/5, 1/6)
     assert np.isin(golden["r_nh"], [3, 5, 6]).any()
@@ -70,10 +84,26 @@ def test_oracle_matches_live_reference(tmp_path, case):
         a = synth.make_adversarial(seed=int(case[-1]) + 10, n_bundles=14)
     src, dst = str(tmp_path / "in.stgb"), str(tmp_path / "out.stgb")
     write_stgb(src, a)
-    subprocess.check_call([REF_HOT, src, "--dump", dst, "--a7"], stdout=subprocess.DEVNULL)
+    subprocess.check_call([REF_HOT, src, "--dump", dst, "--a9"], stdout=subprocess.DEVNULL)
     ref = read_stgb(dst)
     _check(a, ref)
     _check_a7(a, ref)
+    _check_a9(a, ref)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_HOT), reason="reference harness not built (oracle/_ref is built from /root/reference)")
+@pytest.mark.parametrize("seed", [38, 43])
+def test_oracle_read_loop_appended_junctions(tmp_path, seed):
+    """Seeds on which the repair appends a junction row and the table is re-sorted with the reference's quicksort."""
+    a = synth.make_adversarial(seed=seed, n_bundles=10, max_reads=250)
+    rng = np.random.default_rng(seed)
+    a["j_nm"] = np.where(rng.random(a["j_nm"].size) < 0.5, a["j_nreads"], a["j_nm"])
+    src, dst = str(tmp_path / "in.stgb"), str(tmp_path / "out.stgb")
+    write_stgb(src, a)
+    subprocess.check_call([REF_HOT, src, "--dump", dst, "--a9"], stdout=subprocess.DEVNULL)
+    ref = read_stgb(dst)
+    assert ref["a9_j_start"].size > a["j_start"].size
+    _check_a9(a, ref)
 
 
 def test_get_cov_against_bruteforce(golden):
