@@ -206,11 +206,14 @@ def main():
             totals_dev.copy_(torch.from_numpy(np.array([t[:, 1].sum(), float(n_reads), float(n_bundles)])))
             dist.all_reduce(totals_dev)
 
+    # clocks / throttle reasons are sampled under this workload: the sampler (nvidia-smi -lms 100) needs a few hundred
+    # ms to deliver its first line on a multi-GPU box, longer than the timed region, so it starts before the warm-up
+    # and, if it still has too few lines afterwards, untimed passes of the same workload keep the load up for it
+    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step_resident()
     eng.set_profiling(True)
     barrier()
-    sampler = ClockSampler(local_rank)
     l0 = eng.launch_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ktimes = {}
@@ -222,9 +225,15 @@ def main():
             ktimes.setdefault(name, []).append(ms)
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop()
     launches = eng.launch_counter() - l0
     ms_total = ev0.elapsed_time(ev1)
+    eng.set_profiling(False)
+    t_extra, n_extra = time.perf_counter(), 0
+    while len(sampler.rows) < 5 and time.perf_counter() - t_extra < 3.0:   # untimed: same kernels, for the clock sampler
+        eng.run(batch, sync=True)                                           # (no collective: ranks loop independently)
+        n_extra += 1
+    clocks = sampler.stop()
+    clocks["window"] = "warm-up + timed passes" + (f" + {n_extra} untimed passes of the same workload" if n_extra else "")
     if dist is not None:
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
