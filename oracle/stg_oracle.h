@@ -62,6 +62,14 @@ typedef struct orc_groups_out {
   int32_t* merge;                 /* [n_groups] */
   int32_t* eqcol;                 /* [n_colors] */
   uint32_t* rg_off; int32_t* rg;  /* readgroup[n] = rg[rg_off[n] .. rg_off[n+1]) */
+  /* second half of a9 — colour pass (rlink.cpp:15196-15299) and bundle creation (:15340-15427) */
+  int32_t* g_color2;              /* [n_groups] CGroup::color after both passes */
+  float* g_neg_prop;              /* [n_groups] */
+  int32_t *eqcol2, *eqnegcol, *eqposcol;   /* [n_colors] equalcolor after the passes, eqnegcol, eqposcol */
+  int32_t bun_off[4], bn_off[4];  /* bundles / bundlenodes of strand lane s: [off[s], off[s+1]) */
+  int32_t *bun_len, *bun_start, *bun_last; float *bun_cov, *bun_multi;        /* CBundle, bundle.h:260-268 */
+  uint32_t *bn_start, *bn_end; float* bn_cov; int32_t* bn_next;                /* CBundlenode, rlink.h:56-62 */
+  int32_t* group2bundle;          /* [3 * n_groups] */
 } orc_groups_out;
 void orc_groups_bundle(const stg_packed_batch* B, const orc_params* P, int64_t b, const float* cov,
                        const double* good_in, const double* left_in, const double* right_in, uint32_t bundledist,

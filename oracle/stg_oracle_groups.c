@@ -7,6 +7,8 @@
  *   fragment counting                                          rlink.cpp:15105-15116
  *   re-sort of the junction table after appended rows          rlink.cpp:15122-15125
  *   merging of neighbouring groups (bundledist)                rlink.cpp:15134-15164
+ *   colour pass over the three lanes (set_strandcol, neg_prop) rlink.cpp:15196-15299, 1028-1056, 984-1026
+ *   bundles and bundlenodes (create_bundle, add_group_to_bundle) rlink.cpp:15340-15427, 1058-1095
  * The three are ONE sequential loop in the reference (repair read n -> group read n -> count it), and they share
  * state both ways (merge_read_to_group itself un-pairs reads, rlink.cpp:1383-1389), so they are restated together.
  * Pointers become indices: group g = slot in the group arrays (== CGroup::grid at creation), junction = row.
@@ -349,12 +351,216 @@ static int junc_default_cmp(const junc_t* a, const junc_t* b) { /* GList::Defaul
   return 0;
 }
 
+
+/* ---- second half of a9: colours across the three lanes, then bundles ---------------------------------------- */
+static int get_min_start(const st_t* S, const int* cur) { /* rlink.cpp:984-1026 */
+  if (cur[0] != -1) {
+    if (cur[1] != -1) {
+      if (cur[2] != -1) {
+        int two = S->g_start[cur[0]] < S->g_start[cur[1]] ? 0 : 1;
+        return S->g_start[cur[two]] < S->g_start[cur[2]] ? two : 2;
+      }
+      return S->g_start[cur[0]] < S->g_start[cur[1]] ? 0 : 1;
+    }
+    if (cur[2] != -1) return S->g_start[cur[0]] < S->g_start[cur[2]] ? 0 : 2;
+    return 0;
+  }
+  if (cur[1] != -1) {
+    if (cur[2] != -1) return S->g_start[cur[1]] < S->g_start[cur[2]] ? 1 : 2;
+    return 1;
+  }
+  return 2;
+}
+
+/* rlink.cpp:1028-1056: U = the unstranded group, G = the stranded one, grcol = G's colour */
+static void set_strandcol(int32_t* color, int U, int G, int grcol, int32_t* eqcol, int32_t* equalcolor) {
+  int zerocol = eqcol[color[U]];
+  if (zerocol > -1) {
+    while (eqcol[zerocol] != -1 && eqcol[zerocol] != zerocol) zerocol = eqcol[zerocol];
+    int tmpcol = zerocol;
+    while (equalcolor[zerocol] != zerocol) zerocol = equalcolor[zerocol];
+    eqcol[color[U]] = zerocol;
+    eqcol[tmpcol] = zerocol;
+    if (zerocol < grcol) { equalcolor[grcol] = zerocol; color[G] = zerocol; }
+    else if (grcol < zerocol) { equalcolor[zerocol] = grcol; eqcol[color[U]] = grcol; }
+  } else eqcol[color[U]] = grcol;
+}
+
+typedef struct { int n, cap; int32_t *len, *start, *last; float *cov, *multi; } bun_t;
+typedef struct { int n, cap; uint32_t *s, *e; float* cov; int32_t* next; } bn_t;
+
+static int bn_add(bn_t* N, uint32_t s, uint32_t e, float cov) {
+  if (N->n == N->cap) {
+    N->cap = N->cap * 2 + 16;
+    N->s = (uint32_t*)realloc(N->s, 4 * (size_t)N->cap); N->e = (uint32_t*)realloc(N->e, 4 * (size_t)N->cap);
+    N->cov = (float*)realloc(N->cov, 4 * (size_t)N->cap); N->next = (int32_t*)realloc(N->next, 4 * (size_t)N->cap);
+  }
+  N->s[N->n] = s; N->e[N->n] = e; N->cov[N->n] = cov; N->next[N->n] = -1;
+  return N->n++;
+}
+
+static int create_bundle(const st_t* S, bun_t* Bn, int g, bn_t* N) { /* rlink.cpp:1083-1095 */
+  int bid = bn_add(N, S->g_start[g], S->g_end[g], S->g_cov[g]);
+  if (Bn->n == Bn->cap) {
+    Bn->cap = Bn->cap * 2 + 16;
+    Bn->len = (int32_t*)realloc(Bn->len, 4 * (size_t)Bn->cap); Bn->start = (int32_t*)realloc(Bn->start, 4 * (size_t)Bn->cap);
+    Bn->last = (int32_t*)realloc(Bn->last, 4 * (size_t)Bn->cap); Bn->cov = (float*)realloc(Bn->cov, 4 * (size_t)Bn->cap);
+    Bn->multi = (float*)realloc(Bn->multi, 4 * (size_t)Bn->cap);
+  }
+  int bno = Bn->n++;
+  Bn->len[bno] = (int32_t)(S->g_end[g] - S->g_start[g] + 1); Bn->cov[bno] = S->g_cov[g]; Bn->multi[bno] = S->g_multi[g];
+  Bn->start[bno] = bid; Bn->last[bno] = bid;
+  return bno;
+}
+
+static void add_group_to_bundle(const st_t* S, int g, bun_t* Bn, int bno, bn_t* N, uint32_t localdist) { /* rlink.cpp:1058-1081 */
+  int last = Bn->last[bno];
+  if (S->g_start[g] > N->e[last] + localdist) {
+    int bid = bn_add(N, S->g_start[g], S->g_end[g], S->g_cov[g]);
+    N->next[last] = bid;
+    Bn->last[bno] = bid;
+    Bn->len[bno] += (int32_t)(S->g_end[g] - S->g_start[g] + 1);
+    Bn->cov[bno] += S->g_cov[g];
+    Bn->multi[bno] += S->g_multi[g];
+  } else {
+    if (N->e[last] < S->g_end[g]) { Bn->len[bno] += (int32_t)(S->g_end[g] - N->e[last]); N->e[last] = S->g_end[g]; }
+    Bn->cov[bno] += S->g_cov[g];
+    Bn->multi[bno] += S->g_multi[g];
+    N->cov[last] += S->g_cov[g];
+  }
+}
+
+static void second_half(st_t* S, orc_groups_out* o) {
+  const int ng = S->ng, nc = S->ncol;
+  const uint32_t bd = S->bundledist;
+  int32_t* color = (int32_t*)malloc(4 * ((size_t)ng + 1)); memcpy(color, S->g_color, 4 * (size_t)ng);
+  int32_t* eq = (int32_t*)malloc(4 * ((size_t)nc + 1)); memcpy(eq, S->eqcol, 4 * (size_t)nc);
+  int32_t* eqneg = (int32_t*)malloc(4 * ((size_t)nc + 1)); int32_t* eqpos = (int32_t*)malloc(4 * ((size_t)nc + 1));
+  for (int c = 0; c < nc; c++) { eqneg[c] = -1; eqpos[c] = -1; }
+  float* negp = (float*)calloc((size_t)ng + 1, sizeof(float));
+#define GLEN(g) (S->g_end[g] - S->g_start[g] + 1u)
+#define OVL(U, G, acc) do { \
+    uint32_t maxstart = S->g_start[U] > S->g_start[G] ? S->g_start[U] : S->g_start[G]; \
+    uint32_t minend = S->g_end[U] < S->g_end[G] ? S->g_end[U] : S->g_end[G]; \
+    if (minend < maxstart) minend = maxstart; \
+    acc += S->g_cov[G] * (float)(minend - maxstart + 1u) / (float)GLEN(G); } while (0)
+  int cur[3], prev[3] = {-1, -1, -1};
+  for (int i = 0; i < 3; i++) cur[i] = S->startg[i];
+  while (cur[0] != -1 || cur[1] != -1 || cur[2] != -1) {
+    const int nextgr = get_min_start(S, cur);
+    const int g = cur[nextgr];
+    int grcol = color[g];
+    while (eq[grcol] != grcol) grcol = eq[grcol];
+    color[g] = grcol;
+    if (nextgr == 1) {
+      if (prev[0] != -1 && S->g_start[g] <= S->g_end[prev[0]] + bd) {
+        set_strandcol(color, g, prev[0], color[prev[0]], eqneg, eq);
+        OVL(g, prev[0], negp[g]);
+      }
+      while (cur[0] != -1 && S->g_start[g] <= S->g_end[cur[0]] + bd && S->g_start[cur[0]] <= S->g_end[g] + bd) {
+        int c0 = color[cur[0]];
+        while (eq[c0] != c0) c0 = eq[c0];
+        color[cur[0]] = c0;
+        negp[cur[0]] = 1;
+        set_strandcol(color, g, cur[0], color[cur[0]], eqneg, eq);
+        OVL(g, cur[0], negp[g]);
+        prev[0] = cur[0];
+        cur[0] = S->g_next[cur[0]];
+      }
+      float pos_prop = 0;
+      if (prev[2] != -1 && S->g_start[g] <= S->g_end[prev[2]] + bd) {
+        set_strandcol(color, g, prev[2], color[prev[2]], eqpos, eq);
+        if (negp[g]) OVL(g, prev[2], pos_prop);
+      }
+      while (cur[2] != -1 && S->g_start[g] <= S->g_end[cur[2]] + bd && S->g_start[cur[2]] <= S->g_end[g] + bd) {
+        int c2 = color[cur[2]];
+        while (eq[c2] != c2) c2 = eq[c2];
+        color[cur[2]] = c2;
+        set_strandcol(color, g, cur[2], color[cur[2]], eqpos, eq);
+        if (negp[g]) OVL(g, cur[2], pos_prop);
+        prev[2] = cur[2];
+        cur[2] = S->g_next[cur[2]];
+      }
+      if (pos_prop) negp[g] /= (negp[g] + pos_prop);
+      else if (negp[g]) negp[g] = 1;
+    } else if (nextgr == 0) negp[g] = 1;
+    prev[nextgr] = g;
+    cur[nextgr] = S->g_next[g];
+  }
+
+  bun_t Bn[3]; bn_t N[3];
+  memset(Bn, 0, sizeof(Bn)); memset(N, 0, sizeof(N));
+  int32_t* g2b = (int32_t*)malloc(4 * (3 * (size_t)ng + 1));
+  for (int k = 0; k < 3 * ng; k++) g2b[k] = -1;
+  int32_t* bundlecol = (int32_t*)malloc(4 * ((size_t)nc + 1));
+  for (int c = 0; c < nc; c++) bundlecol[c] = -1;
+  for (int i = 0; i < 3; i++) cur[i] = S->startg[i];
+  while (cur[0] != -1 || cur[1] != -1 || cur[2] != -1) {
+    const int nextgr = get_min_start(S, cur);
+    const int g = cur[nextgr];
+    int grcol = color[g];
+    while (eq[grcol] != grcol) grcol = eq[grcol];
+    color[g] = grcol;
+    if (nextgr == 0 || nextgr == 2 || (nextgr == 1 && eqneg[grcol] == -1 && eqpos[grcol] == -1)) {
+      int bno = bundlecol[grcol];
+      if (bno > -1) add_group_to_bundle(S, g, &Bn[nextgr], bno, &N[nextgr], bd);
+      else { bno = create_bundle(S, &Bn[nextgr], g, &N[nextgr]); bundlecol[grcol] = bno; }
+      g2b[nextgr * ng + g] = Bn[nextgr].last[bno];
+    } else {
+      if (eqneg[grcol] != -1) {
+        int negcol = eqneg[grcol];
+        while (eq[negcol] != negcol) negcol = eq[negcol];
+        int bno = bundlecol[negcol];
+        if (bno > -1) add_group_to_bundle(S, g, &Bn[0], bno, &N[0], bd);
+        else { bno = create_bundle(S, &Bn[0], g, &N[0]); bundlecol[negcol] = bno; }
+        g2b[0 * ng + g] = Bn[0].last[bno];
+      }
+      if (eqpos[grcol] != -1) {
+        int poscol = eqpos[grcol];
+        while (eq[poscol] != poscol) poscol = eq[poscol];
+        int bno = bundlecol[poscol];
+        if (bno > -1) add_group_to_bundle(S, g, &Bn[2], bno, &N[2], bd);
+        else { bno = create_bundle(S, &Bn[2], g, &N[2]); bundlecol[poscol] = bno; }
+        g2b[2 * ng + g] = Bn[2].last[bno];
+      }
+    }
+    cur[nextgr] = S->g_next[g];
+  }
+#undef OVL
+#undef GLEN
+  o->g_color2 = color; o->g_neg_prop = negp; o->eqcol2 = eq; o->eqnegcol = eqneg; o->eqposcol = eqpos; o->group2bundle = g2b;
+  int nbun = Bn[0].n + Bn[1].n + Bn[2].n, nbn = N[0].n + N[1].n + N[2].n;
+  o->bun_len = (int32_t*)malloc(4 * ((size_t)nbun + 1)); o->bun_start = (int32_t*)malloc(4 * ((size_t)nbun + 1));
+  o->bun_last = (int32_t*)malloc(4 * ((size_t)nbun + 1)); o->bun_cov = (float*)malloc(4 * ((size_t)nbun + 1));
+  o->bun_multi = (float*)malloc(4 * ((size_t)nbun + 1));
+  o->bn_start = (uint32_t*)malloc(4 * ((size_t)nbn + 1)); o->bn_end = (uint32_t*)malloc(4 * ((size_t)nbn + 1));
+  o->bn_cov = (float*)malloc(4 * ((size_t)nbn + 1)); o->bn_next = (int32_t*)malloc(4 * ((size_t)nbn + 1));
+  int ob = 0, on = 0;
+  for (int s = 0; s < 3; s++) {
+    o->bun_off[s] = ob; o->bn_off[s] = on;
+    for (int k = 0; k < Bn[s].n; k++, ob++) {
+      o->bun_len[ob] = Bn[s].len[k]; o->bun_start[ob] = Bn[s].start[k]; o->bun_last[ob] = Bn[s].last[k];
+      o->bun_cov[ob] = Bn[s].cov[k]; o->bun_multi[ob] = Bn[s].multi[k];
+    }
+    for (int k = 0; k < N[s].n; k++, on++) {
+      o->bn_start[on] = N[s].s[k]; o->bn_end[on] = N[s].e[k]; o->bn_cov[on] = N[s].cov[k]; o->bn_next[on] = N[s].next[k];
+    }
+    free(Bn[s].len); free(Bn[s].start); free(Bn[s].last); free(Bn[s].cov); free(Bn[s].multi);
+    free(N[s].s); free(N[s].e); free(N[s].cov); free(N[s].next);
+  }
+  o->bun_off[3] = ob; o->bn_off[3] = on;
+  free(bundlecol);
+}
+
 void orc_groups_free(orc_groups_out* o) {
   free(o->r_strand); free(o->pair_idx); free(o->seg_start); free(o->seg_end); free(o->rjunc);
   free(o->j_start); free(o->j_end); free(o->j_strand); free(o->j_nreads); free(o->j_nreads_good); free(o->j_left);
   free(o->j_right); free(o->j_nm); free(o->j_mm);
   free(o->g_start); free(o->g_end); free(o->g_color); free(o->g_next); free(o->g_cov_sum); free(o->g_multi);
   free(o->g_alive); free(o->merge); free(o->eqcol); free(o->rg_off); free(o->rg);
+  free(o->g_color2); free(o->g_neg_prop); free(o->eqcol2); free(o->eqnegcol); free(o->eqposcol);
+  free(o->bun_len); free(o->bun_start); free(o->bun_last); free(o->bun_cov); free(o->bun_multi);
+  free(o->bn_start); free(o->bn_end); free(o->bn_cov); free(o->bn_next); free(o->group2bundle);
   memset(o, 0, sizeof(*o));
 }
 
@@ -586,6 +792,7 @@ void orc_groups_bundle(const stg_packed_batch* B, const orc_params* P, int64_t b
   o->rg = (int32_t*)malloc(4 * ((size_t)tot + 1));
   for (int n = 0; n < nr; n++) { memcpy(o->rg + o->rg_off[n], S.rg[n], 4 * (size_t)S.rgn[n]); free(S.rg[n]); }
   o->num_fragments = num_fragments; o->frag_len = frag_len; o->color = color;
+  second_half(&S, o);
   free(S.rg); free(S.rgn); free(S.rgcap); free(S.J); free(S.ej); free(perm); free(inv); free(grid);
 #undef EJ
 }

@@ -3,7 +3,7 @@ build_graphs (arrays a9_* written by oracle/ref_hook.cpp) and the comparison wit
 import numpy as np
 
 J_KEYS = ("start", "end", "strand", "nreads", "nreads_good", "left", "right", "nm", "mm")
-GROUP_KEYS = ("g_start", "g_end", "g_color", "g_next", "g_cov", "g_multi")
+GROUP_KEYS = ("g_start", "g_end", "g_color", "g_next", "g_cov", "g_multi", "g_color2", "g_neg_prop")
 
 
 def split_reference_dump(ref, a):
@@ -28,6 +28,17 @@ def split_reference_dump(ref, a):
              "rg_off": ref["a9_rg_off"][r0:r1 + 1] - ref["a9_rg_off"][r0], "rg": ref["a9_rg"][rg0:rg1]}
         for k in J_KEYS:
             d["j_" + k] = ref["a9_j_" + k][j0:j1]
+        if "a9b_g_color" in ref and ref["a9b_bun_off"].size == 3 * nb + 1:   # second half dumped as well
+            bo, no = ref["a9b_bun_off"].astype(np.int64), ref["a9b_bn_off"].astype(np.int64)
+            d.update({"g_color2": ref["a9b_g_color"][g0:g1], "g_neg_prop": ref["a9b_g_neg_prop"][g0:g1],
+                      "eqcol2": ref["a9b_eqcol"][c0:c1], "eqneg": ref["a9b_eqneg"][c0:c1], "eqpos": ref["a9b_eqpos"][c0:c1],
+                      "bun_off": (bo[3 * b:3 * b + 4] - bo[3 * b]).astype(np.int32),
+                      "bn_off": (no[3 * b:3 * b + 4] - no[3 * b]).astype(np.int32),
+                      "g2b": ref["a9b_g2b"][3 * g0:3 * g1]})
+            for k in ("len", "start", "last", "cov", "multi"):
+                d["bun_" + k] = ref["a9b_bun_" + k][bo[3 * b]:bo[3 * b + 3]]
+            for k in ("start", "end", "cov", "next"):
+                d["bn_" + k] = ref["a9b_bn_" + k][no[3 * b]:no[3 * b + 3]]
         out.append(d)
     return out
 

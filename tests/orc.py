@@ -133,7 +133,14 @@ class OrcGroupsOut(C.Structure):
                  ("g_start", C.POINTER(C.c_uint32)), ("g_end", C.POINTER(C.c_uint32)), ("g_color", C.POINTER(C.c_int32)),
                  ("g_next", C.POINTER(C.c_int32)), ("g_cov_sum", c_f32p), ("g_multi", c_f32p),
                  ("g_alive", C.POINTER(C.c_int8)), ("merge", C.POINTER(C.c_int32)), ("eqcol", C.POINTER(C.c_int32)),
-                 ("rg_off", C.POINTER(C.c_uint32)), ("rg", C.POINTER(C.c_int32))])
+                 ("rg_off", C.POINTER(C.c_uint32)), ("rg", C.POINTER(C.c_int32)),
+                 ("g_color2", C.POINTER(C.c_int32)), ("g_neg_prop", c_f32p), ("eqcol2", C.POINTER(C.c_int32)),
+                 ("eqnegcol", C.POINTER(C.c_int32)), ("eqposcol", C.POINTER(C.c_int32)),
+                 ("bun_off", C.c_int32 * 4), ("bn_off", C.c_int32 * 4),
+                 ("bun_len", C.POINTER(C.c_int32)), ("bun_start", C.POINTER(C.c_int32)), ("bun_last", C.POINTER(C.c_int32)),
+                 ("bun_cov", c_f32p), ("bun_multi", c_f32p),
+                 ("bn_start", C.POINTER(C.c_uint32)), ("bn_end", C.POINTER(C.c_uint32)), ("bn_cov", c_f32p),
+                 ("bn_next", C.POINTER(C.c_int32)), ("group2bundle", C.POINTER(C.c_int32))])
 
 
 def _np(ptr, n, dtype):
@@ -185,7 +192,18 @@ def groups(arrays: Dict[str, np.ndarray], cov: np.ndarray, cov_off: np.ndarray, 
              "g_next": _np(o.g_next, o.n_groups, np.int32), "g_cov": _np(o.g_cov_sum, o.n_groups, np.float32),
              "g_multi": _np(o.g_multi, o.n_groups, np.float32), "merge": _np(o.merge, o.n_groups, np.int32),
              "eqcol": _np(o.eqcol, o.n_colors, np.int32), "rg_off": _np(o.rg_off, o.n_reads + 1, np.uint32),
-             "rg": _np(o.rg, int(o.rg_off[o.n_reads]) if o.n_reads else 0, np.int32)}
+             "rg": _np(o.rg, int(o.rg_off[o.n_reads]) if o.n_reads else 0, np.int32),
+             # second half of a9: colour pass + bundles
+             "g_color2": _np(o.g_color2, o.n_groups, np.int32), "g_neg_prop": _np(o.g_neg_prop, o.n_groups, np.float32),
+             "eqcol2": _np(o.eqcol2, o.n_colors, np.int32), "eqneg": _np(o.eqnegcol, o.n_colors, np.int32),
+             "eqpos": _np(o.eqposcol, o.n_colors, np.int32),
+             "bun_off": np.array(list(o.bun_off), dtype=np.int32), "bn_off": np.array(list(o.bn_off), dtype=np.int32),
+             "bun_len": _np(o.bun_len, o.bun_off[3], np.int32), "bun_start": _np(o.bun_start, o.bun_off[3], np.int32),
+             "bun_last": _np(o.bun_last, o.bun_off[3], np.int32), "bun_cov": _np(o.bun_cov, o.bun_off[3], np.float32),
+             "bun_multi": _np(o.bun_multi, o.bun_off[3], np.float32),
+             "bn_start": _np(o.bn_start, o.bn_off[3], np.uint32), "bn_end": _np(o.bn_end, o.bn_off[3], np.uint32),
+             "bn_cov": _np(o.bn_cov, o.bn_off[3], np.float32), "bn_next": _np(o.bn_next, o.bn_off[3], np.int32),
+             "g2b": _np(o.group2bundle, 3 * o.n_groups, np.int32)}
         L.orc_groups_free(C.byref(o))
         res.append(d)
     return res

@@ -84,7 +84,7 @@ def test_oracle_matches_live_reference(tmp_path, case):
         a = synth.make_adversarial(seed=int(case[-1]) + 10, n_bundles=14)
     src, dst = str(tmp_path / "in.stgb"), str(tmp_path / "out.stgb")
     write_stgb(src, a)
-    subprocess.check_call([REF_HOT, src, "--dump", dst, "--a9"], stdout=subprocess.DEVNULL)
+    subprocess.check_call([REF_HOT, src, "--dump", dst, "--a9b"], stdout=subprocess.DEVNULL)
     ref = read_stgb(dst)
     _check(a, ref)
     _check_a7(a, ref)
@@ -100,7 +100,7 @@ def test_oracle_read_loop_appended_junctions(tmp_path, seed):
     a["j_nm"] = np.where(rng.random(a["j_nm"].size) < 0.5, a["j_nreads"], a["j_nm"])
     src, dst = str(tmp_path / "in.stgb"), str(tmp_path / "out.stgb")
     write_stgb(src, a)
-    subprocess.check_call([REF_HOT, src, "--dump", dst, "--a9"], stdout=subprocess.DEVNULL)
+    subprocess.check_call([REF_HOT, src, "--dump", dst, "--a9b"], stdout=subprocess.DEVNULL)
     ref = read_stgb(dst)
     assert ref["a9_j_start"].size > a["j_start"].size
     _check_a9(a, ref)
