@@ -10,8 +10,10 @@
 // Design: thousands of bundles are processed at once; float32 deposits must land on every address in
 // the reference's order (read order), so the events are BINNED, not scattered with atomics:
 //   K0  junc_anchor    one thread per junction row: the anchor length it demands (10 or 25).
-//   K1  expand_count   one thread per read: counts the coverage intervals the read deposits (mate merge walk)
-//                      and adds its junction support with f64 atomics (exact, hence order-free: DESIGN.md §3.4).
+//   K1  expand_count   one thread per read: counts the coverage intervals the read deposits (mate merge walk),
+//                      validates offsets / mate / junction indices, and adds its junction support: the warp groups
+//                      its updates by (junction row, weight) and issues one f64 atomic of count * w per group
+//                      (f64 sums of float weights are exact, hence order-free: DESIGN.md §5).
 //   K2  scan           exclusive prefix sum of the counts (3-phase block scan).
 //   K3  expand_write   one thread per read: writes its intervals {tile(+w), tile(-w), positions, lane, w}
 //                      in reference order, so "index order" == the order the reference applies deposits in.
@@ -22,13 +24,19 @@
 //                      slot in the tile's event list; per-tile totals -> scan -> list offsets.
 //   K7  bin_scatter    one warp per chunk, walking its intervals in order: a STABLE counting sort of the events by
 //                      tile (rank = slot of chunk + rank inside the warp by ballot) -> tight per-tile event lists.
-//   K8  tile_plan      one thread per sub-tile: one 32-byte record, in column-major ticket order (all first
-//                      sub-tiles of all bundles, then all second ones ...).
-//   K9  cov_tile       one WARP per sub-tile of 512 positions x 3 strand lanes held in shared memory:
+//   K8  tile_plan      one thread per sub-tile: one 32-byte record; sub-tiles with events get tickets in a
+//                      proportional schedule (sub-tile j of nt runs in round j*R/nt), deep ones are listed for
+//                      K8b, event-free ones are listed for K10.
+//   K8b deep_deposit   one CTA per deep sub-tile (>= 2048 events): stable counting sort of its events by position,
+//                      short per-position lists summed by one thread each; K8c deep_long: one warp per long list
+//                      (a splice site of a deep locus) runs the bare chain of dependent adds.
+//   K9  cov_tile       one WARP per sub-tile with events, 512 positions x 3 strand lanes in shared memory:
 //                      ordered deposit of its event list (same-position events of a 32-group are chained in lane
 //                      order inside one thread: bit-exact for any weights), then the two sequential recurrences
-//                      with the (c, b) state taken from the nearest earlier sub-tile that had events, then one
-//                      coalesced streaming write of the finished bpcov.  The difference array never exists in HBM.
+//                      with the (c, b) state taken from the nearest earlier sub-tile that had events (bridged over
+//                      the event-free gap in closed form, advance_bs), then one coalesced streaming write of the
+//                      finished bpcov.  The difference array never exists in HBM.
+//   K10 cov_fill       one warp per event-free sub-tile: state from the carry + closed form, streaming write.
 // All float arithmetic is compiled without FMA contraction (-fmad=false): the reference is plain x86-64 SSE.
 #include "stgpu_internal.h"
 

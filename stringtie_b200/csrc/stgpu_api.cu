@@ -34,23 +34,71 @@ struct stg_ctx {
   std::mutex mu;
   std::vector<PoolBlock> pool_free;
   size_t pool_bytes = 0;          // bytes currently parked in pool_free
+  struct stg_builder* one_bundle = nullptr;   // batcher reused by stg_infer_transcripts (keeps its pinned buffers)
+  std::mutex one_bundle_mu;
+};
+
+// Growable host array in PINNED memory (cudaMallocHost), so that stg_upload's copies out of the batcher run
+// asynchronously at full PCIe rate; it keeps its capacity across stg_builder_reset.  Without a CUDA driver (CPU-only
+// test boxes) it falls back to malloc.
+template <class T>
+struct PinnedVec {
+  T* p = nullptr;
+  size_t n = 0, cap = 0;
+  bool pinned = false;
+  PinnedVec() {}
+  PinnedVec(const PinnedVec&) = delete;
+  PinnedVec& operator=(const PinnedVec&) = delete;
+  ~PinnedVec() { drop(); }
+  void drop() {
+    if (p) { if (pinned) cudaFreeHost(p); else free(p); }
+    p = nullptr; n = cap = 0;
+  }
+  bool reserve(size_t want) {
+    if (want <= cap) return true;
+    size_t nc = std::max(want, std::max(cap * 2, (size_t)(1 << 16) / sizeof(T)));
+    T* q = nullptr;
+    bool pin = cudaMallocHost((void**)&q, nc * sizeof(T)) == cudaSuccess;
+    if (!pin) { cudaGetLastError(); q = (T*)malloc(nc * sizeof(T)); if (!q) return false; }
+    if (n) memcpy(q, p, n * sizeof(T));
+    if (p) { if (pinned) cudaFreeHost(p); else free(p); }
+    p = q; cap = nc; pinned = pin;
+    return true;
+  }
+  bool push_back(T v) { if (n == cap && !reserve(n + 1)) return false; p[n++] = v; return true; }
+  bool append(const T* src, size_t k) {
+    if (!k) return true;
+    if (n + k > cap && !reserve(n + k)) return false;
+    memcpy(p + n, src, k * sizeof(T)); n += k;
+    return true;
+  }
+  T* data() { return p; }
+  size_t size() const { return n; }
+  void clear() { n = 0; }
 };
 
 struct stg_builder {
   stg_ctx* ctx;
-  std::vector<int32_t> b_start, b_end;
-  std::vector<uint32_t> b_read_off{0}, b_junc_off{0};
-  std::vector<uint32_t> r_start, r_end, r_len;
-  std::vector<float> r_count;
-  std::vector<int16_t> r_nh;
-  std::vector<int8_t> r_strand;
-  std::vector<uint8_t> r_flags;
-  std::vector<uint32_t> r_seg_off{0}, r_pair_off{0}, seg_start, seg_end;
-  std::vector<int32_t> rjunc_idx, pair_idx;
-  std::vector<float> pair_cnt;
-  std::vector<uint32_t> j_start, j_end;
-  std::vector<int8_t> j_strand, j_guide_match;
-  std::vector<double> j_nreads, j_nm, j_mm;
+  PinnedVec<int32_t> b_start, b_end;
+  PinnedVec<uint32_t> b_read_off, b_junc_off;
+  PinnedVec<uint32_t> r_start, r_end, r_len;
+  PinnedVec<float> r_count;
+  PinnedVec<int16_t> r_nh;
+  PinnedVec<int8_t> r_strand;
+  PinnedVec<uint8_t> r_flags;
+  PinnedVec<uint32_t> r_seg_off, r_pair_off, seg_start, seg_end;
+  PinnedVec<int32_t> rjunc_idx, pair_idx;
+  PinnedVec<float> pair_cnt;
+  PinnedVec<uint32_t> j_start, j_end;
+  PinnedVec<int8_t> j_strand, j_guide_match;
+  PinnedVec<double> j_nreads, j_nm, j_mm;
+  void reset() {
+    b_start.clear(); b_end.clear(); b_read_off.clear(); b_junc_off.clear(); r_start.clear(); r_end.clear();
+    r_len.clear(); r_count.clear(); r_nh.clear(); r_strand.clear(); r_flags.clear(); r_seg_off.clear();
+    r_pair_off.clear(); seg_start.clear(); seg_end.clear(); rjunc_idx.clear(); pair_idx.clear(); pair_cnt.clear();
+    j_start.clear(); j_end.clear(); j_strand.clear(); j_guide_match.clear(); j_nreads.clear(); j_nm.clear(); j_mm.clear();
+    b_read_off.push_back(0); b_junc_off.push_back(0); r_seg_off.push_back(0); r_pair_off.push_back(0);
+  }
 };
 
 struct stg_dbatch {
@@ -246,6 +294,7 @@ int stg_shutdown(stg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   pool_release_all(ctx);
+  if (ctx->one_bundle) stg_builder_destroy(ctx->one_bundle);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -265,8 +314,10 @@ int stg_trim(stg_ctx* ctx) {
 // ---- bundle batcher -----------------------------------------------------------------------------------------
 int stg_builder_create(stg_ctx* ctx, stg_builder** out) {
   if (!out) return fail(ctx, STG_EINVAL, "stg_builder_create: out is null");
+  if (ctx) cudaSetDevice(ctx->device);
   stg_builder* b = new stg_builder();
   b->ctx = ctx;
+  b->reset();
   *out = b;
   return STG_OK;
 }
@@ -275,34 +326,35 @@ int stg_builder_add(stg_builder* b, const stg_bundle_view* v) {
   if (!b || !v) return fail(nullptr, STG_EINVAL, "stg_builder_add: null argument");
   if (v->n_reads < 0 || v->n_juncs < 0 || v->end < v->start) return fail(b->ctx, STG_EINVAL, "stg_builder_add: bad view");
   const int32_t nr = v->n_reads;
-  const uint32_t nseg = nr ? v->r_seg_off[nr] - v->r_seg_off[0] : 0;
-  const uint32_t npair = nr ? v->r_pair_off[nr] - v->r_pair_off[0] : 0;
-  const uint32_t seg_base = (uint32_t)b->seg_start.size(), pair_base = (uint32_t)b->pair_idx.size();
-  b->b_start.push_back(v->start); b->b_end.push_back(v->end);
-  for (int32_t n = 0; n < nr; n++) {
-    const uint32_t ns = v->r_seg_off[n + 1] - v->r_seg_off[n];
-    if (ns < 1) return fail(b->ctx, STG_EINVAL, "stg_builder_add: read without segments");
-    b->r_start.push_back(v->r_start[n]); b->r_end.push_back(v->r_end[n]); b->r_len.push_back(v->r_len[n]);
-    b->r_count.push_back(v->r_count[n]); b->r_nh.push_back(v->r_nh[n]); b->r_strand.push_back(v->r_strand[n]);
-    b->r_flags.push_back(v->r_flags[n]);
-    b->r_seg_off.push_back(seg_base + (v->r_seg_off[n + 1] - v->r_seg_off[0]));
-    b->r_pair_off.push_back(pair_base + (v->r_pair_off[n + 1] - v->r_pair_off[0]));
-  }
   const uint32_t s0 = nr ? v->r_seg_off[0] : 0, p0 = nr ? v->r_pair_off[0] : 0;
-  b->seg_start.insert(b->seg_start.end(), v->seg_start + s0, v->seg_start + s0 + nseg);
-  b->seg_end.insert(b->seg_end.end(), v->seg_end + s0, v->seg_end + s0 + nseg);
-  b->rjunc_idx.insert(b->rjunc_idx.end(), v->rjunc_idx, v->rjunc_idx + (nseg - (uint32_t)nr));
-  b->pair_idx.insert(b->pair_idx.end(), v->pair_idx + p0, v->pair_idx + p0 + npair);
-  b->pair_cnt.insert(b->pair_cnt.end(), v->pair_cnt + p0, v->pair_cnt + p0 + npair);
-  b->j_start.insert(b->j_start.end(), v->j_start, v->j_start + v->n_juncs);
-  b->j_end.insert(b->j_end.end(), v->j_end, v->j_end + v->n_juncs);
-  b->j_strand.insert(b->j_strand.end(), v->j_strand, v->j_strand + v->n_juncs);
-  b->j_guide_match.insert(b->j_guide_match.end(), v->j_guide_match, v->j_guide_match + v->n_juncs);
-  b->j_nreads.insert(b->j_nreads.end(), v->j_nreads, v->j_nreads + v->n_juncs);
-  b->j_nm.insert(b->j_nm.end(), v->j_nm, v->j_nm + v->n_juncs);
-  b->j_mm.insert(b->j_mm.end(), v->j_mm, v->j_mm + v->n_juncs);
-  b->b_read_off.push_back((uint32_t)b->r_start.size());
-  b->b_junc_off.push_back((uint32_t)b->j_start.size());
+  const uint32_t nseg = nr ? v->r_seg_off[nr] - s0 : 0;
+  const uint32_t npair = nr ? v->r_pair_off[nr] - p0 : 0;
+  for (int32_t n = 0; n < nr; n++)
+    if (v->r_seg_off[n + 1] <= v->r_seg_off[n]) return fail(b->ctx, STG_EINVAL, "stg_builder_add: read without segments");
+  const uint32_t seg_base = (uint32_t)b->seg_start.size(), pair_base = (uint32_t)b->pair_idx.size();
+  bool ok = b->b_start.push_back(v->start) && b->b_end.push_back(v->end);
+  // the per-read arrays of a view are contiguous: bulk copies, only the CSR offsets are rebased one by one
+  ok = ok && b->r_start.append(v->r_start, nr) && b->r_end.append(v->r_end, nr) && b->r_len.append(v->r_len, nr) &&
+       b->r_count.append(v->r_count, nr) && b->r_nh.append(v->r_nh, nr) && b->r_strand.append(v->r_strand, nr) &&
+       b->r_flags.append(v->r_flags, nr);
+  ok = ok && b->r_seg_off.reserve(b->r_seg_off.size() + nr) && b->r_pair_off.reserve(b->r_pair_off.size() + nr);
+  if (ok) {
+    uint32_t* so = b->r_seg_off.data() + b->r_seg_off.size();
+    uint32_t* po = b->r_pair_off.data() + b->r_pair_off.size();
+    for (int32_t n = 0; n < nr; n++) {
+      so[n] = seg_base + (v->r_seg_off[n + 1] - s0);
+      po[n] = pair_base + (v->r_pair_off[n + 1] - p0);
+    }
+    b->r_seg_off.n += nr; b->r_pair_off.n += nr;
+  }
+  ok = ok && b->seg_start.append(v->seg_start + s0, nseg) && b->seg_end.append(v->seg_end + s0, nseg) &&
+       b->rjunc_idx.append(v->rjunc_idx, nseg - (uint32_t)nr) && b->pair_idx.append(v->pair_idx + p0, npair) &&
+       b->pair_cnt.append(v->pair_cnt + p0, npair) && b->j_start.append(v->j_start, v->n_juncs) &&
+       b->j_end.append(v->j_end, v->n_juncs) && b->j_strand.append(v->j_strand, v->n_juncs) &&
+       b->j_guide_match.append(v->j_guide_match, v->n_juncs) && b->j_nreads.append(v->j_nreads, v->n_juncs) &&
+       b->j_nm.append(v->j_nm, v->n_juncs) && b->j_mm.append(v->j_mm, v->n_juncs);
+  ok = ok && b->b_read_off.push_back((uint32_t)b->r_start.size()) && b->b_junc_off.push_back((uint32_t)b->j_start.size());
+  if (!ok) return fail(b->ctx, STG_ENOMEM, "stg_builder_add: out of host memory");
   return STG_OK;
 }
 
@@ -321,11 +373,9 @@ int stg_builder_packed(stg_builder* b, stg_packed_batch* o) {
   return STG_OK;
 }
 
-int stg_builder_reset(stg_builder* b) {
+int stg_builder_reset(stg_builder* b) {   // keeps the pinned buffers for the next batch
   if (!b) return STG_OK;
-  stg_ctx* ctx = b->ctx;
-  *b = stg_builder();
-  b->ctx = ctx;
+  b->reset();
   return STG_OK;
 }
 
@@ -626,9 +676,11 @@ int stg_query_cov(stg_ctx* ctx, const stg_dbatch* d, int64_t n, const int32_t* b
 
 int stg_infer_transcripts(stg_ctx* ctx, const stg_bundle_view* view, stg_bundle_result* result) {
   if (!ctx || !view || !result) return fail(ctx, STG_EINVAL, "stg_infer_transcripts: null argument");
-  stg_builder* b = nullptr;
-  int rc = stg_builder_create(ctx, &b);
-  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(ctx->one_bundle_mu);   // one context, one stream: callers take turns
+  int rc = STG_OK;
+  if (!ctx->one_bundle && (rc = stg_builder_create(ctx, &ctx->one_bundle))) return rc;
+  stg_builder* b = ctx->one_bundle;
+  stg_builder_reset(b);
   stg_dbatch* d = nullptr;
   stg_packed_batch pb;
   if (!(rc = stg_builder_add(b, view)) && !(rc = stg_builder_packed(b, &pb)) && !(rc = stg_upload(ctx, &pb, &d)) &&
@@ -637,7 +689,6 @@ int stg_infer_transcripts(stg_ctx* ctx, const stg_bundle_view* view, stg_bundle_
     if (!rc) rc = stg_fetch_junction_support(ctx, d, result->j_nreads_good, result->j_leftsupport, result->j_rightsupport);
   }
   stg_free_batch(ctx, d);
-  stg_builder_destroy(b);
   return rc;
 }
 
