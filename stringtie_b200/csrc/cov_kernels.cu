@@ -352,8 +352,82 @@ static cudaError_t run_scan(const uint32_t* in, uint32_t* out, int64_t n, uint32
   return cudaGetLastError();
 }
 
-cudaError_t launch_scan_exclusive_add(uint32_t* data, int64_t n_plus_1, uint32_t* partials, cudaStream_t st) {
-  return run_scan<OP_ADD, false, true>(data, data, n_plus_1, partials, st);
+// Single-pass exclusive prefix sum, in place (chained scan with decoupled look-back): every block scans its chunk,
+// publishes its total, and its first warp sums the totals of the blocks before it, 32 at a time, until it meets one
+// that already knows its inclusive prefix.  Block ids come from a ticket so that every earlier block is running or
+// done; the chunks are uniform streaming work, so nobody waits long (unlike a chained scan inside the read walk).
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p);
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long x);
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(uint32_t* __restrict__ data, int64_t n,
+                                                                      unsigned long long* state, uint32_t* ticket) {
+  __shared__ uint32_t s_blk, s_prefix;
+  if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t blk = s_blk;
+  const int lane = threadIdx.x & 31;
+  const int64_t base = (int64_t)blk * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t x[SCAN_ITEMS];
+  uint32_t acc = 0;
+  if (base + SCAN_ITEMS <= n) {
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS / 4; q++) {
+      const uint4 t = *reinterpret_cast<const uint4*>(data + base + 4 * q);
+      x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < SCAN_ITEMS; it++) x[it] = base + it < n ? data[base + it] : 0u;
+  }
+#pragma unroll
+  for (int it = 0; it < SCAN_ITEMS; it++) acc += x[it];
+  uint32_t total;
+  const uint32_t excl = block_exclusive<OP_ADD>(acc, &total);
+  if (threadIdx.x < 32) {
+    uint32_t prefix = 0;   // (flag << 32) | value; flag 1: this block's total, 2: inclusive prefix
+    if (blk > 0) {
+      if (lane == 0) st_relaxed_u64(state + blk, (1ull << 32) | total);
+      int64_t b0 = (int64_t)blk - 1;
+      for (;;) {
+        const int64_t idx = b0 - lane;
+        unsigned long long w = 2ull << 32;               // before the first block: inclusive prefix 0
+        if (idx >= 0) {
+          w = ld_relaxed_u64(state + idx);
+          while ((w >> 32) == 0ull) { __nanosleep(20); w = ld_relaxed_u64(state + idx); }
+        }
+        const uint32_t incl = __ballot_sync(FULL, (w >> 32) == 2ull);
+        const int first = incl ? __ffs(incl) - 1 : 32;
+        prefix += __reduce_add_sync(FULL, lane <= first ? (uint32_t)w : 0u);
+        if (incl) break;
+        b0 -= 32;
+      }
+    }
+    if (lane == 0) { st_relaxed_u64(state + blk, (2ull << 32) | (unsigned long long)(prefix + total)); s_prefix = prefix; }
+  }
+  __syncthreads();
+  uint32_t run = s_prefix + excl;
+  if (base + SCAN_ITEMS <= n) {
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS / 4; q++) {
+      uint4 t;
+      t.x = run; run += x[4 * q]; t.y = run; run += x[4 * q + 1]; t.z = run; run += x[4 * q + 2]; t.w = run; run += x[4 * q + 3];
+      *reinterpret_cast<uint4*>(data + base + 4 * q) = t;
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < SCAN_ITEMS; it++) { if (base + it < n) data[base + it] = run; run += x[it]; }
+  }
+}
+
+cudaError_t launch_scan_exclusive_add(uint32_t* data, int64_t n_plus_1, unsigned long long* state, uint32_t* ticket,
+                                      cudaStream_t st) {
+  if (n_plus_1 <= 0) return cudaSuccess;
+  const int64_t nb = (n_plus_1 + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  cudaError_t e = cudaMemsetAsync(state, 0, sizeof(unsigned long long) * (size_t)nb, st);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st)) != cudaSuccess) return e;
+  scan_lookback_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(data, n_plus_1, state, ticket);
+  return cudaGetLastError();
 }
 
 

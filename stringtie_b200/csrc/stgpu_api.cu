@@ -442,10 +442,10 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
   // the layout vectors are pageable locals: make sure their copies have left the host before they die
   CK(ctx, cudaStreamSynchronize(ctx->stream));
 #define AL(field, count) do { rc = dev_alloc(ctx, d, &v.field, (int64_t)(count)); if (rc) { free_batch_allocs(ctx, d); delete d; return rc; } } while (0)
-  AL(r_ivl_cnt, h->n_reads + 1);
+  AL(r_ivl_cnt, h->n_reads + 1 + 16); AL(scan_state, (h->n_reads + 1) / 4096 + 2);
   d->scan_capacity = std::max<int64_t>(std::max<int64_t>(h->n_reads + 1, v.n_tiles + 1), v.n_rounds + 1);
   AL(scan_partials, scan_partials_needed(d->scan_capacity));
-  AL(tile_carry, v.n_tiles * 4); AL(tile_ticket, 3); AL(deep_count, 2); AL(err_flag, 1);
+  AL(tile_carry, v.n_tiles * 4); AL(tile_ticket, 4); AL(deep_count, 2); AL(err_flag, 1);
   AL(round_off, v.n_rounds + 1); AL(round_cur, v.n_rounds + 1);
   AL(tile_plan, v.n_tiles); AL(tile_evoff, v.n_tiles + 1); AL(tile_lastne, v.n_tiles); AL(junc_anchor, h->n_juncs);
   AL(bpcov, 3 * v.total_pos);
@@ -486,7 +486,7 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   CK(ctx, cudaMemsetAsync(v.err_flag, 0, sizeof(uint32_t), st));
   { Scope s(ctx, "junc_anchor", 1); CK(ctx, launch_junc_anchor(v, kp, st)); }
   { Scope s(ctx, "expand_count+junction_support", 1); CK(ctx, launch_expand_count(v, st)); }
-  { Scope s(ctx, "scan_interval_offsets", 3); CK(ctx, launch_scan_exclusive_add(v.r_ivl_cnt, v.n_reads + 1, v.scan_partials, st)); }
+  { Scope s(ctx, "scan_interval_offsets", 1); CK(ctx, launch_scan_exclusive_add(v.r_ivl_cnt, v.n_reads + 1, v.scan_state, v.tile_ticket + 3, st)); }
   // the interval count sizes the next buffers: a 4-byte read-back (one of the two host syncs inside the stage)
   uint32_t n_ivl = 0;
   if (v.n_reads) {

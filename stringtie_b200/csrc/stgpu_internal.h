@@ -56,6 +56,7 @@ struct DevBatchView {
   int64_t total_pos;           // b_gbase[n_bundles]
   // scratch
   uint32_t* err_flag;          // [1] STG_ERR_* bits raised by the kernels on malformed input
+  unsigned long long* scan_state;  // [ceil((n_reads+1)/4096)] status words of the single-pass scan
   uint32_t* r_ivl_cnt;         // [n_reads+1] per-read interval count, then exclusive prefix (in place)
   int64_t n_ivl;               // filled after the count pass (host reads it back)
   uint4* ivl;                  // [n_ivl] {tile of the +w deposit, tile of the -w deposit,
@@ -85,7 +86,7 @@ struct DevBatchView {
   TileRec* tile_plan;          // [n_tiles] [0, n_main): tiles with events in ticket order; [n_main, n_tiles): the rest
   unsigned long long* tile_carry;  // [n_tiles*4] per strand lane (c | bs << 32) after the last position of a
                                //             sub-tile with events; all-ones until published (bundle-major tile id)
-  uint32_t* tile_ticket;       // [3] work counters: cov_tile_kernel, deep_deposit_kernel, deep_long_kernel
+  uint32_t* tile_ticket;       // [4] work counters: cov_tile_kernel, deep_deposit_kernel, deep_long_kernel, scan blocks
   // outputs
   float* bpcov;                // [3*total_pos]: bundle b lane s index i at 3*b_gbase[b] + s*b_stride[b] + i
   double *j_nreads_good, *j_leftsupport, *j_rightsupport;  // [n_juncs]
@@ -111,7 +112,8 @@ struct KernelParams {
 
 // kernel launchers (cov_kernels.cu). Each enqueues on `st` and returns the CUDA error of the launch.
 cudaError_t launch_expand_count(const DevBatchView& v, cudaStream_t st);
-cudaError_t launch_scan_exclusive_add(uint32_t* data, int64_t n_plus_1, uint32_t* partials, cudaStream_t st);
+cudaError_t launch_scan_exclusive_add(uint32_t* data, int64_t n_plus_1, unsigned long long* state, uint32_t* ticket,
+                                      cudaStream_t st);
 cudaError_t launch_expand_write(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_chunk_hull(const DevBatchView& v, cudaStream_t st);      // + the three chunk-level scans
 cudaError_t launch_bin_count(const DevBatchView& v, cudaStream_t st);
