@@ -18,6 +18,7 @@
  *   a4  clamped + BSIZE-blocked prefix scan      -> stg_run(), kernel cov_tile
  *   a5  get_cov / get_cov_sign                   -> stg_query_cov()
  *   a7  junction pass of build_graphs, good_junc -> stg_run(), kernel junc_pass; stg_fetch_junction_pass()
+ *   a10 (part) find_all_trims                    -> stg_find_trims(), kernel find_trims
  */
 #ifndef STGPU_H_
 #define STGPU_H_
@@ -190,6 +191,18 @@ int stg_fetch_cov_totals(stg_ctx* ctx, const stg_dbatch* batch, double* totals);
  * start/end are bundle-relative (pos - refstart), lane is the reference's `s` argument. Host arrays. */
 int stg_query_cov(stg_ctx* ctx, const stg_dbatch* batch, int64_t n, const int32_t* bundle, const int8_t* lane,
                   const uint32_t* start, const uint32_t* end, int sign, double* out);
+
+/* find_all_trims (rlink.cpp:2118-2419, part of row a10; one of the bpcov range-query consumers): for n regions
+ * (bundle[i], sno[i] in {0, 2} as at the call sites rlink.cpp:2813 / 15559, genomic start[i]..end[i]) of a batch that
+ * has been run, the reference's `trimpoint` vector of each region: candidate source / sink trim positions with their
+ * abundance; entries the reference's global re-validation rejected keep pos = 0.  Region i may return up to
+ * stg_trims_capacity(start[i], end[i]) points; the caller passes cap_off = exclusive prefix of those capacities
+ * ([n+1]) and arrays of cap_off[n] elements; count[i] points are written from element cap_off[i] on.  Host arrays.
+ * Point features (--ptf, `tstartend`) are not supported. */
+int stg_trims_capacity(uint32_t start, uint32_t end);
+int stg_find_trims(stg_ctx* ctx, const stg_dbatch* batch, int64_t n, const int32_t* bundle, const int8_t* sno,
+                   const uint32_t* start, const uint32_t* end, const uint32_t* cap_off, uint32_t* count,
+                   uint32_t* pos, float* abundance, uint8_t* is_start);
 
 /* Convenience drop-in for ONE bundle, synchronous (upload + run + fetch), the shape of the reference call. */
 typedef struct stg_bundle_result {

@@ -76,6 +76,14 @@ void orc_groups_bundle(const stg_packed_batch* B, const orc_params* P, int64_t b
                        orc_groups_out* out);
 void orc_groups_free(orc_groups_out* out);
 
+/* find_all_trims (rlink.cpp:2118-2419, part of SURVEY.md §8 row a10) on one region of one bundle (no point features):
+ * cov = the bundle's finished bpcov [3*blen], sno in {0, 2} as at the call sites (rlink.cpp:2813, 15559), start / end
+ * genomic.  Writes the reference's `trimpoint` vector (rejected points keep pos = 0) and returns its length, at most
+ * orc_trims_capacity(start, end). */
+int orc_trims_capacity(uint32_t start, uint32_t end);
+int orc_find_all_trims(const float* cov, int64_t blen, int64_t refstart, int sno, uint32_t start, uint32_t end,
+                       uint32_t* o_pos, float* o_abund, uint8_t* o_start);
+
 /* work counters for the roofline: S = mate-merged coverage intervals emitted, J = junction-support updates */
 void orc_batch_stats(const stg_packed_batch* B, int64_t* L, int64_t* S, int64_t* J);
 

@@ -107,6 +107,7 @@ struct stg_dbatch {
   std::vector<int64_t> h_cov_off;  // [n_bundles] float offset of lane 0 of bundle b (= 3*gbase)
   std::vector<int64_t> h_stride;   // [n_bundles]
   std::vector<uint32_t> h_len;
+  std::vector<int32_t> h_start;    // [n_bundles] BundleData::start
   int64_t ivl_capacity = 0;     // intervals the interval / event / chunk arrays can hold
   int64_t cell_capacity = 0;    // counter cells of the binning matrix
   int64_t scan_capacity = 0;    // elements the scan scratch covers
@@ -395,14 +396,14 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
   const int64_t nb = h->n_bundles;
   // layout
   std::vector<uint32_t> len(nb), stride(nb), gbase(nb + 1), tile_off(nb + 1);
-  d->h_cov_off.resize(nb); d->h_stride.resize(nb); d->h_len.resize(nb);
+  d->h_cov_off.resize(nb); d->h_stride.resize(nb); d->h_len.resize(nb); d->h_start.resize(nb);
   uint64_t g = 0, t = 0;
   for (int64_t b = 0; b < nb; b++) {
     const uint64_t l = (uint64_t)((int64_t)h->b_end[b] - (int64_t)h->b_start[b] + 3);
     const uint64_t s = (l + STG_LANE_ALIGN - 1) / STG_LANE_ALIGN * STG_LANE_ALIGN;
     if (l >= 0x7fffffffull) { delete d; return fail(ctx, STG_ERANGE, "bundle span too large"); }
     len[b] = (uint32_t)l; stride[b] = (uint32_t)s; gbase[b] = (uint32_t)g; tile_off[b] = (uint32_t)t;
-    d->h_cov_off[b] = (int64_t)(3 * g); d->h_stride[b] = (int64_t)s; d->h_len[b] = (uint32_t)l;
+    d->h_cov_off[b] = (int64_t)(3 * g); d->h_stride[b] = (int64_t)s; d->h_len[b] = (uint32_t)l; d->h_start[b] = h->b_start[b];
     d->sum_len += (int64_t)l;
     g += s; t += (l + STG_TILE_W - 1) / STG_TILE_W;
     if (g >= 0xffffffffull || t >= 0xffffffffull) { delete d; return fail(ctx, STG_ERANGE, "batch spans more than 2^32 positions; split it"); }
@@ -671,6 +672,57 @@ int stg_query_cov(stg_ctx* ctx, const stg_dbatch* d, int64_t n, const int32_t* b
   CK(ctx, cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, st));
   CK(ctx, cudaStreamSynchronize(st));
   cudaFree(db); cudaFree(dl); cudaFree(ds); cudaFree(de); cudaFree(dout);
+  return STG_OK;
+}
+
+int stg_trims_capacity(uint32_t start, uint32_t end) { return end < start ? 0 : (int)((end - start + 1) / 50u) + 2; }
+
+int stg_find_trims(stg_ctx* ctx, const stg_dbatch* d, int64_t n, const int32_t* bundle, const int8_t* sno,
+                   const uint32_t* start, const uint32_t* end, const uint32_t* cap_off, uint32_t* count, uint32_t* pos,
+                   float* abundance, uint8_t* is_start) {
+  if (!ctx || !d || n < 0 || (n && (!bundle || !sno || !start || !end || !cap_off || !count || !pos || !abundance || !is_start)))
+    return fail(ctx, STG_EINVAL, "stg_find_trims: bad argument");
+  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_find_trims: batch has not been run");
+  if (ctx->params.havePtFeatures) return fail(ctx, STG_EUNSUPPORTED, "stg_find_trims: point features are not supported");
+  if (n == 0) return STG_OK;
+  if (cap_off[0] != 0) return fail(ctx, STG_EINVAL, "stg_find_trims: cap_off[0] must be 0");
+  for (int64_t i = 0; i < n; i++) {
+    if (bundle[i] < 0 || bundle[i] >= d->v.n_bundles || (sno[i] != 0 && sno[i] != 2) || end[i] < start[i])
+      return fail(ctx, STG_EINVAL, "stg_find_trims: bad region");
+    const int64_t lo = (int64_t)start[i] - (int64_t)d->h_start[bundle[i]], hi = (int64_t)end[i] - (int64_t)d->h_start[bundle[i]];
+    if (lo < 0 || hi + 1 >= (int64_t)d->h_len[bundle[i]]) return fail(ctx, STG_EINVAL, "stg_find_trims: region outside its bundle");
+    if ((int64_t)cap_off[i + 1] - (int64_t)cap_off[i] < stg_trims_capacity(start[i], end[i]))
+      return fail(ctx, STG_EINVAL, "stg_find_trims: cap_off leaves a region less room than stg_trims_capacity");
+  }
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t tot = cap_off[n];
+  int32_t* db = nullptr; int8_t* ds = nullptr; uint32_t *da = nullptr, *dz = nullptr, *dc = nullptr, *dn = nullptr, *dp = nullptr;
+  float* df = nullptr; uint8_t* dt = nullptr;
+  CK(ctx, cudaMalloc(&db, n * 4)); CK(ctx, cudaMalloc(&ds, n)); CK(ctx, cudaMalloc(&da, n * 4)); CK(ctx, cudaMalloc(&dz, n * 4));
+  CK(ctx, cudaMalloc(&dc, (n + 1) * 4)); CK(ctx, cudaMalloc(&dn, n * 4)); CK(ctx, cudaMalloc(&dp, (tot + 1) * 4));
+  CK(ctx, cudaMalloc(&df, (tot + 1) * 4)); CK(ctx, cudaMalloc(&dt, tot + 1));
+  CK(ctx, cudaMemcpyAsync(db, bundle, n * 4, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(ds, sno, n, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(da, start, n * 4, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(dz, end, n * 4, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(dc, cap_off, (n + 1) * 4, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemsetAsync(dp, 0, (tot + 1) * 4, st));
+  CK(ctx, cudaMemsetAsync(df, 0, (tot + 1) * 4, st));
+  CK(ctx, cudaMemsetAsync(dt, 0, tot + 1, st));
+  ctx->launches++;
+  {
+    Scope s(ctx, "find_trims", 0);
+    CK(ctx, launch_find_trims(d->v, n, db, ds, da, dz, dc, dn, dp, df, dt, st));
+  }
+  CK(ctx, cudaMemcpyAsync(count, dn, n * 4, cudaMemcpyDeviceToHost, st));
+  if (tot) {
+    CK(ctx, cudaMemcpyAsync(pos, dp, tot * 4, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemcpyAsync(abundance, df, tot * 4, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemcpyAsync(is_start, dt, tot, cudaMemcpyDeviceToHost, st));
+  }
+  CK(ctx, cudaStreamSynchronize(st));
+  cudaFree(db); cudaFree(ds); cudaFree(da); cudaFree(dz); cudaFree(dc); cudaFree(dn); cudaFree(dp); cudaFree(df); cudaFree(dt);
   return STG_OK;
 }
 

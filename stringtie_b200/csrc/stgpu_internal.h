@@ -128,5 +128,8 @@ cudaError_t launch_cov_totals(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_query_cov(const DevBatchView& v, int64_t n, const int32_t* bundle, const int8_t* lane,
                              const uint32_t* start, const uint32_t* end, int sign, double* out, cudaStream_t st);
 cudaError_t launch_junc_pass(const DevBatchView& v, const JuncParams& p, cudaStream_t st);
+cudaError_t launch_find_trims(const DevBatchView& v, int64_t n, const int32_t* bundle, const int8_t* sno, const uint32_t* start,
+                              const uint32_t* end, const uint32_t* cap_off, uint32_t* o_cnt, uint32_t* o_pos, float* o_ab,
+                              uint8_t* o_st, cudaStream_t st);
 int64_t scan_partials_needed(int64_t n);
 int cov_tile_smem_bytes();

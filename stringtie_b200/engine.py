@@ -22,7 +22,7 @@ EXPORTS = [
     "stg_params_default", "stg_init", "stg_shutdown", "stg_last_error", "stg_abi_version", "stg_builder_create",
     "stg_builder_add", "stg_builder_packed", "stg_builder_reset", "stg_builder_destroy", "stg_upload", "stg_run",
     "stg_sync", "stg_free_batch", "stg_trim", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
-    "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_infer_transcripts",
+    "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_trims_capacity", "stg_find_trims", "stg_infer_transcripts",
     "stg_shard_assign", "stg_set_profiling", "stg_kernel_count", "stg_kernel_time", "stg_launch_counter", "stg_batch_stats", "stg_stream",
 ]
 
@@ -71,6 +71,10 @@ def load_library() -> C.CDLL:
     L.stg_fetch_cov_totals.argtypes = [vp, vp, c_f64p]
     L.stg_query_cov.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int8), C.POINTER(C.c_uint32),
                                 C.POINTER(C.c_uint32), C.c_int, c_f64p]
+    u32p, u8p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+    L.stg_trims_capacity.argtypes = [C.c_uint32, C.c_uint32]
+    L.stg_find_trims.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int8), u32p, u32p, u32p, u32p, u32p,
+                                 c_f32p, u8p]
     L.stg_infer_transcripts.argtypes = [vp, C.POINTER(StgBundleView), C.POINTER(StgBundleResult)]
     L.stg_shard_assign.argtypes = [C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
                                    C.POINTER(C.c_int32), c_f64p]
@@ -197,6 +201,28 @@ class Engine:
             ptr(out["leftsupport"]), ptr(out["rightsupport"]), ptr(out["mm"]), out["ej"].ctypes.data_as(i32p),
             out["good"].ctypes.data_as(i8p), out["good_strand"].ctypes.data_as(i8p)))
         return out
+
+    def find_trims(self, batch: DeviceBatch, bundle, sno, start, end):
+        """find_all_trims (stg_find_trims) on regions; returns (off [n+1], pos, abundance, is_start), compacted."""
+        bundle = np.ascontiguousarray(bundle, dtype=np.int32); sno = np.ascontiguousarray(sno, dtype=np.int8)
+        start = np.ascontiguousarray(start, dtype=np.uint32); end = np.ascontiguousarray(end, dtype=np.uint32)
+        n = bundle.size
+        cap = np.array([self.L.stg_trims_capacity(int(a), int(z)) for a, z in zip(start, end)], dtype=np.int64)
+        cap_off = np.zeros(n + 1, dtype=np.uint32)
+        np.cumsum(cap, out=cap_off[1:])
+        tot = int(cap_off[-1])
+        cnt = np.zeros(n, np.uint32); pos = np.zeros(tot + 1, np.uint32); ab = np.zeros(tot + 1, np.float32)
+        st = np.zeros(tot + 1, np.uint8)
+        u32p, u8p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+        self._ck(self.L.stg_find_trims(self.ctx, batch.handle, n, bundle.ctypes.data_as(C.POINTER(C.c_int32)),
+                                       sno.ctypes.data_as(C.POINTER(C.c_int8)), start.ctypes.data_as(u32p),
+                                       end.ctypes.data_as(u32p), cap_off.ctypes.data_as(u32p), cnt.ctypes.data_as(u32p),
+                                       pos.ctypes.data_as(u32p), ab.ctypes.data_as(c_f32p), st.ctypes.data_as(u8p)))
+        off = np.zeros(n + 1, dtype=np.uint32)
+        np.cumsum(cnt, out=off[1:])
+        sel = np.concatenate([np.arange(int(cap_off[i]), int(cap_off[i]) + int(cnt[i])) for i in range(n)]) if n else np.zeros(0, int)
+        sel = sel.astype(np.int64)
+        return off, pos[sel], ab[sel], st[sel]
 
     def fetch_cov_totals(self, batch: DeviceBatch) -> np.ndarray:
         out = np.empty(batch.n_bundles * 3, dtype=np.float64)

@@ -207,3 +207,30 @@ def groups(arrays: Dict[str, np.ndarray], cov: np.ndarray, cov_off: np.ndarray, 
         L.orc_groups_free(C.byref(o))
         res.append(d)
     return res
+
+
+def find_trims(arrays: Dict[str, np.ndarray], cov: np.ndarray, cov_off: np.ndarray, bundle, sno, start, end):
+    """find_all_trims (oracle/stg_oracle_trims.c) on regions (bundle[i], sno[i], start[i], end[i]).
+    Returns (off [n+1], pos, abund, isstart): the reference's trimpoint vectors, concatenated."""
+    L = lib()
+    if not hasattr(L, "_ft_ready"):
+        L.orc_trims_capacity.argtypes = [C.c_uint32, C.c_uint32]
+        L.orc_trims_capacity.restype = C.c_int
+        L.orc_find_all_trims.argtypes = [c_f32p, C.c_int64, C.c_int64, C.c_int, C.c_uint32, C.c_uint32,
+                                         C.POINTER(C.c_uint32), c_f32p, C.POINTER(C.c_uint8)]
+        L.orc_find_all_trims.restype = C.c_int
+        L._ft_ready = True
+    lens = arrays["b_end"].astype(np.int64) - arrays["b_start"].astype(np.int64) + 3
+    off = [0]
+    pos, ab, st = [], [], []
+    for b, s, a, z in zip(bundle, sno, start, end):
+        cap = L.orc_trims_capacity(int(a), int(z))
+        p = np.zeros(cap, np.uint32); f = np.zeros(cap, np.float32); t = np.zeros(cap, np.uint8)
+        n = L.orc_find_all_trims(C.cast(cov.ctypes.data + int(cov_off[b]) * 4, c_f32p), int(lens[b]),
+                                 int(arrays["b_start"][b]), int(s), int(a), int(z),
+                                 p.ctypes.data_as(C.POINTER(C.c_uint32)), f.ctypes.data_as(c_f32p),
+                                 t.ctypes.data_as(C.POINTER(C.c_uint8)))
+        pos.append(p[:n]); ab.append(f[:n]); st.append(t[:n])
+        off.append(off[-1] + n)
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+    return np.array(off, dtype=np.uint32), cat(pos, np.uint32), cat(ab, np.float32), cat(st, np.uint8)

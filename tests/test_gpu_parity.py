@@ -231,3 +231,47 @@ def test_malformed_batches_are_rejected_not_executed(engine):
         engine.run(batch)
     batch.free()
     check_batch(engine, good).free()   # the context still works
+
+
+def _regions_from_oracle(a, cov, off, good, left, right):
+    """Bundlenodes of the oracle (rows a8 + a9) and their halves: the kind of regions create_graph hands to find_all_trims."""
+    bun, sno, st, en = [], [], [], []
+    for b, g in enumerate(orc.groups(a, cov, off, good, left, right)):
+        for s in range(3):
+            for k in range(int(g["bn_off"][s]), int(g["bn_off"][s + 1])):
+                x, z = int(g["bn_start"][k]), int(g["bn_end"][k])
+                m = x + (z - x) // 2
+                for lo, hi in ((x, z), (x, m), (m + 1, z)):
+                    if hi > lo:
+                        bun.append(b); sno.append(2 if s == 2 else 0); st.append(lo); en.append(hi)
+    return np.array(bun, np.int32), np.array(sno, np.int8), np.array(st, np.uint32), np.array(en, np.uint32)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_find_trims_golden(engine, name):
+    """find_all_trims on the GPU against the reference's own results (dumped with the fixtures)."""
+    g = load_golden(name)
+    from stringtie_b200.stgb import input_view
+    batch = engine.upload(input_view(g))
+    engine.run(batch)
+    off, pos, ab, st = engine.find_trims(batch, g["ft_bundle"], g["ft_sno"], g["ft_start"], g["ft_end"])
+    assert np.array_equal(off, g["ft_off"]) and np.array_equal(pos, g["ft_pos"]) and np.array_equal(st, g["ft_isstart"])
+    assert np.array_equal(ab.view(np.uint32), g["ft_abund"].view(np.uint32))
+    batch.free()
+
+
+@pytest.mark.parametrize("kind,seed", [("synth", 3), ("deep", 4), ("adv", 1), ("adv", 3)])
+def test_find_trims_vs_oracle(engine, kind, seed):
+    a = (synth.make_batch(n_bundles=60, reads_per_bundle=3000, seed=seed) if kind == "synth" else
+         synth.make_batch(n_bundles=12, reads_per_bundle=40000, seed=seed) if kind == "deep" else
+         synth.make_adversarial(seed=seed, n_bundles=14))
+    cov, off, good, left, right = orc.run(a)
+    bun, sno, st, en = _regions_from_oracle(a, cov, off, good, left, right)
+    assert bun.size > 50
+    batch = engine.upload(a)
+    engine.run(batch)
+    got = engine.find_trims(batch, bun, sno, st, en)
+    want = orc.find_trims(a, cov, off, bun, sno, st, en)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[3], want[3])
+    assert np.array_equal(got[2].view(np.uint32), want[2].view(np.uint32))
+    batch.free()

@@ -70,6 +70,21 @@ def test_oracle_read_loop_and_groups_match_golden(golden):
     _check_a9(input_view(golden), golden)
 
 
+def _check_trims(arrays, ref):
+    """find_all_trims (part of row a10): the reference's own function, called from the dump hook on every bundlenode and
+    on its halves, against the restatement — positions, abundances (float32 bits), source/sink flags, rejected points."""
+    cov, off, *_ = orc.run(arrays)
+    o, p, f, t = orc.find_trims(arrays, cov, off, ref["ft_bundle"], ref["ft_sno"], ref["ft_start"], ref["ft_end"])
+    assert np.array_equal(o, ref["ft_off"]) and np.array_equal(p, ref["ft_pos"]) and np.array_equal(t, ref["ft_isstart"])
+    assert np.array_equal(f.view(np.uint32), ref["ft_abund"].view(np.uint32))
+
+
+def test_oracle_find_all_trims_matches_golden(golden):
+    from stringtie_b200.stgb import input_view
+    assert golden["ft_start"].size > 100
+    _check_trims(input_view(golden), golden)
+
+
 def test_golden_has_inexact_weights(golden):
     # the fixtures must exercise order-dependent float accumulation (NH=3,5,6 -> 1/3, 1/5, 1/6)
     assert np.isin(golden["r_nh"], [3, 5, 6]).any()
@@ -89,6 +104,7 @@ def test_oracle_matches_live_reference(tmp_path, case):
     _check(a, ref)
     _check_a7(a, ref)
     _check_a9(a, ref)
+    _check_trims(a, ref)
 
 
 @pytest.mark.skipif(not os.path.exists(REF_HOT), reason="reference harness not built (oracle/_ref is built from /root/reference)")
