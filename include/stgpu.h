@@ -18,6 +18,8 @@
  *   a4  clamped + BSIZE-blocked prefix scan      -> stg_run(), kernel cov_tile
  *   a5  get_cov / get_cov_sign                   -> stg_query_cov()
  *   a7  junction pass of build_graphs, good_junc -> stg_run(), kernel junc_pass; stg_fetch_junction_pass()
+ *   a8  per-read junction repair, un-pairing     -> stg_build_groups(), kernel groups_walk
+ *   a9  groups, colours, bundles / bundlenodes   -> stg_build_groups(), kernels groups_walk / groups_colour
  *   a10 (part) find_all_trims                    -> stg_find_trims(), kernel find_trims
  */
 #ifndef STGPU_H_
@@ -191,6 +193,51 @@ int stg_fetch_cov_totals(stg_ctx* ctx, const stg_dbatch* batch, double* totals);
  * start/end are bundle-relative (pos - refstart), lane is the reference's `s` argument. Host arrays. */
 int stg_query_cov(stg_ctx* ctx, const stg_dbatch* batch, int64_t n, const int32_t* bundle, const int8_t* lane,
                   const uint32_t* start, const uint32_t* end, int sign, double* out);
+
+/* ---- rows a8 + a9: the read loop of build_graphs and what follows it up to the bundlenodes ------------------------
+ * stg_build_groups runs, for every bundle of a batch that has been run (stg_run), the reference's
+ *   per-read junction repair, un-pairing and un-stranding            rlink.cpp:14845-15092
+ *   add_read_to_group / merge_read_to_group / merge_fwd_groups       rlink.cpp:1633-1727, 1281-1631, 1246-1278
+ *   fragment counting (BundleData::num_fragments, frag_len)          rlink.cpp:15105-15116
+ *   re-sort of the junction table after appended rows                rlink.cpp:15122-15125
+ *   merging of groups closer than bundledist                         rlink.cpp:15134-15164
+ *   colour pass over the three strand lanes (set_strandcol, neg_prop) rlink.cpp:15196-15299
+ *   create_bundle / add_group_to_bundle -> CBundle, CBundlenode      rlink.cpp:15340-15427
+ * on the device and keeps the results there for the stages that follow.  Short-read de novo path only: returns
+ * STG_EUNSUPPORTED with longreads, mixedMode, viral or guided set.  The results are read with stg_fetch_groups_array:
+ * every array is batch-wide; per-bundle slices are given by the *_OFF arrays (exclusive prefixes, [n_bundles+1]).
+ *   reads after the loop (same CSR as the input): R_STRAND i8[n_reads], PAIR_IDX i32[n_pairs], SEG_START / SEG_END
+ *     u32[n_segs], RJUNC i32[n_segs-n_reads] (row in the bundle's junction table BELOW)
+ *   junction table after the loop, in the order the reference re-sorts it into; bundle b owns rows
+ *     [b_junc_off[b] + APP_OFF[b], b_junc_off[b+1] + APP_OFF[b+1]): J_START, J_END u32, J_STRAND i8, J_NREADS,
+ *     J_NREADS_GOOD, J_LEFT, J_RIGHT, J_NM, J_MM f64
+ *   groups (CGroup; slot == CGroup::grid at creation), bundle b owns [GROUP_OFF[b], GROUP_OFF[b+1]): G_START, G_END
+ *     u32, G_COLOR i32 (after the loop), G_NEXT i32 (next group of the strand lane, bundle-local, -1: none), G_MERGE
+ *     i32 (slot it was merged into), G_COV, G_MULTI f32, G_ALIVE i8, G_COLOR2 i32 and G_NEG_PROP f32 (after the colour
+ *     pass); STARTGROUP i32[3*n_bundles] first group of each lane
+ *   colours, bundle b owns [COLOR_OFF[b], COLOR_OFF[b+1]): EQCOL (after the loop), EQCOL2, EQNEG, EQPOS i32
+ *   readgroup: read n owns RG[RG_OFF[n] .. RG_OFF[n+1]) (i32 group slots)
+ *   bundles / bundlenodes of strand lane s of bundle b: N_BUN / N_BN u32[3*n_bundles] entries from element
+ *     3*GROUP_OFF[b] + s*(GROUP_OFF[b+1]-GROUP_OFF[b]) on: BUN_LEN, BUN_START, BUN_LAST i32, BUN_COV, BUN_MULTI f32
+ *     (CBundle, bundle.h:260-268; start / last = bundlenode ids of the lane); BN_START, BN_END u32, BN_COV f32, BN_NEXT
+ *     i32 (CBundlenode, rlink.h:56-62); G2B i32[3*groups]: group2bundle, same layout
+ *   NUM_FRAGMENTS, FRAG_LEN f64[n_bundles] */
+enum stg_groups_array {
+  STG_GA_R_STRAND = 0, STG_GA_PAIR_IDX, STG_GA_SEG_START, STG_GA_SEG_END, STG_GA_RJUNC,
+  STG_GA_GROUP_OFF, STG_GA_COLOR_OFF, STG_GA_APP_OFF, STG_GA_RG_OFF, STG_GA_STARTGROUP, STG_GA_NUM_FRAGMENTS, STG_GA_FRAG_LEN,
+  STG_GA_G_START, STG_GA_G_END, STG_GA_G_COLOR, STG_GA_G_NEXT, STG_GA_G_MERGE, STG_GA_G_COV, STG_GA_G_MULTI, STG_GA_G_ALIVE,
+  STG_GA_G_COLOR2, STG_GA_G_NEG_PROP, STG_GA_EQCOL, STG_GA_EQCOL2, STG_GA_EQNEG, STG_GA_EQPOS, STG_GA_G2B,
+  STG_GA_BUN_LEN, STG_GA_BUN_START, STG_GA_BUN_LAST, STG_GA_BUN_COV, STG_GA_BUN_MULTI,
+  STG_GA_BN_START, STG_GA_BN_END, STG_GA_BN_COV, STG_GA_BN_NEXT, STG_GA_N_BUN, STG_GA_N_BN, STG_GA_RG,
+  STG_GA_J_START, STG_GA_J_END, STG_GA_J_STRAND, STG_GA_J_NREADS, STG_GA_J_NREADS_GOOD, STG_GA_J_LEFT, STG_GA_J_RIGHT,
+  STG_GA_J_NM, STG_GA_J_MM,
+  STG_GA_COUNT
+};
+int stg_build_groups(stg_ctx* ctx, stg_dbatch* batch);
+/* element count and element size in bytes of array `which` (enum stg_groups_array) of a batch whose groups are built */
+int stg_groups_array_info(const stg_dbatch* batch, int which, int64_t* count, int32_t* elem_bytes);
+/* copies elements [first, first+count) of array `which` to the host buffer `out` */
+int stg_fetch_groups_array(stg_ctx* ctx, const stg_dbatch* batch, int which, int64_t first, int64_t count, void* out);
 
 /* find_all_trims (rlink.cpp:2118-2419, part of row a10; one of the bpcov range-query consumers): for n regions
  * (bundle[i], sno[i] in {0, 2} as at the call sites rlink.cpp:2813 / 15559, genomic start[i]..end[i]) of a batch that

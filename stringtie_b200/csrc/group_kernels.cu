@@ -1,0 +1,203 @@
+// group_kernels.cu — sm_100a kernels of SURVEY.md §8 rows a8 + a9 (read loop of build_graphs, groups, colours,
+// bundles / bundlenodes).  The per-bundle algorithm is in groups_device.cuh; this file maps it onto the GPU:
+//   group_caps_kernel    one thread per read: how many readgroup / group / colour slots the read can need at most
+//   groups_walk_kernel   one warp per bundle, bundles in order of decreasing read count; lane 0 walks the reads
+//   groups_colour_kernel one warp per bundle: the lanes compact the bundle's groups and colours into the dense
+//                        arrays, lane 0 runs the colour pass and builds bundles / bundlenodes
+//   groups_rg_kernel     one thread per read: compacts readgroup
+//   groups_junc_kernel   one warp per bundle: the junction table in the order the reference re-sorts it into
+// The walk is the reference's sequential loop (its state flows both ways between repair, grouping and un-pairing), so
+// the parallelism of this first version is ACROSS bundles; the longest bundle bounds the stage.
+#include "groups_device.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t bundle_of_read(const DevBatchView& v, uint32_t n) {
+  uint32_t b = v.cta_bundle[n / STG_READ_BLOCK];
+  while (v.b_read_off[b + 1] <= n) b++;
+  return b;
+}
+
+// Upper bounds (groups_device.cuh): a call of merge_read_to_group for read n visits the segments of n and, when the
+// mate continues the fragment, those of the mate; each visit creates at most one group and one readgroup entry, and
+// there is one call per pair link plus one for the unpaired share.  Colours: at most 3 more per read.
+__global__ void __launch_bounds__(STG_READ_BLOCK) group_caps_kernel(DevBatchView v, uint32_t* rcap, unsigned long long* total,
+                                                                  int32_t* rj) {
+  const int64_t n = (int64_t)blockIdx.x * STG_READ_BLOCK + threadIdx.x;
+  unsigned long long cap = 0;
+  if (n < v.n_reads) {
+    const uint32_t b = bundle_of_read(v, (uint32_t)n);
+    const uint32_t r0 = v.b_read_off[b], r1 = v.b_read_off[b + 1];
+    const uint32_t s0 = v.r_seg_off[n], ns = v.r_seg_off[n + 1] - s0;
+    const uint32_t p0 = v.r_pair_off[n], np = v.r_pair_off[n + 1] - p0;
+    cap = (unsigned long long)(2 * np + 1) * ns;
+    for (uint32_t p = 0; p < np; p++) {
+      const int32_t m = v.pair_idx[p0 + p];
+      if (m >= 0 && r0 + (uint32_t)m < r1) cap += v.r_seg_off[r0 + m + 1] - v.r_seg_off[r0 + m];
+    }
+    rcap[n] = (uint32_t)cap;
+    // junction rows of the read: "no row" (-1) reads as the sentinel row 0, as in the reference's juncs[] of a read
+    // whose junction was not found (rlink.cpp keeps a pointer; the flattened batch keeps -1)
+    for (uint32_t i = 0; i + 1 < ns; i++) {
+      const uint32_t k = s0 - (uint32_t)n + i;
+      const int32_t j = v.rjunc_idx[k];
+      rj[k] = j < 0 ? 0 : j;
+    }
+  } else if (n == v.n_reads) rcap[n] = 0;
+  // block sum -> one atomic
+  __shared__ unsigned long long sh[STG_READ_BLOCK / 32];
+  for (int o = 16; o; o >>= 1) cap += __shfl_down_sync(0xffffffffu, cap, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cap;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+    for (int i = 0; i < STG_READ_BLOCK / 32; i++) s += sh[i];
+    if (s) atomicAdd(total, s);
+  }
+}
+
+__global__ void __launch_bounds__(128) groups_walk_kernel(DevBatchView v, GroupsView g, JuncParams prm) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= v.n_bundles || (threadIdx.x & 31)) return;
+  const uint32_t b = g.order[w];
+  const uint32_t r0 = v.b_read_off[b], nr = v.b_read_off[b + 1] - r0;
+  const uint32_t j0 = v.b_junc_off[b], nj0 = v.b_junc_off[b + 1] - j0;
+  g.b_startgroup[3 * b] = g.b_startgroup[3 * b + 1] = g.b_startgroup[3 * b + 2] = -1;
+  g.b_ng[b] = 0; g.b_ncol[b] = 0; g.b_napp[b] = 0; g.b_numfrag[b] = 0; g.b_fraglen[b] = 0;
+  if (b == 0) { g.b_ng[v.n_bundles] = 0; g.b_ncol[v.n_bundles] = 0; g.b_napp[v.n_bundles] = 0; }
+  if (nr == 0) return;
+  Grp S;
+  S.nr = (int)nr;
+  S.seg0 = v.r_seg_off[r0]; S.pair0 = v.r_pair_off[r0];
+  const uint32_t i0 = S.seg0 - r0;                                         // intron base of the bundle
+  const uint32_t nintr = (v.r_seg_off[r0 + nr] - S.seg0) - nr;
+  S.r_start = v.r_start + r0; S.r_end = v.r_end + r0; S.r_len = v.r_len + r0; S.seg_off = v.r_seg_off + r0;
+  S.pair_off = v.r_pair_off + r0; S.r_count = v.r_count + r0; S.pair_cnt = v.pair_cnt + S.pair0; S.r_nh = v.r_nh + r0;
+  S.r_flags = v.r_flags + r0;
+  S.strand = g.strand + r0; S.seg_s = g.seg_start + S.seg0; S.seg_e = g.seg_end + S.seg0; S.pair = g.pair + S.pair0;
+  S.rj = g.rj + i0;
+  S.j_start = v.j_start + j0; S.j_end = v.j_end + j0; S.j_nreads = v.jp_nreads + j0; S.j_good = v.jp_nreads_good + j0;
+  S.j_ej = v.jp_ej + j0; S.jp_good = v.jp_good + j0; S.jp_good_strand = v.jp_good_strand + j0;
+  S.jt_strand = g.jt_strand + j0; S.jt_mm = g.jt_mm + j0;
+  S.ap_start = g.ap_start + i0; S.ap_end = g.ap_end + i0; S.ap_strand = g.ap_strand + i0; S.ap_mm = g.ap_mm + i0;
+  S.nj0 = (int)nj0; S.nJ = (int)nj0; S.apcap = (int)nintr;
+  const size_t G0 = g.rcap_off[r0];
+  const uint32_t gcap = g.rcap_off[r0 + nr] - g.rcap_off[r0];
+  S.g_start = g.g_start + G0; S.g_end = g.g_end + G0; S.g_color = g.g_color + G0; S.g_next = g.g_next + G0;
+  S.g_merge = g.g_merge + G0; S.g_grid = g.g_grid + G0; S.g_cov = g.g_cov + G0; S.g_multi = g.g_multi + G0;
+  S.g_alive = g.g_alive + G0;
+  S.ng = 0; S.gcap = (int)gcap;
+  S.eqcol = g.eqcol + G0 + 3 * (size_t)r0; S.ncol = 0; S.ccap = (int)(gcap + 3 * nr);
+  S.rg = g.rg; S.rg_cnt = g.rg_cnt + r0; S.rcap_off = g.rcap_off + r0;
+  S.curr[0] = S.curr[1] = S.curr[2] = -1; S.startg[0] = S.startg[1] = S.startg[2] = -1;
+  S.junctionsupport = prm.junctionsupport; S.bundledist = g.bundledist;
+  S.refstart = v.b_start[b]; S.len = v.b_len[b];
+  S.c1 = v.bpcov + 3 * (size_t)v.b_gbase[b] + v.b_stride[b];
+  S.prm = prm; S.err = 0;
+  if (gcap == 0 || gcap > 0x7fffffffu) { atomicOr(v.err_flag, STG_GERR_GROUPS); return; }
+  double nf = 0, fl = 0;
+  groups_first_half(S, g.jt_perm + j0 + i0, g.jt_inv + j0 + i0, &nf, &fl);
+  if (S.err) { atomicOr(v.err_flag, S.err); return; }
+  g.b_ng[b] = (uint32_t)S.ng; g.b_ncol[b] = (uint32_t)S.ncol; g.b_napp[b] = (uint32_t)(S.nJ - S.nj0);
+  g.b_numfrag[b] = nf; g.b_fraglen[b] = fl;
+  for (int s = 0; s < 3; s++) g.b_startgroup[3 * b + s] = S.startg[s];
+}
+
+// after the scans: b_ng / b_ncol / b_napp are exclusive prefixes
+__global__ void __launch_bounds__(128) groups_colour_kernel(DevBatchView v, GroupsView g) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= v.n_bundles) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t b = g.order[w];
+  const uint32_t r0 = v.b_read_off[b];
+  const size_t G0 = g.rcap_off[r0], C0 = G0 + 3 * (size_t)r0;
+  const size_t Gd = g.b_ng[b], Cd = g.b_ncol[b];
+  const int ng = (int)(g.b_ng[b + 1] - g.b_ng[b]), nc = (int)(g.b_ncol[b + 1] - g.b_ncol[b]);
+  for (int i = lane; i < ng; i += 32) {
+    g.d_g_start[Gd + i] = g.g_start[G0 + i]; g.d_g_end[Gd + i] = g.g_end[G0 + i]; g.d_g_color[Gd + i] = g.g_color[G0 + i];
+    g.d_g_next[Gd + i] = g.g_next[G0 + i]; g.d_g_merge[Gd + i] = g.g_merge[G0 + i]; g.d_g_cov[Gd + i] = g.g_cov[G0 + i];
+    g.d_g_multi[Gd + i] = g.g_multi[G0 + i]; g.d_g_alive[Gd + i] = g.g_alive[G0 + i];
+    g.d_color2[Gd + i] = g.g_color[G0 + i]; g.d_negp[Gd + i] = 0.f;
+  }
+  for (int i = lane; i < 3 * ng; i += 32) g.d_g2b[3 * Gd + i] = -1;
+  for (int i = lane; i < nc; i += 32) {
+    const int32_t e = g.eqcol[C0 + i];
+    g.d_eqcol[Cd + i] = e; g.d_eq2[Cd + i] = e; g.d_eqneg[Cd + i] = -1; g.d_eqpos[Cd + i] = -1; g.d_bundlecol[Cd + i] = -1;
+  }
+  __syncwarp();
+  if (lane) return;
+  for (int s = 0; s < 3; s++) { g.b_nbun[3 * b + s] = 0; g.b_nbn[3 * b + s] = 0; }
+  if (ng == 0) return;
+  Grp2 S;
+  S.ng = ng; S.ncol = nc; S.bundledist = g.bundledist; S.startg = g.b_startgroup + 3 * (size_t)b;
+  S.g_start = g.d_g_start + Gd; S.g_end = g.d_g_end + Gd; S.g_next = g.d_g_next + Gd; S.g_cov = g.d_g_cov + Gd;
+  S.g_multi = g.d_g_multi + Gd;
+  S.color = g.d_color2 + Gd; S.negp = g.d_negp + Gd;
+  S.eq = g.d_eq2 + Cd; S.eqneg = g.d_eqneg + Cd; S.eqpos = g.d_eqpos + Cd; S.bundlecol = g.d_bundlecol + Cd;
+  S.g2b = g.d_g2b + 3 * Gd;
+  S.bun_len = g.bun_len + 3 * Gd; S.bun_start = g.bun_start + 3 * Gd; S.bun_last = g.bun_last + 3 * Gd;
+  S.bun_cov = g.bun_cov + 3 * Gd; S.bun_multi = g.bun_multi + 3 * Gd;
+  S.bn_s = g.bn_start + 3 * Gd; S.bn_e = g.bn_end + 3 * Gd; S.bn_cov = g.bn_cov + 3 * Gd; S.bn_next = g.bn_next + 3 * Gd;
+  groups_second_half(S);
+  for (int s = 0; s < 3; s++) { g.b_nbun[3 * b + s] = (uint32_t)S.nbun[s]; g.b_nbn[3 * b + s] = (uint32_t)S.nbn[s]; }
+}
+
+// rg_off = exclusive prefix of rg_cnt
+__global__ void __launch_bounds__(256) groups_rg_kernel(DevBatchView v, GroupsView g) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= v.n_reads) return;
+  const uint32_t cnt = g.rg_off[n + 1] - g.rg_off[n];
+  const size_t src = g.rcap_off[n], dst = g.rg_off[n];
+  for (uint32_t k = 0; k < cnt; k++) g.d_rg[dst + k] = g.rg[src + k];
+}
+
+__global__ void __launch_bounds__(128) groups_junc_kernel(DevBatchView v, GroupsView g) {
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= v.n_bundles) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t r0 = v.b_read_off[b], nr = v.b_read_off[b + 1] - r0;
+  const uint32_t j0 = v.b_junc_off[b], nj0 = v.b_junc_off[b + 1] - j0;
+  const uint32_t napp = g.b_napp[b + 1] - g.b_napp[b];
+  const uint32_t i0 = nr ? v.r_seg_off[r0] - r0 : 0;
+  const size_t o0 = (size_t)j0 + g.b_napp[b];
+  const int32_t* perm = g.jt_perm + j0 + i0;
+  for (uint32_t k = lane; k < nj0 + napp; k += 32) {
+    const uint32_t r = nr ? (uint32_t)perm[k] : k;   // a bundle without reads keeps the order of the junction pass
+    const size_t o = o0 + k;
+    if (r < nj0) {
+      const size_t j = (size_t)j0 + r;
+      g.oj_start[o] = v.j_start[j]; g.oj_end[o] = v.j_end[j]; g.oj_strand[o] = g.jt_strand[j];
+      g.oj_nreads[o] = v.jp_nreads[j]; g.oj_nreads_good[o] = v.jp_nreads_good[j]; g.oj_left[o] = v.jp_left[j];
+      g.oj_right[o] = v.jp_right[j]; g.oj_nm[o] = v.j_nm[j]; g.oj_mm[o] = g.jt_mm[j];
+    } else {
+      const size_t a = (size_t)i0 + (r - nj0);
+      g.oj_start[o] = g.ap_start[a]; g.oj_end[o] = g.ap_end[a]; g.oj_strand[o] = g.ap_strand[a];
+      g.oj_nreads[o] = 0; g.oj_nreads_good[o] = 0; g.oj_left[o] = 0; g.oj_right[o] = 0; g.oj_nm[o] = 0;
+      g.oj_mm[o] = g.ap_mm[a] ? -1.0 : 0.0;
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_group_caps(const DevBatchView& v, uint32_t* rcap, unsigned long long* total, int32_t* rj, cudaStream_t st) {
+  group_caps_kernel<<<(unsigned)((v.n_reads + 1 + STG_READ_BLOCK - 1) / STG_READ_BLOCK), STG_READ_BLOCK, 0, st>>>(v, rcap, total, rj);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, cudaStream_t st) {
+  if (v.n_bundles == 0) return cudaSuccess;
+  groups_walk_kernel<<<(unsigned)((v.n_bundles + 3) / 4), 128, 0, st>>>(v, g, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_groups_finish(const DevBatchView& v, const GroupsView& g, cudaStream_t st) {
+  if (v.n_bundles == 0) return cudaSuccess;
+  groups_colour_kernel<<<(unsigned)((v.n_bundles + 3) / 4), 128, 0, st>>>(v, g);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (v.n_reads) groups_rg_kernel<<<(unsigned)((v.n_reads + 255) / 256), 256, 0, st>>>(v, g);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  groups_junc_kernel<<<(unsigned)((v.n_bundles + 3) / 4), 128, 0, st>>>(v, g);
+  return cudaGetLastError();
+}

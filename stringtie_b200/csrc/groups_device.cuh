@@ -1,0 +1,777 @@
+// groups_device.cuh — SURVEY.md §8 rows a8 + a9 for ONE bundle: the read loop of build_graphs() (per-read junction
+// repair, un-pairing, un-stranding, add_read_to_group, fragment counting), the merging of neighbouring groups, the
+// colour pass over the three strand lanes and the creation of bundles / bundlenodes.
+//
+// Reference (CPU, sequential per bundle; short-read de novo path: no --viral, --mix, -L, guides):
+//   read loop                                   rlink.cpp:14845-15127
+//   add_read_to_group / merge_read_to_group     rlink.cpp:1633-1727, 1281-1631;  merge_fwd_groups :1246-1278
+//   re-sort of the junction table               rlink.cpp:15122-15125 (GList::Sort -> gclib/GVec.hh:896-920, not stable)
+//   merging of groups closer than bundledist    rlink.cpp:15134-15164
+//   colour pass, set_strandcol, neg_prop        rlink.cpp:15196-15299, 1028-1056, 984-1026
+//   create_bundle / add_group_to_bundle         rlink.cpp:15340-15427, 1058-1095
+//
+// The loop is sequential in the reference and its state flows both ways between the three parts (the repair of read n
+// looks at what earlier reads did to the junction table, merge_read_to_group un-pairs reads), so this first CUDA
+// version keeps ONE walker per bundle and lets the 60 000 bundles of a batch run side by side (group_kernels.cu).
+// Pointers of the reference become indices: group = slot in the bundle's group arrays (== CGroup::grid at creation),
+// junction = row of the bundle's table, rows >= nj0 being the ones appended here.
+// The functions are __host__ __device__ so that tools/groups_hostcheck.cu can step through them on a CPU-only box
+// during development; libstgpu only ever calls them from kernels.
+#pragma once
+#include "stgpu_internal.h"
+#include <math.h>
+
+#ifdef __CUDA_ARCH__
+#define STG_FSUB(a, b) __fsub_rn((a), (b))
+#else
+#define STG_FSUB(a, b) ((a) - (b))
+#endif
+#define STG_HD __host__ __device__ __forceinline__
+#define STG_HDN __host__ __device__
+
+#define STG_GERR_GROUPS 0x100u    // capacity of the group / colour / readgroup / appended-junction arrays exceeded
+#define STG_LONGINTRONANCHOR 25u  // rlink.h:32
+
+// get_cov(1, a, b, bpcov), rlink.cpp:1830-1838, on lane 1 of the bundle (blocked clamped prefix, BSIZE = 10000)
+STG_HD double cov_all(const float* __restrict__ c, uint32_t a, uint32_t b) {
+  const int m = (int)((b + 1) / STG_BSIZE);
+  const int k = (int)(a / STG_BSIZE);
+  double cov = 0;
+  for (int i = k + 1; i <= m; i++) cov += (double)c[(size_t)i * STG_BSIZE - 1];
+  cov += (double)STG_FSUB(c[b + 1], c[a]);
+  if (cov < 0) cov = 0;
+  return cov;
+}
+
+// good_junc, rlink.cpp:13967-14070, !longreads, on the fields of one row; returns the verdict and the strand the
+// reference would leave behind
+STG_HDN inline bool good_junc_row(uint32_t jstart, uint32_t jend, int8_t strand, int8_t guide_match, double nreads, double good,
+                                  double nm, double ls, double rs, int64_t refstart, const float* __restrict__ c1, int64_t len,
+                                  const JuncParams& p, int8_t* strand_out) {
+  *strand_out = strand;
+  if (p.eonly && !guide_match) { *strand_out = 0; return false; }
+  if (guide_match) return true;
+  if (good < (double)p.junctionthr) { *strand_out = 0; return false; }
+  bool mismatch = false;
+  if (nm != 0.0 && round(nm) == round(nreads)) {
+    mismatch = true;
+    if (jend - jstart > 100000u /*longintron*/ && nreads < 100 * 0.1 /*CHI_WIN*ERROR_PERC*/) { *strand_out = 0; return false; }
+  }
+  const float mult = (float)(1 / 0.1);
+  const int bw = 5;
+  int j = (int)((int64_t)jstart - refstart);
+  double lleft = 0, lright = 0;
+  if (j + bw + 1 < len && j >= bw) {
+    lleft = cov_all(c1, (uint32_t)(j - bw + 1), (uint32_t)j);
+    lright = cov_all(c1, (uint32_t)(j + 1), (uint32_t)(j + bw));
+  }
+  if (lleft > 1 / 0.1 && ls * mult < 0.1 * lleft && (mismatch || lright > lleft * (1 - 0.1))) { *strand_out = 0; return false; }
+  j = (int)((int64_t)jend - refstart - 1);
+  double rleft = 0, rright = 0;
+  if (j + bw + 1 < len && j >= bw) {
+    rleft = cov_all(c1, (uint32_t)(j - bw + 1), (uint32_t)j);
+    rright = cov_all(c1, (uint32_t)(j + 1), (uint32_t)(j + bw));
+  }
+  if (rright > 1 / 0.1 && rs * mult < rright * 0.1 && (mismatch || rleft > rright * (1 - 0.1))) { *strand_out = 0; return false; }
+  if (nreads * 10 < 0.1 * ls || nreads * 10 < 0.1 * rs) { *strand_out = 0; return false; }
+  return true;
+}
+
+// ---- state of one bundle's walk --------------------------------------------------------------------------------
+struct Grp {
+  // reads: pointers already offset to the first read / segment / pair link / intron of the bundle
+  const uint32_t *r_start, *r_end, *r_len, *seg_off, *pair_off;
+  const float *r_count, *pair_cnt;
+  const int16_t* r_nh;
+  const uint8_t* r_flags;
+  int8_t* strand; uint32_t *seg_s, *seg_e; int32_t *pair, *rj;   // mutable copies
+  uint32_t seg0, pair0;
+  int nr;
+  // junction table: rows [0, nj0) are the bundle's rows after the junction pass, rows [nj0, nJ) are appended here
+  const uint32_t *j_start, *j_end;
+  const double *j_nreads, *j_good;
+  const int32_t* j_ej;
+  const int8_t *jp_good, *jp_good_strand;
+  int8_t* jt_strand; double* jt_mm;
+  uint32_t *ap_start, *ap_end; int8_t *ap_strand, *ap_mm;
+  int nj0, nJ, apcap;
+  // groups, colours, readgroup
+  uint32_t *g_start, *g_end; int32_t *g_color, *g_next, *g_merge, *g_grid; float *g_cov, *g_multi; int8_t* g_alive;
+  int ng, gcap;
+  int32_t* eqcol; int ncol, ccap;
+  int32_t* rg; uint32_t* rg_cnt; const uint32_t* rcap_off;   // rg is batch-wide; rg_cnt / rcap_off offset to the bundle
+  int32_t curr[3], startg[3];
+  uint32_t junctionsupport, bundledist;
+  int64_t refstart, len;
+  const float* c1;
+  JuncParams prm;
+  uint32_t err;
+
+  STG_HD int nseg(int n) const { return (int)(seg_off[n + 1] - seg_off[n]); }
+  STG_HD uint32_t segi(int n, int i) const { return seg_off[n] - seg0 + (uint32_t)i; }
+  STG_HD int njunc(int n) const { return nseg(n) - 1; }
+  STG_HD uint32_t rji(int n, int i) const { return seg_off[n] - seg0 - (uint32_t)n + (uint32_t)i; }
+  STG_HD int npair(int n) const { return (int)(pair_off[n + 1] - pair_off[n]); }
+  STG_HD uint32_t pairi(int n, int p) const { return pair_off[n] - pair0 + (uint32_t)p; }
+  STG_HD uint32_t slen(int n, int i) const { const uint32_t k = segi(n, i); return seg_e[k] - seg_s[k] + 1u; }
+  STG_HD bool unitig(int n) const { return (r_flags[n] & STG_RF_UNITIG) != 0; }
+  STG_HD int8_t jstrand(int k) const { return k < nj0 ? jt_strand[k] : ap_strand[k - nj0]; }
+  STG_HD void set_jstrand(int k, int8_t s) { if (k < nj0) jt_strand[k] = s; else ap_strand[k - nj0] = s; }
+  STG_HD uint32_t jstart(int k) const { return k < nj0 ? j_start[k] : ap_start[k - nj0]; }
+  STG_HD uint32_t jend(int k) const { return k < nj0 ? j_end[k] : ap_end[k - nj0]; }
+  STG_HD double jnreads(int k) const { return k < nj0 ? j_nreads[k] : 0.0; }
+  STG_HD double jgood(int k) const { return k < nj0 ? j_good[k] : 0.0; }
+  STG_HD bool jmm_neg(int k) const { return k < nj0 ? jt_mm[k] < 0 : ap_mm[k - nj0] != 0; }
+  STG_HD void set_jmm_neg(int k) { if (k < nj0) jt_mm[k] = -1; else ap_mm[k - nj0] = 1; }
+  STG_HD int ej(int k) const { return k < nj0 ? j_ej[k] : k; }
+  STG_HD int8_t rjstrand(int n, int i) const { return jstrand(rj[rji(n, i)]); }   // CReadAln::juncs[i]->strand
+};
+
+// good_junc, mutating like the reference (rlink.cpp:13967): on failure the junction loses its strand.  For the rows of
+// the junction pass the verdict was computed once per row by junc_pass_kernel (it only depends on the row and bpcov,
+// and a row is only evaluated while its strand is still the one the pass left); appended rows are evaluated here.
+STG_HD bool good_junc_mut(Grp& S, int j) {
+  int8_t s;
+  bool g;
+  if (j < S.nj0) { g = S.jp_good[j] == 1; s = S.jp_good_strand[j]; }
+  else g = good_junc_row(S.jstart(j), S.jend(j), S.jstrand(j), 0, 0.0, 0.0, 0.0, 0.0, 0.0, S.refstart, S.c1, S.len, S.prm, &s);
+  S.set_jstrand(j, s);
+  return g;
+}
+
+STG_HD int new_color(Grp& S, int* color) {   // eqcol.Add(color); color++
+  if (S.ncol < S.ccap) S.eqcol[S.ncol++] = *color;
+  else S.err |= STG_GERR_GROUPS;
+  return (*color)++;
+}
+
+STG_HD int new_group(Grp& S, uint32_t start, uint32_t end, int color, float cov, float multi) {
+  int g = S.ng;
+  if (g < S.gcap) S.ng++;
+  else { S.err |= STG_GERR_GROUPS; g = S.gcap - 1; }
+  S.g_start[g] = start; S.g_end[g] = end; S.g_color[g] = color; S.g_next[g] = -1;
+  S.g_cov[g] = cov; S.g_multi[g] = multi; S.g_alive[g] = 1; S.g_merge[g] = g;
+  return g;
+}
+
+STG_HD void rg_add(Grp& S, int n, int g) {
+  const uint32_t base = S.rcap_off[n], cap = S.rcap_off[n + 1] - base, k = S.rg_cnt[n];
+  if (k < cap) { S.rg[(size_t)base + k] = g; S.rg_cnt[n] = k + 1; }
+  else S.err |= STG_GERR_GROUPS;
+}
+
+STG_HD int find_color(const Grp& S, int c) {
+  while (S.eqcol[c] != c) c = S.eqcol[c];
+  return c;
+}
+
+// rlink.cpp:1246-1278
+STG_HD void merge_fwd_groups(Grp& S, int g1, int g2) {
+  S.g_end[g1] = S.g_end[g2];
+  int c1 = find_color(S, S.g_color[g1]), c2 = find_color(S, S.g_color[g2]);
+  S.g_color[g2] = c2;
+  if (c1 < c2) S.eqcol[c2] = c1;
+  else if (c1 > c2) { S.eqcol[c1] = c2; c1 = c2; }
+  S.g_color[g1] = c1;
+  S.g_cov[g1] += S.g_cov[g2];
+  S.g_next[g1] = S.g_next[g2];
+  S.g_merge[g2] = g1;
+  S.g_multi[g1] += S.g_multi[g2];
+  S.g_alive[g2] = 0;
+}
+
+STG_HD void unpair(Grp& S, int n, int p, int np) {   // readlist[n]->pair_idx[p] = -1 and the mirror entry of np
+  S.pair[S.pairi(n, p)] = -1;
+  const int m = S.npair(np);
+  for (int j = 0; j < m; j++)
+    if (S.pair[S.pairi(np, j)] == n) { S.pair[S.pairi(np, j)] = -1; break; }
+}
+
+STG_HD bool keep_exon(const Grp& S, int n, int i) {   // the small-exon rule, rlink.cpp:1327-1342 (short reads)
+  if (S.slen(n, i) >= S.junctionsupport) return true;
+  const int nj = S.njunc(n);
+  if (i < nj) {
+    if (!S.rjstrand(n, i) && (!i || !S.rjstrand(n, i - 1))) return false;
+  } else if (nj) {
+    if (!S.rjstrand(n, i - 1)) return false;
+  }
+  return true;
+}
+
+// the mate np (> n) continues the fragment of read n: rlink.cpp:1561-1567 / 1604-1608
+STG_HD bool mate_continues(const Grp& S, int n, int np, uint32_t localdist) {
+  return np != -1 && np > n && S.r_end[n] < S.r_start[np] && S.r_end[n] + localdist > S.r_start[np] &&
+         (S.slen(np, 0) >= S.junctionsupport || (S.njunc(np) && S.rjstrand(np, 0)));
+}
+
+// rlink.cpp:1281-1631
+STG_HDN inline int merge_read_to_group(Grp& S, int n, int np, int p, float readcov, int sno, int readcol, int color, int* usedcol) {
+  const uint32_t localdist = S.bundledist + STG_LONGINTRONANCHOR;   // !longreads && !mixedMode
+  if (np > -1 && np < n && S.r_end[np] < S.r_start[n] && S.r_end[np] + localdist > S.r_start[n] &&
+      (S.slen(np, S.nseg(np) - 1) >= S.junctionsupport || (S.njunc(np) && S.rjstrand(np, S.njunc(np) - 1))) &&
+      (S.slen(n, 0) >= S.junctionsupport || (S.njunc(n) && S.rjstrand(n, 0))))
+    return color;   // the pair was placed as one fragment when np was processed
+  bool first = true;
+  int currgroup = S.curr[sno];
+  if (currgroup != -1) {
+    int lastgroup = -1;
+    const uint32_t rstart = S.r_start[n];
+    while (currgroup != -1 && rstart > S.g_end[currgroup]) { lastgroup = currgroup; currgroup = S.g_next[currgroup]; }
+    if (currgroup == -1 || S.seg_e[S.segi(n, 0)] < S.g_start[currgroup]) currgroup = lastgroup;
+    int thisgroup = currgroup;
+    int ncoord = S.nseg(n);
+    int lastpushedgroup = -1;
+    int i = 0;
+    while (i < ncoord) {
+      bool keep = true;
+      if (S.slen(n, i) < S.junctionsupport) {
+        const int nj = S.njunc(n);
+        if (i < nj) {
+          if (!S.rjstrand(n, i)) {
+            if (!i || !S.rjstrand(n, i - 1)) {
+              keep = false;
+              if (!i && lastgroup != -1) currgroup = lastgroup;
+            }
+          }
+        } else if (nj) {
+          if (!S.rjstrand(n, i - 1)) keep = false;
+        }
+      }
+      if (keep) {
+        const uint32_t ss = S.seg_s[S.segi(n, i)], se = S.seg_e[S.segi(n, i)];
+        while (thisgroup != -1 && ss > S.g_end[thisgroup]) { lastgroup = thisgroup; thisgroup = S.g_next[thisgroup]; }
+        if (thisgroup != -1 && se + localdist >= S.g_start[thisgroup]) {
+          if (!i) {
+            int gr = S.g_grid[thisgroup];
+            while (S.g_merge[gr] != gr) gr = S.g_merge[gr];
+            S.g_grid[thisgroup] = gr;
+            const uint32_t base = S.rcap_off[n], cnt = S.rg_cnt[n];
+            for (uint32_t g = 0; g < cnt; g++) {
+              int x = S.rg[(size_t)base + g];
+              while (S.g_merge[x] != x) x = S.g_merge[x];
+              if (x == gr) { first = false; break; }
+            }
+            if (np > -1 && S.r_nh[np] && np < n) {
+              const int thiscol = find_color(S, S.g_color[thisgroup]);
+              S.g_color[thisgroup] = thiscol;
+              if (thiscol != readcol) {
+                unpair(S, n, p, np);
+                readcol = usedcol[sno];
+                if (readcol < 0) { usedcol[sno] = color; readcol = new_color(S, &color); }
+              }
+            }
+          }
+          if (S.r_nh[n] > 1) S.g_multi[thisgroup] += readcov * (float)(se - ss + 1u);
+          if (ss < S.g_start[thisgroup]) S.g_start[thisgroup] = ss;
+          int nextgroup = S.g_next[thisgroup];
+          while (nextgroup != -1 && se >= S.g_start[nextgroup]) {
+            merge_fwd_groups(S, thisgroup, nextgroup);
+            nextgroup = S.g_next[thisgroup];
+          }
+          if (se > S.g_end[thisgroup]) S.g_end[thisgroup] = se;
+          int gc = find_color(S, S.g_color[thisgroup]);
+          S.g_color[thisgroup] = gc;
+          if (readcol != gc) {
+            if (i && !S.rjstrand(n, i - 1)) readcol = gc;
+            else if (readcol < gc) { S.eqcol[gc] = readcol; S.g_color[thisgroup] = readcol; }
+            else { S.eqcol[readcol] = gc; readcol = gc; }
+          }
+          if (S.g_grid[thisgroup] != lastpushedgroup) {
+            if (first) rg_add(S, n, S.g_grid[thisgroup]);
+            lastpushedgroup = S.g_grid[thisgroup];
+          }
+          S.g_cov[thisgroup] += (float)(se - ss + 1u) * readcov;
+        } else {
+          if (!i && np > -1 && S.r_nh[np] && np < n) {
+            unpair(S, n, p, np);
+            readcol = usedcol[sno];
+            if (readcol < 0) { usedcol[sno] = color; readcol = new_color(S, &color); }
+          } else if (i && !S.rjstrand(n, i - 1)) {
+            usedcol[sno] = color; readcol = new_color(S, &color);
+          }
+          float multi = 0;
+          if (S.r_nh[n] > 1) multi = readcov * (float)(se - ss + 1u);
+          const int ngroup = new_group(S, ss, se, readcol, (float)(se - ss + 1u) * readcov, multi);
+          S.g_grid[ngroup] = ngroup;
+          if (lastgroup != -1) S.g_next[lastgroup] = ngroup;
+          S.g_next[ngroup] = thisgroup;
+          rg_add(S, n, ngroup);
+          lastpushedgroup = ngroup;
+          thisgroup = ngroup;
+        }
+        if (i == ncoord - 1 && mate_continues(S, n, np, localdist)) {
+          n = np; np = -1;
+          ncoord = S.nseg(n);
+          first = true;
+          if (S.r_start[n] > S.g_end[thisgroup]) {
+            int nextgroup = S.g_next[thisgroup];
+            while (nextgroup != -1 && S.r_start[n] >= S.g_start[nextgroup]) {
+              merge_fwd_groups(S, thisgroup, nextgroup);
+              nextgroup = S.g_next[thisgroup];
+            }
+            if (S.r_start[n] > S.g_end[thisgroup]) S.g_end[thisgroup] = S.r_start[n];
+          }
+          lastpushedgroup = -1;
+          i = -1;
+        }
+      }
+      i++;
+    }
+  } else {   // first group of this strand lane
+    if (np > -1 && S.r_nh[np] && np < n) {
+      unpair(S, n, p, np);
+      readcol = usedcol[sno];
+      if (readcol < 0) { usedcol[sno] = color; readcol = new_color(S, &color); }
+    }
+    int ncoord = S.nseg(n);
+    int lastgroup = -1;
+    float multi = 0;
+    if (S.r_nh[n] > 1) multi = readcov;
+    int i = 0;
+    while (i < ncoord) {
+      const bool keep = keep_exon(S, n, i);
+      if (!i || keep) {
+        if (i && !S.rjstrand(n, i - 1)) { usedcol[sno] = color; readcol = new_color(S, &color); }
+        const uint32_t ss = S.seg_s[S.segi(n, i)], se = S.seg_e[S.segi(n, i)];
+        const float flen = (float)(se - ss + 1u);
+        const int ngroup = new_group(S, ss, se, readcol, flen * readcov, flen * multi);
+        S.g_grid[ngroup] = ngroup;
+        if (lastgroup != -1) S.g_next[lastgroup] = ngroup;
+        else currgroup = ngroup;
+        lastgroup = ngroup;
+        if (keep) {
+          rg_add(S, n, ngroup);
+          if (i == ncoord - 1 && mate_continues(S, n, np, localdist)) {
+            n = np; np = -1;
+            ncoord = S.nseg(n);
+            if (S.seg_e[S.segi(n, 0)] > S.g_end[lastgroup]) {
+              S.g_end[lastgroup] = S.seg_e[S.segi(n, 0)];
+              if (first) rg_add(S, n, ngroup);
+              S.g_cov[lastgroup] += (float)S.slen(n, 0) * readcov;
+            }
+            i = 0;
+          }
+        }
+      }
+      i++;
+    }
+  }
+  S.curr[sno] = currgroup;
+  if (S.startg[sno] == -1) S.startg[sno] = currgroup;
+  return color;
+}
+
+// rlink.cpp:1633-1727
+STG_HDN inline int add_read_to_group(Grp& S, int n, int color) {
+  int usedcol[3] = {-1, -1, -1};
+  float single_count = S.r_count[n];
+  const int npr = S.npair(n);
+  for (int p = 0; p < npr; p++) {
+    int sno = (int)S.strand[n] + 1;
+    int np = S.pair[S.pairi(n, p)];
+    if (np > -1 && S.r_nh[np]) {
+      const int snop = (int)S.strand[np] + 1;
+      if (sno != snop) {
+        if (sno == 1) sno = snop;
+        else if (snop != 1) { unpair(S, n, p, np); np = -1; }
+      }
+      if (np > -1) {
+        const float pc = S.pair_cnt[S.pairi(n, p)];
+        single_count -= pc;
+        int readcol = usedcol[sno];
+        if (np < n) {
+          int grouppair = S.rg[(size_t)S.rcap_off[np]];
+          while (S.g_merge[grouppair] != grouppair) grouppair = S.g_merge[grouppair];
+          S.rg[(size_t)S.rcap_off[np]] = grouppair;
+          readcol = find_color(S, S.g_color[grouppair]);
+          S.g_color[grouppair] = readcol;
+        } else if (usedcol[sno] < 0) { usedcol[sno] = color; readcol = new_color(S, &color); }
+        double readcov = 0;
+        if (!S.unitig(n)) readcov = pc;
+        color = merge_read_to_group(S, n, np, p, (float)readcov, sno, readcol, color, usedcol);
+      }
+    }
+  }
+  if (single_count > 0.000001 /*epsilon, rlink.h:25*/) {
+    const int sn = (int)S.strand[n] + 1;
+    int readcol = usedcol[sn];
+    if (readcol < 0) { usedcol[sn] = color; readcol = new_color(S, &color); }
+    double readcov = 0;
+    if (!S.unitig(n)) readcov = single_count;
+    color = merge_read_to_group(S, n, -1, -1, (float)readcov, sn, readcol, color, usedcol);
+  }
+  return color;
+}
+
+// CJunction::operator< (bundle.h:155-162) through GList::DefaultCompareProc (gclib/GList.hh:85-90)
+STG_HD int junc_default_cmp(const Grp& S, int a, int b) {
+  const uint32_t sa = S.jstart(a), sb = S.jstart(b);
+  if (sa != sb) return sa < sb ? -1 : 1;
+  const uint32_t ea = S.jend(a), eb = S.jend(b);
+  if (ea != eb) return ea < eb ? -1 : 1;
+  const int8_t ta = S.jstrand(a), tb = S.jstrand(b);
+  if (ta != tb) return ta > tb ? -1 : 1;
+  return 0;
+}
+
+// the reference's quicksort (gclib/GVec.hh:896-920: Hoare partition, middle pivot, not stable) on a row list; the
+// sub-ranges of a partition are disjoint, so the order in which they are finished does not change the permutation
+STG_HDN inline void sort_rows_ref(const Grp& S, int32_t* list, int n) {
+  int stack[2 * 48];
+  int sp = 0;
+  if (n < 2) return;
+  stack[sp++] = 0; stack[sp++] = n - 1;
+  while (sp) {
+    const int R = stack[--sp], L = stack[--sp];
+    int I = L, Jx = R;
+    const int P = list[L + ((R - L) >> 1)];
+    do {
+      while (junc_default_cmp(S, list[I], P) < 0) I++;
+      while (junc_default_cmp(S, list[Jx], P) > 0) Jx--;
+      if (I <= Jx) {
+        const int t = list[I]; list[I] = list[Jx]; list[Jx] = t;
+        I++; Jx--;
+      }
+    } while (I <= Jx);
+    const bool left_todo = L < Jx, right_todo = I < R;
+    if (left_todo && right_todo) {
+      if (Jx - L > R - I) { stack[sp++] = L; stack[sp++] = Jx; stack[sp++] = I; stack[sp++] = R; }
+      else { stack[sp++] = I; stack[sp++] = R; stack[sp++] = L; stack[sp++] = Jx; }
+    } else if (left_todo) { stack[sp++] = L; stack[sp++] = Jx; }
+    else if (right_todo) { stack[sp++] = I; stack[sp++] = R; }
+  }
+}
+
+// the repair of the junctions of read n, its un-pairing and un-stranding: rlink.cpp:14845-15092.  Returns `keep`.
+STG_HDN inline bool repair_read(Grp& S, int n) {
+  bool keep = true;
+  const int nj = S.njunc(n);
+  for (int i = 0; i < nj; i++) {
+    const int jd = S.rj[S.rji(n, i)];
+    const bool changeright = S.jgood(jd) < 0;
+    const bool changeleft = S.jnreads(jd) < 0;
+    if (S.jstrand(jd)) {
+      if (!good_junc_mut(S, jd)) S.set_jmm_neg(jd);
+      if (changeleft || changeright) S.set_jstrand(jd, 0);
+      if (S.jmm_neg(jd)) S.set_jstrand(jd, 0);
+    }
+    if (!S.jstrand(jd)) {
+      if (changeleft || changeright) {
+        const uint32_t k0 = S.segi(n, i), k1 = S.segi(n, i + 1);
+        uint32_t newstart = S.seg_e[k0], newend = S.seg_s[k1];
+        int jk = -1, ek = -1;
+        if (changeleft) {
+          jk = abs((int)S.jnreads(jd));
+          if (S.jnreads(jk) < 0) newstart = S.seg_s[k0] - 1;
+          else { newstart = S.jstart(jk); if (S.jstrand(jk)) jk = -1; }
+        }
+        if (changeright) {
+          ek = abs((int)S.jgood(jd));
+          const int er = S.ej(ek);
+          if (S.jgood(er) < 0) newend = S.seg_e[k1] + 1;
+          else { newend = S.jend(er); if (S.jstrand(er)) ek = -1; }
+        }
+        if (newstart >= S.seg_s[k0] && newend <= S.seg_e[k1] && newstart <= newend) {
+          S.seg_e[k0] = newstart;
+          S.seg_s[k1] = newend;
+          if (!S.jmm_neg(jd)) {
+            const int8_t rs = S.strand[n];
+            int found = -1;
+            bool search = false;
+            if (jk > 0) {   // neighbours of jk in start order, then the appended rows
+              search = true;
+              for (int k = jk; found < 0 && k > 0 && S.jstart(k) == newstart; k--)
+                if (rs == S.jstrand(k) && S.jend(k) == newend) found = k;
+              for (int k = jk + 1; found < 0 && k < S.nJ && S.jstart(k) == newstart; k++)
+                if (rs == S.jstrand(k) && S.jend(k) == newend) found = k;
+            } else if (ek > 0) {   // neighbours of ek in end order
+              search = true;
+              for (int k = ek; found < 0 && k > 0 && S.jend(S.ej(k)) == newend; k--) {
+                const int r = S.ej(k);
+                if (rs == S.jstrand(r) && S.jstart(r) == newstart) found = r;
+              }
+              for (int k = ek + 1; found < 0 && k < S.nJ && S.jend(S.ej(k)) == newend; k++) {
+                const int r = S.ej(k);
+                if (rs == S.jstrand(r) && S.jstart(r) == newstart) found = r;
+              }
+            }
+            if (search) {
+              for (int k = S.nj0; found < 0 && k < S.nJ; k++)
+                if (rs == S.jstrand(k) && S.jstart(k) == newstart && S.jend(k) == newend) found = k;
+              if (found < 0) {   // new CJunction(newstart, newend, strand): rlink.cpp:14958-14969, 15000-15011
+                const int a = S.nJ - S.nj0;
+                if (a < S.apcap) {
+                  S.ap_start[a] = newstart; S.ap_end[a] = newend; S.ap_strand[a] = rs; S.ap_mm[a] = 0;
+                  found = S.nJ++;
+                } else S.err |= STG_GERR_GROUPS;
+              }
+              if (found >= 0) S.rj[S.rji(n, i)] = found;
+            }
+          }
+        }
+      }
+      if (keep) {   // a bad junction: the read loses its mates (rlink.cpp:15027-15043)
+        const int npr = S.npair(n);
+        for (int p = 0; p < npr; p++) {
+          const int np = S.pair[S.pairi(n, p)];
+          if (np > -1) {
+            unpair(S, n, p, np);
+            if (!S.njunc(np)) S.strand[np] = 0;
+          }
+        }
+        keep = false;
+      }
+    }
+  }
+  if (!keep) {
+    if (S.strand[n]) {
+      bool keepstrand = false;
+      for (int j = 0; j < nj; j++) if (S.rjstrand(n, j)) { keepstrand = true; break; }
+      if (!keepstrand) S.strand[n] = 0;
+    }
+  } else if (!nj && S.strand[n]) {   // unspliced stranded read: it keeps its strand only if a later mate supports it
+    const int npr = S.npair(n);
+    if (npr) {
+      bool keepstrand = false;
+      for (int p = 0; p < npr && !keepstrand; p++) {
+        const int np = S.pair[S.pairi(n, p)];
+        if (np > -1 && n < np) {
+          const int njp = S.njunc(np);
+          if (!njp) {
+            if (S.strand[np] == S.strand[n]) keepstrand = true;
+          } else {
+            for (int j = 0; j < njp; j++) {
+              const int jx = S.rj[S.rji(np, j)];
+              if (S.jstrand(jx) && good_junc_mut(S, jx)) { keepstrand = true; break; }
+            }
+            if (!keepstrand) S.strand[np] = 0;
+          }
+        }
+      }
+      if (!keepstrand) S.strand[n] = 0;
+    }
+  }
+  return keep;
+}
+
+// Walks the reads of the bundle in order.  jt_perm / jt_inv: [nj0 + apcap] scratch for the re-sort of the junction
+// table; on return jt_perm[k] = working row of the k-th row of the re-sorted table and rj[] holds re-sorted rows.
+STG_HDN inline void groups_first_half(Grp& S, int32_t* jt_perm, int32_t* jt_inv, double* num_fragments_out, double* frag_len_out) {
+  int color = 0;
+  double num_fragments = 0, frag_len = 0;
+  for (int n = 0; n < S.nr && !S.err; n++) {
+    const bool keep = repair_read(S, n);
+    color = add_read_to_group(S, n, color);
+    // fragment counting: rlink.cpp:15105-15116
+    if (!S.unitig(n)) frag_len += (double)((float)S.r_len[n] * S.r_count[n]);
+    double single_count = S.r_count[n];
+    if (keep) {
+      const int npr = S.npair(n);
+      for (int p = 0; p < npr; p++) {
+        const int pi = S.pair[S.pairi(n, p)];
+        if (pi != -1 && n > pi && S.r_nh[pi]) single_count -= S.pair_cnt[S.pairi(n, p)];
+      }
+    }
+    if (!S.unitig(n) && single_count > 0.000001) num_fragments += single_count;
+  }
+  *num_fragments_out = num_fragments; *frag_len_out = frag_len;
+  if (S.err) return;
+
+  // merge groups that are close together: rlink.cpp:15134-15164 (no guides: no boundaries)
+  if (S.bundledist) {
+    for (int sno = 0; sno < 3; sno++) {
+      int lastgroup = -1, procgroup = S.startg[sno];
+      while (procgroup != -1) {
+        if (lastgroup != -1 && S.g_start[procgroup] - S.g_end[lastgroup] <= S.bundledist) {
+          merge_fwd_groups(S, lastgroup, procgroup);
+          procgroup = S.g_next[lastgroup];
+          continue;
+        }
+        lastgroup = procgroup;
+        procgroup = S.g_next[procgroup];
+      }
+    }
+  }
+
+  // appended rows force a re-sort of the table (rlink.cpp:15122-15125); rows whose strand was zeroed meanwhile have
+  // CHANGED keys and may tie with other rows, so the reference's own quicksort decides the order
+  for (int j = 0; j < S.nJ; j++) jt_perm[j] = j;
+  if (S.nJ > S.nj0) {
+    sort_rows_ref(S, jt_perm, S.nJ);
+    for (int j = 0; j < S.nJ; j++) jt_inv[jt_perm[j]] = j;
+    const uint32_t nintr = (S.seg_off[S.nr] - S.seg0) - (uint32_t)S.nr;
+    for (uint32_t k = 0; k < nintr; k++) S.rj[k] = jt_inv[S.rj[k]];
+  }
+}
+
+// ---- second half of a9: colours across the three lanes, then bundles ------------------------------------------
+struct Grp2 {
+  int ng, ncol;
+  uint32_t bundledist;
+  const int32_t* startg;
+  // groups after the first half (read only)
+  const uint32_t *g_start, *g_end; const int32_t* g_next; const float *g_cov, *g_multi;
+  // working / output arrays of this bundle
+  int32_t* color;       // [ng]   CGroup::color
+  float* negp;          // [ng]   CGroup::neg_prop
+  int32_t *eq, *eqneg, *eqpos, *bundlecol;   // [ncol]
+  int32_t* g2b;         // [3*ng]
+  int32_t *bun_len, *bun_start, *bun_last; float *bun_cov, *bun_multi;   // [3][ng]
+  uint32_t *bn_s, *bn_e; float* bn_cov; int32_t* bn_next;                // [3][ng]
+  int nbun[3], nbn[3];
+};
+
+STG_HD int get_min_start(const Grp2& S, const int* cur) {   // rlink.cpp:984-1026
+  if (cur[0] != -1) {
+    if (cur[1] != -1) {
+      if (cur[2] != -1) {
+        const int two = S.g_start[cur[0]] < S.g_start[cur[1]] ? 0 : 1;
+        return S.g_start[cur[two]] < S.g_start[cur[2]] ? two : 2;
+      }
+      return S.g_start[cur[0]] < S.g_start[cur[1]] ? 0 : 1;
+    }
+    if (cur[2] != -1) return S.g_start[cur[0]] < S.g_start[cur[2]] ? 0 : 2;
+    return 0;
+  }
+  if (cur[1] != -1) {
+    if (cur[2] != -1) return S.g_start[cur[1]] < S.g_start[cur[2]] ? 1 : 2;
+    return 1;
+  }
+  return 2;
+}
+
+// rlink.cpp:1028-1056: U = the unstranded group, G = the stranded one, grcol = G's colour
+STG_HD void set_strandcol(int32_t* color, int U, int G, int grcol, int32_t* eqcol, int32_t* equalcolor) {
+  int zerocol = eqcol[color[U]];
+  if (zerocol > -1) {
+    while (eqcol[zerocol] != -1 && eqcol[zerocol] != zerocol) zerocol = eqcol[zerocol];
+    const int tmpcol = zerocol;
+    while (equalcolor[zerocol] != zerocol) zerocol = equalcolor[zerocol];
+    eqcol[color[U]] = zerocol;
+    eqcol[tmpcol] = zerocol;
+    if (zerocol < grcol) { equalcolor[grcol] = zerocol; color[G] = zerocol; }
+    else if (grcol < zerocol) { equalcolor[zerocol] = grcol; eqcol[color[U]] = grcol; }
+  } else eqcol[color[U]] = grcol;
+}
+
+STG_HD int bn_add(Grp2& S, int s, uint32_t a, uint32_t e, float cov) {
+  const int k = S.nbn[s]++, o = s * S.ng + k;
+  S.bn_s[o] = a; S.bn_e[o] = e; S.bn_cov[o] = cov; S.bn_next[o] = -1;
+  return k;
+}
+
+STG_HD int create_bundle(Grp2& S, int s, int g) {   // rlink.cpp:1083-1095
+  const int bid = bn_add(S, s, S.g_start[g], S.g_end[g], S.g_cov[g]);
+  const int bno = S.nbun[s]++, o = s * S.ng + bno;
+  S.bun_len[o] = (int32_t)(S.g_end[g] - S.g_start[g] + 1); S.bun_cov[o] = S.g_cov[g]; S.bun_multi[o] = S.g_multi[g];
+  S.bun_start[o] = bid; S.bun_last[o] = bid;
+  return bno;
+}
+
+STG_HD void add_group_to_bundle(Grp2& S, int s, int g, int bno) {   // rlink.cpp:1058-1081
+  const int o = s * S.ng + bno;
+  const int last = S.bun_last[o], lo = s * S.ng + last;
+  if (S.g_start[g] > S.bn_e[lo] + S.bundledist) {
+    const int bid = bn_add(S, s, S.g_start[g], S.g_end[g], S.g_cov[g]);
+    S.bn_next[lo] = bid;
+    S.bun_last[o] = bid;
+    S.bun_len[o] += (int32_t)(S.g_end[g] - S.g_start[g] + 1);
+    S.bun_cov[o] += S.g_cov[g];
+    S.bun_multi[o] += S.g_multi[g];
+  } else {
+    if (S.bn_e[lo] < S.g_end[g]) { S.bun_len[o] += (int32_t)(S.g_end[g] - S.bn_e[lo]); S.bn_e[lo] = S.g_end[g]; }
+    S.bun_cov[o] += S.g_cov[g];
+    S.bun_multi[o] += S.g_multi[g];
+    S.bn_cov[lo] += S.g_cov[g];
+  }
+}
+
+STG_HD float ovl_share(const Grp2& S, int U, int G) {   // share of G's coverage that overlaps U: rlink.cpp:15230-15290
+  const uint32_t maxstart = S.g_start[U] > S.g_start[G] ? S.g_start[U] : S.g_start[G];
+  uint32_t minend = S.g_end[U] < S.g_end[G] ? S.g_end[U] : S.g_end[G];
+  if (minend < maxstart) minend = maxstart;
+  return S.g_cov[G] * (float)(minend - maxstart + 1u) / (float)(S.g_end[G] - S.g_start[G] + 1u);
+}
+
+// expects color[] = the groups' colours and eq[] = eqcol after the first half, eqneg/eqpos/bundlecol = -1, negp = 0,
+// g2b = -1
+STG_HDN inline void groups_second_half(Grp2& S) {
+  const uint32_t bd = S.bundledist;
+  int32_t* color = S.color; int32_t* eq = S.eq;
+  int cur[3], prev[3] = {-1, -1, -1};
+  for (int i = 0; i < 3; i++) cur[i] = S.startg[i];
+  while (cur[0] != -1 || cur[1] != -1 || cur[2] != -1) {
+    const int nextgr = get_min_start(S, cur);
+    const int g = cur[nextgr];
+    int grcol = color[g];
+    while (eq[grcol] != grcol) grcol = eq[grcol];
+    color[g] = grcol;
+    if (nextgr == 1) {
+      if (prev[0] != -1 && S.g_start[g] <= S.g_end[prev[0]] + bd) {
+        set_strandcol(color, g, prev[0], color[prev[0]], S.eqneg, eq);
+        S.negp[g] += ovl_share(S, g, prev[0]);
+      }
+      while (cur[0] != -1 && S.g_start[g] <= S.g_end[cur[0]] + bd && S.g_start[cur[0]] <= S.g_end[g] + bd) {
+        int c0 = color[cur[0]];
+        while (eq[c0] != c0) c0 = eq[c0];
+        color[cur[0]] = c0;
+        S.negp[cur[0]] = 1;
+        set_strandcol(color, g, cur[0], color[cur[0]], S.eqneg, eq);
+        S.negp[g] += ovl_share(S, g, cur[0]);
+        prev[0] = cur[0];
+        cur[0] = S.g_next[cur[0]];
+      }
+      float pos_prop = 0;
+      if (prev[2] != -1 && S.g_start[g] <= S.g_end[prev[2]] + bd) {
+        set_strandcol(color, g, prev[2], color[prev[2]], S.eqpos, eq);
+        if (S.negp[g]) pos_prop += ovl_share(S, g, prev[2]);
+      }
+      while (cur[2] != -1 && S.g_start[g] <= S.g_end[cur[2]] + bd && S.g_start[cur[2]] <= S.g_end[g] + bd) {
+        int c2 = color[cur[2]];
+        while (eq[c2] != c2) c2 = eq[c2];
+        color[cur[2]] = c2;
+        set_strandcol(color, g, cur[2], color[cur[2]], S.eqpos, eq);
+        if (S.negp[g]) pos_prop += ovl_share(S, g, cur[2]);
+        prev[2] = cur[2];
+        cur[2] = S.g_next[cur[2]];
+      }
+      if (pos_prop) S.negp[g] /= (S.negp[g] + pos_prop);
+      else if (S.negp[g]) S.negp[g] = 1;
+    } else if (nextgr == 0) S.negp[g] = 1;
+    prev[nextgr] = g;
+    cur[nextgr] = S.g_next[g];
+  }
+
+  for (int i = 0; i < 3; i++) { cur[i] = S.startg[i]; S.nbun[i] = 0; S.nbn[i] = 0; }
+  while (cur[0] != -1 || cur[1] != -1 || cur[2] != -1) {
+    const int nextgr = get_min_start(S, cur);
+    const int g = cur[nextgr];
+    int grcol = color[g];
+    while (eq[grcol] != grcol) grcol = eq[grcol];
+    color[g] = grcol;
+    if (nextgr == 0 || nextgr == 2 || (S.eqneg[grcol] == -1 && S.eqpos[grcol] == -1)) {
+      int bno = S.bundlecol[grcol];
+      if (bno > -1) add_group_to_bundle(S, nextgr, g, bno);
+      else { bno = create_bundle(S, nextgr, g); S.bundlecol[grcol] = bno; }
+      S.g2b[nextgr * S.ng + g] = S.bun_last[nextgr * S.ng + bno];
+    } else {
+      if (S.eqneg[grcol] != -1) {
+        int negcol = S.eqneg[grcol];
+        while (eq[negcol] != negcol) negcol = eq[negcol];
+        int bno = S.bundlecol[negcol];
+        if (bno > -1) add_group_to_bundle(S, 0, g, bno);
+        else { bno = create_bundle(S, 0, g); S.bundlecol[negcol] = bno; }
+        S.g2b[0 * S.ng + g] = S.bun_last[0 * S.ng + bno];
+      }
+      if (S.eqpos[grcol] != -1) {
+        int poscol = S.eqpos[grcol];
+        while (eq[poscol] != poscol) poscol = eq[poscol];
+        int bno = S.bundlecol[poscol];
+        if (bno > -1) add_group_to_bundle(S, 2, g, bno);
+        else { bno = create_bundle(S, 2, g); S.bundlecol[poscol] = bno; }
+        S.g2b[2 * S.ng + g] = S.bun_last[2 * S.ng + bno];
+      }
+    }
+    cur[nextgr] = S.g_next[g];
+  }
+}

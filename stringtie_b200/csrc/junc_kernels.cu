@@ -17,7 +17,7 @@
 // (running sums per start / end, "support so far", demotion pointers) carries from row to row, while the 60 000
 // bundles of a batch are independent — so one thread walks one bundle and the batch supplies the parallelism.  All
 // arithmetic is f64 / f32 exactly as in the reference (the `support` and `tolerance` temporaries are float).
-#include "stgpu_internal.h"
+#include "groups_device.cuh"
 
 namespace {
 
@@ -84,48 +84,11 @@ __device__ __forceinline__ bool ok_to_demote(const JView& J, int cur, int better
   return (na / nb) <= ratio_threshold(na);
 }
 
-// get_cov(1, a, b, bpcov), rlink.cpp:1830-1838, on lane 1 of the bundle
-__device__ __forceinline__ double cov_all(const float* __restrict__ c, uint32_t a, uint32_t b) {
-  const int m = (int)((b + 1) / STG_BSIZE);
-  const int k = (int)(a / STG_BSIZE);
-  double cov = 0;
-  for (int i = k + 1; i <= m; i++) cov += (double)c[(size_t)i * STG_BSIZE - 1];
-  cov += (double)__fsub_rn(c[b + 1], c[a]);
-  if (cov < 0) cov = 0;
-  return cov;
-}
-
-// good_junc, rlink.cpp:13967-14070, !longreads; returns the verdict and the strand the reference would leave behind
+// good_junc, rlink.cpp:13967-14070 (good_junc_row in groups_device.cuh, shared with the read loop of rows a8 + a9)
 __device__ bool good_junc(const JView& J, int i, int64_t refstart, const float* __restrict__ c1, int64_t len,
                           const JuncParams& p, int8_t* strand_out) {
-  *strand_out = J.strand[i];
-  if (p.eonly && !J.guide_match[i]) { *strand_out = 0; return false; }
-  if (J.guide_match[i]) return true;
-  const double nreads = J.nreads[i], good = J.nreads_good[i], nm = J.nm[i], ls = J.left[i], rs = J.right[i];
-  if (good < (double)p.junctionthr) { *strand_out = 0; return false; }
-  bool mismatch = false;
-  if (nm != 0.0 && round(nm) == round(nreads)) {
-    mismatch = true;
-    if (J.end[i] - J.start[i] > 100000u /*longintron*/ && nreads < 100 * 0.1 /*CHI_WIN*ERROR_PERC*/) { *strand_out = 0; return false; }
-  }
-  const float mult = (float)(1 / 0.1);
-  const int bw = 5;
-  int j = (int)((int64_t)J.start[i] - refstart);
-  double lleft = 0, lright = 0;
-  if (j + bw + 1 < len && j >= bw) {
-    lleft = cov_all(c1, (uint32_t)(j - bw + 1), (uint32_t)j);
-    lright = cov_all(c1, (uint32_t)(j + 1), (uint32_t)(j + bw));
-  }
-  if (lleft > 1 / 0.1 && ls * mult < 0.1 * lleft && (mismatch || lright > lleft * (1 - 0.1))) { *strand_out = 0; return false; }
-  j = (int)((int64_t)J.end[i] - refstart - 1);
-  double rleft = 0, rright = 0;
-  if (j + bw + 1 < len && j >= bw) {
-    rleft = cov_all(c1, (uint32_t)(j - bw + 1), (uint32_t)j);
-    rright = cov_all(c1, (uint32_t)(j + 1), (uint32_t)(j + bw));
-  }
-  if (rright > 1 / 0.1 && rs * mult < rright * 0.1 && (mismatch || rleft > rright * (1 - 0.1))) { *strand_out = 0; return false; }
-  if (nreads * 10 < 0.1 * ls || nreads * 10 < 0.1 * rs) { *strand_out = 0; return false; }
-  return true;
+  return good_junc_row(J.start[i], J.end[i], J.strand[i], J.guide_match[i], J.nreads[i], J.nreads_good[i], J.nm[i], J.left[i],
+                       J.right[i], refstart, c1, len, p, strand_out);
 }
 
 }  // namespace

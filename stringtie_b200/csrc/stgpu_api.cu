@@ -113,6 +113,10 @@ struct stg_dbatch {
   int64_t scan_capacity = 0;    // elements the scan scratch covers
   int64_t sum_len = 0;
   bool ran = false;
+  // rows a8 + a9 (stg_build_groups)
+  GroupsView gv;
+  bool groups_built = false;
+  std::vector<uint32_t> h_nreads;  // [n_bundles]
 };
 
 namespace {
@@ -405,6 +409,7 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
     len[b] = (uint32_t)l; stride[b] = (uint32_t)s; gbase[b] = (uint32_t)g; tile_off[b] = (uint32_t)t;
     d->h_cov_off[b] = (int64_t)(3 * g); d->h_stride[b] = (int64_t)s; d->h_len[b] = (uint32_t)l; d->h_start[b] = h->b_start[b];
     d->sum_len += (int64_t)l;
+    d->h_nreads.push_back(h->b_read_off[b + 1] - h->b_read_off[b]);
     g += s; t += (l + STG_TILE_W - 1) / STG_TILE_W;
     if (g >= 0xffffffffull || t >= 0xffffffffull) { delete d; return fail(ctx, STG_ERANGE, "batch spans more than 2^32 positions; split it"); }
   }
@@ -723,6 +728,194 @@ int stg_find_trims(stg_ctx* ctx, const stg_dbatch* d, int64_t n, const int32_t* 
   }
   CK(ctx, cudaStreamSynchronize(st));
   cudaFree(db); cudaFree(ds); cudaFree(da); cudaFree(dz); cudaFree(dc); cudaFree(dn); cudaFree(dp); cudaFree(df); cudaFree(dt);
+  return STG_OK;
+}
+
+// ---- rows a8 + a9 ---------------------------------------------------------------------------------------------
+int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
+  if (!ctx || !d) return fail(ctx, STG_EINVAL, "stg_build_groups: null argument");
+  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_build_groups: batch has not been run");
+  if (d->groups_built) return fail(ctx, STG_EINVAL, "stg_build_groups: groups of this batch are already built");
+  const stg_params& pr = ctx->params;
+  if (pr.longreads || pr.mixedMode || pr.viral || pr.guided)
+    return fail(ctx, STG_EUNSUPPORTED, "stg_build_groups: only the short-read de novo path is implemented");
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevBatchView& v = d->v;
+  GroupsView& g = d->gv;
+  memset(&g, 0, sizeof(g));
+  g.bundledist = pr.bundledist;
+  const int64_t nb = v.n_bundles, nr = v.n_reads, ns = v.n_segs, np = v.n_pairs, nj = v.n_juncs, ni = ns - nr;
+  int rc = STG_OK;
+  stg_dbatch tmp;   // scratch of this call: handed back to the pool at the end
+  struct Release { stg_ctx* c; stg_dbatch* t; ~Release() { free_batch_allocs(c, t); } } release{ctx, &tmp};
+#define KEEP(ptr, count) do { if ((rc = dev_alloc(ctx, d, &(ptr), (int64_t)(count)))) return rc; } while (0)
+#define TEMP(ptr, count) do { if ((rc = dev_alloc(ctx, &tmp, &(ptr), (int64_t)(count)))) return rc; } while (0)
+  // the longest walks first
+  std::vector<uint32_t> order((size_t)nb);
+  for (int64_t b = 0; b < nb; b++) order[b] = (uint32_t)b;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return d->h_nreads[a] > d->h_nreads[b]; });
+  uint32_t* d_order = nullptr;
+  KEEP(d_order, nb);
+  if (nb) CK(ctx, cudaMemcpyAsync(d_order, order.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, st));
+  g.order = d_order;
+  // capacities
+  uint32_t* rcap = nullptr; unsigned long long* d_total = nullptr; unsigned long long* scan_state = nullptr; uint32_t* ticket = nullptr;
+  TEMP(rcap, nr + 1 + 16); TEMP(d_total, 1); TEMP(ticket, 1);
+  TEMP(scan_state, std::max(nr, nb) / 4096 + 4);
+  KEEP(g.rj, ni);
+  CK(ctx, cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
+  { Scope s(ctx, "groups_caps+scan", 2);
+    CK(ctx, launch_group_caps(v, rcap, d_total, g.rj, st));
+    CK(ctx, launch_scan_exclusive_add(rcap, nr + 1, scan_state, ticket, st)); }
+  g.rcap_off = rcap;
+  unsigned long long total = 0;
+  CK(ctx, cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));   // also: `order` has left the host
+  if (total + 3ull * (unsigned long long)nr >= 0x7fffffffull)
+    return fail(ctx, STG_ERANGE, "stg_build_groups: batch needs more than 2^31 group slots; split it");
+  const int64_t R = (int64_t)total;
+  // mutable copies of the reads and of the junction-pass state
+  KEEP(g.strand, nr); KEEP(g.seg_start, ns); KEEP(g.seg_end, ns); KEEP(g.pair, np);
+  TEMP(g.jt_strand, nj); TEMP(g.jt_mm, nj);
+  TEMP(g.ap_start, ni); TEMP(g.ap_end, ni); TEMP(g.ap_strand, ni); TEMP(g.ap_mm, ni);
+  TEMP(g.jt_perm, nj + ni); TEMP(g.jt_inv, nj + ni);
+  if (nr) CK(ctx, cudaMemcpyAsync(g.strand, v.r_strand, (size_t)nr, cudaMemcpyDeviceToDevice, st));
+  if (ns) CK(ctx, cudaMemcpyAsync(g.seg_start, v.seg_start, sizeof(uint32_t) * ns, cudaMemcpyDeviceToDevice, st));
+  if (ns) CK(ctx, cudaMemcpyAsync(g.seg_end, v.seg_end, sizeof(uint32_t) * ns, cudaMemcpyDeviceToDevice, st));
+  if (np) CK(ctx, cudaMemcpyAsync(g.pair, v.pair_idx, sizeof(int32_t) * np, cudaMemcpyDeviceToDevice, st));
+  if (nj) CK(ctx, cudaMemcpyAsync(g.jt_strand, v.jp_strand, (size_t)nj, cudaMemcpyDeviceToDevice, st));
+  if (nj) CK(ctx, cudaMemcpyAsync(g.jt_mm, v.jp_mm, sizeof(double) * nj, cudaMemcpyDeviceToDevice, st));
+  // sparse groups / colours / readgroup
+  TEMP(g.g_start, R); TEMP(g.g_end, R); TEMP(g.g_color, R); TEMP(g.g_next, R); TEMP(g.g_merge, R); TEMP(g.g_grid, R);
+  TEMP(g.g_cov, R); TEMP(g.g_multi, R); TEMP(g.g_alive, R); TEMP(g.eqcol, R + 3 * nr); TEMP(g.rg, R);
+  KEEP(g.rg_off, nr + 1 + 16);
+  g.rg_cnt = g.rg_off;
+  KEEP(g.b_ng, nb + 1 + 16); KEEP(g.b_ncol, nb + 1 + 16); KEEP(g.b_napp, nb + 1 + 16);
+  KEEP(g.b_startgroup, 3 * nb); KEEP(g.b_numfrag, nb); KEEP(g.b_fraglen, nb); KEEP(g.b_nbun, 3 * nb); KEEP(g.b_nbn, 3 * nb);
+  CK(ctx, cudaMemsetAsync(g.rg_off, 0, sizeof(uint32_t) * (nr + 1), st));
+  CK(ctx, cudaMemsetAsync(g.b_ng, 0, sizeof(uint32_t) * (nb + 1), st));
+  CK(ctx, cudaMemsetAsync(g.b_ncol, 0, sizeof(uint32_t) * (nb + 1), st));
+  CK(ctx, cudaMemsetAsync(g.b_napp, 0, sizeof(uint32_t) * (nb + 1), st));
+  if (nb) {
+    CK(ctx, cudaMemsetAsync(g.b_startgroup, 0xff, sizeof(int32_t) * 3 * nb, st));
+    CK(ctx, cudaMemsetAsync(g.b_numfrag, 0, sizeof(double) * nb, st));
+    CK(ctx, cudaMemsetAsync(g.b_fraglen, 0, sizeof(double) * nb, st));
+    CK(ctx, cudaMemsetAsync(g.b_nbun, 0, sizeof(uint32_t) * 3 * nb, st));
+    CK(ctx, cudaMemsetAsync(g.b_nbn, 0, sizeof(uint32_t) * 3 * nb, st));
+  }
+  CK(ctx, cudaMemsetAsync(v.err_flag, 0, sizeof(uint32_t), st));
+  JuncParams jp{pr.junctionsupport, pr.sserror, pr.junctionthr, pr.eonly};
+  { Scope s(ctx, "groups_walk", 1); CK(ctx, launch_groups_walk(v, g, jp, st)); }
+  { Scope s(ctx, "groups_scans", 4);
+    CK(ctx, launch_scan_exclusive_add(g.b_ng, nb + 1, scan_state, ticket, st));
+    CK(ctx, launch_scan_exclusive_add(g.b_ncol, nb + 1, scan_state, ticket, st));
+    CK(ctx, launch_scan_exclusive_add(g.b_napp, nb + 1, scan_state, ticket, st));
+    CK(ctx, launch_scan_exclusive_add(g.rg_off, nr + 1, scan_state, ticket, st)); }
+  uint32_t tot[4] = {0, 0, 0, 0}, err = 0;
+  CK(ctx, cudaMemcpyAsync(&tot[0], g.b_ng + nb, 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaMemcpyAsync(&tot[1], g.b_ncol + nb, 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaMemcpyAsync(&tot[2], g.b_napp + nb, 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaMemcpyAsync(&tot[3], g.rg_off + nr, 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaMemcpyAsync(&err, v.err_flag, 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  if (err) return fail(ctx, STG_ERANGE, "stg_build_groups: a bundle exceeded the capacity bound of its group arrays");
+  g.n_groups = tot[0]; g.n_colors = tot[1]; g.n_app = tot[2]; g.n_rg = tot[3];
+  const int64_t NG = g.n_groups, NC = g.n_colors, NJ = nj + g.n_app;
+  KEEP(g.d_g_start, NG); KEEP(g.d_g_end, NG); KEEP(g.d_g_color, NG); KEEP(g.d_g_next, NG); KEEP(g.d_g_merge, NG);
+  KEEP(g.d_g_cov, NG); KEEP(g.d_g_multi, NG); KEEP(g.d_g_alive, NG); KEEP(g.d_color2, NG); KEEP(g.d_negp, NG);
+  KEEP(g.d_eqcol, NC); KEEP(g.d_eq2, NC); KEEP(g.d_eqneg, NC); KEEP(g.d_eqpos, NC); TEMP(g.d_bundlecol, NC);
+  KEEP(g.d_g2b, 3 * NG);
+  KEEP(g.bun_len, 3 * NG); KEEP(g.bun_start, 3 * NG); KEEP(g.bun_last, 3 * NG); KEEP(g.bun_cov, 3 * NG); KEEP(g.bun_multi, 3 * NG);
+  KEEP(g.bn_start, 3 * NG); KEEP(g.bn_end, 3 * NG); KEEP(g.bn_cov, 3 * NG); KEEP(g.bn_next, 3 * NG);
+  KEEP(g.d_rg, g.n_rg);
+  KEEP(g.oj_start, NJ); KEEP(g.oj_end, NJ); KEEP(g.oj_strand, NJ); KEEP(g.oj_nreads, NJ); KEEP(g.oj_nreads_good, NJ);
+  KEEP(g.oj_left, NJ); KEEP(g.oj_right, NJ); KEEP(g.oj_nm, NJ); KEEP(g.oj_mm, NJ);
+  { Scope s(ctx, "groups_colour+compact", 3); CK(ctx, launch_groups_finish(v, g, st)); }
+#undef KEEP
+#undef TEMP
+  d->groups_built = true;
+  return STG_OK;   // `release` parks the scratch in the pool; everything that reuses it runs on the same stream
+}
+
+namespace {
+struct GArr { const void* p; int64_t n; int32_t sz; };
+GArr groups_array(const stg_dbatch* d, int which) {
+  const DevBatchView& v = d->v;
+  const GroupsView& g = d->gv;
+  const int64_t nb = v.n_bundles, nr = v.n_reads, NG = g.n_groups, NC = g.n_colors, NJ = v.n_juncs + g.n_app;
+  switch (which) {
+    case STG_GA_R_STRAND: return {g.strand, nr, 1};
+    case STG_GA_PAIR_IDX: return {g.pair, v.n_pairs, 4};
+    case STG_GA_SEG_START: return {g.seg_start, v.n_segs, 4};
+    case STG_GA_SEG_END: return {g.seg_end, v.n_segs, 4};
+    case STG_GA_RJUNC: return {g.rj, v.n_segs - nr, 4};
+    case STG_GA_GROUP_OFF: return {g.b_ng, nb + 1, 4};
+    case STG_GA_COLOR_OFF: return {g.b_ncol, nb + 1, 4};
+    case STG_GA_APP_OFF: return {g.b_napp, nb + 1, 4};
+    case STG_GA_RG_OFF: return {g.rg_off, nr + 1, 4};
+    case STG_GA_STARTGROUP: return {g.b_startgroup, 3 * nb, 4};
+    case STG_GA_NUM_FRAGMENTS: return {g.b_numfrag, nb, 8};
+    case STG_GA_FRAG_LEN: return {g.b_fraglen, nb, 8};
+    case STG_GA_G_START: return {g.d_g_start, NG, 4};
+    case STG_GA_G_END: return {g.d_g_end, NG, 4};
+    case STG_GA_G_COLOR: return {g.d_g_color, NG, 4};
+    case STG_GA_G_NEXT: return {g.d_g_next, NG, 4};
+    case STG_GA_G_MERGE: return {g.d_g_merge, NG, 4};
+    case STG_GA_G_COV: return {g.d_g_cov, NG, 4};
+    case STG_GA_G_MULTI: return {g.d_g_multi, NG, 4};
+    case STG_GA_G_ALIVE: return {g.d_g_alive, NG, 1};
+    case STG_GA_G_COLOR2: return {g.d_color2, NG, 4};
+    case STG_GA_G_NEG_PROP: return {g.d_negp, NG, 4};
+    case STG_GA_EQCOL: return {g.d_eqcol, NC, 4};
+    case STG_GA_EQCOL2: return {g.d_eq2, NC, 4};
+    case STG_GA_EQNEG: return {g.d_eqneg, NC, 4};
+    case STG_GA_EQPOS: return {g.d_eqpos, NC, 4};
+    case STG_GA_G2B: return {g.d_g2b, 3 * NG, 4};
+    case STG_GA_BUN_LEN: return {g.bun_len, 3 * NG, 4};
+    case STG_GA_BUN_START: return {g.bun_start, 3 * NG, 4};
+    case STG_GA_BUN_LAST: return {g.bun_last, 3 * NG, 4};
+    case STG_GA_BUN_COV: return {g.bun_cov, 3 * NG, 4};
+    case STG_GA_BUN_MULTI: return {g.bun_multi, 3 * NG, 4};
+    case STG_GA_BN_START: return {g.bn_start, 3 * NG, 4};
+    case STG_GA_BN_END: return {g.bn_end, 3 * NG, 4};
+    case STG_GA_BN_COV: return {g.bn_cov, 3 * NG, 4};
+    case STG_GA_BN_NEXT: return {g.bn_next, 3 * NG, 4};
+    case STG_GA_N_BUN: return {g.b_nbun, 3 * nb, 4};
+    case STG_GA_N_BN: return {g.b_nbn, 3 * nb, 4};
+    case STG_GA_RG: return {g.d_rg, g.n_rg, 4};
+    case STG_GA_J_START: return {g.oj_start, NJ, 4};
+    case STG_GA_J_END: return {g.oj_end, NJ, 4};
+    case STG_GA_J_STRAND: return {g.oj_strand, NJ, 1};
+    case STG_GA_J_NREADS: return {g.oj_nreads, NJ, 8};
+    case STG_GA_J_NREADS_GOOD: return {g.oj_nreads_good, NJ, 8};
+    case STG_GA_J_LEFT: return {g.oj_left, NJ, 8};
+    case STG_GA_J_RIGHT: return {g.oj_right, NJ, 8};
+    case STG_GA_J_NM: return {g.oj_nm, NJ, 8};
+    case STG_GA_J_MM: return {g.oj_mm, NJ, 8};
+  }
+  return {nullptr, -1, 0};
+}
+}  // namespace
+
+int stg_groups_array_info(const stg_dbatch* d, int which, int64_t* count, int32_t* elem_bytes) {
+  if (!d || !d->groups_built) return fail(nullptr, STG_EINVAL, "stg_groups_array_info: groups of this batch are not built");
+  const GArr a = groups_array(d, which);
+  if (a.n < 0) return fail(nullptr, STG_EINVAL, "stg_groups_array_info: unknown array");
+  if (count) *count = a.n;
+  if (elem_bytes) *elem_bytes = a.sz;
+  return STG_OK;
+}
+
+int stg_fetch_groups_array(stg_ctx* ctx, const stg_dbatch* d, int which, int64_t first, int64_t count, void* out) {
+  if (!ctx || !d || !d->groups_built) return fail(ctx, STG_EINVAL, "stg_fetch_groups_array: groups of this batch are not built");
+  const GArr a = groups_array(d, which);
+  if (a.n < 0) return fail(ctx, STG_EINVAL, "stg_fetch_groups_array: unknown array");
+  if (first < 0 || count < 0 || first + count > a.n || (count && !out)) return fail(ctx, STG_EINVAL, "stg_fetch_groups_array: bad range");
+  if (count == 0) return STG_OK;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaMemcpyAsync(out, (const char*)a.p + (size_t)first * a.sz, (size_t)count * a.sz, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
   return STG_OK;
 }
 

@@ -98,6 +98,42 @@ struct DevBatchView {
   int8_t *jp_good, *jp_good_strand;  // good_junc verdict (-1: row has no strand) and the strand it leaves
 };
 
+// Rows a8 + a9 (groups_device.cuh, group_kernels.cu).  "sparse" arrays are laid out by CAPACITY: read n owns the slots
+// [rcap_off[n], rcap_off[n+1]) of rg, bundle b (first read r0) owns the group slots from rcap_off[r0] and the colour
+// slots from rcap_off[r0] + 3*r0; "dense" arrays are compacted by the real counts once the walk has finished.
+struct GroupsView {
+  uint32_t bundledist;
+  const uint32_t* order;       // [n_bundles] bundles by decreasing read count (the longest walks start first)
+  const uint32_t* rcap_off;    // [n_reads+1]
+  // mutable copies of the reads (after the stage: the repaired reads)
+  int8_t* strand; uint32_t *seg_start, *seg_end; int32_t *pair, *rj;
+  // junction table state: copies of jp_strand / jp_mm, rows appended by the repair (bundle b: intron base of b)
+  int8_t* jt_strand; double* jt_mm;
+  uint32_t *ap_start, *ap_end; int8_t *ap_strand, *ap_mm;
+  int32_t *jt_perm, *jt_inv;   // [n_juncs + n_introns] bundle b at b_junc_off[b] + intron base of b
+  // sparse groups / colours / readgroup
+  uint32_t *g_start, *g_end; int32_t *g_color, *g_next, *g_merge, *g_grid; float *g_cov, *g_multi; int8_t* g_alive;
+  int32_t* eqcol;
+  int32_t* rg; uint32_t* rg_cnt;
+  // per bundle
+  uint32_t *b_ng, *b_ncol, *b_napp;   // [n_bundles+1] counts, then exclusive prefixes (in place, after the walk)
+  int32_t* b_startgroup;              // [3*n_bundles]
+  double *b_numfrag, *b_fraglen;      // [n_bundles]
+  uint32_t* rg_off;                   // [n_reads+1] rg_cnt, then its exclusive prefix
+  int64_t n_groups, n_colors, n_rg, n_app;   // totals (host fills them after the scans)
+  // dense results
+  uint32_t *d_g_start, *d_g_end; int32_t *d_g_color, *d_g_next, *d_g_merge; float *d_g_cov, *d_g_multi; int8_t* d_g_alive;
+  int32_t* d_color2; float* d_negp;                    // [n_groups] colour / neg_prop after the colour pass
+  int32_t *d_eqcol, *d_eq2, *d_eqneg, *d_eqpos, *d_bundlecol;   // [n_colors]
+  int32_t* d_g2b;                                      // [3*n_groups] bundle b: 3*ng_off[b] + lane*ng + group
+  int32_t *bun_len, *bun_start, *bun_last; float *bun_cov, *bun_multi;   // [3*n_groups] lane s of bundle b at 3*ng_off[b] + s*ng
+  uint32_t *bn_start, *bn_end; float* bn_cov; int32_t* bn_next;          // same layout
+  uint32_t *b_nbun, *b_nbn;                            // [3*n_bundles]
+  int32_t* d_rg;                                       // [n_rg]
+  // junction table after the stage, re-sorted as the reference does: bundle b at b_junc_off[b] + b_napp[b] (prefix)
+  uint32_t *oj_start, *oj_end; int8_t* oj_strand; double *oj_nreads, *oj_nreads_good, *oj_left, *oj_right, *oj_nm, *oj_mm;
+};
+
 struct JuncParams {
   uint32_t junctionsupport, sserror;
   int32_t junctionthr;
@@ -131,5 +167,8 @@ cudaError_t launch_junc_pass(const DevBatchView& v, const JuncParams& p, cudaStr
 cudaError_t launch_find_trims(const DevBatchView& v, int64_t n, const int32_t* bundle, const int8_t* sno, const uint32_t* start,
                               const uint32_t* end, const uint32_t* cap_off, uint32_t* o_cnt, uint32_t* o_pos, float* o_ab,
                               uint8_t* o_st, cudaStream_t st);
+cudaError_t launch_group_caps(const DevBatchView& v, uint32_t* rcap, unsigned long long* total, int32_t* rj, cudaStream_t st);
+cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, cudaStream_t st);
+cudaError_t launch_groups_finish(const DevBatchView& v, const GroupsView& g, cudaStream_t st);
 int64_t scan_partials_needed(int64_t n);
 int cov_tile_smem_bytes();

@@ -23,8 +23,25 @@ EXPORTS = [
     "stg_builder_add", "stg_builder_packed", "stg_builder_reset", "stg_builder_destroy", "stg_upload", "stg_run",
     "stg_sync", "stg_free_batch", "stg_trim", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
     "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_trims_capacity", "stg_find_trims", "stg_infer_transcripts",
+    "stg_build_groups", "stg_groups_array_info", "stg_fetch_groups_array",
     "stg_shard_assign", "stg_set_profiling", "stg_kernel_count", "stg_kernel_time", "stg_launch_counter", "stg_batch_stats", "stg_stream",
 ]
+
+
+# enum stg_groups_array (include/stgpu.h), in order
+GROUPS_ARRAYS = [
+    "R_STRAND", "PAIR_IDX", "SEG_START", "SEG_END", "RJUNC", "GROUP_OFF", "COLOR_OFF", "APP_OFF", "RG_OFF", "STARTGROUP",
+    "NUM_FRAGMENTS", "FRAG_LEN", "G_START", "G_END", "G_COLOR", "G_NEXT", "G_MERGE", "G_COV", "G_MULTI", "G_ALIVE", "G_COLOR2",
+    "G_NEG_PROP", "EQCOL", "EQCOL2", "EQNEG", "EQPOS", "G2B", "BUN_LEN", "BUN_START", "BUN_LAST", "BUN_COV", "BUN_MULTI",
+    "BN_START", "BN_END", "BN_COV", "BN_NEXT", "N_BUN", "N_BN", "RG", "J_START", "J_END", "J_STRAND", "J_NREADS",
+    "J_NREADS_GOOD", "J_LEFT", "J_RIGHT", "J_NM", "J_MM",
+]
+GROUPS_DTYPES = {k: np.int32 for k in GROUPS_ARRAYS}
+GROUPS_DTYPES.update({k: np.uint32 for k in ("SEG_START", "SEG_END", "GROUP_OFF", "COLOR_OFF", "APP_OFF", "RG_OFF", "G_START", "G_END",
+                                             "BN_START", "BN_END", "N_BUN", "N_BN", "J_START", "J_END")})
+GROUPS_DTYPES.update({k: np.int8 for k in ("R_STRAND", "G_ALIVE", "J_STRAND")})
+GROUPS_DTYPES.update({k: np.float32 for k in ("G_COV", "G_MULTI", "G_NEG_PROP", "BUN_COV", "BUN_MULTI", "BN_COV")})
+GROUPS_DTYPES.update({k: np.float64 for k in ("NUM_FRAGMENTS", "FRAG_LEN", "J_NREADS", "J_NREADS_GOOD", "J_LEFT", "J_RIGHT", "J_NM", "J_MM")})
 
 
 class StgError(RuntimeError):
@@ -76,6 +93,9 @@ def load_library() -> C.CDLL:
     L.stg_find_trims.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int8), u32p, u32p, u32p, u32p, u32p,
                                  c_f32p, u8p]
     L.stg_infer_transcripts.argtypes = [vp, C.POINTER(StgBundleView), C.POINTER(StgBundleResult)]
+    L.stg_build_groups.argtypes = [vp, vp]
+    L.stg_groups_array_info.argtypes = [vp, C.c_int, c_i64p, C.POINTER(C.c_int32)]
+    L.stg_fetch_groups_array.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
     L.stg_shard_assign.argtypes = [C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
                                    C.POINTER(C.c_int32), c_f64p]
     L.stg_set_profiling.argtypes = [vp, C.c_int]
@@ -223,6 +243,24 @@ class Engine:
         sel = np.concatenate([np.arange(int(cap_off[i]), int(cap_off[i]) + int(cnt[i])) for i in range(n)]) if n else np.zeros(0, int)
         sel = sel.astype(np.int64)
         return off, pos[sel], ab[sel], st[sel]
+
+    # ---- rows a8 + a9 -------------------------------------------------------------------------------------
+    def build_groups(self, batch: DeviceBatch):
+        """Read repair, groups, colours, bundles / bundlenodes of every bundle (stg_build_groups); results stay on the device."""
+        self._ck(self.L.stg_build_groups(self.ctx, batch.handle))
+
+    def fetch_groups_array(self, batch: DeviceBatch, which: str) -> np.ndarray:
+        """One batch-wide result array of stg_build_groups by name (enum stg_groups_array without the STG_GA_ prefix)."""
+        idx = GROUPS_ARRAYS.index(which)
+        n, sz = C.c_int64(), C.c_int32()
+        self._ck(self.L.stg_groups_array_info(batch.handle, idx, C.byref(n), C.byref(sz)))
+        out = np.empty(n.value, dtype=GROUPS_DTYPES[which])
+        assert out.itemsize == sz.value, which
+        self._ck(self.L.stg_fetch_groups_array(self.ctx, batch.handle, idx, 0, n.value, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def fetch_groups(self, batch: DeviceBatch) -> Dict[str, np.ndarray]:
+        return {k: self.fetch_groups_array(batch, k) for k in GROUPS_ARRAYS}
 
     def fetch_cov_totals(self, batch: DeviceBatch) -> np.ndarray:
         out = np.empty(batch.n_bundles * 3, dtype=np.float64)

@@ -57,3 +57,41 @@ def assert_same(got, want):
                 gv, wv = gv.view(np.uint32), wv.view(np.uint32)
             bad = np.nonzero(gv != wv)[0] if gv.ndim else (np.array([0]) if gv != wv else np.array([], dtype=int))
             assert bad.size == 0, f"bundle {b}, {k}: {bad.size} entries differ, first at {bad[:5]}"
+
+
+def split_engine_groups(G, a):
+    """Per-bundle dicts (keys as orc.groups / split_reference_dump) from the batch-wide arrays of Engine.fetch_groups."""
+    nb = a["b_start"].size
+    ro, so, po, jo = (a[k].astype(np.int64) for k in ("b_read_off", "r_seg_off", "r_pair_off", "b_junc_off"))
+    go, co, ao, rgo = (G[k].astype(np.int64) for k in ("GROUP_OFF", "COLOR_OFF", "APP_OFF", "RG_OFF"))
+    out = []
+    for b in range(nb):
+        r0, r1 = int(ro[b]), int(ro[b + 1])
+        s0, s1, p0, p1 = int(so[r0]), int(so[r1]), int(po[r0]), int(po[r1])
+        g0, g1, c0, c1 = int(go[b]), int(go[b + 1]), int(co[b]), int(co[b + 1])
+        j0, j1 = int(jo[b] + ao[b]), int(jo[b + 1] + ao[b + 1])
+        ng = g1 - g0
+        d = {"startgroup": G["STARTGROUP"][3 * b:3 * b + 3], "num_fragments": G["NUM_FRAGMENTS"][b], "frag_len": G["FRAG_LEN"][b],
+             "color": c1 - c0,
+             "r_strand": G["R_STRAND"][r0:r1], "pair_idx": G["PAIR_IDX"][p0:p1], "seg_start": G["SEG_START"][s0:s1],
+             "seg_end": G["SEG_END"][s0:s1], "rjunc": G["RJUNC"][s0 - r0:s1 - r1],
+             "g_alive": G["G_ALIVE"][g0:g1], "g_start": G["G_START"][g0:g1], "g_end": G["G_END"][g0:g1],
+             "g_color": G["G_COLOR"][g0:g1], "g_next": G["G_NEXT"][g0:g1], "g_cov": G["G_COV"][g0:g1],
+             "g_multi": G["G_MULTI"][g0:g1], "merge": G["G_MERGE"][g0:g1], "eqcol": G["EQCOL"][c0:c1],
+             "rg_off": (rgo[r0:r1 + 1] - rgo[r0]).astype(np.uint32), "rg": G["RG"][int(rgo[r0]):int(rgo[r1])],
+             "g_color2": G["G_COLOR2"][g0:g1], "g_neg_prop": G["G_NEG_PROP"][g0:g1], "eqcol2": G["EQCOL2"][c0:c1],
+             "eqneg": G["EQNEG"][c0:c1], "eqpos": G["EQPOS"][c0:c1], "g2b": G["G2B"][3 * g0:3 * g1]}
+        for k in J_KEYS:
+            d["j_" + k] = G["J_" + k.upper()][j0:j1]
+        nbun = G["N_BUN"][3 * b:3 * b + 3].astype(np.int64)
+        nbn = G["N_BN"][3 * b:3 * b + 3].astype(np.int64)
+        d["bun_off"] = np.concatenate([[0], np.cumsum(nbun)]).astype(np.int32)
+        d["bn_off"] = np.concatenate([[0], np.cumsum(nbn)]).astype(np.int32)
+        for k in ("len", "start", "last", "cov", "multi"):
+            src = G["BUN_" + k.upper()]
+            d["bun_" + k] = np.concatenate([src[3 * g0 + s * ng:3 * g0 + s * ng + int(nbun[s])] for s in range(3)])
+        for k in ("start", "end", "cov", "next"):
+            src = G["BN_" + k.upper()]
+            d["bn_" + k] = np.concatenate([src[3 * g0 + s * ng:3 * g0 + s * ng + int(nbn[s])] for s in range(3)])
+        out.append(d)
+    return out

@@ -275,3 +275,80 @@ def test_find_trims_vs_oracle(engine, kind, seed):
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[3], want[3])
     assert np.array_equal(got[2].view(np.uint32), want[2].view(np.uint32))
     batch.free()
+
+
+# ---- rows a8 + a9: read repair, groups, colours, bundles / bundlenodes (stg_build_groups) ----------------------
+def _gpu_groups(engine, a):
+    from tests import a9_util
+    batch = engine.upload(a)
+    try:
+        engine.run(batch)
+        engine.build_groups(batch)
+        return a9_util.split_engine_groups(engine.fetch_groups(batch), a)
+    finally:
+        batch.free()
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_groups_golden(engine, name):
+    """State after the read loop, the colour pass and the bundle creation against the dumps taken INSIDE the reference's
+    build_graphs (hooks at rlink.cpp:15194 and :15433), committed with the fixtures."""
+    from tests import a9_util
+    from stringtie_b200.stgb import input_view
+    g = load_golden(name)
+    a = input_view(g)
+    a9_util.assert_same(_gpu_groups(engine, a), a9_util.split_reference_dump(g, a))
+
+
+@pytest.mark.parametrize("kind,seed", [("synth", 3), ("synth", 7), ("deep", 4), ("adv", 1), ("adv", 2), ("adv", 3), ("adv", 5)])
+def test_groups_vs_oracle(engine, kind, seed):
+    from tests import a9_util
+    a = (synth.make_batch(n_bundles=60, reads_per_bundle=3000, seed=seed) if kind == "synth" else
+         synth.make_batch(n_bundles=8, reads_per_bundle=30000, seed=seed) if kind == "deep" else
+         synth.make_adversarial(seed=seed, n_bundles=14))
+    cov, off, good, left, right = orc.run(a)
+    a9_util.assert_same(_gpu_groups(engine, a), orc.groups(a, cov, off, good, left, right))
+
+
+@pytest.mark.parametrize("seed", [38, 43])
+def test_groups_appended_junctions(engine, seed):
+    """Seeds on which the repair appends junction rows and the table is re-sorted with the reference's quicksort (the
+    oracle is pinned on exactly these inputs against the live reference, tests/test_oracle_vs_reference.py)."""
+    from tests import a9_util
+    a = synth.make_adversarial(seed=seed, n_bundles=10, max_reads=250)
+    rng = np.random.default_rng(seed)
+    a["j_nm"] = np.where(rng.random(a["j_nm"].size) < 0.5, a["j_nreads"], a["j_nm"])
+    cov, off, good, left, right = orc.run(a)
+    want = orc.groups(a, cov, off, good, left, right)
+    assert sum(w["j_start"].size for w in want) > a["j_start"].size
+    a9_util.assert_same(_gpu_groups(engine, a), want)
+
+
+def test_groups_bundledist_zero_and_empty():
+    """bundledist = 0 (no merging of neighbouring groups) and a batch with empty bundles."""
+    from tests import a9_util
+    from stringtie_b200.engine import Engine, default_params
+    p = default_params()
+    p.bundledist = 0
+    e = Engine(0, p)
+    try:
+        a = synth.make_adversarial(seed=9, n_bundles=12)
+        cov, off, good, left, right = orc.run(a)
+        a9_util.assert_same(_gpu_groups(e, a), orc.groups(a, cov, off, good, left, right, bundledist=0))
+    finally:
+        e.close()
+
+
+def test_groups_refuses_unsupported_modes():
+    from stringtie_b200.engine import Engine, StgError, default_params
+    p = default_params()
+    p.guided = 1   # guide boundaries change the merging of groups (rlink.cpp:15134-15164): not built
+    e = Engine(0, p)
+    try:
+        batch = e.upload(synth.make_batch(n_bundles=3, reads_per_bundle=50, seed=1))
+        e.run(batch)
+        with pytest.raises(StgError):
+            e.build_groups(batch)
+        batch.free()
+    finally:
+        e.close()
