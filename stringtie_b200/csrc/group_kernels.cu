@@ -56,15 +56,38 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) group_caps_kernel(DevBatchView
   }
 }
 
-__global__ void __launch_bounds__(128) groups_walk_kernel(DevBatchView v, GroupsView g, JuncParams prm) {
+// The group arrays of a bundle live in SHARED memory while they fit (a bundle has ~10 groups on average, a few hundred
+// when it is deep): every read touches a handful of group fields read-modify-write, and from global memory each of
+// those is an L2 round trip on the walker's critical path.  GROUPS_SMEM slots per warp; a bundle that outgrows them
+// is moved to its global arrays and carries on there.
+#define GROUPS_SMEM 256
+#define GROUPS_WARPS 2
+struct GroupSmem {
+  uint32_t start[GROUPS_SMEM], end[GROUPS_SMEM];
+  int32_t color[GROUPS_SMEM], next[GROUPS_SMEM], merge[GROUPS_SMEM], grid[GROUPS_SMEM];
+  float cov[GROUPS_SMEM], multi[GROUPS_SMEM];
+  int8_t alive[GROUPS_SMEM];
+};
+
+struct GroupGlobal { uint32_t *start, *end; int32_t *color, *next, *merge, *grid; float *cov, *multi; int8_t* alive; int cap; };
+
+__device__ __forceinline__ void groups_to_global(Grp& S, const GroupGlobal& G, int from, int step) {
+  for (int i = from; i < S.ng; i += step) {
+    G.start[i] = S.g_start[i]; G.end[i] = S.g_end[i]; G.color[i] = S.g_color[i]; G.next[i] = S.g_next[i];
+    G.merge[i] = S.g_merge[i]; G.grid[i] = S.g_grid[i]; G.cov[i] = S.g_cov[i]; G.multi[i] = S.g_multi[i]; G.alive[i] = S.g_alive[i];
+  }
+}
+
+__global__ void __maxnreg__(232) groups_walk_kernel(DevBatchView v, GroupsView g, JuncParams prm) {
+  __shared__ GroupSmem sm[GROUPS_WARPS];
+  __shared__ FastRec fr[GROUPS_WARPS][32];
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= v.n_bundles || (threadIdx.x & 31)) return;
+  if (w >= v.n_bundles) return;
+  const int lane = threadIdx.x & 31;
+  GroupSmem& M = sm[threadIdx.x >> 5];
   const uint32_t b = g.order[w];
   const uint32_t r0 = v.b_read_off[b], nr = v.b_read_off[b + 1] - r0;
   const uint32_t j0 = v.b_junc_off[b], nj0 = v.b_junc_off[b + 1] - j0;
-  g.b_startgroup[3 * b] = g.b_startgroup[3 * b + 1] = g.b_startgroup[3 * b + 2] = -1;
-  g.b_ng[b] = 0; g.b_ncol[b] = 0; g.b_napp[b] = 0; g.b_numfrag[b] = 0; g.b_fraglen[b] = 0;
-  if (b == 0) { g.b_ng[v.n_bundles] = 0; g.b_ncol[v.n_bundles] = 0; g.b_napp[v.n_bundles] = 0; }
   if (nr == 0) return;
   Grp S;
   S.nr = (int)nr;
@@ -83,24 +106,87 @@ __global__ void __launch_bounds__(128) groups_walk_kernel(DevBatchView v, Groups
   S.nj0 = (int)nj0; S.nJ = (int)nj0; S.apcap = (int)nintr;
   const size_t G0 = g.rcap_off[r0];
   const uint32_t gcap = g.rcap_off[r0 + nr] - g.rcap_off[r0];
-  S.g_start = g.g_start + G0; S.g_end = g.g_end + G0; S.g_color = g.g_color + G0; S.g_next = g.g_next + G0;
-  S.g_merge = g.g_merge + G0; S.g_grid = g.g_grid + G0; S.g_cov = g.g_cov + G0; S.g_multi = g.g_multi + G0;
-  S.g_alive = g.g_alive + G0;
-  S.ng = 0; S.gcap = (int)gcap;
+  GroupGlobal GG{g.g_start + G0, g.g_end + G0, g.g_color + G0, g.g_next + G0, g.g_merge + G0, g.g_grid + G0, g.g_cov + G0,
+                 g.g_multi + G0, g.g_alive + G0, (int)gcap};
+  S.g_start = M.start; S.g_end = M.end; S.g_color = M.color; S.g_next = M.next; S.g_merge = M.merge; S.g_grid = M.grid;
+  S.g_cov = M.cov; S.g_multi = M.multi; S.g_alive = M.alive;
+  S.ng = 0; S.gcap = GROUPS_SMEM;
   S.eqcol = g.eqcol + G0 + 3 * (size_t)r0; S.ncol = 0; S.ccap = (int)(gcap + 3 * nr);
   S.rg = g.rg; S.rg_cnt = g.rg_cnt + r0; S.rcap_off = g.rcap_off + r0;
-  S.curr[0] = S.curr[1] = S.curr[2] = -1; S.startg[0] = S.startg[1] = S.startg[2] = -1;
+  S.curr.fill(-1); S.startg.fill(-1);
   S.junctionsupport = prm.junctionsupport; S.bundledist = g.bundledist;
   S.refstart = v.b_start[b]; S.len = v.b_len[b];
   S.c1 = v.bpcov + 3 * (size_t)v.b_gbase[b] + v.b_stride[b];
   S.prm = prm; S.err = 0;
-  if (gcap == 0 || gcap > 0x7fffffffu) { atomicOr(v.err_flag, STG_GERR_GROUPS); return; }
+  if (gcap == 0 || gcap > 0x7fffffffu) { if (!lane) atomicOr(v.err_flag, STG_GERR_GROUPS); return; }
+  // The warp's schedule (groups_device.cuh, "the parallel form of the loop"): classify 32 reads, commit the leading
+  // run of simple ones, walk the first non-simple read the reference's way, start over behind it.  Mutable scalars of
+  // S (group / colour counts, cursors, appended rows) are only valid in lane 0; the cursors are broadcast every step.
+  FastRec* R = fr[threadIdx.x >> 5];
+  const unsigned FULL = 0xffffffffu;
+  bool in_smem = true;
+  int color = 0;
   double nf = 0, fl = 0;
-  groups_first_half(S, g.jt_perm + j0 + i0, g.jt_inv + j0 + i0, &nf, &fl);
-  if (S.err) { atomicOr(v.err_flag, S.err); return; }
-  g.b_ng[b] = (uint32_t)S.ng; g.b_ncol[b] = (uint32_t)S.ncol; g.b_napp[b] = (uint32_t)(S.nJ - S.nj0);
-  g.b_numfrag[b] = nf; g.b_fraglen[b] = fl;
-  for (int s = 0; s < 3; s++) g.b_startgroup[3 * b + s] = S.startg[s];
+  int n = 0, slow_len = 0, slow_budget = 0;
+  const int inr = (int)nr;
+  while (n < inr) {
+    S.curr.a = __shfl_sync(FULL, S.curr.a, 0); S.curr.b = __shfl_sync(FULL, S.curr.b, 0); S.curr.c = __shfl_sync(FULL, S.curr.c, 0);
+    if (__any_sync(FULL, S.err != 0)) { S.err |= STG_GERR_GROUPS; break; }
+    int k = 0;
+    if (slow_budget == 0) {
+      const int hi = n + 32 < inr ? n + 32 : inr, me = n + lane;
+      bool ok = me < hi && classify_read(S, me, n, hi, R[lane]);
+      // reads that continue into the SAME mate see each other's readgroup pushes: only the first one stays simple
+      const int key = (ok && R[lane].npc >= 0) ? R[lane].npc : -1 - lane;
+      const unsigned same = __match_any_sync(FULL, key);
+      if (ok && R[lane].npc >= 0 && __ffs(same) - 1 != lane) ok = false;
+      const unsigned m = __ballot_sync(FULL, ok);
+      k = m == FULL ? 32 : __ffs(~m) - 1;
+      const unsigned run = k == 32 ? FULL : (1u << k) - 1u;
+      const unsigned minters = __ballot_sync(FULL, ok && R[lane].newcol) & run;
+      const int color0 = __shfl_sync(FULL, color, 0);
+      if (lane < k) commit_free(S, R[lane], color0 + __popc(minters & ((1u << lane) - 1u)));
+      __syncwarp();
+      if (lane == 0) {
+        for (int j = 0; j < k; j++) commit_ordered(S, R[j], n + j, nf, fl);
+        const int minted = __popc(minters);
+        color += minted; S.ncol += minted;
+      }
+      n += k;
+      if (k == 0) { slow_len = slow_len * 2 + 1 < 15 ? slow_len * 2 + 1 : 15; slow_budget = slow_len; }
+      else if (k >= 8) slow_len = 0;
+    } else slow_budget--;
+    if (n < inr && k < 32) {
+      // the read may create groups: leave shared memory before it can overflow
+      const int ng0 = __shfl_sync(FULL, S.ng, 0);
+      if (in_smem && ng0 + (int)(S.rcap_off[n + 1] - S.rcap_off[n]) > GROUPS_SMEM) {
+        __syncwarp();
+        S.ng = ng0;
+        groups_to_global(S, GG, lane, 32);
+        S.g_start = GG.start; S.g_end = GG.end; S.g_color = GG.color; S.g_next = GG.next; S.g_merge = GG.merge; S.g_grid = GG.grid;
+        S.g_cov = GG.cov; S.g_multi = GG.multi; S.g_alive = GG.alive; S.gcap = GG.cap;
+        in_smem = false;
+        __syncwarp();
+      }
+      if (lane == 0) color = walk_read(S, n, color, nf, fl);
+      n++;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    if (!S.err) walk_finish(S, g.jt_perm + j0 + i0, g.jt_inv + j0 + i0);
+    if (S.err) atomicOr(v.err_flag, S.err);
+    else {
+      g.b_ng[b] = (uint32_t)S.ng; g.b_ncol[b] = (uint32_t)S.ncol; g.b_napp[b] = (uint32_t)(S.nJ - S.nj0);
+      g.b_numfrag[b] = nf; g.b_fraglen[b] = fl;
+      g.b_startgroup[3 * b] = S.startg.a; g.b_startgroup[3 * b + 1] = S.startg.b; g.b_startgroup[3 * b + 2] = S.startg.c;
+    }
+  }
+  __syncwarp();
+  // the warp writes the groups out of shared memory
+  const int ng = __shfl_sync(FULL, S.ng, 0);
+  const bool spill = __shfl_sync(FULL, (int)(in_smem && !S.err), 0) != 0;
+  if (spill) { S.ng = ng; groups_to_global(S, GG, lane, 32); }
 }
 
 // after the scans: b_ng / b_ncol / b_napp are exclusive prefixes
@@ -187,7 +273,7 @@ cudaError_t launch_group_caps(const DevBatchView& v, uint32_t* rcap, unsigned lo
 
 cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, cudaStream_t st) {
   if (v.n_bundles == 0) return cudaSuccess;
-  groups_walk_kernel<<<(unsigned)((v.n_bundles + 3) / 4), 128, 0, st>>>(v, g, p);
+  groups_walk_kernel<<<(unsigned)((v.n_bundles + GROUPS_WARPS - 1) / GROUPS_WARPS), 32 * GROUPS_WARPS, 0, st>>>(v, g, p);
   return cudaGetLastError();
 }
 

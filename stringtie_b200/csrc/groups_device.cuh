@@ -45,7 +45,7 @@ STG_HD double cov_all(const float* __restrict__ c, uint32_t a, uint32_t b) {
 
 // good_junc, rlink.cpp:13967-14070, !longreads, on the fields of one row; returns the verdict and the strand the
 // reference would leave behind
-STG_HDN inline bool good_junc_row(uint32_t jstart, uint32_t jend, int8_t strand, int8_t guide_match, double nreads, double good,
+STG_HD bool good_junc_row(uint32_t jstart, uint32_t jend, int8_t strand, int8_t guide_match, double nreads, double good,
                                   double nm, double ls, double rs, int64_t refstart, const float* __restrict__ c1, int64_t len,
                                   const JuncParams& p, int8_t* strand_out) {
   *strand_out = strand;
@@ -77,6 +77,15 @@ STG_HDN inline bool good_junc_row(uint32_t jstart, uint32_t jend, int8_t strand,
   return true;
 }
 
+// three values selected by strand lane: kept as scalars (no indexed local array) so that the walker's state stays in
+// registers
+struct Tri {
+  int32_t a, b, c;
+  STG_HD int32_t get(int i) const { return i == 0 ? a : (i == 1 ? b : c); }
+  STG_HD void set(int i, int32_t v) { if (i == 0) a = v; else if (i == 1) b = v; else c = v; }
+  STG_HD void fill(int32_t v) { a = b = c = v; }
+};
+
 // ---- state of one bundle's walk --------------------------------------------------------------------------------
 struct Grp {
   // reads: pointers already offset to the first read / segment / pair link / intron of the bundle
@@ -100,7 +109,7 @@ struct Grp {
   int ng, gcap;
   int32_t* eqcol; int ncol, ccap;
   int32_t* rg; uint32_t* rg_cnt; const uint32_t* rcap_off;   // rg is batch-wide; rg_cnt / rcap_off offset to the bundle
-  int32_t curr[3], startg[3];
+  Tri curr, startg;
   uint32_t junctionsupport, bundledist;
   int64_t refstart, len;
   const float* c1;
@@ -205,14 +214,14 @@ STG_HD bool mate_continues(const Grp& S, int n, int np, uint32_t localdist) {
 }
 
 // rlink.cpp:1281-1631
-STG_HDN inline int merge_read_to_group(Grp& S, int n, int np, int p, float readcov, int sno, int readcol, int color, int* usedcol) {
+STG_HD int merge_read_to_group(Grp& S, int n, int np, int p, float readcov, int sno, int readcol, int color, Tri& usedcol) {
   const uint32_t localdist = S.bundledist + STG_LONGINTRONANCHOR;   // !longreads && !mixedMode
   if (np > -1 && np < n && S.r_end[np] < S.r_start[n] && S.r_end[np] + localdist > S.r_start[n] &&
       (S.slen(np, S.nseg(np) - 1) >= S.junctionsupport || (S.njunc(np) && S.rjstrand(np, S.njunc(np) - 1))) &&
       (S.slen(n, 0) >= S.junctionsupport || (S.njunc(n) && S.rjstrand(n, 0))))
     return color;   // the pair was placed as one fragment when np was processed
   bool first = true;
-  int currgroup = S.curr[sno];
+  int currgroup = S.curr.get(sno);
   if (currgroup != -1) {
     int lastgroup = -1;
     const uint32_t rstart = S.r_start[n];
@@ -256,8 +265,8 @@ STG_HDN inline int merge_read_to_group(Grp& S, int n, int np, int p, float readc
               S.g_color[thisgroup] = thiscol;
               if (thiscol != readcol) {
                 unpair(S, n, p, np);
-                readcol = usedcol[sno];
-                if (readcol < 0) { usedcol[sno] = color; readcol = new_color(S, &color); }
+                readcol = usedcol.get(sno);
+                if (readcol < 0) { usedcol.set(sno, color); readcol = new_color(S, &color); }
               }
             }
           }
@@ -284,10 +293,10 @@ STG_HDN inline int merge_read_to_group(Grp& S, int n, int np, int p, float readc
         } else {
           if (!i && np > -1 && S.r_nh[np] && np < n) {
             unpair(S, n, p, np);
-            readcol = usedcol[sno];
-            if (readcol < 0) { usedcol[sno] = color; readcol = new_color(S, &color); }
+            readcol = usedcol.get(sno);
+            if (readcol < 0) { usedcol.set(sno, color); readcol = new_color(S, &color); }
           } else if (i && !S.rjstrand(n, i - 1)) {
-            usedcol[sno] = color; readcol = new_color(S, &color);
+            usedcol.set(sno, color); readcol = new_color(S, &color);
           }
           float multi = 0;
           if (S.r_nh[n] > 1) multi = readcov * (float)(se - ss + 1u);
@@ -320,8 +329,8 @@ STG_HDN inline int merge_read_to_group(Grp& S, int n, int np, int p, float readc
   } else {   // first group of this strand lane
     if (np > -1 && S.r_nh[np] && np < n) {
       unpair(S, n, p, np);
-      readcol = usedcol[sno];
-      if (readcol < 0) { usedcol[sno] = color; readcol = new_color(S, &color); }
+      readcol = usedcol.get(sno);
+      if (readcol < 0) { usedcol.set(sno, color); readcol = new_color(S, &color); }
     }
     int ncoord = S.nseg(n);
     int lastgroup = -1;
@@ -331,7 +340,7 @@ STG_HDN inline int merge_read_to_group(Grp& S, int n, int np, int p, float readc
     while (i < ncoord) {
       const bool keep = keep_exon(S, n, i);
       if (!i || keep) {
-        if (i && !S.rjstrand(n, i - 1)) { usedcol[sno] = color; readcol = new_color(S, &color); }
+        if (i && !S.rjstrand(n, i - 1)) { usedcol.set(sno, color); readcol = new_color(S, &color); }
         const uint32_t ss = S.seg_s[S.segi(n, i)], se = S.seg_e[S.segi(n, i)];
         const float flen = (float)(se - ss + 1u);
         const int ngroup = new_group(S, ss, se, readcol, flen * readcov, flen * multi);
@@ -356,49 +365,51 @@ STG_HDN inline int merge_read_to_group(Grp& S, int n, int np, int p, float readc
       i++;
     }
   }
-  S.curr[sno] = currgroup;
-  if (S.startg[sno] == -1) S.startg[sno] = currgroup;
+  S.curr.set(sno, currgroup);
+  if (S.startg.get(sno) == -1) S.startg.set(sno, currgroup);
   return color;
 }
 
-// rlink.cpp:1633-1727
-STG_HDN inline int add_read_to_group(Grp& S, int n, int color) {
-  int usedcol[3] = {-1, -1, -1};
+// rlink.cpp:1633-1727: one pass per pair link, then one for the unpaired share of the read (p == npair)
+STG_HD int add_read_to_group(Grp& S, int n, int color) {
+  Tri usedcol;
+  usedcol.fill(-1);
   float single_count = S.r_count[n];
   const int npr = S.npair(n);
-  for (int p = 0; p < npr; p++) {
-    int sno = (int)S.strand[n] + 1;
-    int np = S.pair[S.pairi(n, p)];
-    if (np > -1 && S.r_nh[np]) {
-      const int snop = (int)S.strand[np] + 1;
-      if (sno != snop) {
-        if (sno == 1) sno = snop;
-        else if (snop != 1) { unpair(S, n, p, np); np = -1; }
-      }
-      if (np > -1) {
-        const float pc = S.pair_cnt[S.pairi(n, p)];
-        single_count -= pc;
-        int readcol = usedcol[sno];
-        if (np < n) {
-          int grouppair = S.rg[(size_t)S.rcap_off[np]];
-          while (S.g_merge[grouppair] != grouppair) grouppair = S.g_merge[grouppair];
-          S.rg[(size_t)S.rcap_off[np]] = grouppair;
-          readcol = find_color(S, S.g_color[grouppair]);
-          S.g_color[grouppair] = readcol;
-        } else if (usedcol[sno] < 0) { usedcol[sno] = color; readcol = new_color(S, &color); }
-        double readcov = 0;
-        if (!S.unitig(n)) readcov = pc;
-        color = merge_read_to_group(S, n, np, p, (float)readcov, sno, readcol, color, usedcol);
-      }
-    }
-  }
-  if (single_count > 0.000001 /*epsilon, rlink.h:25*/) {
-    const int sn = (int)S.strand[n] + 1;
-    int readcol = usedcol[sn];
-    if (readcol < 0) { usedcol[sn] = color; readcol = new_color(S, &color); }
+  for (int p = 0; p <= npr; p++) {
+    int sno = (int)S.strand[n] + 1, np = -1, readcol = -1;
     double readcov = 0;
-    if (!S.unitig(n)) readcov = single_count;
-    color = merge_read_to_group(S, n, -1, -1, (float)readcov, sn, readcol, color, usedcol);
+    bool go = false;
+    if (p < npr) {
+      np = S.pair[S.pairi(n, p)];
+      if (np > -1 && S.r_nh[np]) {
+        const int snop = (int)S.strand[np] + 1;
+        if (sno != snop) {
+          if (sno == 1) sno = snop;
+          else if (snop != 1) { unpair(S, n, p, np); np = -1; }
+        }
+        if (np > -1) {
+          const float pc = S.pair_cnt[S.pairi(n, p)];
+          single_count -= pc;
+          readcol = usedcol.get(sno);
+          if (np < n) {
+            int grouppair = S.rg[(size_t)S.rcap_off[np]];
+            while (S.g_merge[grouppair] != grouppair) grouppair = S.g_merge[grouppair];
+            S.rg[(size_t)S.rcap_off[np]] = grouppair;
+            readcol = find_color(S, S.g_color[grouppair]);
+            S.g_color[grouppair] = readcol;
+          } else if (usedcol.get(sno) < 0) { usedcol.set(sno, color); readcol = new_color(S, &color); }
+          if (!S.unitig(n)) readcov = pc;
+          go = true;
+        }
+      }
+    } else if (single_count > 0.000001 /*epsilon, rlink.h:25*/) {
+      readcol = usedcol.get(sno);
+      if (readcol < 0) { usedcol.set(sno, color); readcol = new_color(S, &color); }
+      if (!S.unitig(n)) readcov = single_count;
+      go = true;
+    }
+    if (go) color = merge_read_to_group(S, n, np, p < npr ? p : -1, (float)readcov, sno, readcol, color, usedcol);
   }
   return color;
 }
@@ -416,7 +427,7 @@ STG_HD int junc_default_cmp(const Grp& S, int a, int b) {
 
 // the reference's quicksort (gclib/GVec.hh:896-920: Hoare partition, middle pivot, not stable) on a row list; the
 // sub-ranges of a partition are disjoint, so the order in which they are finished does not change the permutation
-STG_HDN inline void sort_rows_ref(const Grp& S, int32_t* list, int n) {
+STG_HD void sort_rows_ref(const Grp& S, int32_t* list, int n) {
   int stack[2 * 48];
   int sp = 0;
   if (n < 2) return;
@@ -443,7 +454,7 @@ STG_HDN inline void sort_rows_ref(const Grp& S, int32_t* list, int n) {
 }
 
 // the repair of the junctions of read n, its un-pairing and un-stranding: rlink.cpp:14845-15092.  Returns `keep`.
-STG_HDN inline bool repair_read(Grp& S, int n) {
+STG_HD bool repair_read(Grp& S, int n) {
   bool keep = true;
   const int nj = S.njunc(n);
   for (int i = 0; i < nj; i++) {
@@ -556,31 +567,30 @@ STG_HDN inline bool repair_read(Grp& S, int n) {
 
 // Walks the reads of the bundle in order.  jt_perm / jt_inv: [nj0 + apcap] scratch for the re-sort of the junction
 // table; on return jt_perm[k] = working row of the k-th row of the re-sorted table and rj[] holds re-sorted rows.
-STG_HDN inline void groups_first_half(Grp& S, int32_t* jt_perm, int32_t* jt_inv, double* num_fragments_out, double* frag_len_out) {
-  int color = 0;
-  double num_fragments = 0, frag_len = 0;
-  for (int n = 0; n < S.nr && !S.err; n++) {
-    const bool keep = repair_read(S, n);
-    color = add_read_to_group(S, n, color);
-    // fragment counting: rlink.cpp:15105-15116
-    if (!S.unitig(n)) frag_len += (double)((float)S.r_len[n] * S.r_count[n]);
-    double single_count = S.r_count[n];
-    if (keep) {
-      const int npr = S.npair(n);
-      for (int p = 0; p < npr; p++) {
-        const int pi = S.pair[S.pairi(n, p)];
-        if (pi != -1 && n > pi && S.r_nh[pi]) single_count -= S.pair_cnt[S.pairi(n, p)];
-      }
+// one read of the loop, the reference's way: repair -> add_read_to_group -> fragment counting (rlink.cpp:15105-15116)
+STG_HD int walk_read(Grp& S, int n, int color, double& num_fragments, double& frag_len) {
+  const bool keep = repair_read(S, n);
+  color = add_read_to_group(S, n, color);
+  if (!S.unitig(n)) frag_len += (double)((float)S.r_len[n] * S.r_count[n]);
+  double single_count = S.r_count[n];
+  if (keep) {
+    const int npr = S.npair(n);
+    for (int p = 0; p < npr; p++) {
+      const int pi = S.pair[S.pairi(n, p)];
+      if (pi != -1 && n > pi && S.r_nh[pi]) single_count -= S.pair_cnt[S.pairi(n, p)];
     }
-    if (!S.unitig(n) && single_count > 0.000001) num_fragments += single_count;
   }
-  *num_fragments_out = num_fragments; *frag_len_out = frag_len;
-  if (S.err) return;
+  if (!S.unitig(n) && single_count > 0.000001) num_fragments += single_count;
+  return color;
+}
 
+// after the last read: jt_perm / jt_inv: [nj0 + apcap] scratch for the re-sort of the junction table; on return
+// jt_perm[k] = working row of the k-th row of the re-sorted table and rj[] holds re-sorted rows
+STG_HD void walk_finish(Grp& S, int32_t* jt_perm, int32_t* jt_inv) {
   // merge groups that are close together: rlink.cpp:15134-15164 (no guides: no boundaries)
   if (S.bundledist) {
     for (int sno = 0; sno < 3; sno++) {
-      int lastgroup = -1, procgroup = S.startg[sno];
+      int lastgroup = -1, procgroup = S.startg.get(sno);
       while (procgroup != -1) {
         if (lastgroup != -1 && S.g_start[procgroup] - S.g_end[lastgroup] <= S.bundledist) {
           merge_fwd_groups(S, lastgroup, procgroup);
@@ -592,7 +602,6 @@ STG_HDN inline void groups_first_half(Grp& S, int32_t* jt_perm, int32_t* jt_inv,
       }
     }
   }
-
   // appended rows force a re-sort of the table (rlink.cpp:15122-15125); rows whose strand was zeroed meanwhile have
   // CHANGED keys and may tie with other rows, so the reference's own quicksort decides the order
   for (int j = 0; j < S.nJ; j++) jt_perm[j] = j;
@@ -602,6 +611,233 @@ STG_HDN inline void groups_first_half(Grp& S, int32_t* jt_perm, int32_t* jt_inv,
     const uint32_t nintr = (S.seg_off[S.nr] - S.seg0) - (uint32_t)S.nr;
     for (uint32_t k = 0; k < nintr; k++) S.rj[k] = jt_inv[S.rj[k]];
   }
+}
+
+struct NoHook { STG_HD void operator()(Grp&, int) const {} };
+
+// The whole loop, one read after the other.  `before_read(S, n)` runs ahead of every read (the kernel uses it to move
+// the group arrays out of shared memory before they can overflow).
+template <class Hook = NoHook>
+STG_HD void groups_first_half(Grp& S, int32_t* jt_perm, int32_t* jt_inv, double* num_fragments_out, double* frag_len_out,
+                              Hook before_read = Hook()) {
+  int color = 0;
+  double num_fragments = 0, frag_len = 0;
+  for (int n = 0; n < S.nr && !S.err; n++) {
+    before_read(S, n);
+    color = walk_read(S, n, color, num_fragments, frag_len);
+  }
+  *num_fragments_out = num_fragments; *frag_len_out = frag_len;
+  if (S.err) return;
+  walk_finish(S, jt_perm, jt_inv);
+}
+
+// ---- the parallel form of the loop ------------------------------------------------------------------------------
+// In a deep bundle almost every read is "simple": its junctions are all good, every exon it brings lies INSIDE a group
+// that already exists, and the colours it meets are already united.  Such a read changes no structure — it adds
+// coverage to groups, records its readgroup entries, may mint one fresh colour that is immediately attached to the
+// group's colour, and moves the lane cursor — so what it does can be worked out from a snapshot of the state without
+// knowing what the simple reads just before it did.  classify_read() does that, read-only, for one read; a warp
+// classifies 32 consecutive reads at once, commits the leading run of simple ones (order only matters for the float
+// sums, which one lane adds in read order), hands the first non-simple read to walk_read(), and starts over behind it.
+// Anything classify_read() is not sure about is "not simple": the sequential code is the definition of the result.
+#define STG_FP_MAXV 10   // group visits of one read (its exons + the exons of a mate that continues the fragment)
+struct FastRec {
+  int32_t grp[STG_FP_MAXV];     // visited groups, in order
+  float cov[STG_FP_MAXV];       // coverage added to cov_sum
+  float multi[STG_FP_MAXV];     // ... to multi (valid where has_multi has the bit)
+  int32_t gcol[STG_FP_MAXV];    // root colour of the visited group (CGroup::color is left pointing at it)
+  int32_t rgv[STG_FP_MAXV];     // readgroup pushes: the first nrg0 go to the read, the next nrg1 to the mate npc
+  int32_t nv, nrg0, nrg1, has_multi;
+  int32_t sno, curr;            // currgroup[sno] = curr afterwards (sno = -1: untouched)
+  int32_t newcol, fresh_gc;     // mints a colour, attached to fresh_gc
+  int32_t gp_np, gp_root, gp_col;   // earlier mate: readgroup[np][0] = gp_root, color of gp_root = gp_col (gp_np = -1: none)
+  int32_t npc;                  // mate that continued the fragment (-1: none)
+  double frag_len, numfrag;     // what the read adds to the bundle's sums
+};
+
+STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
+  R.nv = 0; R.nrg0 = 0; R.nrg1 = 0; R.has_multi = 0; R.sno = -1; R.newcol = 0; R.fresh_gc = -1; R.gp_np = -1; R.npc = -1;
+  const int nj = S.njunc(n);
+  // the repair must leave the read alone: every junction stranded, good, not demoted, not flagged
+  for (int i = 0; i < nj; i++) {
+    const int jd = S.rj[S.rji(n, i)];
+    if (jd >= S.nj0) return false;
+    const int8_t st = S.jt_strand[jd];
+    if (!st || S.jp_good[jd] != 1 || S.jp_good_strand[jd] != st || S.j_nreads[jd] < 0 || S.j_good[jd] < 0 || S.jt_mm[jd] < 0)
+      return false;
+  }
+  const int npr = S.npair(n);
+  if (npr > 1) return false;
+  const int8_t strand_n = S.strand[n];
+  if (!nj && strand_n && npr) return false;   // may lose its strand (rlink.cpp:15056-15092)
+  int sno = (int)strand_n + 1;
+  float single_count = S.r_count[n];
+  int np = -1, readcol = -1;
+  bool pass = false, fresh = false;
+  double readcov = 0;
+  if (npr == 1) {
+    const int m = S.pair[S.pairi(n, 0)];
+    if (m > -1 && S.r_nh[m]) {
+      if (m >= lo && m < hi) return false;   // the mate is classified in the same step
+      const int snop = (int)S.strand[m] + 1;
+      if (sno != snop) {
+        if (sno == 1) sno = snop;
+        else if (snop != 1) return false;    // un-pairing
+      }
+      const float pc = S.pair_cnt[S.pairi(n, 0)];
+      single_count -= pc;
+      if (m < n) {
+        if (!S.rg_cnt[m]) return false;
+        int grouppair = S.rg[(size_t)S.rcap_off[m]];
+        while (S.g_merge[grouppair] != grouppair) grouppair = S.g_merge[grouppair];
+        readcol = find_color(S, S.g_color[grouppair]);
+        R.gp_np = m; R.gp_root = grouppair; R.gp_col = readcol;
+      } else fresh = true;
+      if (!S.unitig(n)) readcov = pc;
+      np = m;
+      pass = true;
+    }
+  }
+  if (single_count > 0.000001) {
+    if (pass) return false;                  // two passes of the same read see each other's effects
+    sno = (int)strand_n + 1;
+    fresh = true;
+    if (!S.unitig(n)) readcov = single_count;
+    np = -1;
+    pass = true;
+  }
+  if (pass) {
+    const float rc = (float)readcov;
+    const uint32_t localdist = S.bundledist + STG_LONGINTRONANCHOR;
+    int cn = n, cnp = np;
+    const bool placed = cnp > -1 && cnp < cn && S.r_end[cnp] < S.r_start[cn] && S.r_end[cnp] + localdist > S.r_start[cn] &&
+                        (S.slen(cnp, S.nseg(cnp) - 1) >= S.junctionsupport || (S.njunc(cnp) && S.rjstrand(cnp, S.njunc(cnp) - 1))) &&
+                        (S.slen(cn, 0) >= S.junctionsupport || (S.njunc(cn) && S.rjstrand(cn, 0)));
+    if (!placed) {
+      int currgroup = S.curr.get(sno);
+      if (currgroup == -1) return false;
+      int lastgroup = -1;
+      const uint32_t rstart = S.r_start[cn];
+      while (currgroup != -1 && rstart > S.g_end[currgroup]) { lastgroup = currgroup; currgroup = S.g_next[currgroup]; }
+      if (currgroup == -1 || S.seg_e[S.segi(cn, 0)] < S.g_start[currgroup]) currgroup = lastgroup;
+      if (currgroup == -1) return false;
+      int thisgroup = currgroup, ncoord = S.nseg(cn), lastpushed = -1, i = 0;
+      bool first = true;
+      while (i < ncoord) {
+        if (!keep_exon(S, cn, i)) return false;
+        const uint32_t ss = S.seg_s[S.segi(cn, i)], se = S.seg_e[S.segi(cn, i)];
+        while (thisgroup != -1 && ss > S.g_end[thisgroup]) thisgroup = S.g_next[thisgroup];
+        if (thisgroup == -1 || se + localdist < S.g_start[thisgroup]) return false;      // a new group
+        if (ss < S.g_start[thisgroup] || se > S.g_end[thisgroup]) return false;           // the group would grow
+        if (S.g_grid[thisgroup] != thisgroup || S.g_merge[thisgroup] != thisgroup) return false;
+        if (!i) {
+          const uint32_t base = S.rcap_off[cn], cnt = S.rg_cnt[cn];
+          for (uint32_t g = 0; g < cnt; g++) {
+            int x = S.rg[(size_t)base + g];
+            while (S.g_merge[x] != x) x = S.g_merge[x];
+            if (x == thisgroup) { first = false; break; }
+          }
+          if (cnp > -1 && S.r_nh[cnp] && cnp < cn && find_color(S, S.g_color[thisgroup]) != readcol) return false;   // un-pairing
+        }
+        if (R.nv == STG_FP_MAXV) return false;
+        const float flen = (float)(se - ss + 1u);
+        const int v = R.nv++;
+        R.grp[v] = thisgroup;
+        R.multi[v] = 0.f;
+        if (S.r_nh[cn] > 1) { R.multi[v] = rc * flen; R.has_multi |= 1 << v; }
+        const int gc = find_color(S, S.g_color[thisgroup]);
+        R.gcol[v] = gc;
+        if (fresh) { R.newcol = 1; R.fresh_gc = gc; readcol = gc; fresh = false; }
+        else if (readcol != gc) {
+          if (i && !S.rjstrand(cn, i - 1)) readcol = gc;
+          else return false;                                                              // two colours are united
+        }
+        if (thisgroup != lastpushed) {
+          if (first) { R.rgv[R.nrg0 + R.nrg1] = thisgroup; if (cn == n) R.nrg0++; else R.nrg1++; }
+          lastpushed = thisgroup;
+        }
+        R.cov[v] = flen * rc;
+        if (i == ncoord - 1 && mate_continues(S, cn, cnp, localdist)) {
+          cn = cnp; cnp = -1;
+          ncoord = S.nseg(cn);
+          first = true;
+          if (S.r_start[cn] > S.g_end[thisgroup]) return false;                           // the group would grow
+          lastpushed = -1;
+          i = -1;
+          R.npc = cn;
+        }
+        i++;
+      }
+      R.sno = sno; R.curr = currgroup;
+    }
+  }
+  // fragment counting
+  R.frag_len = 0; R.numfrag = 0;
+  if (!S.unitig(n)) {
+    R.frag_len = (double)((float)S.r_len[n] * S.r_count[n]);
+    double sc = S.r_count[n];
+    if (npr == 1) {
+      const int pi = S.pair[S.pairi(n, 0)];
+      if (pi != -1 && n > pi && S.r_nh[pi]) sc -= S.pair_cnt[S.pairi(n, 0)];
+    }
+    if (sc > 0.000001) R.numfrag = sc;
+  }
+  return true;
+}
+
+// the part of a simple read's effect that does not depend on the other reads of the step; fresh_id = the colour it mints
+STG_HD void commit_free(Grp& S, const FastRec& R, int fresh_id) {
+  if (R.gp_np >= 0) { S.rg[(size_t)S.rcap_off[R.gp_np]] = R.gp_root; S.g_color[R.gp_root] = R.gp_col; }
+  for (int v = 0; v < R.nv; v++) S.g_color[R.grp[v]] = R.gcol[v];
+  if (R.newcol) {
+    if (fresh_id < S.ccap) S.eqcol[fresh_id] = R.fresh_gc;
+    else S.err |= STG_GERR_GROUPS;
+  }
+}
+
+// the ordered part: float sums in read order, readgroup pushes, the lane cursor, the bundle's fragment sums
+STG_HD void commit_ordered(Grp& S, const FastRec& R, int n, double& num_fragments, double& frag_len) {
+  for (int v = 0; v < R.nv; v++) {
+    if (R.has_multi >> v & 1) S.g_multi[R.grp[v]] += R.multi[v];
+    S.g_cov[R.grp[v]] += R.cov[v];
+  }
+  for (int k = 0; k < R.nrg0; k++) rg_add(S, n, R.rgv[k]);
+  for (int k = 0; k < R.nrg1; k++) rg_add(S, R.npc, R.rgv[R.nrg0 + k]);
+  if (R.sno >= 0) S.curr.set(R.sno, R.curr);
+  if (R.frag_len != 0) frag_len += R.frag_len;
+  if (R.numfrag != 0) num_fragments += R.numfrag;
+}
+
+// Host-side emulation of the warp's schedule (tools/groups_hostcheck.cu): the lanes of a step are run one after the
+// other against the same state, which is what the warp does, since classify_read() only reads.
+inline void groups_first_half_steps(Grp& S, int32_t* jt_perm, int32_t* jt_inv, double* num_fragments_out, double* frag_len_out,
+                                    int64_t* n_simple = nullptr) {
+  int color = 0;
+  double num_fragments = 0, frag_len = 0;
+  static FastRec R[32];
+  int n = 0;
+  while (n < S.nr && !S.err) {
+    const int hi = n + 32 < S.nr ? n + 32 : S.nr;
+    int k = 0;
+    bool ok[32];
+    for (int l = 0; n + l < hi; l++) ok[l] = classify_read(S, n + l, n, hi, R[l]);
+    // two reads of the step that continue into the SAME mate (a read with several pair links) see each other's
+    // readgroup pushes: the later one is not simple
+    for (int l = 1; n + l < hi; l++)
+      for (int l2 = 0; l2 < l && ok[l]; l2++)
+        if (ok[l2] && R[l].npc >= 0 && R[l2].npc == R[l].npc) ok[l] = false;
+    while (n + k < hi && ok[k]) k++;
+    int minted = 0;
+    for (int l = 0; l < k; l++) { commit_free(S, R[l], color + minted); minted += R[l].newcol; }
+    for (int l = 0; l < k; l++) commit_ordered(S, R[l], n + l, num_fragments, frag_len);
+    S.ncol += minted; color += minted;
+    if (n_simple) *n_simple += k;
+    n += k;
+    if (n < S.nr && k < 32 && !S.err) { color = walk_read(S, n, color, num_fragments, frag_len); n++; }
+  }
+  *num_fragments_out = num_fragments; *frag_len_out = frag_len;
+  if (S.err) return;
+  walk_finish(S, jt_perm, jt_inv);
 }
 
 // ---- second half of a9: colours across the three lanes, then bundles ------------------------------------------

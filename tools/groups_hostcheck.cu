@@ -21,7 +21,7 @@ static int cmp(const char* what, int64_t b, const T* got, const T* want, size_t 
 }
 
 extern "C" int hostcheck_groups(const stg_packed_batch* B, uint32_t junctionsupport, int32_t junctionthr, uint32_t bundledist,
-                                int64_t b_first, int64_t b_last) {
+                                int64_t b_first, int64_t b_last, int steps, int64_t* stats) {
   orc_params P = {junctionsupport, junctionthr, 0};
   JuncParams prm = {junctionsupport, 25, junctionthr, 0};
   int bad = 0;
@@ -82,11 +82,13 @@ extern "C" int hostcheck_groups(const stg_packed_batch* B, uint32_t junctionsupp
     S.g_merge = g_merge.data(); S.g_grid = g_grid.data(); S.g_cov = g_cov.data(); S.g_multi = g_multi.data(); S.g_alive = g_alive.data();
     S.ng = 0; S.gcap = (int)R; S.eqcol = eqcol.data(); S.ncol = 0; S.ccap = (int)(R + 3 * nr);
     S.rg = rgv.data(); S.rg_cnt = rg_cnt.data(); S.rcap_off = rcap_off.data();
-    S.curr[0] = S.curr[1] = S.curr[2] = -1; S.startg[0] = S.startg[1] = S.startg[2] = -1;
+    S.curr.fill(-1); S.startg.fill(-1);
     S.junctionsupport = junctionsupport; S.bundledist = bundledist; S.refstart = B->b_start[b]; S.len = len;
     S.c1 = cov.data() + len; S.prm = prm; S.err = 0;
     double nf = 0, fl = 0;
-    groups_first_half(S, perm.data(), inv.data(), &nf, &fl);
+    if (steps) groups_first_half_steps(S, perm.data(), inv.data(), &nf, &fl, stats);   // the warp's schedule, emulated
+    else groups_first_half(S, perm.data(), inv.data(), &nf, &fl);
+    if (stats) stats[1] += nr;
     int e = 0;
     if (S.err) { fprintf(stderr, "bundle %lld: capacity error\n", (long long)b); e = 1; }
     if (!e && (S.ng != o.n_groups || S.ncol != o.n_colors || S.nJ != o.n_juncs)) {
@@ -100,7 +102,8 @@ extern "C" int hostcheck_groups(const stg_packed_batch* B, uint32_t junctionsupp
       e |= cmp("seg_start", b, seg_s.data(), o.seg_start, nseg);
       e |= cmp("seg_end", b, seg_e.data(), o.seg_end, nseg);
       e |= cmp("rjunc", b, rj.data(), o.rjunc, nintr);
-      e |= cmp("startgroup", b, S.startg, o.startgroup, 3);
+      const int32_t sg[3] = {S.startg.a, S.startg.b, S.startg.c};
+      e |= cmp("startgroup", b, sg, o.startgroup, 3);
       e |= cmp("num_fragments", b, &nf, &o.num_fragments, 1);
       e |= cmp("frag_len", b, &fl, &o.frag_len, 1);
       const int8_t* al = o.g_alive;
@@ -114,7 +117,10 @@ extern "C" int hostcheck_groups(const stg_packed_batch* B, uint32_t junctionsupp
       e |= cmp("merge", b, g_merge.data(), o.merge, S.ng);
       e |= cmp("eqcol", b, eqcol.data(), o.eqcol, S.ncol);
       for (uint32_t n = 0; n < nr && !e; n++) {
-        if (rg_cnt[n] != o.rg_off[n + 1] - o.rg_off[n]) { fprintf(stderr, "bundle %lld: rg count of read %u\n", (long long)b, n); e = 1; break; }
+        if (rg_cnt[n] != o.rg_off[n + 1] - o.rg_off[n]) {
+          fprintf(stderr, "bundle %lld: rg count of read %u: got %u want %u; nseg %d npair %d mate %d strand %d nh %d\n", (long long)b, n, rg_cnt[n],
+                  o.rg_off[n + 1] - o.rg_off[n], S.nseg(n), S.npair(n), S.npair(n) ? B->pair_idx[B->r_pair_off[r0 + n]] : -9, B->r_strand[r0 + n], B->r_nh[r0 + n]);
+          e = 1; break; }
         e |= cmp("rg", b, rgv.data() + rcap_off[n], o.rg + o.rg_off[n], rg_cnt[n]);
       }
       // junction table in re-sorted order
@@ -132,7 +138,8 @@ extern "C" int hostcheck_groups(const stg_packed_batch* B, uint32_t junctionsupp
       std::vector<float> negp(ng + 1, 0.f), bun_cov(3 * ng + 1), bun_multi(3 * ng + 1), bn_cov(3 * ng + 1);
       std::vector<uint32_t> bn_s(3 * ng + 1), bn_e(3 * ng + 1);
       Grp2 T;
-      T.ng = ng; T.ncol = nc; T.bundledist = bundledist; T.startg = S.startg;
+      T.ng = ng; T.ncol = nc; T.bundledist = bundledist; const int32_t sg2[3] = {S.startg.a, S.startg.b, S.startg.c};
+      T.startg = sg2;
       T.g_start = g_start.data(); T.g_end = g_end.data(); T.g_next = g_next.data(); T.g_cov = g_cov.data(); T.g_multi = g_multi.data();
       T.color = color.data(); T.negp = negp.data(); T.eq = eq.data(); T.eqneg = eqneg.data(); T.eqpos = eqpos.data();
       T.bundlecol = bundlecol.data(); T.g2b = g2b.data();

@@ -26,7 +26,7 @@ def main():
     import orc
     from stringtie_b200 import synth
     L = C.CDLL(build())
-    L.hostcheck_groups.argtypes = [C.POINTER(orc.StgPackedBatch), C.c_uint32, C.c_int32, C.c_uint32, C.c_int64, C.c_int64]
+    L.hostcheck_groups.argtypes = [C.POINTER(orc.StgPackedBatch), C.c_uint32, C.c_int32, C.c_uint32, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_int64)]
     L.hostcheck_groups.restype = C.c_int
     cases = []
     gd = os.path.join(ROOT, "tests", "golden")
@@ -35,6 +35,7 @@ def main():
         cases.append((name, {k: z[k] for k in z.files}))
     for seed in (1, 2, 3):
         cases.append((f"synth{seed}", synth.make_batch(n_bundles=40, seed=seed)))
+    cases.append(("deep", synth.make_batch(n_bundles=6, reads_per_bundle=40000, seed=4)))
     cases.append(("adversarial", synth.make_adversarial(seed=5)))
     for seed in (38, 43):   # the repair appends junction rows and the table is re-sorted
         a = synth.make_adversarial(seed=seed, n_bundles=10, max_reads=250)
@@ -45,9 +46,12 @@ def main():
     for name, a in cases:
         pb, keep = orc.make_packed(a)
         for bd in (50, 0):
-            r = L.hostcheck_groups(C.byref(pb), 10, 1, bd, 0, int(pb.n_bundles))
-            print(f"{name}: bundledist {bd}: {int(pb.n_bundles)} bundles, {r} differ")
-            bad += r
+            for steps in (0, 1):
+                st = (C.c_int64 * 2)(0, 0)
+                r = L.hostcheck_groups(C.byref(pb), 10, 1, bd, 0, int(pb.n_bundles), steps, st)
+                print(f"{name}: bundledist {bd}, {'warp steps' if steps else 'sequential'}: {int(pb.n_bundles)} bundles, {r} differ"
+                      + (f", {st[0]}/{st[1]} reads simple" if steps else ""))
+                bad += r
     sys.exit(1 if bad else 0)
 
 
