@@ -145,10 +145,10 @@ __global__ void __maxnreg__(232) groups_walk_kernel(DevBatchView v, GroupsView g
       const unsigned run = k == 32 ? FULL : (1u << k) - 1u;
       const unsigned minters = __ballot_sync(FULL, ok && R[lane].newcol) & run;
       const int color0 = __shfl_sync(FULL, color, 0);
-      if (lane < k) commit_free(S, R[lane], color0 + __popc(minters & ((1u << lane) - 1u)));
+      if (lane < k) commit_free(S, R[lane], me, color0 + __popc(minters & ((1u << lane) - 1u)));
       __syncwarp();
       if (lane == 0) {
-        for (int j = 0; j < k; j++) commit_ordered(S, R[j], n + j, nf, fl);
+        for (int j = 0; j < k; j++) commit_ordered(S, R[j], nf, fl);
         const int minted = __popc(minters);
         color += minted; S.ncol += minted;
       }

@@ -655,21 +655,32 @@ struct FastRec {
   double frag_len, numfrag;     // what the read adds to the bundle's sums
 };
 
+// development aid: tools/groups_hostcheck.cu counts why reads were not simple (reason = position of the test below)
+#if defined(STG_FP_COUNT_BAILS)
+extern long long stg_fp_bails[64];   // [why]: steps whose run of simple reads was cut by test `why`; [0]: steps; [63]: full steps
+extern int stg_fp_last;
+#endif
+#if !defined(__CUDA_ARCH__) && defined(STG_FP_COUNT_BAILS)
+inline bool fp_bail(int why) { stg_fp_last = why; return false; }
+#else
+STG_HD bool fp_bail(int) { return false; }
+#endif
+
 STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
   R.nv = 0; R.nrg0 = 0; R.nrg1 = 0; R.has_multi = 0; R.sno = -1; R.newcol = 0; R.fresh_gc = -1; R.gp_np = -1; R.npc = -1;
   const int nj = S.njunc(n);
   // the repair must leave the read alone: every junction stranded, good, not demoted, not flagged
   for (int i = 0; i < nj; i++) {
     const int jd = S.rj[S.rji(n, i)];
-    if (jd >= S.nj0) return false;
+    if (jd >= S.nj0) return fp_bail(1);
     const int8_t st = S.jt_strand[jd];
     if (!st || S.jp_good[jd] != 1 || S.jp_good_strand[jd] != st || S.j_nreads[jd] < 0 || S.j_good[jd] < 0 || S.jt_mm[jd] < 0)
-      return false;
+      return fp_bail(2);
   }
   const int npr = S.npair(n);
-  if (npr > 1) return false;
+  if (npr > 1) return fp_bail(3);
   const int8_t strand_n = S.strand[n];
-  if (!nj && strand_n && npr) return false;   // may lose its strand (rlink.cpp:15056-15092)
+  if (!nj && strand_n && npr) return fp_bail(4);   // may lose its strand (rlink.cpp:15056-15092)
   int sno = (int)strand_n + 1;
   float single_count = S.r_count[n];
   int np = -1, readcol = -1;
@@ -678,16 +689,16 @@ STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
   if (npr == 1) {
     const int m = S.pair[S.pairi(n, 0)];
     if (m > -1 && S.r_nh[m]) {
-      if (m >= lo && m < hi) return false;   // the mate is classified in the same step
+      if (m >= lo && m < hi) return fp_bail(5);   // the mate is classified in the same step
       const int snop = (int)S.strand[m] + 1;
       if (sno != snop) {
         if (sno == 1) sno = snop;
-        else if (snop != 1) return false;    // un-pairing
+        else if (snop != 1) return fp_bail(6);    // un-pairing
       }
       const float pc = S.pair_cnt[S.pairi(n, 0)];
       single_count -= pc;
       if (m < n) {
-        if (!S.rg_cnt[m]) return false;
+        if (!S.rg_cnt[m]) return fp_bail(7);
         int grouppair = S.rg[(size_t)S.rcap_off[m]];
         while (S.g_merge[grouppair] != grouppair) grouppair = S.g_merge[grouppair];
         readcol = find_color(S, S.g_color[grouppair]);
@@ -699,7 +710,7 @@ STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
     }
   }
   if (single_count > 0.000001) {
-    if (pass) return false;                  // two passes of the same read see each other's effects
+    if (pass) return fp_bail(8);                  // two passes of the same read see each other's effects
     sno = (int)strand_n + 1;
     fresh = true;
     if (!S.unitig(n)) readcov = single_count;
@@ -715,21 +726,21 @@ STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
                         (S.slen(cn, 0) >= S.junctionsupport || (S.njunc(cn) && S.rjstrand(cn, 0)));
     if (!placed) {
       int currgroup = S.curr.get(sno);
-      if (currgroup == -1) return false;
+      if (currgroup == -1) return fp_bail(9);
       int lastgroup = -1;
       const uint32_t rstart = S.r_start[cn];
       while (currgroup != -1 && rstart > S.g_end[currgroup]) { lastgroup = currgroup; currgroup = S.g_next[currgroup]; }
       if (currgroup == -1 || S.seg_e[S.segi(cn, 0)] < S.g_start[currgroup]) currgroup = lastgroup;
-      if (currgroup == -1) return false;
+      if (currgroup == -1) return fp_bail(10);
       int thisgroup = currgroup, ncoord = S.nseg(cn), lastpushed = -1, i = 0;
       bool first = true;
       while (i < ncoord) {
-        if (!keep_exon(S, cn, i)) return false;
+        if (!keep_exon(S, cn, i)) return fp_bail(11);
         const uint32_t ss = S.seg_s[S.segi(cn, i)], se = S.seg_e[S.segi(cn, i)];
         while (thisgroup != -1 && ss > S.g_end[thisgroup]) thisgroup = S.g_next[thisgroup];
-        if (thisgroup == -1 || se + localdist < S.g_start[thisgroup]) return false;      // a new group
-        if (ss < S.g_start[thisgroup] || se > S.g_end[thisgroup]) return false;           // the group would grow
-        if (S.g_grid[thisgroup] != thisgroup || S.g_merge[thisgroup] != thisgroup) return false;
+        if (thisgroup == -1 || se + localdist < S.g_start[thisgroup]) return fp_bail(12);      // a new group
+        if (ss < S.g_start[thisgroup] || se > S.g_end[thisgroup]) return fp_bail(13);           // the group would grow
+        if (S.g_grid[thisgroup] != thisgroup || S.g_merge[thisgroup] != thisgroup) return fp_bail(14);
         if (!i) {
           const uint32_t base = S.rcap_off[cn], cnt = S.rg_cnt[cn];
           for (uint32_t g = 0; g < cnt; g++) {
@@ -737,9 +748,9 @@ STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
             while (S.g_merge[x] != x) x = S.g_merge[x];
             if (x == thisgroup) { first = false; break; }
           }
-          if (cnp > -1 && S.r_nh[cnp] && cnp < cn && find_color(S, S.g_color[thisgroup]) != readcol) return false;   // un-pairing
+          if (cnp > -1 && S.r_nh[cnp] && cnp < cn && find_color(S, S.g_color[thisgroup]) != readcol) return fp_bail(15);   // un-pairing
         }
-        if (R.nv == STG_FP_MAXV) return false;
+        if (R.nv == STG_FP_MAXV) return fp_bail(16);
         const float flen = (float)(se - ss + 1u);
         const int v = R.nv++;
         R.grp[v] = thisgroup;
@@ -750,7 +761,7 @@ STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
         if (fresh) { R.newcol = 1; R.fresh_gc = gc; readcol = gc; fresh = false; }
         else if (readcol != gc) {
           if (i && !S.rjstrand(cn, i - 1)) readcol = gc;
-          else return false;                                                              // two colours are united
+          else return fp_bail(17);                                                              // two colours are united
         }
         if (thisgroup != lastpushed) {
           if (first) { R.rgv[R.nrg0 + R.nrg1] = thisgroup; if (cn == n) R.nrg0++; else R.nrg1++; }
@@ -761,7 +772,7 @@ STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
           cn = cnp; cnp = -1;
           ncoord = S.nseg(cn);
           first = true;
-          if (S.r_start[cn] > S.g_end[thisgroup]) return false;                           // the group would grow
+          if (S.r_start[cn] > S.g_end[thisgroup]) return fp_bail(18);                           // the group would grow
           lastpushed = -1;
           i = -1;
           R.npc = cn;
@@ -785,24 +796,26 @@ STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
   return true;
 }
 
-// the part of a simple read's effect that does not depend on the other reads of the step; fresh_id = the colour it mints
-STG_HD void commit_free(Grp& S, const FastRec& R, int fresh_id) {
+// the part of a simple read's effect that does not depend on the other reads of the step; fresh_id = the colour it
+// mints.  The readgroup pushes belong here: read n's list is only touched by n itself, and a mate's list by the one
+// read of the step that continues into it (the caller makes sure of that).
+STG_HD void commit_free(Grp& S, const FastRec& R, int n, int fresh_id) {
   if (R.gp_np >= 0) { S.rg[(size_t)S.rcap_off[R.gp_np]] = R.gp_root; S.g_color[R.gp_root] = R.gp_col; }
   for (int v = 0; v < R.nv; v++) S.g_color[R.grp[v]] = R.gcol[v];
   if (R.newcol) {
     if (fresh_id < S.ccap) S.eqcol[fresh_id] = R.fresh_gc;
     else S.err |= STG_GERR_GROUPS;
   }
+  for (int k = 0; k < R.nrg0; k++) rg_add(S, n, R.rgv[k]);
+  for (int k = 0; k < R.nrg1; k++) rg_add(S, R.npc, R.rgv[R.nrg0 + k]);
 }
 
-// the ordered part: float sums in read order, readgroup pushes, the lane cursor, the bundle's fragment sums
-STG_HD void commit_ordered(Grp& S, const FastRec& R, int n, double& num_fragments, double& frag_len) {
+// the ordered part: float sums in read order, the lane cursor, the bundle's fragment sums
+STG_HD void commit_ordered(Grp& S, const FastRec& R, double& num_fragments, double& frag_len) {
   for (int v = 0; v < R.nv; v++) {
     if (R.has_multi >> v & 1) S.g_multi[R.grp[v]] += R.multi[v];
     S.g_cov[R.grp[v]] += R.cov[v];
   }
-  for (int k = 0; k < R.nrg0; k++) rg_add(S, n, R.rgv[k]);
-  for (int k = 0; k < R.nrg1; k++) rg_add(S, R.npc, R.rgv[R.nrg0 + k]);
   if (R.sno >= 0) S.curr.set(R.sno, R.curr);
   if (R.frag_len != 0) frag_len += R.frag_len;
   if (R.numfrag != 0) num_fragments += R.numfrag;
@@ -820,16 +833,25 @@ inline void groups_first_half_steps(Grp& S, int32_t* jt_perm, int32_t* jt_inv, d
     const int hi = n + 32 < S.nr ? n + 32 : S.nr;
     int k = 0;
     bool ok[32];
+#if defined(STG_FP_COUNT_BAILS)
+    int why[32];
+    for (int l = 0; n + l < hi; l++) { ok[l] = classify_read(S, n + l, n, hi, R[l]); why[l] = stg_fp_last; }
+#else
     for (int l = 0; n + l < hi; l++) ok[l] = classify_read(S, n + l, n, hi, R[l]);
+#endif
     // two reads of the step that continue into the SAME mate (a read with several pair links) see each other's
     // readgroup pushes: the later one is not simple
     for (int l = 1; n + l < hi; l++)
       for (int l2 = 0; l2 < l && ok[l]; l2++)
         if (ok[l2] && R[l].npc >= 0 && R[l2].npc == R[l].npc) ok[l] = false;
     while (n + k < hi && ok[k]) k++;
+#if defined(STG_FP_COUNT_BAILS)
+    stg_fp_bails[0]++;
+    if (n + k < hi) stg_fp_bails[why[k] > 0 && why[k] < 60 ? why[k] : 62]++; else stg_fp_bails[63]++;
+#endif
     int minted = 0;
-    for (int l = 0; l < k; l++) { commit_free(S, R[l], color + minted); minted += R[l].newcol; }
-    for (int l = 0; l < k; l++) commit_ordered(S, R[l], n + l, num_fragments, frag_len);
+    for (int l = 0; l < k; l++) { commit_free(S, R[l], n + l, color + minted); minted += R[l].newcol; }
+    for (int l = 0; l < k; l++) commit_ordered(S, R[l], num_fragments, frag_len);
     S.ncol += minted; color += minted;
     if (n_simple) *n_simple += k;
     n += k;

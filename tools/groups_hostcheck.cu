@@ -2,7 +2,11 @@
 // Steps through the per-bundle code of stringtie_b200/csrc/groups_device.cuh (rows a8 + a9) compiled for the HOST and
 // compares every field with the oracle (oracle/liborc.so), so that the logic can be debugged on a box without a GPU
 // before the kernels go to the B200.  Build + run: python tools/groups_hostcheck.py
+#define STG_FP_COUNT_BAILS 1
 #include "../stringtie_b200/csrc/groups_device.cuh"
+long long stg_fp_bails[64];
+int stg_fp_last;
+extern "C" long long* hostcheck_bails() { return stg_fp_bails; }
 #include "../oracle/stg_oracle.h"
 #include <cstdio>
 #include <cstring>
