@@ -652,6 +652,7 @@ struct FastRec {
   int32_t newcol, fresh_gc;     // mints a colour, attached to fresh_gc
   int32_t gp_np, gp_root, gp_col;   // earlier mate: readgroup[np][0] = gp_root, color of gp_root = gp_col (gp_np = -1: none)
   int32_t npc;                  // mate that continued the fragment (-1: none)
+  int32_t unpair_np;            // earlier mate the read is un-paired from (-1: none)
   double frag_len, numfrag;     // what the read adds to the bundle's sums
 };
 
@@ -667,7 +668,7 @@ STG_HD bool fp_bail(int) { return false; }
 #endif
 
 STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
-  R.nv = 0; R.nrg0 = 0; R.nrg1 = 0; R.has_multi = 0; R.sno = -1; R.newcol = 0; R.fresh_gc = -1; R.gp_np = -1; R.npc = -1;
+  R.nv = 0; R.nrg0 = 0; R.nrg1 = 0; R.has_multi = 0; R.sno = -1; R.newcol = 0; R.fresh_gc = -1; R.gp_np = -1; R.npc = -1; R.unpair_np = -1;
   const int nj = S.njunc(n);
   // the repair must leave the read alone: every junction stranded, good, not demoted, not flagged
   for (int i = 0; i < nj; i++) {
@@ -748,7 +749,12 @@ STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
             while (S.g_merge[x] != x) x = S.g_merge[x];
             if (x == thisgroup) { first = false; break; }
           }
-          if (cnp > -1 && S.r_nh[cnp] && cnp < cn && find_color(S, S.g_color[thisgroup]) != readcol) return fp_bail(15);   // un-pairing
+          if (cnp > -1 && S.r_nh[cnp] && cnp < cn && find_color(S, S.g_color[thisgroup]) != readcol) {
+            // the mates lie in groups of different colours: the link is cut and the read carries on with a colour of
+            // its own (rlink.cpp:1383-1389).  Nothing else looks at the two link entries during this step.
+            R.unpair_np = cnp;
+            fresh = true;
+          }
         }
         if (R.nv == STG_FP_MAXV) return fp_bail(16);
         const float flen = (float)(se - ss + 1u);
@@ -788,7 +794,7 @@ STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
     R.frag_len = (double)((float)S.r_len[n] * S.r_count[n]);
     double sc = S.r_count[n];
     if (npr == 1) {
-      const int pi = S.pair[S.pairi(n, 0)];
+      const int pi = R.unpair_np >= 0 ? -1 : S.pair[S.pairi(n, 0)];
       if (pi != -1 && n > pi && S.r_nh[pi]) sc -= S.pair_cnt[S.pairi(n, 0)];
     }
     if (sc > 0.000001) R.numfrag = sc;
@@ -806,6 +812,7 @@ STG_HD void commit_free(Grp& S, const FastRec& R, int n, int fresh_id) {
     if (fresh_id < S.ccap) S.eqcol[fresh_id] = R.fresh_gc;
     else S.err |= STG_GERR_GROUPS;
   }
+  if (R.unpair_np >= 0) unpair(S, n, 0, R.unpair_np);
   for (int k = 0; k < R.nrg0; k++) rg_add(S, n, R.rgv[k]);
   for (int k = 0; k < R.nrg1; k++) rg_add(S, R.npc, R.rgv[R.nrg0 + k]);
 }
