@@ -1,13 +1,13 @@
 // group_kernels.cu — sm_100a kernels of SURVEY.md §8 rows a8 + a9 (read loop of build_graphs, groups, colours,
 // bundles / bundlenodes).  The per-bundle algorithm is in groups_device.cuh; this file maps it onto the GPU:
 //   group_caps_kernel    one thread per read: how many readgroup / group / colour slots the read can need at most
-//   groups_walk_kernel   one warp per bundle, bundles in order of decreasing read count; lane 0 walks the reads
+//   groups_walk_kernel   one CTA per bundle, bundles in order of decreasing read count: 128 reads classified per step
 //   groups_colour_kernel one warp per bundle: the lanes compact the bundle's groups and colours into the dense
 //                        arrays, lane 0 runs the colour pass and builds bundles / bundlenodes
 //   groups_rg_kernel     one thread per read: compacts readgroup
 //   groups_junc_kernel   one warp per bundle: the junction table in the order the reference re-sorts it into
-// The walk is the reference's sequential loop (its state flows both ways between repair, grouping and un-pairing), so
-// the parallelism of this first version is ACROSS bundles; the longest bundle bounds the stage.
+// The reference's loop is sequential (its state flows both ways between repair, grouping and un-pairing); the walk
+// kernel runs the reads that change no structure in parallel and only the others one by one (groups_device.cuh).
 #include "groups_device.cuh"
 
 namespace {
@@ -58,10 +58,11 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) group_caps_kernel(DevBatchView
 
 // The group arrays of a bundle live in SHARED memory while they fit (a bundle has ~10 groups on average, a few hundred
 // when it is deep): every read touches a handful of group fields read-modify-write, and from global memory each of
-// those is an L2 round trip on the walker's critical path.  GROUPS_SMEM slots per warp; a bundle that outgrows them
-// is moved to its global arrays and carries on there.
-#define GROUPS_SMEM 256
-#define GROUPS_WARPS 2
+// those is an L2 round trip on the critical path.  A bundle that outgrows GROUPS_SMEM slots is moved to its global
+// arrays and carries on there.
+#define GROUPS_SMEM 384
+#define GROUPS_WARPS 4                      // warps of a CTA; one CTA walks one bundle
+#define GROUPS_STEP (32 * GROUPS_WARPS)     // reads classified per step
 struct GroupSmem {
   uint32_t start[GROUPS_SMEM], end[GROUPS_SMEM];
   int32_t color[GROUPS_SMEM], next[GROUPS_SMEM], merge[GROUPS_SMEM], grid[GROUPS_SMEM];
@@ -71,21 +72,31 @@ struct GroupSmem {
 
 struct GroupGlobal { uint32_t *start, *end; int32_t *color, *next, *merge, *grid; float *cov, *multi; int8_t* alive; int cap; };
 
-__device__ __forceinline__ void groups_to_global(Grp& S, const GroupGlobal& G, int from, int step) {
-  for (int i = from; i < S.ng; i += step) {
+__device__ __forceinline__ void groups_to_global(const Grp& S, const GroupGlobal& G, int ng, int from, int step) {
+  for (int i = from; i < ng; i += step) {
     G.start[i] = S.g_start[i]; G.end[i] = S.g_end[i]; G.color[i] = S.g_color[i]; G.next[i] = S.g_next[i];
     G.merge[i] = S.g_merge[i]; G.grid[i] = S.g_grid[i]; G.cov[i] = S.g_cov[i]; G.multi[i] = S.g_multi[i]; G.alive[i] = S.g_alive[i];
   }
 }
 
-__global__ void __maxnreg__(232) groups_walk_kernel(DevBatchView v, GroupsView g, JuncParams prm) {
-  __shared__ GroupSmem sm[GROUPS_WARPS];
-  __shared__ FastRec fr[GROUPS_WARPS][32];
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= v.n_bundles) return;
-  const int lane = threadIdx.x & 31;
-  GroupSmem& M = sm[threadIdx.x >> 5];
-  const uint32_t b = g.order[w];
+// what thread 0 (the owner of the walk's mutable scalars) shares with the CTA between steps
+struct WalkCtl {
+  int32_t curr[3];
+  int32_t ng, color, err;
+  uint32_t ok_mask[GROUPS_WARPS], mint_mask[GROUPS_WARPS];
+  int32_t npc[GROUPS_STEP];
+};
+
+// The CTA's schedule (groups_device.cuh, "the parallel form of the loop"): classify GROUPS_STEP reads against the
+// state as it stands, commit the leading run of simple ones — the order-free part by every thread for its own read,
+// the float sums by warp 0 with one lane per group residue so that every group's sum is added in read order — walk
+// the first non-simple read the reference's way (thread 0), start over behind it.
+__global__ void __launch_bounds__(GROUPS_STEP) groups_walk_kernel(DevBatchView v, GroupsView g, JuncParams prm) {
+  __shared__ GroupSmem M;
+  __shared__ FastRec R[GROUPS_STEP];
+  __shared__ WalkCtl ctl;
+  const uint32_t b = g.order[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t r0 = v.b_read_off[b], nr = v.b_read_off[b + 1] - r0;
   const uint32_t j0 = v.b_junc_off[b], nj0 = v.b_junc_off[b + 1] - j0;
   if (nr == 0) return;
@@ -106,8 +117,8 @@ __global__ void __maxnreg__(232) groups_walk_kernel(DevBatchView v, GroupsView g
   S.nj0 = (int)nj0; S.nJ = (int)nj0; S.apcap = (int)nintr;
   const size_t G0 = g.rcap_off[r0];
   const uint32_t gcap = g.rcap_off[r0 + nr] - g.rcap_off[r0];
-  GroupGlobal GG{g.g_start + G0, g.g_end + G0, g.g_color + G0, g.g_next + G0, g.g_merge + G0, g.g_grid + G0, g.g_cov + G0,
-                 g.g_multi + G0, g.g_alive + G0, (int)gcap};
+  const GroupGlobal GG{g.g_start + G0, g.g_end + G0, g.g_color + G0, g.g_next + G0, g.g_merge + G0, g.g_grid + G0, g.g_cov + G0,
+                       g.g_multi + G0, g.g_alive + G0, (int)gcap};
   S.g_start = M.start; S.g_end = M.end; S.g_color = M.color; S.g_next = M.next; S.g_merge = M.merge; S.g_grid = M.grid;
   S.g_cov = M.cov; S.g_multi = M.multi; S.g_alive = M.alive;
   S.ng = 0; S.gcap = GROUPS_SMEM;
@@ -118,62 +129,113 @@ __global__ void __maxnreg__(232) groups_walk_kernel(DevBatchView v, GroupsView g
   S.refstart = v.b_start[b]; S.len = v.b_len[b];
   S.c1 = v.bpcov + 3 * (size_t)v.b_gbase[b] + v.b_stride[b];
   S.prm = prm; S.err = 0;
-  if (gcap == 0 || gcap > 0x7fffffffu) { if (!lane) atomicOr(v.err_flag, STG_GERR_GROUPS); return; }
-  // The warp's schedule (groups_device.cuh, "the parallel form of the loop"): classify 32 reads, commit the leading
-  // run of simple ones, walk the first non-simple read the reference's way, start over behind it.  Mutable scalars of
-  // S (group / colour counts, cursors, appended rows) are only valid in lane 0; the cursors are broadcast every step.
-  FastRec* R = fr[threadIdx.x >> 5];
-  const unsigned FULL = 0xffffffffu;
+  if (gcap == 0 || gcap > 0x7fffffffu) { if (!tid) atomicOr(v.err_flag, STG_GERR_GROUPS); return; }
   bool in_smem = true;
-  int color = 0;
-  double nf = 0, fl = 0;
-  int n = 0, slow_len = 0, slow_budget = 0;
+  int color = 0;                 // thread 0
+  double nf = 0, fl = 0;         // thread 0
+  int n = 0, slow_len = 0, slow_budget = 0;   // uniform
   const int inr = (int)nr;
+  const unsigned FULL = 0xffffffffu;
+  if (tid == 0) ctl.err = 0;
+  __syncthreads();
   while (n < inr) {
-    S.curr.a = __shfl_sync(FULL, S.curr.a, 0); S.curr.b = __shfl_sync(FULL, S.curr.b, 0); S.curr.c = __shfl_sync(FULL, S.curr.c, 0);
-    if (__any_sync(FULL, S.err != 0)) { S.err |= STG_GERR_GROUPS; break; }
+    if (tid == 0) {
+      S.err |= (uint32_t)ctl.err;   // raised by the other threads during the last step
+      ctl.curr[0] = S.curr.a; ctl.curr[1] = S.curr.b; ctl.curr[2] = S.curr.c;
+      ctl.ng = S.ng; ctl.color = color; ctl.err = (int)S.err;
+    }
+    __syncthreads();   // (A) thread 0's state and everything the previous step wrote is visible
+    S.curr.a = ctl.curr[0]; S.curr.b = ctl.curr[1]; S.curr.c = ctl.curr[2];
+    if (ctl.err) break;
+    const int ng0 = ctl.ng, color0 = ctl.color;
     int k = 0;
     if (slow_budget == 0) {
-      const int hi = n + 32 < inr ? n + 32 : inr, me = n + lane;
-      bool ok = me < hi && classify_read(S, me, n, hi, R[lane]);
+      const int hi = n + GROUPS_STEP < inr ? n + GROUPS_STEP : inr, me = n + tid;
+      bool ok = me < hi && classify_read(S, me, n, hi, R[tid]);
+      ctl.npc[tid] = ok ? R[tid].npc : -1;
+      __syncthreads();   // (B)
       // reads that continue into the SAME mate see each other's readgroup pushes: only the first one stays simple
-      const int key = (ok && R[lane].npc >= 0) ? R[lane].npc : -1 - lane;
-      const unsigned same = __match_any_sync(FULL, key);
-      if (ok && R[lane].npc >= 0 && __ffs(same) - 1 != lane) ok = false;
-      const unsigned m = __ballot_sync(FULL, ok);
-      k = m == FULL ? 32 : __ffs(~m) - 1;
-      const unsigned run = k == 32 ? FULL : (1u << k) - 1u;
-      const unsigned minters = __ballot_sync(FULL, ok && R[lane].newcol) & run;
-      const int color0 = __shfl_sync(FULL, color, 0);
-      if (lane < k) commit_free(S, R[lane], me, color0 + __popc(minters & ((1u << lane) - 1u)));
-      __syncwarp();
-      if (lane == 0) {
-        for (int j = 0; j < k; j++) commit_ordered(S, R[j], nf, fl);
-        const int minted = __popc(minters);
-        color += minted; S.ncol += minted;
+      if (ok && R[tid].npc >= 0) {
+        const int mine = R[tid].npc;
+        for (int t = 0; t < tid; t++)
+          if (ctl.npc[t] == mine) { ok = false; break; }
+      }
+      const unsigned okm = __ballot_sync(FULL, ok), mim = __ballot_sync(FULL, ok && R[tid].newcol);
+      if (lane == 0) { ctl.ok_mask[warp] = okm; ctl.mint_mask[warp] = mim; }
+      __syncthreads();   // (C)
+      // k = length of the leading run of simple reads; fresh colours are numbered in read order
+      bool open = true;
+      int before = 0;     // colours minted by the run's reads ahead of this thread
+      int minted = 0;
+      for (int w2 = 0; w2 < GROUPS_WARPS; w2++) {
+        const unsigned m = ctl.ok_mask[w2];
+        const int kw = !open ? 0 : (m == FULL ? 32 : __ffs(~m) - 1);
+        const unsigned run = kw == 32 ? FULL : (1u << kw) - 1u;
+        const unsigned mi = ctl.mint_mask[w2] & run;
+        if (w2 < warp) before += __popc(mi);
+        else if (w2 == warp) before += __popc(mi & ((1u << lane) - 1u));
+        minted += __popc(mi);
+        k += kw;
+        if (kw < 32) open = false;
+      }
+      if (tid < k) {
+        commit_free(S, R[tid], me, color0 + before);
+        if (S.err) atomicOr(&ctl.err, (int)S.err);
+      }
+      __syncthreads();   // (D) colours and readgroup entries of the run are in place
+      if (warp == 0) {
+        // ordered float sums: lane l owns the groups with slot % 32 == l and adds their visits in read order; the sum
+        // of the group being worked on is kept in registers
+        int cur = -1;
+        float acc_cov = 0.f, acc_multi = 0.f;
+        for (int j = 0; j < k; j++) {
+          const int nv = R[j].nv, hm = R[j].has_multi;
+          for (int x = 0; x < nv; x++) {
+            const int gr = R[j].grp[x];
+            if ((gr & 31) == lane) {
+              if (gr != cur) {
+                if (cur >= 0) { S.g_cov[cur] = acc_cov; S.g_multi[cur] = acc_multi; }
+                cur = gr; acc_cov = S.g_cov[gr]; acc_multi = S.g_multi[gr];
+              }
+              if (hm >> x & 1) acc_multi += R[j].multi[x];
+              acc_cov += R[j].cov[x];
+            }
+          }
+        }
+        if (cur >= 0) { S.g_cov[cur] = acc_cov; S.g_multi[cur] = acc_multi; }
+        if (lane == 0) {
+          for (int j = 0; j < k; j++) {
+            if (R[j].sno >= 0) S.curr.set(R[j].sno, R[j].curr);
+            if (R[j].frag_len != 0) fl += R[j].frag_len;
+            if (R[j].numfrag != 0) nf += R[j].numfrag;
+          }
+          color += minted; S.ncol += minted;
+        }
       }
       n += k;
       if (k == 0) { slow_len = slow_len * 2 + 1 < 15 ? slow_len * 2 + 1 : 15; slow_budget = slow_len; }
       else if (k >= 8) slow_len = 0;
     } else slow_budget--;
-    if (n < inr && k < 32) {
+    if (n < inr && k < GROUPS_STEP) {
       // the read may create groups: leave shared memory before it can overflow
-      const int ng0 = __shfl_sync(FULL, S.ng, 0);
       if (in_smem && ng0 + (int)(S.rcap_off[n + 1] - S.rcap_off[n]) > GROUPS_SMEM) {
-        __syncwarp();
-        S.ng = ng0;
-        groups_to_global(S, GG, lane, 32);
+        __syncthreads();
+        groups_to_global(S, GG, ng0, tid, GROUPS_STEP);
         S.g_start = GG.start; S.g_end = GG.end; S.g_color = GG.color; S.g_next = GG.next; S.g_merge = GG.merge; S.g_grid = GG.grid;
         S.g_cov = GG.cov; S.g_multi = GG.multi; S.g_alive = GG.alive; S.gcap = GG.cap;
         in_smem = false;
-        __syncwarp();
       }
-      if (lane == 0) color = walk_read(S, n, color, nf, fl);
+      __syncthreads();   // (E) the float sums of warp 0 (and a move out of shared memory) are done
+      if (tid == 0) {
+        if (ctl.err) S.err |= (uint32_t)ctl.err;
+        if (!S.err) color = walk_read(S, n, color, nf, fl);
+      }
       n++;
     }
-    __syncwarp();
   }
-  if (lane == 0) {
+  __syncthreads();
+  if (tid == 0) {
+    if (ctl.err) S.err |= (uint32_t)ctl.err;
     if (!S.err) walk_finish(S, g.jt_perm + j0 + i0, g.jt_inv + j0 + i0);
     if (S.err) atomicOr(v.err_flag, S.err);
     else {
@@ -181,12 +243,10 @@ __global__ void __maxnreg__(232) groups_walk_kernel(DevBatchView v, GroupsView g
       g.b_numfrag[b] = nf; g.b_fraglen[b] = fl;
       g.b_startgroup[3 * b] = S.startg.a; g.b_startgroup[3 * b + 1] = S.startg.b; g.b_startgroup[3 * b + 2] = S.startg.c;
     }
+    ctl.ng = S.err ? 0 : S.ng;
   }
-  __syncwarp();
-  // the warp writes the groups out of shared memory
-  const int ng = __shfl_sync(FULL, S.ng, 0);
-  const bool spill = __shfl_sync(FULL, (int)(in_smem && !S.err), 0) != 0;
-  if (spill) { S.ng = ng; groups_to_global(S, GG, lane, 32); }
+  __syncthreads();
+  if (in_smem) groups_to_global(S, GG, ctl.ng, tid, GROUPS_STEP);   // the CTA writes the groups out of shared memory
 }
 
 // after the scans: b_ng / b_ncol / b_napp are exclusive prefixes
@@ -273,7 +333,7 @@ cudaError_t launch_group_caps(const DevBatchView& v, uint32_t* rcap, unsigned lo
 
 cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, cudaStream_t st) {
   if (v.n_bundles == 0) return cudaSuccess;
-  groups_walk_kernel<<<(unsigned)((v.n_bundles + GROUPS_WARPS - 1) / GROUPS_WARPS), 32 * GROUPS_WARPS, 0, st>>>(v, g, p);
+  groups_walk_kernel<<<(unsigned)v.n_bundles, GROUPS_STEP, 0, st>>>(v, g, p);
   return cudaGetLastError();
 }
 

@@ -830,18 +830,19 @@ STG_HD void commit_ordered(Grp& S, const FastRec& R, double& num_fragments, doub
 
 // Host-side emulation of the warp's schedule (tools/groups_hostcheck.cu): the lanes of a step are run one after the
 // other against the same state, which is what the warp does, since classify_read() only reads.
+#define STG_STEP_MAX 256
 inline void groups_first_half_steps(Grp& S, int32_t* jt_perm, int32_t* jt_inv, double* num_fragments_out, double* frag_len_out,
-                                    int64_t* n_simple = nullptr) {
+                                    int64_t* n_simple = nullptr, int W = 128) {
   int color = 0;
   double num_fragments = 0, frag_len = 0;
-  static FastRec R[32];
+  static FastRec R[STG_STEP_MAX];
   int n = 0;
   while (n < S.nr && !S.err) {
-    const int hi = n + 32 < S.nr ? n + 32 : S.nr;
+    const int hi = n + W < S.nr ? n + W : S.nr;
     int k = 0;
-    bool ok[32];
+    bool ok[STG_STEP_MAX];
 #if defined(STG_FP_COUNT_BAILS)
-    int why[32];
+    int why[STG_STEP_MAX];
     for (int l = 0; n + l < hi; l++) { ok[l] = classify_read(S, n + l, n, hi, R[l]); why[l] = stg_fp_last; }
 #else
     for (int l = 0; n + l < hi; l++) ok[l] = classify_read(S, n + l, n, hi, R[l]);
@@ -862,7 +863,7 @@ inline void groups_first_half_steps(Grp& S, int32_t* jt_perm, int32_t* jt_inv, d
     S.ncol += minted; color += minted;
     if (n_simple) *n_simple += k;
     n += k;
-    if (n < S.nr && k < 32 && !S.err) { color = walk_read(S, n, color, num_fragments, frag_len); n++; }
+    if (n < S.nr && k < W && !S.err) { color = walk_read(S, n, color, num_fragments, frag_len); n++; }
   }
   *num_fragments_out = num_fragments; *frag_len_out = frag_len;
   if (S.err) return;
