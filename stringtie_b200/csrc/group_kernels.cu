@@ -1,7 +1,7 @@
 // group_kernels.cu — sm_100a kernels of SURVEY.md §8 rows a8 + a9 (read loop of build_graphs, groups, colours,
 // bundles / bundlenodes).  The per-bundle algorithm is in groups_device.cuh; this file maps it onto the GPU:
 //   group_caps_kernel    one thread per read: how many readgroup / group / colour slots the read can need at most
-//   groups_walk_kernel   one CTA per bundle, bundles in order of decreasing read count: 128 reads classified per step
+//   groups_walk_kernel   one CTA per bundle, bundles in order of decreasing read count: 64 reads classified per step
 //   groups_colour_kernel one warp per bundle: the lanes compact the bundle's groups and colours into the dense
 //                        arrays, lane 0 runs the colour pass and builds bundles / bundlenodes
 //   groups_rg_kernel     one thread per read: compacts readgroup
@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) group_caps_kernel(DevBatchView
 // those is an L2 round trip on the critical path.  A bundle that outgrows GROUPS_SMEM slots is moved to its global
 // arrays and carries on there.
 #define GROUPS_SMEM 384
-#define GROUPS_WARPS 4                      // warps of a CTA; one CTA walks one bundle
+#define GROUPS_WARPS 2                      // warps of a CTA; one CTA walks one bundle (measured on C2: 4 warps 271 ms,
+                                            // 2 warps 210 ms; 4 warps for deep bundles beside 1-2 for the rest: 225-296 ms)
 #define GROUPS_STEP (32 * GROUPS_WARPS)     // reads classified per step
 struct GroupSmem {
   uint32_t start[GROUPS_SMEM], end[GROUPS_SMEM];
