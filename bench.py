@@ -107,8 +107,12 @@ def reference_hot(arrays, nbundles: int, threads: int, reps: int):
             path = os.path.join(td, "sample.stgb")
             write_stgb(path, sample)
             out = subprocess.check_output([tool, path, "--threads", str(threads), "--reps", str(reps), "--a7"], text=True)
+            out9 = subprocess.check_output([tool, path, "--threads", str(threads), "--reps", str(reps), "--a9b"], text=True)
         j = json.loads(out.strip().splitlines()[-1])
+        j9 = json.loads(out9.strip().splitlines()[-1])
         return {"value": j["reads_per_s"], "unit": "reads/s", "cores": threads, "kind": "reference",
+                "through_rows_a8_a9": {"reads_per_s": j9["reads_per_s"], "compute_s": j9["compute_s_max"],
+                                       "note": "same sample, the reference run on to the end of its bundle creation (rlink.cpp:15433)"},
                 "sample": desc + "; reference count_good_junctions (rlink.cpp:16656) + build_graphs up to the end of its "
                           "junction pass (rlink.cpp:14165-14842) on rebuilt BundleData, "
                           "aggregate of per-thread reads / per-thread compute time",
@@ -132,6 +136,7 @@ def main():
     ap.add_argument("--base-bundles", type=int, default=BASE_BUNDLES)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-groups", action="store_true", help="do not run the rows a8 + a9 stage after the timed passes")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -240,8 +245,28 @@ def main():
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     L, S, J = eng.stats(batch)
-    eng.set_profiling(False)
     kmean = {k: statistics.mean(v) for k, v in ktimes.items()}
+    # ---- the next rows (SURVEY §8 a8 + a9: read repair, groups, colours, bundles / bundlenodes), measured once on
+    # the resident batch, outside the timed region: reported beside the headline, not part of it
+    groups_stage = None
+    if not args.skip_groups:
+        try:
+            eng.set_profiling(True)
+            eng.sync()
+            t0 = time.perf_counter()
+            eng.build_groups(batch)
+            eng.sync()
+            wall = time.perf_counter() - t0
+            gk = {n: ms for n, ms in eng.kernel_times() if n.startswith("groups")}
+            gms = sum(gk.values())
+            groups_stage = {"rows": "a8 + a9 (stg_build_groups)", "kernel_ms": gk, "ms": gms, "wall_ms": 1e3 * wall,
+                            "reads_per_s": n_reads / (gms * 1e-3) if gms else None,
+                            "groups": int(eng.fetch_groups_array(batch, "GROUP_OFF")[-1]),
+                            "bundlenodes": int(eng.fetch_groups_array(batch, "N_BN").sum()),
+                            "note": "per GPU, one pass, outside the timed region; wall includes first-use cudaMalloc of the stage's buffers"}
+        except Exception as ex:   # the headline must not depend on the newer stage
+            groups_stage = {"error": str(ex)}
+    eng.set_profiling(False)
     batch.free()
 
     # ---- end-to-end through the C ABI from pinned host buffers ------------------------------------------------
@@ -326,7 +351,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config, "bundles_per_sec": world * n_bundles / (ms_step * 1e-3), "reads_per_gpu": n_reads,
             "bundles_per_gpu": n_bundles, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "kernel_ms": kmean}
+            "cpu_baseline": cpu_baseline, "kernel_ms": kmean, "rows_a8_a9": groups_stage}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
