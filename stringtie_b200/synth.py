@@ -230,12 +230,13 @@ def make_batch(n_bundles: int = 64, reads_per_bundle: float = 1700.0, seed: int 
 
 
 def make_adversarial(seed: int = 1, n_bundles: int = 12, max_reads: int = 400,
-                     neg_links: bool = False) -> Dict[str, np.ndarray]:
+                     neg_links: bool = False, spans=None) -> Dict[str, np.ndarray]:
     """Small random batches built to stress the kernels rather than to look like RNA-seq: spans that straddle
     the 1024-position sub-tiles and the BSIZE=10000 blocks, inexact weights (1/3, 1/7, 0.1 ...), many deposits on
     one position, overlapping / nested / opposite-strand / unstranded mates, unpaired remainders, negative
     pair_idx (only with neg_links=True: the reference itself indexes rd[-1] there, rlink.cpp:151-152, so such
-    inputs can only be checked against the C oracle), unitig reads, reads with many segments, empty bundles."""
+    inputs can only be checked against the C oracle), unitig reads, reads with many segments, empty bundles.
+    `spans`: bundle lengths to draw from (long spans with few reads give bundles of many separate groups)."""
     rng = np.random.default_rng(seed)
     out = {k: [] for k in ("b_start", "b_end", "r_start", "r_end", "r_len", "r_count", "r_nh", "r_strand", "r_flags",
                            "seg_start", "seg_end", "rjunc_idx", "pair_idx", "pair_cnt", "j_start", "j_end", "j_strand",
@@ -244,7 +245,7 @@ def make_adversarial(seed: int = 1, n_bundles: int = 12, max_reads: int = 400,
     weights = np.array([1.0, 0.5, 1.0 / 3.0, 0.25, 0.2, 1.0 / 7.0, 0.1, 2.0, 3.0, 1.0 / 3.0 + 1.0 / 3.0], dtype=np.float32)
     pos0 = 5000
     for b in range(n_bundles):
-        span = int(rng.choice([40, 900, 1023, 1024, 1025, 2048, 3000, 9999, 10000, 10001, 20500, 31000]))
+        span = int(rng.choice(spans if spans is not None else [40, 900, 1023, 1024, 1025, 2048, 3000, 9999, 10000, 10001, 20500, 31000]))
         nreads = 0 if b == 3 else int(rng.integers(1, max_reads))
         start = pos0
         end = pos0 + span - 1
@@ -332,6 +333,46 @@ def make_adversarial(seed: int = 1, n_bundles: int = 12, max_reads: int = 400,
         out["b_start"].append(start); out["b_end"].append(end)
         b_read_off.append(len(out["r_start"])); b_junc_off.append(len(out["j_start"]))
     from .stgb import INPUT_FIELDS
+    res = {k: np.asarray(v, dtype=INPUT_FIELDS[k]) for k, v in out.items()}
+    res["b_read_off"] = np.asarray(b_read_off, dtype=np.uint32)
+    res["b_junc_off"] = np.asarray(b_junc_off, dtype=np.uint32)
+    res["r_seg_off"] = np.asarray(r_seg_off, dtype=np.uint32)
+    res["r_pair_off"] = np.asarray(r_pair_off, dtype=np.uint32)
+    return res
+
+
+def make_sparse(n_reads: int = 3000, seed: int = 1, n_bundles: int = 2) -> Dict[str, np.ndarray]:
+    """Bundles of short unspliced reads spaced further apart than the grouping distance: every read (or mate pair)
+    founds its own group, so a bundle holds thousands of groups.  Odd bundles are paired (mates 3 reads apart)."""
+    from .stgb import INPUT_FIELDS
+    rng = np.random.default_rng(seed)
+    out = {k: [] for k in ("b_start", "b_end", "r_start", "r_end", "r_len", "r_count", "r_nh", "r_strand", "r_flags",
+                           "seg_start", "seg_end", "rjunc_idx", "pair_idx", "pair_cnt", "j_start", "j_end", "j_strand",
+                           "j_guide_match", "j_nreads", "j_nm", "j_mm")}
+    b_read_off, b_junc_off, r_seg_off, r_pair_off = [0], [0], [0], [0]
+    pos0 = 20000
+    for b in range(n_bundles):
+        starts = pos0 + np.cumsum(rng.integers(130, 400, size=n_reads))
+        lens = rng.integers(30, 60, size=n_reads)
+        counts = rng.choice(np.array([1.0, 0.5, 1.0 / 3.0], dtype=np.float32), size=n_reads)
+        if b % 2 == 0:   # every third position carries a second, shorter read inside the first one's group
+            keep = np.repeat(np.arange(n_reads), np.where(np.arange(n_reads) % 3 == 0, 2, 1))
+            first = np.concatenate([[True], keep[1:] != keep[:-1]])
+            starts, lens, counts = starts[keep] + np.where(first, 0, 5), np.where(first, lens[keep], lens[keep] - 10), counts[keep]
+        nr = starts.size
+        for n in range(nr):
+            out["r_start"].append(int(starts[n])); out["r_end"].append(int(starts[n] + lens[n] - 1))
+            out["r_len"].append(int(lens[n])); out["r_count"].append(counts[n]); out["r_nh"].append(int(rng.choice([1, 1, 2])))
+            out["r_strand"].append(0); out["r_flags"].append(0)
+            out["seg_start"].append(int(starts[n])); out["seg_end"].append(int(starts[n] + lens[n] - 1))
+            if b % 2 == 1:   # mates: n <-> n + 3 within blocks of 6
+                m = n + 3 if n % 6 < 3 else n - 3
+                if 0 <= m < nr:
+                    out["pair_idx"].append(m); out["pair_cnt"].append(np.float32(min(counts[n], counts[m])))
+            r_seg_off.append(len(out["seg_start"])); r_pair_off.append(len(out["pair_idx"]))
+        out["b_start"].append(pos0); out["b_end"].append(int(starts[-1] + 100))
+        pos0 = int(starts[-1]) + 100000
+        b_read_off.append(len(out["r_start"])); b_junc_off.append(0)
     res = {k: np.asarray(v, dtype=INPUT_FIELDS[k]) for k, v in out.items()}
     res["b_read_off"] = np.asarray(b_read_off, dtype=np.uint32)
     res["b_junc_off"] = np.asarray(b_junc_off, dtype=np.uint32)

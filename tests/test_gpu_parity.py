@@ -352,3 +352,50 @@ def test_groups_refuses_unsupported_modes():
         batch.free()
     finally:
         e.close()
+
+
+def test_groups_many_groups_leave_shared_memory(engine):
+    """Bundles whose group arrays outgrow the shared-memory slots of the walk kernel (sparse reads over long spans:
+    hundreds of separate groups per strand lane) carry on in global memory."""
+    from tests import a9_util
+    a = synth.make_sparse(n_reads=3000, seed=21, n_bundles=3)
+    cov, off, good, left, right = orc.run(a)
+    want = orc.groups(a, cov, off, good, left, right)
+    assert min(w["g_start"].size for w in want) > 600
+    a9_util.assert_same(_gpu_groups(engine, a), want)
+
+
+def test_groups_c2_base_sample(engine):
+    """The seeded base of the bench workload (6000 loci, ~10^7 alignments): the three deepest bundles and a random
+    sample of 150 others, every field equal to the oracle; the whole base is walked on the GPU."""
+    import bench
+    from stringtie_b200 import shard
+    from tests import a9_util
+    base, _ = bench.build_workload(1, bench.BASE_BUNDLES, 0)
+    nreads = np.diff(base["b_read_off"].astype(np.int64))
+    rng = np.random.default_rng(7)
+    pick = np.unique(np.concatenate([rng.choice(nreads.size, size=150, replace=False), np.argsort(nreads)[-3:]]))
+    batch = engine.upload(base)
+    try:
+        engine.run(batch)
+        engine.build_groups(batch)
+        G = engine.fetch_groups(batch)
+    finally:
+        batch.free()
+    got_all = a9_util.split_engine_groups(G, base)
+    sub = shard.take_bundles(base, pick)
+    cov, off, good, left, right = orc.run(sub, threads=0)
+    want = orc.groups(sub, cov, off, good, left, right)
+    a9_util.assert_same([got_all[int(b)] for b in pick], want)
+    # size-independent properties over ALL bundles: live groups of a lane are disjoint and sorted along the chain
+    go = G["GROUP_OFF"].astype(np.int64)
+    for b in rng.choice(nreads.size, size=400, replace=False):
+        g0, g1 = int(go[b]), int(go[b + 1])
+        st, en, nx = G["G_START"][g0:g1].astype(np.int64), G["G_END"][g0:g1].astype(np.int64), G["G_NEXT"][g0:g1]
+        for s in range(3):
+            g = int(G["STARTGROUP"][3 * b + s])
+            last_end = -1
+            while g != -1:
+                assert G["G_ALIVE"][g0 + g] == 1 and st[g] > last_end and en[g] >= st[g]
+                last_end = int(en[g]) + 50   # neighbours closer than bundledist were merged
+                g = int(nx[g])

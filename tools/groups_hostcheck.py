@@ -37,6 +37,7 @@ def main():
         cases.append((f"synth{seed}", synth.make_batch(n_bundles=40, seed=seed)))
     cases.append(("deep", synth.make_batch(n_bundles=6, reads_per_bundle=40000, seed=4)))
     cases.append(("adversarial", synth.make_adversarial(seed=5)))
+    cases.append(("sparse", synth.make_sparse(n_reads=1500, seed=3, n_bundles=2)))
     for seed in (38, 43):   # the repair appends junction rows and the table is re-sorted
         a = synth.make_adversarial(seed=seed, n_bundles=10, max_reads=250)
         rng = np.random.default_rng(seed)
