@@ -1,7 +1,7 @@
 // group_kernels.cu — sm_100a kernels of SURVEY.md §8 rows a8 + a9 (read loop of build_graphs, groups, colours,
 // bundles / bundlenodes).  The per-bundle algorithm is in groups_device.cuh; this file maps it onto the GPU:
 //   group_caps_kernel    one thread per read: how many readgroup / group / colour slots the read can need at most
-//   groups_walk_kernel   one CTA per bundle, bundles in order of decreasing read count: 64 reads classified per step
+//   groups_walk_kernel   one CTA per bundle, bundles in order of decreasing read count: 128 reads classified per step
 //   groups_colour_kernel one warp per bundle: the lanes compact the bundle's groups and colours into the dense
 //                        arrays, lane 0 runs the colour pass and builds bundles / bundlenodes
 //   groups_rg_kernel     one thread per read: compacts readgroup
@@ -61,8 +61,7 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) group_caps_kernel(DevBatchView
 // those is an L2 round trip on the critical path.  A bundle that outgrows GROUPS_SMEM slots is moved to its global
 // arrays and carries on there.
 #define GROUPS_SMEM 384
-#define GROUPS_WARPS 2                      // warps of a CTA; one CTA walks one bundle (measured on C2: 4 warps 271 ms,
-                                            // 2 warps 210 ms; 4 warps for deep bundles beside 1-2 for the rest: 225-296 ms)
+#define GROUPS_WARPS 4                      // warps of a CTA; one CTA walks one bundle (C2: 201 ms with 4 warps, 210 with 2)
 #define GROUPS_STEP (32 * GROUPS_WARPS)     // reads classified per step
 struct GroupSmem {
   uint32_t start[GROUPS_SMEM], end[GROUPS_SMEM];
@@ -84,7 +83,7 @@ __device__ __forceinline__ void groups_to_global(const Grp& S, const GroupGlobal
 struct WalkCtl {
   int32_t curr[3];
   int32_t ng, color, err;
-  uint32_t ok_mask[GROUPS_WARPS], mint_mask[GROUPS_WARPS];
+  uint32_t ok_mask[GROUPS_WARPS], mint_mask[GROUPS_WARPS], wait_mask[GROUPS_WARPS];
   int32_t npc[GROUPS_STEP];
 };
 
@@ -152,17 +151,19 @@ __global__ void __launch_bounds__(GROUPS_STEP) groups_walk_kernel(DevBatchView v
     int k = 0;
     if (slow_budget == 0) {
       const int hi = n + GROUPS_STEP < inr ? n + GROUPS_STEP : inr, me = n + tid;
-      bool ok = me < hi && classify_read(S, me, n, hi, R[tid]);
+      int st = me < hi ? classify_read(S, me, n, hi, R[tid]) : 0;   // 1 simple, 0 not simple, 2 waits for its mate
+      bool ok = st == 1;
       ctl.npc[tid] = ok ? R[tid].npc : -1;
       __syncthreads();   // (B)
-      // reads that continue into the SAME mate see each other's readgroup pushes: only the first one stays simple
+      // reads that continue into the SAME mate see each other's readgroup pushes: only the first one stays simple, the
+      // others wait for the next step
       if (ok && R[tid].npc >= 0) {
         const int mine = R[tid].npc;
         for (int t = 0; t < tid; t++)
-          if (ctl.npc[t] == mine) { ok = false; break; }
+          if (ctl.npc[t] == mine) { ok = false; st = 2; break; }
       }
-      const unsigned okm = __ballot_sync(FULL, ok), mim = __ballot_sync(FULL, ok && R[tid].newcol);
-      if (lane == 0) { ctl.ok_mask[warp] = okm; ctl.mint_mask[warp] = mim; }
+      const unsigned okm = __ballot_sync(FULL, ok), mim = __ballot_sync(FULL, ok && R[tid].newcol), wam = __ballot_sync(FULL, st == 2);
+      if (lane == 0) { ctl.ok_mask[warp] = okm; ctl.mint_mask[warp] = mim; ctl.wait_mask[warp] = wam; }
       __syncthreads();   // (C)
       // k = length of the leading run of simple reads; fresh colours are numbered in read order
       bool open = true;
@@ -213,9 +214,12 @@ __global__ void __launch_bounds__(GROUPS_STEP) groups_walk_kernel(DevBatchView v
           color += minted; S.ncol += minted;
         }
       }
+      // the read that ended the run: walked the reference's way unless it only has to wait for the commit of its mate
+      const bool waits = k < GROUPS_STEP && (ctl.wait_mask[k >> 5] >> (k & 31) & 1u);
       n += k;
       if (k == 0) { slow_len = slow_len * 2 + 1 < 15 ? slow_len * 2 + 1 : 15; slow_budget = slow_len; }
       else if (k >= 8) slow_len = 0;
+      if (waits) k = GROUPS_STEP;   // no sequential read in this step
     } else slow_budget--;
     if (n < inr && k < GROUPS_STEP) {
       // the read may create groups: leave shared memory before it can overflow

@@ -662,12 +662,14 @@ extern long long stg_fp_bails[64];   // [why]: steps whose run of simple reads w
 extern int stg_fp_last;
 #endif
 #if !defined(__CUDA_ARCH__) && defined(STG_FP_COUNT_BAILS)
-inline bool fp_bail(int why) { stg_fp_last = why; return false; }
+inline int fp_bail(int why) { stg_fp_last = why; return 0; }
 #else
-STG_HD bool fp_bail(int) { return false; }
+STG_HD int fp_bail(int) { return 0; }
 #endif
 
-STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
+// returns 1: simple (R holds what the read does); 0: not simple; 2: simple or not, it has to wait for an earlier read of
+// the same step (its mate), i.e. the step ends in front of it and the next one starts with it
+STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
   R.nv = 0; R.nrg0 = 0; R.nrg1 = 0; R.has_multi = 0; R.sno = -1; R.newcol = 0; R.fresh_gc = -1; R.gp_np = -1; R.npc = -1; R.unpair_np = -1;
   const int nj = S.njunc(n);
   // the repair must leave the read alone: every junction stranded, good, not demoted, not flagged
@@ -690,7 +692,7 @@ STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
   if (npr == 1) {
     const int m = S.pair[S.pairi(n, 0)];
     if (m > -1 && S.r_nh[m]) {
-      if (m >= lo && m < hi) return fp_bail(5);   // the mate is classified in the same step
+      if (m >= lo && m < n) { fp_bail(5); return 2; }   // the earlier mate is committed in this very step
       const int snop = (int)S.strand[m] + 1;
       if (sno != snop) {
         if (sno == 1) sno = snop;
@@ -799,7 +801,7 @@ STG_HD bool classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
     }
     if (sc > 0.000001) R.numfrag = sc;
   }
-  return true;
+  return 1;
 }
 
 // the part of a simple read's effect that does not depend on the other reads of the step; fresh_id = the colour it
@@ -840,7 +842,7 @@ inline void groups_first_half_steps(Grp& S, int32_t* jt_perm, int32_t* jt_inv, d
   while (n < S.nr && !S.err) {
     const int hi = n + W < S.nr ? n + W : S.nr;
     int k = 0;
-    bool ok[STG_STEP_MAX];
+    int ok[STG_STEP_MAX];
 #if defined(STG_FP_COUNT_BAILS)
     int why[STG_STEP_MAX];
     for (int l = 0; n + l < hi; l++) { ok[l] = classify_read(S, n + l, n, hi, R[l]); why[l] = stg_fp_last; }
@@ -848,14 +850,14 @@ inline void groups_first_half_steps(Grp& S, int32_t* jt_perm, int32_t* jt_inv, d
     for (int l = 0; n + l < hi; l++) ok[l] = classify_read(S, n + l, n, hi, R[l]);
 #endif
     // two reads of the step that continue into the SAME mate (a read with several pair links) see each other's
-    // readgroup pushes: the later one is not simple
+    // readgroup pushes: the later one has to wait
     for (int l = 1; n + l < hi; l++)
-      for (int l2 = 0; l2 < l && ok[l]; l2++)
-        if (ok[l2] && R[l].npc >= 0 && R[l2].npc == R[l].npc) ok[l] = false;
-    while (n + k < hi && ok[k]) k++;
+      for (int l2 = 0; l2 < l && ok[l] == 1; l2++)
+        if (ok[l2] == 1 && R[l].npc >= 0 && R[l2].npc == R[l].npc) ok[l] = 2;
+    while (n + k < hi && ok[k] == 1) k++;
 #if defined(STG_FP_COUNT_BAILS)
     stg_fp_bails[0]++;
-    if (n + k < hi) stg_fp_bails[why[k] > 0 && why[k] < 60 ? why[k] : 62]++; else stg_fp_bails[63]++;
+    if (n + k < hi) stg_fp_bails[ok[k] == 2 ? 61 : (why[k] > 0 && why[k] < 60 ? why[k] : 62)]++; else stg_fp_bails[63]++;
 #endif
     int minted = 0;
     for (int l = 0; l < k; l++) { commit_free(S, R[l], n + l, color + minted); minted += R[l].newcol; }
@@ -863,7 +865,7 @@ inline void groups_first_half_steps(Grp& S, int32_t* jt_perm, int32_t* jt_inv, d
     S.ncol += minted; color += minted;
     if (n_simple) *n_simple += k;
     n += k;
-    if (n < S.nr && k < W && !S.err) { color = walk_read(S, n, color, num_fragments, frag_len); n++; }
+    if (n < S.nr && n < hi && ok[k] == 0 && !S.err) { color = walk_read(S, n, color, num_fragments, frag_len); n++; }
   }
   *num_fragments_out = num_fragments; *frag_len_out = frag_len;
   if (S.err) return;
