@@ -83,6 +83,7 @@ __device__ __forceinline__ void groups_to_global(const Grp& S, const GroupGlobal
 struct WalkCtl {
   int32_t curr[3];
   int32_t ng, color, err;
+  int32_t last[3];             // last read of the run that set the cursor of strand lane s (atomicMax of the thread index)
   uint32_t ok_mask[GROUPS_WARPS], mint_mask[GROUPS_WARPS], wait_mask[GROUPS_WARPS];
   int32_t npc[GROUPS_STEP];
 };
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(GROUPS_STEP) groups_walk_kernel(DevBatchView v
       S.err |= (uint32_t)ctl.err;   // raised by the other threads during the last step
       ctl.curr[0] = S.curr.a; ctl.curr[1] = S.curr.b; ctl.curr[2] = S.curr.c;
       ctl.ng = S.ng; ctl.color = color; ctl.err = (int)S.err;
+      ctl.last[0] = ctl.last[1] = ctl.last[2] = -1;
     }
     __syncthreads();   // (A) thread 0's state and everything the previous step wrote is visible
     S.curr.a = ctl.curr[0]; S.curr.b = ctl.curr[1]; S.curr.c = ctl.curr[2];
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(GROUPS_STEP) groups_walk_kernel(DevBatchView v
       if (tid < k) {
         commit_free(S, R[tid], me, color0 + before);
         if (S.err) atomicOr(&ctl.err, (int)S.err);
+        if (R[tid].sno >= 0) atomicMax(&ctl.last[R[tid].sno], tid);
       }
       __syncthreads();   // (D) colours and readgroup entries of the run are in place
       if (warp == 0) {
@@ -206,11 +209,16 @@ __global__ void __launch_bounds__(GROUPS_STEP) groups_walk_kernel(DevBatchView v
         }
         if (cur >= 0) { S.g_cov[cur] = acc_cov; S.g_multi[cur] = acc_multi; }
         if (lane == 0) {
-          for (int j = 0; j < k; j++) {
-            if (R[j].sno >= 0) S.curr.set(R[j].sno, R[j].curr);
-            if (R[j].frag_len != 0) fl += R[j].frag_len;
-            if (R[j].numfrag != 0) nf += R[j].numfrag;
-          }
+          // lane cursors: the last read of the run that moved the cursor of a strand lane decides it
+          const int last0 = ctl.last[0], last1 = ctl.last[1], last2 = ctl.last[2];
+          if (last0 >= 0) S.curr.a = R[last0].curr;
+          if (last1 >= 0) S.curr.b = R[last1].curr;
+          if (last2 >= 0) S.curr.c = R[last2].curr;
+          // the bundle's fragment sums, in read order (a read that adds nothing holds 0)
+          double a = fl, c = nf;
+#pragma unroll 8
+          for (int j = 0; j < k; j++) { a += R[j].frag_len; c += R[j].numfrag; }
+          fl = a; nf = c;
           color += minted; S.ncol += minted;
         }
       }
