@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) group_caps_kernel(DevBatchView
 // when it is deep): every read touches a handful of group fields read-modify-write, and from global memory each of
 // those is an L2 round trip on the critical path.  A bundle that outgrows GROUPS_SMEM slots is moved to its global
 // arrays and carries on there.
-#define GROUPS_SMEM 384
+#define GROUPS_SMEM 320
 #define GROUPS_WARPS 4                      // warps of a CTA; one CTA walks one bundle (C2: 201 ms with 4 warps, 210 with 2)
 #define GROUPS_STEP (32 * GROUPS_WARPS)     // reads classified per step
 struct GroupSmem {
@@ -84,7 +84,7 @@ struct WalkCtl {
   int32_t curr[3];
   int32_t ng, color, err;
   int32_t last[3];             // last read of the run that set the cursor of strand lane s (atomicMax of the thread index)
-  uint32_t ok_mask[GROUPS_WARPS], mint_mask[GROUPS_WARPS], wait_mask[GROUPS_WARPS];
+  uint32_t ok_mask[GROUPS_WARPS], mint_mask[GROUPS_WARPS], wait_mask[GROUPS_WARPS], grow_mask[GROUPS_WARPS];
   int32_t npc[GROUPS_STEP];
 };
 
@@ -92,7 +92,7 @@ struct WalkCtl {
 // state as it stands, commit the leading run of simple ones — the order-free part by every thread for its own read,
 // the float sums by warp 0 with one lane per group residue so that every group's sum is added in read order — walk
 // the first non-simple read the reference's way (thread 0), start over behind it.
-__global__ void __launch_bounds__(GROUPS_STEP) groups_walk_kernel(DevBatchView v, GroupsView g, JuncParams prm) {
+__global__ void __launch_bounds__(GROUPS_STEP, 5) groups_walk_kernel(DevBatchView v, GroupsView g, JuncParams prm) {
   __shared__ GroupSmem M;
   __shared__ FastRec R[GROUPS_STEP];
   __shared__ WalkCtl ctl;
@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(GROUPS_STEP) groups_walk_kernel(DevBatchView v
   int color = 0;                 // thread 0
   double nf = 0, fl = 0;         // thread 0
   int n = 0, slow_len = 0, slow_budget = 0;   // uniform
+  int width = 32;                             // uniform: reads classified in the next step (follows the length of the runs)
   const int inr = (int)nr;
   const unsigned FULL = 0xffffffffu;
   if (tid == 0) ctl.err = 0;
@@ -152,35 +153,45 @@ __global__ void __launch_bounds__(GROUPS_STEP) groups_walk_kernel(DevBatchView v
     const int ng0 = ctl.ng, color0 = ctl.color;
     int k = 0;
     if (slow_budget == 0) {
-      const int hi = n + GROUPS_STEP < inr ? n + GROUPS_STEP : inr, me = n + tid;
-      int st = me < hi ? classify_read(S, me, n, hi, R[tid]) : 0;   // 1 simple, 0 not simple, 2 waits for its mate
-      bool ok = st == 1;
-      ctl.npc[tid] = ok ? R[tid].npc : -1;
+      const int hi = n + width < inr ? n + width : inr, me = n + tid;
+      int st = me < hi ? classify_read(S, me, n, hi, R[tid]) : 0;   // 1 simple, 3 simple + grows a group, 0 not simple, 2 waits
+      ctl.npc[tid] = st == 1 ? R[tid].npc : -1;
       __syncthreads();   // (B)
       // reads that continue into the SAME mate see each other's readgroup pushes: only the first one stays simple, the
       // others wait for the next step
-      if (ok && R[tid].npc >= 0) {
+      if ((st == 1 || st == 3) && R[tid].npc >= 0) {
         const int mine = R[tid].npc;
         for (int t = 0; t < tid; t++)
-          if (ctl.npc[t] == mine) { ok = false; st = 2; break; }
+          if (ctl.npc[t] == mine) { st = 2; break; }
       }
-      const unsigned okm = __ballot_sync(FULL, ok), mim = __ballot_sync(FULL, ok && R[tid].newcol), wam = __ballot_sync(FULL, st == 2);
-      if (lane == 0) { ctl.ok_mask[warp] = okm; ctl.mint_mask[warp] = mim; ctl.wait_mask[warp] = wam; }
+      const bool ok = st == 1;
+      const unsigned okm = __ballot_sync(FULL, ok), mim = __ballot_sync(FULL, (st == 1 || st == 3) && R[tid].newcol);
+      const unsigned wam = __ballot_sync(FULL, st == 2), grm = __ballot_sync(FULL, st == 3);
+      if (lane == 0) { ctl.ok_mask[warp] = okm; ctl.mint_mask[warp] = mim; ctl.wait_mask[warp] = wam; ctl.grow_mask[warp] = grm; }
       __syncthreads();   // (C)
-      // k = length of the leading run of simple reads; fresh colours are numbered in read order
-      bool open = true;
+      // k = length of the leading run of simple reads, plus the read behind it if all it does beyond that is to grow a
+      // group; fresh colours are numbered in read order
+      {
+        bool open = true;
+        for (int w2 = 0; w2 < GROUPS_WARPS; w2++) {
+          const unsigned m = ctl.ok_mask[w2];
+          const int kw = !open ? 0 : (m == FULL ? 32 : __ffs(~m) - 1);
+          k += kw;
+          if (kw < 32) open = false;
+        }
+      }
+      const bool grows = k < GROUPS_STEP && (ctl.grow_mask[k >> 5] >> (k & 31) & 1u);
+      const bool waits0 = k < GROUPS_STEP && (ctl.wait_mask[k >> 5] >> (k & 31) & 1u);
+      if (grows) k++;
       int before = 0;     // colours minted by the run's reads ahead of this thread
       int minted = 0;
       for (int w2 = 0; w2 < GROUPS_WARPS; w2++) {
-        const unsigned m = ctl.ok_mask[w2];
-        const int kw = !open ? 0 : (m == FULL ? 32 : __ffs(~m) - 1);
+        const int kw = k - 32 * w2 >= 32 ? 32 : (k - 32 * w2 > 0 ? k - 32 * w2 : 0);
         const unsigned run = kw == 32 ? FULL : (1u << kw) - 1u;
         const unsigned mi = ctl.mint_mask[w2] & run;
         if (w2 < warp) before += __popc(mi);
         else if (w2 == warp) before += __popc(mi & ((1u << lane) - 1u));
         minted += __popc(mi);
-        k += kw;
-        if (kw < 32) open = false;
       }
       if (tid < k) {
         commit_free(S, R[tid], me, color0 + before);
@@ -223,7 +234,12 @@ __global__ void __launch_bounds__(GROUPS_STEP) groups_walk_kernel(DevBatchView v
         }
       }
       // the read that ended the run: walked the reference's way unless it only has to wait for the commit of its mate
-      const bool waits = k < GROUPS_STEP && (ctl.wait_mask[k >> 5] >> (k & 31) & 1u);
+      // the run reached the end of the window, ended with a read that grows a group, or stopped at a read that waits for
+      // its mate: no sequential read in this step
+      const bool waits = k >= hi - n || grows || waits0;
+      // short runs: classify fewer reads next time (fewer divergent lanes make a cheaper step); full runs: widen again
+      if (k >= width) width = width * 2 < GROUPS_STEP ? width * 2 : GROUPS_STEP;
+      else { const int w2 = 2 * k + 8; width = w2 < 16 ? 16 : (w2 < GROUPS_STEP ? w2 : GROUPS_STEP); }
       n += k;
       if (k == 0) { slow_len = slow_len * 2 + 1 < 15 ? slow_len * 2 + 1 : 15; slow_budget = slow_len; }
       else if (k >= 8) slow_len = 0;

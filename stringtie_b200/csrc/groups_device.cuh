@@ -640,7 +640,7 @@ STG_HD void groups_first_half(Grp& S, int32_t* jt_perm, int32_t* jt_inv, double*
 // classifies 32 consecutive reads at once, commits the leading run of simple ones (order only matters for the float
 // sums, which one lane adds in read order), hands the first non-simple read to walk_read(), and starts over behind it.
 // Anything classify_read() is not sure about is "not simple": the sequential code is the definition of the result.
-#define STG_FP_MAXV 10   // group visits of one read (its exons + the exons of a mate that continues the fragment)
+#define STG_FP_MAXV 8   // group visits of one read (its exons + the exons of a mate that continues the fragment)
 struct FastRec {
   int32_t grp[STG_FP_MAXV];     // visited groups, in order
   float cov[STG_FP_MAXV];       // coverage added to cov_sum
@@ -653,6 +653,7 @@ struct FastRec {
   int32_t gp_np, gp_root, gp_col;   // earlier mate: readgroup[np][0] = gp_root, color of gp_root = gp_col (gp_np = -1: none)
   int32_t npc;                  // mate that continued the fragment (-1: none)
   int32_t unpair_np;            // earlier mate the read is un-paired from (-1: none)
+  int32_t xg; uint32_t xs, xe;  // group the read grows and its new bounds (-1: none); such a read ends the run
   double frag_len, numfrag;     // what the read adds to the bundle's sums
 };
 
@@ -667,10 +668,12 @@ inline int fp_bail(int why) { stg_fp_last = why; return 0; }
 STG_HD int fp_bail(int) { return 0; }
 #endif
 
-// returns 1: simple (R holds what the read does); 0: not simple; 2: simple or not, it has to wait for an earlier read of
-// the same step (its mate), i.e. the step ends in front of it and the next one starts with it
+// returns 1: simple (R holds what the read does); 3: simple but for growing ONE group (R.xg, no merge): it may be
+// committed as the last read of a run, the reads behind it have to be classified against the grown group; 0: not
+// simple; 2: simple or not, it has to wait for an earlier read of the same step (its mate), i.e. the step ends in front
+// of it and the next one starts with it
 STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
-  R.nv = 0; R.nrg0 = 0; R.nrg1 = 0; R.has_multi = 0; R.sno = -1; R.newcol = 0; R.fresh_gc = -1; R.gp_np = -1; R.npc = -1; R.unpair_np = -1;
+  R.nv = 0; R.nrg0 = 0; R.nrg1 = 0; R.has_multi = 0; R.sno = -1; R.newcol = 0; R.fresh_gc = -1; R.gp_np = -1; R.npc = -1; R.unpair_np = -1; R.xg = -1;
   const int nj = S.njunc(n);
   // the repair must leave the read alone: every junction stranded, good, not demoted, not flagged
   for (int i = 0; i < nj; i++) {
@@ -728,21 +731,32 @@ STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
                         (S.slen(cnp, S.nseg(cnp) - 1) >= S.junctionsupport || (S.njunc(cnp) && S.rjstrand(cnp, S.njunc(cnp) - 1))) &&
                         (S.slen(cn, 0) >= S.junctionsupport || (S.njunc(cn) && S.rjstrand(cn, 0)));
     if (!placed) {
+      // a read may GROW one group (no merge, no new group): its later tests see the grown bounds
+      int xg = -1;
+      uint32_t xs = 0, xe = 0;
+      auto GS = [&](int gq) -> uint32_t { return gq == xg ? xs : S.g_start[gq]; };
+      auto GE = [&](int gq) -> uint32_t { return gq == xg ? xe : S.g_end[gq]; };
       int currgroup = S.curr.get(sno);
       if (currgroup == -1) return fp_bail(9);
       int lastgroup = -1;
       const uint32_t rstart = S.r_start[cn];
-      while (currgroup != -1 && rstart > S.g_end[currgroup]) { lastgroup = currgroup; currgroup = S.g_next[currgroup]; }
-      if (currgroup == -1 || S.seg_e[S.segi(cn, 0)] < S.g_start[currgroup]) currgroup = lastgroup;
+      while (currgroup != -1 && rstart > GE(currgroup)) { lastgroup = currgroup; currgroup = S.g_next[currgroup]; }
+      if (currgroup == -1 || S.seg_e[S.segi(cn, 0)] < GS(currgroup)) currgroup = lastgroup;
       if (currgroup == -1) return fp_bail(10);
       int thisgroup = currgroup, ncoord = S.nseg(cn), lastpushed = -1, i = 0;
       bool first = true;
       while (i < ncoord) {
         if (!keep_exon(S, cn, i)) return fp_bail(11);
         const uint32_t ss = S.seg_s[S.segi(cn, i)], se = S.seg_e[S.segi(cn, i)];
-        while (thisgroup != -1 && ss > S.g_end[thisgroup]) thisgroup = S.g_next[thisgroup];
-        if (thisgroup == -1 || se + localdist < S.g_start[thisgroup]) return fp_bail(12);      // a new group
-        if (ss < S.g_start[thisgroup] || se > S.g_end[thisgroup]) return fp_bail(13);           // the group would grow
+        while (thisgroup != -1 && ss > GE(thisgroup)) thisgroup = S.g_next[thisgroup];
+        if (thisgroup == -1 || se + localdist < GS(thisgroup)) return fp_bail(12);             // a new group
+        if (ss < GS(thisgroup) || se > GE(thisgroup)) {                                          // the group grows
+          if (xg != -1 && xg != thisgroup) return fp_bail(13);                                   // ... a second one
+          const int nx = S.g_next[thisgroup];
+          const uint32_t ns2 = ss < GS(thisgroup) ? ss : GS(thisgroup), ne2 = se > GE(thisgroup) ? se : GE(thisgroup);
+          if (nx != -1 && se >= S.g_start[nx]) return fp_bail(13);                               // ... into the next one: a merge
+          xg = thisgroup; xs = ns2; xe = ne2;
+        }
         if (S.g_grid[thisgroup] != thisgroup || S.g_merge[thisgroup] != thisgroup) return fp_bail(14);
         if (!i) {
           const uint32_t base = S.rcap_off[cn], cnt = S.rg_cnt[cn];
@@ -780,7 +794,12 @@ STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
           cn = cnp; cnp = -1;
           ncoord = S.nseg(cn);
           first = true;
-          if (S.r_start[cn] > S.g_end[thisgroup]) return fp_bail(18);                           // the group would grow
+          if (S.r_start[cn] > GE(thisgroup)) {                                                   // the group grows up to the mate
+            if (xg != -1 && xg != thisgroup) return fp_bail(18);
+            const int nx = S.g_next[thisgroup];
+            if (nx != -1 && S.r_start[cn] >= S.g_start[nx]) return fp_bail(18);                  // a merge
+            xs = GS(thisgroup); xe = S.r_start[cn]; xg = thisgroup;
+          }
           lastpushed = -1;
           i = -1;
           R.npc = cn;
@@ -788,6 +807,7 @@ STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
         i++;
       }
       R.sno = sno; R.curr = currgroup;
+      R.xg = xg; R.xs = xs; R.xe = xe;
     }
   }
   // fragment counting
@@ -801,7 +821,7 @@ STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
     }
     if (sc > 0.000001) R.numfrag = sc;
   }
-  return 1;
+  return R.xg >= 0 ? 3 : 1;
 }
 
 // the part of a simple read's effect that does not depend on the other reads of the step; fresh_id = the colour it
@@ -815,6 +835,7 @@ STG_HD void commit_free(Grp& S, const FastRec& R, int n, int fresh_id) {
     else S.err |= STG_GERR_GROUPS;
   }
   if (R.unpair_np >= 0) unpair(S, n, 0, R.unpair_np);
+  if (R.xg >= 0) { S.g_start[R.xg] = R.xs; S.g_end[R.xg] = R.xe; }
   for (int k = 0; k < R.nrg0; k++) rg_add(S, n, R.rgv[k]);
   for (int k = 0; k < R.nrg1; k++) rg_add(S, R.npc, R.rgv[R.nrg0 + k]);
 }
@@ -854,10 +875,15 @@ inline void groups_first_half_steps(Grp& S, int32_t* jt_perm, int32_t* jt_inv, d
     for (int l = 1; n + l < hi; l++)
       for (int l2 = 0; l2 < l && ok[l] == 1; l2++)
         if (ok[l2] == 1 && R[l].npc >= 0 && R[l2].npc == R[l].npc) ok[l] = 2;
+    for (int l = 1; n + l < hi; l++)   // the same for a read that grows a group
+      for (int l2 = 0; l2 < l && ok[l] == 3; l2++)
+        if (ok[l2] == 1 && R[l].npc >= 0 && R[l2].npc == R[l].npc) ok[l] = 2;
     while (n + k < hi && ok[k] == 1) k++;
+    const int stop = n + k < hi ? ok[k] : 1;   // what ended the run
+    if (stop == 3) k++;                         // a read that grows a group is the run's last read
 #if defined(STG_FP_COUNT_BAILS)
     stg_fp_bails[0]++;
-    if (n + k < hi) stg_fp_bails[ok[k] == 2 ? 61 : (why[k] > 0 && why[k] < 60 ? why[k] : 62)]++; else stg_fp_bails[63]++;
+    if (stop == 3) stg_fp_bails[60]++; else if (n + k < hi) stg_fp_bails[ok[k] == 2 ? 61 : (why[k] > 0 && why[k] < 60 ? why[k] : 62)]++; else stg_fp_bails[63]++;
 #endif
     int minted = 0;
     for (int l = 0; l < k; l++) { commit_free(S, R[l], n + l, color + minted); minted += R[l].newcol; }
@@ -865,7 +891,7 @@ inline void groups_first_half_steps(Grp& S, int32_t* jt_perm, int32_t* jt_inv, d
     S.ncol += minted; color += minted;
     if (n_simple) *n_simple += k;
     n += k;
-    if (n < S.nr && n < hi && ok[k] == 0 && !S.err) { color = walk_read(S, n, color, num_fragments, frag_len); n++; }
+    if (n < S.nr && n < hi && stop == 0 && !S.err) { color = walk_read(S, n, color, num_fragments, frag_len); n++; }
   }
   *num_fragments_out = num_fragments; *frag_len_out = frag_len;
   if (S.err) return;
