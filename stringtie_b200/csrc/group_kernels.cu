@@ -60,9 +60,10 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) group_caps_kernel(DevBatchView
 // when it is deep): every read touches a handful of group fields read-modify-write, and from global memory each of
 // those is an L2 round trip on the critical path.  A bundle that outgrows GROUPS_SMEM slots is moved to its global
 // arrays and carries on there.
-#define GROUPS_SMEM 320
+#define GROUPS_SMEM 256
 #define GROUPS_WARPS 4                      // warps of a CTA; one CTA walks one bundle (C2: 201 ms with 4 warps, 210 with 2)
-#define GROUPS_STEP (32 * GROUPS_WARPS)     // reads classified per step
+#define GROUPS_STEP (32 * GROUPS_WARPS)     // threads of a CTA
+#define GROUPS_CLS (GROUPS_STEP - 32)        // of which classify reads (warp 0 adds the float sums of the previous run)
 struct GroupSmem {
   uint32_t start[GROUPS_SMEM], end[GROUPS_SMEM];
   int32_t color[GROUPS_SMEM], next[GROUPS_SMEM], merge[GROUPS_SMEM], grid[GROUPS_SMEM];
@@ -84,17 +85,19 @@ struct WalkCtl {
   int32_t curr[3];
   int32_t ng, color, err;
   int32_t last[3];             // last read of the run that set the cursor of strand lane s (atomicMax of the thread index)
-  uint32_t ok_mask[GROUPS_WARPS], mint_mask[GROUPS_WARPS], wait_mask[GROUPS_WARPS], grow_mask[GROUPS_WARPS];
-  int32_t npc[GROUPS_STEP];
+  uint32_t ok_mask[GROUPS_WARPS], mint_mask[GROUPS_WARPS], wait_mask[GROUPS_WARPS], grow_mask[GROUPS_WARPS];   // [0] unused
+  int32_t npc[GROUPS_CLS];
 };
 
-// The CTA's schedule (groups_device.cuh, "the parallel form of the loop"): classify GROUPS_STEP reads against the
-// state as it stands, commit the leading run of simple ones — the order-free part by every thread for its own read,
-// the float sums by warp 0 with one lane per group residue so that every group's sum is added in read order — walk
-// the first non-simple read the reference's way (thread 0), start over behind it.
+// The CTA's schedule (groups_device.cuh, "the parallel form of the loop"): warps 1.. classify the next GROUPS_CLS reads
+// against the state as it stands and commit the order-free part of the leading run of simple ones, each thread for
+// its own read; MEANWHILE warp 0 adds the float sums of the PREVIOUS run (one lane per group residue, so that every
+// group's sum is added in read order) and the bundle's fragment sums — classification never reads those sums, so
+// the two overlap and only meet at the barrier that ends a step.  A read that is not simple is walked the reference's
+// way by thread 0 once the pending sums are in.
 __global__ void __launch_bounds__(GROUPS_STEP, 5) groups_walk_kernel(DevBatchView v, GroupsView g, JuncParams prm) {
   __shared__ GroupSmem M;
-  __shared__ FastRec R[GROUPS_STEP];
+  __shared__ FastRec Rb[2][GROUPS_CLS];   // records of the step being classified / of the run whose sums are pending
   __shared__ WalkCtl ctl;
   const uint32_t b = g.order[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -132,136 +135,156 @@ __global__ void __launch_bounds__(GROUPS_STEP, 5) groups_walk_kernel(DevBatchVie
   S.prm = prm; S.err = 0;
   if (gcap == 0 || gcap > 0x7fffffffu) { if (!tid) atomicOr(v.err_flag, STG_GERR_GROUPS); return; }
   bool in_smem = true;
-  int color = 0;                 // thread 0
+  int color = 0;                 // uniform (every thread follows the colour counter)
+  int ng_u = 0;                  // uniform copy of thread 0's S.ng (changes only when a read is walked)
   double nf = 0, fl = 0;         // thread 0
   int n = 0, slow_len = 0, slow_budget = 0;   // uniform
   int width = 32;                             // uniform: reads classified in the next step (follows the length of the runs)
+  int buf = 0, pend_k = 0, pend_buf = 0;      // uniform: record buffer of this step; run whose float sums are pending
   const int inr = (int)nr;
   const unsigned FULL = 0xffffffffu;
-  if (tid == 0) ctl.err = 0;
+  const int ct = tid - 32;                    // index among the classifying threads (warp 0: negative)
+  if (tid == 0) { ctl.err = 0; ctl.last[0] = ctl.last[1] = ctl.last[2] = -1; }
   __syncthreads();
-  while (n < inr) {
-    if (tid == 0) {
-      S.err |= (uint32_t)ctl.err;   // raised by the other threads during the last step
-      ctl.curr[0] = S.curr.a; ctl.curr[1] = S.curr.b; ctl.curr[2] = S.curr.c;
-      ctl.ng = S.ng; ctl.color = color; ctl.err = (int)S.err;
-      ctl.last[0] = ctl.last[1] = ctl.last[2] = -1;
-    }
-    __syncthreads();   // (A) thread 0's state and everything the previous step wrote is visible
-    S.curr.a = ctl.curr[0]; S.curr.b = ctl.curr[1]; S.curr.c = ctl.curr[2];
-    if (ctl.err) break;
-    const int ng0 = ctl.ng, color0 = ctl.color;
-    int k = 0;
-    if (slow_budget == 0) {
-      const int hi = n + width < inr ? n + width : inr, me = n + tid;
-      int st = me < hi ? classify_read(S, me, n, hi, R[tid]) : 0;   // 1 simple, 3 simple + grows a group, 0 not simple, 2 waits
-      ctl.npc[tid] = st == 1 ? R[tid].npc : -1;
-      __syncthreads();   // (B)
-      // reads that continue into the SAME mate see each other's readgroup pushes: only the first one stays simple, the
-      // others wait for the next step
-      if ((st == 1 || st == 3) && R[tid].npc >= 0) {
-        const int mine = R[tid].npc;
-        for (int t = 0; t < tid; t++)
-          if (ctl.npc[t] == mine) { st = 2; break; }
+
+  // float sums of a committed run, in read order: lane l owns the groups with slot % 32 == l; the sum of the group being
+  // worked on is kept in registers.  Thread 0 also adds the bundle's fragment sums (a read that adds nothing holds 0).
+  auto pending_sums = [&](const FastRec* R, int k) {
+    int cur = -1;
+    float acc_cov = 0.f, acc_multi = 0.f;
+    for (int j = 0; j < k; j++) {
+      const int nv = R[j].nv, hm = R[j].has_multi;
+      for (int x = 0; x < nv; x++) {
+        const int gr = R[j].grp[x];
+        if ((gr & 31) == lane) {
+          if (gr != cur) {
+            if (cur >= 0) { S.g_cov[cur] = acc_cov; S.g_multi[cur] = acc_multi; }
+            cur = gr; acc_cov = S.g_cov[gr]; acc_multi = S.g_multi[gr];
+          }
+          if (hm >> x & 1) acc_multi += R[j].multi[x];
+          acc_cov += R[j].cov[x];
+        }
       }
-      const bool ok = st == 1;
-      const unsigned okm = __ballot_sync(FULL, ok), mim = __ballot_sync(FULL, (st == 1 || st == 3) && R[tid].newcol);
-      const unsigned wam = __ballot_sync(FULL, st == 2), grm = __ballot_sync(FULL, st == 3);
-      if (lane == 0) { ctl.ok_mask[warp] = okm; ctl.mint_mask[warp] = mim; ctl.wait_mask[warp] = wam; ctl.grow_mask[warp] = grm; }
+    }
+    if (cur >= 0) { S.g_cov[cur] = acc_cov; S.g_multi[cur] = acc_multi; }
+    if (lane == 0) {
+      double a = fl, c = nf;
+#pragma unroll 8
+      for (int j = 0; j < k; j++) { a += R[j].frag_len; c += R[j].numfrag; }
+      fl = a; nf = c;
+    }
+  };
+
+  while (true) {
+    const bool classify = n < inr && slow_budget == 0;
+    FastRec* R = Rb[buf];
+    const int hi = n + width < inr ? n + width : inr, me = n + ct;
+    int st = 0;                                 // 1 simple, 3 simple + grows a group, 0 not simple, 2 waits
+    if (warp == 0) { if (pend_k) pending_sums(Rb[pend_buf], pend_k); }
+    else if (classify) {
+      if (me < hi) st = classify_read(S, me, n, hi, R[ct]);
+      ctl.npc[ct] = st == 1 ? R[ct].npc : -1;
+    }
+    pend_k = 0;
+    __syncthreads();   // (B) the pending sums are in; the records of this step are written
+    if (n >= inr) break;
+    if (tid == 32) ctl.last[0] = ctl.last[1] = ctl.last[2] = -1;   // everybody read them before (B); set again after (C)
+    int k = 0;
+    bool no_walk = false;
+    if (classify) {
+      if (warp != 0) {
+        // reads that continue into the SAME mate see each other's readgroup pushes: only the first one stays simple, the
+        // others wait for the next step
+        if ((st == 1 || st == 3) && R[ct].npc >= 0) {
+          const int mine = R[ct].npc;
+          for (int t = 0; t < ct; t++)
+            if (ctl.npc[t] == mine) { st = 2; break; }
+        }
+        const unsigned okm = __ballot_sync(FULL, st == 1), mim = __ballot_sync(FULL, (st == 1 || st == 3) && R[ct].newcol);
+        const unsigned wam = __ballot_sync(FULL, st == 2), grm = __ballot_sync(FULL, st == 3);
+        if (lane == 0) { ctl.ok_mask[warp] = okm; ctl.mint_mask[warp] = mim; ctl.wait_mask[warp] = wam; ctl.grow_mask[warp] = grm; }
+      }
       __syncthreads();   // (C)
       // k = length of the leading run of simple reads, plus the read behind it if all it does beyond that is to grow a
       // group; fresh colours are numbered in read order
       {
         bool open = true;
-        for (int w2 = 0; w2 < GROUPS_WARPS; w2++) {
+        for (int w2 = 1; w2 < GROUPS_WARPS; w2++) {
           const unsigned m = ctl.ok_mask[w2];
           const int kw = !open ? 0 : (m == FULL ? 32 : __ffs(~m) - 1);
           k += kw;
           if (kw < 32) open = false;
         }
       }
-      const bool grows = k < GROUPS_STEP && (ctl.grow_mask[k >> 5] >> (k & 31) & 1u);
-      const bool waits0 = k < GROUPS_STEP && (ctl.wait_mask[k >> 5] >> (k & 31) & 1u);
+      const bool grows = k < GROUPS_CLS && (ctl.grow_mask[1 + (k >> 5)] >> (k & 31) & 1u);
+      const bool waits0 = k < GROUPS_CLS && (ctl.wait_mask[1 + (k >> 5)] >> (k & 31) & 1u);
       if (grows) k++;
       int before = 0;     // colours minted by the run's reads ahead of this thread
       int minted = 0;
-      for (int w2 = 0; w2 < GROUPS_WARPS; w2++) {
-        const int kw = k - 32 * w2 >= 32 ? 32 : (k - 32 * w2 > 0 ? k - 32 * w2 : 0);
+      for (int w2 = 1; w2 < GROUPS_WARPS; w2++) {
+        const int rem = k - 32 * (w2 - 1);
+        const int kw = rem >= 32 ? 32 : (rem > 0 ? rem : 0);
         const unsigned run = kw == 32 ? FULL : (1u << kw) - 1u;
         const unsigned mi = ctl.mint_mask[w2] & run;
         if (w2 < warp) before += __popc(mi);
         else if (w2 == warp) before += __popc(mi & ((1u << lane) - 1u));
         minted += __popc(mi);
       }
-      if (tid < k) {
-        commit_free(S, R[tid], me, color0 + before);
+      if (warp != 0 && ct < k) {
+        commit_free(S, R[ct], me, color + before);
         if (S.err) atomicOr(&ctl.err, (int)S.err);
-        if (R[tid].sno >= 0) atomicMax(&ctl.last[R[tid].sno], tid);
+        if (R[ct].sno >= 0) atomicMax(&ctl.last[R[ct].sno], ct);
       }
-      __syncthreads();   // (D) colours and readgroup entries of the run are in place
-      if (warp == 0) {
-        // ordered float sums: lane l owns the groups with slot % 32 == l and adds their visits in read order; the sum
-        // of the group being worked on is kept in registers
-        int cur = -1;
-        float acc_cov = 0.f, acc_multi = 0.f;
-        for (int j = 0; j < k; j++) {
-          const int nv = R[j].nv, hm = R[j].has_multi;
-          for (int x = 0; x < nv; x++) {
-            const int gr = R[j].grp[x];
-            if ((gr & 31) == lane) {
-              if (gr != cur) {
-                if (cur >= 0) { S.g_cov[cur] = acc_cov; S.g_multi[cur] = acc_multi; }
-                cur = gr; acc_cov = S.g_cov[gr]; acc_multi = S.g_multi[gr];
-              }
-              if (hm >> x & 1) acc_multi += R[j].multi[x];
-              acc_cov += R[j].cov[x];
-            }
-          }
-        }
-        if (cur >= 0) { S.g_cov[cur] = acc_cov; S.g_multi[cur] = acc_multi; }
-        if (lane == 0) {
-          // lane cursors: the last read of the run that moved the cursor of a strand lane decides it
-          const int last0 = ctl.last[0], last1 = ctl.last[1], last2 = ctl.last[2];
-          if (last0 >= 0) S.curr.a = R[last0].curr;
-          if (last1 >= 0) S.curr.b = R[last1].curr;
-          if (last2 >= 0) S.curr.c = R[last2].curr;
-          // the bundle's fragment sums, in read order (a read that adds nothing holds 0)
-          double a = fl, c = nf;
-#pragma unroll 8
-          for (int j = 0; j < k; j++) { a += R[j].frag_len; c += R[j].numfrag; }
-          fl = a; nf = c;
-          color += minted; S.ncol += minted;
-        }
+      __syncthreads();   // (D) colours, readgroup entries and cursors of the run are in place
+      if (ctl.err) break;
+      // lane cursors: the last read of the run that moved the cursor of a strand lane decides it
+      {
+        const int l0 = ctl.last[0], l1 = ctl.last[1], l2 = ctl.last[2];
+        if (l0 >= 0) S.curr.a = R[l0].curr;
+        if (l1 >= 0) S.curr.b = R[l1].curr;
+        if (l2 >= 0) S.curr.c = R[l2].curr;
       }
-      // the read that ended the run: walked the reference's way unless it only has to wait for the commit of its mate
+      color += minted;
+      if (tid == 0) S.ncol += minted;
+      pend_k = k; pend_buf = buf; buf ^= 1;
       // the run reached the end of the window, ended with a read that grows a group, or stopped at a read that waits for
       // its mate: no sequential read in this step
-      const bool waits = k >= hi - n || grows || waits0;
+      no_walk = k >= hi - n || grows || waits0;
       // short runs: classify fewer reads next time (fewer divergent lanes make a cheaper step); full runs: widen again
-      if (k >= width) width = width * 2 < GROUPS_STEP ? width * 2 : GROUPS_STEP;
-      else { const int w2 = 2 * k + 8; width = w2 < 16 ? 16 : (w2 < GROUPS_STEP ? w2 : GROUPS_STEP); }
+      if (k >= width) width = width * 2 < GROUPS_CLS ? width * 2 : GROUPS_CLS;
+      else { const int w2 = 2 * k + 8; width = w2 < 16 ? 16 : (w2 < GROUPS_CLS ? w2 : GROUPS_CLS); }
       n += k;
       if (k == 0) { slow_len = slow_len * 2 + 1 < 15 ? slow_len * 2 + 1 : 15; slow_budget = slow_len; }
       else if (k >= 8) slow_len = 0;
-      if (waits) k = GROUPS_STEP;   // no sequential read in this step
     } else slow_budget--;
-    if (n < inr && k < GROUPS_STEP) {
-      // the read may create groups: leave shared memory before it can overflow
-      if (in_smem && ng0 + (int)(S.rcap_off[n + 1] - S.rcap_off[n]) > GROUPS_SMEM) {
-        __syncthreads();
-        groups_to_global(S, GG, ng0, tid, GROUPS_STEP);
+    if (n < inr && !no_walk) {
+      // a read for thread 0 to walk: it works on the float sums (they have to be in) and may create groups (leave
+      // shared memory before it can overflow)
+      if (warp == 0 && pend_k) pending_sums(Rb[pend_buf], pend_k);
+      pend_k = 0;
+      __syncthreads();   // (E1) sums in; everybody has read ctl.last
+      if (in_smem && ng_u + (int)(S.rcap_off[n + 1] - S.rcap_off[n]) > GROUPS_SMEM) {
+        groups_to_global(S, GG, ng_u, tid, GROUPS_STEP);
         S.g_start = GG.start; S.g_end = GG.end; S.g_color = GG.color; S.g_next = GG.next; S.g_merge = GG.merge; S.g_grid = GG.grid;
         S.g_cov = GG.cov; S.g_multi = GG.multi; S.g_alive = GG.alive; S.gcap = GG.cap;
         in_smem = false;
+        __syncthreads();
       }
-      __syncthreads();   // (E) the float sums of warp 0 (and a move out of shared memory) are done
       if (tid == 0) {
-        if (ctl.err) S.err |= (uint32_t)ctl.err;
+        S.err |= (uint32_t)ctl.err;
         if (!S.err) color = walk_read(S, n, color, nf, fl);
+        ctl.curr[0] = S.curr.a; ctl.curr[1] = S.curr.b; ctl.curr[2] = S.curr.c;
+        ctl.ng = S.ng; ctl.color = color; ctl.err = (int)S.err;
       }
+      __syncthreads();   // (E2)
+      S.curr.a = ctl.curr[0]; S.curr.b = ctl.curr[1]; S.curr.c = ctl.curr[2];
+      ng_u = ctl.ng; color = ctl.color;
+      if (ctl.err) break;
       n++;
     }
   }
+  __syncthreads();
+  if (warp == 0 && pend_k) pending_sums(Rb[pend_buf], pend_k);
   __syncthreads();
   if (tid == 0) {
     if (ctl.err) S.err |= (uint32_t)ctl.err;

@@ -640,7 +640,7 @@ STG_HD void groups_first_half(Grp& S, int32_t* jt_perm, int32_t* jt_inv, double*
 // classifies 32 consecutive reads at once, commits the leading run of simple ones (order only matters for the float
 // sums, which one lane adds in read order), hands the first non-simple read to walk_read(), and starts over behind it.
 // Anything classify_read() is not sure about is "not simple": the sequential code is the definition of the result.
-#define STG_FP_MAXV 8   // group visits of one read (its exons + the exons of a mate that continues the fragment)
+#define STG_FP_MAXV 6   // group visits of one read (its exons + the exons of a mate that continues the fragment)
 struct FastRec {
   int32_t grp[STG_FP_MAXV];     // visited groups, in order
   float cov[STG_FP_MAXV];       // coverage added to cov_sum
