@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) group_caps_kernel(DevBatchView
 // those is an L2 round trip on the critical path.  A bundle that outgrows GROUPS_SMEM slots is moved to its global
 // arrays and carries on there.
 #define GROUPS_SMEM 256
-#define GROUPS_WARPS 4                      // warps of a CTA; one CTA walks one bundle (C2: 201 ms with 4 warps, 210 with 2)
+#define GROUPS_WARPS 3                      // warps of a CTA; one CTA walks one bundle (C2: 201 ms with 4 warps, 210 with 2)
 #define GROUPS_STEP (32 * GROUPS_WARPS)     // threads of a CTA
 #define GROUPS_CLS (GROUPS_STEP - 32)        // of which classify reads (warp 0 adds the float sums of the previous run)
 struct GroupSmem {
