@@ -672,7 +672,7 @@ STG_HD int fp_bail(int) { return 0; }
 // committed as the last read of a run, the reads behind it have to be classified against the grown group; 0: not
 // simple; 2: simple or not, it has to wait for an earlier read of the same step (its mate), i.e. the step ends in front
 // of it and the next one starts with it
-STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& R) {
+STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& __restrict__ R) {
   R.nv = 0; R.nrg0 = 0; R.nrg1 = 0; R.has_multi = 0; R.sno = -1; R.newcol = 0; R.fresh_gc = -1; R.gp_np = -1; R.npc = -1; R.unpair_np = -1; R.xg = -1;
   const int nj = S.njunc(n);
   // the repair must leave the read alone: every junction stranded, good, not demoted, not flagged

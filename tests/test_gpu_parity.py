@@ -399,3 +399,36 @@ def test_groups_c2_base_sample(engine):
                 assert G["G_ALIVE"][g0 + g] == 1 and st[g] > last_end and en[g] >= st[g]
                 last_end = int(en[g]) + 50   # neighbours closer than bundledist were merged
                 g = int(nx[g])
+
+
+def test_groups_call_order_is_checked(engine):
+    from stringtie_b200.engine import StgError
+    a = synth.make_batch(n_bundles=4, reads_per_bundle=200, seed=2)
+    batch = engine.upload(a)
+    try:
+        with pytest.raises(StgError):          # the junction pass has not run yet
+            engine.build_groups(batch)
+        with pytest.raises(StgError):          # nothing to fetch either
+            engine.fetch_groups_array(batch, "G_START")
+        engine.run(batch)
+        engine.build_groups(batch)
+        with pytest.raises(StgError):          # once per batch
+            engine.build_groups(batch)
+        assert engine.fetch_groups_array(batch, "GROUP_OFF").size == 5
+    finally:
+        batch.free()
+
+
+def test_groups_empty_bundles_and_reads_without_junctions(engine):
+    """Bundles without reads, bundles without junction rows, a batch that is all of that."""
+    from tests import a9_util
+    from stringtie_b200 import shard
+    a = synth.make_adversarial(seed=4, n_bundles=10)         # bundle 3 has no reads
+    cov, off, good, left, right = orc.run(a)
+    a9_util.assert_same(_gpu_groups(engine, a), orc.groups(a, cov, off, good, left, right))
+    only_empty = shard.take_bundles(a, np.array([3]))
+    got = _gpu_groups(engine, only_empty)
+    assert got[0]["g_start"].size == 0 and got[0]["rg"].size == 0 and list(got[0]["startgroup"]) == [-1, -1, -1]
+    b = synth.make_sparse(n_reads=50, seed=1, n_bundles=2)  # no junction rows at all
+    cov, off, good, left, right = orc.run(b)
+    a9_util.assert_same(_gpu_groups(engine, b), orc.groups(b, cov, off, good, left, right))
