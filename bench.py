@@ -352,6 +352,9 @@ def main():
             "config": config, "bundles_per_sec": world * n_bundles / (ms_step * 1e-3), "reads_per_gpu": n_reads,
             "bundles_per_gpu": n_bundles, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "kernel_ms": kmean, "rows_a8_a9": groups_stage}
+    if groups_stage and groups_stage.get("ms"):
+        # everything built so far in one figure: rows a1-a9 resident (the headline `value` stays the stages of round 1)
+        groups_stage["pipeline_a1_to_a9_reads_per_s"] = world * n_reads / ((ms_step + groups_stage["ms"]) * 1e-3)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
