@@ -84,6 +84,13 @@ int orc_trims_capacity(uint32_t start, uint32_t end);
 int orc_find_all_trims(const float* cov, int64_t blen, int64_t refstart, int sno, uint32_t start, uint32_t end,
                        uint32_t* o_pos, float* o_abund, uint8_t* o_start);
 
+/* SURVEY.md §8 row a19 (de novo part) — single-exon predictions of the neutral bundles (rlink.cpp:15500-15634), for one
+ * bundle: G = its groups / bundles (orc_groups_bundle).  Writes up to `cap` predictions (genomic start / end, mean
+ * coverage, length, geneno as stored: the reference's counter minus one) and returns how many there are. */
+int orc_neutral_preds(const float* cov, int64_t blen, int64_t refstart, const orc_groups_out* G, int mintranscriptlen,
+                      float mcov, int cap, uint32_t* o_start, uint32_t* o_end, double* o_cov, int32_t* o_tlen,
+                      int32_t* o_geneno);
+
 /* work counters for the roofline: S = mate-merged coverage intervals emitted, J = junction-support updates */
 void orc_batch_stats(const stg_packed_batch* B, int64_t* L, int64_t* S, int64_t* J);
 

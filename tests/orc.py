@@ -234,3 +234,50 @@ def find_trims(arrays: Dict[str, np.ndarray], cov: np.ndarray, cov_off: np.ndarr
         off.append(off[-1] + n)
     cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
     return np.array(off, dtype=np.uint32), cat(pos, np.uint32), cat(ab, np.float32), cat(st, np.uint8)
+
+
+def neutral_preds(arrays: Dict[str, np.ndarray], cov: np.ndarray, cov_off: np.ndarray, good: np.ndarray, left: np.ndarray,
+                  right: np.ndarray, bundles=None, junctionsupport: int = 10, junctionthr: int = 1, bundledist: int = 50,
+                  mintranscriptlen: int = 200, mcov: float = 1.0):
+    """SURVEY §8 row a19 (de novo part) per bundle (oracle/stg_oracle_neutral.c): list of dicts start, end, cov, tlen,
+    geneno — the single-exon predictions of the neutral bundles, in the reference's order."""
+    L = lib()
+    groups(arrays, cov, cov_off, good, left, right, bundles=[])   # sets the argtypes of orc_groups_bundle
+    if not hasattr(L, "_np_ready"):
+        u32p, i32p = C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+        L.orc_neutral_preds.argtypes = [c_f32p, C.c_int64, C.c_int64, C.POINTER(OrcGroupsOut), C.c_int, C.c_float, C.c_int, u32p,
+                                        u32p, c_f64p, i32p, i32p]
+        L.orc_neutral_preds.restype = C.c_int
+        L._np_ready = True
+    pb, keep = make_packed(arrays)
+    P = OrcParams(junctionsupport, junctionthr, 0)
+    joff = arrays["b_junc_off"].astype(np.int64)
+    good = np.ascontiguousarray(good, dtype=np.float64)
+    left = np.ascontiguousarray(left, dtype=np.float64)
+    right = np.ascontiguousarray(right, dtype=np.float64)
+    lens, _ = cov_layout(arrays)
+
+    def at(a, o, t):
+        return C.cast(a.ctypes.data + o * a.itemsize, t)
+
+    res = []
+    for b in (range(int(pb.n_bundles)) if bundles is None else bundles):
+        o = OrcGroupsOut()
+        j0 = int(joff[b])
+        covp = at(cov, int(cov_off[b]), c_f32p)
+        L.orc_groups_bundle(C.byref(pb), C.byref(P), b, covp, at(good, j0, c_f64p), at(left, j0, c_f64p),
+                            at(right, j0, c_f64p), bundledist, C.byref(o))
+        cap = 16
+        while True:
+            st, en = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+            cv, tl, gn = np.zeros(cap, np.float64), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+            n = L.orc_neutral_preds(covp, int(lens[b]), int(arrays["b_start"][b]), C.byref(o), mintranscriptlen, mcov, cap,
+                                    st.ctypes.data_as(C.POINTER(C.c_uint32)), en.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                    cv.ctypes.data_as(c_f64p), tl.ctypes.data_as(C.POINTER(C.c_int32)),
+                                    gn.ctypes.data_as(C.POINTER(C.c_int32)))
+            if n <= cap:
+                break
+            cap = n
+        L.orc_groups_free(C.byref(o))
+        res.append({"start": st[:n].copy(), "end": en[:n].copy(), "cov": cv[:n].copy(), "tlen": tl[:n].copy(), "geneno": gn[:n].copy()})
+    return res

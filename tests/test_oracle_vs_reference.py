@@ -85,26 +85,56 @@ def test_oracle_find_all_trims_matches_golden(golden):
     _check_trims(input_view(golden), golden)
 
 
+def _check_a19(arrays, ref):
+    """Row a19 (de novo part): the single-exon predictions of the neutral bundles against the prediction list dumped
+    inside the reference's build_graphs right after that section (hook before rlink.cpp:15637)."""
+    cov, off, good, left, right = orc.run(arrays)
+    got = orc.neutral_preds(arrays, cov, off, good, left, right)
+    po = ref["a19_pred_off"].astype(np.int64)
+    assert po.size == len(got) + 1
+    for b, g in enumerate(got):
+        w0, w1 = int(po[b]), int(po[b + 1])
+        assert g["start"].size == w1 - w0, f"bundle {b}: {g['start'].size} predictions, reference {w1 - w0}"
+        assert np.array_equal(g["start"], ref["a19_start"][w0:w1]) and np.array_equal(g["end"], ref["a19_end"][w0:w1])
+        assert np.array_equal(g["cov"], ref["a19_cov"][w0:w1]), f"bundle {b}: coverage differs"   # f64, exactly
+        assert np.array_equal(g["tlen"], ref["a19_tlen"][w0:w1]) and np.array_equal(g["geneno"], ref["a19_geneno"][w0:w1])
+        assert np.array_equal(g["cov"].astype(np.float32), ref["a19_exoncov"][w0:w1])
+    assert np.all(ref["a19_strand"] == ord("."))
+
+
+def test_oracle_neutral_predictions_match_golden(golden):
+    from stringtie_b200.stgb import input_view
+    _check_a19(input_view(golden), golden)
+
+
+def test_goldens_hold_neutral_predictions():
+    from tests.conftest import load_golden, GOLDEN
+    assert sum(load_golden(n)["a19_start"].size for n in GOLDEN) >= 15
+
+
 def test_golden_has_inexact_weights(golden):
     # the fixtures must exercise order-dependent float accumulation (NH=3,5,6 -> 1/3, 1/5, 1/6)
     assert np.isin(golden["r_nh"], [3, 5, 6]).any()
 
 
 @pytest.mark.skipif(not os.path.exists(REF_HOT), reason="reference harness not built (oracle/_ref is built from /root/reference)")
-@pytest.mark.parametrize("case", ["synth", "adv1", "adv2"])
+@pytest.mark.parametrize("case", ["synth", "wide", "adv1", "adv2"])
 def test_oracle_matches_live_reference(tmp_path, case):
     if case == "synth":
         a = synth.make_batch(n_bundles=40, reads_per_bundle=800, seed=3)
+    elif case == "wide":   # many loci: dozens of neutral bundles and single-exon predictions
+        a = synth.make_batch(n_bundles=300, reads_per_bundle=500, seed=8)
     else:
         a = synth.make_adversarial(seed=int(case[-1]) + 10, n_bundles=14)
     src, dst = str(tmp_path / "in.stgb"), str(tmp_path / "out.stgb")
     write_stgb(src, a)
-    subprocess.check_call([REF_HOT, src, "--dump", dst, "--a9b"], stdout=subprocess.DEVNULL)
+    subprocess.check_call([REF_HOT, src, "--dump", dst, "--a19"], stdout=subprocess.DEVNULL)
     ref = read_stgb(dst)
     _check(a, ref)
     _check_a7(a, ref)
     _check_a9(a, ref)
     _check_trims(a, ref)
+    _check_a19(a, ref)
 
 
 @pytest.mark.skipif(not os.path.exists(REF_HOT), reason="reference harness not built (oracle/_ref is built from /root/reference)")
