@@ -21,6 +21,7 @@
  *   a8  per-read junction repair, un-pairing     -> stg_build_groups(), kernel groups_walk
  *   a9  groups, colours, bundles / bundlenodes   -> stg_build_groups(), kernels groups_walk / groups_colour
  *   a10 (part) find_all_trims                    -> stg_find_trims(), kernel find_trims
+ *   a19 (part) neutral single-exon predictions   -> stg_neutral_predictions(), kernels neutral_* + find_trims
  */
 #ifndef STGPU_H_
 #define STGPU_H_
@@ -231,6 +232,8 @@ enum stg_groups_array {
   STG_GA_BN_START, STG_GA_BN_END, STG_GA_BN_COV, STG_GA_BN_NEXT, STG_GA_N_BUN, STG_GA_N_BN, STG_GA_RG,
   STG_GA_J_START, STG_GA_J_END, STG_GA_J_STRAND, STG_GA_J_NREADS, STG_GA_J_NREADS_GOOD, STG_GA_J_LEFT, STG_GA_J_RIGHT,
   STG_GA_J_NM, STG_GA_J_MM,
+  /* after stg_neutral_predictions: */
+  STG_GA_NP_OFF, STG_GA_NP_START, STG_GA_NP_END, STG_GA_NP_COV, STG_GA_NP_TLEN, STG_GA_NP_GENENO,
   STG_GA_COUNT
 };
 int stg_build_groups(stg_ctx* ctx, stg_dbatch* batch);
@@ -238,6 +241,15 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* batch);
 int stg_groups_array_info(const stg_dbatch* batch, int which, int64_t* count, int32_t* elem_bytes);
 /* copies elements [first, first+count) of array `which` to the host buffer `out` */
 int stg_fetch_groups_array(stg_ctx* ctx, const stg_dbatch* batch, int which, int64_t first, int64_t count, void* out);
+
+/* ---- row a19 (de novo part): single-exon predictions of the neutral bundles ---------------------------------------
+ * build_graphs, rlink.cpp:15500-15634, without guides / rawreads / long reads: a neutral bundle (strand lane 1) whose
+ * coverage is not mostly multi-mapped (multi / cov <= mcov * 0.9) is cut, bundlenode by bundlenode, at the trim points
+ * of find_all_trims; every piece longer than mintranscriptlen becomes a CPrediction (strand '.', one exon) with the mean
+ * coverage of get_cov(1, ...).  Needs stg_build_groups.  Results through stg_fetch_groups_array: NP_OFF u32[n_bundles+1]
+ * (bundle b owns predictions [NP_OFF[b], NP_OFF[b+1]), in the reference's order), NP_START / NP_END u32 (GSeg), NP_COV
+ * f64 (CPrediction::cov; exoncov[0] is its float), NP_TLEN i32, NP_GENENO i32 (as stored: the bundle's gene counter). */
+int stg_neutral_predictions(stg_ctx* ctx, stg_dbatch* batch);
 
 /* find_all_trims (rlink.cpp:2118-2419, part of row a10; one of the bpcov range-query consumers): for n regions
  * (bundle[i], sno[i] in {0, 2} as at the call sites rlink.cpp:2813 / 15559, genomic start[i]..end[i]) of a batch that

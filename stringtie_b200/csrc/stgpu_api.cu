@@ -116,6 +116,8 @@ struct stg_dbatch {
   // rows a8 + a9 (stg_build_groups)
   GroupsView gv;
   bool groups_built = false;
+  NeutralView nv;                  // row a19 (stg_neutral_predictions)
+  bool neutral_done = false;
   std::vector<uint32_t> h_nreads;  // [n_bundles]
 };
 
@@ -838,6 +840,75 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
   return STG_OK;   // `release` parks the scratch in the pool; everything that reuses it runs on the same stream
 }
 
+// ---- row a19, de novo part ------------------------------------------------------------------------------------
+int stg_neutral_predictions(stg_ctx* ctx, stg_dbatch* d) {
+  if (!ctx || !d) return fail(ctx, STG_EINVAL, "stg_neutral_predictions: null argument");
+  if (!d->groups_built) return fail(ctx, STG_EINVAL, "stg_neutral_predictions: groups of this batch are not built");
+  if (d->neutral_done) return fail(ctx, STG_EINVAL, "stg_neutral_predictions: already done for this batch");
+  const stg_params& pr = ctx->params;
+  if (pr.guided || pr.rawreads || pr.longreads || pr.havePtFeatures)
+    return fail(ctx, STG_EUNSUPPORTED, "stg_neutral_predictions: only the short-read de novo path is implemented");
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevBatchView& v = d->v;
+  GroupsView& g = d->gv;
+  NeutralView& n = d->nv;
+  memset(&n, 0, sizeof(n));
+  n.mcov = pr.mcov; n.mintranscriptlen = pr.mintranscriptlen;
+  const int64_t nb = v.n_bundles;
+  int rc = STG_OK;
+  stg_dbatch tmp;
+  struct Release { stg_ctx* c; stg_dbatch* t; ~Release() { free_batch_allocs(c, t); } } release{ctx, &tmp};
+#define KEEP(ptr, count) do { if ((rc = dev_alloc(ctx, d, &(ptr), (int64_t)(count)))) return rc; } while (0)
+#define TEMP(ptr, count) do { if ((rc = dev_alloc(ctx, &tmp, &(ptr), (int64_t)(count)))) return rc; } while (0)
+  unsigned long long* scan_state = nullptr; uint32_t* ticket = nullptr;
+  TEMP(ticket, 1);
+  TEMP(n.reg_off, nb + 1 + 16);
+  TEMP(scan_state, nb / 4096 + 4);
+  { Scope s(ctx, "neutral_regions", 4);
+    CK(ctx, launch_neutral_count(v, g, n.reg_off, st));
+    CK(ctx, launch_scan_exclusive_add(n.reg_off, nb + 1, scan_state, ticket, st));
+    uint32_t nreg = 0;
+    CK(ctx, cudaMemcpyAsync(&nreg, n.reg_off + nb, 4, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    n.n_regions = nreg;
+    TEMP(n.reg_cnt, nb); TEMP(n.reg_bundle, nreg); TEMP(n.reg_sno, nreg); TEMP(n.reg_start, nreg); TEMP(n.reg_end, nreg);
+    TEMP(n.reg_first, nreg); TEMP(n.cap_off, (int64_t)nreg + 1 + 16); TEMP(n.trim_cnt, nreg);
+    CK(ctx, cudaMemsetAsync(n.cap_off, 0, sizeof(uint32_t) * ((size_t)nreg + 1), st));
+    CK(ctx, launch_neutral_regions(v, g, n, st));
+    unsigned long long* scan_state2 = nullptr;
+    TEMP(scan_state2, (int64_t)nreg / 4096 + 4);
+    CK(ctx, launch_scan_exclusive_add(n.cap_off, (int64_t)nreg + 1, scan_state2, ticket, st)); }
+  uint32_t tcap = 0;
+  CK(ctx, cudaMemcpyAsync(&tcap, n.cap_off + n.n_regions, 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  TEMP(n.trim_pos, (int64_t)tcap + 1); TEMP(n.trim_ab, (int64_t)tcap + 1); TEMP(n.trim_st, (int64_t)tcap + 1);
+  CK(ctx, cudaMemsetAsync(n.trim_cnt, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(n.n_regions, 1), st));
+  CK(ctx, cudaMemsetAsync(n.trim_pos, 0, sizeof(uint32_t) * ((size_t)tcap + 1), st));
+  CK(ctx, cudaMemsetAsync(n.trim_ab, 0, sizeof(float) * ((size_t)tcap + 1), st));
+  CK(ctx, cudaMemsetAsync(n.trim_st, 0, (size_t)tcap + 1, st));
+  { Scope s(ctx, "find_trims", 1);
+    CK(ctx, launch_find_trims(v, n.n_regions, n.reg_bundle, n.reg_sno, n.reg_start, n.reg_end, n.cap_off, n.trim_cnt, n.trim_pos,
+                              n.trim_ab, n.trim_st, st)); }
+  const int64_t pcap = (int64_t)tcap + n.n_regions + 1;
+  TEMP(n.p_start, pcap); TEMP(n.p_end, pcap); TEMP(n.p_cov, pcap); TEMP(n.p_tlen, pcap); TEMP(n.p_geneno, pcap);
+  KEEP(n.pred_off, nb + 1 + 16);
+  CK(ctx, cudaMemsetAsync(n.pred_off, 0, sizeof(uint32_t) * (nb + 1), st));
+  { Scope s(ctx, "neutral_preds", 3);
+    CK(ctx, launch_neutral_preds(v, g, n, st));
+    CK(ctx, launch_scan_exclusive_add(n.pred_off, nb + 1, scan_state, ticket, st));
+    uint32_t np = 0;
+    CK(ctx, cudaMemcpyAsync(&np, n.pred_off + nb, 4, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    n.n_preds = np;
+    KEEP(n.o_start, np); KEEP(n.o_end, np); KEEP(n.o_cov, np); KEEP(n.o_tlen, np); KEEP(n.o_geneno, np);
+    CK(ctx, launch_neutral_compact(v, n, st)); }
+#undef KEEP
+#undef TEMP
+  d->neutral_done = true;
+  return STG_OK;
+}
+
 namespace {
 struct GArr { const void* p; int64_t n; int32_t sz; };
 GArr groups_array(const stg_dbatch* d, int which) {
@@ -893,6 +964,17 @@ GArr groups_array(const stg_dbatch* d, int which) {
     case STG_GA_J_RIGHT: return {g.oj_right, NJ, 8};
     case STG_GA_J_NM: return {g.oj_nm, NJ, 8};
     case STG_GA_J_MM: return {g.oj_mm, NJ, 8};
+  }
+  if (d->neutral_done) {
+    const NeutralView& n = d->nv;
+    switch (which) {
+      case STG_GA_NP_OFF: return {n.pred_off, nb + 1, 4};
+      case STG_GA_NP_START: return {n.o_start, n.n_preds, 4};
+      case STG_GA_NP_END: return {n.o_end, n.n_preds, 4};
+      case STG_GA_NP_COV: return {n.o_cov, n.n_preds, 8};
+      case STG_GA_NP_TLEN: return {n.o_tlen, n.n_preds, 4};
+      case STG_GA_NP_GENENO: return {n.o_geneno, n.n_preds, 4};
+    }
   }
   return {nullptr, -1, 0};
 }

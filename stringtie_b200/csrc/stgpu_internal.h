@@ -134,6 +134,20 @@ struct GroupsView {
   uint32_t *oj_start, *oj_end; int8_t* oj_strand; double *oj_nreads, *oj_nreads_good, *oj_left, *oj_right, *oj_nm, *oj_mm;
 };
 
+// Row a19, de novo part (neutral_kernels.cu): single-exon predictions of the neutral bundles
+struct NeutralView {
+  float mcov; int32_t mintranscriptlen;
+  int64_t n_regions, n_preds;
+  uint32_t* reg_off;           // [n_bundles+1] first region slot of bundle b (bound: its neutral bundlenodes)
+  uint32_t* reg_cnt;           // [n_bundles]   regions in use
+  int32_t* reg_bundle; int8_t* reg_sno; uint32_t *reg_start, *reg_end; uint8_t* reg_first;   // [n_regions]
+  uint32_t* cap_off;           // [n_regions+1] trim point capacity, then exclusive prefix
+  uint32_t *trim_cnt, *trim_pos; float* trim_ab; uint8_t* trim_st;    // find_trims results
+  uint32_t *p_start, *p_end; double* p_cov; int32_t *p_tlen, *p_geneno;   // [cap_off[n_regions] + n_regions] uncompacted
+  uint32_t* pred_off;          // [n_bundles+1] counts, then exclusive prefix
+  uint32_t *o_start, *o_end; double* o_cov; int32_t *o_tlen, *o_geneno;   // [n_preds]
+};
+
 struct JuncParams {
   uint32_t junctionsupport, sserror;
   int32_t junctionthr;
@@ -170,5 +184,9 @@ cudaError_t launch_find_trims(const DevBatchView& v, int64_t n, const int32_t* b
 cudaError_t launch_group_caps(const DevBatchView& v, uint32_t* rcap, unsigned long long* total, int32_t* rj, cudaStream_t st);
 cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, cudaStream_t st);
 cudaError_t launch_groups_finish(const DevBatchView& v, const GroupsView& g, cudaStream_t st);
+cudaError_t launch_neutral_count(const DevBatchView& v, const GroupsView& g, uint32_t* reg_off, cudaStream_t st);
+cudaError_t launch_neutral_regions(const DevBatchView& v, const GroupsView& g, const NeutralView& nv, cudaStream_t st);
+cudaError_t launch_neutral_preds(const DevBatchView& v, const GroupsView& g, const NeutralView& nv, cudaStream_t st);
+cudaError_t launch_neutral_compact(const DevBatchView& v, const NeutralView& nv, cudaStream_t st);
 int64_t scan_partials_needed(int64_t n);
 int cov_tile_smem_bytes();

@@ -23,7 +23,7 @@ EXPORTS = [
     "stg_builder_add", "stg_builder_packed", "stg_builder_reset", "stg_builder_destroy", "stg_upload", "stg_run",
     "stg_sync", "stg_free_batch", "stg_trim", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
     "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_trims_capacity", "stg_find_trims", "stg_infer_transcripts",
-    "stg_build_groups", "stg_groups_array_info", "stg_fetch_groups_array",
+    "stg_build_groups", "stg_groups_array_info", "stg_fetch_groups_array", "stg_neutral_predictions",
     "stg_shard_assign", "stg_set_profiling", "stg_kernel_count", "stg_kernel_time", "stg_launch_counter", "stg_batch_stats", "stg_stream",
 ]
 
@@ -35,13 +35,15 @@ GROUPS_ARRAYS = [
     "G_NEG_PROP", "EQCOL", "EQCOL2", "EQNEG", "EQPOS", "G2B", "BUN_LEN", "BUN_START", "BUN_LAST", "BUN_COV", "BUN_MULTI",
     "BN_START", "BN_END", "BN_COV", "BN_NEXT", "N_BUN", "N_BN", "RG", "J_START", "J_END", "J_STRAND", "J_NREADS",
     "J_NREADS_GOOD", "J_LEFT", "J_RIGHT", "J_NM", "J_MM",
+    "NP_OFF", "NP_START", "NP_END", "NP_COV", "NP_TLEN", "NP_GENENO",
 ]
+NEUTRAL_ARRAYS = GROUPS_ARRAYS[-6:]
 GROUPS_DTYPES = {k: np.int32 for k in GROUPS_ARRAYS}
-GROUPS_DTYPES.update({k: np.uint32 for k in ("SEG_START", "SEG_END", "GROUP_OFF", "COLOR_OFF", "APP_OFF", "RG_OFF", "G_START", "G_END",
+GROUPS_DTYPES.update({k: np.uint32 for k in ("NP_OFF", "NP_START", "NP_END", "SEG_START", "SEG_END", "GROUP_OFF", "COLOR_OFF", "APP_OFF", "RG_OFF", "G_START", "G_END",
                                              "BN_START", "BN_END", "N_BUN", "N_BN", "J_START", "J_END")})
 GROUPS_DTYPES.update({k: np.int8 for k in ("R_STRAND", "G_ALIVE", "J_STRAND")})
 GROUPS_DTYPES.update({k: np.float32 for k in ("G_COV", "G_MULTI", "G_NEG_PROP", "BUN_COV", "BUN_MULTI", "BN_COV")})
-GROUPS_DTYPES.update({k: np.float64 for k in ("NUM_FRAGMENTS", "FRAG_LEN", "J_NREADS", "J_NREADS_GOOD", "J_LEFT", "J_RIGHT", "J_NM", "J_MM")})
+GROUPS_DTYPES.update({k: np.float64 for k in ("NP_COV", "NUM_FRAGMENTS", "FRAG_LEN", "J_NREADS", "J_NREADS_GOOD", "J_LEFT", "J_RIGHT", "J_NM", "J_MM")})
 
 
 class StgError(RuntimeError):
@@ -94,6 +96,7 @@ def load_library() -> C.CDLL:
                                  c_f32p, u8p]
     L.stg_infer_transcripts.argtypes = [vp, C.POINTER(StgBundleView), C.POINTER(StgBundleResult)]
     L.stg_build_groups.argtypes = [vp, vp]
+    L.stg_neutral_predictions.argtypes = [vp, vp]
     L.stg_groups_array_info.argtypes = [vp, C.c_int, c_i64p, C.POINTER(C.c_int32)]
     L.stg_fetch_groups_array.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
     L.stg_shard_assign.argtypes = [C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
@@ -260,7 +263,14 @@ class Engine:
         return out
 
     def fetch_groups(self, batch: DeviceBatch) -> Dict[str, np.ndarray]:
-        return {k: self.fetch_groups_array(batch, k) for k in GROUPS_ARRAYS}
+        return {k: self.fetch_groups_array(batch, k) for k in GROUPS_ARRAYS if k not in NEUTRAL_ARRAYS}
+
+    # ---- row a19 (de novo part) ----------------------------------------------------------------------------
+    def neutral_predictions(self, batch: DeviceBatch) -> Dict[str, np.ndarray]:
+        """Single-exon predictions of the neutral bundles (stg_neutral_predictions; needs build_groups): batch-wide
+        arrays off [n_bundles+1], start, end, cov (f64), tlen, geneno."""
+        self._ck(self.L.stg_neutral_predictions(self.ctx, batch.handle))
+        return {k[3:].lower(): self.fetch_groups_array(batch, k) for k in NEUTRAL_ARRAYS}
 
     def fetch_cov_totals(self, batch: DeviceBatch) -> np.ndarray:
         out = np.empty(batch.n_bundles * 3, dtype=np.float64)

@@ -432,3 +432,56 @@ def test_groups_empty_bundles_and_reads_without_junctions(engine):
     b = synth.make_sparse(n_reads=50, seed=1, n_bundles=2)  # no junction rows at all
     cov, off, good, left, right = orc.run(b)
     a9_util.assert_same(_gpu_groups(engine, b), orc.groups(b, cov, off, good, left, right))
+
+
+# ---- row a19 (de novo part): single-exon predictions of the neutral bundles (stg_neutral_predictions) -------------
+def _gpu_neutral(engine, a):
+    batch = engine.upload(a)
+    try:
+        engine.run(batch)
+        engine.build_groups(batch)
+        return engine.neutral_predictions(batch)
+    finally:
+        batch.free()
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_neutral_predictions_golden(engine, name):
+    """Against the prediction list dumped INSIDE the reference's build_graphs right after its neutral-bundle section
+    (hook before rlink.cpp:15637): coordinates, length, gene number equal, coverage equal as f64."""
+    from stringtie_b200.stgb import input_view
+    g = load_golden(name)
+    got = _gpu_neutral(engine, input_view(g))
+    assert np.array_equal(got["off"], g["a19_pred_off"])
+    assert np.array_equal(got["start"], g["a19_start"]) and np.array_equal(got["end"], g["a19_end"])
+    assert np.array_equal(got["tlen"], g["a19_tlen"]) and np.array_equal(got["geneno"], g["a19_geneno"])
+    assert np.array_equal(got["cov"], g["a19_cov"])
+    assert np.array_equal(got["cov"].astype(np.float32), g["a19_exoncov"])
+
+
+@pytest.mark.parametrize("kind,seed", [("wide", 8), ("wide", 9), ("synth", 3), ("adv", 2)])
+def test_neutral_predictions_vs_oracle(engine, kind, seed):
+    a = (synth.make_batch(n_bundles=400, reads_per_bundle=500, seed=seed) if kind == "wide" else
+         synth.make_batch(n_bundles=60, reads_per_bundle=3000, seed=seed) if kind == "synth" else
+         synth.make_adversarial(seed=seed, n_bundles=14))
+    cov, off, good, left, right = orc.run(a)
+    want = orc.neutral_preds(a, cov, off, good, left, right)
+    got = _gpu_neutral(engine, a)
+    woff = np.concatenate([[0], np.cumsum([w["start"].size for w in want])]).astype(np.uint32)
+    assert np.array_equal(got["off"], woff)
+    if kind == "wide":
+        assert woff[-1] > 20
+    for k in ("start", "end", "cov", "tlen", "geneno"):
+        w = np.concatenate([x[k] for x in want]) if want else np.zeros(0)
+        assert np.array_equal(got[k], w.astype(got[k].dtype)), k
+
+
+def test_neutral_predictions_need_groups(engine):
+    from stringtie_b200.engine import StgError
+    batch = engine.upload(synth.make_batch(n_bundles=3, reads_per_bundle=100, seed=1))
+    try:
+        engine.run(batch)
+        with pytest.raises(StgError):
+            engine.neutral_predictions(batch)
+    finally:
+        batch.free()
