@@ -264,6 +264,15 @@ def main():
                             "groups": int(eng.fetch_groups_array(batch, "GROUP_OFF")[-1]),
                             "bundlenodes": int(eng.fetch_groups_array(batch, "N_BN").sum()),
                             "note": "per GPU, one pass, outside the timed region; wall includes first-use cudaMalloc of the stage's buffers"}
+            # row a19 (de novo part): single-exon predictions of the neutral bundles, from the device-resident bundlenodes
+            eng.sync()
+            t0 = time.perf_counter()
+            npred = eng.neutral_predictions(batch)
+            eng.sync()
+            nk = {n: ms for n, ms in eng.kernel_times() if n.startswith("neutral") or n == "find_trims"}
+            groups_stage["row_a19_neutral_predictions"] = {"kernel_ms": nk, "ms": sum(nk.values()),
+                                                           "wall_ms": 1e3 * (time.perf_counter() - t0),
+                                                           "predictions": int(npred["start"].size)}
         except Exception as ex:   # the headline must not depend on the newer stage
             groups_stage = {"error": str(ex)}
     eng.set_profiling(False)
