@@ -108,11 +108,15 @@ def reference_hot(arrays, nbundles: int, threads: int, reps: int):
             write_stgb(path, sample)
             out = subprocess.check_output([tool, path, "--threads", str(threads), "--reps", str(reps), "--a7"], text=True)
             out9 = subprocess.check_output([tool, path, "--threads", str(threads), "--reps", str(reps), "--a9b"], text=True)
+            out19 = subprocess.check_output([tool, path, "--threads", str(threads), "--reps", str(reps), "--a19"], text=True)
         j = json.loads(out.strip().splitlines()[-1])
         j9 = json.loads(out9.strip().splitlines()[-1])
+        j19 = json.loads(out19.strip().splitlines()[-1])
         return {"value": j["reads_per_s"], "unit": "reads/s", "cores": threads, "kind": "reference",
                 "through_rows_a8_a9": {"reads_per_s": j9["reads_per_s"], "compute_s": j9["compute_s_max"],
                                        "note": "same sample, the reference run on to the end of its bundle creation (rlink.cpp:15433)"},
+                "through_row_a19": {"reads_per_s": j19["reads_per_s"], "compute_s": j19["compute_s_max"],
+                                    "note": "... and on to the end of its neutral-bundle predictions (rlink.cpp:15637)"},
                 "sample": desc + "; reference count_good_junctions (rlink.cpp:16656) + build_graphs up to the end of its "
                           "junction pass (rlink.cpp:14165-14842) on rebuilt BundleData, "
                           "aggregate of per-thread reads / per-thread compute time",
