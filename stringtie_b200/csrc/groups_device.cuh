@@ -674,6 +674,28 @@ STG_HD int fp_bail(int) { return 0; }
 // of it and the next one starts with it
 STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& __restrict__ R) {
   R.nv = 0; R.nrg0 = 0; R.nrg1 = 0; R.has_multi = 0; R.sno = -1; R.newcol = 0; R.fresh_gc = -1; R.gp_np = -1; R.npc = -1; R.unpair_np = -1; R.xg = -1;
+#ifdef __CUDA_ARCH__
+  // the lines this read will need one after the other (its exons and junction rows, its mate's fields) are asked for
+  // at once: the classification is a chain of dependent loads, this shortens it
+  {
+    const uint32_t so = S.seg_off[n] - S.seg0, po = S.pair_off[n];
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.seg_s + so));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.seg_e + so));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.rj + (so - (uint32_t)n)));
+    if (S.pair_off[n + 1] != po) {
+      const int m = S.pair[po - S.pair0];
+      if (m >= 0 && m < S.nr) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(S.strand + m));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(S.r_nh + m));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(S.r_start + m));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(S.r_end + m));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(S.seg_off + m));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(S.rg_cnt + m));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(S.rcap_off + m));
+      }
+    }
+  }
+#endif
   const int nj = S.njunc(n);
   // the repair must leave the read alone: every junction stranded, good, not demoted, not flagged
   for (int i = 0; i < nj; i++) {
