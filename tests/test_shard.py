@@ -60,6 +60,9 @@ def _worker(rank, world, port, q):
         tot[0] += orc.get_cov(cov[off[b]:off[b + 1]], int(lens[b]), 1, 0, int(lens[b]) - 2)
     tot[1] = float(mine["r_start"].size)
     tot[2] = float(lens.size)
+    # the reference's global sums Num_Fragments / Frag_Len (stringtie.cpp:1490-1497) come out of rows a8 + a9
+    gr = orc.groups(mine, cov, off, good, left, right)
+    tot = np.concatenate([tot, [sum(g["num_fragments"] for g in gr), sum(g["frag_len"] for g in gr)]])
     red = shard.allreduce_totals(tot, dist)
     q.put((rank, red.tolist(), parts[rank].tolist(), float(good.sum())))
     dist.destroy_process_group()
@@ -84,8 +87,12 @@ def test_two_ranks_gloo_allreduce_matches_single_process():
     cov, off, good, left, right = orc.run(a)
     lens, _ = orc.cov_layout(a)
     want = sum(orc.get_cov(cov[off[b]:off[b + 1]], int(lens[b]), 1, 0, int(lens[b]) - 2) for b in range(lens.size))
+    full = orc.groups(a, cov, off, good, left, right)
+    want_nf, want_fl = sum(g["num_fragments"] for g in full), sum(g["frag_len"] for g in full)
+    assert want_nf > 0
     for rank, red, part, gsum in res:
         assert abs(red[0] - want) <= 1e-9 * max(1.0, want)
         assert red[1] == a["r_start"].size and red[2] == lens.size
+        assert abs(red[3] - want_nf) <= 1e-9 * max(1.0, want_nf) and abs(red[4] - want_fl) <= 1e-9 * max(1.0, want_fl)
     assert abs(sum(r[3] for r in res) - good.sum()) < 1e-9
     assert sorted(res[0][2] + res[1][2]) == list(range(lens.size))
