@@ -61,9 +61,12 @@ __global__ void __launch_bounds__(STG_READ_BLOCK) group_caps_kernel(DevBatchView
 // those is an L2 round trip on the critical path.  A bundle that outgrows GROUPS_SMEM slots is moved to its global
 // arrays and carries on there.
 #define GROUPS_SMEM 256
-#define GROUPS_WARPS 3                      // warps of a CTA; one CTA walks one bundle (C2: 201 ms with 4 warps, 210 with 2)
-#define GROUPS_STEP (32 * GROUPS_WARPS)     // threads of a CTA
-#define GROUPS_CLS (GROUPS_STEP - 32)        // of which classify reads (warp 0 adds the float sums of the previous run)
+// One CTA walks one bundle; NW warps, of which NW - 1 classify reads (warp 0 adds the float sums of the previous run).
+// Deep bundles (>= GROUPS_DEEP_READS reads) get 4 warps: their runs of simple reads fill the widest window.  The rest get
+// 2 (one classifying warp): their runs are short and what counts is how many bundles an SM holds.  The two grids run
+// side by side on two streams; both kernels ask for the same shared-memory carve-out, otherwise an SM would have to
+// drain before it can take a CTA of the other kernel.
+#define GROUPS_DEEP_READS 16384
 struct GroupSmem {
   uint32_t start[GROUPS_SMEM], end[GROUPS_SMEM];
   int32_t color[GROUPS_SMEM], next[GROUPS_SMEM], merge[GROUPS_SMEM], grid[GROUPS_SMEM];
@@ -81,7 +84,9 @@ __device__ __forceinline__ void groups_to_global(const Grp& S, const GroupGlobal
 }
 
 // what thread 0 (the owner of the walk's mutable scalars) shares with the CTA between steps
+template <int GROUPS_WARPS>
 struct WalkCtl {
+  static constexpr int GROUPS_CLS = 32 * GROUPS_WARPS - 32;
   int32_t curr[3];
   int32_t ng, color, err;
   int32_t last[3];             // last read of the run that set the cursor of strand lane s (atomicMax of the thread index)
@@ -95,11 +100,14 @@ struct WalkCtl {
 // group's sum is added in read order) and the bundle's fragment sums — classification never reads those sums, so
 // the two overlap and only meet at the barrier that ends a step.  A read that is not simple is walked the reference's
 // way by thread 0 once the pending sums are in.
-__global__ void __launch_bounds__(GROUPS_STEP, 5) groups_walk_kernel(DevBatchView v, GroupsView g, JuncParams prm) {
+template <int GROUPS_WARPS, int MINB>
+__global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(DevBatchView v, GroupsView g, JuncParams prm,
+                                                                             uint32_t order_base) {
+  constexpr int GROUPS_STEP = 32 * GROUPS_WARPS, GROUPS_CLS = GROUPS_STEP - 32;
   __shared__ GroupSmem M;
   __shared__ FastRec Rb[2][GROUPS_CLS];   // records of the step being classified / of the run whose sums are pending
-  __shared__ WalkCtl ctl;
-  const uint32_t b = g.order[blockIdx.x];
+  __shared__ WalkCtl<GROUPS_WARPS> ctl;
+  const uint32_t b = g.order[order_base + blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t r0 = v.b_read_off[b], nr = v.b_read_off[b + 1] - r0;
   const uint32_t j0 = v.b_junc_off[b], nj0 = v.b_junc_off[b + 1] - j0;
@@ -383,11 +391,29 @@ cudaError_t launch_group_caps(const DevBatchView& v, uint32_t* rcap, unsigned lo
   return cudaGetLastError();
 }
 
-cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, cudaStream_t st) {
+cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, int64_t n_deep, cudaStream_t st,
+                               cudaStream_t aux, cudaEvent_t fork, cudaEvent_t join) {
   if (v.n_bundles == 0) return cudaSuccess;
-  groups_walk_kernel<<<(unsigned)v.n_bundles, GROUPS_STEP, 0, st>>>(v, g, p);
-  return cudaGetLastError();
+  static bool configured = false;
+  cudaError_t e;
+  if (!configured) {
+    if ((e = cudaFuncSetAttribute(groups_walk_kernel<4, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(groups_walk_kernel<2, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
+      return e;
+    configured = true;
+  }
+  if (n_deep > 0) {   // the deep bundles on the second stream, next to the shallow mass
+    if ((e = cudaEventRecord(fork, st)) != cudaSuccess || (e = cudaStreamWaitEvent(aux, fork, 0)) != cudaSuccess) return e;
+    groups_walk_kernel<4, 4><<<(unsigned)n_deep, 128, 0, aux>>>(v, g, p, 0u);
+    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaEventRecord(join, aux)) != cudaSuccess) return e;
+  }
+  if (v.n_bundles > n_deep) groups_walk_kernel<2, 8><<<(unsigned)(v.n_bundles - n_deep), 64, 0, st>>>(v, g, p, (uint32_t)n_deep);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (n_deep > 0 && (e = cudaStreamWaitEvent(st, join, 0)) != cudaSuccess) return e;
+  return cudaSuccess;
 }
+
+int64_t groups_deep_reads() { return GROUPS_DEEP_READS; }
 
 cudaError_t launch_groups_finish(const DevBatchView& v, const GroupsView& g, cudaStream_t st) {
   if (v.n_bundles == 0) return cudaSuccess;

@@ -25,6 +25,8 @@ struct stg_ctx {
   int num_sms = 0;
   stg_params params;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux_stream = nullptr;   // second stream of the rows a8 + a9 stage (deep bundles beside the shallow mass)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string error;
   bool profiling = false;
   std::vector<Timed> timed;      // events of the last stg_run
@@ -292,6 +294,9 @@ int stg_init(const stg_params* params, int device, stg_ctx** out) {
     return fail(nullptr, STG_ENODEV, "libstgpu is built for sm_100a (B200) only");
   }
   CK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(nullptr, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+  CK(nullptr, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  CK(nullptr, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   *out = ctx;
   return STG_OK;
 }
@@ -304,6 +309,9 @@ int stg_shutdown(stg_ctx* ctx) {
   if (ctx->one_bundle) stg_builder_destroy(ctx->one_bundle);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
+  if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
   return STG_OK;
 }
@@ -808,7 +816,9 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
   }
   CK(ctx, cudaMemsetAsync(v.err_flag, 0, sizeof(uint32_t), st));
   JuncParams jp{pr.junctionsupport, pr.sserror, pr.junctionthr, pr.eonly};
-  { Scope s(ctx, "groups_walk", 1); CK(ctx, launch_groups_walk(v, g, jp, st)); }
+  int64_t n_deep = 0;   // `order` is sorted by decreasing read count
+  while (n_deep < nb && (int64_t)d->h_nreads[order[n_deep]] >= groups_deep_reads()) n_deep++;
+  { Scope s(ctx, "groups_walk", 2); CK(ctx, launch_groups_walk(v, g, jp, n_deep, st, ctx->aux_stream, ctx->ev_fork, ctx->ev_join)); }
   { Scope s(ctx, "groups_scans", 4);
     CK(ctx, launch_scan_exclusive_add(g.b_ng, nb + 1, scan_state, ticket, st));
     CK(ctx, launch_scan_exclusive_add(g.b_ncol, nb + 1, scan_state, ticket, st));

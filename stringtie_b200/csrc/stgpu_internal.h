@@ -182,7 +182,9 @@ cudaError_t launch_find_trims(const DevBatchView& v, int64_t n, const int32_t* b
                               const uint32_t* end, const uint32_t* cap_off, uint32_t* o_cnt, uint32_t* o_pos, float* o_ab,
                               uint8_t* o_st, cudaStream_t st);
 cudaError_t launch_group_caps(const DevBatchView& v, uint32_t* rcap, unsigned long long* total, int32_t* rj, cudaStream_t st);
-cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, cudaStream_t st);
+cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, int64_t n_deep, cudaStream_t st,
+                               cudaStream_t aux, cudaEvent_t fork, cudaEvent_t join);
+int64_t groups_deep_reads();   // bundles with at least this many reads are walked by the wide kernel
 cudaError_t launch_groups_finish(const DevBatchView& v, const GroupsView& g, cudaStream_t st);
 cudaError_t launch_neutral_count(const DevBatchView& v, const GroupsView& g, uint32_t* reg_off, cudaStream_t st);
 cudaError_t launch_neutral_regions(const DevBatchView& v, const GroupsView& g, const NeutralView& nv, cudaStream_t st);
