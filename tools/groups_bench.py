@@ -13,6 +13,7 @@ from tests import orc, a9_util
 ap = argparse.ArgumentParser()
 ap.add_argument("--replicas", type=int, default=1)
 ap.add_argument("--check", type=int, default=200, help="bundles of the base compared with the oracle")
+ap.add_argument("--prewarm", type=int, default=0, help="passes of stg_run before the stage (the state bench.py measures it in)")
 args = ap.parse_args()
 base, work = bench.build_workload(args.replicas, bench.BASE_BUNDLES, 0)
 eng = Engine(0)
@@ -20,6 +21,8 @@ eng.set_profiling(True)
 res = {"replicas": args.replicas, "bundles": int(work["b_start"].size), "reads": int(work["r_start"].size)}
 batch = eng.upload(work)
 eng.run(batch)
+for _ in range(args.prewarm):
+    eng.run(batch)
 eng.sync()
 t = time.time()
 eng.build_groups(batch)
