@@ -151,7 +151,10 @@ def main():
     config = {"workload": workload_name, "per_gpu": "one full copy of the workload per rank (weak scaling)",
               "l2": "inputs_larger_than_L2", "stages": ["cov_edge_add/add_read_to_cov", "junction support",
                                                          "blocked clamped scan", "get_cov totals",
-                                                         "build_graphs junction pass + good_junc"]}
+                                                         "build_graphs junction pass + good_junc"],
+              "scope": "value / e2e / roofline cover SURVEY rows a1-a7 (the reference arm times the same rows); rows a8 + a9 "
+                       "(read loop, groups, bundles) and a19 (neutral predictions) are built too and reported beside "
+                       "them under rows_a8_a9 (one pass outside the timed region; pipeline_a1_to_a9_reads_per_s)"}
 
     # ---------------- reference arm: the reference's own CPU code, all host threads, bounded sample ----------
     if args.impl == "reference":
