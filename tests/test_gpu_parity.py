@@ -380,6 +380,7 @@ def test_groups_c2_base_sample(engine):
         engine.run(batch)
         engine.build_groups(batch)
         G = engine.fetch_groups(batch)
+        N = engine.neutral_predictions(batch)
     finally:
         batch.free()
     got_all = a9_util.split_engine_groups(G, base)
@@ -387,6 +388,14 @@ def test_groups_c2_base_sample(engine):
     cov, off, good, left, right = orc.run(sub, threads=0)
     want = orc.groups(sub, cov, off, good, left, right)
     a9_util.assert_same([got_all[int(b)] for b in pick], want)
+    # row a19 on the same sample: the neutral bundles' predictions of every picked bundle
+    wantn = orc.neutral_preds(sub, cov, off, good, left, right)
+    noff = N["off"].astype(np.int64)
+    assert noff[-1] > 100
+    for k, b in enumerate(pick):
+        p0, p1 = int(noff[b]), int(noff[b + 1])
+        for key in ("start", "end", "cov", "tlen", "geneno"):
+            assert np.array_equal(N[key][p0:p1], wantn[k][key].astype(N[key].dtype)), (int(b), key)
     # size-independent properties over ALL bundles: live groups of a lane are disjoint and sorted along the chain
     go = G["GROUP_OFF"].astype(np.int64)
     for b in rng.choice(nreads.size, size=400, replace=False):
