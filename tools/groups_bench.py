@@ -14,7 +14,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--replicas", type=int, default=1)
 ap.add_argument("--check", type=int, default=200, help="bundles of the base compared with the oracle")
 ap.add_argument("--prewarm", type=int, default=0, help="passes of stg_run before the stage (the state bench.py measures it in)")
+ap.add_argument("--torch", action="store_true", help="initialise torch.cuda first, as bench.py does")
 args = ap.parse_args()
+if args.torch:
+    import torch
+    torch.zeros(1, device="cuda")
 base, work = bench.build_workload(args.replicas, bench.BASE_BUNDLES, 0)
 eng = Engine(0)
 eng.set_profiling(True)
