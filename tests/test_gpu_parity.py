@@ -354,11 +354,12 @@ def test_groups_refuses_unsupported_modes():
         e.close()
 
 
-def test_groups_many_groups_leave_shared_memory(engine):
+@pytest.mark.parametrize("n_reads", [3000, 17000])   # walked by the 2-warp kernel / by the 4-warp kernel of deep bundles
+def test_groups_many_groups_leave_shared_memory(engine, n_reads):
     """Bundles whose group arrays outgrow the shared-memory slots of the walk kernel (sparse reads over long spans:
-    hundreds of separate groups per strand lane) carry on in global memory."""
+    thousands of separate groups per strand lane) carry on in global memory."""
     from tests import a9_util
-    a = synth.make_sparse(n_reads=3000, seed=21, n_bundles=3)
+    a = synth.make_sparse(n_reads=n_reads, seed=21, n_bundles=3 if n_reads < 10000 else 2)
     cov, off, good, left, right = orc.run(a)
     want = orc.groups(a, cov, off, good, left, right)
     assert min(w["g_start"].size for w in want) > 600
