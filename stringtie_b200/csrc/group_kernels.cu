@@ -394,14 +394,11 @@ cudaError_t launch_group_caps(const DevBatchView& v, uint32_t* rcap, unsigned lo
 cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, int64_t n_deep, cudaStream_t st,
                                cudaStream_t aux, cudaEvent_t fork, cudaEvent_t join) {
   if (v.n_bundles == 0) return cudaSuccess;
-  static bool configured = false;
   cudaError_t e;
-  if (!configured) {
-    if ((e = cudaFuncSetAttribute(groups_walk_kernel<4, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(groups_walk_kernel<2, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
-      return e;
-    configured = true;
-  }
+  // per device and cheap: both kernels must prefer the same carve-out to be able to share an SM
+  if ((e = cudaFuncSetAttribute(groups_walk_kernel<4, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(groups_walk_kernel<2, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
+    return e;
   if (n_deep > 0) {   // the deep bundles on the second stream, next to the shallow mass
     if ((e = cudaEventRecord(fork, st)) != cudaSuccess || (e = cudaStreamWaitEvent(aux, fork, 0)) != cudaSuccess) return e;
     groups_walk_kernel<4, 4><<<(unsigned)n_deep, 128, 0, aux>>>(v, g, p, 0u);
