@@ -92,6 +92,8 @@ struct WalkCtl {
   int32_t last[3];             // last read of the run that set the cursor of strand lane s (atomicMax of the thread index)
   uint32_t ok_mask[GROUPS_WARPS], mint_mask[GROUPS_WARPS], wait_mask[GROUPS_WARPS], grow_mask[GROUPS_WARPS];   // [0] unused
   int32_t npc[GROUPS_CLS];
+  int32_t n_grow[2];            // window positions of the step's reads that grow a group (GROW kernels; double-buffered)
+  int32_t grow[2][GROUPS_CLS];
 };
 
 // The CTA's schedule (groups_device.cuh, "the parallel form of the loop"): warps 1.. classify the next GROUPS_CLS reads
@@ -100,12 +102,15 @@ struct WalkCtl {
 // group's sum is added in read order) and the bundle's fragment sums — classification never reads those sums, so
 // the two overlap and only meet at the barrier that ends a step.  A read that is not simple is walked the reference's
 // way by thread 0 once the pending sums are in.
-template <int GROUPS_WARPS, int MINB>
+// GROW: reads that grow a group stay inside the runs (they record the bounds they depend on; pays off where runs are
+// short, i.e. in shallow bundles); otherwise such a read ends its run.
+template <int GROUPS_WARPS, int MINB, bool GROW>
 __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(DevBatchView v, GroupsView g, JuncParams prm,
                                                                              uint32_t order_base) {
   constexpr int GROUPS_STEP = 32 * GROUPS_WARPS, GROUPS_CLS = GROUPS_STEP - 32;
   __shared__ GroupSmem M;
   __shared__ FastRec Rb[2][GROUPS_CLS];   // records of the step being classified / of the run whose sums are pending
+  __shared__ FastDeps Db[GROW ? GROUPS_CLS : 1];
   __shared__ WalkCtl<GROUPS_WARPS> ctl;
   const uint32_t b = g.order[order_base + blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
   const int inr = (int)nr;
   const unsigned FULL = 0xffffffffu;
   const int ct = tid - 32;                    // index among the classifying threads (warp 0: negative)
-  if (tid == 0) { ctl.err = 0; ctl.last[0] = ctl.last[1] = ctl.last[2] = -1; }
+  if (tid == 0) { ctl.err = 0; ctl.last[0] = ctl.last[1] = ctl.last[2] = -1; ctl.n_grow[0] = ctl.n_grow[1] = 0; }
   __syncthreads();
 
   // float sums of a committed run, in read order: lane l owns the groups with slot % 32 == l; the sum of the group being
@@ -190,13 +195,17 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
     int st = 0;                                 // 1 simple, 3 simple + grows a group, 0 not simple, 2 waits
     if (warp == 0) { if (pend_k) pending_sums(Rb[pend_buf], pend_k); }
     else if (classify) {
-      if (me < hi) st = classify_read(S, me, n, hi, R[ct]);
-      ctl.npc[ct] = st == 1 ? R[ct].npc : -1;
+      if (me < hi) st = GROW ? classify_read<true>(S, me, n, hi, R[ct], &Db[GROW ? ct : 0]) : classify_read<false>(S, me, n, hi, R[ct]);
+      ctl.npc[ct] = (st == 1 || (GROW && st == 3)) ? R[ct].npc : -1;
+      if (GROW && st == 3) ctl.grow[buf][atomicAdd(&ctl.n_grow[buf], 1)] = ct;
     }
     pend_k = 0;
     __syncthreads();   // (B) the pending sums are in; the records of this step are written
     if (n >= inr) break;
-    if (tid == 32) ctl.last[0] = ctl.last[1] = ctl.last[2] = -1;   // everybody read them before (B); set again after (C)
+    if (tid == 32) {   // everybody read them before (B); the cursors are set again after (C), the list is filled next step
+      ctl.last[0] = ctl.last[1] = ctl.last[2] = -1;
+      ctl.n_grow[buf ^ 1] = 0;
+    }
     int k = 0;
     bool no_walk = false;
     if (classify) {
@@ -208,8 +217,16 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
           for (int t = 0; t < ct; t++)
             if (ctl.npc[t] == mine) { st = 2; break; }
         }
-        const unsigned okm = __ballot_sync(FULL, st == 1), mim = __ballot_sync(FULL, (st == 1 || st == 3) && R[ct].newcol);
-        const unsigned wam = __ballot_sync(FULL, st == 2), grm = __ballot_sync(FULL, st == 3);
+        if (GROW && (st == 1 || st == 3) && Db[GROW ? ct : 0].n) {
+          // a read that took for granted a bound which an earlier read of the step moves waits for the next step
+          const int ngr = ctl.n_grow[buf];
+          for (int q = 0; q < ngr; q++) {
+            const int t = ctl.grow[buf][q];
+            if (t < ct && grows_past(Db[GROW ? ct : 0], R[t])) { st = 2; break; }
+          }
+        }
+        const unsigned okm = __ballot_sync(FULL, st == 1 || (GROW && st == 3)), mim = __ballot_sync(FULL, (st == 1 || st == 3) && R[ct].newcol);
+        const unsigned wam = __ballot_sync(FULL, st == 2), grm = __ballot_sync(FULL, !GROW && st == 3);
         if (lane == 0) { ctl.ok_mask[warp] = okm; ctl.mint_mask[warp] = mim; ctl.wait_mask[warp] = wam; ctl.grow_mask[warp] = grm; }
       }
       __syncthreads();   // (C)
@@ -397,15 +414,15 @@ cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const
   cudaError_t e;
   // per device and cheap: both kernels must prefer the same carve-out to be able to share an SM.  72 % (164 KB of
   // shared memory, ~90 KB of L1) measured best on C2: 100 % 121 ms, 72-80 % 110 ms, 50 % 133 ms (too few shallow CTAs)
-  if ((e = cudaFuncSetAttribute(groups_walk_kernel<4, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 72)) != cudaSuccess ||
-      (e = cudaFuncSetAttribute(groups_walk_kernel<2, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 72)) != cudaSuccess)
+  if ((e = cudaFuncSetAttribute(groups_walk_kernel<4, 4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 72)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(groups_walk_kernel<2, 8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 72)) != cudaSuccess)
     return e;
   if (n_deep > 0) {   // the deep bundles on the second stream, next to the shallow mass
     if ((e = cudaEventRecord(fork, st)) != cudaSuccess || (e = cudaStreamWaitEvent(aux, fork, 0)) != cudaSuccess) return e;
-    groups_walk_kernel<4, 4><<<(unsigned)n_deep, 128, 0, aux>>>(v, g, p, 0u);
+    groups_walk_kernel<4, 4, false><<<(unsigned)n_deep, 128, 0, aux>>>(v, g, p, 0u);
     if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaEventRecord(join, aux)) != cudaSuccess) return e;
   }
-  if (v.n_bundles > n_deep) groups_walk_kernel<2, 8><<<(unsigned)(v.n_bundles - n_deep), 64, 0, st>>>(v, g, p, (uint32_t)n_deep);
+  if (v.n_bundles > n_deep) groups_walk_kernel<2, 8, true><<<(unsigned)(v.n_bundles - n_deep), 64, 0, st>>>(v, g, p, (uint32_t)n_deep);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (n_deep > 0 && (e = cudaStreamWaitEvent(st, join, 0)) != cudaSuccess) return e;
   return cudaSuccess;

@@ -672,8 +672,16 @@ STG_HD int fp_bail(int) { return 0; }
 // committed as the last read of a run, the reads behind it have to be classified against the grown group; 0: not
 // simple; 2: simple or not, it has to wait for an earlier read of the same step (its mate), i.e. the step ends in front
 // of it and the next one starts with it
-STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& __restrict__ R) {
+// What a read took for granted about the bounds of groups it walked past or stopped in front of: group g[i] must keep
+// its END below x[i] (bit i of kind clear) or its START above x[i] (bit set).  With these recorded, reads that grow a
+// group need not end a run: a later read of the step waits only if an earlier one moves a bound it depends on.
+#define STG_FP_MAXC 6
+struct FastDeps { int32_t n; uint32_t kind; int32_t g[STG_FP_MAXC]; uint32_t x[STG_FP_MAXC]; };
+
+template <bool DEPS>
+STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& __restrict__ R, FastDeps* __restrict__ D = nullptr) {
   R.nv = 0; R.nrg0 = 0; R.nrg1 = 0; R.has_multi = 0; R.sno = -1; R.newcol = 0; R.fresh_gc = -1; R.gp_np = -1; R.npc = -1; R.unpair_np = -1; R.xg = -1;
+  if (DEPS) { D->n = 0; D->kind = 0; }
 #ifdef __CUDA_ARCH__
   // the lines this read will need one after the other (its exons and junction rows, its mate's fields) are asked for
   // at once: the classification is a chain of dependent loads, this shortens it
@@ -758,11 +766,21 @@ STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& __restric
       uint32_t xs = 0, xe = 0;
       auto GS = [&](int gq) -> uint32_t { return gq == xg ? xs : S.g_start[gq]; };
       auto GE = [&](int gq) -> uint32_t { return gq == xg ? xe : S.g_end[gq]; };
+      bool full = false;   // more bounds than FastDeps holds
+      auto depends = [&](int gq, bool start_above, uint32_t x) {
+        if (!DEPS) return;
+        if (D->n == STG_FP_MAXC) { full = true; return; }
+        D->g[D->n] = gq; D->x[D->n] = x;
+        if (start_above) D->kind |= 1u << D->n;
+        D->n++;
+      };
       int currgroup = S.curr.get(sno);
       if (currgroup == -1) return fp_bail(9);
       int lastgroup = -1;
       const uint32_t rstart = S.r_start[cn];
       while (currgroup != -1 && rstart > GE(currgroup)) { lastgroup = currgroup; currgroup = S.g_next[currgroup]; }
+      if (lastgroup != -1) depends(lastgroup, false, rstart);           // the last group walked past ends below the read
+      if (currgroup != -1 && S.seg_e[S.segi(cn, 0)] < GS(currgroup)) depends(currgroup, true, S.seg_e[S.segi(cn, 0)]);
       if (currgroup == -1 || S.seg_e[S.segi(cn, 0)] < GS(currgroup)) currgroup = lastgroup;
       if (currgroup == -1) return fp_bail(10);
       int thisgroup = currgroup, ncoord = S.nseg(cn), lastpushed = -1, i = 0;
@@ -770,13 +788,18 @@ STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& __restric
       while (i < ncoord) {
         if (!keep_exon(S, cn, i)) return fp_bail(11);
         const uint32_t ss = S.seg_s[S.segi(cn, i)], se = S.seg_e[S.segi(cn, i)];
-        while (thisgroup != -1 && ss > GE(thisgroup)) thisgroup = S.g_next[thisgroup];
+        {
+          int skipped = -1;
+          while (thisgroup != -1 && ss > GE(thisgroup)) { skipped = thisgroup; thisgroup = S.g_next[thisgroup]; }
+          if (skipped != -1) depends(skipped, false, ss);
+        }
         if (thisgroup == -1 || se + localdist < GS(thisgroup)) return fp_bail(12);             // a new group
         if (ss < GS(thisgroup) || se > GE(thisgroup)) {                                          // the group grows
           if (xg != -1 && xg != thisgroup) return fp_bail(13);                                   // ... a second one
           const int nx = S.g_next[thisgroup];
           const uint32_t ns2 = ss < GS(thisgroup) ? ss : GS(thisgroup), ne2 = se > GE(thisgroup) ? se : GE(thisgroup);
           if (nx != -1 && se >= S.g_start[nx]) return fp_bail(13);                               // ... into the next one: a merge
+          if (nx != -1 && se > GE(thisgroup)) depends(nx, true, se);                              // the next group starts above it
           xg = thisgroup; xs = ns2; xe = ne2;
         }
         if (S.g_grid[thisgroup] != thisgroup || S.g_merge[thisgroup] != thisgroup) return fp_bail(14);
@@ -820,6 +843,7 @@ STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& __restric
             if (xg != -1 && xg != thisgroup) return fp_bail(18);
             const int nx = S.g_next[thisgroup];
             if (nx != -1 && S.r_start[cn] >= S.g_start[nx]) return fp_bail(18);                  // a merge
+            if (nx != -1) depends(nx, true, S.r_start[cn]);
             xs = GS(thisgroup); xe = S.r_start[cn]; xg = thisgroup;
           }
           lastpushed = -1;
@@ -828,6 +852,7 @@ STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& __restric
         }
         i++;
       }
+      if (full) return fp_bail(19);
       R.sno = sno; R.curr = currgroup;
       R.xg = xg; R.xs = xs; R.xe = xe;
     }
@@ -846,6 +871,24 @@ STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& __restric
   return R.xg >= 0 ? 3 : 1;
 }
 
+// does the growth of `earlier` (a read of the same step, outcome 3) move a bound that the later read depends on?
+STG_HD bool grows_past(const FastDeps& later, const FastRec& earlier) {
+  for (int i = 0; i < later.n; i++)
+    if (later.g[i] == earlier.xg) {
+      if (later.kind >> i & 1u) { if (earlier.xs <= later.x[i]) return true; }
+      else if (earlier.xe >= later.x[i]) return true;
+    }
+  return false;
+}
+
+#ifdef __CUDA_ARCH__
+#define STG_MIN_INTO(p, v) atomicMin((p), (v))
+#define STG_MAX_INTO(p, v) atomicMax((p), (v))
+#else
+#define STG_MIN_INTO(p, v) do { if ((v) < *(p)) *(p) = (v); } while (0)
+#define STG_MAX_INTO(p, v) do { if ((v) > *(p)) *(p) = (v); } while (0)
+#endif
+
 // the part of a simple read's effect that does not depend on the other reads of the step; fresh_id = the colour it
 // mints.  The readgroup pushes belong here: read n's list is only touched by n itself, and a mate's list by the one
 // read of the step that continues into it (the caller makes sure of that).
@@ -857,7 +900,7 @@ STG_HD void commit_free(Grp& S, const FastRec& R, int n, int fresh_id) {
     else S.err |= STG_GERR_GROUPS;
   }
   if (R.unpair_np >= 0) unpair(S, n, 0, R.unpair_np);
-  if (R.xg >= 0) { S.g_start[R.xg] = R.xs; S.g_end[R.xg] = R.xe; }
+  if (R.xg >= 0) { STG_MIN_INTO(&S.g_start[R.xg], R.xs); STG_MAX_INTO(&S.g_end[R.xg], R.xe); }   // several reads of a run may grow a group
   for (int k = 0; k < R.nrg0; k++) rg_add(S, n, R.rgv[k]);
   for (int k = 0; k < R.nrg1; k++) rg_add(S, R.npc, R.rgv[R.nrg0 + k]);
 }
@@ -877,10 +920,11 @@ STG_HD void commit_ordered(Grp& S, const FastRec& R, double& num_fragments, doub
 // other against the same state, which is what the warp does, since classify_read() only reads.
 #define STG_STEP_MAX 256
 inline void groups_first_half_steps(Grp& S, int32_t* jt_perm, int32_t* jt_inv, double* num_fragments_out, double* frag_len_out,
-                                    int64_t* n_simple = nullptr, int W = 128) {
+                                    int64_t* n_simple = nullptr, int W = 128, bool grow_inside = false) {
   int color = 0;
   double num_fragments = 0, frag_len = 0;
   static FastRec R[STG_STEP_MAX];
+  static FastDeps D[STG_STEP_MAX];
   int n = 0;
   while (n < S.nr && !S.err) {
     const int hi = n + W < S.nr ? n + W : S.nr;
@@ -888,24 +932,36 @@ inline void groups_first_half_steps(Grp& S, int32_t* jt_perm, int32_t* jt_inv, d
     int ok[STG_STEP_MAX];
 #if defined(STG_FP_COUNT_BAILS)
     int why[STG_STEP_MAX];
-    for (int l = 0; n + l < hi; l++) { ok[l] = classify_read(S, n + l, n, hi, R[l]); why[l] = stg_fp_last; }
+    for (int l = 0; n + l < hi; l++) {
+      ok[l] = grow_inside ? classify_read<true>(S, n + l, n, hi, R[l], &D[l]) : classify_read<false>(S, n + l, n, hi, R[l]);
+      why[l] = stg_fp_last;
+    }
 #else
-    for (int l = 0; n + l < hi; l++) ok[l] = classify_read(S, n + l, n, hi, R[l]);
+    for (int l = 0; n + l < hi; l++)
+      ok[l] = grow_inside ? classify_read<true>(S, n + l, n, hi, R[l], &D[l]) : classify_read<false>(S, n + l, n, hi, R[l]);
 #endif
     // two reads of the step that continue into the SAME mate (a read with several pair links) see each other's
     // readgroup pushes: the later one has to wait
     for (int l = 1; n + l < hi; l++)
-      for (int l2 = 0; l2 < l && ok[l] == 1; l2++)
-        if (ok[l2] == 1 && R[l].npc >= 0 && R[l2].npc == R[l].npc) ok[l] = 2;
-    for (int l = 1; n + l < hi; l++)   // the same for a read that grows a group
-      for (int l2 = 0; l2 < l && ok[l] == 3; l2++)
-        if (ok[l2] == 1 && R[l].npc >= 0 && R[l2].npc == R[l].npc) ok[l] = 2;
-    while (n + k < hi && ok[k] == 1) k++;
-    const int stop = n + k < hi ? ok[k] : 1;   // what ended the run
-    if (stop == 3) k++;                         // a read that grows a group is the run's last read
+      for (int l2 = 0; l2 < l && (ok[l] == 1 || ok[l] == 3); l2++)
+        if ((ok[l2] == 1 || (grow_inside && ok[l2] == 3)) && R[l].npc >= 0 && R[l2].npc == R[l].npc) ok[l] = 2;
+    int stop;
+    if (grow_inside) {
+      // reads that grow a group stay inside the run; a read that took for granted a bound which an earlier read of the
+      // step moves has to wait
+      for (int l = 1; n + l < hi; l++)
+        for (int l2 = 0; l2 < l && (ok[l] == 1 || ok[l] == 3); l2++)
+          if (ok[l2] == 3 && grows_past(D[l], R[l2])) ok[l] = 2;
+      while (n + k < hi && (ok[k] == 1 || ok[k] == 3)) k++;
+      stop = n + k < hi ? ok[k] : 1;
+    } else {
+      while (n + k < hi && ok[k] == 1) k++;
+      stop = n + k < hi ? ok[k] : 1;              // what ended the run
+      if (stop == 3) k++;                         // a read that grows a group is the run's last read
+    }
 #if defined(STG_FP_COUNT_BAILS)
     stg_fp_bails[0]++;
-    if (stop == 3) stg_fp_bails[60]++; else if (n + k < hi) stg_fp_bails[ok[k] == 2 ? 61 : (why[k] > 0 && why[k] < 60 ? why[k] : 62)]++; else stg_fp_bails[63]++;
+    if (stop == 3 && !grow_inside) stg_fp_bails[60]++; else if (n + k < hi) stg_fp_bails[ok[k] == 2 ? 61 : (why[k] > 0 && why[k] < 60 ? why[k] : 62)]++; else stg_fp_bails[63]++;
 #endif
     int minted = 0;
     for (int l = 0; l < k; l++) { commit_free(S, R[l], n + l, color + minted); minted += R[l].newcol; }

@@ -44,7 +44,7 @@ def _cases():
         yield f"appended{seed}", a
 
 
-@pytest.mark.parametrize("steps", [0, 32, 128])
+@pytest.mark.parametrize("steps", [0, 32, 128, -32, -96])   # < 0: reads that grow a group stay inside the runs
 def test_device_code_on_host_equals_oracle(hostcheck, steps):
     for name, a in _cases():
         pb, keep = orc.make_packed(a)

@@ -90,7 +90,7 @@ extern "C" int hostcheck_groups(const stg_packed_batch* B, uint32_t junctionsupp
     S.junctionsupport = junctionsupport; S.bundledist = bundledist; S.refstart = B->b_start[b]; S.len = len;
     S.c1 = cov.data() + len; S.prm = prm; S.err = 0;
     double nf = 0, fl = 0;
-    if (steps) groups_first_half_steps(S, perm.data(), inv.data(), &nf, &fl, stats, steps);   // the warp's schedule, emulated
+    if (steps) groups_first_half_steps(S, perm.data(), inv.data(), &nf, &fl, stats, steps < 0 ? -steps : steps, steps < 0);   // < 0: growth inside runs   // the warp's schedule, emulated
     else groups_first_half(S, perm.data(), inv.data(), &nf, &fl);
     if (stats) stats[1] += nr;
     int e = 0;

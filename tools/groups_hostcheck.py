@@ -47,10 +47,10 @@ def main():
     for name, a in cases:
         pb, keep = orc.make_packed(a)
         for bd in (50, 0):
-            for steps in (0, 32, 128):
+            for steps in (0, 32, 128, -32, -128):
                 st = (C.c_int64 * 2)(0, 0)
                 r = L.hostcheck_groups(C.byref(pb), 10, 1, bd, 0, int(pb.n_bundles), steps, st)
-                print(f"{name}: bundledist {bd}, {('steps of %d' % steps) if steps else 'sequential'}: {int(pb.n_bundles)} bundles, {r} differ"
+                print(f"{name}: bundledist {bd}, {('steps of %d%s' % (abs(steps), ', growth inside runs' if steps < 0 else '')) if steps else 'sequential'}: {int(pb.n_bundles)} bundles, {r} differ"
                       + (f", {st[0]}/{st[1]} reads simple" if steps else ""))
                 bad += r
     sys.exit(1 if bad else 0)
