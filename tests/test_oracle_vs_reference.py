@@ -182,3 +182,36 @@ def test_stats_counts(golden):
     assert L == int(lens.sum())
     assert J == golden["seg_start"].size - golden["r_start"].size
     assert S > 0
+
+
+def test_reference_graph_dump_is_consistent(golden):
+    """Row a10 groundwork: the splice graphs dumped right after the reference's create_graph (hook before
+    rlink.cpp:15784, arrays a10_*) are structurally sound and line up with the stranded bundles of the a9b dump — the
+    next round pins its create_graph restatement on them."""
+    nb = golden["b_start"].size
+    go = golden["a10_graph_off"].astype(np.int64)
+    bo = golden["a9b_bun_off"].astype(np.int64)
+    assert go.size == nb + 1
+    no, po, co = (golden[k].astype(np.int64) for k in ("a10_node_off", "a10_n_par_off", "a10_n_child_off"))
+    seen_graph = False
+    for b in range(nb):
+        n_neg, n_pos = int(bo[3 * b + 1] - bo[3 * b]), int(bo[3 * b + 3] - bo[3 * b + 2])
+        assert go[b + 1] - go[b] == n_neg + n_pos                       # one record per stranded bundle
+        for g in range(int(go[b]), int(go[b + 1])):
+            gn = int(golden["a10_g_graphno"][g])
+            n0, n1 = int(no[g]), int(no[g + 1])
+            if gn == 0:
+                assert n1 == n0
+                continue
+            seen_graph = True
+            assert n1 - n0 == gn                                        # source, the nodes, sink
+            st, en = golden["a10_n_start"][n0:n1].astype(np.int64), golden["a10_n_end"][n0:n1].astype(np.int64)
+            assert st[0] == 0 and en[0] == 0 and st[-1] == 0 and en[-1] == 0   # source and sink carry no interval
+            ist, ien = st[1:-1], en[1:-1]
+            assert np.all(ist >= golden["b_start"][b]) and np.all(ien <= golden["b_end"][b]) and np.all(ien >= ist)
+            assert np.all(ist[1:] > ien[:-1])                           # nodes in genomic order, disjoint
+            for i in range(n0, n1):                                     # parent / child lists mirror each other
+                for c in golden["a10_n_child"][co[i]:co[i + 1]]:
+                    if 0 <= c < n1 - n0:
+                        assert (i - n0) in golden["a10_n_par"][po[n0 + c]:po[n0 + c + 1]]
+    assert seen_graph
