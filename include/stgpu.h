@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define STG_ABI_VERSION 1
+#define STG_ABI_VERSION 2 /* 2: stg_build_groups, stg_neutral_predictions, stg_find_trims and the groups array fetch */
 #define STG_BSIZE 10000 /* rlink.cpp:11 — block size of the blocked prefix sums in bpcov */
 
 enum {
