@@ -130,8 +130,6 @@ int main(int argc, char** argv) {
     const uint32_t jo = a9_junc_off[b]; const int nj = (int)(a9_junc_off[b + 1] - jo);
     const int r0 = (int)b_read_off[b], nr = (int)(b_read_off[b + 1] - b_read_off[b]);
     // per bundle: the graphs of both strands
-    std::vector<BundleGraphs> BG(1);
-    BundleGraphs& bg = BG[0];
     std::vector<std::vector<uint32_t>> js_s(2), js_e(2), je_e(2); std::vector<std::vector<int32_t>> je_k(2), regn(2), regg(2);
     struct GStore {
       std::vector<uint32_t> n_start, n_end; std::vector<float> n_cov; std::vector<int32_t> ch_off, ch_cnt, ch, pa_off, pa_cnt, pa;
@@ -220,9 +218,168 @@ int main(int argc, char** argv) {
     }
     o_graph_off.push_back((uint32_t)o_gs.size());
     if (stage < 11) continue;
-    (void)ng; (void)r0; (void)nr; (void)g2b_all; (void)negp_all; (void)merge_all; (void)rg_off; (void)rg_all; (void)r_start; (void)r_count;
-    (void)r_nh; (void)r_flags; (void)r_seg_off; (void)r_pair_off; (void)pair_cnt; (void)a9_strand; (void)a9_pair; (void)a9_seg_s; (void)a9_seg_e;
-    (void)a9_rjunc; (void)bg; (void)first_graph;
+    (void)first_graph;
+    // ---- a11: reads -> node coverage + transfrags
+    BundleCtx B; memset(&B, 0, sizeof(B));
+    B.nr = nr; B.ng = ng;
+    B.r_start = r_start + r0; B.r_end = r_end + r0; B.r_nh = r_nh + r0; B.r_flags = r_flags + r0; B.r_count = r_count + r0;
+    B.strand = a9_strand + r0; B.seg_off = r_seg_off + r0; B.seg0 = r_seg_off[r0]; B.seg_s = a9_seg_s + r_seg_off[r0]; B.seg_e = a9_seg_e + r_seg_off[r0];
+    B.pair_off = r_pair_off + r0; B.pair0 = r_pair_off[r0]; B.pair = a9_pair + r_pair_off[r0]; B.pair_cnt = pair_cnt + r_pair_off[r0];
+    B.rj = a9_rjunc + (r_seg_off[r0] - r0);
+    B.j_start = j_start + jo; B.j_end = j_end + jo; B.j_strand = j_strand + jo;
+    B.rg_off = rg_off + r0; B.rg0 = rg_off[r0]; B.rg = rg_all + rg_off[r0];
+    B.merge = merge_all + group_off[b]; B.negp = negp_all + group_off[b]; B.g2b = g2b_all + 3 * (size_t)group_off[b];
+    for (int s = 0; s < 2; s++) { B.bn_graph[s] = bngraph[s].data(); B.bn_first[s] = bnfirst[s].data(); B.bn_cnt[s] = bncnt[s].data(); }
+    B.graphs = graphs.data();
+    std::vector<int32_t> gnode_off(graphs.size() + 1, 0);
+    for (size_t gi = 0; gi < graphs.size(); gi++) gnode_off[gi + 1] = gnode_off[gi] + graphs[gi].gno;
+    std::vector<uint32_t> c_off(nr + 1, 0), t_off(nr + 1, 0), k_off(nr + 1, 0);
+    for (int n = 0; n < nr; n++) {
+      FragCount fc{0, 0, 0};
+      read_fragments(B, n, fc, &err);
+      c_off[n + 1] = c_off[n] + fc.ncov; t_off[n + 1] = t_off[n] + fc.ntf; k_off[n + 1] = k_off[n] + fc.nkey;
+    }
+    int nt0 = 0; for (auto& g : graphs) nt0 += g.gno ? g.ntf0 : 0;
+    const uint32_t NREC = (uint32_t)nt0 + t_off[nr], NKEY = 2u * (uint32_t)nt0 + k_off[nr];
+    std::vector<uint32_t> cov_node(c_off[nr] + 1), rec_koff(NREC + 1), rec_klen(NREC + 1), key(NKEY + 1); std::vector<float> cov_val(c_off[nr] + 1), rec_ab(NREC + 1);
+    std::vector<int32_t> rec_graph(NREC + 1), rec_tf(NREC + 1), tf_rep(NREC + 1), tf_graph(NREC + 1); std::vector<unsigned long long> rec_hash(NREC + 1);
+    std::vector<float> tf_abund(NREC + 1);
+    {  // the transfrags create_graph left, as records in front
+      FragWrite w; memset(&w, 0, sizeof(w));
+      w.graph_node_off = gnode_off.data(); w.cov_node = cov_node.data(); w.cov_val = cov_val.data(); w.tf_graph = rec_graph.data(); w.tf_ab = rec_ab.data();
+      w.tf_key_off = rec_koff.data(); w.tf_key_len = rec_klen.data(); w.tf_hash = rec_hash.data(); w.key = key.data();
+      for (size_t gi = 0; gi < graphs.size(); gi++) if (graphs[gi].gno) for (int t = 0; t < graphs[gi].ntf0; t++) {
+        int32_t nd[2] = {graphs[gi].tf_n1[t], graphs[gi].tf_n2[t]}; uint8_t fl[2] = {0, 1};
+        w.tf((int)gi, nd, fl, 2, graphs[gi].tf_ab[t]);
+      }
+      for (int n = 0; n < nr; n++) {
+        w.icov = c_off[n]; w.itf = (uint32_t)nt0 + t_off[n]; w.ikey = 2u * (uint32_t)nt0 + k_off[n];
+        read_fragments(B, n, w, &err);
+      }
+    }
+    uint32_t cap = 16; while (cap < 2 * NREC + 2) cap <<= 1;
+    std::vector<unsigned long long> slot_hash(cap, 0ull); std::vector<int32_t> slot_id(cap, -1);
+    TfTable T; T.slot_hash = slot_hash.data(); T.slot_id = slot_id.data(); T.cap = cap; T.rec_graph = rec_graph.data(); T.rec_ab = rec_ab.data();
+    T.rec_key_off = rec_koff.data(); T.rec_key_len = rec_klen.data(); T.rec_hash = rec_hash.data(); T.key = key.data(); T.rec_tf = rec_tf.data();
+    T.tf_rep = tf_rep.data(); T.tf_abund = tf_abund.data(); T.tf_graph = tf_graph.data();
+    float stagebuf[32];
+    int ntf = tf_commit_warp(T, 0, (uint32_t)nt0, stagebuf, 0);
+    ntf = tf_commit_warp(T, (uint32_t)nt0, NREC, stagebuf, ntf);
+    std::vector<float> ncov_flat(gnode_off.back() + 1, 0.f);
+    nodecov_commit_warp(cov_node.data(), cov_val.data(), 0, c_off[nr], ncov_flat.data());
+    for (size_t gi = 0; gi < graphs.size(); gi++) for (int i = 0; i < graphs[gi].gno; i++) graphs[gi].n_cov[i] = ncov_flat[gnode_off[gi] + i];
+    // per graph transfrag lists, in order of first appearance
+    std::vector<std::vector<int>> gtf(graphs.size());
+    for (int t = 0; t < ntf; t++) gtf[tf_graph[t]].push_back(t);
+    for (size_t gi = 0; gi < graphs.size(); gi++) {
+      const Graph& g = graphs[gi];
+      for (int i = 0; i < g.gno; i++) q_ncov.push_back(g.n_cov[i]);
+      for (int t : gtf[gi]) {
+        q_tf_ab.push_back(tf_abund[t]);
+        const uint32_t ko = rec_koff[tf_rep[t]], kl = rec_klen[tf_rep[t]];
+        int pc = 0;
+        for (uint32_t x = 0; x < kl; x++) { q_tf_nodes.push_back((int32_t)(key[ko + x] & ~FR_FLAG)); pc += 1 + ((key[ko + x] & FR_FLAG) ? 1 : 0); }
+        q_tf_node_off.push_back((uint32_t)q_tf_nodes.size()); q_tf_pcount.push_back(pc);
+      }
+      q_node_off.push_back((uint32_t)q_ncov.size()); q_tf_off.push_back((uint32_t)q_tf_ab.size());
+    }
+    q_graph_off.push_back((uint32_t)(q_node_off.size() - 1));
+    if (stage < 12) { h_pred_off.push_back((uint32_t)h_start.size()); continue; }
+    // ---- a12: process_transfrags, then a13-a15 per graph, in the reference's processing order
+    const uint32_t* a19_off = arr<uint32_t>(m, "a19_pred_off"); const int32_t* a19_geneno = arr<int32_t>(m, "a19_geneno");
+    int geneno = a19_off[b + 1] > a19_off[b] ? a19_geneno[a19_off[b + 1] - 1] + 1 : 0;
+    for (size_t gi = 0; gi < graphs.size(); gi++) {
+      Graph& g = graphs[gi];
+      if (!g.gno) continue;
+      const int gno = g.gno, nwn = g.nwn;
+      const int nedges = g.ch_off[gno - 1] + g.ch_cnt[gno - 1];
+      const int nt0 = (int)gtf[gi].size();
+      const int cap = nt0 + nedges + 1;
+      std::vector<uint32_t> keyx(key);   // this graph's private copy of the key pool + room for the edge transfrags
+      const uint32_t xkey0 = (uint32_t)keyx.size();
+      keyx.resize(keyx.size() + 2 * (size_t)nedges + 2);
+      std::vector<uint32_t> koff(cap), klen(cap), wkoff(cap), wklen(cap); std::vector<float> ab(cap), wab(cap), path_ab; std::vector<uint8_t> real(cap), ecov(nedges + 1);
+      std::vector<int32_t> usepath(cap), path_off(cap), path_cnt(cap), path_node, path_cont, order(cap), ntrf_off(gno + 1), ntrf_cnt(gno + 1), ntrf;
+      std::vector<unsigned long long> pat((size_t)cap * nwn), skey(cap);
+      int gmax = 1; for (int i = 1; i < gno; i++) if (g.ch_cnt[i] > gmax) gmax = g.ch_cnt[i];
+      int ngap = 0; size_t reach_sum = 0;
+      for (int x = 0; x < nt0; x++) {
+        const int t = gtf[gi][x];
+        wkoff[x] = rec_koff[tf_rep[t]]; wklen[x] = rec_klen[tf_rep[t]]; wab[x] = tf_abund[t];
+        const uint32_t* k = keyx.data() + wkoff[x];
+        bool gap = false;
+        for (uint32_t i = 1; i < wklen[x]; i++) if (!(k[i] & TF_FLAG)) gap = true;
+        if (gap) ngap++;
+        reach_sum += (k[wklen[x] - 1] & ~TF_FLAG) - (k[0] & ~TF_FLAG) + 1;
+      }
+      path_ab.resize((size_t)ngap * gmax + 1); path_node.resize((size_t)ngap * gmax + 1); path_cont.resize((size_t)ngap * gmax + 1);
+      ntrf.resize(reach_sum + 2 * (size_t)nedges + 2);
+      TfG f; memset(&f, 0, sizeof(f));
+      f.nt = nt0; f.cap = cap; f.koff = koff.data(); f.klen = klen.data(); f.key = keyx.data(); f.xkey0 = xkey0; f.ab = ab.data(); f.real = real.data();
+      f.usepath = usepath.data(); f.path_off = path_off.data(); f.path_cnt = path_cnt.data(); f.path_node = path_node.data(); f.path_cont = path_cont.data();
+      f.path_ab = path_ab.data(); f.path_cap = ngap * gmax; f.pat = pat.data(); f.ntrf_off = ntrf_off.data(); f.ntrf_cnt = ntrf_cnt.data(); f.ntrf = ntrf.data();
+      f.ntrf_cap = (int)ntrf.size(); f.order = order.data(); f.w_koff = wkoff.data(); f.w_klen = wklen.data(); f.w_ab = wab.data(); f.skey = skey.data();
+      f.e_cov = ecov.data();
+      const int nt = process_transfrags_warp(g, f, &err);
+      f.nt = nt;
+      w_gs.push_back((int8_t)g_s[gi]); w_gb.push_back(g_b[gi]);
+      for (int t = 0; t < nt; t++) {
+        w_tf_ab.push_back(f.ab[t]); w_tf_real.push_back(f.real[t]);
+        for (uint32_t i = 0; i < f.klen[t]; i++) w_tf_nodes.push_back(tf_node(f, t, (int)i));
+        w_tf_node_off.push_back((uint32_t)w_tf_nodes.size());
+        for (int x = 0; x < f.path_cnt[t]; x++) {
+          w_path_node.push_back(f.path_node[f.path_off[t] + x]); w_path_cont.push_back(f.path_cont[f.path_off[t] + x]); w_path_ab.push_back(f.path_ab[f.path_off[t] + x]);
+        }
+        w_path_off.push_back((uint32_t)w_path_node.size());
+      }
+      w_tf_off.push_back((uint32_t)w_tf_ab.size());
+      for (int i = 0; i < gno; i++) {
+        for (int x = 0; x < f.ntrf_cnt[i]; x++) w_ntrf.push_back(f.ntrf[f.ntrf_off[i] + x]);
+        w_ntrf_off.push_back((uint32_t)w_ntrf.size());
+      }
+      w_node_off.push_back((uint32_t)w_ntrf_off.size() - 1);
+      if (stage < 15) continue;
+      // ---- a13-a15
+      std::vector<float> nodecov(gno), capl(gno + 1), capr(gno + 1), suml(gno + 1), sumr(gno + 1), nodeflux(gno + 1), ex_c(gno + 1);
+      std::vector<int32_t> pathv(gno + 2), succ(gno), node2path(gno); std::vector<unsigned long long> pathpat(nwn), istr((cap + 63) / 64 + 1);
+      std::vector<uint8_t> used(gno), prevn(gno), preve(nedges + 1); std::vector<uint32_t> ex_s(gno + 1), ex_e(gno + 1);
+      FlowScratch S; memset(&S, 0, sizeof(S));
+      S.nodecov = nodecov.data(); S.path = pathv.data(); S.succ = succ.data(); S.pathpat = pathpat.data(); S.istr = istr.data(); S.usednode = used.data();
+      S.prev_node = prevn.data(); S.prev_edge = preve.data(); S.node2path = node2path.data(); S.capl = capl.data(); S.capr = capr.data(); S.suml = suml.data();
+      S.sumr = sumr.data(); S.nodeflux = nodeflux.data();
+      const uint32_t PC = 4096, EC = 65536;
+      std::vector<int32_t> pg(PC), ps(PC), ptl(PC); std::vector<uint32_t> pst(PC), pen(PC), pe0(PC), pnx(PC), est(EC), een(EC); std::vector<double> pcv(PC);
+      std::vector<float> ecv(EC); uint32_t ctr[2] = {0, 0};
+      PredOut po; po.counters = ctr; po.cap_pred = PC; po.cap_exon = EC; po.p_graph = pg.data(); po.p_seq = ps.data(); po.p_start = pst.data(); po.p_end = pen.data();
+      po.p_cov = pcv.data(); po.p_tlen = ptl.data(); po.p_exon0 = pe0.data(); po.p_nex = pnx.data(); po.e_start = est.data(); po.e_end = een.data(); po.e_cov = ecv.data();
+      const int ns = find_transcripts_warp(g, f, S, P, po, (int)gi, ex_s.data(), ex_e.data(), ex_c.data(), &err);
+      if (ns) geneno++;
+      for (uint32_t x = 0; x < ctr[0]; x++) {
+        h_start.push_back((int32_t)pst[x]); h_end.push_back((int32_t)pen[x]); h_cov.push_back(pcv[x]); h_tlen.push_back(ptl[x]); h_geneno.push_back(geneno - 1);
+        h_strand.push_back((int8_t)(g_s[gi] ? '+' : '-'));
+        for (uint32_t e = 0; e < pnx[x]; e++) { h_es.push_back(est[pe0[x] + e]); h_ee.push_back(een[pe0[x] + e]); h_ecov.push_back(ecv[pe0[x] + e]); }
+        h_exon_off.push_back((uint32_t)h_es.size());
+      }
+    }
+    w_graph_off.push_back((uint32_t)w_gs.size());
+    h_pred_off.push_back((uint32_t)h_start.size());
+  }
+  if (stage >= 12) {
+    out.add("a12_graph_off", STG_DT_U32, w_graph_off); out.add("a12_g_strand", STG_DT_I8, w_gs); out.add("a12_g_bundle", STG_DT_I32, w_gb);
+    out.add("a12_tf_off", STG_DT_U32, w_tf_off); out.add("a12_tf_abund", STG_DT_F32, w_tf_ab); out.add("a12_tf_real", STG_DT_U8, w_tf_real);
+    out.add("a12_tf_node_off", STG_DT_U32, w_tf_node_off); out.add("a12_tf_nodes", STG_DT_I32, w_tf_nodes); out.add("a12_tf_path_off", STG_DT_U32, w_path_off);
+    out.add("a12_tf_path_node", STG_DT_I32, w_path_node); out.add("a12_tf_path_cont", STG_DT_I32, w_path_cont); out.add("a12_tf_path_ab", STG_DT_F32, w_path_ab);
+    out.add("a12_node_off", STG_DT_U32, w_node_off); out.add("a12_ntrf_off", STG_DT_U32, w_ntrf_off); out.add("a12_ntrf", STG_DT_I32, w_ntrf);
+  }
+  if (stage >= 15) {
+    out.add("hp_pred_off", STG_DT_U32, h_pred_off); out.add("hp_start", STG_DT_I32, h_start); out.add("hp_end", STG_DT_I32, h_end); out.add("hp_cov", STG_DT_F64, h_cov);
+    out.add("hp_tlen", STG_DT_I32, h_tlen); out.add("hp_geneno", STG_DT_I32, h_geneno); out.add("hp_strand", STG_DT_I8, h_strand);
+    out.add("hp_exon_off", STG_DT_U32, h_exon_off); out.add("hp_es", STG_DT_U32, h_es); out.add("hp_ee", STG_DT_U32, h_ee); out.add("hp_ecov", STG_DT_F32, h_ecov);
+  }
+  if (stage >= 11) {
+    out.add("a11_graph_off", STG_DT_U32, q_graph_off); out.add("a11_node_off", STG_DT_U32, q_node_off); out.add("a11_n_cov", STG_DT_F32, q_ncov);
+    out.add("a11_tf_off", STG_DT_U32, q_tf_off); out.add("a11_tf_abund", STG_DT_F32, q_tf_ab); out.add("a11_tf_node_off", STG_DT_U32, q_tf_node_off);
+    out.add("a11_tf_nodes", STG_DT_I32, q_tf_nodes); out.add("a11_tf_pcount", STG_DT_I32, q_tf_pcount);
   }
   out.add("a10_graph_off", STG_DT_U32, o_graph_off); out.add("a10_g_strand", STG_DT_I8, o_gs); out.add("a10_g_bundle", STG_DT_I32, o_gb);
   out.add("a10_g_graphno", STG_DT_I32, o_gno); out.add("a10_g_edgeno", STG_DT_I32, o_edgeno); out.add("a10_node_off", STG_DT_U32, o_node_off);
