@@ -251,6 +251,35 @@ int stg_fetch_groups_array(stg_ctx* ctx, const stg_dbatch* batch, int which, int
  * f64 (CPrediction::cov; exoncov[0] is its float), NP_TLEN i32, NP_GENENO i32 (as stored: the bundle's gene counter). */
 int stg_neutral_predictions(stg_ctx* ctx, stg_dbatch* batch);
 
+/* ---- rows a10-a15: splice graphs, read -> transfrag mapping, flow decomposition, predictions --------------------------
+ * stg_assemble runs, for every stranded CBundle of a batch whose groups are built and whose neutral predictions are made,
+ *   create_graph (with trimnode_all, the coverage-drop links, traverse_dfs)          rlink.cpp:3579-4351, 2809, 2874
+ *   get_fragment_pattern / get_read_pattern / update_abundance for every fragment   rlink.cpp:15796-15820, 4870, 4354, 4680
+ *   process_transfrags (threshold, edge transfrags, trCmp sort, trf_real)            rlink.cpp:5768-6910
+ *   find_transcripts / parse_trf / back_to_source_fast / fwd_to_sink_fast / push_max_flow / store_transcript
+ *                                                                                    rlink.cpp:13633, 11992, 8651, 8483, 9075, 9688
+ * on the device, i.e. the rest of build_graphs (rlink.cpp:15637-15935) on the short-read de novo path, and leaves the
+ * CPrediction list of every bundle there.  Returns STG_EUNSUPPORTED with guides, -e, -L, --mix, -N / --nasc, --viral,
+ * --ptf or rawreads set, or when the batch carries unitigs (super-reads); STG_ERANGE when a graph exceeds allowed_nodes
+ * (prune_graph_nodes, rlink.cpp:3270, is not built) or a read spans more graph nodes than the kernels allow.
+ * Results through stg_fetch_asm_array (batch-wide arrays):
+ *   PRED_OFF u32[n_bundles+1]: bundle b owns predictions [PRED_OFF[b], PRED_OFF[b+1]) in the reference's order; they
+ *     follow the bundle's neutral predictions (stg_neutral_predictions) in BundleData::pred
+ *   P_START / P_END u32 (CPrediction::start / end), P_COV f64, P_TLEN i32, P_GENENO i32, P_STRAND i8 ('+' / '-'),
+ *   P_EXON_OFF u32[n_pred+1] -> E_START / E_END u32 (CPrediction::exons), E_COV f32 (exoncov)
+ *   stage views for tests: G_BUNDLE i32 / G_STRAND i8 / G_K i32 [n_graphs] (candidate graphs: input bundle, strand 0 '-' 1
+ *   '+', CBundle index in its lane), G_NODE_OFF u32[n_graphs+1] (graphno = difference; 0: graph not built) -> N_START /
+ *   N_END u32, N_COV f32 (CGraphnode incl. source and sink), G_NTF u32[n_graphs] (transfrags before process_transfrags) */
+enum stg_asm_array {
+  STG_AA_PRED_OFF = 0, STG_AA_P_START, STG_AA_P_END, STG_AA_P_COV, STG_AA_P_TLEN, STG_AA_P_GENENO, STG_AA_P_STRAND,
+  STG_AA_P_EXON_OFF, STG_AA_E_START, STG_AA_E_END, STG_AA_E_COV,
+  STG_AA_G_BUNDLE, STG_AA_G_STRAND, STG_AA_G_K, STG_AA_G_NODE_OFF, STG_AA_N_START, STG_AA_N_END, STG_AA_N_COV, STG_AA_G_NTF,
+  STG_AA_COUNT
+};
+int stg_assemble(stg_ctx* ctx, stg_dbatch* batch);
+int stg_asm_array_info(const stg_dbatch* batch, int which, int64_t* count, int32_t* elem_bytes);
+int stg_fetch_asm_array(stg_ctx* ctx, const stg_dbatch* batch, int which, int64_t first, int64_t count, void* out);
+
 /* find_all_trims (rlink.cpp:2118-2419, part of row a10; one of the bpcov range-query consumers): for n regions
  * (bundle[i], sno[i] in {0, 2} as at the call sites rlink.cpp:2813 / 15559, genomic start[i]..end[i]) of a batch that
  * has been run, the reference's `trimpoint` vector of each region: candidate source / sink trim positions with their

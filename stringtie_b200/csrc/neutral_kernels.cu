@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(128) neutral_preds_kernel(DevBatchView v, Grou
     if (len > nv.mintranscriptlen) emit(predstart, ne, len);
   }
   nv.pred_off[b] = np;
+  nv.b_geneno[b] = geneno;
   if (b == 0) nv.pred_off[v.n_bundles] = 0;
 }
 

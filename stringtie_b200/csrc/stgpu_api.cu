@@ -1,6 +1,7 @@
 // stgpu_api.cu — host side of libstgpu: the C ABI of include/stgpu.h, the bundle batcher, HBM layout planning,
 // kernel sequencing and result fetch.  No CPU compute path exists here: without a CUDA device stg_init fails.
 #include "stgpu_internal.h"
+#include "asm_device.cuh"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -121,6 +122,8 @@ struct stg_dbatch {
   NeutralView nv;                  // row a19 (stg_neutral_predictions)
   bool neutral_done = false;
   std::vector<uint32_t> h_nreads;  // [n_bundles]
+  AsmView av;                      // rows a10-a15 (stg_assemble)
+  bool assembled = false;
 };
 
 namespace {
@@ -903,6 +906,7 @@ int stg_neutral_predictions(stg_ctx* ctx, stg_dbatch* d) {
   const int64_t pcap = (int64_t)tcap + n.n_regions + 1;
   TEMP(n.p_start, pcap); TEMP(n.p_end, pcap); TEMP(n.p_cov, pcap); TEMP(n.p_tlen, pcap); TEMP(n.p_geneno, pcap);
   KEEP(n.pred_off, nb + 1 + 16);
+  KEEP(n.b_geneno, nb);
   CK(ctx, cudaMemsetAsync(n.pred_off, 0, sizeof(uint32_t) * (nb + 1), st));
   { Scope s(ctx, "neutral_preds", 3);
     CK(ctx, launch_neutral_preds(v, g, n, st));
@@ -1004,6 +1008,229 @@ int stg_fetch_groups_array(stg_ctx* ctx, const stg_dbatch* d, int which, int64_t
   const GArr a = groups_array(d, which);
   if (a.n < 0) return fail(ctx, STG_EINVAL, "stg_fetch_groups_array: unknown array");
   if (first < 0 || count < 0 || first + count > a.n || (count && !out)) return fail(ctx, STG_EINVAL, "stg_fetch_groups_array: bad range");
+  if (count == 0) return STG_OK;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaMemcpyAsync(out, (const char*)a.p + (size_t)first * a.sz, (size_t)count * a.sz, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return STG_OK;
+}
+
+// ---- rows a10-a15 -----------------------------------------------------------------------------------------------
+int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
+  if (!ctx || !d) return fail(ctx, STG_EINVAL, "stg_assemble: null argument");
+  if (!d->groups_built || !d->neutral_done) return fail(ctx, STG_EINVAL, "stg_assemble: needs stg_build_groups and stg_neutral_predictions");
+  if (d->assembled) return fail(ctx, STG_EINVAL, "stg_assemble: already done for this batch");
+  const stg_params& pr = ctx->params;
+  if (pr.guided || pr.eonly || pr.longreads || pr.mixedMode || pr.isnascent || pr.printNascent || pr.viral || pr.rawreads || pr.havePtFeatures)
+    return fail(ctx, STG_EUNSUPPORTED, "stg_assemble: only the short-read de novo path is implemented");
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevBatchView& v = d->v;
+  GroupsView& g = d->gv;
+  AsmView& A = d->av;
+  memset(&A, 0, sizeof(A));
+  AsmParams P;
+  P.junctionsupport = pr.junctionsupport; P.trim = pr.trim; P.mcov = pr.mcov; P.mintranscriptlen = pr.mintranscriptlen;
+  P.allowed_nodes = pr.allowed_nodes; P.isofrac = pr.isofrac; P.includesource = pr.includesource;
+  const int64_t nb = v.n_bundles, nr = v.n_reads, NG = g.n_groups;
+  int rc = STG_OK;
+  stg_dbatch tmp;   // scratch of this call
+  struct Release { stg_ctx* c; stg_dbatch* t; ~Release() { free_batch_allocs(c, t); } } release{ctx, &tmp};
+#define KEEP(ptr, count) do { if ((rc = dev_alloc(ctx, d, &(ptr), (int64_t)(count)))) return rc; } while (0)
+#define TEMP(ptr, count) do { if ((rc = dev_alloc(ctx, &tmp, &(ptr), (int64_t)(count)))) return rc; } while (0)
+#define ZERO(ptr, count) CK(ctx, cudaMemsetAsync((ptr), 0, sizeof(*(ptr)) * (size_t)std::max<int64_t>((count), 1), st))
+#define ONES(ptr, count) CK(ctx, cudaMemsetAsync((ptr), 0xff, sizeof(*(ptr)) * (size_t)std::max<int64_t>((count), 1), st))
+#define SCAN(ptr, n1) CK(ctx, launch_scan_exclusive_add((ptr), (n1), scan_state, ticket, st))
+#define TOTAL(dst, ptr, n) CK(ctx, cudaMemcpyAsync(&(dst), (ptr) + (n), 4, cudaMemcpyDeviceToHost, st))
+  // graph ids and the rows of the junction table, from the per-bundle counts of rows a8 + a9
+  std::vector<uint32_t> h_nbun((size_t)3 * nb + 1), h_napp((size_t)nb + 1), h_joff((size_t)nb + 1);
+  if (nb) {
+    CK(ctx, cudaMemcpyAsync(h_nbun.data(), g.b_nbun, sizeof(uint32_t) * 3 * nb, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemcpyAsync(h_joff.data(), v.b_junc_off, sizeof(uint32_t) * (nb + 1), cudaMemcpyDeviceToHost, st));
+  }
+  CK(ctx, cudaMemcpyAsync(h_napp.data(), g.b_napp, sizeof(uint32_t) * (nb + 1), cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  std::vector<uint32_t> h_first((size_t)2 * nb + 1), h_jrow((size_t)nb + 1);
+  uint32_t G = 0;
+  for (int64_t b = 0; b < nb; b++) {
+    h_first[2 * b] = G; G += h_nbun[3 * b];
+    h_first[2 * b + 1] = G; G += h_nbun[3 * b + 2];
+    h_jrow[b] = h_joff[b] + h_napp[b];
+  }
+  h_first[2 * nb] = G;
+  h_jrow[nb] = (nb ? h_joff[nb] : 0) + h_napp[nb];
+  A.n_graphs = G; A.n_junc_rows = h_jrow[nb];
+  const int64_t NJ = A.n_junc_rows;
+  uint32_t *d_first = nullptr, *d_jrow = nullptr;
+  KEEP(d_first, 2 * nb + 1); KEEP(d_jrow, nb + 1);
+  CK(ctx, cudaMemcpyAsync(d_first, h_first.data(), sizeof(uint32_t) * (2 * nb + 1), cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(d_jrow, h_jrow.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
+  A.gr_first = d_first; A.jrow_off = d_jrow;
+  unsigned long long* scan_state = nullptr; uint32_t* ticket = nullptr;
+  TEMP(ticket, 1);
+  TEMP(scan_state, std::max<int64_t>(std::max<int64_t>(nr, nb), (int64_t)G) / 2048 + 8);
+  KEEP(A.g_bundle, G); KEEP(A.g_k, G); KEEP(A.g_s, G);
+  TEMP(A.js_start, 2 * NJ); TEMP(A.js_end, 2 * NJ); TEMP(A.je_end, 2 * NJ); TEMP(A.je_k, 2 * NJ); TEMP(A.reg_node, 2 * NJ); TEMP(A.reg_graph, 2 * NJ);
+  TEMP(A.jl_cnt, 2 * nb);
+  TEMP(A.cap_n, (int64_t)G + 1 + 16); TEMP(A.cap_e, (int64_t)G + 1 + 16); TEMP(A.cap_f, (int64_t)G + 1 + 16); TEMP(A.cap_t, (int64_t)G + 1 + 16);
+  TEMP(A.sw_nn, G); TEMP(A.sw_ne, G); TEMP(A.sw_nf, G); TEMP(A.sw_edgeno, G);
+  KEEP(A.bn_first, 3 * NG); KEEP(A.bn_cnt, 3 * NG); KEEP(A.bn_graph, 3 * NG);
+  ONES(A.reg_node, 2 * NJ); ONES(A.reg_graph, 2 * NJ); ONES(A.bn_first, 3 * NG); ONES(A.bn_graph, 3 * NG); ZERO(A.bn_cnt, 3 * NG);
+  CK(ctx, cudaMemsetAsync(v.err_flag, 0, sizeof(uint32_t), st));
+  uint32_t tn = 0, te = 0, tf = 0, tt = 0, err = 0;
+  { Scope s(ctx, "asm_lists+bounds", 7);
+    CK(ctx, launch_asm_enum(v, A, st));
+    CK(ctx, launch_asm_junc_lists(v, g, A, st));
+    CK(ctx, launch_asm_bounds(v, g, A, P, st));
+    SCAN(A.cap_n, (int64_t)G + 1); SCAN(A.cap_e, (int64_t)G + 1); SCAN(A.cap_f, (int64_t)G + 1); SCAN(A.cap_t, (int64_t)G + 1); }
+  TOTAL(tn, A.cap_n, G); TOTAL(te, A.cap_e, G); TOTAL(tf, A.cap_f, G); TOTAL(tt, A.cap_t, G);
+  CK(ctx, cudaStreamSynchronize(st));
+  TEMP(A.t_nstart, tn); TEMP(A.t_nend, tn); TEMP(A.t_evu, te); TEMP(A.t_evv, te); TEMP(A.t_ft1, tf); TEMP(A.t_ft2, tf); TEMP(A.t_ftab, tf);
+  TEMP(A.t_trpos, tt); TEMP(A.t_trab, tt); TEMP(A.t_trst, tt);
+  KEEP(A.x_node, (int64_t)G + 1 + 16); KEEP(A.x_edge, (int64_t)G + 1 + 16); TEMP(A.x_tf0, (int64_t)G + 1 + 16); KEEP(A.x_reach, (int64_t)G + 1 + 16);
+  { Scope s(ctx, "asm_sweep", 6);
+    CK(ctx, launch_asm_sweep(v, g, A, P, st));
+    CK(ctx, launch_asm_sizes(A, st));
+    SCAN(A.x_node, (int64_t)G + 1); SCAN(A.x_edge, (int64_t)G + 1); SCAN(A.x_tf0, (int64_t)G + 1); SCAN(A.x_reach, (int64_t)G + 1); }
+  uint32_t xn = 0, xe = 0, xt = 0, xr = 0;
+  TOTAL(xn, A.x_node, G); TOTAL(xe, A.x_edge, G); TOTAL(xt, A.x_tf0, G); TOTAL(xr, A.x_reach, G);
+  CK(ctx, cudaMemcpyAsync(&err, v.err_flag, 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  if (err) return fail(ctx, STG_ERANGE, "stg_assemble: a graph exceeded the capacity bound of its sweep");
+  A.n_nodes = xn; A.n_edges = xe; A.n_tf0cap = xt; A.n_reach = xr;
+  const int64_t NN = (int64_t)xn + 2 * (int64_t)G + 2;   // per-node scratch: gno + 2 entries per graph
+  { void* gp = nullptr; uint8_t* raw = nullptr; KEEP(raw, (int64_t)asm_graph_struct_bytes() * std::max<int64_t>(G, 1)); gp = raw; A.graphs = (Graph*)gp; }
+  KEEP(A.n_start, xn); KEEP(A.n_end, xn); KEEP(A.n_cov, xn); KEEP(A.ch_off, xn); KEEP(A.ch_cnt, xn); KEEP(A.ch, xe); KEEP(A.pa_off, xn);
+  KEEP(A.pa_cnt, xn); KEEP(A.pa, xe); KEEP(A.n_sinkpar, xn); KEEP(A.reach, xr); TEMP(A.tf_n1, xt); TEMP(A.tf_n2, xt); TEMP(A.tf_ab, xt);
+  TEMP(A.fin_stack, 2 * NN); TEMP(A.fin_ncs, NN); TEMP(A.fin_visit, NN);
+  KEEP(A.tf0_off, (int64_t)G + 1 + 16); KEEP(A.g_node_off, G);
+  KEEP(A.r_ncov, nr + 1 + 16); KEEP(A.r_ntf, nr + 1 + 16); TEMP(A.r_nkey, nr + 1 + 16);
+  { Scope s(ctx, "asm_finish+frag_count", 6);
+    CK(ctx, launch_asm_finish(v, g, A, P, st));
+    SCAN(A.tf0_off, (int64_t)G + 1);
+    CK(ctx, launch_asm_frag_count(v, g, A, st));
+    SCAN(A.r_ncov, nr + 1); SCAN(A.r_ntf, nr + 1); SCAN(A.r_nkey, nr + 1); }
+  uint32_t t0 = 0, tc = 0, tr = 0, tk = 0;
+  TOTAL(t0, A.tf0_off, G); TOTAL(tc, A.r_ncov, nr); TOTAL(tr, A.r_ntf, nr); TOTAL(tk, A.r_nkey, nr);
+  CK(ctx, cudaMemcpyAsync(&err, v.err_flag, 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  if (err & 0x800u) return fail(ctx, STG_EUNSUPPORTED, "stg_assemble: the batch carries unitigs (super-reads), which are not supported");
+  if (err & 0x400u) return fail(ctx, STG_ERANGE, "stg_assemble: a graph has more than allowed_nodes nodes (prune_graph_nodes is not built)");
+  if (err) return fail(ctx, STG_ERANGE, "stg_assemble: a read spans more graph nodes than the kernels allow");
+  A.n_tf0 = t0; A.n_covrec = tc; A.n_rec = tr; A.n_key = tk;
+  const int64_t NR = (int64_t)t0 + tr;
+  A.xkey_base = 2 * t0 + tk;
+  TEMP(A.cov_node, tc); TEMP(A.cov_val, tc);
+  TEMP(A.rec_graph, NR); TEMP(A.rec_ab, NR); TEMP(A.rec_koff, NR); TEMP(A.rec_klen, NR); TEMP(A.rec_hash, NR); TEMP(A.rec_tf, NR);
+  TEMP(A.key, (int64_t)A.xkey_base + 2 * (int64_t)xe + 2 * (int64_t)G + 16);
+  TEMP(A.tab_off, nb + 1 + 16);
+  { Scope s(ctx, "asm_frag_write", 4);
+    CK(ctx, launch_asm_frag_write(v, g, A, st));
+    CK(ctx, launch_asm_table_caps(v, A, st));
+    SCAN(A.tab_off, nb + 1); }
+  uint32_t ts = 0;
+  TOTAL(ts, A.tab_off, nb);
+  CK(ctx, cudaStreamSynchronize(st));
+  TEMP(A.slot_hash, ts); TEMP(A.slot_id, ts);
+  ZERO(A.slot_hash, ts);
+  TEMP(A.tf_rep, NR); TEMP(A.tf_abund, NR); TEMP(A.tf_graph, NR); TEMP(A.b_ntf, nb);
+  KEEP(A.g_nt, G); TEMP(A.g_ngap, G); TEMP(A.g_reachsum, G); TEMP(A.g_fill, G);
+  ZERO(A.g_nt, G); ZERO(A.g_ngap, G); ZERO(A.g_reachsum, G); ZERO(A.g_fill, G);
+  TEMP(A.y_tf, (int64_t)G + 1 + 16); TEMP(A.y_pat, (int64_t)G + 1 + 16); TEMP(A.y_path, (int64_t)G + 1 + 16); TEMP(A.y_ntrf, (int64_t)G + 1 + 16);
+  TEMP(A.y_istr, (int64_t)G + 1 + 16);
+  { Scope s(ctx, "asm_commit", 9);
+    CK(ctx, launch_asm_commit(v, A, st));
+    SCAN(A.y_tf, (int64_t)G + 1); SCAN(A.y_pat, (int64_t)G + 1); SCAN(A.y_path, (int64_t)G + 1); SCAN(A.y_ntrf, (int64_t)G + 1); SCAN(A.y_istr, (int64_t)G + 1); }
+  uint32_t yt = 0, yp = 0, yh = 0, yn = 0, yi = 0;
+  TOTAL(yt, A.y_tf, G); TOTAL(yp, A.y_pat, G); TOTAL(yh, A.y_path, G); TOTAL(yn, A.y_ntrf, G); TOTAL(yi, A.y_istr, G);
+  CK(ctx, cudaStreamSynchronize(st));
+  A.n_ytf = yt; A.n_ypat = yp; A.n_ypath = yh; A.n_yntrf = yn; A.n_yistr = yi;
+  TEMP(A.f_koff, yt); TEMP(A.f_klen, yt); TEMP(A.f_wkoff, yt); TEMP(A.f_wklen, yt); TEMP(A.f_ab, yt); TEMP(A.f_wab, yt); TEMP(A.f_real, yt);
+  TEMP(A.f_usepath, yt); TEMP(A.f_path_off, yt); TEMP(A.f_path_cnt, yt); TEMP(A.f_order, yt); TEMP(A.f_pat, yp); TEMP(A.f_skey, yt);
+  TEMP(A.f_path_node, yh); TEMP(A.f_path_cont, yh); TEMP(A.f_path_ab, yh); TEMP(A.f_ntrf_off, NN); TEMP(A.f_ntrf_cnt, NN); TEMP(A.f_ntrf, yn);
+  TEMP(A.f_ecov, xe);
+  TEMP(A.s_nodecov, NN); TEMP(A.s_capl, NN); TEMP(A.s_capr, NN); TEMP(A.s_suml, NN); TEMP(A.s_sumr, NN); TEMP(A.s_flux, NN); TEMP(A.s_exc, NN);
+  TEMP(A.s_path, NN); TEMP(A.s_succ, NN); TEMP(A.s_n2p, NN); TEMP(A.s_exs, NN); TEMP(A.s_exe, NN); TEMP(A.s_pathpat, NN); TEMP(A.s_istr, yi);
+  TEMP(A.s_used, NN); TEMP(A.s_prevn, NN); TEMP(A.s_preve, xe);
+  A.cap_pred = yt + xn + 16; A.cap_exon = 8 * A.cap_pred + 1024;
+  TEMP(A.p_counters, 2); ZERO(A.p_counters, 2);
+  TEMP(A.pp_graph, A.cap_pred); TEMP(A.pp_seq, A.cap_pred); TEMP(A.pp_tlen, A.cap_pred); TEMP(A.pp_start, A.cap_pred); TEMP(A.pp_end, A.cap_pred);
+  TEMP(A.pp_exon0, A.cap_pred); TEMP(A.pp_nex, A.cap_pred); TEMP(A.pp_cov, A.cap_pred);
+  TEMP(A.pe_start, A.cap_exon); TEMP(A.pe_end, A.cap_exon); TEMP(A.pe_cov, A.cap_exon);
+  KEEP(A.g_npred, (int64_t)G + 1 + 16); KEEP(A.g_geneno, G); KEEP(A.o_pred_off, nb + 1);
+  { Scope s(ctx, "asm_gather", 1); CK(ctx, launch_asm_gather(v, A, st)); }
+  { Scope s(ctx, "asm_flow", 1); CK(ctx, launch_asm_flow(v, A, P, st)); }
+  uint32_t ctr[2] = {0, 0};
+  CK(ctx, cudaMemcpyAsync(ctr, A.p_counters, 8, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaMemcpyAsync(&err, v.err_flag, 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  if (err) return fail(ctx, STG_ERANGE, "stg_assemble: a capacity bound of the flow stage was exceeded");
+  A.n_pred = ctr[0]; A.n_exon = ctr[1];
+  const int64_t NP = A.n_pred;
+  KEEP(A.o_start, NP); KEEP(A.o_end, NP); KEEP(A.o_exon_off, NP + 1 + 16); KEEP(A.o_cov, NP); KEEP(A.o_tlen, NP); KEEP(A.o_geneno, NP);
+  TEMP(A.o_src, NP); KEEP(A.o_strand, NP); KEEP(A.oe_start, A.n_exon); KEEP(A.oe_end, A.n_exon); KEEP(A.oe_cov, A.n_exon);
+  unsigned long long* scan_state2 = nullptr;
+  TEMP(scan_state2, NP / 2048 + 8);
+  { Scope s(ctx, "asm_predictions", 5);
+    SCAN(A.g_npred, (int64_t)G + 1);
+    CK(ctx, launch_asm_geneno(v, A, d->nv.b_geneno, st));
+    CK(ctx, launch_asm_pred_scatter(A, (uint32_t)NP, st));
+    CK(ctx, launch_scan_exclusive_add(A.o_exon_off, NP + 1, scan_state2, ticket, st));
+    CK(ctx, launch_asm_exon_scatter(A, (uint32_t)NP, st)); }
+  CK(ctx, cudaStreamSynchronize(st));
+#undef KEEP
+#undef TEMP
+#undef ZERO
+#undef ONES
+#undef SCAN
+#undef TOTAL
+  d->assembled = true;
+  return STG_OK;
+}
+
+namespace {
+GArr asm_array(const stg_dbatch* d, int which) {
+  const AsmView& A = d->av;
+  const int64_t nb = d->v.n_bundles, G = A.n_graphs, NP = A.n_pred;
+  switch (which) {
+    case STG_AA_PRED_OFF: return {A.o_pred_off, nb + 1, 4};
+    case STG_AA_P_START: return {A.o_start, NP, 4};
+    case STG_AA_P_END: return {A.o_end, NP, 4};
+    case STG_AA_P_COV: return {A.o_cov, NP, 8};
+    case STG_AA_P_TLEN: return {A.o_tlen, NP, 4};
+    case STG_AA_P_GENENO: return {A.o_geneno, NP, 4};
+    case STG_AA_P_STRAND: return {A.o_strand, NP, 1};
+    case STG_AA_P_EXON_OFF: return {A.o_exon_off, NP + 1, 4};
+    case STG_AA_E_START: return {A.oe_start, A.n_exon, 4};
+    case STG_AA_E_END: return {A.oe_end, A.n_exon, 4};
+    case STG_AA_E_COV: return {A.oe_cov, A.n_exon, 4};
+    case STG_AA_G_BUNDLE: return {A.g_bundle, G, 4};
+    case STG_AA_G_STRAND: return {A.g_s, G, 1};
+    case STG_AA_G_K: return {A.g_k, G, 4};
+    case STG_AA_G_NODE_OFF: return {A.x_node, G + 1, 4};
+    case STG_AA_N_START: return {A.n_start, A.n_nodes, 4};
+    case STG_AA_N_END: return {A.n_end, A.n_nodes, 4};
+    case STG_AA_N_COV: return {A.n_cov, A.n_nodes, 4};
+    case STG_AA_G_NTF: return {A.g_nt, G, 4};
+  }
+  return {nullptr, -1, 0};
+}
+}  // namespace
+
+int stg_asm_array_info(const stg_dbatch* d, int which, int64_t* count, int32_t* elem_bytes) {
+  if (!d || !d->assembled) return fail(nullptr, STG_EINVAL, "stg_asm_array_info: batch is not assembled");
+  const GArr a = asm_array(d, which);
+  if (a.n < 0) return fail(nullptr, STG_EINVAL, "stg_asm_array_info: unknown array");
+  if (count) *count = a.n;
+  if (elem_bytes) *elem_bytes = a.sz;
+  return STG_OK;
+}
+
+int stg_fetch_asm_array(stg_ctx* ctx, const stg_dbatch* d, int which, int64_t first, int64_t count, void* out) {
+  if (!ctx || !d || !d->assembled) return fail(ctx, STG_EINVAL, "stg_fetch_asm_array: batch is not assembled");
+  const GArr a = asm_array(d, which);
+  if (a.n < 0) return fail(ctx, STG_EINVAL, "stg_fetch_asm_array: unknown array");
+  if (first < 0 || count < 0 || first + count > a.n || (count && !out)) return fail(ctx, STG_EINVAL, "stg_fetch_asm_array: bad range");
   if (count == 0) return STG_OK;
   CK(ctx, cudaSetDevice(ctx->device));
   CK(ctx, cudaMemcpyAsync(out, (const char*)a.p + (size_t)first * a.sz, (size_t)count * a.sz, cudaMemcpyDeviceToHost, ctx->stream));

@@ -146,6 +146,64 @@ struct NeutralView {
   uint32_t *p_start, *p_end; double* p_cov; int32_t *p_tlen, *p_geneno;   // [cap_off[n_regions] + n_regions] uncompacted
   uint32_t* pred_off;          // [n_bundles+1] counts, then exclusive prefix
   uint32_t *o_start, *o_end; double* o_cov; int32_t *o_tlen, *o_geneno;   // [n_preds]
+  int32_t* b_geneno;           // [n_bundles] the gene counter after the neutral bundles (where the graphs' genes start)
+};
+
+// Rows a10-a15 (asm_device.cuh, frag_device.cuh, asm_kernels.cu): splice graphs, read -> transfrag mapping, flow,
+// predictions.  A "graph" is a candidate (strand lane, CBundle) pair; graph ids run bundle by bundle, '-' lane first —
+// the order in which the reference builds and parses them (rlink.cpp:15660-15752, 15838-15926).
+struct Graph;
+struct AsmView {
+  int64_t n_graphs, n_junc_rows;        // candidate graphs; rows of the junction table after rows a8 + a9 (n_juncs + n_app)
+  const uint32_t* gr_first;             // [2*n_bundles+1] first graph of (bundle b, strand s) at 2b+s
+  const uint32_t* jrow_off;             // [n_bundles+1]   first row of bundle b in GroupsView::oj_*
+  int32_t *g_bundle, *g_k; int8_t* g_s; // [G] input bundle, CBundle index inside the lane, strand (0: '-', 1: '+')
+  // strand-filtered junction lists: bundle b, strand s at 2*jrow_off[b] + s*(rows of b); jl_cnt[2b+s] entries in use
+  uint32_t *js_start, *js_end, *je_end; int32_t *je_k, *reg_node, *reg_graph; uint32_t* jl_cnt;
+  // sweep: bound-sized temporaries (cap_*: capacities per graph, then exclusive prefixes)
+  uint32_t *cap_n, *cap_e, *cap_f, *cap_t;
+  uint32_t *t_nstart, *t_nend; int32_t *t_evu, *t_evv, *t_ft1, *t_ft2; float* t_ftab; uint32_t* t_trpos; float* t_trab; uint8_t* t_trst;
+  int32_t *sw_nn, *sw_ne, *sw_nf, *sw_edgeno;       // [G] what the sweep produced (nn == 0: graph not built)
+  int32_t *bn_first, *bn_cnt, *bn_graph;            // [3*n_groups] bundle2graph, laid out like GroupsView::bn_start
+  // exact-size graph storage (x_*: sizes per graph, then exclusive prefixes)
+  uint32_t *x_node, *x_edge, *x_tf0, *x_reach;
+  Graph* graphs;                                    // [G]
+  uint32_t *n_start, *n_end; float* n_cov; int32_t *ch_off, *ch_cnt, *ch, *pa_off, *pa_cnt, *pa; uint8_t* n_sinkpar;
+  unsigned long long* reach; int32_t *tf_n1, *tf_n2; float* tf_ab;
+  int32_t* fin_stack; double* fin_ncs; uint8_t* fin_visit;   // scratch of graph_finish
+  int64_t n_nodes, n_edges, n_tf0cap, n_reach;
+  // a11: per-read counts -> prefixes; records; transfrag tables
+  uint32_t *r_ncov, *r_ntf, *r_nkey;                // [n_reads+1]
+  uint32_t* tf0_off;                                // [G+1] transfrags create_graph left, then exclusive prefix
+  int32_t* g_node_off;                              // [G] = x_node (as int32, for FragWrite)
+  int64_t n_covrec, n_rec, n_key, n_tf0;
+  uint32_t* cov_node; float* cov_val;               // [n_covrec]
+  int32_t* rec_graph; float* rec_ab; uint32_t *rec_koff, *rec_klen; unsigned long long* rec_hash; int32_t* rec_tf;   // [n_tf0 + n_rec]
+  uint32_t* key;                                    // [2*n_tf0 + n_key + extra]: a11's keys, then the edge transfrags' of a12
+  uint32_t* tab_off;                                // [n_bundles+1] table slots per bundle (powers of two), then exclusive prefix
+  unsigned long long* slot_hash; int32_t* slot_id;  // [tab_off[n_bundles]]
+  int32_t* tf_rep; float* tf_abund; int32_t* tf_graph;   // [n_tf0 + n_rec] bundle b from tfslot0(b) = tf0_off[first graph] + r_ntf[first read]
+  int32_t* b_ntf;                                   // [n_bundles] distinct transfrags of the bundle
+  // a12-a15: per-graph sizes -> prefixes
+  uint32_t *g_nt, *g_ngap, *g_reachsum, *g_fill;    // [G] transfrags after a11, with an unflagged pair, sum of (last-first+1); gather cursor
+  uint32_t *y_tf, *y_pat, *y_path, *y_ntrf, *y_istr;   // [G+1] capacities, then prefixes
+  int64_t n_ytf, n_ypat, n_ypath, n_yntrf, n_yistr;
+  uint32_t xkey_base;                               // first entry of `key` past a11's keys; graph g's edge transfrags at + 2*x_edge[g] + 2g
+  uint32_t *f_koff, *f_klen, *f_wkoff, *f_wklen; float *f_ab, *f_wab; uint8_t* f_real; int32_t *f_usepath, *f_path_off, *f_path_cnt, *f_order;
+  unsigned long long *f_pat, *f_skey; int32_t *f_path_node, *f_path_cont; float* f_path_ab; int32_t *f_ntrf_off, *f_ntrf_cnt, *f_ntrf;
+  uint8_t* f_ecov;
+  // flow scratch: per node arrays at x_node[g] + 2g (gno + 2 entries per graph), per edge arrays at x_edge[g]
+  float *s_nodecov, *s_capl, *s_capr, *s_suml, *s_sumr, *s_flux, *s_exc; int32_t *s_path, *s_succ, *s_n2p; uint32_t *s_exs, *s_exe;
+  unsigned long long *s_pathpat, *s_istr; uint8_t *s_used, *s_prevn, *s_preve;
+  // predictions: pool (any order), then final (graph order)
+  uint32_t* p_counters; uint32_t cap_pred, cap_exon;
+  int32_t *pp_graph, *pp_seq, *pp_tlen; uint32_t *pp_start, *pp_end, *pp_exon0, *pp_nex; double* pp_cov; uint32_t *pe_start, *pe_end; float* pe_cov;
+  uint32_t* g_npred;                                // [G+1] predictions per graph, then exclusive prefix
+  int32_t* g_geneno;                                // [G]
+  int64_t n_pred, n_exon;
+  uint32_t* o_pred_off;                             // [n_bundles+1] bundle b owns predictions [o_pred_off[b], o_pred_off[b+1])
+  uint32_t *o_start, *o_end, *o_exon_off; double* o_cov; int32_t *o_tlen, *o_geneno, *o_src; int8_t* o_strand;   // [n_pred] (+1 for exon_off)
+  uint32_t *oe_start, *oe_end; float* oe_cov;       // [n_exon]
 };
 
 struct JuncParams {
@@ -190,5 +248,22 @@ cudaError_t launch_neutral_count(const DevBatchView& v, const GroupsView& g, uin
 cudaError_t launch_neutral_regions(const DevBatchView& v, const GroupsView& g, const NeutralView& nv, cudaStream_t st);
 cudaError_t launch_neutral_preds(const DevBatchView& v, const GroupsView& g, const NeutralView& nv, cudaStream_t st);
 cudaError_t launch_neutral_compact(const DevBatchView& v, const NeutralView& nv, cudaStream_t st);
+struct AsmParams;
+cudaError_t launch_asm_enum(const DevBatchView& v, const AsmView& A, cudaStream_t st);
+cudaError_t launch_asm_junc_lists(const DevBatchView& v, const GroupsView& g, const AsmView& A, cudaStream_t st);
+cudaError_t launch_asm_bounds(const DevBatchView& v, const GroupsView& g, const AsmView& A, const AsmParams& P, cudaStream_t st);
+cudaError_t launch_asm_sweep(const DevBatchView& v, const GroupsView& g, const AsmView& A, const AsmParams& P, cudaStream_t st);
+cudaError_t launch_asm_sizes(const AsmView& A, cudaStream_t st);
+cudaError_t launch_asm_finish(const DevBatchView& v, const GroupsView& g, const AsmView& A, const AsmParams& P, cudaStream_t st);
+cudaError_t launch_asm_frag_count(const DevBatchView& v, const GroupsView& g, const AsmView& A, cudaStream_t st);
+cudaError_t launch_asm_frag_write(const DevBatchView& v, const GroupsView& g, const AsmView& A, cudaStream_t st);
+cudaError_t launch_asm_table_caps(const DevBatchView& v, const AsmView& A, cudaStream_t st);
+cudaError_t launch_asm_commit(const DevBatchView& v, const AsmView& A, cudaStream_t st);
+cudaError_t launch_asm_gather(const DevBatchView& v, const AsmView& A, cudaStream_t st);
+cudaError_t launch_asm_flow(const DevBatchView& v, const AsmView& A, const AsmParams& P, cudaStream_t st);
+cudaError_t launch_asm_geneno(const DevBatchView& v, const AsmView& A, const int32_t* b_geneno, cudaStream_t st);
+cudaError_t launch_asm_pred_scatter(const AsmView& A, uint32_t npool, cudaStream_t st);
+cudaError_t launch_asm_exon_scatter(const AsmView& A, uint32_t npool, cudaStream_t st);
+size_t asm_graph_struct_bytes();
 int64_t scan_partials_needed(int64_t n);
 int cov_tile_smem_bytes();

@@ -24,6 +24,7 @@ EXPORTS = [
     "stg_sync", "stg_free_batch", "stg_trim", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
     "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_trims_capacity", "stg_find_trims", "stg_infer_transcripts",
     "stg_build_groups", "stg_groups_array_info", "stg_fetch_groups_array", "stg_neutral_predictions",
+    "stg_assemble", "stg_asm_array_info", "stg_fetch_asm_array",
     "stg_shard_assign", "stg_set_profiling", "stg_kernel_count", "stg_kernel_time", "stg_launch_counter", "stg_batch_stats", "stg_stream",
 ]
 
@@ -44,6 +45,15 @@ GROUPS_DTYPES.update({k: np.uint32 for k in ("NP_OFF", "NP_START", "NP_END", "SE
 GROUPS_DTYPES.update({k: np.int8 for k in ("R_STRAND", "G_ALIVE", "J_STRAND")})
 GROUPS_DTYPES.update({k: np.float32 for k in ("G_COV", "G_MULTI", "G_NEG_PROP", "BUN_COV", "BUN_MULTI", "BN_COV")})
 GROUPS_DTYPES.update({k: np.float64 for k in ("NP_COV", "NUM_FRAGMENTS", "FRAG_LEN", "J_NREADS", "J_NREADS_GOOD", "J_LEFT", "J_RIGHT", "J_NM", "J_MM")})
+
+
+# enum stg_asm_array (include/stgpu.h), in order
+ASM_ARRAYS = ["PRED_OFF", "P_START", "P_END", "P_COV", "P_TLEN", "P_GENENO", "P_STRAND", "P_EXON_OFF", "E_START", "E_END", "E_COV",
+              "G_BUNDLE", "G_STRAND", "G_K", "G_NODE_OFF", "N_START", "N_END", "N_COV", "G_NTF"]
+ASM_DTYPES = {"PRED_OFF": np.uint32, "P_START": np.uint32, "P_END": np.uint32, "P_COV": np.float64, "P_TLEN": np.int32,
+              "P_GENENO": np.int32, "P_STRAND": np.int8, "P_EXON_OFF": np.uint32, "E_START": np.uint32, "E_END": np.uint32,
+              "E_COV": np.float32, "G_BUNDLE": np.int32, "G_STRAND": np.int8, "G_K": np.int32, "G_NODE_OFF": np.uint32,
+              "N_START": np.uint32, "N_END": np.uint32, "N_COV": np.float32, "G_NTF": np.uint32}
 
 
 class StgError(RuntimeError):
@@ -99,6 +109,9 @@ def load_library() -> C.CDLL:
     L.stg_neutral_predictions.argtypes = [vp, vp]
     L.stg_groups_array_info.argtypes = [vp, C.c_int, c_i64p, C.POINTER(C.c_int32)]
     L.stg_fetch_groups_array.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
+    L.stg_assemble.argtypes = [vp, vp]
+    L.stg_asm_array_info.argtypes = [vp, C.c_int, c_i64p, C.POINTER(C.c_int32)]
+    L.stg_fetch_asm_array.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
     L.stg_shard_assign.argtypes = [C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
                                    C.POINTER(C.c_int32), c_f64p]
     L.stg_set_profiling.argtypes = [vp, C.c_int]
@@ -271,6 +284,28 @@ class Engine:
         arrays off [n_bundles+1], start, end, cov (f64), tlen, geneno."""
         self._ck(self.L.stg_neutral_predictions(self.ctx, batch.handle))
         return {k[3:].lower(): self.fetch_groups_array(batch, k) for k in NEUTRAL_ARRAYS}
+
+    # ---- rows a10-a15 ---------------------------------------------------------------------------------------
+    def assemble(self, batch: DeviceBatch) -> None:
+        """Splice graphs, read -> transfrag mapping, flow decomposition, predictions (stg_assemble; needs build_groups
+        and neutral_predictions)."""
+        self._ck(self.L.stg_assemble(self.ctx, batch.handle))
+
+    def fetch_asm_array(self, batch: DeviceBatch, which: str) -> np.ndarray:
+        idx = ASM_ARRAYS.index(which)
+        n, sz = C.c_int64(), C.c_int32()
+        self._ck(self.L.stg_asm_array_info(batch.handle, idx, C.byref(n), C.byref(sz)))
+        out = np.empty(n.value, dtype=ASM_DTYPES[which])
+        assert out.itemsize == sz.value, which
+        self._ck(self.L.stg_fetch_asm_array(self.ctx, batch.handle, idx, 0, n.value, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def fetch_predictions(self, batch: DeviceBatch) -> Dict[str, np.ndarray]:
+        """CPrediction list of the graphs of every bundle (after assemble): off [n_bundles+1], start, end, cov, tlen,
+        geneno, strand, exon_off [n_pred+1], e_start, e_end, e_cov."""
+        m = {"PRED_OFF": "off", "P_START": "start", "P_END": "end", "P_COV": "cov", "P_TLEN": "tlen", "P_GENENO": "geneno",
+             "P_STRAND": "strand", "P_EXON_OFF": "exon_off", "E_START": "e_start", "E_END": "e_end", "E_COV": "e_cov"}
+        return {v: self.fetch_asm_array(batch, k) for k, v in m.items()}
 
     def fetch_cov_totals(self, batch: DeviceBatch) -> np.ndarray:
         out = np.empty(batch.n_bundles * 3, dtype=np.float64)

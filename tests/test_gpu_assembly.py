@@ -1,0 +1,76 @@
+"""Rows a10-a15 on the GPU (stg_assemble) against the reference itself: golden fixtures dumped by ref_tool and live
+ref_hot --full runs on seeded batches.  Bar: every integer equal, every float (node coverage, prediction and exon
+coverage) bit-equal."""
+import numpy as np
+import pytest
+
+from stringtie_b200 import synth
+from tests import asm_util
+from tests.conftest import load_golden, GOLDEN
+
+pytestmark = pytest.mark.gpu
+need_ref = pytest.mark.skipif(not asm_util.have_ref_hot(), reason="oracle/_ref/ref_hot not built")
+
+
+def _no_unitigs(a):
+    a = dict(a)
+    a["r_flags"] = (a["r_flags"] & ~np.uint8(1)).astype(np.uint8)
+    return a
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_assembly_golden(engine, name):
+    g = load_golden(name)
+    neu, pr, stage = asm_util.gpu_predictions(engine, g)
+    asm_util.assert_same_graph_stage(stage, g)
+    asm_util.assert_same_predictions(neu, pr, g)
+
+
+@need_ref
+@pytest.mark.parametrize("nb,rpb,seed", [(64, 1700.0, 7), (300, 1700.0, 8), (40, 12000.0, 9), (400, 300.0, 10)])
+def test_assembly_synthetic_vs_reference(engine, nb, rpb, seed):
+    a = synth.make_batch(n_bundles=nb, reads_per_bundle=rpb, seed=seed)
+    ref = asm_util.ref_full(a)
+    neu, pr, stage = asm_util.gpu_predictions(engine, a)
+    asm_util.assert_same_graph_stage(stage, ref)
+    asm_util.assert_same_predictions(neu, pr, ref)
+
+
+@need_ref
+@pytest.mark.parametrize("seed", [4, 5, 6, 8])
+def test_assembly_adversarial_vs_reference(engine, seed):
+    a = _no_unitigs(synth.make_adversarial(seed=seed, n_bundles=40, max_reads=600))
+    ref = asm_util.ref_full(a)
+    try:
+        neu, pr, stage = asm_util.gpu_predictions(engine, a)
+    except Exception as e:   # a read spanning more graph nodes than the kernels allow is refused, not mis-assembled
+        assert "spans more graph nodes" in str(e), e
+        return
+    asm_util.assert_same_graph_stage(stage, ref)
+    asm_util.assert_same_predictions(neu, pr, ref)
+
+
+def test_assembly_refuses_unitigs_and_call_order(engine):
+    from stringtie_b200.stgb import input_view
+    a = input_view(synth.make_adversarial(seed=3, n_bundles=6, max_reads=200))
+    a["r_flags"][:] |= 1
+    batch = engine.upload(a)
+    with pytest.raises(Exception):
+        engine.assemble(batch)        # groups not built
+    engine.run(batch)
+    engine.build_groups(batch)
+    engine.neutral_predictions(batch)
+    with pytest.raises(Exception) as ei:
+        engine.assemble(batch)
+    assert "unitig" in str(ei.value)
+    batch.free()
+
+
+def test_assembly_idempotent_across_batches(engine):
+    """The same input assembled twice (pool blocks reused in between) gives identical predictions."""
+    a = synth.make_batch(n_bundles=48, reads_per_bundle=900.0, seed=21)
+    _, p1, s1 = asm_util.gpu_predictions(engine, a)
+    _, p2, s2 = asm_util.gpu_predictions(engine, a)
+    for k in p1:
+        assert np.array_equal(p1[k].view(np.uint8), p2[k].view(np.uint8)), k
+    assert np.array_equal(s1["N_COV"].view(np.uint32), s2["N_COV"].view(np.uint32))
