@@ -1,16 +1,19 @@
 // host/stgpu_adaptor.cpp — the reference-side binding of libstgpu (made real).
 //
 // Built by host/Makefile into host/_build/stringtie_stgpu: the reference program (stringtie.cpp main, htslib decode,
-// bundle queue, build_graphs, printResults — all its own sources, compiled where they lie) with ONE function replaced:
-//     void count_good_junctions(BundleData* bdata)        rlink.cpp:16656, called from infer_transcripts (:17256)
-// is provided here and runs on the GPU through the C ABI of include/stgpu.h.  For short reads that function is exactly
-// the stage the library implements (add_read_to_cov + junction support + the blocked clamped scan; the long-read /
-// mixed-mode junction correction and strand inference never run, rlink.cpp:16668, 16902-16975, 17067).  The rest of the
-// reference then works on the bpcov and junction counters the GPU produced, so the GTF must come out byte-identical
-// to the unmodified reference's — tests/test_host_integration.py checks exactly that.
+// processRead, the GThreads bundle queue, printResults, the GTF writer — all its own sources, compiled where they lie)
+// with ONE function replaced:
+//     int infer_transcripts(BundleData* bundle)        rlink.h:380, body rlink.cpp:17161, call site stringtie.cpp:1477
+// is provided here and runs on the GPU through the C ABI of include/stgpu.h: the bundle is flattened into a
+// stg_bundle_view, stg_infer_transcripts(assemble = 1) runs count_good_junctions and build_graphs to its end on the
+// device, and what the reference function writes back — BundleData::pred, bpcov, num_fragments, frag_len — is put
+// back into the BundleData, so that the reference's own printResults / FPKM-TPM pass work on it unchanged.  The GTF
+// must come out byte-identical to the unmodified reference's: tests/test_host_integration.py checks exactly that.
+// Modes the library does not implement yet (guides / -e, -L, --mix, -N, --merge, --viral, --ptf) stop with an error:
+// there is no CPU path behind this call.
 //
-// This is the one-bundle synchronous form (stg_infer_transcripts): a correctness demonstration of the boundary, not
-// the fast path — a production host batches thousands of bundles per call.
+// This is the one-bundle synchronous form: a correctness demonstration of the boundary, not the fast path — a
+// production host batches thousands of bundles per call.
 #include "rlink.h"
 #include "stgpu.h"
 #include <mutex>
@@ -22,34 +25,41 @@ extern uint junctionsupport;   // rlink.cpp:35 (stringtie.cpp:140)
 extern uint sserror;           // rlink.cpp:36
 extern int junctionthr;        // rlink.cpp:37
 extern uint bundledist;
-extern bool longreads, mixedMode, eonly, viral;
-
-void count_good_junctions_reference(BundleData* bdata);   // the reference's own body, renamed by host/Makefile
+extern int mintranscriptlen, allowed_nodes;
+extern float isofrac, mcov, readthr, singlethr;
+extern bool longreads, mixedMode, eonly, viral, trim, includesource, isnascent, printNascent, rawreads, guided, mergeMode, havePtFeatures;
 
 namespace {
 stg_ctx* g_ctx = nullptr;
 std::mutex g_mu;          // one context, one stream: worker threads (-p N) take turns
-long g_calls = 0;
+long g_calls = 0, g_preds = 0;
+
+void die(const char* what) {
+  fprintf(stderr, "libstgpu: %s\n", what);
+  _exit(1);                                  // (exit() would wait on the reference's worker threads)
+}
 
 stg_ctx* context() {
   if (g_ctx) return g_ctx;
   stg_params p;
   stg_params_default(&p);
   p.junctionsupport = junctionsupport; p.sserror = sserror; p.junctionthr = junctionthr; p.bundledist = bundledist;
-  p.eonly = eonly ? 1 : 0;
-  if (stg_init(&p, 0, &g_ctx) != STG_OK) {   // no GPU, no result: there is no CPU fallback behind this call
-    fprintf(stderr, "libstgpu: %s\n", stg_last_error(nullptr));
-    _exit(1);                                // (exit() would wait on the reference's worker threads)
-  }
-  atexit([] { if (getenv("STGPU_VERBOSE")) fprintf(stderr, "libstgpu: %ld bundles went through the GPU\n", g_calls); });
+  p.mintranscriptlen = mintranscriptlen; p.allowed_nodes = allowed_nodes; p.isofrac = isofrac; p.mcov = mcov; p.readthr = readthr;
+  p.singlethr = singlethr; p.trim = trim ? 1 : 0; p.includesource = includesource ? 1 : 0;
+  p.eonly = eonly ? 1 : 0; p.longreads = longreads ? 1 : 0; p.mixedMode = mixedMode ? 1 : 0; p.viral = viral ? 1 : 0;
+  p.isnascent = isnascent ? 1 : 0; p.printNascent = printNascent ? 1 : 0; p.rawreads = rawreads ? 1 : 0; p.guided = guided ? 1 : 0;
+  p.havePtFeatures = havePtFeatures ? 1 : 0;
+  if (stg_init(&p, 0, &g_ctx) != STG_OK) die(stg_last_error(nullptr));   // no GPU, no result
+  atexit([] { if (getenv("STGPU_VERBOSE")) fprintf(stderr, "libstgpu: %ld bundles went through the GPU, %ld predictions came back\n", g_calls, g_preds); });
   return g_ctx;
 }
 }  // namespace
 
-void count_good_junctions(BundleData* bdata) {
-  if (longreads || mixedMode || viral) { count_good_junctions_reference(bdata); return; }   // stages not built yet
-  GList<CReadAln>& rd = bdata->readlist;
-  GList<CJunction>& jn = bdata->junction;
+int infer_transcripts(BundleData* bundle) {
+  if (mergeMode) die("--merge is not implemented by libstgpu");
+  if (bundle->keepguides.Count() == 0 && eonly) return 0;   // rlink.cpp:17177: nothing to do for this bundle
+  GList<CReadAln>& rd = bundle->readlist;
+  GList<CJunction>& jn = bundle->junction;
   const int nr = rd.Count(), nj = jn.Count();
   std::vector<uint32_t> r_start(nr), r_end(nr), r_len(nr), seg_off(nr + 1, 0), pair_off(nr + 1, 0), seg_s, seg_e;
   std::vector<float> r_count(nr), pair_cnt;
@@ -82,28 +92,43 @@ void count_good_junctions(BundleData* bdata) {
   if (rjunc.empty()) rjunc.push_back(0);
   stg_bundle_view v;
   memset(&v, 0, sizeof(v));
-  v.start = bdata->start; v.end = bdata->end; v.n_reads = nr; v.n_juncs = nj;
+  v.start = bundle->start; v.end = bundle->end; v.n_reads = nr; v.n_juncs = nj;
   v.r_start = r_start.data(); v.r_end = r_end.data(); v.r_len = r_len.data(); v.r_count = r_count.data();
   v.r_nh = r_nh.data(); v.r_strand = r_strand.data(); v.r_flags = r_flags.data(); v.r_seg_off = seg_off.data();
   v.seg_start = seg_s.data(); v.seg_end = seg_e.data(); v.rjunc_idx = rjunc.data(); v.r_pair_off = pair_off.data();
   v.pair_idx = pair_idx.data(); v.pair_cnt = pair_cnt.data(); v.j_start = j_s.data(); v.j_end = j_e.data();
   v.j_strand = j_strand.data(); v.j_guide_match = j_gm.data(); v.j_nreads = j_nreads.data(); v.j_nm = j_nm.data();
   v.j_mm = j_mm.data();
-  const int len = bdata->end - bdata->start + 3;       // rlink.cpp:16875
+  const int len = bundle->end - bundle->start + 3;     // rlink.cpp:16875
   std::vector<float> cov(3 * (size_t)len);
-  std::vector<double> good(nj), left(nj), right(nj);
-  stg_bundle_result res = {cov.data(), good.data(), left.data(), right.data()};
+  stg_bundle_result res;
+  memset(&res, 0, sizeof(res));
+  res.bpcov = cov.data();
+  res.assemble = 1;
+  int geneno = 0;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     stg_ctx* ctx = context();
-    if (stg_infer_transcripts(ctx, &v, &res) != STG_OK) { fprintf(stderr, "libstgpu: %s\n", stg_last_error(ctx)); _exit(1); }
-    g_calls++;
+    if (stg_infer_transcripts(ctx, &v, &res) != STG_OK) die(stg_last_error(ctx));
+    g_calls++; g_preds += res.n_pred;
+    // BundleData::pred (CPrediction, bundle.h:270-311) — copied out while the context's buffers are ours
+    for (int i = 0; i < res.n_pred; i++) {
+      CPrediction* p = new CPrediction(res.p_geneno[i], NULL, res.p_start[i], res.p_end[i], res.p_cov[i], (char)res.p_strand[i], res.p_tlen[i]);
+      for (uint32_t e = res.p_exon_off[i]; e < res.p_exon_off[i + 1]; e++) {
+        GSeg exon(res.e_start[e], res.e_end[e]);
+        p->exons.Add(exon);
+        float ec = res.e_cov[e];
+        p->exoncov.Add(ec);
+      }
+      bundle->pred.Add(p);
+      if (res.p_geneno[i] + 1 > geneno) geneno = res.p_geneno[i] + 1;
+    }
   }
-  for (int s = 0; s < 3; s++) {                        // BundleData::bpcov, bundle.h:329
-    bdata->bpcov[s].Resize(len);
-    memcpy(&bdata->bpcov[s][0], &cov[(size_t)s * len], (size_t)len * sizeof(float));
+  for (int s = 0; s < 3; s++) {                        // BundleData::bpcov, bundle.h:329 (printResults reads it)
+    bundle->bpcov[s].Resize(len);
+    memcpy(&bundle->bpcov[s][0], &cov[(size_t)s * len], (size_t)len * sizeof(float));
   }
-  for (int j = 0; j < nj; j++) {                       // the reference accumulates into fields that start at 0
-    jn[j]->nreads_good += good[j]; jn[j]->leftsupport += left[j]; jn[j]->rightsupport += right[j];
-  }
+  bundle->num_fragments += res.num_fragments;         // rlink.cpp:15105-15116 (both start at 0 for a fresh bundle)
+  bundle->frag_len += res.frag_len;
+  return geneno;
 }

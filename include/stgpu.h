@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define STG_ABI_VERSION 2 /* 2: stg_build_groups, stg_neutral_predictions, stg_find_trims and the groups array fetch */
+#define STG_ABI_VERSION 3 /* 2: stg_build_groups, stg_neutral_predictions, stg_find_trims and the groups array fetch */
 #define STG_BSIZE 10000 /* rlink.cpp:11 — block size of the blocked prefix sums in bpcov */
 
 enum {
@@ -292,12 +292,29 @@ int stg_find_trims(stg_ctx* ctx, const stg_dbatch* batch, int64_t n, const int32
                    const uint32_t* start, const uint32_t* end, const uint32_t* cap_off, uint32_t* count,
                    uint32_t* pos, float* abundance, uint8_t* is_start);
 
-/* Convenience drop-in for ONE bundle, synchronous (upload + run + fetch), the shape of the reference call. */
+/* Drop-in for ONE bundle, synchronous, the shape of the reference call `int infer_transcripts(BundleData*)` (rlink.h:380,
+ * call site stringtie.cpp:1477): upload, every stage, fetch of what the reference writes back into BundleData.
+ * With `assemble` == 0 only count_good_junctions runs (bpcov + junction support: the ABI-2 behaviour).  With `assemble`
+ * != 0 the whole function runs — count_good_junctions, then build_graphs to its end — and the result carries
+ * BundleData::pred (the neutral bundles' single-exon predictions, then the graphs' transcripts, in the reference's order),
+ * BundleData::num_fragments and frag_len.  The prediction arrays are owned by the context and stay valid until the next
+ * stg_infer_transcripts call on it. */
 typedef struct stg_bundle_result {
   float* bpcov;            /* caller-allocated [3*(end-start+3)] or NULL */
   double* j_nreads_good;   /* caller-allocated [n_juncs] or NULL */
   double* j_leftsupport;
   double* j_rightsupport;
+  /* ---- ABI 3 ---- */
+  int32_t assemble;        /* in */
+  int32_t n_pred, n_exon;  /* out */
+  double num_fragments, frag_len;              /* out (rlink.cpp:15105-15116) */
+  const int32_t *p_start, *p_end;              /* CPrediction::start / end (GSeg) */
+  const double* p_cov;                         /* CPrediction::cov */
+  const int32_t *p_tlen, *p_geneno;            /* CPrediction::tlen / geneno */
+  const int8_t* p_strand;                      /* '+', '-' or '.' */
+  const uint32_t* p_exon_off;                  /* [n_pred+1] */
+  const uint32_t *e_start, *e_end;             /* CPrediction::exons */
+  const float* e_cov;                          /* CPrediction::exoncov */
 } stg_bundle_result;
 int stg_infer_transcripts(stg_ctx* ctx, const stg_bundle_view* view, stg_bundle_result* result);
 

@@ -56,7 +56,12 @@ class StgBundleView(C.Structure):
 
 
 class StgBundleResult(C.Structure):
-    _fields_ = [("bpcov", c_f32p), ("j_nreads_good", c_f64p), ("j_leftsupport", c_f64p), ("j_rightsupport", c_f64p)]
+    _fields_ = [("bpcov", c_f32p), ("j_nreads_good", c_f64p), ("j_leftsupport", c_f64p), ("j_rightsupport", c_f64p),
+                ("assemble", C.c_int32), ("n_pred", C.c_int32), ("n_exon", C.c_int32), ("num_fragments", C.c_double),
+                ("frag_len", C.c_double), ("p_start", C.POINTER(C.c_int32)), ("p_end", C.POINTER(C.c_int32)), ("p_cov", c_f64p),
+                ("p_tlen", C.POINTER(C.c_int32)), ("p_geneno", C.POINTER(C.c_int32)), ("p_strand", C.POINTER(C.c_int8)),
+                ("p_exon_off", C.POINTER(C.c_uint32)), ("e_start", C.POINTER(C.c_uint32)), ("e_end", C.POINTER(C.c_uint32)),
+                ("e_cov", c_f32p)]
 
 
 def ptr(a: np.ndarray):

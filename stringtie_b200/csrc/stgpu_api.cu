@@ -21,6 +21,11 @@ struct Timed { const char* name; cudaEvent_t e0, e1; };
 // on every one.  Blocks are handed back on stg_free_batch and reused best-fit; stg_shutdown / stg_trim release them.
 struct PoolBlock { void* p; size_t bytes; };
 
+struct OneBundleOut {   // BundleData::pred of the last stg_infer_transcripts call (owned by the context)
+  std::vector<int32_t> p_start, p_end, p_tlen, p_geneno; std::vector<double> p_cov; std::vector<int8_t> p_strand;
+  std::vector<uint32_t> p_exon_off, e_start, e_end; std::vector<float> e_cov;
+};
+
 struct stg_ctx {
   int device = 0;
   int num_sms = 0;
@@ -39,6 +44,7 @@ struct stg_ctx {
   size_t pool_bytes = 0;          // bytes currently parked in pool_free
   struct stg_builder* one_bundle = nullptr;   // batcher reused by stg_infer_transcripts (keeps its pinned buffers)
   std::mutex one_bundle_mu;
+  OneBundleOut one_out;
 };
 
 // Growable host array in PINNED memory (cudaMallocHost), so that stg_upload's copies out of the batcher run
@@ -1247,10 +1253,54 @@ int stg_infer_transcripts(stg_ctx* ctx, const stg_bundle_view* view, stg_bundle_
   stg_builder_reset(b);
   stg_dbatch* d = nullptr;
   stg_packed_batch pb;
+  result->n_pred = 0; result->n_exon = 0; result->num_fragments = 0; result->frag_len = 0;
   if (!(rc = stg_builder_add(b, view)) && !(rc = stg_builder_packed(b, &pb)) && !(rc = stg_upload(ctx, &pb, &d)) &&
       !(rc = stg_run(ctx, d))) {
     if (result->bpcov) rc = stg_fetch_bpcov(ctx, d, 0, result->bpcov);
     if (!rc) rc = stg_fetch_junction_support(ctx, d, result->j_nreads_good, result->j_leftsupport, result->j_rightsupport);
+    if (!rc && result->assemble && !(rc = stg_build_groups(ctx, d)) && !(rc = stg_neutral_predictions(ctx, d)) && !(rc = stg_assemble(ctx, d))) {
+      // BundleData::pred: the neutral bundles' predictions, then the graphs'
+      OneBundleOut& o = ctx->one_out;
+      const int64_t nn = d->nv.n_preds, np = d->av.n_pred, ne = d->av.n_exon;
+      const int64_t NP = nn + np, NE = nn + ne;
+      o.p_start.resize(NP); o.p_end.resize(NP); o.p_cov.resize(NP); o.p_tlen.resize(NP); o.p_geneno.resize(NP); o.p_strand.resize(NP);
+      o.p_exon_off.resize(NP + 1); o.e_start.resize(NE); o.e_end.resize(NE); o.e_cov.resize(NE);
+      std::vector<uint32_t> us(std::max<int64_t>(nn, 1)), ue(std::max<int64_t>(nn, 1));
+      if (nn) {
+        if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NP_START, 0, nn, us.data());
+        if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NP_END, 0, nn, ue.data());
+        if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NP_COV, 0, nn, o.p_cov.data());
+        if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NP_TLEN, 0, nn, o.p_tlen.data());
+        if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NP_GENENO, 0, nn, o.p_geneno.data());
+        for (int64_t i = 0; i < nn && !rc; i++) {
+          o.p_start[i] = (int32_t)us[i]; o.p_end[i] = (int32_t)ue[i]; o.p_strand[i] = '.';
+          o.p_exon_off[i] = (uint32_t)i; o.e_start[i] = us[i]; o.e_end[i] = ue[i]; o.e_cov[i] = (float)o.p_cov[i];
+        }
+      }
+      if (np && !rc) {
+        std::vector<uint32_t> gs(np), ge(np), xo(np + 1);
+        rc = stg_fetch_asm_array(ctx, d, STG_AA_P_START, 0, np, gs.data());
+        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_END, 0, np, ge.data());
+        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_COV, 0, np, o.p_cov.data() + nn);
+        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_TLEN, 0, np, o.p_tlen.data() + nn);
+        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_GENENO, 0, np, o.p_geneno.data() + nn);
+        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_STRAND, 0, np, o.p_strand.data() + nn);
+        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_EXON_OFF, 0, np + 1, xo.data());
+        if (!rc && ne) rc = stg_fetch_asm_array(ctx, d, STG_AA_E_START, 0, ne, o.e_start.data() + nn);
+        if (!rc && ne) rc = stg_fetch_asm_array(ctx, d, STG_AA_E_END, 0, ne, o.e_end.data() + nn);
+        if (!rc && ne) rc = stg_fetch_asm_array(ctx, d, STG_AA_E_COV, 0, ne, o.e_cov.data() + nn);
+        for (int64_t i = 0; i < np && !rc; i++) { o.p_start[nn + i] = (int32_t)gs[i]; o.p_end[nn + i] = (int32_t)ge[i]; o.p_exon_off[nn + i] = (uint32_t)nn + xo[i]; }
+      }
+      o.p_exon_off[NP] = (uint32_t)NE;
+      if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NUM_FRAGMENTS, 0, 1, &result->num_fragments);
+      if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_FRAG_LEN, 0, 1, &result->frag_len);
+      if (!rc) {
+        result->n_pred = (int32_t)NP; result->n_exon = (int32_t)NE;
+        result->p_start = o.p_start.data(); result->p_end = o.p_end.data(); result->p_cov = o.p_cov.data(); result->p_tlen = o.p_tlen.data();
+        result->p_geneno = o.p_geneno.data(); result->p_strand = o.p_strand.data(); result->p_exon_off = o.p_exon_off.data();
+        result->e_start = o.e_start.data(); result->e_end = o.e_end.data(); result->e_cov = o.e_cov.data();
+      }
+    }
   }
   stg_free_batch(ctx, d);
   return rc;

@@ -358,3 +358,23 @@ class Engine:
         res = StgBundleResult(ptr(cov), ptr(good), ptr(left), ptr(right))
         self._ck(self.L.stg_infer_transcripts(self.ctx, C.byref(view), C.byref(res)))
         return cov.reshape(3, length), good, left, right
+
+    def infer_transcripts_full(self, arrays: Dict[str, np.ndarray], b: int = 0):
+        """The whole of `infer_transcripts(BundleData*)` (rlink.h:380) for bundle b: returns (bpcov, predictions dict,
+        num_fragments, frag_len); predictions = BundleData::pred in the reference's order."""
+        view, keep = bundle_view(arrays, b)
+        length = view.end - view.start + 3
+        cov = np.empty(3 * length, dtype=np.float32)
+        good = np.zeros(view.n_juncs, dtype=np.float64)
+        left = np.zeros(view.n_juncs, dtype=np.float64)
+        right = np.zeros(view.n_juncs, dtype=np.float64)
+        res = StgBundleResult(ptr(cov), ptr(good), ptr(left), ptr(right))
+        res.assemble = 1
+        self._ck(self.L.stg_infer_transcripts(self.ctx, C.byref(view), C.byref(res)))
+        n, ne = res.n_pred, res.n_exon
+        cp = lambda p, k, dt: np.ctypeslib.as_array(p, shape=(k,)).astype(dt, copy=True) if k else np.empty(0, dtype=dt)
+        pred = {"start": cp(res.p_start, n, np.int32), "end": cp(res.p_end, n, np.int32), "cov": cp(res.p_cov, n, np.float64),
+                "tlen": cp(res.p_tlen, n, np.int32), "geneno": cp(res.p_geneno, n, np.int32), "strand": cp(res.p_strand, n, np.int8),
+                "exon_off": cp(res.p_exon_off, n + 1, np.uint32) if n else np.zeros(1, dtype=np.uint32),
+                "e_start": cp(res.e_start, ne, np.uint32), "e_end": cp(res.e_end, ne, np.uint32), "e_cov": cp(res.e_cov, ne, np.float32)}
+        return cov.reshape(3, length), pred, res.num_fragments, res.frag_len

@@ -1,6 +1,7 @@
-"""End-to-end drop-in check: the REFERENCE program with count_good_junctions() served by libstgpu through
-host/stgpu_adaptor.cpp (built by host/Makefile into host/_build/stringtie_stgpu) must write the same GTF, byte for byte,
-as the unmodified reference.  The expected GTFs (tests/golden/gtf_*.gtf) were written by oracle/_ref/stringtie -p 1 on
+"""End-to-end drop-in check: the REFERENCE program with infer_transcripts() (rlink.h:380, call site stringtie.cpp:1477)
+served by libstgpu through host/stgpu_adaptor.cpp (built by host/Makefile into host/_build/stringtie_stgpu) — i.e. coverage,
+junctions, groups, splice graphs, flow and predictions all come from the GPU, the reference's own producer, printResults and
+GTF writer run around them — must write the same GTF, byte for byte, as the unmodified reference.  The expected GTFs (tests/golden/gtf_*.gtf) were written by oracle/_ref/stringtie -p 1 on
 the seeded SAM files tools/gen_sam.py regenerates here."""
 import os
 import subprocess
@@ -36,6 +37,7 @@ def test_reference_host_with_gpu_stage_writes_identical_gtf(tmp_path, name, thre
     p = subprocess.run([BIN, sam, "-p", str(threads), "-o", gtf], env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
     assert "bundles went through the GPU" in p.stderr and not p.stderr.startswith("libstgpu: 0 ")
+    assert ", 0 predictions came back" not in p.stderr
     got, want = _body(gtf), _body(os.path.join(ROOT, "tests", "golden", name + ".gtf"))
     if threads == 1:
         assert got == want
@@ -47,4 +49,4 @@ def test_reference_host_with_gpu_stage_writes_identical_gtf(tmp_path, name, thre
 
 def test_adaptor_source_declares_the_replaced_symbol():
     src = open(os.path.join(ROOT, "host", "stgpu_adaptor.cpp")).read()
-    assert "void count_good_junctions(BundleData* bdata)" in src and "stg_infer_transcripts" in src
+    assert "int infer_transcripts(BundleData* bundle)" in src and "stg_infer_transcripts" in src and "assemble = 1" in src
