@@ -1,15 +1,16 @@
 #!/usr/bin/env python3
-"""bench.py — throughput of the per-bundle assembly hot path (the stages built so far: the reference's
-count_good_junctions = coverage + junction support, and the junction pass that opens build_graphs) on the C2 workload
-of BASELINE.json:
-synthetic 100 M 2x150 paired-end spliced alignments over ~60 k loci.
+"""bench.py — throughput of the per-bundle assembly hot path, infer_transcripts() (rlink.h:380): coverage + junction
+support (count_good_junctions), then build_graphs to its end — junction pass, read repair, groups / bundles, neutral
+predictions, splice graphs, read -> transfrag mapping, transfrag processing, flow decomposition, predictions — on the C2
+workload of BASELINE.json: synthetic ~100 M 2x150 paired-end spliced alignments over 60 000 independently drawn loci.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one rank per GPU under torchrun for N>1)
-  python bench.py --impl reference [--gpus N] [--steps K] ...    the reference's own CPU code on the host cores
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--scaling weak|strong]   our arm (one rank per GPU under torchrun)
+  python bench.py --impl reference [--gpus N] [--steps K] ...                   the reference's own CPU code, all host cores
 
-One "step" = one pass of the hot path over the whole batch.  `value` is measured with the batch resident in HBM,
-`e2e` through the C ABI from pinned HOST buffers (H2D of all inputs + D2H of the stage's results inside the timed
-region).  Prints ONE JSON line (rank 0).
+One "step" = one pass of the whole path over the whole batch (every SURVEY §8 row built so far, a1-a15 + a19, is inside the
+timed region).  `value` is measured with the batch resident in HBM; `e2e` through the C ABI from pinned HOST buffers:
+H2D of all inputs + every stage + D2H of what the host's printResults needs (BundleData::pred, num_fragments, frag_len
+and bpcov) inside the timed region.  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -29,27 +30,45 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = ("aligned reads/sec through assembly (stages built: count_good_junctions = coverage + junction support, "
-          "and the junction pass of build_graphs)")
-BASE_BUNDLES = 6000          # one seeded base of ~9.7 M alignments ...
-BASE_READS_PER_BUNDLE = 1667
-REPLICAS = 10                # ... x 10 coordinate-shifted replicas = ~97 M alignments over 60 000 loci
+METRIC = "aligned reads/sec through assembly (infer_transcripts: count_good_junctions + build_graphs, short-read de novo)"
+PART_BUNDLES = 6000          # loci per independently seeded part
+READS_PER_BUNDLE = 1667
+PARTS = 10                   # 10 parts x 6 000 loci = 60 000 loci, ~97 M alignments
 SEED = 20251019
+BASE_BUNDLES, REPLICAS = PART_BUNDLES, PARTS   # names the tests / tools of round 1 use
 
 
-def build_workload(replicas: int, base_bundles: int, rank: int):
+def _make_part(args):
+    nb, seed, path = args
     from stringtie_b200 import synth
-    cache = os.path.join(tempfile.gettempdir(), f"stg_c2_base_{base_bundles}_{SEED + rank}.npz")
-    if os.path.exists(cache):
-        with np.load(cache) as z:
-            base = {k: z[k] for k in z.files}
-    else:
-        base = synth.make_batch(n_bundles=base_bundles, reads_per_bundle=BASE_READS_PER_BUNDLE, seed=SEED + rank)
-        try:
-            np.savez(cache, **base)
-        except Exception:
-            pass
-    return base, synth.replicate(base, replicas)
+    a = synth.make_batch(n_bundles=nb, reads_per_bundle=READS_PER_BUNDLE, seed=seed)
+    try:
+        np.savez(path + ".tmp.npz", **a)
+        os.replace(path + ".tmp.npz", path)
+    except Exception:
+        pass
+    return path
+
+
+def build_workload(parts: int, part_bundles: int, rank: int):
+    """`parts` independently drawn sets of loci (seed SEED + 1000*rank + i), concatenated.  Parts are cached under the
+    temp dir; missing ones are generated in parallel processes (call this before CUDA is initialised)."""
+    from stringtie_b200 import synth
+    paths = [os.path.join(tempfile.gettempdir(), f"stg_c2_part_{part_bundles}_{SEED + 1000 * rank + i}.npz") for i in range(parts)]
+    todo = [(part_bundles, SEED + 1000 * rank + i, p) for i, p in enumerate(paths) if not os.path.exists(p)]
+    if todo:
+        import multiprocessing as mp
+        nproc = max(1, min(len(todo), (os.cpu_count() or 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+        with mp.get_context("fork").Pool(nproc) as pool:
+            pool.map(_make_part, todo)
+    loaded = []
+    for i, p in enumerate(paths):
+        if os.path.exists(p):
+            with np.load(p) as z:
+                loaded.append({k: z[k] for k in z.files})
+        else:   # the cache could not be written: generate in-process
+            loaded.append(synth.make_batch(n_bundles=part_bundles, reads_per_bundle=READS_PER_BUNDLE, seed=SEED + 1000 * rank + i))
+    return loaded[0], synth.concat(loaded)
 
 
 class ClockSampler:
@@ -93,41 +112,34 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_hot(arrays, nbundles: int, threads: int, reps: int):
-    """Time the reference's own count_good_junctions on the first `nbundles` bundles via oracle/_ref/ref_hot
-    (kind 'reference'); if that binary is absent fall back to the C port (kind 'port')."""
+def reference_hot(arrays, nbundles: int, threads: int, reps: int, stages=("--full",)):
+    """Time the reference's own infer_transcripts body (count_good_junctions + build_graphs, rlink.cpp:17256-17258) on the
+    first `nbundles` bundles via oracle/_ref/ref_hot (kind 'reference': the reference's sources compiled where they lie,
+    BundleData rebuilt from the packed batch outside the timed part)."""
     from stringtie_b200.stgb import slice_bundles, write_stgb
     nb = min(nbundles, arrays["b_start"].size)
     sample = slice_bundles(arrays, 0, nb)
     nreads = int(sample["r_start"].size)
     tool = os.path.join(ROOT, "oracle", "_ref", "ref_hot")
+    if not os.path.exists(tool):
+        raise SystemExit("bench.py: oracle/_ref/ref_hot is missing (built by __graft_entry__.build() where /root/reference exists)")
     desc = f"first {nb} bundles ({nreads} alignments) of the workload x {reps} reps"
-    if os.path.exists(tool):
-        with tempfile.TemporaryDirectory() as td:
-            path = os.path.join(td, "sample.stgb")
-            write_stgb(path, sample)
-            out = subprocess.check_output([tool, path, "--threads", str(threads), "--reps", str(reps), "--a7"], text=True)
-            out9 = subprocess.check_output([tool, path, "--threads", str(threads), "--reps", str(reps), "--a9b"], text=True)
-            out19 = subprocess.check_output([tool, path, "--threads", str(threads), "--reps", str(reps), "--a19"], text=True)
-        j = json.loads(out.strip().splitlines()[-1])
-        j9 = json.loads(out9.strip().splitlines()[-1])
-        j19 = json.loads(out19.strip().splitlines()[-1])
-        return {"value": j["reads_per_s"], "unit": "reads/s", "cores": threads, "kind": "reference",
-                "through_rows_a8_a9": {"reads_per_s": j9["reads_per_s"], "compute_s": j9["compute_s_max"],
-                                       "note": "same sample, the reference run on to the end of its bundle creation (rlink.cpp:15433)"},
-                "through_row_a19": {"reads_per_s": j19["reads_per_s"], "compute_s": j19["compute_s_max"],
-                                    "note": "... and on to the end of its neutral-bundle predictions (rlink.cpp:15637)"},
-                "sample": desc + "; reference count_good_junctions (rlink.cpp:16656) + build_graphs up to the end of its "
-                          "junction pass (rlink.cpp:14165-14842) on rebuilt BundleData, "
-                          "aggregate of per-thread reads / per-thread compute time",
-                "bundles_per_s": j["reads_per_s"] * nb / max(nreads, 1), "compute_s": j["compute_s_max"]}
-    from tests import orc
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        orc.run(sample, want_cov=True, threads=threads)
-    dt = (time.perf_counter() - t0) / reps
-    return {"value": nreads / dt, "unit": "reads/s", "cores": threads, "kind": "port", "sample": desc + "; oracle/liborc.so",
-            "bundles_per_s": nb / dt, "compute_s": dt}
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "sample.stgb")
+        write_stgb(path, sample)
+        for st in stages:
+            out = subprocess.check_output([tool, path, "--threads", str(threads), "--reps", str(reps), st], text=True)
+            res[st] = json.loads(out.strip().splitlines()[-1])
+    j = res["--full"]
+    cb = {"value": j["reads_per_s"], "unit": "reads/s", "cores": threads, "kind": "reference",
+          "sample": desc + "; the reference's count_good_junctions (rlink.cpp:16656) + build_graphs (rlink.cpp:14165) to its end "
+                    "on rebuilt BundleData, aggregate of per-thread reads / per-thread compute time",
+          "bundles_per_s": j["reads_per_s"] * nb / max(nreads, 1), "compute_s": j["compute_s_max"]}
+    for st, key in (("--a7", "through_rows_a1_a7"), ("--a9b", "through_rows_a8_a9"), ("--a10", "through_row_a10"), ("--a11", "through_row_a11")):
+        if st in res:
+            cb[key] = {"reads_per_s": res[st]["reads_per_s"], "compute_s": res[st]["compute_s_max"]}
+    return cb
 
 
 def main():
@@ -136,34 +148,39 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--replicas", type=int, default=REPLICAS)
-    ap.add_argument("--base-bundles", type=int, default=BASE_BUNDLES)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank assembles its own C2-sized workload; strong: ONE workload is split across the ranks "
+                         "by stg_shard_assign (greedy least-loaded by reads + span/64)")
+    ap.add_argument("--parts", type=int, default=PARTS)
+    ap.add_argument("--part-bundles", type=int, default=PART_BUNDLES)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--skip-groups", action="store_true", help="do not run the rows a8 + a9 stage after the timed passes")
+    ap.add_argument("--e2e-no-bpcov", action="store_true", help="leave bpcov in HBM in the end-to-end measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload_name = (f"C2 synthetic short-read: {args.replicas} x seeded base of {args.base_bundles} loci "
-                     f"(~{args.replicas * args.base_bundles * BASE_READS_PER_BUNDLE / 1e6:.0f} M alignments, 2x150 PE, de novo)")
-    config = {"workload": workload_name, "per_gpu": "one full copy of the workload per rank (weak scaling)",
-              "l2": "inputs_larger_than_L2", "stages": ["cov_edge_add/add_read_to_cov", "junction support",
-                                                         "blocked clamped scan", "get_cov totals",
-                                                         "build_graphs junction pass + good_junc"],
-              "scope": "value / e2e / roofline cover SURVEY rows a1-a7 (the reference arm times the same rows); rows a8 + a9 "
-                       "(read loop, groups, bundles) and a19 (neutral predictions) are built too and reported beside "
-                       "them under rows_a8_a9 (one pass outside the timed region; pipeline_a1_to_a9_reads_per_s)"}
+    workload_name = (f"C2 synthetic short-read: {args.parts} x {args.part_bundles} independently drawn loci "
+                     f"(~{args.parts * args.part_bundles * READS_PER_BUNDLE / 1e6:.0f} M alignments, 2x150 PE, de novo)")
+    config = {"workload": workload_name,
+              "per_gpu": ("one full workload per rank, seeds differ by rank (weak scaling)" if args.scaling == "weak" else
+                          "ONE workload split across the ranks by stg_shard_assign (strong scaling)"),
+              "l2": "inputs_larger_than_L2",
+              "stages": ["a1-a5 coverage + junction support (count_good_junctions)", "a7 junction pass + good_junc",
+                         "a8 + a9 read repair, groups, colours, bundles", "a19 neutral single-exon predictions",
+                         "a10 create_graph", "a11 read -> transfrag", "a12 process_transfrags",
+                         "a13-a15 find_transcripts / push_max_flow / store_transcript"],
+              "scope": "value / e2e cover the whole of infer_transcripts (rows a1-a15 + a19, short-read de novo); the reference arm "
+                       "times the reference's own count_good_junctions + build_graphs on the same bundles"}
 
     # ---------------- reference arm: the reference's own CPU code, all host threads, bounded sample ----------
     if args.impl == "reference":
         if rank != 0:
             return
         threads = os.cpu_count() or 1
-        base, _ = build_workload(1, args.base_bundles, 0)
-        # a step = one pass over a bounded sample sized for ~seconds of CPU work
-        nb = min(2000, base["b_start"].size)
+        base, _ = build_workload(1, args.part_bundles, 0)
+        nb = min(2000, base["b_start"].size)   # a step = one pass over a bounded sample sized for ~seconds of CPU work
         for _ in range(args.warmup):
             reference_hot(base, nb, threads, 1)
         vals = [reference_hot(base, nb, threads, 1) for _ in range(max(1, args.steps))]
@@ -172,13 +189,15 @@ def main():
         cb["value"] = v
         line = {"metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * statistics.median(x["compute_s"] for x in vals),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "impl": "reference", "cpu_baseline": cb,
                 "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
     # ---------------- our arm ----------------------------------------------------------------------------------
+    # the workload first (worker processes are forked: no CUDA context may exist yet)
+    base, arrays = build_workload(args.parts, args.part_bundles, rank if args.scaling == "weak" else 0)
     import torch
     from stringtie_b200 import synth
     from stringtie_b200.abi import make_packed
@@ -191,10 +210,19 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    base, arrays = build_workload(args.replicas, args.base_bundles, rank)
+    shard_info = None
+    if args.scaling == "strong" and world > 1:
+        from stringtie_b200 import shard as shard_mod
+        idx, cost = shard_mod.shard(arrays, world)
+        total_reads = int(arrays["r_start"].size); total_bundles = int(arrays["b_start"].size)
+        arrays = shard_mod.take_bundles(arrays, idx[rank])
+        shard_info = {"rank_cost": [float(c) for c in cost], "bundles_this_rank": int(idx[rank].size)}
     n_reads = int(arrays["r_start"].size)
     n_bundles = int(arrays["b_start"].size)
+    if args.scaling == "strong" and world > 1:
+        job_reads, job_bundles = total_reads, total_bundles
+    else:
+        job_reads, job_bundles = world * n_reads, world * n_bundles
     in_bytes = synth.total_input_bytes(arrays)
 
     eng = Engine(local_rank)
@@ -207,23 +235,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def all_stages(b):
+        eng.run(b, sync=False)
+        eng.build_groups(b)
+        eng.neutral_predictions_only(b)
+        eng.assemble(b)
+        if dist is not None:
+            # the path's only collective (stringtie.cpp:1490-1497): the global totals of the FPKM / TPM pass, reduced on the
+            # device and all-reduced from there — no host round trip
+            eng.reduce_totals(b, totals_dev.data_ptr())
+            with torch.cuda.stream(stream):
+                dist.all_reduce(totals_dev)
+
     # ---- resident-input measurement -------------------------------------------------------------------------
     batch = eng.upload(arrays)
 
     def step_resident():
-        eng.run(batch, sync=False)
-        if dist is not None:  # the path's only collective: the global totals needed for TPM normalisation
-            eng.sync()
-            t = eng.fetch_cov_totals(batch)
-            totals_dev.copy_(torch.from_numpy(np.array([t[:, 1].sum(), float(n_reads), float(n_bundles)])))
-            dist.all_reduce(totals_dev)
+        eng.rewind(batch)
+        all_stages(batch)
 
-    # clocks / throttle reasons are sampled under this workload: the sampler (nvidia-smi -lms 100) needs a few hundred
-    # ms to deliver its first line on a multi-GPU box, longer than the timed region, so it starts before the warm-up
-    # and, if it still has too few lines afterwards, untimed passes of the same workload keep the load up for it
     sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step_resident()
+    eng.sync()
     eng.set_profiling(True)
     barrier()
     l0 = eng.launch_counter()
@@ -242,7 +276,7 @@ def main():
     eng.set_profiling(False)
     t_extra, n_extra = time.perf_counter(), 0
     while len(sampler.rows) < 5 and time.perf_counter() - t_extra < 3.0:   # untimed: same kernels, for the clock sampler
-        eng.run(batch, sync=True)                                           # (no collective: ranks loop independently)
+        step_resident(); eng.sync()
         n_extra += 1
     clocks = sampler.stop()
     clocks["window"] = "warm-up + timed passes" + (f" + {n_extra} untimed passes of the same workload" if n_extra else "")
@@ -253,56 +287,42 @@ def main():
     ms_step = ms_total / args.steps
     L, S, J = eng.stats(batch)
     kmean = {k: statistics.mean(v) for k, v in ktimes.items()}
-    # ---- the next rows (SURVEY §8 a8 + a9: read repair, groups, colours, bundles / bundlenodes), measured once on
-    # the resident batch, outside the timed region: reported beside the headline, not part of it
-    groups_stage = None
-    if not args.skip_groups:
-        try:
-            eng.set_profiling(True)
-            eng.sync()
-            t0 = time.perf_counter()
-            eng.build_groups(batch)
-            eng.sync()
-            wall = time.perf_counter() - t0
-            gk = {n: ms for n, ms in eng.kernel_times() if n.startswith("groups")}
-            gms = sum(gk.values())
-            groups_stage = {"rows": "a8 + a9 (stg_build_groups)", "kernel_ms": gk, "ms": gms, "wall_ms": 1e3 * wall,
-                            "reads_per_s": n_reads / (gms * 1e-3) if gms else None,
-                            "groups": int(eng.fetch_groups_array(batch, "GROUP_OFF")[-1]),
-                            "bundlenodes": int(eng.fetch_groups_array(batch, "N_BN").sum()),
-                            "note": "per GPU, one pass, outside the timed region; wall includes first-use cudaMalloc of the stage's buffers"}
-            # row a19 (de novo part): single-exon predictions of the neutral bundles, from the device-resident bundlenodes
-            eng.sync()
-            t0 = time.perf_counter()
-            npred = eng.neutral_predictions(batch)
-            eng.sync()
-            nk = {n: ms for n, ms in eng.kernel_times() if n.startswith("neutral") or n == "find_trims"}
-            groups_stage["row_a19_neutral_predictions"] = {"kernel_ms": nk, "ms": sum(nk.values()),
-                                                           "wall_ms": 1e3 * (time.perf_counter() - t0),
-                                                           "predictions": int(npred["start"].size)}
-        except Exception as ex:   # the headline must not depend on the newer stage
-            groups_stage = {"error": str(ex)}
-    eng.set_profiling(False)
+    pr = eng.fetch_predictions(batch)
+    results = {"graphs": int(eng.fetch_asm_array(batch, "G_BUNDLE").size), "graph_nodes": int(eng.fetch_asm_array(batch, "N_START").size),
+               "transfrags": int(eng.fetch_asm_array(batch, "G_NTF").sum()), "predictions": int(pr["start"].size),
+               "exons": int(pr["e_start"].size), "groups": int(eng.fetch_groups_array(batch, "GROUP_OFF")[-1])}
     batch.free()
 
     # ---- end-to-end through the C ABI from pinned host buffers ------------------------------------------------
     e2e = None
     if not args.skip_e2e:
         from stringtie_b200.stgb import INPUT_FIELDS
-        pinned = {}
-        for k in INPUT_FIELDS:
-            tns = torch.from_numpy(np.ascontiguousarray(arrays[k])).pin_memory()
-            pinned[k] = tns
+        pinned = {k: torch.from_numpy(np.ascontiguousarray(arrays[k])).pin_memory() for k in INPUT_FIELDS}
         parr = {k: v.numpy() for k, v in pinned.items()}
         pb, keep = make_packed(parr)
-        d2h_bytes = (3 * 8 + 1 + 5 * 8 + 4 + 2) * int(pb.n_juncs) + 3 * 8 * n_bundles
+        cov_host = None
+        if not args.e2e_no_bpcov:
+            try:   # BundleData::bpcov of every bundle comes back too: the reference's printResults reads it on the host
+                b0 = eng.upload_packed(pb, keep)
+                cov_floats = eng.cov_total_floats(b0)
+                b0.free()
+                cov_host = torch.empty(cov_floats, dtype=torch.float32).pin_memory()
+            except Exception as ex:
+                cov_host = None
+                config["e2e_bpcov"] = f"not copied back (pinned allocation failed: {ex})"
+        d2h = [0]
 
         def step_e2e():
             b = eng.upload_packed(pb, keep)
-            eng.run(b, sync=False)
-            eng.fetch_junction_support(b)
-            eng.fetch_junction_pass(b)
-            eng.fetch_cov_totals(b)
+            all_stages(b)
+            p = eng.fetch_predictions(b)
+            n = eng.fetch_neutral(b)
+            nf = eng.fetch_groups_array(b, "NUM_FRAGMENTS"); fl = eng.fetch_groups_array(b, "FRAG_LEN")
+            nbytes = sum(x.nbytes for x in p.values()) + sum(x.nbytes for x in n.values()) + nf.nbytes + fl.nbytes
+            if cov_host is not None:
+                eng.fetch_bpcov_all_into(b, cov_host.data_ptr())
+                nbytes += cov_host.numel() * 4
+            d2h[0] = nbytes
             b.free()
 
         for _ in range(max(1, min(args.warmup, 2))):
@@ -310,23 +330,22 @@ def main():
         barrier()
         n_e2e = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
-        ev0.record(stream)
         for _ in range(n_e2e):
             step_e2e()
-        ev1.record(stream)
         barrier()
         wall = (time.perf_counter() - t0) / n_e2e
         if dist is not None:
             t = torch.tensor([wall], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             wall = float(t.item())
-        e2e = {"value": world * n_reads / wall, "unit": "reads/s", "h2d_bytes_per_step": in_bytes,
-               "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * wall, "steps": n_e2e,
-               "timing": "host wall clock around stg_upload (H2D of every input array from pinned memory) + stg_run + D2H of "
-                         "junction support, the junction-pass table and coverage totals + stg_free_batch (device blocks "
-                         "recycled by the context pool), max over ranks; bpcov stays in HBM for the stages that follow. "
-                         "(Streaming the workload as 5 batches over 2 contexts/threads measured 120 ms: PCIe is the "
-                         "bound, splitting only adds fixed costs.)"}
+        e2e = {"value": job_reads / wall, "unit": "reads/s", "h2d_bytes_per_step": in_bytes,
+               "d2h_bytes_per_step": d2h[0], "ms_per_step": 1e3 * wall, "steps": n_e2e,
+               "bpcov_copied_back": cov_host is not None,
+               "timing": "host wall clock around stg_upload (H2D of every input array from pinned memory) + stg_run + "
+                         "stg_build_groups + stg_neutral_predictions + stg_assemble + D2H of BundleData::pred (neutral and graph "
+                         "predictions with exons), num_fragments, frag_len and — unless --e2e-no-bpcov — the whole of bpcov into "
+                         "pinned host memory (the reference's printResults, which stays on the host, reads it) + stg_free_batch; "
+                         "max over ranks"}
 
     if rank != 0:
         if dist is not None:
@@ -339,38 +358,41 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    cov_kernels = [k for k in kmean if not (k.startswith("groups") or k.startswith("asm") or k.startswith("neutral") or k == "find_trims")]
+    t_cov = sum(kmean[k] for k in cov_kernels) or float("nan")
     t_tile = sum(kmean.get(k, 0.0) for k in ("deep_deposit", "cov_tile", "cov_fill")) or float("nan")
-    alg_tile = 24.0 * L + 13.0 * S          # bytes the dominant kernel's work amounts to
+    alg_cov = 24.0 * L + 13.0 * S + 8.0 * J       # DESIGN.md §6 / SURVEY.md §8d: algorithmic bytes of the coverage stage
     traffic = None
-    try:  # DRAM bytes of the same kernels from the committed ncu --set full capture (only valid for the default workload)
+    try:  # DRAM bytes of the bpcov kernels from the committed ncu --set full capture (valid for the default workload shape)
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if args.replicas == REPLICAS and args.base_bundles == BASE_BUNDLES:
-            traffic = float(tj["traffic_bytes_per_pass"])
+        traffic = float(tj["traffic_bytes_per_pass"])
     except Exception:
         pass
-    alg_stage = alg_tile + 8.0 * J
-    t_stage = sum(kmean.values())
-    roofline = {"bound": "hbm", "kernel": "deep_deposit + cov_tile + cov_fill (ordered deposit, recurrences and the bpcov write)", "achieved": alg_tile / (t_tile * 1e-3) / 1e9, "peak": peak,
+    t_all = sum(kmean.values())
+    dom = max(kmean, key=kmean.get) if kmean else None
+    roofline = {"bound": "hbm", "kernel": "coverage stage: every kernel of count_good_junctions + the junction pass (rows a1-a7)",
+                "achieved": alg_cov / (t_cov * 1e-3) / 1e9, "peak": peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 (B200_PROFILING.md)",
-                "unit": "GB/s", "frac": alg_tile / (t_tile * 1e-3) / 1e9 / peak, "traffic": traffic,
-                "algorithmic_bytes": alg_tile, "formula": "24*L + 13*S (SURVEY.md §8d; the 8*J term belongs to expand_count)",
-                "L": L, "S": S, "J": J, "kernel_ms": t_tile,
-                "stage": {"achieved": alg_stage / (t_stage * 1e-3) / 1e9, "frac": alg_stage / (t_stage * 1e-3) / 1e9 / peak,
-                          "ms": t_stage, "formula": "24*L + 13*S + 8*J over all kernels of the stage"}}
+                "unit": "GB/s", "frac": alg_cov / (t_cov * 1e-3) / 1e9 / peak, "traffic": traffic,
+                "algorithmic_bytes": alg_cov, "formula": "24*L + 13*S + 8*J (SURVEY.md §8d) over all kernels of the stage",
+                "L": L, "S": S, "J": J, "kernel_ms": t_cov, "share_of_step": t_cov / t_all if t_all else None,
+                "bpcov_kernels": {"kernels": "deep_deposit + cov_tile + cov_fill", "ms": t_tile,
+                                  "achieved": (24.0 * L) / (t_tile * 1e-3) / 1e9, "formula": "24*L (difference array read + bpcov write)"},
+                "dominant_kernel": {"name": dom, "ms": kmean.get(dom) if dom else None, "share_of_step": (kmean[dom] / t_all) if dom and t_all else None,
+                                    "bound": "latency of the deepest bundle (one CTA / warp walks it in read order): not an HBM-bound kernel"}}
 
     cpu_baseline = None
     if not args.skip_cpu_baseline:
-        cpu_baseline = reference_hot(base, 2000, os.cpu_count() or 1, 3)
+        cpu_baseline = reference_hot(base, 2000, os.cpu_count() or 1, 2, stages=("--full", "--a7", "--a9b", "--a11"))
 
-    line = {"metric": METRIC, "value": world * n_reads / (ms_step * 1e-3), "unit": "reads/s", "n_gpus": world,
+    line = {"metric": METRIC, "value": job_reads / (ms_step * 1e-3), "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config, "bundles_per_sec": world * n_bundles / (ms_step * 1e-3), "reads_per_gpu": n_reads,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config, "bundles_per_sec": job_bundles / (ms_step * 1e-3), "reads_per_gpu": n_reads,
             "bundles_per_gpu": n_bundles, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "kernel_ms": kmean, "rows_a8_a9": groups_stage}
-    if groups_stage and groups_stage.get("ms"):
-        # everything built so far in one figure: rows a1-a9 resident (the headline `value` stays the stages of round 1)
-        groups_stage["pipeline_a1_to_a9_reads_per_s"] = world * n_reads / ((ms_step + groups_stage["ms"]) * 1e-3)
+            "cpu_baseline": cpu_baseline, "kernel_ms": kmean, "kernel_ms_total": t_all, "results": results}
+    if shard_info:
+        line["shard"] = shard_info
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -277,6 +277,13 @@ enum stg_asm_array {
   STG_AA_COUNT
 };
 int stg_assemble(stg_ctx* ctx, stg_dbatch* batch);
+/* Forget what stg_build_groups / stg_neutral_predictions / stg_assemble left for a resident batch (the device blocks go
+ * back to the context's pool), so that these stages can run again on it (bench.py times them this way). */
+int stg_rewind(stg_ctx* ctx, stg_dbatch* batch);
+/* Sums over the batch of BundleData::num_fragments and frag_len (0 before stg_build_groups) and of the clamped lane-1
+ * coverage, written to three f64 in DEVICE memory, asynchronously on the context stream: the values a multi-GPU host
+ * all-reduces for the FPKM / TPM pass (stringtie.cpp:1490-1497, 915-917). */
+int stg_reduce_totals(stg_ctx* ctx, stg_dbatch* batch, void* dev_out3);
 int stg_asm_array_info(const stg_dbatch* batch, int which, int64_t* count, int32_t* elem_bytes);
 int stg_fetch_asm_array(stg_ctx* ctx, const stg_dbatch* batch, int which, int64_t first, int64_t count, void* out);
 

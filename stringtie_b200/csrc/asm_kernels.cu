@@ -465,9 +465,30 @@ __global__ void __launch_bounds__(256) asm_exon_scatter_kernel(AsmView A, uint32
   for (uint32_t x = 0; x < n; x++) { A.oe_start[o + x] = A.pe_start[e0 + x]; A.oe_end[o + x] = A.pe_end[e0 + x]; A.oe_cov[o + x] = A.pe_cov[e0 + x]; }
 }
 
+// global sums the host accumulates per bundle under countMutex (stringtie.cpp:1490-1497): sum of the bundles'
+// num_fragments and frag_len, plus the total clamped coverage of lane 1; one block, fixed order (deterministic)
+__global__ void __launch_bounds__(1024) asm_totals_kernel(int64_t nb, const double* __restrict__ numfrag, const double* __restrict__ fraglen,
+                                                          const double* __restrict__ covtot, double* out) {
+  __shared__ double sh[3][1024];
+  double a = 0, b = 0, c = 0;
+  for (int64_t i = threadIdx.x; i < nb; i += 1024) { a += numfrag ? numfrag[i] : 0.0; b += fraglen ? fraglen[i] : 0.0; c += covtot[3 * i + 1]; }
+  sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b; sh[2][threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 512; o; o >>= 1) {
+    if ((int)threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; sh[2][threadIdx.x] += sh[2][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = sh[0][0]; out[1] = sh[1][0]; out[2] = sh[2][0]; }
+}
+
 unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
 }  // namespace
+
+cudaError_t launch_asm_totals(int64_t nb, const double* numfrag, const double* fraglen, const double* covtot, double* out, cudaStream_t st) {
+  asm_totals_kernel<<<1, 1024, 0, st>>>(nb, numfrag, fraglen, covtot, out);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_asm_enum(const DevBatchView& v, const AsmView& A, cudaStream_t st) {
   if (v.n_bundles) asm_enum_kernel<<<blocks(2 * v.n_bundles, 256), 256, 0, st>>>(v, A);

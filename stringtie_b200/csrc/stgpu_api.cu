@@ -130,6 +130,7 @@ struct stg_dbatch {
   std::vector<uint32_t> h_nreads;  // [n_bundles]
   AsmView av;                      // rows a10-a15 (stg_assemble)
   bool assembled = false;
+  size_t stage_mark = 0;           // allocs.size() when stg_build_groups started: what stg_rewind gives back
 };
 
 namespace {
@@ -763,6 +764,7 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
   DevBatchView& v = d->v;
   GroupsView& g = d->gv;
   memset(&g, 0, sizeof(g));
+  d->stage_mark = d->allocs.size();
   g.bundledist = pr.bundledist;
   const int64_t nb = v.n_bundles, nr = v.n_reads, ns = v.n_segs, np = v.n_pairs, nj = v.n_juncs, ni = ns - nr;
   int rc = STG_OK;
@@ -1018,6 +1020,35 @@ int stg_fetch_groups_array(stg_ctx* ctx, const stg_dbatch* d, int which, int64_t
   CK(ctx, cudaSetDevice(ctx->device));
   CK(ctx, cudaMemcpyAsync(out, (const char*)a.p + (size_t)first * a.sz, (size_t)count * a.sz, cudaMemcpyDeviceToHost, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return STG_OK;
+}
+
+// Forget the results of stg_build_groups / stg_neutral_predictions / stg_assemble of a resident batch (their device
+// blocks go back to the context's pool) so that the stages can run again on it.
+int stg_rewind(stg_ctx* ctx, stg_dbatch* d) {
+  if (!ctx || !d) return fail(ctx, STG_EINVAL, "stg_rewind: null argument");
+  if (!d->groups_built) return STG_OK;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (size_t i = d->stage_mark; i < d->allocs.size(); i++) { ctx->pool_free.push_back(d->allocs[i]); ctx->pool_bytes += d->allocs[i].bytes; }
+  }
+  d->allocs.resize(d->stage_mark);
+  d->groups_built = false; d->neutral_done = false; d->assembled = false;
+  return STG_OK;
+}
+
+// sums over the batch of BundleData::num_fragments, frag_len (after stg_build_groups; 0 before) and of the clamped lane-1
+// coverage, written to three doubles in DEVICE memory (asynchronous on the context stream): what a multi-GPU host
+// all-reduces for the FPKM / TPM pass (stringtie.cpp:1490-1497, 915-917)
+int stg_reduce_totals(stg_ctx* ctx, stg_dbatch* d, void* dev_out3) {
+  if (!ctx || !d || !dev_out3) return fail(ctx, STG_EINVAL, "stg_reduce_totals: null argument");
+  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_reduce_totals: batch has not been run");
+  CK(ctx, cudaSetDevice(ctx->device));
+  ctx->launches += 1;
+  CK(ctx, launch_asm_totals(d->v.n_bundles, d->groups_built ? d->gv.b_numfrag : nullptr, d->groups_built ? d->gv.b_fraglen : nullptr,
+                            d->v.b_cov_total, (double*)dev_out3, ctx->stream));
   return STG_OK;
 }
 

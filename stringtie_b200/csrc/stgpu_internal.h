@@ -265,5 +265,6 @@ cudaError_t launch_asm_geneno(const DevBatchView& v, const AsmView& A, const int
 cudaError_t launch_asm_pred_scatter(const AsmView& A, uint32_t npool, cudaStream_t st);
 cudaError_t launch_asm_exon_scatter(const AsmView& A, uint32_t npool, cudaStream_t st);
 size_t asm_graph_struct_bytes();
+cudaError_t launch_asm_totals(int64_t nb, const double* numfrag, const double* fraglen, const double* covtot, double* out, cudaStream_t st);
 int64_t scan_partials_needed(int64_t n);
 int cov_tile_smem_bytes();

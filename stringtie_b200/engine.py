@@ -24,7 +24,7 @@ EXPORTS = [
     "stg_sync", "stg_free_batch", "stg_trim", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
     "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_trims_capacity", "stg_find_trims", "stg_infer_transcripts",
     "stg_build_groups", "stg_groups_array_info", "stg_fetch_groups_array", "stg_neutral_predictions",
-    "stg_assemble", "stg_asm_array_info", "stg_fetch_asm_array",
+    "stg_assemble", "stg_asm_array_info", "stg_fetch_asm_array", "stg_rewind", "stg_reduce_totals",
     "stg_shard_assign", "stg_set_profiling", "stg_kernel_count", "stg_kernel_time", "stg_launch_counter", "stg_batch_stats", "stg_stream",
 ]
 
@@ -112,6 +112,8 @@ def load_library() -> C.CDLL:
     L.stg_assemble.argtypes = [vp, vp]
     L.stg_asm_array_info.argtypes = [vp, C.c_int, c_i64p, C.POINTER(C.c_int32)]
     L.stg_fetch_asm_array.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
+    L.stg_rewind.argtypes = [vp, vp]
+    L.stg_reduce_totals.argtypes = [vp, vp, vp]
     L.stg_shard_assign.argtypes = [C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
                                    C.POINTER(C.c_int32), c_f64p]
     L.stg_set_profiling.argtypes = [vp, C.c_int]
@@ -291,6 +293,13 @@ class Engine:
         and neutral_predictions)."""
         self._ck(self.L.stg_assemble(self.ctx, batch.handle))
 
+    def rewind(self, batch: DeviceBatch) -> None:
+        self._ck(self.L.stg_rewind(self.ctx, batch.handle))
+
+    def reduce_totals(self, batch: DeviceBatch, dev_ptr: int) -> None:
+        """num_fragments, frag_len and lane-1 coverage totals of the batch into 3 f64 at device address dev_ptr (async)."""
+        self._ck(self.L.stg_reduce_totals(self.ctx, batch.handle, C.c_void_p(dev_ptr)))
+
     def fetch_asm_array(self, batch: DeviceBatch, which: str) -> np.ndarray:
         idx = ASM_ARRAYS.index(which)
         n, sz = C.c_int64(), C.c_int32()
@@ -306,6 +315,24 @@ class Engine:
         m = {"PRED_OFF": "off", "P_START": "start", "P_END": "end", "P_COV": "cov", "P_TLEN": "tlen", "P_GENENO": "geneno",
              "P_STRAND": "strand", "P_EXON_OFF": "exon_off", "E_START": "e_start", "E_END": "e_end", "E_COV": "e_cov"}
         return {v: self.fetch_asm_array(batch, k) for k, v in m.items()}
+
+    def neutral_predictions_only(self, batch: DeviceBatch) -> None:
+        self._ck(self.L.stg_neutral_predictions(self.ctx, batch.handle))
+
+    def fetch_neutral(self, batch: DeviceBatch) -> Dict[str, np.ndarray]:
+        return {k[3:].lower(): self.fetch_groups_array(batch, k) for k in NEUTRAL_ARRAYS}
+
+    def cov_total_floats(self, batch: DeviceBatch) -> int:
+        """Number of floats stg_fetch_bpcov_all writes (the padded 3-lane bpcov of every bundle)."""
+        off = np.zeros(batch.n_bundles, dtype=np.int64)
+        stride = np.zeros(batch.n_bundles, dtype=np.int64)
+        tot = C.c_int64()
+        self._ck(self.L.stg_cov_layout(batch.handle, ptr(off), ptr(stride), C.byref(tot)))
+        return int(tot.value)
+
+    def fetch_bpcov_all_into(self, batch: DeviceBatch, host_ptr: int) -> None:
+        """bpcov of every bundle into caller memory (pinned memory makes it one DMA)."""
+        self._ck(self.L.stg_fetch_bpcov_all(self.ctx, batch.handle, C.cast(C.c_void_p(host_ptr), c_f32p)))
 
     def fetch_cov_totals(self, batch: DeviceBatch) -> np.ndarray:
         out = np.empty(batch.n_bundles * 3, dtype=np.float64)

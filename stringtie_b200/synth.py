@@ -413,6 +413,39 @@ def replicate(a: Dict[str, np.ndarray], k: int, gap: int = 100000) -> Dict[str, 
     return out
 
 
+def concat(parts, gap: int = 100000) -> Dict[str, np.ndarray]:
+    """Independent packed batches laid one after the other on the coordinate axis (each shifted past the previous one)."""
+    if len(parts) == 1:
+        return parts[0]
+    out = {k: [] for k in parts[0]}
+    shift = 0
+    nr = ns = npair = nj = 0
+    for i, a in enumerate(parts):
+        last = i == len(parts) - 1
+        for key in ("b_start", "b_end"):
+            out[key].append((a[key].astype(np.int64) + shift).astype(np.int32))
+        for key in ("r_start", "r_end", "seg_start", "seg_end"):
+            out[key].append((a[key].astype(np.int64) + shift).astype(np.uint32))
+        sentinel = (a["j_start"] == 0) & (a["j_end"] == 0)
+        for key in ("j_start", "j_end"):
+            x = a[key].astype(np.int64) + shift
+            x[sentinel] = 0
+            out[key].append(x.astype(np.uint32))
+        for key in ("r_len", "r_count", "r_nh", "r_strand", "r_flags", "rjunc_idx", "pair_idx", "pair_cnt", "j_strand",
+                    "j_guide_match", "j_nreads", "j_nm", "j_mm"):
+            out[key].append(a[key])
+        for key, n in (("b_read_off", nr), ("b_junc_off", nj), ("r_seg_off", ns), ("r_pair_off", npair)):
+            body = a[key].astype(np.int64) + n
+            out[key].append((body if last else body[:-1]).astype(np.uint32))
+        nr += a["r_start"].size; ns += a["seg_start"].size; npair += a["pair_idx"].size; nj += a["j_start"].size
+        shift += int(a["b_end"].max()) + gap - (0 if i else 0)
+        if shift >= 2 ** 31 - 2 ** 27:
+            raise ValueError("concatenated coordinates overflow int32")
+        shift = shift if i == 0 else shift
+    # shifts are cumulative: part i starts past the end of part i-1
+    return {k: np.concatenate(v) for k, v in out.items()}
+
+
 def total_input_bytes(a: Dict[str, np.ndarray]) -> int:
     from .stgb import INPUT_FIELDS
     return int(sum(a[k].nbytes for k in INPUT_FIELDS))
