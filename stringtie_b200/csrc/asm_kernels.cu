@@ -280,53 +280,6 @@ __device__ __forceinline__ uint32_t tf_slot0(const DevBatchView& v, const AsmVie
   return A.tf0_off[A.gr_first[2 * b]] + A.r_ntf[v.b_read_off[b]];
 }
 
-__global__ void __launch_bounds__(128) asm_tf_commit_kernel(DevBatchView v, AsmView A) {
-  __shared__ float stage[4][32];
-  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= v.n_bundles) return;
-  const int lane = threadIdx.x & 31;
-  uint32_t nt0;
-  const uint32_t nrec = bundle_nrec(v, A, (uint32_t)b, &nt0);
-  if (nrec + nt0 == 0) { if (lane == 0) A.b_ntf[b] = 0; return; }
-  const uint32_t s0 = tf_slot0(v, A, (uint32_t)b);
-  TfTable T;
-  T.slot_hash = A.slot_hash + A.tab_off[b]; T.slot_id = A.slot_id + A.tab_off[b]; T.cap = A.tab_off[b + 1] - A.tab_off[b];
-  T.rec_graph = A.rec_graph; T.rec_ab = A.rec_ab; T.rec_key_off = A.rec_koff; T.rec_key_len = A.rec_klen; T.rec_hash = A.rec_hash; T.key = A.key;
-  T.rec_tf = A.rec_tf; T.tf_rep = A.tf_rep + s0; T.tf_abund = A.tf_abund + s0; T.tf_graph = A.tf_graph + s0;
-  // the transfrags of create_graph: each is its own transfrag (the reference never looks them up among themselves); the
-  // ones that do not start at the source can be met again by reads (update_abundance finds them in the trie)
-  const uint32_t t0a = A.tf0_off[A.gr_first[2 * b]];
-  int ntf = 0;
-  if (lane == 0) {
-    for (uint32_t r = t0a; r < t0a + nt0; r++) {
-      const int id = ntf++;
-      T.tf_rep[id] = (int32_t)r; T.tf_abund[id] = T.rec_ab[r]; T.tf_graph[id] = T.rec_graph[r]; T.rec_tf[r] = id;
-      if ((T.key[T.rec_key_off[r]] & ~FR_FLAG) != 0u) {
-        const unsigned long long h = T.rec_hash[r];
-        uint32_t slot = (uint32_t)(h >> 17) & (T.cap - 1);
-        for (;;) {
-          const unsigned long long sh = T.slot_hash[slot];
-          if (sh == 0ull) { T.slot_hash[slot] = h; T.slot_id[slot] = id; break; }
-          if (sh == h && tf_same_key(T, (uint32_t)T.tf_rep[T.slot_id[slot]], r)) { T.slot_id[slot] = id; break; }   // a later one replaces it
-          slot = (slot + 1) & (T.cap - 1);
-        }
-      }
-    }
-  }
-  ntf = __shfl_sync(0xffffffffu, ntf, 0);
-  __syncwarp();
-  const uint32_t r0 = (uint32_t)A.n_tf0 + A.r_ntf[v.b_read_off[b]];
-  ntf = tf_commit_warp(T, r0, r0 + nrec, stage[(threadIdx.x >> 5) & 3], ntf);
-  if (lane == 0) A.b_ntf[b] = ntf;
-}
-
-__global__ void __launch_bounds__(128) asm_nodecov_commit_kernel(DevBatchView v, AsmView A) {
-  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= v.n_bundles) return;
-  const uint32_t c0 = A.r_ncov[v.b_read_off[b]], c1 = A.r_ncov[v.b_read_off[b + 1]];
-  if (c1 > c0) nodecov_commit_warp(A.cov_node, A.cov_val, c0, c1, A.n_cov);
-}
-
 // per graph: how many transfrags, how many of them have a pair of consecutive nodes without a pattern edge, and the
 // sum of their node spans (bounds of the incidence lists of a12)
 __global__ void __launch_bounds__(256) asm_tf_stats_kernel(DevBatchView v, AsmView A) {
@@ -527,11 +480,8 @@ cudaError_t launch_asm_table_caps(const DevBatchView& v, const AsmView& A, cudaS
   asm_table_caps_kernel<<<blocks(v.n_bundles + 1, 256), 256, 0, st>>>(v, A);
   return cudaGetLastError();
 }
-cudaError_t launch_asm_commit(const DevBatchView& v, const AsmView& A, cudaStream_t st) {
-  if (!v.n_bundles) return cudaSuccess;
-  asm_tf_commit_kernel<<<blocks(v.n_bundles * 32, 128), 128, 0, st>>>(v, A);
-  asm_nodecov_commit_kernel<<<blocks(v.n_bundles * 32, 128), 128, 0, st>>>(v, A);
-  asm_tf_stats_kernel<<<blocks(v.n_bundles * 32, 256), 256, 0, st>>>(v, A);
+cudaError_t launch_asm_tf_stats(const DevBatchView& v, const AsmView& A, cudaStream_t st) {
+  if (v.n_bundles) asm_tf_stats_kernel<<<blocks(v.n_bundles * 32, 256), 256, 0, st>>>(v, A);
   asm_flow_sizes_kernel<<<blocks(A.n_graphs + 1, 256), 256, 0, st>>>(A);
   return cudaGetLastError();
 }

@@ -1168,15 +1168,29 @@ int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
   uint32_t ts = 0;
   TOTAL(ts, A.tab_off, nb);
   CK(ctx, cudaStreamSynchronize(st));
-  TEMP(A.slot_hash, ts); TEMP(A.slot_id, ts);
-  ZERO(A.slot_hash, ts);
-  TEMP(A.tf_rep, NR); TEMP(A.tf_abund, NR); TEMP(A.tf_graph, NR); TEMP(A.b_ntf, nb);
+  TEMP(A.slot_hash, ts); TEMP(A.slot_minrec, ts); TEMP(A.slot_tf0, ts);
+  ZERO(A.slot_hash, ts); ONES(A.slot_minrec, ts); ONES(A.slot_tf0, ts);
+  TEMP(A.tf_rep, NR); TEMP(A.tf_abund, NR); TEMP(A.tf_graph, NR); TEMP(A.b_ntf, nb); TEMP(A.b_deep, nb);
+  TEMP(A.rec_slot, tr); TEMP(A.rec_first, (int64_t)tr + 1 + 16); TEMP(A.ab_sorted, tr); TEMP(A.cov_sorted, tc);
+  A.pool_cap = (unsigned long long)(((int64_t)tr + tc) / 2 + (4 << 20));
+  A.deep_cap = 8192;
+  TEMP(A.pool, (int64_t)A.pool_cap); TEMP(A.pool_ctr, 1); TEMP(A.deep_cnt, 2);
+  TEMP(A.deep_tf_bundle, A.deep_cap); TEMP(A.deep_cov_bundle, A.deep_cap); TEMP(A.deep_tf_off, A.deep_cap); TEMP(A.deep_cov_off, A.deep_cap);
+  ZERO(A.pool_ctr, 1); ZERO(A.deep_cnt, 2);
   KEEP(A.g_nt, G); TEMP(A.g_ngap, G); TEMP(A.g_reachsum, G); TEMP(A.g_fill, G);
   ZERO(A.g_nt, G); ZERO(A.g_ngap, G); ZERO(A.g_reachsum, G); ZERO(A.g_fill, G);
   TEMP(A.y_tf, (int64_t)G + 1 + 16); TEMP(A.y_pat, (int64_t)G + 1 + 16); TEMP(A.y_path, (int64_t)G + 1 + 16); TEMP(A.y_ntrf, (int64_t)G + 1 + 16);
   TEMP(A.y_istr, (int64_t)G + 1 + 16);
-  { Scope s(ctx, "asm_commit", 9);
-    CK(ctx, launch_asm_commit(v, A, st));
+  unsigned long long* scan_state3 = nullptr;
+  TEMP(scan_state3, (int64_t)tr / 2048 + 8);
+  { Scope s(ctx, "asm_tf_table", 6);
+    CK(ctx, launch_asm_tf_commit(v, A, st));
+    CK(ctx, launch_scan_exclusive_add(A.rec_first, (int64_t)tr + 1, scan_state3, ticket, st));
+    CK(ctx, launch_asm_tf_ids(v, A, st)); }
+  { Scope s(ctx, "asm_tf_sums", 2); CK(ctx, launch_asm_tf_sums(v, A, st)); }
+  { Scope s(ctx, "asm_nodecov_commit", 2); CK(ctx, launch_asm_nodecov_commit(v, A, st)); }
+  { Scope s(ctx, "asm_tf_stats+sizes", 7);
+    CK(ctx, launch_asm_tf_stats(v, A, st));
     SCAN(A.y_tf, (int64_t)G + 1); SCAN(A.y_pat, (int64_t)G + 1); SCAN(A.y_path, (int64_t)G + 1); SCAN(A.y_ntrf, (int64_t)G + 1); SCAN(A.y_istr, (int64_t)G + 1); }
   uint32_t yt = 0, yp = 0, yh = 0, yn = 0, yi = 0;
   TOTAL(yt, A.y_tf, G); TOTAL(yp, A.y_pat, G); TOTAL(yh, A.y_path, G); TOTAL(yn, A.y_ntrf, G); TOTAL(yi, A.y_istr, G);
@@ -1201,6 +1215,7 @@ int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
   CK(ctx, cudaMemcpyAsync(ctr, A.p_counters, 8, cudaMemcpyDeviceToHost, st));
   CK(ctx, cudaMemcpyAsync(&err, v.err_flag, 4, cudaMemcpyDeviceToHost, st));
   CK(ctx, cudaStreamSynchronize(st));
+  if (err & 0x1000u) return fail(ctx, STG_ERANGE, "stg_assemble: two transfrag keys of one bundle share a 64-bit hash");
   if (err) return fail(ctx, STG_ERANGE, "stg_assemble: a capacity bound of the flow stage was exceeded");
   A.n_pred = ctr[0]; A.n_exon = ctr[1];
   const int64_t NP = A.n_pred;

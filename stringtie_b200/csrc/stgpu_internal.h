@@ -184,6 +184,13 @@ struct AsmView {
   unsigned long long* slot_hash; int32_t* slot_id;  // [tab_off[n_bundles]]
   int32_t* tf_rep; float* tf_abund; int32_t* tf_graph;   // [n_tf0 + n_rec] bundle b from tfslot0(b) = tf0_off[first graph] + r_ntf[first read]
   int32_t* b_ntf;                                   // [n_bundles] distinct transfrags of the bundle
+  uint32_t* slot_minrec; int32_t* slot_tf0;         // [slots] first record of the key; last transfrag of create_graph with this key (-1)
+  uint32_t *rec_slot, *rec_first;                   // [n_rec] slot of the record's key; [n_rec+1] first occurrence flags -> exclusive prefix
+  float *ab_sorted, *cov_sorted;                    // [n_rec], [n_covrec] values in key order (deep bundles)
+  uint32_t* pool; unsigned long long* pool_ctr; unsigned long long pool_cap;   // scratch of the deep bundles' counting sorts
+  uint32_t* deep_cnt; uint32_t deep_cap;            // [2] deep bundles on the transfrag / node-coverage list
+  uint32_t *deep_tf_bundle, *deep_cov_bundle; unsigned long long *deep_tf_off, *deep_cov_off;   // [deep_cap]
+  uint8_t* b_deep;                                  // [n_bundles] bit 0: transfrag sums on the CTA path, bit 1: node coverage
   // a12-a15: per-graph sizes -> prefixes
   uint32_t *g_nt, *g_ngap, *g_reachsum, *g_fill;    // [G] transfrags after a11, with an unflagged pair, sum of (last-first+1); gather cursor
   uint32_t *y_tf, *y_pat, *y_path, *y_ntrf, *y_istr;   // [G+1] capacities, then prefixes
@@ -258,7 +265,11 @@ cudaError_t launch_asm_finish(const DevBatchView& v, const GroupsView& g, const 
 cudaError_t launch_asm_frag_count(const DevBatchView& v, const GroupsView& g, const AsmView& A, cudaStream_t st);
 cudaError_t launch_asm_frag_write(const DevBatchView& v, const GroupsView& g, const AsmView& A, cudaStream_t st);
 cudaError_t launch_asm_table_caps(const DevBatchView& v, const AsmView& A, cudaStream_t st);
-cudaError_t launch_asm_commit(const DevBatchView& v, const AsmView& A, cudaStream_t st);
+cudaError_t launch_asm_tf_commit(const DevBatchView& v, const AsmView& A, cudaStream_t st);
+cudaError_t launch_asm_tf_ids(const DevBatchView& v, const AsmView& A, cudaStream_t st);
+cudaError_t launch_asm_tf_sums(const DevBatchView& v, const AsmView& A, cudaStream_t st);
+cudaError_t launch_asm_nodecov_commit(const DevBatchView& v, const AsmView& A, cudaStream_t st);
+cudaError_t launch_asm_tf_stats(const DevBatchView& v, const AsmView& A, cudaStream_t st);
 cudaError_t launch_asm_gather(const DevBatchView& v, const AsmView& A, cudaStream_t st);
 cudaError_t launch_asm_flow(const DevBatchView& v, const AsmView& A, const AsmParams& P, cudaStream_t st);
 cudaError_t launch_asm_geneno(const DevBatchView& v, const AsmView& A, const int32_t* b_geneno, cudaStream_t st);

@@ -74,3 +74,22 @@ def test_assembly_idempotent_across_batches(engine):
     for k in p1:
         assert np.array_equal(p1[k].view(np.uint8), p2[k].view(np.uint8)), k
     assert np.array_equal(s1["N_COV"].view(np.uint32), s2["N_COV"].view(np.uint32))
+
+
+@need_ref
+def test_assembly_deepest_bundles_of_the_bench_workload(engine):
+    """The deepest bundles of one part of the bench workload (hundreds of thousands of reads in one locus: the CTA paths of
+    the commit stage, the wide kernels of the group stage) plus a random sample, against the reference."""
+    import bench
+    from stringtie_b200 import shard
+    base, _ = bench.build_workload(1, bench.PART_BUNDLES, 0)
+    nr = np.diff(base["b_read_off"].astype(np.int64))
+    order = np.argsort(-nr)
+    rng = np.random.default_rng(5)
+    pick = np.unique(np.concatenate([order[:4], rng.choice(nr.size, 60, replace=False)]))
+    a = shard.take_bundles(base, pick)
+    assert int(np.diff(a["b_read_off"].astype(np.int64)).max()) >= 100000
+    ref = asm_util.ref_full(a)
+    neu, pr, stage = asm_util.gpu_predictions(engine, a)
+    asm_util.assert_same_graph_stage(stage, ref)
+    asm_util.assert_same_predictions(neu, pr, ref)
