@@ -19,6 +19,7 @@
 //                            the only serial part left is the chain of dependent float adds of one key
 #include "asm_device.cuh"
 #include "frag_device.cuh"
+#include "ordered_sum.cuh"
 
 #define ASM_ERR_HASH 0x1000u      // two different transfrag keys of one bundle share a 64-bit hash
 #define DEEP_RECORDS 8192u        // bundles with at least this many records take the CTA path
@@ -142,83 +143,6 @@ __global__ void __launch_bounds__(256) commit_plan_kernel(DevBatchView v, AsmVie
     }
   }
   A.b_deep[b] = deep;
-}
-
-// ---- ordered keyed float sums ------------------------------------------------------------------------------------
-// acc[k] = (...((acc[k] + v_i1) + v_i2) + ...) over the records i1 < i2 < ... of key k, i.e. the reference's "+=" loop
-// over the records in order, for all keys at once.  One CTA; scratch: cnt [W * K] (zeroed), kbase [K + 1], sorted [n].
-template <class KeyFn, class ValFn>
-__device__ void cta_ordered_keyed_sum(uint32_t n, KeyFn key, ValFn val, uint32_t K, float* acc, uint32_t* cnt, uint32_t* kbase, float* sorted) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t W = blockDim.x >> 5;
-  uint32_t S = (n + W - 1) / W;
-  S = (S + 31u) & ~31u;                                  // slices start on a multiple of 32: whole warps step together
-  const uint32_t lo = min(n, w * S), hi = min(n, lo + S);
-  uint32_t* row = cnt + (size_t)w * K;
-  // 1. records per key in this warp's slice
-  for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
-    const uint32_t i = i0 + lane;
-    const bool have = i < hi;
-    const uint32_t k = have ? key(i) : 0xffffffffu - lane;
-    const uint32_t peers = __match_any_sync(0xffffffffu, k);
-    if (have && (__ffs(peers) - 1) == lane) row[k] += __popc(peers);
-    __syncwarp();
-  }
-  __syncthreads();
-  // 2. first slot of every (key, slice): prefix over the slices, then over the keys
-  for (uint32_t k = threadIdx.x; k < K; k += blockDim.x) {
-    uint32_t run = 0;
-    for (uint32_t x = 0; x < W; x++) { const uint32_t c = cnt[(size_t)x * K + k]; cnt[(size_t)x * K + k] = run; run += c; }
-    kbase[k + 1] = run;
-  }
-  __syncthreads();
-  if (w == 0) {   // exclusive scan of the totals (K is small next to n)
-    uint32_t carry = 0;
-    for (uint32_t k0 = 0; k0 < K; k0 += 32) {
-      const uint32_t k = k0 + lane;
-      uint32_t x = k < K ? kbase[k + 1] : 0u;
-      uint32_t inc = x;
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
-      if (k < K) kbase[k + 1] = carry + inc;
-      carry += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    if (lane == 0) kbase[0] = 0;
-  }
-  __syncthreads();
-  // 3. stable scatter of the values
-  for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
-    const uint32_t i = i0 + lane;
-    const bool have = i < hi;
-    const uint32_t k = have ? key(i) : 0xffffffffu - lane;
-    const uint32_t peers = __match_any_sync(0xffffffffu, k);
-    uint32_t at = 0;
-    if (have) at = row[k];
-    __syncwarp();
-    if (have) {
-      sorted[kbase[k] + at + __popc(peers & ((1u << lane) - 1u))] = val(i);
-      if ((__ffs(peers) - 1) == lane) row[k] = at + __popc(peers);
-    }
-    __syncwarp();
-  }
-  __syncthreads();
-  // 4. one warp per key: its run added in order (every lane carries the same sum; values come 32 at a time)
-  for (uint32_t k = w; k < K; k += W) {
-    const uint32_t a = kbase[k], z = kbase[k + 1];
-    if (a == z) continue;
-    float s = acc[k];
-    for (uint32_t j0 = a; j0 < z; j0 += 32) {
-      const uint32_t j = j0 + lane;
-      const float x = j < z ? sorted[j] : 0.f;
-      const int m = (int)min(32u, z - j0);
-      if (m == 32) {
-#pragma unroll
-        for (int l = 0; l < 32; l++) s = __fadd_rn(s, __shfl_sync(0xffffffffu, x, l));
-      } else {
-        for (int l = 0; l < m; l++) s = __fadd_rn(s, __shfl_sync(0xffffffffu, x, l));
-      }
-    }
-    if (lane == 0) acc[k] = s;
-  }
 }
 
 __global__ void __launch_bounds__(DEEP_THREADS) tf_sum_deep_kernel(DevBatchView v, AsmView A) {

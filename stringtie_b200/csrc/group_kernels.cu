@@ -9,6 +9,7 @@
 // The reference's loop is sequential (its state flows both ways between repair, grouping and un-pairing); the walk
 // kernel runs the reads that change no structure in parallel and only the others one by one (groups_device.cuh).
 #include "groups_device.cuh"
+#include "ordered_sum.cuh"
 
 namespace {
 
@@ -104,12 +105,21 @@ struct WalkCtl {
 // way by thread 0 once the pending sums are in.
 // GROW: reads that grow a group stay inside the runs (they record the bounds they depend on; pays off where runs are
 // short, i.e. in shallow bundles); otherwise such a read ends its run.
-template <int GROUPS_WARPS, int MINB, bool GROW>
+// DEFER (the very deep bundles): the float sums of the simple reads are not added step by step by warp 0 — in a window of
+// hundreds of reads that loop is longer than the classification and the other warps wait for it at the barrier (67 % of
+// the stall samples of the deepest C2 bundle, profiles/r3_groups_deepest.md) — but logged per read (visited group,
+// coverage, multi; fragment sums) and added when a read has to be walked the reference's way (walk_read reads the sums)
+// and at the end: a stable counting sort of the logged visits by group, then one warp per group adds its run in read
+// order (ordered_sum.cuh).  Same sums, same order per group.
+#define VLOG_KMAX 2048                                   // groups the sorted path can take (else: the serial loop)
+#define VLOG_SCRATCH (8 * VLOG_KMAX + VLOG_KMAX + 2)      // uint32 per very deep CTA: counts per (warp, group) + group offsets
+template <int GROUPS_WARPS, int MINB, bool GROW, bool DEFER>
 __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(DevBatchView v, GroupsView g, JuncParams prm,
                                                                              uint32_t order_base) {
   constexpr int GROUPS_STEP = 32 * GROUPS_WARPS, GROUPS_CLS = GROUPS_STEP - 32;
   __shared__ GroupSmem M;
-  __shared__ FastRec Rb[2][GROUPS_CLS];   // records of the step being classified / of the run whose sums are pending
+  extern __shared__ __align__(16) unsigned char groups_dyn_smem[];
+  auto Rb = reinterpret_cast<FastRec (*)[GROUPS_CLS]>(groups_dyn_smem);   // [2][GROUPS_CLS] records of the step being classified / of the run whose sums are pending
   __shared__ FastDeps Db[GROW ? GROUPS_CLS : 1];
   __shared__ WalkCtl<GROUPS_WARPS> ctl;
   const uint32_t b = g.order[order_base + blockIdx.x];
@@ -157,6 +167,8 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
   const int inr = (int)nr;
   const unsigned FULL = 0xffffffffu;
   const int ct = tid - 32;                    // index among the classifying threads (warp 0: negative)
+  const size_t vbase = DEFER ? (size_t)g.vlog_off[blockIdx.x] : 0;   // first log entry of this bundle
+  int flushed = 0;                            // uniform: reads [0, flushed) have their sums added
   if (tid == 0) { ctl.err = 0; ctl.last[0] = ctl.last[1] = ctl.last[2] = -1; ctl.n_grow[0] = ctl.n_grow[1] = 0; }
   __syncthreads();
 
@@ -188,12 +200,51 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
     }
   };
 
+  // DEFER: add the logged sums of the reads [flushed, upto), in read order per group; all threads
+  auto flush = [&](int upto) {
+    if (upto <= flushed) return;
+    const uint32_t n6 = (uint32_t)(upto - flushed) * STG_FP_MAXV;
+    const int32_t* lg = g.vlog_grp + (vbase + (size_t)flushed) * STG_FP_MAXV;
+    const float2* lv = g.vlog_val + (vbase + (size_t)flushed) * STG_FP_MAXV;
+    const uint32_t K = (uint32_t)ng_u + 1u;              // the last key takes the empty slots
+    if (K <= VLOG_KMAX && GROUPS_WARPS <= 8) {
+      uint32_t* cnt = g.vlog_cnt + (size_t)blockIdx.x * VLOG_SCRATCH;
+      cta_ordered_keyed_sum2(n6, [&](uint32_t i) { const int32_t x = lg[i]; return x < 0 ? (uint32_t)ng_u : (uint32_t)x; },
+                             [&](uint32_t i) { return lv[i]; }, K, (uint32_t)ng_u, S.g_cov, S.g_multi, cnt, cnt + (size_t)GROUPS_WARPS * K,
+                             g.vlog_sorted + (vbase + (size_t)flushed) * STG_FP_MAXV);
+    } else if (warp == 0) {   // lane l owns the groups with slot % 32 == l
+      int cur = -1;
+      float acc_cov = 0.f, acc_multi = 0.f;
+      for (uint32_t i = 0; i < n6; i++) {
+        const int gr = lg[i];
+        if (gr >= 0 && (gr & 31) == lane) {
+          if (gr != cur) {
+            if (cur >= 0) { S.g_cov[cur] = acc_cov; S.g_multi[cur] = acc_multi; }
+            cur = gr; acc_cov = S.g_cov[gr]; acc_multi = S.g_multi[gr];
+          }
+          acc_multi += lv[i].y; acc_cov += lv[i].x;
+        }
+      }
+      if (cur >= 0) { S.g_cov[cur] = acc_cov; S.g_multi[cur] = acc_multi; }
+    }
+    if (tid == 0) {
+      double a = fl, c = nf;
+      const double* pf = g.vlog_fl + vbase;
+      const double* pn = g.vlog_nf + vbase;
+#pragma unroll 4
+      for (int r = flushed; r < upto; r++) { a += pf[r]; c += pn[r]; }
+      fl = a; nf = c;
+    }
+    __syncthreads();
+    flushed = upto;
+  };
+
   while (true) {
     const bool classify = n < inr && slow_budget == 0;
     FastRec* R = Rb[buf];
     const int hi = n + width < inr ? n + width : inr, me = n + ct;
     int st = 0;                                 // 1 simple, 3 simple + grows a group, 0 not simple, 2 waits
-    if (warp == 0) { if (pend_k) pending_sums(Rb[pend_buf], pend_k); }
+    if (warp == 0) { if (!DEFER && pend_k) pending_sums(Rb[pend_buf], pend_k); }
     else if (classify) {
       if (me < hi) st = GROW ? classify_read<true>(S, me, n, hi, R[ct], &Db[GROW ? ct : 0]) : classify_read<false>(S, me, n, hi, R[ct]);
       ctl.npc[ct] = (st == 1 || (GROW && st == 3)) ? R[ct].npc : -1;
@@ -259,6 +310,16 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
         commit_free(S, R[ct], me, color + before);
         if (S.err) atomicOr(&ctl.err, (int)S.err);
         if (R[ct].sno >= 0) atomicMax(&ctl.last[R[ct].sno], ct);
+        if (DEFER) {   // the ordered part of this read goes to the log
+          const size_t q = vbase + (size_t)me;
+          const int nv = R[ct].nv, hm = R[ct].has_multi;
+#pragma unroll
+          for (int x = 0; x < STG_FP_MAXV; x++) {
+            g.vlog_grp[q * STG_FP_MAXV + x] = x < nv ? R[ct].grp[x] : -1;
+            g.vlog_val[q * STG_FP_MAXV + x] = x < nv ? make_float2(R[ct].cov[x], (hm >> x & 1) ? R[ct].multi[x] : 0.f) : make_float2(0.f, 0.f);
+          }
+          g.vlog_fl[q] = R[ct].frag_len; g.vlog_nf[q] = R[ct].numfrag;
+        }
       }
       __syncthreads();   // (D) colours, readgroup entries and cursors of the run are in place
       if (ctl.err) break;
@@ -271,7 +332,7 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
       }
       color += minted;
       if (tid == 0) S.ncol += minted;
-      pend_k = k; pend_buf = buf; buf ^= 1;
+      pend_k = DEFER ? 0 : k; pend_buf = buf; buf ^= 1;
       // the run reached the end of the window, ended with a read that grows a group, or stopped at a read that waits for
       // its mate: no sequential read in this step
       no_walk = k >= hi - n || grows || waits0;
@@ -285,7 +346,8 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
     if (n < inr && !no_walk) {
       // a read for thread 0 to walk: it works on the float sums (they have to be in) and may create groups (leave
       // shared memory before it can overflow)
-      if (warp == 0 && pend_k) pending_sums(Rb[pend_buf], pend_k);
+      if (DEFER) flush(n);
+      else if (warp == 0 && pend_k) pending_sums(Rb[pend_buf], pend_k);
       pend_k = 0;
       __syncthreads();   // (E1) sums in; everybody has read ctl.last
       if (in_smem && ng_u + (int)(S.rcap_off[n + 1] - S.rcap_off[n]) > GROUPS_SMEM) {
@@ -306,10 +368,12 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
       ng_u = ctl.ng; color = ctl.color;
       if (ctl.err) break;
       n++;
+      if (DEFER) flushed = n;     // the walked read added its own sums
     }
   }
   __syncthreads();
-  if (warp == 0 && pend_k) pending_sums(Rb[pend_buf], pend_k);
+  if (DEFER) { if (!ctl.err) flush(inr); }
+  else if (warp == 0 && pend_k) pending_sums(Rb[pend_buf], pend_k);
   __syncthreads();
   if (tid == 0) {
     if (ctl.err) S.err |= (uint32_t)ctl.err;
@@ -408,26 +472,44 @@ cudaError_t launch_group_caps(const DevBatchView& v, uint32_t* rcap, unsigned lo
   return cudaGetLastError();
 }
 
-cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, int64_t n_deep, cudaStream_t st,
-                               cudaStream_t aux, cudaEvent_t fork, cudaEvent_t join) {
+// three size classes side by side on three streams: the few very deep bundles (one CTA of 8 warps per SM: their runs of
+// simple reads fill a window of 224 reads, and the step's latency — chains of dependent loads — does not grow with the
+// window), the deep ones (4 warps), the shallow mass (2 warps)
+#define GROUPS_VDEEP_READS 100000
+template <int W, int MINB, bool GROW, bool DEFER>
+static cudaError_t walk_launch(const DevBatchView& v, const GroupsView& g, const JuncParams& p, unsigned grid, uint32_t base, cudaStream_t st) {
+  const size_t dyn = 2 * (size_t)(32 * W - 32) * sizeof(FastRec);
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(groups_walk_kernel<W, MINB, GROW, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
+  // per device and cheap: the kernels must prefer the same carve-out to be able to share an SM.  72 % (164 KB of
+  // shared memory, ~90 KB of L1) measured best on C2: 100 % 121 ms, 72-80 % 110 ms, 50 % 133 ms (too few shallow CTAs)
+  if ((e = cudaFuncSetAttribute(groups_walk_kernel<W, MINB, GROW, DEFER>, cudaFuncAttributePreferredSharedMemoryCarveout, 72)) != cudaSuccess) return e;
+  groups_walk_kernel<W, MINB, GROW, DEFER><<<grid, 32 * W, dyn, st>>>(v, g, p, base);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, int64_t n_vdeep, int64_t n_deep, cudaStream_t st,
+                               cudaStream_t aux, cudaStream_t aux2, cudaEvent_t fork, cudaEvent_t join, cudaEvent_t join2) {
   if (v.n_bundles == 0) return cudaSuccess;
   cudaError_t e;
-  // per device and cheap: both kernels must prefer the same carve-out to be able to share an SM.  72 % (164 KB of
-  // shared memory, ~90 KB of L1) measured best on C2: 100 % 121 ms, 72-80 % 110 ms, 50 % 133 ms (too few shallow CTAs)
-  if ((e = cudaFuncSetAttribute(groups_walk_kernel<4, 4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 72)) != cudaSuccess ||
-      (e = cudaFuncSetAttribute(groups_walk_kernel<2, 8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 72)) != cudaSuccess)
-    return e;
-  if (n_deep > 0) {   // the deep bundles on the second stream, next to the shallow mass
-    if ((e = cudaEventRecord(fork, st)) != cudaSuccess || (e = cudaStreamWaitEvent(aux, fork, 0)) != cudaSuccess) return e;
-    groups_walk_kernel<4, 4, false><<<(unsigned)n_deep, 128, 0, aux>>>(v, g, p, 0u);
-    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaEventRecord(join, aux)) != cudaSuccess) return e;
+  if (n_deep > 0 || n_vdeep > 0) { if ((e = cudaEventRecord(fork, st)) != cudaSuccess) return e; }
+  if (n_vdeep > 0) {
+    if ((e = cudaStreamWaitEvent(aux2, fork, 0)) != cudaSuccess) return e;
+    if ((e = walk_launch<8, 1, false, true>(v, g, p, (unsigned)n_vdeep, 0u, aux2)) != cudaSuccess || (e = cudaEventRecord(join2, aux2)) != cudaSuccess) return e;
   }
-  if (v.n_bundles > n_deep) groups_walk_kernel<2, 8, true><<<(unsigned)(v.n_bundles - n_deep), 64, 0, st>>>(v, g, p, (uint32_t)n_deep);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if (n_deep > 0 && (e = cudaStreamWaitEvent(st, join, 0)) != cudaSuccess) return e;
+  if (n_deep > n_vdeep) {   // the deep bundles next to the shallow mass
+    if ((e = cudaStreamWaitEvent(aux, fork, 0)) != cudaSuccess) return e;
+    if ((e = walk_launch<4, 4, false, false>(v, g, p, (unsigned)(n_deep - n_vdeep), (uint32_t)n_vdeep, aux)) != cudaSuccess ||
+        (e = cudaEventRecord(join, aux)) != cudaSuccess) return e;
+  }
+  if (v.n_bundles > n_deep && (e = walk_launch<2, 8, true, false>(v, g, p, (unsigned)(v.n_bundles - n_deep), (uint32_t)n_deep, st)) != cudaSuccess) return e;
+  if (n_deep > n_vdeep && (e = cudaStreamWaitEvent(st, join, 0)) != cudaSuccess) return e;
+  if (n_vdeep > 0 && (e = cudaStreamWaitEvent(st, join2, 0)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
+int64_t groups_vdeep_reads() { return GROUPS_VDEEP_READS; }
+int64_t groups_vlog_scratch() { return VLOG_SCRATCH; }
 int64_t groups_deep_reads() { return GROUPS_DEEP_READS; }
 
 cudaError_t launch_groups_finish(const DevBatchView& v, const GroupsView& g, cudaStream_t st) {

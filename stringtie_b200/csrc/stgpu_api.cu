@@ -32,7 +32,8 @@ struct stg_ctx {
   stg_params params;
   cudaStream_t stream = nullptr;
   cudaStream_t aux_stream = nullptr;   // second stream of the rows a8 + a9 stage (deep bundles beside the shallow mass)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t aux2_stream = nullptr;  // third stream: the very deep bundles
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
   std::string error;
   bool profiling = false;
   std::vector<Timed> timed;      // events of the last stg_run
@@ -305,6 +306,8 @@ int stg_init(const stg_params* params, int device, stg_ctx** out) {
   }
   CK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CK(nullptr, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+  CK(nullptr, cudaStreamCreateWithFlags(&ctx->aux2_stream, cudaStreamNonBlocking));
+  CK(nullptr, cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
   CK(nullptr, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   CK(nullptr, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   *out = ctx;
@@ -320,6 +323,8 @@ int stg_shutdown(stg_ctx* ctx) {
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+  if (ctx->aux2_stream) { cudaStreamSynchronize(ctx->aux2_stream); cudaStreamDestroy(ctx->aux2_stream); }
+  if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
@@ -829,7 +834,22 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
   JuncParams jp{pr.junctionsupport, pr.sserror, pr.junctionthr, pr.eonly};
   int64_t n_deep = 0;   // `order` is sorted by decreasing read count
   while (n_deep < nb && (int64_t)d->h_nreads[order[n_deep]] >= groups_deep_reads()) n_deep++;
-  { Scope s(ctx, "groups_walk", 2); CK(ctx, launch_groups_walk(v, g, jp, n_deep, st, ctx->aux_stream, ctx->ev_fork, ctx->ev_join)); }
+  int64_t n_vdeep = 0;
+  while (n_vdeep < n_deep && (int64_t)d->h_nreads[order[n_vdeep]] >= groups_vdeep_reads()) n_vdeep++;
+  {  // the log of the very deep bundles' ordered sums
+    std::vector<uint32_t> voff((size_t)n_vdeep + 1, 0);
+    for (int64_t i = 0; i < n_vdeep; i++) voff[i + 1] = voff[i] + d->h_nreads[order[i]];
+    const int64_t vr = voff[n_vdeep];
+    uint32_t* d_voff = nullptr;
+    TEMP(d_voff, n_vdeep + 1);
+    CK(ctx, cudaMemcpyAsync(d_voff, voff.data(), sizeof(uint32_t) * (n_vdeep + 1), cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaStreamSynchronize(st));   // voff leaves the host
+    g.vlog_off = d_voff;
+    TEMP(g.vlog_grp, 6 * vr); TEMP(g.vlog_val, 6 * vr); TEMP(g.vlog_sorted, 6 * vr); TEMP(g.vlog_fl, vr); TEMP(g.vlog_nf, vr);
+    TEMP(g.vlog_cnt, n_vdeep * groups_vlog_scratch());
+  }
+  { Scope s(ctx, "groups_walk", 3);
+    CK(ctx, launch_groups_walk(v, g, jp, n_vdeep, n_deep, st, ctx->aux_stream, ctx->aux2_stream, ctx->ev_fork, ctx->ev_join, ctx->ev_join2)); }
   { Scope s(ctx, "groups_scans", 4);
     CK(ctx, launch_scan_exclusive_add(g.b_ng, nb + 1, scan_state, ticket, st));
     CK(ctx, launch_scan_exclusive_add(g.b_ncol, nb + 1, scan_state, ticket, st));
