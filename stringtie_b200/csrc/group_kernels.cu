@@ -105,15 +105,7 @@ struct WalkCtl {
 // way by thread 0 once the pending sums are in.
 // GROW: reads that grow a group stay inside the runs (they record the bounds they depend on; pays off where runs are
 // short, i.e. in shallow bundles); otherwise such a read ends its run.
-// DEFER (the very deep bundles): the float sums of the simple reads are not added step by step by warp 0 — in a window of
-// hundreds of reads that loop is longer than the classification and the other warps wait for it at the barrier (67 % of
-// the stall samples of the deepest C2 bundle, profiles/r3_groups_deepest.md) — but logged per read (visited group,
-// coverage, multi; fragment sums) and added when a read has to be walked the reference's way (walk_read reads the sums)
-// and at the end: a stable counting sort of the logged visits by group, then one warp per group adds its run in read
-// order (ordered_sum.cuh).  Same sums, same order per group.
-#define VLOG_KMAX 2048                                   // groups the sorted path can take (else: the serial loop)
-#define VLOG_SCRATCH (8 * VLOG_KMAX + VLOG_KMAX + 2)      // uint32 per very deep CTA: counts per (warp, group) + group offsets
-template <int GROUPS_WARPS, int MINB, bool GROW, bool DEFER>
+template <int GROUPS_WARPS, int MINB, bool GROW>
 __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(DevBatchView v, GroupsView g, JuncParams prm,
                                                                              uint32_t order_base) {
   constexpr int GROUPS_STEP = 32 * GROUPS_WARPS, GROUPS_CLS = GROUPS_STEP - 32;
@@ -167,8 +159,6 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
   const int inr = (int)nr;
   const unsigned FULL = 0xffffffffu;
   const int ct = tid - 32;                    // index among the classifying threads (warp 0: negative)
-  const size_t vbase = DEFER ? (size_t)g.vlog_off[blockIdx.x] : 0;   // first log entry of this bundle
-  int flushed = 0;                            // uniform: reads [0, flushed) have their sums added
   if (tid == 0) { ctl.err = 0; ctl.last[0] = ctl.last[1] = ctl.last[2] = -1; ctl.n_grow[0] = ctl.n_grow[1] = 0; }
   __syncthreads();
 
@@ -200,51 +190,12 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
     }
   };
 
-  // DEFER: add the logged sums of the reads [flushed, upto), in read order per group; all threads
-  auto flush = [&](int upto) {
-    if (upto <= flushed) return;
-    const uint32_t n6 = (uint32_t)(upto - flushed) * STG_FP_MAXV;
-    const int32_t* lg = g.vlog_grp + (vbase + (size_t)flushed) * STG_FP_MAXV;
-    const float2* lv = g.vlog_val + (vbase + (size_t)flushed) * STG_FP_MAXV;
-    const uint32_t K = (uint32_t)ng_u + 1u;              // the last key takes the empty slots
-    if (K <= VLOG_KMAX && GROUPS_WARPS <= 8) {
-      uint32_t* cnt = g.vlog_cnt + (size_t)blockIdx.x * VLOG_SCRATCH;
-      cta_ordered_keyed_sum2(n6, [&](uint32_t i) { const int32_t x = lg[i]; return x < 0 ? (uint32_t)ng_u : (uint32_t)x; },
-                             [&](uint32_t i) { return lv[i]; }, K, (uint32_t)ng_u, S.g_cov, S.g_multi, cnt, cnt + (size_t)GROUPS_WARPS * K,
-                             g.vlog_sorted + (vbase + (size_t)flushed) * STG_FP_MAXV);
-    } else if (warp == 0) {   // lane l owns the groups with slot % 32 == l
-      int cur = -1;
-      float acc_cov = 0.f, acc_multi = 0.f;
-      for (uint32_t i = 0; i < n6; i++) {
-        const int gr = lg[i];
-        if (gr >= 0 && (gr & 31) == lane) {
-          if (gr != cur) {
-            if (cur >= 0) { S.g_cov[cur] = acc_cov; S.g_multi[cur] = acc_multi; }
-            cur = gr; acc_cov = S.g_cov[gr]; acc_multi = S.g_multi[gr];
-          }
-          acc_multi += lv[i].y; acc_cov += lv[i].x;
-        }
-      }
-      if (cur >= 0) { S.g_cov[cur] = acc_cov; S.g_multi[cur] = acc_multi; }
-    }
-    if (tid == 0) {
-      double a = fl, c = nf;
-      const double* pf = g.vlog_fl + vbase;
-      const double* pn = g.vlog_nf + vbase;
-#pragma unroll 4
-      for (int r = flushed; r < upto; r++) { a += pf[r]; c += pn[r]; }
-      fl = a; nf = c;
-    }
-    __syncthreads();
-    flushed = upto;
-  };
-
   while (true) {
     const bool classify = n < inr && slow_budget == 0;
     FastRec* R = Rb[buf];
     const int hi = n + width < inr ? n + width : inr, me = n + ct;
     int st = 0;                                 // 1 simple, 3 simple + grows a group, 0 not simple, 2 waits
-    if (warp == 0) { if (!DEFER && pend_k) pending_sums(Rb[pend_buf], pend_k); }
+    if (warp == 0) { if (pend_k) pending_sums(Rb[pend_buf], pend_k); }
     else if (classify) {
       if (me < hi) st = GROW ? classify_read<true>(S, me, n, hi, R[ct], &Db[GROW ? ct : 0]) : classify_read<false>(S, me, n, hi, R[ct]);
       ctl.npc[ct] = (st == 1 || (GROW && st == 3)) ? R[ct].npc : -1;
@@ -310,16 +261,6 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
         commit_free(S, R[ct], me, color + before);
         if (S.err) atomicOr(&ctl.err, (int)S.err);
         if (R[ct].sno >= 0) atomicMax(&ctl.last[R[ct].sno], ct);
-        if (DEFER) {   // the ordered part of this read goes to the log
-          const size_t q = vbase + (size_t)me;
-          const int nv = R[ct].nv, hm = R[ct].has_multi;
-#pragma unroll
-          for (int x = 0; x < STG_FP_MAXV; x++) {
-            g.vlog_grp[q * STG_FP_MAXV + x] = x < nv ? R[ct].grp[x] : -1;
-            g.vlog_val[q * STG_FP_MAXV + x] = x < nv ? make_float2(R[ct].cov[x], (hm >> x & 1) ? R[ct].multi[x] : 0.f) : make_float2(0.f, 0.f);
-          }
-          g.vlog_fl[q] = R[ct].frag_len; g.vlog_nf[q] = R[ct].numfrag;
-        }
       }
       __syncthreads();   // (D) colours, readgroup entries and cursors of the run are in place
       if (ctl.err) break;
@@ -332,7 +273,7 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
       }
       color += minted;
       if (tid == 0) S.ncol += minted;
-      pend_k = DEFER ? 0 : k; pend_buf = buf; buf ^= 1;
+      pend_k = k; pend_buf = buf; buf ^= 1;
       // the run reached the end of the window, ended with a read that grows a group, or stopped at a read that waits for
       // its mate: no sequential read in this step
       no_walk = k >= hi - n || grows || waits0;
@@ -346,8 +287,7 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
     if (n < inr && !no_walk) {
       // a read for thread 0 to walk: it works on the float sums (they have to be in) and may create groups (leave
       // shared memory before it can overflow)
-      if (DEFER) flush(n);
-      else if (warp == 0 && pend_k) pending_sums(Rb[pend_buf], pend_k);
+      if (warp == 0 && pend_k) pending_sums(Rb[pend_buf], pend_k);
       pend_k = 0;
       __syncthreads();   // (E1) sums in; everybody has read ctl.last
       if (in_smem && ng_u + (int)(S.rcap_off[n + 1] - S.rcap_off[n]) > GROUPS_SMEM) {
@@ -368,12 +308,10 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
       ng_u = ctl.ng; color = ctl.color;
       if (ctl.err) break;
       n++;
-      if (DEFER) flushed = n;     // the walked read added its own sums
     }
   }
   __syncthreads();
-  if (DEFER) { if (!ctl.err) flush(inr); }
-  else if (warp == 0 && pend_k) pending_sums(Rb[pend_buf], pend_k);
+  if (warp == 0 && pend_k) pending_sums(Rb[pend_buf], pend_k);
   __syncthreads();
   if (tid == 0) {
     if (ctl.err) S.err |= (uint32_t)ctl.err;
@@ -388,6 +326,268 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
   }
   __syncthreads();
   if (in_smem) groups_to_global(S, GG, ctl.ng, tid, GROUPS_STEP);   // the CTA writes the groups out of shared memory
+}
+
+// ---- oversized bundles: one thread-block CLUSTER per bundle ------------------------------------
+// A bundle of 10^6 reads walked by one CTA is bound by the latency of a step (classification = chains of dependent L2
+// loads, ~40 us whatever the width of the window).  Nearly every read of such a bundle is simple, so the window can be as
+// wide as the hardware allows: CL CTAs of 256 threads on CL SMs of one GPC classify CL * 256 reads per step against the
+// same state; the schedule of a step is the one of groups_walk_kernel (groups_device.cuh, groups_first_half_steps): reads
+// that share a continuation mate yield to the first, the leading run of simple reads commits its order-free part in
+// parallel, its ordered part goes to a log, the first read that is not simple is walked by one thread
+// after the logged sums are in.  Cross-CTA state lives in global memory (group arrays, records, masks); the CTAs meet at
+// cluster barriers (barrier.cluster, which orders global memory at cluster scope).
+__device__ int g_groups_debug = 0;
+#define CLUSTER_CTAS 8
+#define CLUSTER_THREADS 256
+#define CLUSTER_WINDOW (CLUSTER_CTAS * CLUSTER_THREADS)
+struct ClusterCtl {
+  int32_t err, ng, color;
+  int32_t curr[3];
+  int32_t last[2][3];
+  uint32_t ok_mask[CLUSTER_WINDOW / 32], mint_mask[CLUSTER_WINDOW / 32], wait_mask[CLUSTER_WINDOW / 32], grow_mask[CLUSTER_WINDOW / 32];
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+
+__global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel(DevBatchView v, GroupsView g, JuncParams prm,
+                                                                                  uint32_t order_base) {
+  const uint32_t cid = blockIdx.x / CLUSTER_CTAS;                 // which oversized bundle
+  const uint32_t crank = cluster_cta_rank();
+  const uint32_t b = g.order[order_base + cid];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gt = (int)crank * CLUSTER_THREADS + tid;              // slot in the window
+  const int gw = gt >> 5;
+  const uint32_t r0 = v.b_read_off[b], nr = v.b_read_off[b + 1] - r0;
+  const uint32_t j0 = v.b_junc_off[b], nj0 = v.b_junc_off[b + 1] - j0;
+  if (nr == 0) return;                                            // (uniform over the cluster)
+  Grp S;
+  S.nr = (int)nr;
+  S.seg0 = v.r_seg_off[r0]; S.pair0 = v.r_pair_off[r0];
+  const uint32_t i0 = S.seg0 - r0;
+  const uint32_t nintr = (v.r_seg_off[r0 + nr] - S.seg0) - nr;
+  S.r_start = v.r_start + r0; S.r_end = v.r_end + r0; S.r_len = v.r_len + r0; S.seg_off = v.r_seg_off + r0;
+  S.pair_off = v.r_pair_off + r0; S.r_count = v.r_count + r0; S.pair_cnt = v.pair_cnt + S.pair0; S.r_nh = v.r_nh + r0;
+  S.r_flags = v.r_flags + r0;
+  S.strand = g.strand + r0; S.seg_s = g.seg_start + S.seg0; S.seg_e = g.seg_end + S.seg0; S.pair = g.pair + S.pair0;
+  S.rj = g.rj + i0;
+  S.j_start = v.j_start + j0; S.j_end = v.j_end + j0; S.j_nreads = v.jp_nreads + j0; S.j_good = v.jp_nreads_good + j0;
+  S.j_ej = v.jp_ej + j0; S.jp_good = v.jp_good + j0; S.jp_good_strand = v.jp_good_strand + j0;
+  S.jt_strand = g.jt_strand + j0; S.jt_mm = g.jt_mm + j0;
+  S.ap_start = g.ap_start + i0; S.ap_end = g.ap_end + i0; S.ap_strand = g.ap_strand + i0; S.ap_mm = g.ap_mm + i0;
+  S.nj0 = (int)nj0; S.nJ = (int)nj0; S.apcap = (int)nintr;
+  const size_t G0 = g.rcap_off[r0];
+  const uint32_t gcap = g.rcap_off[r0 + nr] - g.rcap_off[r0];
+  // the group arrays stay in global memory: every CTA of the cluster reads them
+  S.g_start = g.g_start + G0; S.g_end = g.g_end + G0; S.g_color = g.g_color + G0; S.g_next = g.g_next + G0; S.g_merge = g.g_merge + G0;
+  S.g_grid = g.g_grid + G0; S.g_cov = g.g_cov + G0; S.g_multi = g.g_multi + G0; S.g_alive = g.g_alive + G0;
+  S.ng = 0; S.gcap = (int)gcap;
+  S.eqcol = g.eqcol + G0 + 3 * (size_t)r0; S.ncol = 0; S.ccap = (int)(gcap + 3 * nr);
+  S.rg = g.rg; S.rg_cnt = g.rg_cnt + r0; S.rcap_off = g.rcap_off + r0;
+  S.curr.fill(-1); S.startg.fill(-1);
+  S.junctionsupport = prm.junctionsupport; S.bundledist = g.bundledist;
+  S.refstart = v.b_start[b]; S.len = v.b_len[b];
+  S.c1 = v.bpcov + 3 * (size_t)v.b_gbase[b] + v.b_stride[b];
+  S.prm = prm; S.err = 0;
+  ClusterCtl* ctl = (ClusterCtl*)g.cl_ctl + cid;
+  FastRec* R = g.cl_rec + (size_t)cid * CLUSTER_WINDOW;
+  const size_t vbase = (size_t)g.vlog_off[order_base + cid];
+  int32_t* claim = g.cl_claim + vbase;                            // [nr] first simple read of the step that continues into read i
+  const bool boss = gt == 0;
+  if (gcap == 0 || gcap > 0x7fffffffu) { if (boss) atomicOr(v.err_flag, STG_GERR_GROUPS); return; }
+  __shared__ OrderedSumSmem osm;   // scratch of the flush
+  __shared__ double red_a[CLUSTER_THREADS / 32], red_c[CLUSTER_THREADS / 32];
+  __shared__ int red_ea[CLUSTER_THREADS / 32], red_ec[CLUSTER_THREADS / 32];
+  int emin_a = 4096, emin_c = 4096;   // the boss: smallest unit of the fragment-sum terms so far
+  int color = 0, ng_u = 0;
+  double nf = 0, fl = 0;         // the boss
+  int n = 0, slow_len = 0, slow_budget = 0, width = 32, pb = 0, flushed = 0;
+  const int inr = (int)nr;
+  const unsigned FULL = 0xffffffffu;
+  if (boss) { ctl->err = 0; for (int x = 0; x < 3; x++) { ctl->last[0][x] = -1; ctl->last[1][x] = -1; } }
+  cluster_sync_all();
+
+  auto flush = [&](int upto) {    // the logged sums of the reads [flushed, upto): CTA 0 adds them (ordered_sum.cuh)
+    if (upto > flushed && crank == 0) {
+      const uint32_t n6 = (uint32_t)(upto - flushed) * STG_FP_MAXV;
+      const int32_t* lg = g.vlog_grp + (vbase + (size_t)flushed) * STG_FP_MAXV;
+      const float2* lv = g.vlog_val + (vbase + (size_t)flushed) * STG_FP_MAXV;
+      const bool sorted_ok = cta_ordered_keyed_sum2(n6, [&](uint32_t i) { return lg[i]; }, [&](uint32_t i) { return lv[i]; }, S.g_cov, S.g_multi, osm,
+                                                    g.vlog_sorted + (vbase + (size_t)flushed) * STG_FP_MAXV);
+      if (!sorted_ok && warp == 0) {   // too many distinct groups for the shared-memory counts: lane l owns the groups with slot % 32 == l
+        int cur = -1;
+        float acc_cov = 0.f, acc_multi = 0.f;
+        for (uint32_t i = 0; i < n6; i++) {
+          const int gr = lg[i];
+          if (gr >= 0 && (gr & 31) == lane) {
+            if (gr != cur) {
+              if (cur >= 0) { S.g_cov[cur] = acc_cov; S.g_multi[cur] = acc_multi; }
+              cur = gr; acc_cov = S.g_cov[gr]; acc_multi = S.g_multi[gr];
+            }
+            acc_multi += lv[i].y; acc_cov += lv[i].x;
+          }
+        }
+        if (cur >= 0) { S.g_cov[cur] = acc_cov; S.g_multi[cur] = acc_multi; }
+      }
+      // the bundle's fragment sums (f64 sums of values that are floats): order-free while every partial sum is exactly
+      // representable — all terms are >= 0 and multiples of 2^emin, the total stays below 2^(emin + 53) — which is checked;
+      // otherwise the boss adds this range one read after the other, as the reference does
+      {
+        const double* pf = g.vlog_fl + vbase;
+        const double* pn = g.vlog_nf + vbase;
+        double pa = 0, pc = 0;
+        int ea = 4096, ec = 4096;
+        for (int r = flushed + tid; r < upto; r += CLUSTER_THREADS) {
+          const double a = pf[r], c = pn[r];
+          pa += a; pc += c;
+          if (a > 0) { const int e = ((__double2hiint(a) >> 20) & 0x7ff) - 1023 - 23; ea = e < ea ? e : ea; }
+          if (c > 0) { const int e = ((__double2hiint(c) >> 20) & 0x7ff) - 1023 - 23; ec = e < ec ? e : ec; }
+        }
+        for (int o = 16; o; o >>= 1) {
+          pa += __shfl_down_sync(FULL, pa, o); pc += __shfl_down_sync(FULL, pc, o);
+          const int xa = __shfl_down_sync(FULL, ea, o), xc = __shfl_down_sync(FULL, ec, o);
+          ea = xa < ea ? xa : ea; ec = xc < ec ? xc : ec;
+        }
+        if (lane == 0) { red_a[warp] = pa; red_c[warp] = pc; red_ea[warp] = ea; red_ec[warp] = ec; }
+        __syncthreads();
+        if (boss) {
+          double ta = 0, tc = 0;
+          for (int x = 0; x < CLUSTER_THREADS / 32; x++) {
+            ta += red_a[x]; tc += red_c[x];
+            emin_a = red_ea[x] < emin_a ? red_ea[x] : emin_a; emin_c = red_ec[x] < emin_c ? red_ec[x] : emin_c;
+          }
+          const double na = fl + ta, nc = nf + tc;
+          const int xa = ((__double2hiint(na) >> 20) & 0x7ff) - 1023, xc = ((__double2hiint(nc) >> 20) & 0x7ff) - 1023;
+          if ((na == 0 || xa + 1 - emin_a <= 52) && (nc == 0 || xc + 1 - emin_c <= 52)) { fl = na; nf = nc; }
+          else {
+            double a = fl, c = nf;
+#pragma unroll 4
+            for (int r = flushed; r < upto; r++) { a += pf[r]; c += pn[r]; }
+            fl = a; nf = c;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (upto > flushed) flushed = upto;
+  };
+
+  long long t_cls = 0, t_commit = 0, t_flush = 0, t_walk = 0, t_bar = 0, steps = 0, walks = 0, t0c = 0;
+  while (true) {
+    const bool classify = n < inr && slow_budget == 0;
+    const int hi = n + width < inr ? n + width : inr, me = n + gt;
+    int st = 0, npc = -1;
+    if (boss) t0c = clock64();
+    if (classify) {
+      if (me < hi) st = classify_read<false>(S, me, n, hi, R[gt]);
+      if (st == 1 || st == 3) npc = R[gt].npc;
+      if (st == 1 && npc >= 0) atomicMin(&claim[npc], gt);
+    }
+    if (boss) { const long long t = clock64(); t_cls += t - t0c; t0c = t; }
+    cluster_sync_all();        // (1) records and claims of this step are written
+    if (boss) { const long long t = clock64(); t_bar += t - t0c; t0c = t; steps++; }
+    if (n >= inr) break;
+    int k = 0;
+    bool no_walk = false;
+    if (classify) {
+      // reads that continue into the SAME mate see each other's readgroup pushes: only the first simple one stays
+      if (npc >= 0 && claim[npc] < gt) st = 2;
+      const unsigned okm = __ballot_sync(FULL, st == 1), mim = __ballot_sync(FULL, (st == 1 || st == 3) && R[gt].newcol);
+      const unsigned wam = __ballot_sync(FULL, st == 2), grm = __ballot_sync(FULL, st == 3);
+      if (lane == 0) { ctl->ok_mask[gw] = okm; ctl->mint_mask[gw] = mim; ctl->wait_mask[gw] = wam; ctl->grow_mask[gw] = grm; }
+      cluster_sync_all();      // (2) masks are in; every claim has been looked at
+      if (npc >= 0) claim[npc] = 0x7f7f7f7f;
+      {
+        bool open = true;
+        for (int w2 = 0; w2 < CLUSTER_WINDOW / 32 && open; w2++) {
+          const unsigned m = ctl->ok_mask[w2];
+          const int kw = m == FULL ? 32 : __ffs(~m) - 1;
+          k += kw;
+          if (kw < 32) open = false;
+        }
+      }
+      const bool grows = k < CLUSTER_WINDOW && (ctl->grow_mask[k >> 5] >> (k & 31) & 1u);
+      const bool waits0 = k < CLUSTER_WINDOW && (ctl->wait_mask[k >> 5] >> (k & 31) & 1u);
+      if (grows) k++;
+      int before = 0, minted = 0;     // colours minted by the run's reads ahead of this thread / by the whole run
+      for (int w2 = 0; w2 * 32 < k; w2++) {
+        const int rem = k - 32 * w2;
+        const unsigned run = rem >= 32 ? FULL : (1u << rem) - 1u;
+        const unsigned mi = ctl->mint_mask[w2] & run;
+        if (w2 < gw) before += __popc(mi);
+        else if (w2 == gw) before += __popc(mi & ((1u << lane) - 1u));
+        minted += __popc(mi);
+      }
+      if (gt < k) {
+        commit_free(S, R[gt], me, color + before);
+        if (S.err) atomicOr(&ctl->err, (int)S.err);
+        if (R[gt].sno >= 0) atomicMax(&ctl->last[pb][R[gt].sno], gt);
+        const size_t q = vbase + (size_t)me;
+        const int nv = R[gt].nv, hm = R[gt].has_multi;
+#pragma unroll
+        for (int x = 0; x < STG_FP_MAXV; x++) {
+          g.vlog_grp[q * STG_FP_MAXV + x] = x < nv ? R[gt].grp[x] : -1;
+          g.vlog_val[q * STG_FP_MAXV + x] = x < nv ? make_float2(R[gt].cov[x], (hm >> x & 1) ? R[gt].multi[x] : 0.f) : make_float2(0.f, 0.f);
+        }
+        g.vlog_fl[q] = R[gt].frag_len; g.vlog_nf[q] = R[gt].numfrag;
+      }
+      cluster_sync_all();      // (3) colours, readgroup entries, cursors and the log of the run are in place
+      if (boss) { const long long t = clock64(); t_commit += t - t0c; t0c = t; }
+      if (ctl->err) break;
+      {
+        const int l0 = ctl->last[pb][0], l1 = ctl->last[pb][1], l2 = ctl->last[pb][2];
+        if (l0 >= 0) S.curr.a = R[l0].curr;
+        if (l1 >= 0) S.curr.b = R[l1].curr;
+        if (l2 >= 0) S.curr.c = R[l2].curr;
+      }
+      if (boss) { ctl->last[pb ^ 1][0] = -1; ctl->last[pb ^ 1][1] = -1; ctl->last[pb ^ 1][2] = -1; S.ncol += minted; }
+      pb ^= 1;
+      color += minted;
+      no_walk = k >= hi - n || grows || waits0;
+      if (k >= width) width = width * 2 < CLUSTER_WINDOW ? width * 2 : CLUSTER_WINDOW;
+      else { const int w2 = 2 * k + 8; width = w2 < 16 ? 16 : (w2 < CLUSTER_WINDOW ? w2 : CLUSTER_WINDOW); }
+      n += k;
+      if (k == 0) { slow_len = slow_len * 2 + 1 < 15 ? slow_len * 2 + 1 : 15; slow_budget = slow_len; }
+      else if (k >= 8) slow_len = 0;
+    } else slow_budget--;
+    if (n < inr && !no_walk) {
+      flush(n);
+      cluster_sync_all();      // (4) the sums are in
+      if (boss) { const long long t = clock64(); t_flush += t - t0c; t0c = t; walks++; }
+      if (boss) {
+        S.err |= (uint32_t)ctl->err;
+        if (!S.err) color = walk_read(S, n, color, nf, fl);
+        ctl->curr[0] = S.curr.a; ctl->curr[1] = S.curr.b; ctl->curr[2] = S.curr.c;
+        ctl->ng = S.ng; ctl->color = color; ctl->err = (int)S.err;
+      }
+      cluster_sync_all();      // (5)
+      if (boss) { const long long t = clock64(); t_walk += t - t0c; t0c = t; }
+      S.curr.a = ctl->curr[0]; S.curr.b = ctl->curr[1]; S.curr.c = ctl->curr[2];
+      ng_u = ctl->ng; color = ctl->color;
+      if (ctl->err) break;
+      n++;
+      flushed = n;
+    }
+  }
+  if (boss) t0c = clock64();
+  if (!ctl->err) flush(inr);
+  cluster_sync_all();
+  if (boss && g_groups_debug)
+    printf("cluster bundle %u: reads %u steps %lld walks %lld | Mcycles: classify %.1f barrier1 %.1f commit %.1f flush %.1f walk %.1f final flush %.1f\n", b, nr,
+           steps, walks, t_cls * 1e-6, t_bar * 1e-6, t_commit * 1e-6, t_flush * 1e-6, t_walk * 1e-6, (clock64() - t0c) * 1e-6);
+  if (boss) {
+    if (ctl->err) S.err |= (uint32_t)ctl->err;
+    if (!S.err) walk_finish(S, g.jt_perm + j0 + i0, g.jt_inv + j0 + i0);
+    if (S.err) atomicOr(v.err_flag, S.err);
+    else {
+      g.b_ng[b] = (uint32_t)S.ng; g.b_ncol[b] = (uint32_t)S.ncol; g.b_napp[b] = (uint32_t)(S.nJ - S.nj0);
+      g.b_numfrag[b] = nf; g.b_fraglen[b] = fl;
+      g.b_startgroup[3 * b] = S.startg.a; g.b_startgroup[3 * b + 1] = S.startg.b; g.b_startgroup[3 * b + 2] = S.startg.c;
+    }
+  }
 }
 
 // after the scans: b_ng / b_ncol / b_napp are exclusive prefixes
@@ -472,44 +672,53 @@ cudaError_t launch_group_caps(const DevBatchView& v, uint32_t* rcap, unsigned lo
   return cudaGetLastError();
 }
 
-// three size classes side by side on three streams: the few very deep bundles (one CTA of 8 warps per SM: their runs of
-// simple reads fill a window of 224 reads, and the step's latency — chains of dependent loads — does not grow with the
-// window), the deep ones (4 warps), the shallow mass (2 warps)
-#define GROUPS_VDEEP_READS 100000
-template <int W, int MINB, bool GROW, bool DEFER>
+// three size classes side by side on three streams: the few oversized bundles (one cluster of CTAs each, below), the deep
+// ones (4 warps), the shallow mass (2 warps)
+template <int W, int MINB, bool GROW>
 static cudaError_t walk_launch(const DevBatchView& v, const GroupsView& g, const JuncParams& p, unsigned grid, uint32_t base, cudaStream_t st) {
   const size_t dyn = 2 * (size_t)(32 * W - 32) * sizeof(FastRec);
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(groups_walk_kernel<W, MINB, GROW, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(groups_walk_kernel<W, MINB, GROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
   // per device and cheap: the kernels must prefer the same carve-out to be able to share an SM.  72 % (164 KB of
   // shared memory, ~90 KB of L1) measured best on C2: 100 % 121 ms, 72-80 % 110 ms, 50 % 133 ms (too few shallow CTAs)
-  if ((e = cudaFuncSetAttribute(groups_walk_kernel<W, MINB, GROW, DEFER>, cudaFuncAttributePreferredSharedMemoryCarveout, 72)) != cudaSuccess) return e;
-  groups_walk_kernel<W, MINB, GROW, DEFER><<<grid, 32 * W, dyn, st>>>(v, g, p, base);
+  if ((e = cudaFuncSetAttribute(groups_walk_kernel<W, MINB, GROW>, cudaFuncAttributePreferredSharedMemoryCarveout, 72)) != cudaSuccess) return e;
+  groups_walk_kernel<W, MINB, GROW><<<grid, 32 * W, dyn, st>>>(v, g, p, base);
   return cudaGetLastError();
 }
 
-cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, int64_t n_vdeep, int64_t n_deep, cudaStream_t st,
-                               cudaStream_t aux, cudaStream_t aux2, cudaEvent_t fork, cudaEvent_t join, cudaEvent_t join2) {
+cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, int64_t n_cluster, int64_t n_deep,
+                               cudaStream_t st, cudaStream_t aux, cudaStream_t aux3, cudaEvent_t fork, cudaEvent_t join, cudaEvent_t join3) {
   if (v.n_bundles == 0) return cudaSuccess;
   cudaError_t e;
-  if (n_deep > 0 || n_vdeep > 0) { if ((e = cudaEventRecord(fork, st)) != cudaSuccess) return e; }
-  if (n_vdeep > 0) {
-    if ((e = cudaStreamWaitEvent(aux2, fork, 0)) != cudaSuccess) return e;
-    if ((e = walk_launch<8, 1, false, true>(v, g, p, (unsigned)n_vdeep, 0u, aux2)) != cudaSuccess || (e = cudaEventRecord(join2, aux2)) != cudaSuccess) return e;
+  const int64_t n_vdeep = n_cluster;
+  if (n_deep > 0) { if ((e = cudaEventRecord(fork, st)) != cudaSuccess) return e; }
+  if (n_cluster > 0) {   // the oversized bundles: one cluster of CTAs each
+    if ((e = cudaStreamWaitEvent(aux3, fork, 0)) != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_cluster * CLUSTER_CTAS)); cfg.blockDim = dim3(CLUSTER_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = aux3;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CLUSTER_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if ((e = cudaLaunchKernelEx(&cfg, groups_walk_cluster_kernel, v, g, p, 0u)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(join3, aux3)) != cudaSuccess) return e;
   }
   if (n_deep > n_vdeep) {   // the deep bundles next to the shallow mass
     if ((e = cudaStreamWaitEvent(aux, fork, 0)) != cudaSuccess) return e;
-    if ((e = walk_launch<4, 4, false, false>(v, g, p, (unsigned)(n_deep - n_vdeep), (uint32_t)n_vdeep, aux)) != cudaSuccess ||
+    if ((e = walk_launch<4, 4, false>(v, g, p, (unsigned)(n_deep - n_vdeep), (uint32_t)n_vdeep, aux)) != cudaSuccess ||
         (e = cudaEventRecord(join, aux)) != cudaSuccess) return e;
   }
-  if (v.n_bundles > n_deep && (e = walk_launch<2, 8, true, false>(v, g, p, (unsigned)(v.n_bundles - n_deep), (uint32_t)n_deep, st)) != cudaSuccess) return e;
+  if (v.n_bundles > n_deep && (e = walk_launch<2, 8, true>(v, g, p, (unsigned)(v.n_bundles - n_deep), (uint32_t)n_deep, st)) != cudaSuccess) return e;
   if (n_deep > n_vdeep && (e = cudaStreamWaitEvent(st, join, 0)) != cudaSuccess) return e;
-  if (n_vdeep > 0 && (e = cudaStreamWaitEvent(st, join2, 0)) != cudaSuccess) return e;
+  if (n_cluster > 0 && (e = cudaStreamWaitEvent(st, join3, 0)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
-int64_t groups_vdeep_reads() { return GROUPS_VDEEP_READS; }
-int64_t groups_vlog_scratch() { return VLOG_SCRATCH; }
+void groups_set_debug(int on) { cudaMemcpyToSymbol(g_groups_debug, &on, sizeof(int)); }
+// measured on C2 (profiles/r3_groups.md): 150 k 181 ms, 250 k 172 ms, 400 k 166 ms, 550 k 187 ms for the whole stage
+#define GROUPS_CLUSTER_READS 400000
+int64_t groups_cluster_reads() { return GROUPS_CLUSTER_READS; }
+size_t groups_cluster_ctl_bytes() { return sizeof(ClusterCtl); }
+size_t groups_cluster_rec_bytes() { return sizeof(FastRec) * CLUSTER_WINDOW; }
 int64_t groups_deep_reads() { return GROUPS_DEEP_READS; }
 
 cudaError_t launch_groups_finish(const DevBatchView& v, const GroupsView& g, cudaStream_t st) {

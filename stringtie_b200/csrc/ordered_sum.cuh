@@ -9,6 +9,7 @@
 // from first to last — the chain of dependent float adds of one key is the only serial part left.
 #pragma once
 #include <stdint.h>
+#define OS_BATCH 8
 
 // acc[k] = (...((acc[k] + v_i1) + v_i2) + ...) over the records i1 < i2 < ... of key k, i.e. the reference's "+=" loop
 // over the records in order, for all keys at once.  One CTA; scratch: cnt [W * K] (zeroed), kbase [K + 1], sorted [n].
@@ -21,13 +22,19 @@ __device__ void cta_ordered_keyed_sum(uint32_t n, KeyFn key, ValFn val, uint32_t
   const uint32_t lo = min(n, w * S), hi = min(n, lo + S);
   uint32_t* row = cnt + (size_t)w * K;
   // 1. records per key in this warp's slice
-  for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
-    const uint32_t i = i0 + lane;
-    const bool have = i < hi;
-    const uint32_t k = have ? key(i) : 0xffffffffu - lane;
-    const uint32_t peers = __match_any_sync(0xffffffffu, k);
-    if (have && (__ffs(peers) - 1) == lane) row[k] += __popc(peers);
-    __syncwarp();
+  for (uint32_t i0 = lo; i0 < hi; i0 += 32 * OS_BATCH) {   // OS_BATCH loads in flight per lane: the pass is bound by load latency
+    uint32_t kk[OS_BATCH];
+#pragma unroll
+    for (int u = 0; u < OS_BATCH; u++) { const uint32_t i = i0 + 32u * u + lane; kk[u] = i < hi ? key(i) : 0xffffffffu; }
+#pragma unroll
+    for (int u = 0; u < OS_BATCH; u++) {
+      if (i0 + 32u * u >= hi) break;
+      const bool have = kk[u] != 0xffffffffu;
+      const uint32_t k = have ? kk[u] : 0xffffffffu - lane;
+      const uint32_t peers = __match_any_sync(0xffffffffu, k);
+      if (have && (__ffs(peers) - 1) == lane) row[k] += __popc(peers);
+      __syncwarp();
+    }
   }
   __syncthreads();
   // 2. first slot of every (key, slice): prefix over the slices, then over the keys
@@ -51,19 +58,28 @@ __device__ void cta_ordered_keyed_sum(uint32_t n, KeyFn key, ValFn val, uint32_t
   }
   __syncthreads();
   // 3. stable scatter of the values
-  for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
-    const uint32_t i = i0 + lane;
-    const bool have = i < hi;
-    const uint32_t k = have ? key(i) : 0xffffffffu - lane;
-    const uint32_t peers = __match_any_sync(0xffffffffu, k);
-    uint32_t at = 0;
-    if (have) at = row[k];
-    __syncwarp();
-    if (have) {
-      sorted[kbase[k] + at + __popc(peers & ((1u << lane) - 1u))] = val(i);
-      if ((__ffs(peers) - 1) == lane) row[k] = at + __popc(peers);
+  for (uint32_t i0 = lo; i0 < hi; i0 += 32 * OS_BATCH) {
+    uint32_t kk[OS_BATCH]; float vv[OS_BATCH];
+#pragma unroll
+    for (int u = 0; u < OS_BATCH; u++) {
+      const uint32_t i = i0 + 32u * u + lane;
+      kk[u] = i < hi ? key(i) : 0xffffffffu; vv[u] = i < hi ? val(i) : 0.f;
     }
-    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < OS_BATCH; u++) {
+      if (i0 + 32u * u >= hi) break;
+      const bool have = kk[u] != 0xffffffffu;
+      const uint32_t k = have ? kk[u] : 0xffffffffu - lane;
+      const uint32_t peers = __match_any_sync(0xffffffffu, k);
+      uint32_t at = 0;
+      if (have) at = row[k];
+      __syncwarp();
+      if (have) {
+        sorted[kbase[k] + at + __popc(peers & ((1u << lane) - 1u))] = vv[u];
+        if ((__ffs(peers) - 1) == lane) row[k] = at + __popc(peers);
+      }
+      __syncwarp();
+    }
   }
   __syncthreads();
   // 4. one warp per key: its run added in order (every lane carries the same sum; values come 32 at a time)
@@ -88,76 +104,140 @@ __device__ void cta_ordered_keyed_sum(uint32_t n, KeyFn key, ValFn val, uint32_t
 }
 
 
-// The same for two sums per key that share the records (CGroup::cov_sum and CGroup::multi).  Keys >= K_sum are sorted
-// like the others but not added (padding entries).  val(i) returns a float2; sorted: [n] float2.
+// The same for two sums per key that share the records (CGroup::cov_sum and CGroup::multi), for keys that are SPARSE in a
+// large range (group slots of a bundle: thousands were created, a handful are visited by the records at hand).  The
+// distinct keys are first collected in a shared-memory hash table and numbered densely; the counting sort runs on the
+// dense numbers, the sums go to acc0 / acc1 [key].  key(i) < 0 marks padding.  Returns false (nothing done) when the
+// records visit more than OS_DENSE_MAX distinct keys: the caller falls back to its serial loop.
+#define OS_TAB 1024            // hash slots
+#define OS_DENSE_MAX 448       // distinct keys the shared-memory counts can take
+struct OrderedSumSmem {
+  uint32_t tkey[OS_TAB]; int32_t tidx[OS_TAB];
+  uint32_t dkey[OS_DENSE_MAX];
+  uint32_t cnt[8 * OS_DENSE_MAX]; uint32_t kbase[OS_DENSE_MAX + 1];
+  uint32_t ndist; int overflow;
+};
+
 template <class KeyFn, class ValFn>
-__device__ void cta_ordered_keyed_sum2(uint32_t n, KeyFn key, ValFn val, uint32_t K, uint32_t K_sum, float* acc0, float* acc1, uint32_t* cnt,
-                                       uint32_t* kbase, float2* sorted) {
+__device__ bool cta_ordered_keyed_sum2(uint32_t n, KeyFn key, ValFn val, float* acc0, float* acc1, OrderedSumSmem& M, float2* sorted) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t W = blockDim.x >> 5;
+  const uint32_t W = blockDim.x >> 5;      // <= 8
+  // 0. the distinct keys
+  for (uint32_t x = threadIdx.x; x < OS_TAB; x += blockDim.x) M.tkey[x] = 0xffffffffu;
+  if (threadIdx.x == 0) { M.ndist = 0; M.overflow = 0; }
+  __syncthreads();
+  for (uint32_t i0 = threadIdx.x; i0 < n; i0 += blockDim.x * OS_BATCH) {
+    int32_t kk[OS_BATCH];
+#pragma unroll
+    for (int u = 0; u < OS_BATCH; u++) { const uint32_t i = i0 + u * blockDim.x; kk[u] = i < n ? key(i) : -1; }
+#pragma unroll
+    for (int u = 0; u < OS_BATCH; u++) {
+      if (kk[u] < 0) continue;
+      uint32_t h = ((uint32_t)kk[u] * 2654435761u) >> 22;
+      for (int probe = 0; probe < OS_TAB; probe++) {
+        const uint32_t old = M.tkey[h];
+        if (old == (uint32_t)kk[u]) break;
+        if (old == 0xffffffffu) { const uint32_t was = atomicCAS(&M.tkey[h], 0xffffffffu, (uint32_t)kk[u]); if (was == 0xffffffffu || was == (uint32_t)kk[u]) break; }
+        h = (h + 1) & (OS_TAB - 1);
+        if (probe == OS_TAB - 1) M.overflow = 1;
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t x = threadIdx.x; x < OS_TAB; x += blockDim.x) {
+    if (M.tkey[x] != 0xffffffffu) {
+      const uint32_t id = atomicAdd(&M.ndist, 1u);
+      M.tidx[x] = (int32_t)id;
+      if (id < OS_DENSE_MAX) M.dkey[id] = M.tkey[x];
+    }
+  }
+  __syncthreads();
+  const uint32_t K = M.ndist;
+  if (M.overflow || K > OS_DENSE_MAX) { __syncthreads(); return false; }
+  if (K == 0) return true;
+  auto dense = [&](int32_t k) -> uint32_t {
+    uint32_t h = ((uint32_t)k * 2654435761u) >> 22;
+    while (M.tkey[h] != (uint32_t)k) h = (h + 1) & (OS_TAB - 1);
+    return (uint32_t)M.tidx[h];
+  };
   uint32_t S = (n + W - 1) / W;
   S = (S + 31u) & ~31u;
   const uint32_t lo = min(n, w * S), hi = min(n, lo + S);
-  uint32_t* row = cnt + (size_t)w * K;
-  for (size_t x = threadIdx.x; x < (size_t)W * K; x += blockDim.x) cnt[x] = 0;
+  uint32_t* row = M.cnt + (size_t)w * K;
+  for (uint32_t x = threadIdx.x; x < W * K; x += blockDim.x) M.cnt[x] = 0;
   __syncthreads();
-  for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
-    const uint32_t i = i0 + lane;
-    const bool have = i < hi;
-    const uint32_t k = have ? key(i) : 0xffffffffu - lane;
-    const uint32_t peers = __match_any_sync(0xffffffffu, k);
-    if (have && (__ffs(peers) - 1) == lane) row[k] += __popc(peers);
-    __syncwarp();
+  for (uint32_t i0 = lo; i0 < hi; i0 += 32 * OS_BATCH) {
+    int32_t kk[OS_BATCH];
+#pragma unroll
+    for (int u = 0; u < OS_BATCH; u++) { const uint32_t i = i0 + 32u * u + lane; kk[u] = i < hi ? key(i) : -1; }
+#pragma unroll
+    for (int u = 0; u < OS_BATCH; u++) {
+      if (i0 + 32u * u >= hi) break;
+      const bool have = kk[u] >= 0;
+      const uint32_t k = have ? dense(kk[u]) : 0xffffffffu - lane;
+      const uint32_t peers = __match_any_sync(0xffffffffu, k);
+      if (have && (__ffs(peers) - 1) == lane) row[k] += __popc(peers);
+      __syncwarp();
+    }
   }
   __syncthreads();
   for (uint32_t k = threadIdx.x; k < K; k += blockDim.x) {
     uint32_t run = 0;
-    for (uint32_t x = 0; x < W; x++) { const uint32_t c = cnt[(size_t)x * K + k]; cnt[(size_t)x * K + k] = run; run += c; }
-    kbase[k + 1] = run;
+    for (uint32_t x = 0; x < W; x++) { const uint32_t c = M.cnt[(size_t)x * K + k]; M.cnt[(size_t)x * K + k] = run; run += c; }
+    M.kbase[k + 1] = run;
   }
   __syncthreads();
-  if (w == 0) {
-    uint32_t carry = 0;
-    for (uint32_t k0 = 0; k0 < K; k0 += 32) {
-      const uint32_t k = k0 + lane;
-      uint32_t inc = k < K ? kbase[k + 1] : 0u;
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
-      if (k < K) kbase[k + 1] = carry + inc;
-      carry += __shfl_sync(0xffffffffu, inc, 31);
+  if (threadIdx.x == 0) { uint32_t run = 0; for (uint32_t k = 0; k < K; k++) { const uint32_t c = M.kbase[k + 1]; M.kbase[k] = run; run += c; } M.kbase[K] = run; }
+  __syncthreads();
+  for (uint32_t i0 = lo; i0 < hi; i0 += 32 * OS_BATCH) {
+    int32_t kk[OS_BATCH]; float2 vv[OS_BATCH];
+#pragma unroll
+    for (int u = 0; u < OS_BATCH; u++) {
+      const uint32_t i = i0 + 32u * u + lane;
+      kk[u] = i < hi ? key(i) : -1; vv[u] = i < hi ? val(i) : make_float2(0.f, 0.f);
     }
-    if (lane == 0) kbase[0] = 0;
-  }
-  __syncthreads();
-  for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
-    const uint32_t i = i0 + lane;
-    const bool have = i < hi;
-    const uint32_t k = have ? key(i) : 0xffffffffu - lane;
-    const uint32_t peers = __match_any_sync(0xffffffffu, k);
-    uint32_t at = 0;
-    if (have) at = row[k];
-    __syncwarp();
-    if (have) {
-      sorted[kbase[k] + at + __popc(peers & ((1u << lane) - 1u))] = val(i);
-      if ((__ffs(peers) - 1) == lane) row[k] = at + __popc(peers);
+#pragma unroll
+    for (int u = 0; u < OS_BATCH; u++) {
+      if (i0 + 32u * u >= hi) break;
+      const bool have = kk[u] >= 0;
+      const uint32_t k = have ? dense(kk[u]) : 0xffffffffu - lane;
+      const uint32_t peers = __match_any_sync(0xffffffffu, k);
+      uint32_t at = 0;
+      if (have) at = row[k];
+      __syncwarp();
+      if (have) {
+        sorted[M.kbase[k] + at + __popc(peers & ((1u << lane) - 1u))] = vv[u];
+        if ((__ffs(peers) - 1) == lane) row[k] = at + __popc(peers);
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
   __syncthreads();
-  for (uint32_t k = w; k < K_sum; k += W) {
-    const uint32_t a = kbase[k], z = kbase[k + 1];
+  for (uint32_t k = w; k < K; k += W) {
+    const uint32_t a = M.kbase[k], z = M.kbase[k + 1];
     if (a == z) continue;
-    float s0 = acc0[k], s1 = acc1[k];
+    const uint32_t real = M.dkey[k];
+    float s0 = acc0[real], s1 = acc1[real];
     float2 xnext = a + lane < z ? sorted[a + lane] : make_float2(0.f, 0.f);
     for (uint32_t j0 = a; j0 < z; j0 += 32) {
       const float2 x = xnext;
       xnext = j0 + 32 + lane < z ? sorted[j0 + 32 + lane] : make_float2(0.f, 0.f);
       const int m = (int)min(32u, z - j0);
-      for (int l = 0; l < m; l++) {
-        s0 = __fadd_rn(s0, __shfl_sync(0xffffffffu, x.x, l));
-        s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, x.y, l));
+      if (m == 32) {   // unrolled: the shuffles of a chunk are independent of the two chains of adds and run ahead of them
+#pragma unroll
+        for (int l = 0; l < 32; l++) {
+          s0 = __fadd_rn(s0, __shfl_sync(0xffffffffu, x.x, l));
+          s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, x.y, l));
+        }
+      } else {
+        for (int l = 0; l < m; l++) {
+          s0 = __fadd_rn(s0, __shfl_sync(0xffffffffu, x.x, l));
+          s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, x.y, l));
+        }
       }
     }
-    if (lane == 0) { acc0[k] = s0; acc1[k] = s1; }
+    if (lane == 0) { acc0[real] = s0; acc1[real] = s1; }
   }
   __syncthreads();
+  return true;
 }

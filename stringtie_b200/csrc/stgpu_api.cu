@@ -32,8 +32,8 @@ struct stg_ctx {
   stg_params params;
   cudaStream_t stream = nullptr;
   cudaStream_t aux_stream = nullptr;   // second stream of the rows a8 + a9 stage (deep bundles beside the shallow mass)
-  cudaStream_t aux2_stream = nullptr;  // third stream: the very deep bundles
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+  cudaStream_t aux3_stream = nullptr;  // third stream: the oversized bundles (one cluster of CTAs each)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
   std::string error;
   bool profiling = false;
   std::vector<Timed> timed;      // events of the last stg_run
@@ -306,8 +306,8 @@ int stg_init(const stg_params* params, int device, stg_ctx** out) {
   }
   CK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CK(nullptr, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
-  CK(nullptr, cudaStreamCreateWithFlags(&ctx->aux2_stream, cudaStreamNonBlocking));
-  CK(nullptr, cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
+  CK(nullptr, cudaStreamCreateWithFlags(&ctx->aux3_stream, cudaStreamNonBlocking));
+  CK(nullptr, cudaEventCreateWithFlags(&ctx->ev_join3, cudaEventDisableTiming));
   CK(nullptr, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   CK(nullptr, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   *out = ctx;
@@ -323,8 +323,8 @@ int stg_shutdown(stg_ctx* ctx) {
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
-  if (ctx->aux2_stream) { cudaStreamSynchronize(ctx->aux2_stream); cudaStreamDestroy(ctx->aux2_stream); }
-  if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
+  if (ctx->aux3_stream) { cudaStreamSynchronize(ctx->aux3_stream); cudaStreamDestroy(ctx->aux3_stream); }
+  if (ctx->ev_join3) cudaEventDestroy(ctx->ev_join3);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
@@ -765,6 +765,7 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
   if (pr.longreads || pr.mixedMode || pr.viral || pr.guided)
     return fail(ctx, STG_EUNSUPPORTED, "stg_build_groups: only the short-read de novo path is implemented");
   CK(ctx, cudaSetDevice(ctx->device));
+  { static int dbg = -1; if (dbg < 0) { dbg = getenv("STGPU_GROUPS_DEBUG") ? 1 : 0; groups_set_debug(dbg); } }
   cudaStream_t st = ctx->stream;
   DevBatchView& v = d->v;
   GroupsView& g = d->gv;
@@ -834,22 +835,28 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
   JuncParams jp{pr.junctionsupport, pr.sserror, pr.junctionthr, pr.eonly};
   int64_t n_deep = 0;   // `order` is sorted by decreasing read count
   while (n_deep < nb && (int64_t)d->h_nreads[order[n_deep]] >= groups_deep_reads()) n_deep++;
-  int64_t n_vdeep = 0;
-  while (n_vdeep < n_deep && (int64_t)d->h_nreads[order[n_vdeep]] >= groups_vdeep_reads()) n_vdeep++;
-  {  // the log of the very deep bundles' ordered sums
-    std::vector<uint32_t> voff((size_t)n_vdeep + 1, 0);
-    for (int64_t i = 0; i < n_vdeep; i++) voff[i + 1] = voff[i] + d->h_nreads[order[i]];
-    const int64_t vr = voff[n_vdeep];
+  int64_t n_cluster = 0;   // the oversized bundles are walked by a cluster of CTAs each; their ordered sums go through a log
+  static int64_t cluster_reads = getenv("STGPU_CLUSTER_READS") ? atoll(getenv("STGPU_CLUSTER_READS")) : groups_cluster_reads();   // (tuning aid)
+  while (n_cluster < n_deep && (int64_t)d->h_nreads[order[n_cluster]] >= cluster_reads) n_cluster++;
+  {
+    std::vector<uint32_t> voff((size_t)n_cluster + 1, 0);
+    for (int64_t i = 0; i < n_cluster; i++) voff[i + 1] = voff[i] + d->h_nreads[order[i]];
+    const int64_t vr = voff[n_cluster];
     uint32_t* d_voff = nullptr;
-    TEMP(d_voff, n_vdeep + 1);
-    CK(ctx, cudaMemcpyAsync(d_voff, voff.data(), sizeof(uint32_t) * (n_vdeep + 1), cudaMemcpyHostToDevice, st));
+    TEMP(d_voff, n_cluster + 1);
+    CK(ctx, cudaMemcpyAsync(d_voff, voff.data(), sizeof(uint32_t) * (n_cluster + 1), cudaMemcpyHostToDevice, st));
     CK(ctx, cudaStreamSynchronize(st));   // voff leaves the host
     g.vlog_off = d_voff;
     TEMP(g.vlog_grp, 6 * vr); TEMP(g.vlog_val, 6 * vr); TEMP(g.vlog_sorted, 6 * vr); TEMP(g.vlog_fl, vr); TEMP(g.vlog_nf, vr);
-    TEMP(g.vlog_cnt, n_vdeep * groups_vlog_scratch());
+    uint8_t *ctl_raw = nullptr, *rec_raw = nullptr;
+    TEMP(ctl_raw, (int64_t)groups_cluster_ctl_bytes() * std::max<int64_t>(n_cluster, 1));
+    TEMP(rec_raw, (int64_t)groups_cluster_rec_bytes() * std::max<int64_t>(n_cluster, 1));
+    g.cl_ctl = (void*)ctl_raw; g.cl_rec = (FastRec*)(void*)rec_raw;
+    TEMP(g.cl_claim, std::max<int64_t>(vr, 1));
+    CK(ctx, cudaMemsetAsync(g.cl_claim, 0x7f, sizeof(int32_t) * (size_t)std::max<int64_t>(vr, 1), st));
   }
   { Scope s(ctx, "groups_walk", 3);
-    CK(ctx, launch_groups_walk(v, g, jp, n_vdeep, n_deep, st, ctx->aux_stream, ctx->aux2_stream, ctx->ev_fork, ctx->ev_join, ctx->ev_join2)); }
+    CK(ctx, launch_groups_walk(v, g, jp, n_cluster, n_deep, st, ctx->aux_stream, ctx->aux3_stream, ctx->ev_fork, ctx->ev_join, ctx->ev_join3)); }
   { Scope s(ctx, "groups_scans", 4);
     CK(ctx, launch_scan_exclusive_add(g.b_ng, nb + 1, scan_state, ticket, st));
     CK(ctx, launch_scan_exclusive_add(g.b_ncol, nb + 1, scan_state, ticket, st));

@@ -112,7 +112,8 @@ struct GroupsView {
   uint32_t *ap_start, *ap_end; int8_t *ap_strand, *ap_mm;
   int32_t *jt_perm, *jt_inv;   // [n_juncs + n_introns] bundle b at b_junc_off[b] + intron base of b
   // very deep bundles (order[0 .. n_vdeep)): log of the ordered part of every simple read; read r of the i-th at vlog_off[i] + r
-  const uint32_t* vlog_off; int32_t* vlog_grp; float2 *vlog_val, *vlog_sorted; double *vlog_fl, *vlog_nf; uint32_t* vlog_cnt;
+  const uint32_t* vlog_off; int32_t* vlog_grp; float2 *vlog_val, *vlog_sorted; double *vlog_fl, *vlog_nf;
+  void* cl_ctl; struct FastRec* cl_rec; int32_t* cl_claim;   // oversized bundles (order[0 .. n_cluster)): control block, window records, claims
   // sparse groups / colours / readgroup
   uint32_t *g_start, *g_end; int32_t *g_color, *g_next, *g_merge, *g_grid; float *g_cov, *g_multi; int8_t* g_alive;
   int32_t* eqcol;
@@ -249,10 +250,11 @@ cudaError_t launch_find_trims(const DevBatchView& v, int64_t n, const int32_t* b
                               const uint32_t* end, const uint32_t* cap_off, uint32_t* o_cnt, uint32_t* o_pos, float* o_ab,
                               uint8_t* o_st, cudaStream_t st);
 cudaError_t launch_group_caps(const DevBatchView& v, uint32_t* rcap, unsigned long long* total, int32_t* rj, cudaStream_t st);
-cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, int64_t n_vdeep, int64_t n_deep, cudaStream_t st,
-                               cudaStream_t aux, cudaStream_t aux2, cudaEvent_t fork, cudaEvent_t join, cudaEvent_t join2);
-int64_t groups_vdeep_reads();
-int64_t groups_vlog_scratch();  // bundles with at least this many reads are walked by the widest kernel
+cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, int64_t n_cluster, int64_t n_deep,
+                               cudaStream_t st, cudaStream_t aux, cudaStream_t aux3, cudaEvent_t fork, cudaEvent_t join, cudaEvent_t join3);
+void groups_set_debug(int on);
+int64_t groups_cluster_reads();   // bundles with at least this many reads are walked by a cluster of CTAs (row x1)
+size_t groups_cluster_ctl_bytes(); size_t groups_cluster_rec_bytes();
 int64_t groups_deep_reads();   // bundles with at least this many reads are walked by the wide kernel
 cudaError_t launch_groups_finish(const DevBatchView& v, const GroupsView& g, cudaStream_t st);
 cudaError_t launch_neutral_count(const DevBatchView& v, const GroupsView& g, uint32_t* reg_off, cudaStream_t st);
