@@ -69,7 +69,9 @@ typedef struct stg_params {
   uint8_t longreads, rawreads;
   uint8_t includesource;    /* 1 */
   uint8_t geneabundance, havePtFeatures;
-  uint8_t reserved[18];
+  uint8_t have_gseq;        /* the host has the genomic sequence loaded (--ref / CRAM reference): the reference then filters
+                               junctions by splice consensus (rlink.cpp:14456-14530); not built -> stg_init refuses */
+  uint8_t reserved[17];
 } stg_params;
 
 /* Fill *p with the reference defaults. */

@@ -31,7 +31,7 @@ class StgParams(C.Structure):
         ("viral", C.c_uint8), ("mixedMode", C.c_uint8), ("isnascent", C.c_uint8), ("printNascent", C.c_uint8),
         ("guided", C.c_uint8), ("isunitig", C.c_uint8), ("longreads", C.c_uint8), ("rawreads", C.c_uint8),
         ("includesource", C.c_uint8), ("geneabundance", C.c_uint8), ("havePtFeatures", C.c_uint8),
-        ("reserved", C.c_uint8 * 18),
+        ("have_gseq", C.c_uint8), ("reserved", C.c_uint8 * 17),
     ]
 
 

@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel
   __shared__ double red_a[CLUSTER_THREADS / 32], red_c[CLUSTER_THREADS / 32];
   __shared__ int red_ea[CLUSTER_THREADS / 32], red_ec[CLUSTER_THREADS / 32];
   int emin_a = 4096, emin_c = 4096;   // the boss: smallest unit of the fragment-sum terms so far
-  int color = 0, ng_u = 0;
+  int color = 0;
   double nf = 0, fl = 0;         // the boss
   int n = 0, slow_len = 0, slow_budget = 0, width = 32, pb = 0, flushed = 0;
   const int inr = (int)nr;
@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel
       cluster_sync_all();      // (5)
       if (boss) { const long long t = clock64(); t_walk += t - t0c; t0c = t; }
       S.curr.a = ctl->curr[0]; S.curr.b = ctl->curr[1]; S.curr.c = ctl->curr[2];
-      ng_u = ctl->ng; color = ctl->color;
+      color = ctl->color;
       if (ctl->err) break;
       n++;
       flushed = n;
@@ -689,28 +689,31 @@ static cudaError_t walk_launch(const DevBatchView& v, const GroupsView& g, const
 cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const JuncParams& p, int64_t n_cluster, int64_t n_deep,
                                cudaStream_t st, cudaStream_t aux, cudaStream_t aux3, cudaEvent_t fork, cudaEvent_t join, cudaEvent_t join3) {
   if (v.n_bundles == 0) return cudaSuccess;
-  cudaError_t e;
-  const int64_t n_vdeep = n_cluster;
-  if (n_deep > 0) { if ((e = cudaEventRecord(fork, st)) != cudaSuccess) return e; }
-  if (n_cluster > 0) {   // the oversized bundles: one cluster of CTAs each
-    if ((e = cudaStreamWaitEvent(aux3, fork, 0)) != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(n_cluster * CLUSTER_CTAS)); cfg.blockDim = dim3(CLUSTER_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = aux3;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CLUSTER_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    if ((e = cudaLaunchKernelEx(&cfg, groups_walk_cluster_kernel, v, g, p, 0u)) != cudaSuccess) return e;
-    if ((e = cudaEventRecord(join3, aux3)) != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess, e2;
+  bool forked_aux = false, forked_aux3 = false;
+  if (n_deep > 0) e = cudaEventRecord(fork, st);
+  if (e == cudaSuccess && n_cluster > 0) {   // the oversized bundles: one cluster of CTAs each
+    if ((e = cudaStreamWaitEvent(aux3, fork, 0)) == cudaSuccess) {
+      forked_aux3 = true;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(n_cluster * CLUSTER_CTAS)); cfg.blockDim = dim3(CLUSTER_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = aux3;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CLUSTER_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, groups_walk_cluster_kernel, v, g, p, 0u);
+    }
   }
-  if (n_deep > n_vdeep) {   // the deep bundles next to the shallow mass
-    if ((e = cudaStreamWaitEvent(aux, fork, 0)) != cudaSuccess) return e;
-    if ((e = walk_launch<4, 4, false>(v, g, p, (unsigned)(n_deep - n_vdeep), (uint32_t)n_vdeep, aux)) != cudaSuccess ||
-        (e = cudaEventRecord(join, aux)) != cudaSuccess) return e;
+  if (e == cudaSuccess && n_deep > n_cluster) {   // the deep bundles next to the shallow mass
+    if ((e = cudaStreamWaitEvent(aux, fork, 0)) == cudaSuccess) {
+      forked_aux = true;
+      e = walk_launch<4, 4, false>(v, g, p, (unsigned)(n_deep - n_cluster), (uint32_t)n_cluster, aux);
+    }
   }
-  if (v.n_bundles > n_deep && (e = walk_launch<2, 8, true>(v, g, p, (unsigned)(v.n_bundles - n_deep), (uint32_t)n_deep, st)) != cudaSuccess) return e;
-  if (n_deep > n_vdeep && (e = cudaStreamWaitEvent(st, join, 0)) != cudaSuccess) return e;
-  if (n_cluster > 0 && (e = cudaStreamWaitEvent(st, join3, 0)) != cudaSuccess) return e;
-  return cudaSuccess;
+  if (e == cudaSuccess && v.n_bundles > n_deep) e = walk_launch<2, 8, true>(v, g, p, (unsigned)(v.n_bundles - n_deep), (uint32_t)n_deep, st);
+  // join: also on the error path, so that nothing still runs on the side streams when the caller releases the scratch
+  if (forked_aux) { if ((e2 = cudaEventRecord(join, aux)) == cudaSuccess) e2 = cudaStreamWaitEvent(st, join, 0); if (e == cudaSuccess) e = e2; }
+  if (forked_aux3) { if ((e2 = cudaEventRecord(join3, aux3)) == cudaSuccess) e2 = cudaStreamWaitEvent(st, join3, 0); if (e == cudaSuccess) e = e2; }
+  return e;
 }
 
 void groups_set_debug(int on) { cudaMemcpyToSymbol(g_groups_debug, &on, sizeof(int)); }

@@ -240,7 +240,18 @@ int validate(stg_ctx* ctx, const stg_packed_batch* h) {
   if (h->n_reads >= (int64_t)0x7fffffff || h->n_segs >= (int64_t)0xffffffffLL || h->n_pairs >= (int64_t)0xffffffffLL ||
       h->n_juncs >= (int64_t)0x7fffffff)
     return fail(ctx, STG_ERANGE, "batch exceeds 32-bit index space; split it");
-  if (h->n_bundles == 0) return STG_OK;
+  if (h->n_bundles == 0) {
+    if (h->n_reads || h->n_segs || h->n_pairs || h->n_juncs) return fail(ctx, STG_EINVAL, "reads / junctions without a bundle");
+    return STG_OK;
+  }
+  if (!h->b_start || !h->b_end || !h->b_read_off || !h->b_junc_off) return fail(ctx, STG_EINVAL, "null bundle array");
+  if (h->n_reads && (!h->r_start || !h->r_end || !h->r_len || !h->r_count || !h->r_nh || !h->r_strand || !h->r_flags || !h->r_seg_off ||
+                     !h->r_pair_off || !h->seg_start || !h->seg_end))
+    return fail(ctx, STG_EINVAL, "null read array");
+  if (h->n_segs > h->n_reads && !h->rjunc_idx) return fail(ctx, STG_EINVAL, "null rjunc_idx");
+  if (h->n_pairs && (!h->pair_idx || !h->pair_cnt)) return fail(ctx, STG_EINVAL, "null pair array");
+  if (h->n_juncs && (!h->j_start || !h->j_end || !h->j_strand || !h->j_guide_match || !h->j_nreads || !h->j_nm || !h->j_mm))
+    return fail(ctx, STG_EINVAL, "null junction array");
   if (h->b_read_off[0] != 0 || h->b_read_off[h->n_bundles] != (uint32_t)h->n_reads)
     return fail(ctx, STG_EINVAL, "b_read_off does not span the reads");
   if (h->b_junc_off[0] != 0 || h->b_junc_off[h->n_bundles] != (uint32_t)h->n_juncs)
@@ -249,6 +260,9 @@ int validate(stg_ctx* ctx, const stg_packed_batch* h) {
     return fail(ctx, STG_EINVAL, "r_seg_off does not span the segments");
   if (h->n_reads && (h->r_pair_off[0] != 0 || h->r_pair_off[h->n_reads] != (uint32_t)h->n_pairs))
     return fail(ctx, STG_EINVAL, "r_pair_off does not span the pair links");
+  // every read has at least one segment: the introns of read n sit at r_seg_off[n] - n, which must not wrap
+  for (int64_t n = 0; n < h->n_reads; n++)
+    if (h->r_seg_off[n + 1] <= h->r_seg_off[n]) return fail(ctx, STG_EINVAL, "read without segments (r_seg_off not strictly increasing)");
   for (int64_t b = 0; b < h->n_bundles; b++) {
     if (h->b_end[b] < h->b_start[b]) return fail(ctx, STG_EINVAL, "bundle with end < start");
     if (h->b_read_off[b + 1] < h->b_read_off[b] || h->b_junc_off[b + 1] < h->b_junc_off[b])
@@ -292,24 +306,41 @@ int stg_init(const stg_params* params, int device, stg_ctx** out) {
     delete ctx;
     return fail(nullptr, STG_EUNSUPPORTED, "long-read / mixed mode junction correction (rlink.cpp:16668-16975) is not built yet");
   }
+  if (ctx->params.have_gseq) {
+    delete ctx;
+    return fail(nullptr, STG_EUNSUPPORTED, "splice-consensus filtering from the genomic sequence (--ref / CRAM reference, rlink.cpp:14456-14530) is not built: "
+                                           "the junction pass would keep junctions the reference drops");
+  }
   if (ctx->params.viral || ctx->params.havePtFeatures) {
     delete ctx;
     return fail(nullptr, STG_EUNSUPPORTED, "--viral / --ptf branches of the junction pass (rlink.cpp:14189-14202, 14543-14589) are not built yet");
   }
-  CK(nullptr, cudaSetDevice(device));
+  auto init_fail = [&](cudaError_t e, const char* what) {
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->aux3_stream) cudaStreamDestroy(ctx->aux3_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_join3) cudaEventDestroy(ctx->ev_join3);
+    delete ctx;
+    return fail(nullptr, STG_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  };
+#define ICK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return init_fail(e__, #call); } while (0)
+  ICK(cudaSetDevice(device));
   cudaDeviceProp prop;
-  CK(nullptr, cudaGetDeviceProperties(&prop, device));
+  ICK(cudaGetDeviceProperties(&prop, device));
   ctx->num_sms = prop.multiProcessorCount;
   if (prop.major < 10) {
     delete ctx;
     return fail(nullptr, STG_ENODEV, "libstgpu is built for sm_100a (B200) only");
   }
-  CK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  CK(nullptr, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
-  CK(nullptr, cudaStreamCreateWithFlags(&ctx->aux3_stream, cudaStreamNonBlocking));
-  CK(nullptr, cudaEventCreateWithFlags(&ctx->ev_join3, cudaEventDisableTiming));
-  CK(nullptr, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-  CK(nullptr, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  ICK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ICK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+  ICK(cudaStreamCreateWithFlags(&ctx->aux3_stream, cudaStreamNonBlocking));
+  ICK(cudaEventCreateWithFlags(&ctx->ev_join3, cudaEventDisableTiming));
+  ICK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  ICK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+#undef ICK
   *out = ctx;
   return STG_OK;
 }
@@ -356,12 +387,17 @@ int stg_builder_add(stg_builder* b, const stg_bundle_view* v) {
   if (!b || !v) return fail(nullptr, STG_EINVAL, "stg_builder_add: null argument");
   if (v->n_reads < 0 || v->n_juncs < 0 || v->end < v->start) return fail(b->ctx, STG_EINVAL, "stg_builder_add: bad view");
   const int32_t nr = v->n_reads;
-  const uint32_t s0 = nr ? v->r_seg_off[0] : 0, p0 = nr ? v->r_pair_off[0] : 0;
+  if (nr && (v->r_seg_off[0] != 0 || v->r_pair_off[0] != 0))
+    return fail(b->ctx, STG_EINVAL, "stg_builder_add: the CSR offsets of a view start at 0 (rjunc_idx is indexed from them)");
+  const uint32_t s0 = 0, p0 = 0;
   const uint32_t nseg = nr ? v->r_seg_off[nr] - s0 : 0;
   const uint32_t npair = nr ? v->r_pair_off[nr] - p0 : 0;
   for (int32_t n = 0; n < nr; n++)
     if (v->r_seg_off[n + 1] <= v->r_seg_off[n]) return fail(b->ctx, STG_EINVAL, "stg_builder_add: read without segments");
   const uint32_t seg_base = (uint32_t)b->seg_start.size(), pair_base = (uint32_t)b->pair_idx.size();
+  // sizes at entry: a failed append leaves the builder as it was
+  const size_t z_b = b->b_start.size(), z_r = b->r_start.size(), z_so = b->r_seg_off.size(), z_po = b->r_pair_off.size(),
+               z_i = b->rjunc_idx.size(), z_j = b->j_start.size(), z_bro = b->b_read_off.size(), z_bjo = b->b_junc_off.size();
   bool ok = b->b_start.push_back(v->start) && b->b_end.push_back(v->end);
   // the per-read arrays of a view are contiguous: bulk copies, only the CSR offsets are rebased one by one
   ok = ok && b->r_start.append(v->r_start, nr) && b->r_end.append(v->r_end, nr) && b->r_len.append(v->r_len, nr) &&
@@ -384,7 +420,13 @@ int stg_builder_add(stg_builder* b, const stg_bundle_view* v) {
        b->j_guide_match.append(v->j_guide_match, v->n_juncs) && b->j_nreads.append(v->j_nreads, v->n_juncs) &&
        b->j_nm.append(v->j_nm, v->n_juncs) && b->j_mm.append(v->j_mm, v->n_juncs);
   ok = ok && b->b_read_off.push_back((uint32_t)b->r_start.size()) && b->b_junc_off.push_back((uint32_t)b->j_start.size());
-  if (!ok) return fail(b->ctx, STG_ENOMEM, "stg_builder_add: out of host memory");
+  if (!ok) {
+    b->b_start.n = z_b; b->b_end.n = z_b; b->r_start.n = z_r; b->r_end.n = z_r; b->r_len.n = z_r; b->r_count.n = z_r; b->r_nh.n = z_r;
+    b->r_strand.n = z_r; b->r_flags.n = z_r; b->r_seg_off.n = z_so; b->r_pair_off.n = z_po; b->seg_start.n = seg_base; b->seg_end.n = seg_base;
+    b->rjunc_idx.n = z_i; b->pair_idx.n = pair_base; b->pair_cnt.n = pair_base; b->j_start.n = z_j; b->j_end.n = z_j; b->j_strand.n = z_j;
+    b->j_guide_match.n = z_j; b->j_nreads.n = z_j; b->j_nm.n = z_j; b->j_mm.n = z_j; b->b_read_off.n = z_bro; b->b_junc_off.n = z_bjo;
+    return fail(b->ctx, STG_ENOMEM, "stg_builder_add: out of host memory");
+  }
   return STG_OK;
 }
 
@@ -690,8 +732,11 @@ int stg_query_cov(stg_ctx* ctx, const stg_dbatch* d, int64_t n, const int32_t* b
   }
   CK(ctx, cudaSetDevice(ctx->device));
   int32_t* db = nullptr; int8_t* dl = nullptr; uint32_t *ds = nullptr, *de = nullptr; double* dout = nullptr;
-  CK(ctx, cudaMalloc(&db, n * sizeof(int32_t))); CK(ctx, cudaMalloc(&dl, n)); CK(ctx, cudaMalloc(&ds, n * 4));
-  CK(ctx, cudaMalloc(&de, n * 4)); CK(ctx, cudaMalloc(&dout, n * 8));
+  stg_dbatch tmp;   // temporaries come from the context's pool and go back to it on every way out
+  struct Release { stg_ctx* c; stg_dbatch* t; ~Release() { cudaStreamSynchronize(c->stream); free_batch_allocs(c, t); } } release{ctx, &tmp};
+  int rc = STG_OK;
+  if ((rc = dev_alloc(ctx, &tmp, &db, n)) || (rc = dev_alloc(ctx, &tmp, &dl, n)) || (rc = dev_alloc(ctx, &tmp, &ds, n)) ||
+      (rc = dev_alloc(ctx, &tmp, &de, n)) || (rc = dev_alloc(ctx, &tmp, &dout, n))) return rc;
   cudaStream_t st = ctx->stream;
   CK(ctx, cudaMemcpyAsync(db, bundle, n * 4, cudaMemcpyHostToDevice, st));
   CK(ctx, cudaMemcpyAsync(dl, lane, n, cudaMemcpyHostToDevice, st));
@@ -701,7 +746,6 @@ int stg_query_cov(stg_ctx* ctx, const stg_dbatch* d, int64_t n, const int32_t* b
   CK(ctx, launch_query_cov(d->v, n, db, dl, ds, de, sign, dout, st));
   CK(ctx, cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, st));
   CK(ctx, cudaStreamSynchronize(st));
-  cudaFree(db); cudaFree(dl); cudaFree(ds); cudaFree(de); cudaFree(dout);
   return STG_OK;
 }
 
@@ -729,9 +773,13 @@ int stg_find_trims(stg_ctx* ctx, const stg_dbatch* d, int64_t n, const int32_t* 
   const size_t tot = cap_off[n];
   int32_t* db = nullptr; int8_t* ds = nullptr; uint32_t *da = nullptr, *dz = nullptr, *dc = nullptr, *dn = nullptr, *dp = nullptr;
   float* df = nullptr; uint8_t* dt = nullptr;
-  CK(ctx, cudaMalloc(&db, n * 4)); CK(ctx, cudaMalloc(&ds, n)); CK(ctx, cudaMalloc(&da, n * 4)); CK(ctx, cudaMalloc(&dz, n * 4));
-  CK(ctx, cudaMalloc(&dc, (n + 1) * 4)); CK(ctx, cudaMalloc(&dn, n * 4)); CK(ctx, cudaMalloc(&dp, (tot + 1) * 4));
-  CK(ctx, cudaMalloc(&df, (tot + 1) * 4)); CK(ctx, cudaMalloc(&dt, tot + 1));
+  stg_dbatch tmp;   // temporaries come from the context's pool and go back to it on every way out
+  struct Release { stg_ctx* c; stg_dbatch* t; ~Release() { cudaStreamSynchronize(c->stream); free_batch_allocs(c, t); } } release{ctx, &tmp};
+  int rc = STG_OK;
+  if ((rc = dev_alloc(ctx, &tmp, &db, n)) || (rc = dev_alloc(ctx, &tmp, &ds, n)) || (rc = dev_alloc(ctx, &tmp, &da, n)) ||
+      (rc = dev_alloc(ctx, &tmp, &dz, n)) || (rc = dev_alloc(ctx, &tmp, &dc, n + 1)) || (rc = dev_alloc(ctx, &tmp, &dn, n)) ||
+      (rc = dev_alloc(ctx, &tmp, &dp, (int64_t)tot + 1)) || (rc = dev_alloc(ctx, &tmp, &df, (int64_t)tot + 1)) ||
+      (rc = dev_alloc(ctx, &tmp, &dt, (int64_t)tot + 1))) return rc;
   CK(ctx, cudaMemcpyAsync(db, bundle, n * 4, cudaMemcpyHostToDevice, st));
   CK(ctx, cudaMemcpyAsync(ds, sno, n, cudaMemcpyHostToDevice, st));
   CK(ctx, cudaMemcpyAsync(da, start, n * 4, cudaMemcpyHostToDevice, st));
@@ -752,7 +800,6 @@ int stg_find_trims(stg_ctx* ctx, const stg_dbatch* d, int64_t n, const int32_t* 
     CK(ctx, cudaMemcpyAsync(is_start, dt, tot, cudaMemcpyDeviceToHost, st));
   }
   CK(ctx, cudaStreamSynchronize(st));
-  cudaFree(db); cudaFree(ds); cudaFree(da); cudaFree(dz); cudaFree(dc); cudaFree(dn); cudaFree(dp); cudaFree(df); cudaFree(dt);
   return STG_OK;
 }
 

@@ -226,10 +226,19 @@ def test_malformed_batches_are_rejected_not_executed(engine):
         batch.free()
     a = {k: v.copy() for k, v in good.items()}
     a["r_seg_off"][5] = a["r_seg_off"][4] - 1 if a["r_seg_off"][4] > 0 else a["r_seg_off"][6] + 7
-    batch = engine.upload(a)
-    with pytest.raises(StgError):
-        engine.run(batch)
-    batch.free()
+    with pytest.raises(StgError, match="segments"):     # refused at upload: nothing reaches a kernel
+        engine.upload(a)
+    # a read without segments followed by a spliced read: r_seg_off[n] - n would wrap in the kernels
+    a = {k: v.copy() for k, v in good.items()}
+    a["r_seg_off"][1] = a["r_seg_off"][0]
+    with pytest.raises(StgError, match="segments"):
+        engine.upload(a)
+    # reads without a bundle
+    a = {k: v.copy() for k, v in good.items()}
+    a["b_start"] = a["b_start"][:0]; a["b_end"] = a["b_end"][:0]
+    a["b_read_off"] = a["b_read_off"][:1]; a["b_junc_off"] = a["b_junc_off"][:1]
+    with pytest.raises(StgError, match="without a bundle"):
+        engine.upload(a)
     check_batch(engine, good).free()   # the context still works
 
 
