@@ -93,3 +93,25 @@ def test_assembly_deepest_bundles_of_the_bench_workload(engine):
     neu, pr, stage = asm_util.gpu_predictions(engine, a)
     asm_util.assert_same_graph_stage(stage, ref)
     asm_util.assert_same_predictions(neu, pr, ref)
+
+
+def test_one_bundle_drop_in_returns_the_reference_prediction_list(engine):
+    """stg_infer_transcripts(assemble = 1), the call with the shape of infer_transcripts(BundleData*): BundleData::pred,
+    bpcov, num_fragments and frag_len of single bundles against the reference's dumps."""
+    g = load_golden("short_s13_jitter")
+    from stringtie_b200.stgb import input_view
+    a = input_view(g)
+    for b in (0, 3, 7, 11, int(g["b_start"].size) - 1):
+        cov, pred, nfrag, flen = engine.infer_transcripts_full(a, b)
+        r0, r1 = int(g["f_pred_off"][b]), int(g["f_pred_off"][b + 1])
+        assert np.array_equal(pred["start"], g["p_start"][r0:r1]) and np.array_equal(pred["end"], g["p_end"][r0:r1])
+        assert np.array_equal(pred["cov"].view(np.uint64), g["p_cov"][r0:r1].view(np.uint64))
+        assert np.array_equal(pred["tlen"], g["p_tlen"][r0:r1]) and np.array_equal(pred["geneno"], g["p_geneno"][r0:r1])
+        assert np.array_equal(pred["strand"], g["p_strand"][r0:r1])
+        e0, e1 = int(g["p_exon_off"][r0]), int(g["p_exon_off"][r1])
+        assert np.array_equal(pred["e_start"], g["pe_start"][e0:e1]) and np.array_equal(pred["e_end"], g["pe_end"][e0:e1])
+        assert np.array_equal(pred["e_cov"].view(np.uint32), g["pe_cov"][e0:e1].view(np.uint32))
+        assert np.array_equal(pred["exon_off"] - pred["exon_off"][0], g["p_exon_off"][r0:r1 + 1] - g["p_exon_off"][r0])
+        assert nfrag == g["f_num_fragments"][b] and flen == g["f_frag_len"][b]
+        c0, c1 = int(g["s1_cov_off"][b]), int(g["s1_cov_off"][b + 1])
+        assert np.array_equal(cov.reshape(-1).view(np.uint32), g["s1_cov"][c0:c1].view(np.uint32))
