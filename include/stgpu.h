@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define STG_ABI_VERSION 3 /* 2: stg_build_groups, stg_neutral_predictions, stg_find_trims and the groups array fetch */
+#define STG_ABI_VERSION 4 /* 2: stg_build_groups, stg_neutral_predictions, stg_find_trims and the groups array fetch */
 #define STG_BSIZE 10000 /* rlink.cpp:11 — block size of the blocked prefix sums in bpcov */
 
 enum {
@@ -160,10 +160,14 @@ int stg_builder_destroy(stg_builder* b);
 
 /* ---- device batches --------------------------------------------------------------------------------
  * stg_upload: validate, plan the HBM layout (bpcov offsets, tiles), allocate, enqueue H2D copies on the
- *             context stream.  `host` may be pageable or pinned (pinned makes the copies asynchronous).
- * stg_run:    enqueue every kernel of the stages listed at the top of this file. Asynchronous.
+ *             context's copy-in stream.  `host` may be pageable or pinned; pinned makes the copies asynchronous, and
+ *             then the arrays must stay valid until stg_upload_wait, stg_run or stg_free_batch of that batch returns.
+ *             The copy-in stream is separate from the compute stream: batch i+1 may be uploaded (from another host
+ *             thread, or before the stage calls of batch i) while batch i computes.
+ * stg_run:    wait for the batch's upload, enqueue every kernel of the stages listed at the top of this file.
  * stg_sync:   wait for the context stream.                                                            */
 int stg_upload(stg_ctx* ctx, const stg_packed_batch* host, stg_dbatch** out);
+int stg_upload_wait(stg_ctx* ctx, stg_dbatch* batch);
 int stg_run(stg_ctx* ctx, stg_dbatch* batch);
 int stg_sync(stg_ctx* ctx);
 int stg_free_batch(stg_ctx* ctx, stg_dbatch* batch);   /* device blocks go back to the context's pool for reuse */
@@ -176,6 +180,12 @@ int stg_cov_layout(const stg_dbatch* batch, int64_t* cov_off /*[n_bundles]*/, in
                    int64_t* total_floats);
 int stg_fetch_bpcov(stg_ctx* ctx, const stg_dbatch* batch, int64_t bundle, float* out /*[3*len_b], lane-major*/);
 int stg_fetch_bpcov_all(stg_ctx* ctx, const stg_dbatch* batch, float* out /*[total_floats]*/);
+/* The same copy started on the context's copy-out stream as soon as the last kernel that writes bpcov (inside stg_run)
+ * has finished: it overlaps stg_build_groups / stg_neutral_predictions / stg_assemble of the same batch, none of which
+ * writes bpcov.  `out` (pinned, or the copy is staged) is complete after stg_fetch_wait; stg_free_batch and a second
+ * stg_run of the batch wait for it too. */
+int stg_fetch_bpcov_all_begin(stg_ctx* ctx, stg_dbatch* batch, float* out /*[total_floats]*/);
+int stg_fetch_wait(stg_ctx* ctx, stg_dbatch* batch);
 const float* stg_device_bpcov(const stg_dbatch* batch); /* device pointer (for consumers that stay on the GPU) */
 /* CJunction::nreads_good / leftsupport / rightsupport after the stage; each [n_juncs] */
 int stg_fetch_junction_support(stg_ctx* ctx, const stg_dbatch* batch, double* nreads_good, double* leftsupport,

@@ -345,7 +345,9 @@ struct ClusterCtl {
   int32_t err, ng, color;
   int32_t curr[3];
   int32_t last[2][3];
-  uint32_t ok_mask[CLUSTER_WINDOW / 32], mint_mask[CLUSTER_WINDOW / 32], wait_mask[CLUSTER_WINDOW / 32], grow_mask[CLUSTER_WINDOW / 32];
+  int32_t n_grow[3];              // reads of the step that grow a group (three buffers: see the reset in the kernel)
+  uint32_t ok_mask[CLUSTER_WINDOW / 32], mint_mask[CLUSTER_WINDOW / 32], wait_mask[CLUSTER_WINDOW / 32];
+  int32_t grow[3][CLUSTER_WINDOW];
 };
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -401,13 +403,18 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel
   __shared__ OrderedSumSmem osm;   // scratch of the flush
   __shared__ double red_a[CLUSTER_THREADS / 32], red_c[CLUSTER_THREADS / 32];
   __shared__ int red_ea[CLUSTER_THREADS / 32], red_ec[CLUSTER_THREADS / 32];
+  __shared__ int32_t gl_t[CLUSTER_THREADS], gl_g[CLUSTER_THREADS];   // a chunk of the step's growing reads: slot, group,
+  __shared__ uint32_t gl_s[CLUSTER_THREADS], gl_e[CLUSTER_THREADS];  // ... new bounds
   int emin_a = 4096, emin_c = 4096;   // the boss: smallest unit of the fragment-sum terms so far
   int color = 0;
   double nf = 0, fl = 0;         // the boss
-  int n = 0, slow_len = 0, slow_budget = 0, width = 32, pb = 0, flushed = 0;
+  // a step costs the same whatever the width of the window (it is the latency of the classification's load chains and of
+  // the cluster barriers), so the window is always as wide as the cluster
+  const int width = CLUSTER_WINDOW;
+  int n = 0, slow_len = 0, slow_budget = 0, pb = 0, gb = 0, flushed = 0;
   const int inr = (int)nr;
   const unsigned FULL = 0xffffffffu;
-  if (boss) { ctl->err = 0; for (int x = 0; x < 3; x++) { ctl->last[0][x] = -1; ctl->last[1][x] = -1; } }
+  if (boss) { ctl->err = 0; for (int x = 0; x < 3; x++) { ctl->last[0][x] = -1; ctl->last[1][x] = -1; ctl->n_grow[x] = 0; } }
   cluster_sync_all();
 
   auto flush = [&](int upto) {    // the logged sums of the reads [flushed, upto): CTA 0 adds them (ordered_sum.cuh)
@@ -481,10 +488,13 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel
     const int hi = n + width < inr ? n + width : inr, me = n + gt;
     int st = 0, npc = -1;
     if (boss) t0c = clock64();
+    FastDeps D;
+    D.n = 0;
     if (classify) {
-      if (me < hi) st = classify_read<false>(S, me, n, hi, R[gt]);
+      if (me < hi) st = classify_read<true>(S, me, n, hi, R[gt], &D);
       if (st == 1 || st == 3) npc = R[gt].npc;
-      if (st == 1 && npc >= 0) atomicMin(&claim[npc], gt);
+      if (npc >= 0) atomicMin(&claim[npc], gt);
+      if (st == 3) ctl->grow[gb][atomicAdd(&ctl->n_grow[gb], 1)] = gt;
     }
     if (boss) { const long long t = clock64(); t_cls += t - t0c; t0c = t; }
     cluster_sync_all();        // (1) records and claims of this step are written
@@ -495,9 +505,36 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel
     if (classify) {
       // reads that continue into the SAME mate see each other's readgroup pushes: only the first simple one stays
       if (npc >= 0 && claim[npc] < gt) st = 2;
-      const unsigned okm = __ballot_sync(FULL, st == 1), mim = __ballot_sync(FULL, (st == 1 || st == 3) && R[gt].newcol);
-      const unsigned wam = __ballot_sync(FULL, st == 2), grm = __ballot_sync(FULL, st == 3);
-      if (lane == 0) { ctl->ok_mask[gw] = okm; ctl->mint_mask[gw] = mim; ctl->wait_mask[gw] = wam; ctl->grow_mask[gw] = grm; }
+      // reads that grow a group stay inside the run (groups_device.cuh, FastDeps): a read that took for granted a bound
+      // which an earlier read of the step moves waits for the next step.  The counter used two steps from now is cleared
+      // here: a cluster barrier lies between this and both its last readers and its next writers.
+      {
+        const int ngr = ctl->n_grow[gb];
+        if (boss) ctl->n_grow[(gb + 2) % 3] = 0;
+        for (int base = 0; base < ngr; base += CLUSTER_THREADS) {
+          if (base + tid < ngr) {
+            const int t = ctl->grow[gb][base + tid];
+            gl_t[tid] = t; gl_g[tid] = R[t].xg; gl_s[tid] = R[t].xs; gl_e[tid] = R[t].xe;
+          }
+          __syncthreads();
+          if ((st == 1 || st == 3) && D.n) {
+            const int m = ngr - base < CLUSTER_THREADS ? ngr - base : CLUSTER_THREADS;
+            for (int q = 0; q < m && st != 2; q++) {
+              if (gl_t[q] >= gt) continue;
+              for (int i = 0; i < D.n; i++)
+                if (D.g[i] == gl_g[q]) {
+                  if (D.kind >> i & 1u) { if (gl_s[q] <= D.x[i]) st = 2; }
+                  else if (gl_e[q] >= D.x[i]) st = 2;
+                }
+            }
+          }
+          __syncthreads();
+        }
+        gb = (gb + 1) % 3;
+      }
+      const unsigned okm = __ballot_sync(FULL, st == 1 || st == 3), mim = __ballot_sync(FULL, (st == 1 || st == 3) && R[gt].newcol);
+      const unsigned wam = __ballot_sync(FULL, st == 2);
+      if (lane == 0) { ctl->ok_mask[gw] = okm; ctl->mint_mask[gw] = mim; ctl->wait_mask[gw] = wam; }
       cluster_sync_all();      // (2) masks are in; every claim has been looked at
       if (npc >= 0) claim[npc] = 0x7f7f7f7f;
       {
@@ -509,9 +546,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel
           if (kw < 32) open = false;
         }
       }
-      const bool grows = k < CLUSTER_WINDOW && (ctl->grow_mask[k >> 5] >> (k & 31) & 1u);
       const bool waits0 = k < CLUSTER_WINDOW && (ctl->wait_mask[k >> 5] >> (k & 31) & 1u);
-      if (grows) k++;
       int before = 0, minted = 0;     // colours minted by the run's reads ahead of this thread / by the whole run
       for (int w2 = 0; w2 * 32 < k; w2++) {
         const int rem = k - 32 * w2;
@@ -546,9 +581,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel
       if (boss) { ctl->last[pb ^ 1][0] = -1; ctl->last[pb ^ 1][1] = -1; ctl->last[pb ^ 1][2] = -1; S.ncol += minted; }
       pb ^= 1;
       color += minted;
-      no_walk = k >= hi - n || grows || waits0;
-      if (k >= width) width = width * 2 < CLUSTER_WINDOW ? width * 2 : CLUSTER_WINDOW;
-      else { const int w2 = 2 * k + 8; width = w2 < 16 ? 16 : (w2 < CLUSTER_WINDOW ? w2 : CLUSTER_WINDOW); }
+      no_walk = k >= hi - n || waits0;
       n += k;
       if (k == 0) { slow_len = slow_len * 2 + 1 < 15 ? slow_len * 2 + 1 : 15; slow_budget = slow_len; }
       else if (k >= 8) slow_len = 0;
@@ -717,8 +750,9 @@ cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const
 }
 
 void groups_set_debug(int on) { cudaMemcpyToSymbol(g_groups_debug, &on, sizeof(int)); }
-// measured on C2 (profiles/r3_groups.md): 150 k 181 ms, 250 k 172 ms, 400 k 166 ms, 550 k 187 ms for the whole stage
-#define GROUPS_CLUSTER_READS 400000
+// measured on C2 (profiles/r3_groups_history.md), whole stage: 400 k 138 ms, 200 k 122 ms, 100 k 177 ms, 50 k 288 ms (more
+// clusters than the GPU holds at once)
+#define GROUPS_CLUSTER_READS 200000
 int64_t groups_cluster_reads() { return GROUPS_CLUSTER_READS; }
 size_t groups_cluster_ctl_bytes() { return sizeof(ClusterCtl); }
 size_t groups_cluster_rec_bytes() { return sizeof(FastRec) * CLUSTER_WINDOW; }

@@ -26,6 +26,8 @@ struct OneBundleOut {   // BundleData::pred of the last stg_infer_transcripts ca
   std::vector<uint32_t> p_exon_off, e_start, e_end; std::vector<float> e_cov;
 };
 
+struct StagePending { void* dst; size_t off, bytes; };
+
 struct stg_ctx {
   int device = 0;
   int num_sms = 0;
@@ -33,6 +35,15 @@ struct stg_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t aux_stream = nullptr;   // second stream of the rows a8 + a9 stage (deep bundles beside the shallow mass)
   cudaStream_t aux3_stream = nullptr;  // third stream: the oversized bundles (one cluster of CTAs each)
+  // staging for the small host<->device transfers of the stage functions (sizes, counters, per-bundle tables): they go
+  // through mapped pinned memory with a copy kernel on the compute stream instead of the copy engines, whose queues may
+  // hold seconds of bulk traffic of the neighbouring batches (stg_upload, stg_fetch_bpcov_all_begin)
+  uint8_t* stage_h = nullptr;
+  size_t stage_cap = 0, stage_used = 0;
+  std::vector<StagePending> stage_pending;
+  int64_t cluster_reads = 0;           // bundles with at least this many reads are walked by a cluster of CTAs (row x1)
+  cudaStream_t in_stream = nullptr;    // H2D copies of stg_upload (a batch can be uploaded while the previous one computes)
+  cudaStream_t out_stream = nullptr;   // D2H of bpcov started by stg_fetch_bpcov_all_begin (overlaps rows a8-a15)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
   std::string error;
   bool profiling = false;
@@ -132,6 +143,9 @@ struct stg_dbatch {
   AsmView av;                      // rows a10-a15 (stg_assemble)
   bool assembled = false;
   size_t stage_mark = 0;           // allocs.size() when stg_build_groups started: what stg_rewind gives back
+  cudaEvent_t ev_uploaded = nullptr;   // on in_stream after the last H2D copy of stg_upload
+  cudaEvent_t ev_cov = nullptr;        // on the context stream after the last kernel that writes bpcov
+  bool out_pending = false;            // a copy of stg_fetch_bpcov_all_begin may be in flight on out_stream
 };
 
 namespace {
@@ -191,12 +205,81 @@ int dev_alloc(stg_ctx* ctx, stg_dbatch* d, T** out, int64_t count) {
   return STG_OK;
 }
 
+// Bulk copies go out in pieces: a copy engine serves its queue one command at a time, so a multi-GB command would hold up
+// the 4-byte read-backs of the batch that is computing meanwhile (they travel in the same direction on another stream).
+cudaError_t copy_chunked(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+  const size_t CH = (size_t)32 << 20;
+  for (size_t o = 0; o < bytes; o += CH) {
+    const cudaError_t e = cudaMemcpyAsync((char*)dst + o, (const char*)src + o, bytes - o < CH ? bytes - o : CH, kind, st);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+__global__ void __launch_bounds__(256) copy_bytes_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t bytes) {
+  const size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = gridDim.x * (size_t)blockDim.x;
+  if ((((uintptr_t)dst | (uintptr_t)src | bytes) & 15u) == 0) {
+    for (size_t i = i0; i < bytes / 16; i += stride) ((uint4*)dst)[i] = ((const uint4*)src)[i];
+  } else if ((((uintptr_t)dst | (uintptr_t)src | bytes) & 3u) == 0) {
+    for (size_t i = i0; i < bytes / 4; i += stride) ((uint32_t*)dst)[i] = ((const uint32_t*)src)[i];
+  } else {
+    for (size_t i = i0; i < bytes; i += stride) dst[i] = src[i];
+  }
+}
+
+cudaError_t launch_copy(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (!bytes) return cudaSuccess;
+  const size_t want = (bytes / 16 + 255) / 256;
+  const unsigned grid = (unsigned)std::min<size_t>(std::max<size_t>(want, 1), 148 * 8);
+  copy_bytes_kernel<<<grid, 256, 0, st>>>((uint8_t*)dst, (const uint8_t*)src, bytes);
+  return cudaGetLastError();
+}
+
+// device -> host, delivered by small_sync()
+cudaError_t small_d2h(stg_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (!bytes) return cudaSuccess;
+  const size_t off = (ctx->stage_used + 15) & ~(size_t)15;
+  if (!ctx->stage_h || off + bytes > ctx->stage_cap) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+  ctx->stage_used = off + bytes;
+  ctx->stage_pending.push_back(StagePending{dst, off, bytes});
+  return launch_copy(ctx->stage_h + off, src, bytes, st);
+}
+
+// host -> device; the host array may be reused as soon as this returns
+cudaError_t small_h2d(stg_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (!bytes) return cudaSuccess;
+  const size_t off = (ctx->stage_used + 15) & ~(size_t)15;
+  if (!ctx->stage_h || off + bytes > ctx->stage_cap) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+  }
+  ctx->stage_used = off + bytes;
+  memcpy(ctx->stage_h + off, src, bytes);
+  return launch_copy(dst, ctx->stage_h + off, bytes, st);
+}
+
+struct StageScope {
+  stg_ctx* c;
+  explicit StageScope(stg_ctx* ctx) : c(ctx) {}
+  ~StageScope() { c->stage_pending.clear(); c->stage_used = 0; }
+};
+
+// wait for the stream, hand the staged read-backs to their destinations, recycle the staging area
+cudaError_t small_sync(stg_ctx* ctx, cudaStream_t st) {
+  const cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess)
+    for (const StagePending& p : ctx->stage_pending) memcpy(p.dst, ctx->stage_h + p.off, p.bytes);
+  ctx->stage_pending.clear();
+  ctx->stage_used = 0;
+  return e;
+}
+
 template <class T>
 int dev_upload(stg_ctx* ctx, stg_dbatch* d, const T** out, const T* host, int64_t count) {
   T* p = nullptr;
   int rc = dev_alloc(ctx, d, &p, count);
   if (rc) return rc;
-  if (count > 0) CK(ctx, cudaMemcpyAsync(p, host, (size_t)count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  if (count > 0) CK(ctx, copy_chunked(p, host, (size_t)count * sizeof(T), cudaMemcpyHostToDevice, ctx->in_stream));
   *out = p;
   return STG_OK;
 }
@@ -319,6 +402,9 @@ int stg_init(const stg_params* params, int device, stg_ctx** out) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->aux3_stream) cudaStreamDestroy(ctx->aux3_stream);
+    if (ctx->in_stream) cudaStreamDestroy(ctx->in_stream);
+    if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
+    if (ctx->stage_h) cudaFreeHost(ctx->stage_h);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_join3) cudaEventDestroy(ctx->ev_join3);
@@ -334,9 +420,16 @@ int stg_init(const stg_params* params, int device, stg_ctx** out) {
     delete ctx;
     return fail(nullptr, STG_ENODEV, "libstgpu is built for sm_100a (B200) only");
   }
+  // tuning / test aid: the tests lower the threshold to drive ordinary bundles through the cluster kernel
+  ctx->cluster_reads = getenv("STGPU_CLUSTER_READS") ? atoll(getenv("STGPU_CLUSTER_READS")) : groups_cluster_reads();
+  if (ctx->cluster_reads < 1) ctx->cluster_reads = 1;
   ICK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ICK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
   ICK(cudaStreamCreateWithFlags(&ctx->aux3_stream, cudaStreamNonBlocking));
+  ctx->stage_cap = (size_t)16 << 20;
+  ICK(cudaHostAlloc((void**)&ctx->stage_h, ctx->stage_cap, cudaHostAllocMapped | cudaHostAllocPortable));
+  ICK(cudaStreamCreateWithFlags(&ctx->in_stream, cudaStreamNonBlocking));
+  ICK(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
   ICK(cudaEventCreateWithFlags(&ctx->ev_join3, cudaEventDisableTiming));
   ICK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   ICK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
@@ -355,6 +448,9 @@ int stg_shutdown(stg_ctx* ctx) {
   cudaStreamDestroy(ctx->stream);
   if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
   if (ctx->aux3_stream) { cudaStreamSynchronize(ctx->aux3_stream); cudaStreamDestroy(ctx->aux3_stream); }
+  if (ctx->in_stream) { cudaStreamSynchronize(ctx->in_stream); cudaStreamDestroy(ctx->in_stream); }
+  if (ctx->out_stream) { cudaStreamSynchronize(ctx->out_stream); cudaStreamDestroy(ctx->out_stream); }
+  if (ctx->stage_h) cudaFreeHost(ctx->stage_h);
   if (ctx->ev_join3) cudaEventDestroy(ctx->ev_join3);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -489,15 +585,6 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
     v.n_rounds = std::max<uint32_t>(max_nt, 2048u);
   }
 
-#define UP(field, count) do { rc = dev_upload(ctx, d, &v.field, h->field, (int64_t)(count)); if (rc) { free_batch_allocs(ctx, d); delete d; return rc; } } while (0)
-  UP(b_start, nb); UP(b_end, nb); UP(b_read_off, nb + 1); UP(b_junc_off, nb + 1);
-  UP(r_start, h->n_reads); UP(r_end, h->n_reads); UP(r_len, h->n_reads); UP(r_count, h->n_reads); UP(r_nh, h->n_reads);
-  UP(r_strand, h->n_reads); UP(r_flags, h->n_reads); UP(r_seg_off, h->n_reads + 1); UP(r_pair_off, h->n_reads + 1);
-  UP(seg_start, h->n_segs); UP(seg_end, h->n_segs); UP(rjunc_idx, h->n_segs - h->n_reads);
-  UP(pair_idx, h->n_pairs); UP(pair_cnt, h->n_pairs);
-  UP(j_start, h->n_juncs); UP(j_end, h->n_juncs); UP(j_strand, h->n_juncs); UP(j_guide_match, h->n_juncs);
-  UP(j_nreads, h->n_juncs); UP(j_nm, h->n_juncs); UP(j_mm, h->n_juncs);
-#undef UP
   // bundle of the first read of every block of STG_READ_BLOCK reads (the per-read kernels start their search there)
   std::vector<uint32_t> cta_bundle((size_t)((h->n_reads + STG_READ_BLOCK - 1) / STG_READ_BLOCK) + 1, 0);
   {
@@ -508,13 +595,27 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
       cta_bundle[i] = (uint32_t)b;
     }
   }
-#define UPV(field, vec) do { rc = dev_upload(ctx, d, &v.field, vec.data(), (int64_t)vec.size()); if (rc) { free_batch_allocs(ctx, d); delete d; return rc; } } while (0)
+  CK(ctx, cudaEventCreateWithFlags(&d->ev_uploaded, cudaEventDisableTiming));
+  CK(ctx, cudaEventCreateWithFlags(&d->ev_cov, cudaEventDisableTiming));
+#define UPFAIL do { cudaStreamSynchronize(ctx->in_stream); free_batch_allocs(ctx, d); cudaEventDestroy(d->ev_uploaded); cudaEventDestroy(d->ev_cov); delete d; return rc; } while (0)
+#define UPV(field, vec) do { rc = dev_upload(ctx, d, &v.field, vec.data(), (int64_t)vec.size()); if (rc) UPFAIL; } while (0)
   UPV(b_len, len); UPV(b_stride, stride); UPV(b_gbase, gbase); UPV(b_tile_off, tile_off);
   UPV(cta_bundle, cta_bundle);
 #undef UPV
-  // the layout vectors are pageable locals: make sure their copies have left the host before they die
-  CK(ctx, cudaStreamSynchronize(ctx->stream));
-#define AL(field, count) do { rc = dev_alloc(ctx, d, &v.field, (int64_t)(count)); if (rc) { free_batch_allocs(ctx, d); delete d; return rc; } } while (0)
+  // the layout vectors are pageable locals: make sure their (small) copies have left the host before they die; the
+  // caller's arrays follow on the same copy stream and are only waited for by stg_run / stg_upload_wait
+  CK(ctx, cudaStreamSynchronize(ctx->in_stream));
+#define UP(field, count) do { rc = dev_upload(ctx, d, &v.field, h->field, (int64_t)(count)); if (rc) UPFAIL; } while (0)
+  UP(b_start, nb); UP(b_end, nb); UP(b_read_off, nb + 1); UP(b_junc_off, nb + 1);
+  UP(r_start, h->n_reads); UP(r_end, h->n_reads); UP(r_len, h->n_reads); UP(r_count, h->n_reads); UP(r_nh, h->n_reads);
+  UP(r_strand, h->n_reads); UP(r_flags, h->n_reads); UP(r_seg_off, h->n_reads + 1); UP(r_pair_off, h->n_reads + 1);
+  UP(seg_start, h->n_segs); UP(seg_end, h->n_segs); UP(rjunc_idx, h->n_segs - h->n_reads);
+  UP(pair_idx, h->n_pairs); UP(pair_cnt, h->n_pairs);
+  UP(j_start, h->n_juncs); UP(j_end, h->n_juncs); UP(j_strand, h->n_juncs); UP(j_guide_match, h->n_juncs);
+  UP(j_nreads, h->n_juncs); UP(j_nm, h->n_juncs); UP(j_mm, h->n_juncs);
+#undef UP
+  CK(ctx, cudaEventRecord(d->ev_uploaded, ctx->in_stream));
+#define AL(field, count) do { rc = dev_alloc(ctx, d, &v.field, (int64_t)(count)); if (rc) UPFAIL; } while (0)
   AL(r_ivl_cnt, h->n_reads + 1 + 16); AL(scan_state, (h->n_reads + 1) / 4096 + 2);
   d->scan_capacity = std::max<int64_t>(std::max<int64_t>(h->n_reads + 1, v.n_tiles + 1), v.n_rounds + 1);
   AL(scan_partials, scan_partials_needed(d->scan_capacity));
@@ -527,6 +628,7 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
   AL(jp_strand, h->n_juncs); AL(jp_nreads, h->n_juncs); AL(jp_nreads_good, h->n_juncs); AL(jp_left, h->n_juncs);
   AL(jp_right, h->n_juncs); AL(jp_mm, h->n_juncs); AL(jp_ej, h->n_juncs); AL(jp_good, h->n_juncs); AL(jp_good_strand, h->n_juncs);
 #undef AL
+#undef UPFAIL
   // the padding between a lane's length and its stride is written by the tile kernels; nothing else to clear
   *out = d;
   return STG_OK;
@@ -534,7 +636,14 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
 
 int stg_free_batch(stg_ctx* ctx, stg_dbatch* d) {
   if (!d) return STG_OK;
-  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    if (d->ev_uploaded) cudaEventSynchronize(d->ev_uploaded);
+    cudaStreamSynchronize(ctx->stream);
+    if (d->out_pending) cudaStreamSynchronize(ctx->out_stream);
+  }
+  if (d->ev_uploaded) cudaEventDestroy(d->ev_uploaded);
+  if (d->ev_cov) cudaEventDestroy(d->ev_cov);
   free_batch_allocs(ctx, d);
   delete d;
   return STG_OK;
@@ -546,6 +655,10 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   CK(ctx, cudaSetDevice(ctx->device));
   DevBatchView& v = d->v;
   cudaStream_t st = ctx->stream;
+  StageScope stage_scope(ctx);   // an early return leaves no staged read-back behind
+  // the caller's host arrays are free again once this returns; a pending D2H of bpcov must not see the rewrite
+  CK(ctx, cudaEventSynchronize(d->ev_uploaded));
+  if (d->out_pending) { CK(ctx, cudaStreamSynchronize(ctx->out_stream)); d->out_pending = false; }
   ctx->timed.clear();
   ctx->event_used = 0;
   KernelParams kp{ctx->params.junctionsupport, ctx->params.junctionthr, ctx->params.longreads};
@@ -564,9 +677,9 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   uint32_t n_ivl = 0;
   if (v.n_reads) {
     uint32_t err = 0;
-    CK(ctx, cudaMemcpyAsync(&n_ivl, v.r_ivl_cnt + v.n_reads, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaMemcpyAsync(&err, v.err_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaStreamSynchronize(st));
+    CK(ctx, small_d2h(ctx, &n_ivl, v.r_ivl_cnt + v.n_reads, sizeof(uint32_t), st));
+    CK(ctx, small_d2h(ctx, &err, v.err_flag, sizeof(uint32_t), st));
+    CK(ctx, small_sync(ctx, st));
     if (err) {
       std::string what;
       if (err & 1u) what += " r_seg_off runs backwards or past n_segs;";
@@ -604,8 +717,8 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   // second read-back: the size of the (chunk x tile) counter matrix
   uint32_t n_cells = 0;
   if (v.n_chunks) {
-    CK(ctx, cudaMemcpyAsync(&n_cells, v.ch_row_off + v.n_chunks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaStreamSynchronize(st));
+    CK(ctx, small_d2h(ctx, &n_cells, v.ch_row_off + v.n_chunks, sizeof(uint32_t), st));
+    CK(ctx, small_sync(ctx, st));
   }
   v.n_cells = n_cells;
   if ((int64_t)n_cells > d->cell_capacity) {
@@ -622,6 +735,7 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   { Scope s(ctx, "deep_deposit", 2); CK(ctx, launch_deep_deposit(v, ctx->num_sms, st)); }
   { Scope s(ctx, "cov_tile", 1); CK(ctx, launch_cov_tiles(v, ctx->num_sms, st)); }
   { Scope s(ctx, "cov_fill", 1); CK(ctx, launch_cov_fill(v, ctx->num_sms, st)); }
+  CK(ctx, cudaEventRecord(d->ev_cov, st));   // bpcov is final from here on (nothing later writes it)
   { Scope s(ctx, "cov_totals", 1); CK(ctx, launch_cov_totals(v, st)); }
   {
     JuncParams jp{ctx->params.junctionsupport, ctx->params.sserror, ctx->params.junctionthr, ctx->params.eonly};
@@ -669,6 +783,30 @@ int stg_fetch_bpcov_all(stg_ctx* ctx, const stg_dbatch* d, float* out) {
   CK(ctx, cudaSetDevice(ctx->device));
   CK(ctx, cudaMemcpyAsync(out, d->v.bpcov, sizeof(float) * 3 * (size_t)d->v.total_pos, cudaMemcpyDeviceToHost, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return STG_OK;
+}
+
+int stg_upload_wait(stg_ctx* ctx, stg_dbatch* d) {
+  if (!ctx || !d) return fail(ctx, STG_EINVAL, "stg_upload_wait: null argument");
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaEventSynchronize(d->ev_uploaded));
+  return STG_OK;
+}
+
+int stg_fetch_bpcov_all_begin(stg_ctx* ctx, stg_dbatch* d, float* out) {
+  if (!ctx || !d || !out) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_all_begin: bad argument");
+  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_all_begin: batch has not been run");
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaStreamWaitEvent(ctx->out_stream, d->ev_cov, 0));
+  d->out_pending = true;
+  CK(ctx, copy_chunked(out, d->v.bpcov, sizeof(float) * 3 * (size_t)d->v.total_pos, cudaMemcpyDeviceToHost, ctx->out_stream));
+  return STG_OK;
+}
+
+int stg_fetch_wait(stg_ctx* ctx, stg_dbatch* d) {
+  if (!ctx || !d) return fail(ctx, STG_EINVAL, "stg_fetch_wait: null argument");
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (d->out_pending) { CK(ctx, cudaStreamSynchronize(ctx->out_stream)); d->out_pending = false; }
   return STG_OK;
 }
 
@@ -738,14 +876,15 @@ int stg_query_cov(stg_ctx* ctx, const stg_dbatch* d, int64_t n, const int32_t* b
   if ((rc = dev_alloc(ctx, &tmp, &db, n)) || (rc = dev_alloc(ctx, &tmp, &dl, n)) || (rc = dev_alloc(ctx, &tmp, &ds, n)) ||
       (rc = dev_alloc(ctx, &tmp, &de, n)) || (rc = dev_alloc(ctx, &tmp, &dout, n))) return rc;
   cudaStream_t st = ctx->stream;
-  CK(ctx, cudaMemcpyAsync(db, bundle, n * 4, cudaMemcpyHostToDevice, st));
-  CK(ctx, cudaMemcpyAsync(dl, lane, n, cudaMemcpyHostToDevice, st));
-  CK(ctx, cudaMemcpyAsync(ds, start, n * 4, cudaMemcpyHostToDevice, st));
-  CK(ctx, cudaMemcpyAsync(de, end, n * 4, cudaMemcpyHostToDevice, st));
+  StageScope stage_scope(ctx);   // an early return leaves no staged read-back behind
+  CK(ctx, small_h2d(ctx, db, bundle, n * 4, st));
+  CK(ctx, small_h2d(ctx, dl, lane, n, st));
+  CK(ctx, small_h2d(ctx, ds, start, n * 4, st));
+  CK(ctx, small_h2d(ctx, de, end, n * 4, st));
   ctx->launches++;
   CK(ctx, launch_query_cov(d->v, n, db, dl, ds, de, sign, dout, st));
-  CK(ctx, cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaStreamSynchronize(st));
+  CK(ctx, small_d2h(ctx, out, dout, n * 8, st));
+  CK(ctx, small_sync(ctx, st));
   return STG_OK;
 }
 
@@ -770,6 +909,7 @@ int stg_find_trims(stg_ctx* ctx, const stg_dbatch* d, int64_t n, const int32_t* 
   }
   CK(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
+  StageScope stage_scope(ctx);   // an early return leaves no staged read-back behind
   const size_t tot = cap_off[n];
   int32_t* db = nullptr; int8_t* ds = nullptr; uint32_t *da = nullptr, *dz = nullptr, *dc = nullptr, *dn = nullptr, *dp = nullptr;
   float* df = nullptr; uint8_t* dt = nullptr;
@@ -780,11 +920,11 @@ int stg_find_trims(stg_ctx* ctx, const stg_dbatch* d, int64_t n, const int32_t* 
       (rc = dev_alloc(ctx, &tmp, &dz, n)) || (rc = dev_alloc(ctx, &tmp, &dc, n + 1)) || (rc = dev_alloc(ctx, &tmp, &dn, n)) ||
       (rc = dev_alloc(ctx, &tmp, &dp, (int64_t)tot + 1)) || (rc = dev_alloc(ctx, &tmp, &df, (int64_t)tot + 1)) ||
       (rc = dev_alloc(ctx, &tmp, &dt, (int64_t)tot + 1))) return rc;
-  CK(ctx, cudaMemcpyAsync(db, bundle, n * 4, cudaMemcpyHostToDevice, st));
-  CK(ctx, cudaMemcpyAsync(ds, sno, n, cudaMemcpyHostToDevice, st));
-  CK(ctx, cudaMemcpyAsync(da, start, n * 4, cudaMemcpyHostToDevice, st));
-  CK(ctx, cudaMemcpyAsync(dz, end, n * 4, cudaMemcpyHostToDevice, st));
-  CK(ctx, cudaMemcpyAsync(dc, cap_off, (n + 1) * 4, cudaMemcpyHostToDevice, st));
+  CK(ctx, small_h2d(ctx, db, bundle, n * 4, st));
+  CK(ctx, small_h2d(ctx, ds, sno, n, st));
+  CK(ctx, small_h2d(ctx, da, start, n * 4, st));
+  CK(ctx, small_h2d(ctx, dz, end, n * 4, st));
+  CK(ctx, small_h2d(ctx, dc, cap_off, (n + 1) * 4, st));
   CK(ctx, cudaMemsetAsync(dp, 0, (tot + 1) * 4, st));
   CK(ctx, cudaMemsetAsync(df, 0, (tot + 1) * 4, st));
   CK(ctx, cudaMemsetAsync(dt, 0, tot + 1, st));
@@ -793,13 +933,13 @@ int stg_find_trims(stg_ctx* ctx, const stg_dbatch* d, int64_t n, const int32_t* 
     Scope s(ctx, "find_trims", 0);
     CK(ctx, launch_find_trims(d->v, n, db, ds, da, dz, dc, dn, dp, df, dt, st));
   }
-  CK(ctx, cudaMemcpyAsync(count, dn, n * 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, small_d2h(ctx, count, dn, n * 4, st));
   if (tot) {
-    CK(ctx, cudaMemcpyAsync(pos, dp, tot * 4, cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaMemcpyAsync(abundance, df, tot * 4, cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaMemcpyAsync(is_start, dt, tot, cudaMemcpyDeviceToHost, st));
+    CK(ctx, small_d2h(ctx, pos, dp, tot * 4, st));
+    CK(ctx, small_d2h(ctx, abundance, df, tot * 4, st));
+    CK(ctx, small_d2h(ctx, is_start, dt, tot, st));
   }
-  CK(ctx, cudaStreamSynchronize(st));
+  CK(ctx, small_sync(ctx, st));
   return STG_OK;
 }
 
@@ -814,6 +954,7 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
   CK(ctx, cudaSetDevice(ctx->device));
   { static int dbg = -1; if (dbg < 0) { dbg = getenv("STGPU_GROUPS_DEBUG") ? 1 : 0; groups_set_debug(dbg); } }
   cudaStream_t st = ctx->stream;
+  StageScope stage_scope(ctx);   // an early return leaves no staged read-back behind
   DevBatchView& v = d->v;
   GroupsView& g = d->gv;
   memset(&g, 0, sizeof(g));
@@ -831,7 +972,7 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return d->h_nreads[a] > d->h_nreads[b]; });
   uint32_t* d_order = nullptr;
   KEEP(d_order, nb);
-  if (nb) CK(ctx, cudaMemcpyAsync(d_order, order.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, st));
+  if (nb) CK(ctx, small_h2d(ctx, d_order, order.data(), sizeof(uint32_t) * nb, st));
   g.order = d_order;
   // capacities
   uint32_t* rcap = nullptr; unsigned long long* d_total = nullptr; unsigned long long* scan_state = nullptr; uint32_t* ticket = nullptr;
@@ -844,8 +985,8 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
     CK(ctx, launch_scan_exclusive_add(rcap, nr + 1, scan_state, ticket, st)); }
   g.rcap_off = rcap;
   unsigned long long total = 0;
-  CK(ctx, cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaStreamSynchronize(st));   // also: `order` has left the host
+  CK(ctx, small_d2h(ctx, &total, d_total, sizeof(total), st));
+  CK(ctx, small_sync(ctx, st));   // also: `order` has left the host
   if (total + 3ull * (unsigned long long)nr >= 0x7fffffffull)
     return fail(ctx, STG_ERANGE, "stg_build_groups: batch needs more than 2^31 group slots; split it");
   const int64_t R = (int64_t)total;
@@ -854,12 +995,12 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
   TEMP(g.jt_strand, nj); TEMP(g.jt_mm, nj);
   TEMP(g.ap_start, ni); TEMP(g.ap_end, ni); TEMP(g.ap_strand, ni); TEMP(g.ap_mm, ni);
   TEMP(g.jt_perm, nj + ni); TEMP(g.jt_inv, nj + ni);
-  if (nr) CK(ctx, cudaMemcpyAsync(g.strand, v.r_strand, (size_t)nr, cudaMemcpyDeviceToDevice, st));
-  if (ns) CK(ctx, cudaMemcpyAsync(g.seg_start, v.seg_start, sizeof(uint32_t) * ns, cudaMemcpyDeviceToDevice, st));
-  if (ns) CK(ctx, cudaMemcpyAsync(g.seg_end, v.seg_end, sizeof(uint32_t) * ns, cudaMemcpyDeviceToDevice, st));
-  if (np) CK(ctx, cudaMemcpyAsync(g.pair, v.pair_idx, sizeof(int32_t) * np, cudaMemcpyDeviceToDevice, st));
-  if (nj) CK(ctx, cudaMemcpyAsync(g.jt_strand, v.jp_strand, (size_t)nj, cudaMemcpyDeviceToDevice, st));
-  if (nj) CK(ctx, cudaMemcpyAsync(g.jt_mm, v.jp_mm, sizeof(double) * nj, cudaMemcpyDeviceToDevice, st));
+  if (nr) CK(ctx, launch_copy(g.strand, v.r_strand, (size_t)nr, st));
+  if (ns) CK(ctx, launch_copy(g.seg_start, v.seg_start, sizeof(uint32_t) * ns, st));
+  if (ns) CK(ctx, launch_copy(g.seg_end, v.seg_end, sizeof(uint32_t) * ns, st));
+  if (np) CK(ctx, launch_copy(g.pair, v.pair_idx, sizeof(int32_t) * np, st));
+  if (nj) CK(ctx, launch_copy(g.jt_strand, v.jp_strand, (size_t)nj, st));
+  if (nj) CK(ctx, launch_copy(g.jt_mm, v.jp_mm, sizeof(double) * nj, st));
   // sparse groups / colours / readgroup
   TEMP(g.g_start, R); TEMP(g.g_end, R); TEMP(g.g_color, R); TEMP(g.g_next, R); TEMP(g.g_merge, R); TEMP(g.g_grid, R);
   TEMP(g.g_cov, R); TEMP(g.g_multi, R); TEMP(g.g_alive, R); TEMP(g.eqcol, R + 3 * nr); TEMP(g.rg, R);
@@ -883,7 +1024,7 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
   int64_t n_deep = 0;   // `order` is sorted by decreasing read count
   while (n_deep < nb && (int64_t)d->h_nreads[order[n_deep]] >= groups_deep_reads()) n_deep++;
   int64_t n_cluster = 0;   // the oversized bundles are walked by a cluster of CTAs each; their ordered sums go through a log
-  static int64_t cluster_reads = getenv("STGPU_CLUSTER_READS") ? atoll(getenv("STGPU_CLUSTER_READS")) : groups_cluster_reads();   // (tuning aid)
+  const int64_t cluster_reads = ctx->cluster_reads;
   while (n_cluster < n_deep && (int64_t)d->h_nreads[order[n_cluster]] >= cluster_reads) n_cluster++;
   {
     std::vector<uint32_t> voff((size_t)n_cluster + 1, 0);
@@ -891,8 +1032,8 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
     const int64_t vr = voff[n_cluster];
     uint32_t* d_voff = nullptr;
     TEMP(d_voff, n_cluster + 1);
-    CK(ctx, cudaMemcpyAsync(d_voff, voff.data(), sizeof(uint32_t) * (n_cluster + 1), cudaMemcpyHostToDevice, st));
-    CK(ctx, cudaStreamSynchronize(st));   // voff leaves the host
+    CK(ctx, small_h2d(ctx, d_voff, voff.data(), sizeof(uint32_t) * (n_cluster + 1), st));
+    CK(ctx, small_sync(ctx, st));   // voff leaves the host
     g.vlog_off = d_voff;
     TEMP(g.vlog_grp, 6 * vr); TEMP(g.vlog_val, 6 * vr); TEMP(g.vlog_sorted, 6 * vr); TEMP(g.vlog_fl, vr); TEMP(g.vlog_nf, vr);
     uint8_t *ctl_raw = nullptr, *rec_raw = nullptr;
@@ -910,12 +1051,12 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
     CK(ctx, launch_scan_exclusive_add(g.b_napp, nb + 1, scan_state, ticket, st));
     CK(ctx, launch_scan_exclusive_add(g.rg_off, nr + 1, scan_state, ticket, st)); }
   uint32_t tot[4] = {0, 0, 0, 0}, err = 0;
-  CK(ctx, cudaMemcpyAsync(&tot[0], g.b_ng + nb, 4, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaMemcpyAsync(&tot[1], g.b_ncol + nb, 4, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaMemcpyAsync(&tot[2], g.b_napp + nb, 4, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaMemcpyAsync(&tot[3], g.rg_off + nr, 4, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaMemcpyAsync(&err, v.err_flag, 4, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaStreamSynchronize(st));
+  CK(ctx, small_d2h(ctx, &tot[0], g.b_ng + nb, 4, st));
+  CK(ctx, small_d2h(ctx, &tot[1], g.b_ncol + nb, 4, st));
+  CK(ctx, small_d2h(ctx, &tot[2], g.b_napp + nb, 4, st));
+  CK(ctx, small_d2h(ctx, &tot[3], g.rg_off + nr, 4, st));
+  CK(ctx, small_d2h(ctx, &err, v.err_flag, 4, st));
+  CK(ctx, small_sync(ctx, st));
   if (err) return fail(ctx, STG_ERANGE, "stg_build_groups: a bundle exceeded the capacity bound of its group arrays");
   g.n_groups = tot[0]; g.n_colors = tot[1]; g.n_app = tot[2]; g.n_rg = tot[3];
   const int64_t NG = g.n_groups, NC = g.n_colors, NJ = nj + g.n_app;
@@ -945,6 +1086,7 @@ int stg_neutral_predictions(stg_ctx* ctx, stg_dbatch* d) {
     return fail(ctx, STG_EUNSUPPORTED, "stg_neutral_predictions: only the short-read de novo path is implemented");
   CK(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
+  StageScope stage_scope(ctx);   // an early return leaves no staged read-back behind
   DevBatchView& v = d->v;
   GroupsView& g = d->gv;
   NeutralView& n = d->nv;
@@ -964,8 +1106,8 @@ int stg_neutral_predictions(stg_ctx* ctx, stg_dbatch* d) {
     CK(ctx, launch_neutral_count(v, g, n.reg_off, st));
     CK(ctx, launch_scan_exclusive_add(n.reg_off, nb + 1, scan_state, ticket, st));
     uint32_t nreg = 0;
-    CK(ctx, cudaMemcpyAsync(&nreg, n.reg_off + nb, 4, cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaStreamSynchronize(st));
+    CK(ctx, small_d2h(ctx, &nreg, n.reg_off + nb, 4, st));
+    CK(ctx, small_sync(ctx, st));
     n.n_regions = nreg;
     TEMP(n.reg_cnt, nb); TEMP(n.reg_bundle, nreg); TEMP(n.reg_sno, nreg); TEMP(n.reg_start, nreg); TEMP(n.reg_end, nreg);
     TEMP(n.reg_first, nreg); TEMP(n.cap_off, (int64_t)nreg + 1 + 16); TEMP(n.trim_cnt, nreg);
@@ -975,8 +1117,8 @@ int stg_neutral_predictions(stg_ctx* ctx, stg_dbatch* d) {
     TEMP(scan_state2, (int64_t)nreg / 4096 + 4);
     CK(ctx, launch_scan_exclusive_add(n.cap_off, (int64_t)nreg + 1, scan_state2, ticket, st)); }
   uint32_t tcap = 0;
-  CK(ctx, cudaMemcpyAsync(&tcap, n.cap_off + n.n_regions, 4, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaStreamSynchronize(st));
+  CK(ctx, small_d2h(ctx, &tcap, n.cap_off + n.n_regions, 4, st));
+  CK(ctx, small_sync(ctx, st));
   TEMP(n.trim_pos, (int64_t)tcap + 1); TEMP(n.trim_ab, (int64_t)tcap + 1); TEMP(n.trim_st, (int64_t)tcap + 1);
   CK(ctx, cudaMemsetAsync(n.trim_cnt, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(n.n_regions, 1), st));
   CK(ctx, cudaMemsetAsync(n.trim_pos, 0, sizeof(uint32_t) * ((size_t)tcap + 1), st));
@@ -994,8 +1136,8 @@ int stg_neutral_predictions(stg_ctx* ctx, stg_dbatch* d) {
     CK(ctx, launch_neutral_preds(v, g, n, st));
     CK(ctx, launch_scan_exclusive_add(n.pred_off, nb + 1, scan_state, ticket, st));
     uint32_t np = 0;
-    CK(ctx, cudaMemcpyAsync(&np, n.pred_off + nb, 4, cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaStreamSynchronize(st));
+    CK(ctx, small_d2h(ctx, &np, n.pred_off + nb, 4, st));
+    CK(ctx, small_sync(ctx, st));
     n.n_preds = np;
     KEEP(n.o_start, np); KEEP(n.o_end, np); KEEP(n.o_cov, np); KEEP(n.o_tlen, np); KEEP(n.o_geneno, np);
     CK(ctx, launch_neutral_compact(v, n, st)); }
@@ -1136,6 +1278,7 @@ int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
     return fail(ctx, STG_EUNSUPPORTED, "stg_assemble: only the short-read de novo path is implemented");
   CK(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
+  StageScope stage_scope(ctx);   // an early return leaves no staged read-back behind
   DevBatchView& v = d->v;
   GroupsView& g = d->gv;
   AsmView& A = d->av;
@@ -1152,15 +1295,15 @@ int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
 #define ZERO(ptr, count) CK(ctx, cudaMemsetAsync((ptr), 0, sizeof(*(ptr)) * (size_t)std::max<int64_t>((count), 1), st))
 #define ONES(ptr, count) CK(ctx, cudaMemsetAsync((ptr), 0xff, sizeof(*(ptr)) * (size_t)std::max<int64_t>((count), 1), st))
 #define SCAN(ptr, n1) CK(ctx, launch_scan_exclusive_add((ptr), (n1), scan_state, ticket, st))
-#define TOTAL(dst, ptr, n) CK(ctx, cudaMemcpyAsync(&(dst), (ptr) + (n), 4, cudaMemcpyDeviceToHost, st))
+#define TOTAL(dst, ptr, n) CK(ctx, small_d2h(ctx, &(dst), (ptr) + (n), 4, st))
   // graph ids and the rows of the junction table, from the per-bundle counts of rows a8 + a9
   std::vector<uint32_t> h_nbun((size_t)3 * nb + 1), h_napp((size_t)nb + 1), h_joff((size_t)nb + 1);
   if (nb) {
-    CK(ctx, cudaMemcpyAsync(h_nbun.data(), g.b_nbun, sizeof(uint32_t) * 3 * nb, cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaMemcpyAsync(h_joff.data(), v.b_junc_off, sizeof(uint32_t) * (nb + 1), cudaMemcpyDeviceToHost, st));
+    CK(ctx, small_d2h(ctx, h_nbun.data(), g.b_nbun, sizeof(uint32_t) * 3 * nb, st));
+    CK(ctx, small_d2h(ctx, h_joff.data(), v.b_junc_off, sizeof(uint32_t) * (nb + 1), st));
   }
-  CK(ctx, cudaMemcpyAsync(h_napp.data(), g.b_napp, sizeof(uint32_t) * (nb + 1), cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaStreamSynchronize(st));
+  CK(ctx, small_d2h(ctx, h_napp.data(), g.b_napp, sizeof(uint32_t) * (nb + 1), st));
+  CK(ctx, small_sync(ctx, st));
   std::vector<uint32_t> h_first((size_t)2 * nb + 1), h_jrow((size_t)nb + 1);
   uint32_t G = 0;
   for (int64_t b = 0; b < nb; b++) {
@@ -1174,8 +1317,8 @@ int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
   const int64_t NJ = A.n_junc_rows;
   uint32_t *d_first = nullptr, *d_jrow = nullptr;
   KEEP(d_first, 2 * nb + 1); KEEP(d_jrow, nb + 1);
-  CK(ctx, cudaMemcpyAsync(d_first, h_first.data(), sizeof(uint32_t) * (2 * nb + 1), cudaMemcpyHostToDevice, st));
-  CK(ctx, cudaMemcpyAsync(d_jrow, h_jrow.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
+  CK(ctx, small_h2d(ctx, d_first, h_first.data(), sizeof(uint32_t) * (2 * nb + 1), st));
+  CK(ctx, small_h2d(ctx, d_jrow, h_jrow.data(), sizeof(uint32_t) * (nb + 1), st));
   A.gr_first = d_first; A.jrow_off = d_jrow;
   unsigned long long* scan_state = nullptr; uint32_t* ticket = nullptr;
   TEMP(ticket, 1);
@@ -1195,7 +1338,7 @@ int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
     CK(ctx, launch_asm_bounds(v, g, A, P, st));
     SCAN(A.cap_n, (int64_t)G + 1); SCAN(A.cap_e, (int64_t)G + 1); SCAN(A.cap_f, (int64_t)G + 1); SCAN(A.cap_t, (int64_t)G + 1); }
   TOTAL(tn, A.cap_n, G); TOTAL(te, A.cap_e, G); TOTAL(tf, A.cap_f, G); TOTAL(tt, A.cap_t, G);
-  CK(ctx, cudaStreamSynchronize(st));
+  CK(ctx, small_sync(ctx, st));
   TEMP(A.t_nstart, tn); TEMP(A.t_nend, tn); TEMP(A.t_evu, te); TEMP(A.t_evv, te); TEMP(A.t_ft1, tf); TEMP(A.t_ft2, tf); TEMP(A.t_ftab, tf);
   TEMP(A.t_trpos, tt); TEMP(A.t_trab, tt); TEMP(A.t_trst, tt);
   KEEP(A.x_node, (int64_t)G + 1 + 16); KEEP(A.x_edge, (int64_t)G + 1 + 16); TEMP(A.x_tf0, (int64_t)G + 1 + 16); KEEP(A.x_reach, (int64_t)G + 1 + 16);
@@ -1205,8 +1348,8 @@ int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
     SCAN(A.x_node, (int64_t)G + 1); SCAN(A.x_edge, (int64_t)G + 1); SCAN(A.x_tf0, (int64_t)G + 1); SCAN(A.x_reach, (int64_t)G + 1); }
   uint32_t xn = 0, xe = 0, xt = 0, xr = 0;
   TOTAL(xn, A.x_node, G); TOTAL(xe, A.x_edge, G); TOTAL(xt, A.x_tf0, G); TOTAL(xr, A.x_reach, G);
-  CK(ctx, cudaMemcpyAsync(&err, v.err_flag, 4, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaStreamSynchronize(st));
+  CK(ctx, small_d2h(ctx, &err, v.err_flag, 4, st));
+  CK(ctx, small_sync(ctx, st));
   if (err) return fail(ctx, STG_ERANGE, "stg_assemble: a graph exceeded the capacity bound of its sweep");
   A.n_nodes = xn; A.n_edges = xe; A.n_tf0cap = xt; A.n_reach = xr;
   const int64_t NN = (int64_t)xn + 2 * (int64_t)G + 2;   // per-node scratch: gno + 2 entries per graph
@@ -1223,8 +1366,8 @@ int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
     SCAN(A.r_ncov, nr + 1); SCAN(A.r_ntf, nr + 1); SCAN(A.r_nkey, nr + 1); }
   uint32_t t0 = 0, tc = 0, tr = 0, tk = 0;
   TOTAL(t0, A.tf0_off, G); TOTAL(tc, A.r_ncov, nr); TOTAL(tr, A.r_ntf, nr); TOTAL(tk, A.r_nkey, nr);
-  CK(ctx, cudaMemcpyAsync(&err, v.err_flag, 4, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaStreamSynchronize(st));
+  CK(ctx, small_d2h(ctx, &err, v.err_flag, 4, st));
+  CK(ctx, small_sync(ctx, st));
   if (err & 0x800u) return fail(ctx, STG_EUNSUPPORTED, "stg_assemble: the batch carries unitigs (super-reads), which are not supported");
   if (err & 0x400u) return fail(ctx, STG_ERANGE, "stg_assemble: a graph has more than allowed_nodes nodes (prune_graph_nodes is not built)");
   if (err) return fail(ctx, STG_ERANGE, "stg_assemble: a read spans more graph nodes than the kernels allow");
@@ -1241,7 +1384,7 @@ int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
     SCAN(A.tab_off, nb + 1); }
   uint32_t ts = 0;
   TOTAL(ts, A.tab_off, nb);
-  CK(ctx, cudaStreamSynchronize(st));
+  CK(ctx, small_sync(ctx, st));
   TEMP(A.slot_hash, ts); TEMP(A.slot_minrec, ts); TEMP(A.slot_tf0, ts);
   ZERO(A.slot_hash, ts); ONES(A.slot_minrec, ts); ONES(A.slot_tf0, ts);
   TEMP(A.tf_rep, NR); TEMP(A.tf_abund, NR); TEMP(A.tf_graph, NR); TEMP(A.b_ntf, nb); TEMP(A.b_deep, nb);
@@ -1268,7 +1411,7 @@ int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
     SCAN(A.y_tf, (int64_t)G + 1); SCAN(A.y_pat, (int64_t)G + 1); SCAN(A.y_path, (int64_t)G + 1); SCAN(A.y_ntrf, (int64_t)G + 1); SCAN(A.y_istr, (int64_t)G + 1); }
   uint32_t yt = 0, yp = 0, yh = 0, yn = 0, yi = 0;
   TOTAL(yt, A.y_tf, G); TOTAL(yp, A.y_pat, G); TOTAL(yh, A.y_path, G); TOTAL(yn, A.y_ntrf, G); TOTAL(yi, A.y_istr, G);
-  CK(ctx, cudaStreamSynchronize(st));
+  CK(ctx, small_sync(ctx, st));
   A.n_ytf = yt; A.n_ypat = yp; A.n_ypath = yh; A.n_yntrf = yn; A.n_yistr = yi;
   TEMP(A.f_koff, yt); TEMP(A.f_klen, yt); TEMP(A.f_wkoff, yt); TEMP(A.f_wklen, yt); TEMP(A.f_ab, yt); TEMP(A.f_wab, yt); TEMP(A.f_real, yt);
   TEMP(A.f_usepath, yt); TEMP(A.f_path_off, yt); TEMP(A.f_path_cnt, yt); TEMP(A.f_order, yt); TEMP(A.f_pat, yp); TEMP(A.f_skey, yt);
@@ -1286,9 +1429,9 @@ int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
   { Scope s(ctx, "asm_gather", 1); CK(ctx, launch_asm_gather(v, A, st)); }
   { Scope s(ctx, "asm_flow", 1); CK(ctx, launch_asm_flow(v, A, P, st)); }
   uint32_t ctr[2] = {0, 0};
-  CK(ctx, cudaMemcpyAsync(ctr, A.p_counters, 8, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaMemcpyAsync(&err, v.err_flag, 4, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaStreamSynchronize(st));
+  CK(ctx, small_d2h(ctx, ctr, A.p_counters, 8, st));
+  CK(ctx, small_d2h(ctx, &err, v.err_flag, 4, st));
+  CK(ctx, small_sync(ctx, st));
   if (err & 0x1000u) return fail(ctx, STG_ERANGE, "stg_assemble: two transfrag keys of one bundle share a 64-bit hash");
   if (err) return fail(ctx, STG_ERANGE, "stg_assemble: a capacity bound of the flow stage was exceeded");
   A.n_pred = ctr[0]; A.n_exon = ctr[1];
@@ -1303,7 +1446,7 @@ int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
     CK(ctx, launch_asm_pred_scatter(A, (uint32_t)NP, st));
     CK(ctx, launch_scan_exclusive_add(A.o_exon_off, NP + 1, scan_state2, ticket, st));
     CK(ctx, launch_asm_exon_scatter(A, (uint32_t)NP, st)); }
-  CK(ctx, cudaStreamSynchronize(st));
+  CK(ctx, small_sync(ctx, st));
 #undef KEEP
 #undef TEMP
 #undef ZERO

@@ -22,6 +22,7 @@ EXPORTS = [
     "stg_params_default", "stg_init", "stg_shutdown", "stg_last_error", "stg_abi_version", "stg_builder_create",
     "stg_builder_add", "stg_builder_packed", "stg_builder_reset", "stg_builder_destroy", "stg_upload", "stg_run",
     "stg_sync", "stg_free_batch", "stg_trim", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
+    "stg_upload_wait", "stg_fetch_bpcov_all_begin", "stg_fetch_wait",
     "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_trims_capacity", "stg_find_trims", "stg_infer_transcripts",
     "stg_build_groups", "stg_groups_array_info", "stg_fetch_groups_array", "stg_neutral_predictions",
     "stg_assemble", "stg_asm_array_info", "stg_fetch_asm_array", "stg_rewind", "stg_reduce_totals",
@@ -92,6 +93,9 @@ def load_library() -> C.CDLL:
     L.stg_cov_layout.argtypes = [vp, c_i64p, c_i64p, c_i64p]
     L.stg_fetch_bpcov.argtypes = [vp, vp, C.c_int64, c_f32p]
     L.stg_fetch_bpcov_all.argtypes = [vp, vp, c_f32p]
+    L.stg_fetch_bpcov_all_begin.argtypes = [vp, vp, c_f32p]
+    L.stg_fetch_wait.argtypes = [vp, vp]
+    L.stg_upload_wait.argtypes = [vp, vp]
     L.stg_device_bpcov.argtypes = [vp]
     L.stg_device_bpcov.restype = vp
     L.stg_fetch_junction_support.argtypes = [vp, vp, c_f64p, c_f64p, c_f64p]
@@ -333,6 +337,16 @@ class Engine:
     def fetch_bpcov_all_into(self, batch: DeviceBatch, host_ptr: int) -> None:
         """bpcov of every bundle into caller memory (pinned memory makes it one DMA)."""
         self._ck(self.L.stg_fetch_bpcov_all(self.ctx, batch.handle, C.cast(C.c_void_p(host_ptr), c_f32p)))
+
+    def fetch_bpcov_all_begin(self, batch: DeviceBatch, host_ptr: int) -> None:
+        """Start the same copy on the copy-out stream (overlaps the group / assembly stages); fetch_wait completes it."""
+        self._ck(self.L.stg_fetch_bpcov_all_begin(self.ctx, batch.handle, C.cast(C.c_void_p(host_ptr), c_f32p)))
+
+    def fetch_wait(self, batch: DeviceBatch) -> None:
+        self._ck(self.L.stg_fetch_wait(self.ctx, batch.handle))
+
+    def upload_wait(self, batch: DeviceBatch) -> None:
+        self._ck(self.L.stg_upload_wait(self.ctx, batch.handle))
 
     def fetch_cov_totals(self, batch: DeviceBatch) -> np.ndarray:
         out = np.empty(batch.n_bundles * 3, dtype=np.float64)

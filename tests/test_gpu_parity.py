@@ -319,6 +319,45 @@ def test_groups_vs_oracle(engine, kind, seed):
     a9_util.assert_same(_gpu_groups(engine, a), orc.groups(a, cov, off, good, left, right))
 
 
+@pytest.fixture(scope="module")
+def cluster_engine():
+    """A context whose oversized-bundle threshold (row x1) is lowered, so that ordinary test bundles are walked by the
+    thread-block-cluster kernel: its window, its grow-inside-the-run dependencies, its logged ordered sums."""
+    import os
+    from stringtie_b200.engine import Engine
+    old = os.environ.get("STGPU_CLUSTER_READS")
+    os.environ["STGPU_CLUSTER_READS"] = "500"
+    try:
+        e = Engine(0)
+    finally:
+        if old is None:
+            del os.environ["STGPU_CLUSTER_READS"]
+        else:
+            os.environ["STGPU_CLUSTER_READS"] = old
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("kind,seed", [("synth", 3), ("deep", 4), ("deep", 9), ("adv", 1), ("adv", 2), ("adv", 5), ("sparse", 21)])
+def test_groups_cluster_kernel_vs_oracle(cluster_engine, kind, seed):
+    from tests import a9_util
+    a = (synth.make_batch(n_bundles=30, reads_per_bundle=3000, seed=seed) if kind == "synth" else
+         synth.make_batch(n_bundles=8, reads_per_bundle=30000, seed=seed) if kind == "deep" else
+         synth.make_sparse(n_reads=40000, seed=seed, n_bundles=2) if kind == "sparse" else
+         synth.make_adversarial(seed=seed, n_bundles=14, max_reads=3000))
+    cov, off, good, left, right = orc.run(a)
+    a9_util.assert_same(_gpu_groups(cluster_engine, a), orc.groups(a, cov, off, good, left, right))
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_groups_cluster_kernel_golden(cluster_engine, name):
+    from tests import a9_util
+    from stringtie_b200.stgb import input_view
+    g = load_golden(name)
+    a = input_view(g)
+    a9_util.assert_same(_gpu_groups(cluster_engine, a), a9_util.split_reference_dump(g, a))
+
+
 @pytest.mark.parametrize("seed", [38, 43])
 def test_groups_appended_junctions(engine, seed):
     """Seeds on which the repair appends junction rows and the table is re-sorted with the reference's quicksort (the

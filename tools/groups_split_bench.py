@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""Where does the group stage's time go: the deepest bundle alone, the very deep class, the deep class, the shallow mass."""
+"""Where does the group stage's time go: single deep bundles alone, the classes of launch_groups_walk, the whole batch;
+optionally for several cluster thresholds (STGPU_CLUSTER_READS is read when a context is created).
+usage: groups_split_bench.py [threshold ...]"""
 import sys, os, json, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,18 +12,23 @@ from stringtie_b200.engine import Engine
 base, a = bench.build_workload(bench.PARTS, bench.PART_BUNDLES, 0)
 nr = np.diff(a["b_read_off"].astype(np.int64))
 order = np.argsort(-nr)
-eng = Engine(0)
-eng.set_profiling(True)
-def run(name, idx):
-    sub = shard.take_bundles(a, np.sort(idx))
+print(json.dumps({"top_reads": nr[order[:40]].tolist(), "ge_100k": int((nr >= 100000).sum()), "ge_200k": int((nr >= 200000).sum()),
+                  "ge_50k": int((nr >= 50000).sum()), "ge_16k": int((nr >= 16384).sum())}))
+def run(eng, name, idx, tag):
+    sub = shard.take_bundles(a, np.sort(idx)) if idx is not None else a
     for rep in range(2):
         b = eng.upload(sub); eng.run(b); eng.build_groups(b); eng.sync()
-        k = {n: ms for n, ms in eng.kernel_times() if n.startswith("groups")}
+        k = {n: round(ms, 2) for n, ms in eng.kernel_times() if n.startswith("groups")}
         b.free()
-    print(json.dumps({"case": name, "bundles": int(idx.size), "reads": int(nr[idx].sum()), "kernel_ms": k}))
-run("deepest", order[:1])
-run("second", order[1:2])
-run("top63", order[:63])
-run("deep_64_to_935", order[63:935])
-run("shallow", order[935:])
-run("all_but_deepest", order[1:])
+    print(json.dumps({"threshold": tag, "case": name, "bundles": int(nr.size if idx is None else idx.size), "kernel_ms": k}), flush=True)
+ths = [int(x) for x in sys.argv[1:]] or [0]
+for th in ths:
+    if th:
+        os.environ["STGPU_CLUSTER_READS"] = str(th)
+    eng = Engine(0)
+    eng.set_profiling(True)
+    if th == ths[0]:
+        for i in range(6):
+            run(eng, f"bundle_rank{i}_reads{int(nr[order[i]])}", order[i:i + 1], th)
+    run(eng, "all", None, th)
+    eng.close()
