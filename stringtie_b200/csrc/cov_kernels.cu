@@ -1135,8 +1135,21 @@ __global__ void __launch_bounds__(STG_TILE_WARPS * 32, 1) cov_tile_kernel(DevBat
 // K10: event-free sub-tiles.  Runs after cov_tile_kernel, so every carry it needs is final: no waiting, no shared
 // memory, full occupancy — a streaming fill.  One warp per sub-tile.
 // --------------------------------------------------------------------------------------------------------------
+// one lane: [dst, dst + bytes) <- shared memory, as one asynchronous bulk copy (bytes and both addresses multiples of 16)
+__device__ __forceinline__ void bulk_store(float* dst, const float* src_smem, uint32_t bytes) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(src_smem);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sa), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(256) cov_fill_kernel(DevBatchView v) {
   const int lane = threadIdx.x & 31;
+  __shared__ __align__(128) float zero_row[TW];
+  __shared__ __align__(128) float warp_rows[8][TW];
+  float* warp_row = warp_rows[threadIdx.x >> 5];
+  for (int q = threadIdx.x; q < TW; q += blockDim.x) zero_row[q] = 0.f;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
   const uint32_t n_main = __ldg(v.round_off + v.n_rounds);
   const uint32_t n_tiles = (uint32_t)v.n_tiles;
   const uint32_t warps = gridDim.x * (blockDim.x >> 5);
@@ -1178,20 +1191,30 @@ __global__ void __launch_bounds__(256) cov_fill_kernel(DevBatchView v) {
     }
     const bool flat = lane >= 3 || (to_reset < npos ? c == 0.f : __fadd_rn(bs, c) == bs);
     if (__all_sync(FULL, flat)) {
-      // every position repeats bs (0 from a block start on)
+      // every position repeats bs (0 from a block start on): each strand lane of the sub-tile leaves as ONE bulk copy
+      // shared -> global (cp.async.bulk, issued by one lane) instead of 32-lane store loops.  Rows that are all zero —
+      // most of them: the gaps between loci — come straight from the CTA's zero row; other rows are laid out in the warp's
+      // own row first (the async proxy must have read it before it is written again: wait_group.read).
       const float b0 = __shfl_sync(FULL, bs, 0), b1 = __shfl_sync(FULL, bs, 1), b2 = __shfl_sync(FULL, bs, 2);
+      const uint32_t lim = to_reset < npos ? to_reset : npos;          // positions [0, lim) hold bs, the rest 0
 #pragma unroll
       for (int s = 0; s < 3; s++) {
         const float bv = s == 0 ? b0 : (s == 1 ? b1 : b2);
-        float4* dst = reinterpret_cast<float4*>(out + (size_t)s * stride);
-        for (uint32_t q = lane; q < n4; q += 32) {
-          const uint32_t p = q * 4;
-          float4 x;
-          x.x = (p + 0 < to_reset && p + 0 < npos) ? bv : 0.f;
-          x.y = (p + 1 < to_reset && p + 1 < npos) ? bv : 0.f;
-          x.z = (p + 2 < to_reset && p + 2 < npos) ? bv : 0.f;
-          x.w = (p + 3 < to_reset && p + 3 < npos) ? bv : 0.f;
-          __stcs(dst + q, x);
+        float* dst = out + (size_t)s * stride;
+        if (bv == 0.f || lim == 0u) {
+          if (lane == 0) bulk_store(dst, zero_row, n4 * 16u);
+        } else {
+          float4* row4 = reinterpret_cast<float4*>(warp_row);
+          for (uint32_t q = lane; q < n4; q += 32) {
+            const uint32_t p = q * 4;
+            float4 x;
+            x.x = p + 0 < lim ? bv : 0.f; x.y = p + 1 < lim ? bv : 0.f; x.z = p + 2 < lim ? bv : 0.f; x.w = p + 3 < lim ? bv : 0.f;
+            row4[q] = x;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) { bulk_store(dst, warp_row, n4 * 16u); asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+          __syncwarp();
         }
       }
     } else {
@@ -1212,6 +1235,7 @@ __global__ void __launch_bounds__(256) cov_fill_kernel(DevBatchView v) {
       }
     }
   }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 cudaError_t launch_cov_tiles(const DevBatchView& v, int num_sms, cudaStream_t st) {
