@@ -347,9 +347,32 @@ __global__ void __launch_bounds__(128) asm_tf_gather_kernel(DevBatchView v, AsmV
 }
 
 // ---- a12–a15 ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) asm_flow_kernel(DevBatchView v, AsmView A, AsmParams P) {
-  const int64_t gi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (gi >= A.n_graphs) return;
+// The graphs of a batch differ in size by four orders of magnitude (a handful of transfrags to tens of thousands), and one
+// warp works on one graph: handed out in bundle order, the large graphs of the last bundles would run alone at the end.
+// So the graphs are first binned by a quasi-logarithmic size key (heaviest bin first: the classic longest-processing-time
+// order; the order inside a bin does not matter) and persistent warps pull them from that list through a ticket counter.
+#define FLOW_BINS 256
+__device__ __forceinline__ uint32_t flow_bin(uint32_t work) {   // 8 sub-bins per power of two, heaviest first
+  if (work < 8u) return FLOW_BINS - 1u - work;
+  const int e = 31 - __clz(work);
+  const uint32_t b = (uint32_t)(e - 2) * 8u + ((work >> (e - 3)) & 7u);
+  return b >= FLOW_BINS ? 0u : FLOW_BINS - 1u - b;
+}
+__device__ __forceinline__ uint32_t flow_work(const AsmView& A, int64_t gi) { return A.g_nt[gi] * 4u + (uint32_t)A.graphs[gi].gno; }
+
+__global__ void __launch_bounds__(256) asm_flow_bin_kernel(AsmView A, uint32_t* __restrict__ bins) {
+  const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi < A.n_graphs) atomicAdd(&bins[flow_bin(flow_work(A, gi))], 1u);
+}
+__global__ void __launch_bounds__(32) asm_flow_bin_scan_kernel(uint32_t* __restrict__ bins) {
+  if (threadIdx.x == 0) { uint32_t run = 0; for (int b = 0; b < FLOW_BINS; b++) { const uint32_t c = bins[b]; bins[b] = run; run += c; } }
+}
+__global__ void __launch_bounds__(256) asm_flow_order_kernel(AsmView A, uint32_t* __restrict__ bins, uint32_t* __restrict__ order) {
+  const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi < A.n_graphs) order[atomicAdd(&bins[flow_bin(flow_work(A, gi))], 1u)] = (uint32_t)gi;
+}
+
+__device__ void asm_flow_graph(const DevBatchView& v, const AsmView& A, const AsmParams& P, const int64_t gi) {
   const int lane = threadIdx.x & 31;
   const Graph gr = A.graphs[gi];
   if (!gr.gno) { if (lane == 0) A.g_npred[gi] = 0; return; }
@@ -382,6 +405,19 @@ __global__ void __launch_bounds__(128) asm_flow_kernel(DevBatchView v, AsmView A
   if (!err) ns = find_transcripts_warp(gr, f, S, P, out, (int)gi, A.s_exs + nb, A.s_exe + nb, A.s_exc + nb, &err);
   if (lane == 0) { A.g_npred[gi] = (uint32_t)ns; if (err) atomicOr(v.err_flag, err); }
   if (gi == 0 && lane == 0) A.g_npred[A.n_graphs] = 0;
+}
+
+__global__ void __launch_bounds__(128) asm_flow_kernel(DevBatchView v, AsmView A, AsmParams P, const uint32_t* __restrict__ order,
+                                                        uint32_t* __restrict__ ticket) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(ticket, 1u);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= (uint32_t)A.n_graphs) return;
+    asm_flow_graph(v, A, P, (int64_t)order[i]);
+    __syncwarp();
+  }
 }
 
 // gene numbers: the counter runs on from the neutral bundles' (rlink.cpp:15491) and takes one step per graph that
@@ -489,10 +525,21 @@ cudaError_t launch_asm_gather(const DevBatchView& v, const AsmView& A, cudaStrea
   if (v.n_bundles) asm_tf_gather_kernel<<<blocks(v.n_bundles * 32, 128), 128, 0, st>>>(v, A);
   return cudaGetLastError();
 }
-cudaError_t launch_asm_flow(const DevBatchView& v, const AsmView& A, const AsmParams& P, cudaStream_t st) {
-  if (A.n_graphs) asm_flow_kernel<<<blocks(A.n_graphs * 32, 128), 128, 0, st>>>(v, A, P);
+// scratch: FLOW_BINS + 1 words (zeroed here) and one word per graph
+cudaError_t launch_asm_flow(const DevBatchView& v, const AsmView& A, const AsmParams& P, uint32_t* bins, uint32_t* order, int num_sms,
+                            cudaStream_t st) {
+  if (!A.n_graphs) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(bins, 0, sizeof(uint32_t) * (FLOW_BINS + 1), st);
+  if (e != cudaSuccess) return e;
+  asm_flow_bin_kernel<<<blocks(A.n_graphs, 256), 256, 0, st>>>(A, bins);
+  asm_flow_bin_scan_kernel<<<1, 32, 0, st>>>(bins);
+  asm_flow_order_kernel<<<blocks(A.n_graphs, 256), 256, 0, st>>>(A, bins, order);
+  if ((e = cudaMemsetAsync(bins + FLOW_BINS, 0, sizeof(uint32_t), st)) != cudaSuccess) return e;
+  const int64_t want = blocks(A.n_graphs * 32, 128), resident = (int64_t)num_sms * 5;   // 96 registers: 5 CTAs of 4 warps per SM
+  asm_flow_kernel<<<(unsigned)(want < resident ? want : resident), 128, 0, st>>>(v, A, P, order, bins + FLOW_BINS);
   return cudaGetLastError();
 }
+size_t asm_flow_bins_words() { return FLOW_BINS + 1; }
 cudaError_t launch_asm_geneno(const DevBatchView& v, const AsmView& A, const int32_t* b_geneno, cudaStream_t st) {
   asm_geneno_kernel<<<blocks(v.n_bundles + 1, 256), 256, 0, st>>>(v, A, b_geneno);
   return cudaGetLastError();

@@ -10,6 +10,7 @@
 #pragma once
 #include <stdint.h>
 #define OS_BATCH 8
+#define OS_CHAIN 8    // groups of 32 values a chain warp keeps in flight
 
 // acc[k] = (...((acc[k] + v_i1) + v_i2) + ...) over the records i1 < i2 < ... of key k, i.e. the reference's "+=" loop
 // over the records in order, for all keys at once.  One CTA; scratch: cnt [W * K] (zeroed), kbase [K + 1], sorted [n].
@@ -82,21 +83,35 @@ __device__ void cta_ordered_keyed_sum(uint32_t n, KeyFn key, ValFn val, uint32_t
     }
   }
   __syncthreads();
-  // 4. one warp per key: its run added in order (every lane carries the same sum; values come 32 at a time)
+  // 4. one warp per key: its run added in order (every lane carries the same sum).  The values come OS_CHAIN groups of 32
+  //    at a time and the next block is loaded while this one is added: a group costs the chain ~130 cycles, a load from
+  //    L2 / HBM several hundred
   for (uint32_t k = w; k < K; k += W) {
     const uint32_t a = kbase[k], z = kbase[k + 1];
     if (a == z) continue;
     float s = acc[k];
-    float xnext = a + lane < z ? sorted[a + lane] : 0.f;
-    for (uint32_t j0 = a; j0 < z; j0 += 32) {
-      const float x = xnext;
-      xnext = j0 + 32 + lane < z ? sorted[j0 + 32 + lane] : 0.f;   // the next 32 values are on their way while these are added
-      const int m = (int)min(32u, z - j0);
-      if (m == 32) {
+    float xn[OS_CHAIN];
 #pragma unroll
-        for (int l = 0; l < 32; l++) s = __fadd_rn(s, __shfl_sync(0xffffffffu, x, l));
-      } else {
-        for (int l = 0; l < m; l++) s = __fadd_rn(s, __shfl_sync(0xffffffffu, x, l));
+    for (int g = 0; g < OS_CHAIN; g++) { const uint32_t i = a + 32u * g + lane; xn[g] = i < z ? sorted[i] : 0.f; }
+    for (uint32_t j0 = a; j0 < z; j0 += 32 * OS_CHAIN) {
+      float x[OS_CHAIN];
+#pragma unroll
+      for (int g = 0; g < OS_CHAIN; g++) {
+        x[g] = xn[g];
+        const uint32_t i = j0 + 32u * (OS_CHAIN + g) + lane;
+        xn[g] = i < z ? sorted[i] : 0.f;
+      }
+#pragma unroll
+      for (int g = 0; g < OS_CHAIN; g++) {
+        const uint32_t g0 = j0 + 32u * g;
+        if (g0 >= z) break;
+        const int m = (int)min(32u, z - g0);
+        if (m == 32) {
+#pragma unroll
+          for (int l = 0; l < 32; l++) s = __fadd_rn(s, __shfl_sync(0xffffffffu, x[g], l));
+        } else {
+          for (int l = 0; l < m; l++) s = __fadd_rn(s, __shfl_sync(0xffffffffu, x[g], l));
+        }
       }
     }
     if (lane == 0) acc[k] = s;
@@ -218,21 +233,34 @@ __device__ bool cta_ordered_keyed_sum2(uint32_t n, KeyFn key, ValFn val, float* 
     if (a == z) continue;
     const uint32_t real = M.dkey[k];
     float s0 = acc0[real], s1 = acc1[real];
-    float2 xnext = a + lane < z ? sorted[a + lane] : make_float2(0.f, 0.f);
-    for (uint32_t j0 = a; j0 < z; j0 += 32) {
-      const float2 x = xnext;
-      xnext = j0 + 32 + lane < z ? sorted[j0 + 32 + lane] : make_float2(0.f, 0.f);
-      const int m = (int)min(32u, z - j0);
-      if (m == 32) {   // unrolled: the shuffles of a chunk are independent of the two chains of adds and run ahead of them
+    const float2 zero2 = make_float2(0.f, 0.f);
+    float2 xn[OS_CHAIN];
 #pragma unroll
-        for (int l = 0; l < 32; l++) {
-          s0 = __fadd_rn(s0, __shfl_sync(0xffffffffu, x.x, l));
-          s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, x.y, l));
-        }
-      } else {
-        for (int l = 0; l < m; l++) {
-          s0 = __fadd_rn(s0, __shfl_sync(0xffffffffu, x.x, l));
-          s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, x.y, l));
+    for (int g = 0; g < OS_CHAIN; g++) { const uint32_t i = a + 32u * g + lane; xn[g] = i < z ? sorted[i] : zero2; }
+    for (uint32_t j0 = a; j0 < z; j0 += 32 * OS_CHAIN) {
+      float2 x[OS_CHAIN];
+#pragma unroll
+      for (int g = 0; g < OS_CHAIN; g++) {
+        x[g] = xn[g];
+        const uint32_t i = j0 + 32u * (OS_CHAIN + g) + lane;
+        xn[g] = i < z ? sorted[i] : zero2;
+      }
+#pragma unroll
+      for (int g = 0; g < OS_CHAIN; g++) {
+        const uint32_t g0 = j0 + 32u * g;
+        if (g0 >= z) break;
+        const int m = (int)min(32u, z - g0);
+        if (m == 32) {   // unrolled: the shuffles of a group are independent of the two chains of adds and run ahead of them
+#pragma unroll
+          for (int l = 0; l < 32; l++) {
+            s0 = __fadd_rn(s0, __shfl_sync(0xffffffffu, x[g].x, l));
+            s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, x[g].y, l));
+          }
+        } else {
+          for (int l = 0; l < m; l++) {
+            s0 = __fadd_rn(s0, __shfl_sync(0xffffffffu, x[g].x, l));
+            s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, x[g].y, l));
+          }
         }
       }
     }

@@ -1427,7 +1427,9 @@ int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
   TEMP(A.pe_start, A.cap_exon); TEMP(A.pe_end, A.cap_exon); TEMP(A.pe_cov, A.cap_exon);
   KEEP(A.g_npred, (int64_t)G + 1 + 16); KEEP(A.g_geneno, G); KEEP(A.o_pred_off, nb + 1);
   { Scope s(ctx, "asm_gather", 1); CK(ctx, launch_asm_gather(v, A, st)); }
-  { Scope s(ctx, "asm_flow", 1); CK(ctx, launch_asm_flow(v, A, P, st)); }
+  uint32_t *flow_bins = nullptr, *flow_order = nullptr;
+  TEMP(flow_bins, (int64_t)asm_flow_bins_words()); TEMP(flow_order, G);
+  { Scope s(ctx, "asm_flow", 4); CK(ctx, launch_asm_flow(v, A, P, flow_bins, flow_order, ctx->num_sms, st)); }
   uint32_t ctr[2] = {0, 0};
   CK(ctx, small_d2h(ctx, ctr, A.p_counters, 8, st));
   CK(ctx, small_d2h(ctx, &err, v.err_flag, 4, st));

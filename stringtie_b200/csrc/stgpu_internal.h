@@ -277,7 +277,9 @@ cudaError_t launch_asm_tf_sums(const DevBatchView& v, const AsmView& A, cudaStre
 cudaError_t launch_asm_nodecov_commit(const DevBatchView& v, const AsmView& A, cudaStream_t st);
 cudaError_t launch_asm_tf_stats(const DevBatchView& v, const AsmView& A, cudaStream_t st);
 cudaError_t launch_asm_gather(const DevBatchView& v, const AsmView& A, cudaStream_t st);
-cudaError_t launch_asm_flow(const DevBatchView& v, const AsmView& A, const AsmParams& P, cudaStream_t st);
+cudaError_t launch_asm_flow(const DevBatchView& v, const AsmView& A, const AsmParams& P, uint32_t* bins, uint32_t* order, int num_sms,
+                            cudaStream_t st);
+size_t asm_flow_bins_words();
 cudaError_t launch_asm_geneno(const DevBatchView& v, const AsmView& A, const int32_t* b_geneno, cudaStream_t st);
 cudaError_t launch_asm_pred_scatter(const AsmView& A, uint32_t npool, cudaStream_t st);
 cudaError_t launch_asm_exon_scatter(const AsmView& A, uint32_t npool, cudaStream_t st);
