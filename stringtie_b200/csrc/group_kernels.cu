@@ -408,9 +408,10 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel
   int emin_a = 4096, emin_c = 4096;   // the boss: smallest unit of the fragment-sum terms so far
   int color = 0;
   double nf = 0, fl = 0;         // the boss
-  // a step costs the same whatever the width of the window (it is the latency of the classification's load chains and of
-  // the cluster barriers), so the window is always as wide as the cluster
-  const int width = CLUSTER_WINDOW;
+  // a step costs nearly the same whatever the width of the window (the latency of the classification's load chains and of
+  // the cluster barriers), so the window is wide: four times the recent run length, at least 512 reads (reads classified
+  // behind the stop only add L2 traffic and a longer wait for the slowest thread)
+  int width = CLUSTER_WINDOW, run_avg = CLUSTER_WINDOW;
   int n = 0, slow_len = 0, slow_budget = 0, pb = 0, gb = 0, flushed = 0;
   const int inr = (int)nr;
   const unsigned FULL = 0xffffffffu;
@@ -537,24 +538,33 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel
       if (lane == 0) { ctl->ok_mask[gw] = okm; ctl->mint_mask[gw] = mim; ctl->wait_mask[gw] = wam; }
       cluster_sync_all();      // (2) masks are in; every claim has been looked at
       if (npc >= 0) claim[npc] = 0x7f7f7f7f;
+      // k = length of the leading run of simple reads: lane l looks at mask words l and 32 + l (one round trip to L2 for the
+      // whole warp instead of a dependent load per word)
+      const unsigned okA = ctl->ok_mask[lane], okB = ctl->ok_mask[32 + lane];
+      const unsigned miA = ctl->mint_mask[lane], miB = ctl->mint_mask[32 + lane];
+      static_assert(CLUSTER_WINDOW == 2048, "two mask words per lane");
       {
-        bool open = true;
-        for (int w2 = 0; w2 < CLUSTER_WINDOW / 32 && open; w2++) {
-          const unsigned m = ctl->ok_mask[w2];
-          const int kw = m == FULL ? 32 : __ffs(~m) - 1;
-          k += kw;
-          if (kw < 32) open = false;
-        }
+        const unsigned notfullA = __ballot_sync(FULL, okA != FULL), notfullB = __ballot_sync(FULL, okB != FULL);
+        int wfirst;                                  // first word with a read that is not simple (64: none)
+        unsigned mfirst = FULL;
+        if (notfullA) { wfirst = __ffs(notfullA) - 1; mfirst = __shfl_sync(FULL, okA, wfirst); }
+        else if (notfullB) { wfirst = __ffs(notfullB) - 1; mfirst = __shfl_sync(FULL, okB, wfirst); wfirst += 32; }
+        else wfirst = 64;
+        k = wfirst * 32 + (wfirst < 64 ? __ffs(~mfirst) - 1 : 0);
       }
       const bool waits0 = k < CLUSTER_WINDOW && (ctl->wait_mask[k >> 5] >> (k & 31) & 1u);
       int before = 0, minted = 0;     // colours minted by the run's reads ahead of this thread / by the whole run
-      for (int w2 = 0; w2 * 32 < k; w2++) {
-        const int rem = k - 32 * w2;
-        const unsigned run = rem >= 32 ? FULL : (1u << rem) - 1u;
-        const unsigned mi = ctl->mint_mask[w2] & run;
-        if (w2 < gw) before += __popc(mi);
-        else if (w2 == gw) before += __popc(mi & ((1u << lane) - 1u));
-        minted += __popc(mi);
+      {
+        auto run_of = [&](int w2) -> unsigned { const int rem = k - 32 * w2; return rem >= 32 ? FULL : (rem > 0 ? (1u << rem) - 1u : 0u); };
+        const unsigned a = miA & run_of(lane), b2 = miB & run_of(32 + lane);
+        int mine = 0;                                // colours of the run in the words this lane holds, below word gw
+        if (lane < gw) mine += __popc(a);
+        if (32 + lane < gw) mine += __popc(b2);
+        int tot = __popc(a) + __popc(b2);
+        for (int o = 16; o; o >>= 1) { mine += __shfl_xor_sync(FULL, mine, o); tot += __shfl_xor_sync(FULL, tot, o); }
+        const unsigned own = __shfl_sync(FULL, gw < 32 ? a : b2, gw & 31);
+        before = mine + __popc(own & ((1u << lane) - 1u));
+        minted = tot;
       }
       if (gt < k) {
         commit_free(S, R[gt], me, color + before);
@@ -582,13 +592,14 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel
       pb ^= 1;
       color += minted;
       no_walk = k >= hi - n || waits0;
+      run_avg = (3 * run_avg + (k >= hi - n ? CLUSTER_WINDOW : k)) / 4;
+      width = 4 * run_avg < 512 ? 512 : (4 * run_avg < CLUSTER_WINDOW ? 4 * run_avg : CLUSTER_WINDOW);
       n += k;
       if (k == 0) { slow_len = slow_len * 2 + 1 < 15 ? slow_len * 2 + 1 : 15; slow_budget = slow_len; }
       else if (k >= 8) slow_len = 0;
     } else slow_budget--;
     if (n < inr && !no_walk) {
-      flush(n);
-      cluster_sync_all();      // (4) the sums are in
+      flush(n);                // CTA 0 (it ends with __syncthreads: the boss, thread 0 of CTA 0, sees the sums)
       if (boss) { const long long t = clock64(); t_flush += t - t0c; t0c = t; walks++; }
       if (boss) {
         S.err |= (uint32_t)ctl->err;
@@ -623,6 +634,18 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel
   }
 }
 
+// compaction of the colour tables, one thread per colour of the batch: its bundle is found by bisection of the prefix b_ncol
+__global__ void __launch_bounds__(256) groups_colcopy_kernel(DevBatchView v, GroupsView g, uint32_t ncol_total) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ncol_total) return;
+  uint32_t lo = 0, hi = (uint32_t)v.n_bundles;          // b_ncol[lo] <= j < b_ncol[hi]
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (g.b_ncol[mid] <= j) lo = mid; else hi = mid; }
+  const uint32_t r0 = v.b_read_off[lo];
+  const size_t C0 = (size_t)g.rcap_off[r0] + 3 * (size_t)r0;
+  const int32_t e = g.eqcol[C0 + (j - g.b_ncol[lo])];
+  g.d_eqcol[j] = e; g.d_eq2[j] = e; g.d_eqneg[j] = -1; g.d_eqpos[j] = -1; g.d_bundlecol[j] = -1;
+}
+
 // after the scans: b_ng / b_ncol / b_napp are exclusive prefixes
 __global__ void __launch_bounds__(128) groups_colour_kernel(DevBatchView v, GroupsView g) {
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -640,10 +663,8 @@ __global__ void __launch_bounds__(128) groups_colour_kernel(DevBatchView v, Grou
     g.d_color2[Gd + i] = g.g_color[G0 + i]; g.d_negp[Gd + i] = 0.f;
   }
   for (int i = lane; i < 3 * ng; i += 32) g.d_g2b[3 * Gd + i] = -1;
-  for (int i = lane; i < nc; i += 32) {
-    const int32_t e = g.eqcol[C0 + i];
-    g.d_eqcol[Cd + i] = e; g.d_eq2[Cd + i] = e; g.d_eqneg[Cd + i] = -1; g.d_eqpos[Cd + i] = -1; g.d_bundlecol[Cd + i] = -1;
-  }
+  // (the colour tables were compacted by groups_colcopy_kernel: a deep bundle has 10^6 colours)
+  (void)C0; (void)Cd; (void)nc;
   __syncwarp();
   if (lane) return;
   for (int s = 0; s < 3; s++) { g.b_nbun[3 * b + s] = 0; g.b_nbn[3 * b + s] = 0; }
@@ -760,6 +781,7 @@ int64_t groups_deep_reads() { return GROUPS_DEEP_READS; }
 
 cudaError_t launch_groups_finish(const DevBatchView& v, const GroupsView& g, cudaStream_t st) {
   if (v.n_bundles == 0) return cudaSuccess;
+  if (g.n_colors) groups_colcopy_kernel<<<(unsigned)((g.n_colors + 255) / 256), 256, 0, st>>>(v, g, (uint32_t)g.n_colors);
   groups_colour_kernel<<<(unsigned)((v.n_bundles + 3) / 4), 128, 0, st>>>(v, g);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

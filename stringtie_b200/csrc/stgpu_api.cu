@@ -1069,7 +1069,7 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
   KEEP(g.d_rg, g.n_rg);
   KEEP(g.oj_start, NJ); KEEP(g.oj_end, NJ); KEEP(g.oj_strand, NJ); KEEP(g.oj_nreads, NJ); KEEP(g.oj_nreads_good, NJ);
   KEEP(g.oj_left, NJ); KEEP(g.oj_right, NJ); KEEP(g.oj_nm, NJ); KEEP(g.oj_mm, NJ);
-  { Scope s(ctx, "groups_colour+compact", 3); CK(ctx, launch_groups_finish(v, g, st)); }
+  { Scope s(ctx, "groups_colour+compact", 4); CK(ctx, launch_groups_finish(v, g, st)); }
 #undef KEEP
 #undef TEMP
   d->groups_built = true;
