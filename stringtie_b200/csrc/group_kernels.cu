@@ -341,6 +341,7 @@ __device__ int g_groups_debug = 0;
 #define CLUSTER_CTAS 8
 #define CLUSTER_THREADS 256
 #define CLUSTER_WINDOW (CLUSTER_CTAS * CLUSTER_THREADS)
+#define CLUSTER_HOPS 24           // links of the group chain a read of the window may follow (classify_read)
 struct ClusterCtl {
   int32_t err, ng, color;
   int32_t curr[3];
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel
     FastDeps D;
     D.n = 0;
     if (classify) {
-      if (me < hi) st = classify_read<true>(S, me, n, hi, R[gt], &D);
+      if (me < hi) st = classify_read<true>(S, me, n, hi, R[gt], &D, CLUSTER_HOPS);
       if (st == 1 || st == 3) npc = R[gt].npc;
       if (npc >= 0) atomicMin(&claim[npc], gt);
       if (st == 3) ctl->grow[gb][atomicAdd(&ctl->n_grow[gb], 1)] = gt;

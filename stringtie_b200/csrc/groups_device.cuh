@@ -678,8 +678,13 @@ STG_HD int fp_bail(int) { return 0; }
 #define STG_FP_MAXC 6
 struct FastDeps { int32_t n; uint32_t kind; int32_t g[STG_FP_MAXC]; uint32_t x[STG_FP_MAXC]; };
 
+// hop_budget: a read that would have to follow the chain of groups for more than this many links (it lies far behind the
+// cursor: every link is a dependent load, and the step waits for its slowest thread) gives up and waits for the next
+// step, whose cursor is closer — unless it is the first read of the window (progress).
 template <bool DEPS>
-STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& __restrict__ R, FastDeps* __restrict__ D = nullptr) {
+STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& __restrict__ R, FastDeps* __restrict__ D = nullptr,
+                         int hop_budget = 0x7fffffff) {
+  if (n == lo) hop_budget = 0x7fffffff;
   R.nv = 0; R.nrg0 = 0; R.nrg1 = 0; R.has_multi = 0; R.sno = -1; R.newcol = 0; R.fresh_gc = -1; R.gp_np = -1; R.npc = -1; R.unpair_np = -1; R.xg = -1;
   if (DEPS) { D->n = 0; D->kind = 0; }
 #ifdef __CUDA_ARCH__
@@ -778,7 +783,10 @@ STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& __restric
       if (currgroup == -1) return fp_bail(9);
       int lastgroup = -1;
       const uint32_t rstart = S.r_start[cn];
-      while (currgroup != -1 && rstart > GE(currgroup)) { lastgroup = currgroup; currgroup = S.g_next[currgroup]; }
+      while (currgroup != -1 && rstart > GE(currgroup)) {
+        if (--hop_budget < 0) { fp_bail(20); return 2; }
+        lastgroup = currgroup; currgroup = S.g_next[currgroup];
+      }
       if (lastgroup != -1) depends(lastgroup, false, rstart);           // the last group walked past ends below the read
       if (currgroup != -1 && S.seg_e[S.segi(cn, 0)] < GS(currgroup)) depends(currgroup, true, S.seg_e[S.segi(cn, 0)]);
       if (currgroup == -1 || S.seg_e[S.segi(cn, 0)] < GS(currgroup)) currgroup = lastgroup;
@@ -790,7 +798,10 @@ STG_HD int classify_read(const Grp& S, int n, int lo, int hi, FastRec& __restric
         const uint32_t ss = S.seg_s[S.segi(cn, i)], se = S.seg_e[S.segi(cn, i)];
         {
           int skipped = -1;
-          while (thisgroup != -1 && ss > GE(thisgroup)) { skipped = thisgroup; thisgroup = S.g_next[thisgroup]; }
+          while (thisgroup != -1 && ss > GE(thisgroup)) {
+            if (--hop_budget < 0) { fp_bail(20); return 2; }
+            skipped = thisgroup; thisgroup = S.g_next[thisgroup];
+          }
           if (skipped != -1) depends(skipped, false, ss);
         }
         if (thisgroup == -1 || se + localdist < GS(thisgroup)) return fp_bail(12);             // a new group
