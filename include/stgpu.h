@@ -336,6 +336,10 @@ typedef struct stg_bundle_result {
   const float* e_cov;                          /* CPrediction::exoncov */
 } stg_bundle_result;
 int stg_infer_transcripts(stg_ctx* ctx, const stg_bundle_view* view, stg_bundle_result* result);
+/* The same for n bundles in ONE device batch (what a host does that collects the bundles of its worker threads, or of its
+ * bundle queue, before it calls: host/stgpu_adaptor.cpp).  results[i] describes bundle i; its p_exon_off is relative to its own e_start /
+ * e_end / e_cov.  The arrays are owned by the context and stay valid until the next stg_infer_transcripts* call on it. */
+int stg_infer_transcripts_batch(stg_ctx* ctx, int64_t n, const stg_bundle_view* views, stg_bundle_result* results);
 
 /* ---- multi-GPU: bundles shard by genomic locus, one rank per GPU ---------------------------------
  * Greedy least-loaded assignment on cost = reads + span/64, heaviest bundles first (the reference has one queue

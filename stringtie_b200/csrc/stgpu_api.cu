@@ -24,6 +24,7 @@ struct PoolBlock { void* p; size_t bytes; };
 struct OneBundleOut {   // BundleData::pred of the last stg_infer_transcripts call (owned by the context)
   std::vector<int32_t> p_start, p_end, p_tlen, p_geneno; std::vector<double> p_cov; std::vector<int8_t> p_strand;
   std::vector<uint32_t> p_exon_off, e_start, e_end; std::vector<float> e_cov;
+  std::vector<double> j_good, j_left, j_right;
 };
 
 struct StagePending { void* dst; size_t off, bytes; };
@@ -1509,8 +1510,9 @@ int stg_fetch_asm_array(stg_ctx* ctx, const stg_dbatch* d, int which, int64_t fi
   return STG_OK;
 }
 
-int stg_infer_transcripts(stg_ctx* ctx, const stg_bundle_view* view, stg_bundle_result* result) {
-  if (!ctx || !view || !result) return fail(ctx, STG_EINVAL, "stg_infer_transcripts: null argument");
+// n bundles through the whole path in ONE device batch; what infer_transcripts(BundleData*) writes back comes out per bundle
+int stg_infer_transcripts_batch(stg_ctx* ctx, int64_t n, const stg_bundle_view* views, stg_bundle_result* results) {
+  if (!ctx || n < 0 || (n && (!views || !results))) return fail(ctx, STG_EINVAL, "stg_infer_transcripts_batch: bad argument");
   std::lock_guard<std::mutex> lk(ctx->one_bundle_mu);   // one context, one stream: callers take turns
   int rc = STG_OK;
   if (!ctx->one_bundle && (rc = stg_builder_create(ctx, &ctx->one_bundle))) return rc;
@@ -1518,57 +1520,106 @@ int stg_infer_transcripts(stg_ctx* ctx, const stg_bundle_view* view, stg_bundle_
   stg_builder_reset(b);
   stg_dbatch* d = nullptr;
   stg_packed_batch pb;
-  result->n_pred = 0; result->n_exon = 0; result->num_fragments = 0; result->frag_len = 0;
-  if (!(rc = stg_builder_add(b, view)) && !(rc = stg_builder_packed(b, &pb)) && !(rc = stg_upload(ctx, &pb, &d)) &&
-      !(rc = stg_run(ctx, d))) {
-    if (result->bpcov) rc = stg_fetch_bpcov(ctx, d, 0, result->bpcov);
-    if (!rc) rc = stg_fetch_junction_support(ctx, d, result->j_nreads_good, result->j_leftsupport, result->j_rightsupport);
-    if (!rc && result->assemble && !(rc = stg_build_groups(ctx, d)) && !(rc = stg_neutral_predictions(ctx, d)) && !(rc = stg_assemble(ctx, d))) {
-      // BundleData::pred: the neutral bundles' predictions, then the graphs'
-      OneBundleOut& o = ctx->one_out;
+  bool assemble = false;
+  for (int64_t i = 0; i < n; i++) {
+    results[i].n_pred = 0; results[i].n_exon = 0; results[i].num_fragments = 0; results[i].frag_len = 0;
+    assemble = assemble || results[i].assemble;
+    if ((rc = stg_builder_add(b, &views[i]))) return rc;
+  }
+  if (n == 0) return STG_OK;
+  if (!(rc = stg_builder_packed(b, &pb)) && !(rc = stg_upload(ctx, &pb, &d)) && !(rc = stg_run(ctx, d))) {
+    // bpcov and the junction support of every bundle that asked for them: the copies are queued together, one wait
+    for (int64_t i = 0; i < n && !rc; i++)
+      if (results[i].bpcov) {
+        const size_t len = d->h_len[i];
+        if (cudaMemcpy2DAsync(results[i].bpcov, len * sizeof(float), d->v.bpcov + d->h_cov_off[i], (size_t)d->h_stride[i] * sizeof(float),
+                              len * sizeof(float), 3, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+          rc = fail(ctx, STG_ECUDA, "stg_infer_transcripts_batch: copy of bpcov failed");
+      }
+    if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, STG_ECUDA, "stg_infer_transcripts_batch: stream failed");
+    OneBundleOut& o = ctx->one_out;
+    if (!rc && pb.n_juncs) {
+      bool want = false;
+      for (int64_t i = 0; i < n; i++) want = want || results[i].j_nreads_good || results[i].j_leftsupport || results[i].j_rightsupport;
+      if (want) {
+        o.j_good.resize(pb.n_juncs); o.j_left.resize(pb.n_juncs); o.j_right.resize(pb.n_juncs);
+        rc = stg_fetch_junction_support(ctx, d, o.j_good.data(), o.j_left.data(), o.j_right.data());
+        for (int64_t i = 0; i < n && !rc; i++) {
+          const uint32_t j0 = pb.b_junc_off[i], nj = pb.b_junc_off[i + 1] - j0;
+          if (results[i].j_nreads_good) memcpy(results[i].j_nreads_good, o.j_good.data() + j0, sizeof(double) * nj);
+          if (results[i].j_leftsupport) memcpy(results[i].j_leftsupport, o.j_left.data() + j0, sizeof(double) * nj);
+          if (results[i].j_rightsupport) memcpy(results[i].j_rightsupport, o.j_right.data() + j0, sizeof(double) * nj);
+        }
+      }
+    }
+    if (!rc && assemble && !(rc = stg_build_groups(ctx, d)) && !(rc = stg_neutral_predictions(ctx, d)) && !(rc = stg_assemble(ctx, d))) {
+      // BundleData::pred of every bundle: its neutral bundles' predictions, then its graphs'
       const int64_t nn = d->nv.n_preds, np = d->av.n_pred, ne = d->av.n_exon;
       const int64_t NP = nn + np, NE = nn + ne;
       o.p_start.resize(NP); o.p_end.resize(NP); o.p_cov.resize(NP); o.p_tlen.resize(NP); o.p_geneno.resize(NP); o.p_strand.resize(NP);
-      o.p_exon_off.resize(NP + 1); o.e_start.resize(NE); o.e_end.resize(NE); o.e_cov.resize(NE);
-      std::vector<uint32_t> us(std::max<int64_t>(nn, 1)), ue(std::max<int64_t>(nn, 1));
+      o.p_exon_off.resize(NP + n); o.e_start.resize(NE); o.e_end.resize(NE); o.e_cov.resize(NE);
+      std::vector<uint32_t> noff(n + 1, 0), poff(n + 1, 0), us(std::max<int64_t>(nn, 1)), ue(std::max<int64_t>(nn, 1)), gs(std::max<int64_t>(np, 1)),
+          ge(std::max<int64_t>(np, 1)), xo(np + 1, 0), es(std::max<int64_t>(ne, 1)), ee(std::max<int64_t>(ne, 1));
+      std::vector<double> ncov(std::max<int64_t>(nn, 1)), gcov(std::max<int64_t>(np, 1)), nf(n), fl(n);
+      std::vector<int32_t> ntl(std::max<int64_t>(nn, 1)), ngn(std::max<int64_t>(nn, 1)), gtl(std::max<int64_t>(np, 1)), ggn(std::max<int64_t>(np, 1));
+      std::vector<int8_t> gst(std::max<int64_t>(np, 1));
+      std::vector<float> ec(std::max<int64_t>(ne, 1));
+      rc = stg_fetch_groups_array(ctx, d, STG_GA_NP_OFF, 0, n + 1, noff.data());
+      if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_PRED_OFF, 0, n + 1, poff.data());
       if (nn) {
         if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NP_START, 0, nn, us.data());
         if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NP_END, 0, nn, ue.data());
-        if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NP_COV, 0, nn, o.p_cov.data());
-        if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NP_TLEN, 0, nn, o.p_tlen.data());
-        if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NP_GENENO, 0, nn, o.p_geneno.data());
-        for (int64_t i = 0; i < nn && !rc; i++) {
-          o.p_start[i] = (int32_t)us[i]; o.p_end[i] = (int32_t)ue[i]; o.p_strand[i] = '.';
-          o.p_exon_off[i] = (uint32_t)i; o.e_start[i] = us[i]; o.e_end[i] = ue[i]; o.e_cov[i] = (float)o.p_cov[i];
-        }
+        if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NP_COV, 0, nn, ncov.data());
+        if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NP_TLEN, 0, nn, ntl.data());
+        if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NP_GENENO, 0, nn, ngn.data());
       }
-      if (np && !rc) {
-        std::vector<uint32_t> gs(np), ge(np), xo(np + 1);
-        rc = stg_fetch_asm_array(ctx, d, STG_AA_P_START, 0, np, gs.data());
+      if (np) {
+        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_START, 0, np, gs.data());
         if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_END, 0, np, ge.data());
-        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_COV, 0, np, o.p_cov.data() + nn);
-        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_TLEN, 0, np, o.p_tlen.data() + nn);
-        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_GENENO, 0, np, o.p_geneno.data() + nn);
-        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_STRAND, 0, np, o.p_strand.data() + nn);
+        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_COV, 0, np, gcov.data());
+        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_TLEN, 0, np, gtl.data());
+        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_GENENO, 0, np, ggn.data());
+        if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_STRAND, 0, np, gst.data());
         if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_EXON_OFF, 0, np + 1, xo.data());
-        if (!rc && ne) rc = stg_fetch_asm_array(ctx, d, STG_AA_E_START, 0, ne, o.e_start.data() + nn);
-        if (!rc && ne) rc = stg_fetch_asm_array(ctx, d, STG_AA_E_END, 0, ne, o.e_end.data() + nn);
-        if (!rc && ne) rc = stg_fetch_asm_array(ctx, d, STG_AA_E_COV, 0, ne, o.e_cov.data() + nn);
-        for (int64_t i = 0; i < np && !rc; i++) { o.p_start[nn + i] = (int32_t)gs[i]; o.p_end[nn + i] = (int32_t)ge[i]; o.p_exon_off[nn + i] = (uint32_t)nn + xo[i]; }
+        if (!rc && ne) rc = stg_fetch_asm_array(ctx, d, STG_AA_E_START, 0, ne, es.data());
+        if (!rc && ne) rc = stg_fetch_asm_array(ctx, d, STG_AA_E_END, 0, ne, ee.data());
+        if (!rc && ne) rc = stg_fetch_asm_array(ctx, d, STG_AA_E_COV, 0, ne, ec.data());
       }
-      o.p_exon_off[NP] = (uint32_t)NE;
-      if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NUM_FRAGMENTS, 0, 1, &result->num_fragments);
-      if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_FRAG_LEN, 0, 1, &result->frag_len);
+      if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_NUM_FRAGMENTS, 0, n, nf.data());
+      if (!rc) rc = stg_fetch_groups_array(ctx, d, STG_GA_FRAG_LEN, 0, n, fl.data());
       if (!rc) {
-        result->n_pred = (int32_t)NP; result->n_exon = (int32_t)NE;
-        result->p_start = o.p_start.data(); result->p_end = o.p_end.data(); result->p_cov = o.p_cov.data(); result->p_tlen = o.p_tlen.data();
-        result->p_geneno = o.p_geneno.data(); result->p_strand = o.p_strand.data(); result->p_exon_off = o.p_exon_off.data();
-        result->e_start = o.e_start.data(); result->e_end = o.e_end.data(); result->e_cov = o.e_cov.data();
+        int64_t P = 0, E = 0, X = 0;   // cursors: predictions, exons, entries of the exon-offset table (n_pred + 1 per bundle)
+        for (int64_t i = 0; i < n; i++) {
+          stg_bundle_result& r = results[i];
+          const int64_t p0 = P, e0 = E, x0 = X;
+          for (uint32_t q = noff[i]; q < noff[i + 1]; q++, P++, E++, X++) {
+            o.p_start[P] = (int32_t)us[q]; o.p_end[P] = (int32_t)ue[q]; o.p_cov[P] = ncov[q]; o.p_tlen[P] = ntl[q]; o.p_geneno[P] = ngn[q];
+            o.p_strand[P] = '.'; o.p_exon_off[X] = (uint32_t)(E - e0);
+            o.e_start[E] = us[q]; o.e_end[E] = ue[q]; o.e_cov[E] = (float)ncov[q];
+          }
+          for (uint32_t q = poff[i]; q < poff[i + 1]; q++, P++, X++) {
+            o.p_start[P] = (int32_t)gs[q]; o.p_end[P] = (int32_t)ge[q]; o.p_cov[P] = gcov[q]; o.p_tlen[P] = gtl[q]; o.p_geneno[P] = ggn[q];
+            o.p_strand[P] = gst[q]; o.p_exon_off[X] = (uint32_t)(E - e0);
+            for (uint32_t x = xo[q]; x < xo[q + 1]; x++, E++) { o.e_start[E] = es[x]; o.e_end[E] = ee[x]; o.e_cov[E] = ec[x]; }
+          }
+          o.p_exon_off[X++] = (uint32_t)(E - e0);
+          if (!r.assemble) continue;
+          r.n_pred = (int32_t)(P - p0); r.n_exon = (int32_t)(E - e0);
+          r.num_fragments = nf[i]; r.frag_len = fl[i];
+          r.p_start = o.p_start.data() + p0; r.p_end = o.p_end.data() + p0; r.p_cov = o.p_cov.data() + p0; r.p_tlen = o.p_tlen.data() + p0;
+          r.p_geneno = o.p_geneno.data() + p0; r.p_strand = o.p_strand.data() + p0; r.p_exon_off = o.p_exon_off.data() + x0;
+          r.e_start = o.e_start.data() + e0; r.e_end = o.e_end.data() + e0; r.e_cov = o.e_cov.data() + e0;
+        }
       }
     }
   }
   stg_free_batch(ctx, d);
   return rc;
+}
+
+int stg_infer_transcripts(stg_ctx* ctx, const stg_bundle_view* view, stg_bundle_result* result) {
+  if (!ctx || !view || !result) return fail(ctx, STG_EINVAL, "stg_infer_transcripts: null argument");
+  return stg_infer_transcripts_batch(ctx, 1, view, result);
 }
 
 // ---- multi-GPU sharding (host only) -----------------------------------------------------------------------------

@@ -23,7 +23,7 @@ EXPORTS = [
     "stg_builder_add", "stg_builder_packed", "stg_builder_reset", "stg_builder_destroy", "stg_upload", "stg_run",
     "stg_sync", "stg_free_batch", "stg_trim", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
     "stg_upload_wait", "stg_fetch_bpcov_all_begin", "stg_fetch_wait",
-    "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_trims_capacity", "stg_find_trims", "stg_infer_transcripts",
+    "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_trims_capacity", "stg_find_trims", "stg_infer_transcripts", "stg_infer_transcripts_batch",
     "stg_build_groups", "stg_groups_array_info", "stg_fetch_groups_array", "stg_neutral_predictions",
     "stg_assemble", "stg_asm_array_info", "stg_fetch_asm_array", "stg_rewind", "stg_reduce_totals",
     "stg_shard_assign", "stg_set_profiling", "stg_kernel_count", "stg_kernel_time", "stg_launch_counter", "stg_batch_stats", "stg_stream",
@@ -109,6 +109,7 @@ def load_library() -> C.CDLL:
     L.stg_find_trims.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int8), u32p, u32p, u32p, u32p, u32p,
                                  c_f32p, u8p]
     L.stg_infer_transcripts.argtypes = [vp, C.POINTER(StgBundleView), C.POINTER(StgBundleResult)]
+    L.stg_infer_transcripts_batch.argtypes = [vp, C.c_int64, C.POINTER(StgBundleView), C.POINTER(StgBundleResult)]
     L.stg_build_groups.argtypes = [vp, vp]
     L.stg_neutral_predictions.argtypes = [vp, vp]
     L.stg_groups_array_info.argtypes = [vp, C.c_int, c_i64p, C.POINTER(C.c_int32)]
@@ -399,6 +400,35 @@ class Engine:
         res = StgBundleResult(ptr(cov), ptr(good), ptr(left), ptr(right))
         self._ck(self.L.stg_infer_transcripts(self.ctx, C.byref(view), C.byref(res)))
         return cov.reshape(3, length), good, left, right
+
+    def infer_transcripts_batch(self, arrays: Dict[str, np.ndarray], bundles):
+        """stg_infer_transcripts_batch on the listed bundles: a list of (bpcov, predictions dict, num_fragments, frag_len), one
+        per bundle, each as infer_transcripts_full returns it."""
+        n = len(bundles)
+        views = (StgBundleView * n)()
+        results = (StgBundleResult * n)()
+        keep, covs = [], []
+        for i, b in enumerate(bundles):
+            view, k = bundle_view(arrays, int(b))
+            keep.append(k)
+            views[i] = view
+            length = view.end - view.start + 3
+            cov = np.empty(3 * length, dtype=np.float32)
+            covs.append((cov, length))
+            results[i] = StgBundleResult(ptr(cov), None, None, None)
+            results[i].assemble = 1
+        self._ck(self.L.stg_infer_transcripts_batch(self.ctx, n, views, results))
+        cp = lambda p, k, dt: np.ctypeslib.as_array(p, shape=(k,)).astype(dt, copy=True) if k else np.empty(0, dtype=dt)
+        out = []
+        for i in range(n):
+            res = results[i]
+            m, ne = res.n_pred, res.n_exon
+            pred = {"start": cp(res.p_start, m, np.int32), "end": cp(res.p_end, m, np.int32), "cov": cp(res.p_cov, m, np.float64),
+                    "tlen": cp(res.p_tlen, m, np.int32), "geneno": cp(res.p_geneno, m, np.int32), "strand": cp(res.p_strand, m, np.int8),
+                    "exon_off": cp(res.p_exon_off, m + 1, np.uint32) if m else np.zeros(1, dtype=np.uint32),
+                    "e_start": cp(res.e_start, ne, np.uint32), "e_end": cp(res.e_end, ne, np.uint32), "e_cov": cp(res.e_cov, ne, np.float32)}
+            out.append((covs[i][0].reshape(3, covs[i][1]), pred, res.num_fragments, res.frag_len))
+        return out
 
     def infer_transcripts_full(self, arrays: Dict[str, np.ndarray], b: int = 0):
         """The whole of `infer_transcripts(BundleData*)` (rlink.h:380) for bundle b: returns (bpcov, predictions dict,

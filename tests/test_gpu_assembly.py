@@ -115,3 +115,20 @@ def test_one_bundle_drop_in_returns_the_reference_prediction_list(engine):
         assert nfrag == g["f_num_fragments"][b] and flen == g["f_frag_len"][b]
         c0, c1 = int(g["s1_cov_off"][b]), int(g["s1_cov_off"][b + 1])
         assert np.array_equal(cov.reshape(-1).view(np.uint32), g["s1_cov"][c0:c1].view(np.uint32))
+
+
+def test_batched_drop_in_equals_one_bundle_calls(engine):
+    """stg_infer_transcripts_batch (several bundles of the host's worker threads in one device batch) returns for every
+    bundle exactly what the one-bundle call returns: BundleData::pred, bpcov, num_fragments, frag_len."""
+    g = load_golden("short_s13_jitter")
+    from stringtie_b200.stgb import input_view
+    a = input_view(g)
+    pick = [0, 3, 4, 7, 11, int(g["b_start"].size) - 1]
+    got = engine.infer_transcripts_batch(a, pick)
+    assert sum(p["start"].size for _, p, _, _ in got) > 10
+    for (cov, pred, nfrag, flen), b in zip(got, pick):
+        cov1, pred1, nfrag1, flen1 = engine.infer_transcripts_full(a, b)
+        assert np.array_equal(cov.view(np.uint32), cov1.view(np.uint32))
+        assert nfrag == nfrag1 and flen == flen1
+        for k in pred1:
+            assert np.array_equal(pred[k].view(np.uint8), pred1[k].view(np.uint8)), (b, k)

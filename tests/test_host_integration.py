@@ -28,7 +28,7 @@ def _body(path):
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(BIN), reason="host/_build/stringtie_stgpu not built (needs /root/reference at build time)")
 @pytest.mark.parametrize("name", sorted(CASES))
-@pytest.mark.parametrize("threads", [1, 4])
+@pytest.mark.parametrize("threads", [1, 4, 16])
 def test_reference_host_with_gpu_stage_writes_identical_gtf(tmp_path, name, threads):
     sam, gtf = str(tmp_path / "in.sam"), str(tmp_path / "out.gtf")
     subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_sam.py"), "--sam", sam] + CASES[name],
@@ -36,8 +36,13 @@ def test_reference_host_with_gpu_stage_writes_identical_gtf(tmp_path, name, thre
     env = dict(os.environ, STGPU_VERBOSE="1")
     p = subprocess.run([BIN, sam, "-p", str(threads), "-o", gtf], env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
-    assert "bundles went through the GPU" in p.stderr and not p.stderr.startswith("libstgpu: 0 ")
-    assert ", 0 predictions came back" not in p.stderr
+    import re as _re
+    m = _re.search(r"libstgpu: (\d+) bundles in (\d+) device batches \(largest (\d+)\), (\d+) predictions", p.stderr)
+    assert m, p.stderr[-2000:]
+    nb, nbatch, largest, npred = (int(x) for x in m.groups())
+    assert nb > 0 and npred > 0 and 1 <= nbatch <= nb and largest <= max(threads, 1)
+    if threads == 1:
+        assert nbatch == nb
     got, want = _body(gtf), _body(os.path.join(ROOT, "tests", "golden", name + ".gtf"))
     if threads == 1:
         assert got == want
@@ -49,4 +54,4 @@ def test_reference_host_with_gpu_stage_writes_identical_gtf(tmp_path, name, thre
 
 def test_adaptor_source_declares_the_replaced_symbol():
     src = open(os.path.join(ROOT, "host", "stgpu_adaptor.cpp")).read()
-    assert "int infer_transcripts(BundleData* bundle)" in src and "stg_infer_transcripts" in src and "assemble = 1" in src
+    assert "int infer_transcripts(BundleData* bundle)" in src and "stg_infer_transcripts_batch" in src and "assemble = 1" in src
