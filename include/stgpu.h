@@ -350,6 +350,13 @@ int stg_shard_assign(int64_t n_bundles, const uint32_t* b_read_off /*[n+1]*/, co
 
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------------
  * With profiling on, stg_run brackets every kernel with CUDA events on the context stream.            */
+/* Self-test of the engine's ordered float sums: out[i] = (((s0[i] + x[off[i]]) + x[off[i]+1]) + ...) in float32 with
+ * round-to-nearest at every step, i.e. what the reference's "+=" loops compute (cov_edge_add rlink.cpp:133-142,
+ * update_abundance :4680), through the kernel code path the coverage and commit stages use for long sums (`plain` == 1:
+ * through the bare chain of dependent adds instead; 2: the form in which a whole CTA shares one list).  kernel_ms (may be NULL) receives the kernel's duration. */
+int stg_selftest_chain(stg_ctx* ctx, int64_t n, const uint32_t* off /*[n+1]*/, const float* x, const float* s0 /*[n]*/,
+                       float* out /*[n]*/, int plain, float* kernel_ms);
+
 int stg_set_profiling(stg_ctx* ctx, int enabled);
 int stg_kernel_count(const stg_ctx* ctx);                       /* kernels launched by the last stg_run */
 int stg_kernel_time(stg_ctx* ctx, int i, const char** name, float* ms); /* after stg_sync */

@@ -39,6 +39,7 @@
 //   K10 cov_fill       one warp per event-free sub-tile: state from the carry + closed form, streaming write.
 // All float arithmetic is compiled without FMA contraction (-fmad=false): the reference is plain x86-64 SSE.
 #include "stgpu_internal.h"
+#include "exact_chain.cuh"
 
 #define FULL 0xffffffffu
 
@@ -673,7 +674,7 @@ cudaError_t launch_tile_plan(const DevBatchView& v, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(v.round_off, 0, sizeof(uint32_t) * (size_t)(v.n_rounds + 1), st);
   if (e != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(v.round_cur, 0, sizeof(uint32_t) * (size_t)(v.n_rounds + 1), st)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(v.deep_count, 0, 2 * sizeof(uint32_t), st)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(v.deep_count, 0, 4 * sizeof(uint32_t), st)) != cudaSuccess) return e;
   tile_plan_kernel<false><<<(unsigned)((v.n_tiles + 255) / 256), 256, 0, st>>>(v);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if ((e = run_scan<OP_ADD, false, true>(v.round_off, v.round_off, v.n_rounds + 1, v.scan_partials, st)) != cudaSuccess) return e;
@@ -791,69 +792,117 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32) deep_deposit_kernel(DevBatchV
       }
       else {
         // handed to deep_long_kernel: the CTA must not idle behind one position's chain of 10^4..10^5 dependent adds
-        const uint32_t slot = atomicAdd(v.deep_count + 1, 1u);
-        v.deep_long[slot] = make_uint4(di, (uint32_t)p, e0 + l0, n);
+        // (lists long enough for a whole CTA are collected from the far end of the array)
+        const bool big = n >= (uint32_t)EC_CTA_MIN;
+        const uint32_t k = atomicAdd(v.deep_count + (big ? 2 : 1), 1u);
+        v.deep_long[big ? v.deep_long_cap - 1u - k : k] = make_uint4(di, (uint32_t)p, e0 + l0, n);
       }
     }
     __syncthreads();
   }
 }
 
-// Long per-position lists of deep sub-tiles (> 64 events on one position: a splice site of a deep locus), one warp
-// per list: 32 events are loaded at a time (coalesced, next group prefetched) and staged in shared memory per strand
-// lane (cov_edge_add, rlink.cpp:133-142: own lane and lane 1; the other lanes get +0.0, a no-op since no accumulator
-// is ever -0); lanes 0..2 then run the bare chain of dependent adds in reference order.
-__global__ void __launch_bounds__(256) deep_long_kernel(DevBatchView v) {
-  __shared__ __align__(16) float stage[8][3][32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint32_t nlong = v.deep_count[1];
-  for (;;) {
-    uint32_t li = 0;
-    if (lane == 0) li = atomicAdd(v.tile_ticket + 2, 1u);
-    li = __shfl_sync(FULL, li, 0);
-    if (li >= nlong) break;
-    const uint4 rec = v.deep_long[li];
-    const uint2* __restrict__ list = v.events2 + rec.z;
-    const uint32_t qn = rec.w;
-    float acc = 0.f;   // lane s < 3 accumulates strand lane s
-    // 4 groups of 32 events (1 KB) are in flight ahead of the chain: the list streams from HBM at ~1 us latency
-    // while one group costs the chain only ~150 cycles
-    constexpr int DEPTH = 4;
-    const uint2 pad = make_uint2(1u, 0u);      // +0.0 on lane 1: a no-op (no accumulator is ever -0)
-    uint2 cur[DEPTH];
+// Long per-position lists of deep sub-tiles (> 64 events on one position: a splice site of a deep locus).  The three
+// strand lanes of a position are three chains of dependent float adds in reference order (cov_edge_add,
+// rlink.cpp:133-142: the strand's own lane and lane 1; the other lanes get +0.0, a no-op since no accumulator is ever
+// -0); each (list, strand lane) gets a warp, which adds the list through warp_chain_list (exact_chain.cuh): inside a
+// binade of the running sum the chain is an integer sum of per-event increments that the warp takes 256 at a time with
+// one scan; a block that leaves the binade is added the plain way.
+struct EcEventList {   // strand lane `c` of a position's event list {tag, value}
+  const uint2* list; int n; uint32_t c;
+  __device__ __forceinline__ void load(int rel, float (&x)[8]) const {
+    uint2 t[8];
+    ec_load8(list, n, rel, t, make_uint2(1u, 0u));
 #pragma unroll
-    for (int g = 0; g < DEPTH; g++) cur[g] = (uint32_t)(g * 32 + lane) < qn ? __ldcs(&list[g * 32 + lane]) : pad;
-    for (uint32_t off = 0; off < qn; off += 32 * DEPTH) {
-      uint2 nxt[DEPTH];
-#pragma unroll
-      for (int g = 0; g < DEPTH; g++) {
-        const uint32_t e = off + 32 * DEPTH + g * 32 + lane;
-        nxt[g] = e < qn ? __ldcs(&list[e]) : pad;
-      }
-#pragma unroll
-      for (int g = 0; g < DEPTH; g++) {
-        if (off + g * 32 >= qn) break;
-        const float val = __uint_as_float(cur[g].y);
-        stage[wid][0][lane] = cur[g].x == 0u ? val : 0.f;
-        stage[wid][1][lane] = val;
-        stage[wid][2][lane] = cur[g].x == 2u ? val : 0.f;
-        __syncwarp();
-        if (lane < 3) {
-          // the padding of a partial group adds +0.0: harmless, so the chain is always the unrolled one
-          const float4* sv = reinterpret_cast<const float4*>(stage[wid][lane]);
-#pragma unroll
-          for (int u = 0; u < 8; u++) {
-            const float4 y = sv[u];
-            acc = __fadd_rn(acc, y.x); acc = __fadd_rn(acc, y.y); acc = __fadd_rn(acc, y.z); acc = __fadd_rn(acc, y.w);
-          }
-        }
-        __syncwarp();
-      }
-#pragma unroll
-      for (int g = 0; g < DEPTH; g++) cur[g] = nxt[g];
-    }
-    if (lane < 3) v.deep_d[(size_t)rec.x * (3 * STG_TILE_W) + lane * STG_TILE_W + rec.y] = acc;
+    for (int e = 0; e < 8; e++) x[e] = (c == 1u || t[e].x == c) ? __uint_as_float(t[e].y) : 0.f;
   }
+  __device__ __forceinline__ void prefetch(int rel) const { if (rel < n) ec_prefetch_l2(list + rel); }
+};
+
+__global__ void __launch_bounds__(256) deep_long_kernel(DevBatchView v) {
+  const int lane = threadIdx.x & 31;
+  // the few very long lists first, a CTA per (list, strand lane): every warp prepares blocks (cta_chain_list)
+  {
+    __shared__ EcCtaState cst;
+    __shared__ uint32_t ticket;
+    const uint32_t nbig = v.deep_count[2] * 3u;
+    for (;;) {
+      __syncthreads();
+      if (threadIdx.x == 0) ticket = atomicAdd(v.tile_ticket + 4, 1u);
+      __syncthreads();
+      const uint32_t wi = ticket;
+      if (wi >= nbig) break;
+      const uint4 rec = v.deep_long[v.deep_long_cap - 1u - wi / 3u];
+      const EcEventList ld{v.events2 + rec.z, (int)rec.w, wi % 3u};
+      const float acc = cta_chain_list(0.f, ld.n, ec_misalign8(ld.list), ld, cst);
+      if (threadIdx.x == 0) v.deep_d[(size_t)rec.x * (3 * STG_TILE_W) + ld.c * STG_TILE_W + rec.y] = acc;
+    }
+  }
+  const uint32_t nwork = v.deep_count[1] * 3u;
+  for (;;) {
+    uint32_t wi = 0;
+    if (lane == 0) wi = atomicAdd(v.tile_ticket + 2, 1u);
+    wi = __shfl_sync(FULL, wi, 0);
+    if (wi >= nwork) break;
+    const uint4 rec = v.deep_long[wi / 3u];
+    const EcEventList ld{v.events2 + rec.z, (int)rec.w, wi % 3u};
+    const float acc = warp_chain_list(0.f, ld.n, ec_misalign8(ld.list), ld, lane);
+    if (lane == 0) v.deep_d[(size_t)rec.x * (3 * STG_TILE_W) + ld.c * STG_TILE_W + rec.y] = acc;
+  }
+}
+
+// Self-test of warp_chain_add (stg_selftest_chain): one warp per list of a CSR, the list added to s0 in order; PLAIN = the
+// bare chain of dependent adds (the timing baseline).
+template <bool PLAIN>
+__global__ void __launch_bounds__(128) chain_selftest_kernel(int64_t nl, const uint32_t* __restrict__ off, const float* __restrict__ x,
+                                                             const float* __restrict__ s0, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t li = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (li >= nl) return;
+  const float* list = x + off[li];
+  const int n = (int)(off[li + 1] - off[li]);
+  float s = s0[li];
+  if (PLAIN) {
+    for (int j0 = 0; j0 < n; j0 += 32) {
+      const float xv = j0 + lane < n ? list[j0 + lane] : 0.f;
+      const int m = min(32, n - j0);
+      for (int l = 0; l < m; l++) s = __fadd_rn(s, __shfl_sync(FULL, xv, l));
+    }
+  } else {
+    const EcFloatList ld{list, n};
+    s = warp_chain_list(s, n, ec_misalign8(list), ld, lane);
+  }
+  if (lane == 0) out[li] = s;
+}
+
+// ... and of cta_chain_list: one CTA per list
+__global__ void __launch_bounds__(256) chain_selftest_cta_kernel(int64_t nl, const uint32_t* __restrict__ off, const float* __restrict__ x,
+                                                                 const float* __restrict__ s0, float* __restrict__ out) {
+  __shared__ EcCtaState cst;
+  for (int64_t li = blockIdx.x; li < nl; li += gridDim.x) {
+    const EcFloatList ld{x + off[li], (int)(off[li + 1] - off[li])};
+    const float s = cta_chain_list(s0[li], ld.n, ec_misalign8(ld.list), ld, cst);
+    if (threadIdx.x == 0) out[li] = s;
+  }
+}
+
+cudaError_t launch_chain_selftest(int64_t n, const uint32_t* off, const float* x, const float* s0, float* out, int plain, cudaStream_t st) {
+  if (n && plain == 2) {
+    chain_selftest_cta_kernel<<<(unsigned)(n < 4096 ? n : 4096), 256, 0, st>>>(n, off, x, s0, out);
+    return cudaGetLastError();
+  }
+  if (n == 0) return cudaSuccess;
+#ifdef EC_STATS
+  {
+    unsigned long long h[4];
+    cudaMemcpyFromSymbol(h, ec_stats, sizeof h);
+    fprintf(stderr, "ec_stats so far: integer %llu plain %llu (right binade %llu, bad lanes %llu)\n", h[0], h[1], h[2], h[3]);
+  }
+#endif
+  const unsigned grid = (unsigned)((n * 32 + 127) / 128);
+  if (plain) chain_selftest_kernel<true><<<grid, 128, 0, st>>>(n, off, x, s0, out);
+  else chain_selftest_kernel<false><<<grid, 128, 0, st>>>(n, off, x, s0, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_deep_deposit(const DevBatchView& v, int num_sms, cudaStream_t st) {

@@ -9,8 +9,9 @@
 // from first to last — the chain of dependent float adds of one key is the only serial part left.
 #pragma once
 #include <stdint.h>
+#include "exact_chain.cuh"
 #define OS_BATCH 8
-#define OS_CHAIN 8    // groups of 32 values a chain warp keeps in flight
+#define OS_E 8        // consecutive values a lane of a chain warp holds: a block of the chain is 32 * OS_E values
 
 // acc[k] = (...((acc[k] + v_i1) + v_i2) + ...) over the records i1 < i2 < ... of key k, i.e. the reference's "+=" loop
 // over the records in order, for all keys at once.  One CTA; scratch: cnt [W * K] (zeroed), kbase [K + 1], sorted [n].
@@ -83,38 +84,25 @@ __device__ void cta_ordered_keyed_sum(uint32_t n, KeyFn key, ValFn val, uint32_t
     }
   }
   __syncthreads();
-  // 4. one warp per key: its run added in order (every lane carries the same sum).  The values come OS_CHAIN groups of 32
-  //    at a time and the next block is loaded while this one is added: a group costs the chain ~130 cycles, a load from
-  //    L2 / HBM several hundred
+  // 4. one warp per key: its run added in order (every lane carries the same sum), 32 * OS_E values at a time through
+  //    warp_chain_add (exact_chain.cuh): inside a binade of the running sum the chain of dependent adds is an integer sum
+  //    the warp takes with one scan; a block that leaves the binade is added the plain way.  The next block is loaded
+  //    while this one is added.
   for (uint32_t k = w; k < K; k += W) {
     const uint32_t a = kbase[k], z = kbase[k + 1];
     if (a == z) continue;
-    float s = acc[k];
-    float xn[OS_CHAIN];
-#pragma unroll
-    for (int g = 0; g < OS_CHAIN; g++) { const uint32_t i = a + 32u * g + lane; xn[g] = i < z ? sorted[i] : 0.f; }
-    for (uint32_t j0 = a; j0 < z; j0 += 32 * OS_CHAIN) {
-      float x[OS_CHAIN];
-#pragma unroll
-      for (int g = 0; g < OS_CHAIN; g++) {
-        x[g] = xn[g];
-        const uint32_t i = j0 + 32u * (OS_CHAIN + g) + lane;
-        xn[g] = i < z ? sorted[i] : 0.f;
-      }
-#pragma unroll
-      for (int g = 0; g < OS_CHAIN; g++) {
-        const uint32_t g0 = j0 + 32u * g;
-        if (g0 >= z) break;
-        const int m = (int)min(32u, z - g0);
-        if (m == 32) {
-#pragma unroll
-          for (int l = 0; l < 32; l++) s = __fadd_rn(s, __shfl_sync(0xffffffffu, x[g], l));
-        } else {
-          for (int l = 0; l < m; l++) s = __fadd_rn(s, __shfl_sync(0xffffffffu, x[g], l));
-        }
-      }
-    }
+    if (z - a >= EC_CTA_MIN) continue;    // below: the whole CTA
+    const EcFloatList ld{sorted + a, (int)(z - a)};
+    const float s = warp_chain_list(acc[k], ld.n, ec_misalign8(ld.list), ld, lane);
     if (lane == 0) acc[k] = s;
+  }
+  __shared__ EcCtaState cst;
+  for (uint32_t k = 0; k < K; k++) {      // the few long runs, one after the other, every warp preparing blocks (CTA-uniform loop)
+    const uint32_t a = kbase[k], z = kbase[k + 1];
+    if (z - a < EC_CTA_MIN) continue;
+    const EcFloatList ld{sorted + a, (int)(z - a)};
+    const float s = cta_chain_list(acc[k], ld.n, ec_misalign8(ld.list), ld, cst);
+    if (threadIdx.x == 0) acc[k] = s;
   }
 }
 
@@ -131,6 +119,18 @@ struct OrderedSumSmem {
   uint32_t dkey[OS_DENSE_MAX];
   uint32_t cnt[8 * OS_DENSE_MAX]; uint32_t kbase[OS_DENSE_MAX + 1];
   uint32_t ndist; int overflow;
+};
+
+// component C of a float2 list
+template <int C> struct EcFloat2List {
+  const float2* list; int n;
+  __device__ __forceinline__ void load(int rel, float (&x)[8]) const {
+    float2 t[8];
+    ec_load8(list, n, rel, t, make_float2(0.f, 0.f));
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = C ? t[e].y : t[e].x;
+  }
+  __device__ __forceinline__ void prefetch(int rel) const { if (rel < n) ec_prefetch_l2(list + rel); }
 };
 
 template <class KeyFn, class ValFn>
@@ -232,39 +232,23 @@ __device__ bool cta_ordered_keyed_sum2(uint32_t n, KeyFn key, ValFn val, float* 
     const uint32_t a = M.kbase[k], z = M.kbase[k + 1];
     if (a == z) continue;
     const uint32_t real = M.dkey[k];
-    float s0 = acc0[real], s1 = acc1[real];
-    const float2 zero2 = make_float2(0.f, 0.f);
-    float2 xn[OS_CHAIN];
-#pragma unroll
-    for (int g = 0; g < OS_CHAIN; g++) { const uint32_t i = a + 32u * g + lane; xn[g] = i < z ? sorted[i] : zero2; }
-    for (uint32_t j0 = a; j0 < z; j0 += 32 * OS_CHAIN) {
-      float2 x[OS_CHAIN];
-#pragma unroll
-      for (int g = 0; g < OS_CHAIN; g++) {
-        x[g] = xn[g];
-        const uint32_t i = j0 + 32u * (OS_CHAIN + g) + lane;
-        xn[g] = i < z ? sorted[i] : zero2;
-      }
-#pragma unroll
-      for (int g = 0; g < OS_CHAIN; g++) {
-        const uint32_t g0 = j0 + 32u * g;
-        if (g0 >= z) break;
-        const int m = (int)min(32u, z - g0);
-        if (m == 32) {   // unrolled: the shuffles of a group are independent of the two chains of adds and run ahead of them
-#pragma unroll
-          for (int l = 0; l < 32; l++) {
-            s0 = __fadd_rn(s0, __shfl_sync(0xffffffffu, x[g].x, l));
-            s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, x[g].y, l));
-          }
-        } else {
-          for (int l = 0; l < m; l++) {
-            s0 = __fadd_rn(s0, __shfl_sync(0xffffffffu, x[g].x, l));
-            s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, x[g].y, l));
-          }
-        }
-      }
-    }
+    if (z - a >= EC_CTA_MIN) continue;    // below: the whole CTA
+    const float2* list = sorted + a;
+    const int n = (int)(z - a), mis = ec_misalign8(list);
+    const float s0 = warp_chain_list(acc0[real], n, mis, EcFloat2List<0>{list, n}, lane);
+    const float s1 = warp_chain_list(acc1[real], n, mis, EcFloat2List<1>{list, n}, lane);
     if (lane == 0) { acc0[real] = s0; acc1[real] = s1; }
+  }
+  __shared__ EcCtaState cst;
+  for (uint32_t k = 0; k < K; k++) {      // the few long runs: every warp prepares blocks (CTA-uniform loop)
+    const uint32_t a = M.kbase[k], z = M.kbase[k + 1];
+    if (z - a < EC_CTA_MIN) continue;
+    const uint32_t real = M.dkey[k];
+    const float2* list = sorted + a;
+    const int n = (int)(z - a), mis = ec_misalign8(list);
+    const float s0 = cta_chain_list(acc0[real], n, mis, EcFloat2List<0>{list, n}, cst);
+    const float s1 = cta_chain_list(acc1[real], n, mis, EcFloat2List<1>{list, n}, cst);
+    if (threadIdx.x == 0) { acc0[real] = s0; acc1[real] = s1; }
   }
   __syncthreads();
   return true;

@@ -620,7 +620,7 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
   AL(r_ivl_cnt, h->n_reads + 1 + 16); AL(scan_state, (h->n_reads + 1) / 4096 + 2);
   d->scan_capacity = std::max<int64_t>(std::max<int64_t>(h->n_reads + 1, v.n_tiles + 1), v.n_rounds + 1);
   AL(scan_partials, scan_partials_needed(d->scan_capacity));
-  AL(tile_carry, v.n_tiles * 4); AL(tile_ticket, 4); AL(deep_count, 2); AL(err_flag, 1);
+  AL(tile_carry, v.n_tiles * 4); AL(tile_ticket, 6); AL(deep_count, 4); AL(err_flag, 1);
   AL(round_off, v.n_rounds + 1); AL(round_cur, v.n_rounds + 1);
   AL(tile_plan, v.n_tiles); AL(tile_evoff, v.n_tiles + 1); AL(tile_lastne, v.n_tiles); AL(junc_anchor, h->n_juncs);
   AL(bpcov, 3 * v.total_pos);
@@ -670,6 +670,7 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   }
   if (v.n_tiles) CK(ctx, cudaMemsetAsync(v.tile_carry, 0xff, sizeof(unsigned long long) * 4 * (size_t)v.n_tiles, st));
   CK(ctx, cudaMemsetAsync(v.tile_ticket, 0, 3 * sizeof(uint32_t), st));
+  CK(ctx, cudaMemsetAsync(v.tile_ticket + 4, 0, 2 * sizeof(uint32_t), st));
   CK(ctx, cudaMemsetAsync(v.err_flag, 0, sizeof(uint32_t), st));
   { Scope s(ctx, "junc_anchor", 1); CK(ctx, launch_junc_anchor(v, kp, st)); }
   { Scope s(ctx, "expand_count+junction_support", 1); CK(ctx, launch_expand_count(v, st)); }
@@ -700,7 +701,7 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
     const int64_t dcap = 2 * cap / STG_DEEP_EVENTS + 1;
     if ((rc = dev_alloc(ctx, d, &v.ivl, cap)) || (rc = dev_alloc(ctx, d, &v.events, 2 * cap)) ||
         (rc = dev_alloc(ctx, d, &v.events2, 2 * cap)) || (rc = dev_alloc(ctx, d, &v.deep_list, dcap)) ||
-        (rc = dev_alloc(ctx, d, &v.deep_d, dcap * 3 * STG_TILE_W)) || (rc = dev_alloc(ctx, d, &v.deep_long, 2 * cap / 64 + 1)) ||
+        (rc = dev_alloc(ctx, d, &v.deep_d, dcap * 3 * STG_TILE_W)) || (rc = dev_alloc(ctx, d, &v.deep_long, 2 * cap / 64 + 1)) || ((v.deep_long_cap = (uint32_t)(2 * cap / 64 + 1)), 0) ||
         (rc = dev_alloc(ctx, d, &v.ch_tlo, ccap)) || (rc = dev_alloc(ctx, d, &v.ch_thi, ccap)) ||
         (rc = dev_alloc(ctx, d, &v.ch_pmax_thi, ccap)) || (rc = dev_alloc(ctx, d, &v.ch_smin_tlo, ccap)) ||
         (rc = dev_alloc(ctx, d, &v.ch_row_off, ccap + 1)))
@@ -941,6 +942,38 @@ int stg_find_trims(stg_ctx* ctx, const stg_dbatch* d, int64_t n, const int32_t* 
     CK(ctx, small_d2h(ctx, is_start, dt, tot, st));
   }
   CK(ctx, small_sync(ctx, st));
+  return STG_OK;
+}
+
+// Self-test of the integer form of ordered float sums (exact_chain.cuh): list i = x[off[i] .. off[i+1]) added to s0[i] in
+// order by one warp; the result must carry the bits of the plain loop.
+int stg_selftest_chain(stg_ctx* ctx, int64_t n, const uint32_t* off, const float* x, const float* s0, float* out, int plain, float* kernel_ms) {
+  if (!ctx || n < 0 || (n && (!off || !s0 || !out))) return fail(ctx, STG_EINVAL, "stg_selftest_chain: bad argument");
+  if (n == 0) return STG_OK;
+  if (off[0] != 0) return fail(ctx, STG_EINVAL, "stg_selftest_chain: off[0] must be 0");
+  for (int64_t i = 0; i < n; i++) if (off[i + 1] < off[i]) return fail(ctx, STG_EINVAL, "stg_selftest_chain: offsets must not decrease");
+  const int64_t tot = off[n];
+  if (tot && !x) return fail(ctx, STG_EINVAL, "stg_selftest_chain: bad argument");
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  StageScope stage_scope(ctx);
+  stg_dbatch tmp;
+  struct Release { stg_ctx* c; stg_dbatch* t; ~Release() { cudaStreamSynchronize(c->stream); free_batch_allocs(c, t); } } release{ctx, &tmp};
+  uint32_t* doff = nullptr; float *dx = nullptr, *ds = nullptr, *dout = nullptr;
+  int rc = STG_OK;
+  if ((rc = dev_alloc(ctx, &tmp, &doff, n + 1)) || (rc = dev_alloc(ctx, &tmp, &dx, tot + 1)) || (rc = dev_alloc(ctx, &tmp, &ds, n)) ||
+      (rc = dev_alloc(ctx, &tmp, &dout, n))) return rc;
+  CK(ctx, cudaMemcpyAsync(doff, off, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (tot) CK(ctx, cudaMemcpyAsync(dx, x, (size_t)tot * 4, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(ds, s0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  ctx->launches++;
+  cudaEvent_t e0 = take_event(ctx), e1 = take_event(ctx);
+  CK(ctx, cudaEventRecord(e0, st));
+  CK(ctx, launch_chain_selftest(n, doff, dx, ds, dout, plain, st));
+  CK(ctx, cudaEventRecord(e1, st));
+  CK(ctx, cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  if (kernel_ms) CK(ctx, cudaEventElapsedTime(kernel_ms, e0, e1));
   return STG_OK;
 }
 

@@ -77,7 +77,8 @@ struct DevBatchView {
   uint4* deep_list;            // [deep_cap]  {tile id, first event, events, -} of every deep sub-tile
   float* deep_d;               // [deep_cap * 3 * STG_TILE_W] their finished difference arrays
   uint4* deep_long;            // [long_cap]  {deep slot, position, first event in events2, events} of every long list
-  uint32_t* deep_count;        // [2] deep sub-tiles, long lists
+  uint32_t* deep_count;        // [4] deep sub-tiles, long lists, very long lists (stored from the far end of deep_long)
+  uint32_t deep_long_cap;      // entries of deep_long
   uint32_t* scan_partials;     // scratch for the 3-phase scans
   uint8_t* junc_anchor;        // [n_juncs] anchor length each junction demands (10 or 25, rlink.cpp:16991-16997)
   uint32_t* round_off;         // [n_rounds+1] tiles with events per round, then exclusive prefix: first ticket of the
@@ -86,7 +87,7 @@ struct DevBatchView {
   TileRec* tile_plan;          // [n_tiles] [0, n_main): tiles with events in ticket order; [n_main, n_tiles): the rest
   unsigned long long* tile_carry;  // [n_tiles*4] per strand lane (c | bs << 32) after the last position of a
                                //             sub-tile with events; all-ones until published (bundle-major tile id)
-  uint32_t* tile_ticket;       // [4] work counters: cov_tile_kernel, deep_deposit_kernel, deep_long_kernel, scan blocks
+  uint32_t* tile_ticket;       // [6] work counters: cov_tile_kernel, deep_deposit_kernel, deep_long_kernel, scan blocks, very long lists
   // outputs
   float* bpcov;                // [3*total_pos]: bundle b lane s index i at 3*b_gbase[b] + s*b_stride[b] + i
   double *j_nreads_good, *j_leftsupport, *j_rightsupport;  // [n_juncs]
@@ -239,6 +240,7 @@ cudaError_t launch_bin_columns(const DevBatchView& v, cudaStream_t st);     // +
 cudaError_t launch_bin_scatter(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_junc_anchor(const DevBatchView& v, const KernelParams& p, cudaStream_t st);
 cudaError_t launch_tile_plan(const DevBatchView& v, cudaStream_t st);
+cudaError_t launch_chain_selftest(int64_t n, const uint32_t* off, const float* x, const float* s0, float* out, int plain, cudaStream_t st);
 cudaError_t launch_deep_deposit(const DevBatchView& v, int num_sms, cudaStream_t st);
 cudaError_t launch_cov_tiles(const DevBatchView& v, int num_sms, cudaStream_t st);
 cudaError_t launch_cov_fill(const DevBatchView& v, int num_sms, cudaStream_t st);

@@ -26,7 +26,7 @@ EXPORTS = [
     "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_trims_capacity", "stg_find_trims", "stg_infer_transcripts", "stg_infer_transcripts_batch",
     "stg_build_groups", "stg_groups_array_info", "stg_fetch_groups_array", "stg_neutral_predictions",
     "stg_assemble", "stg_asm_array_info", "stg_fetch_asm_array", "stg_rewind", "stg_reduce_totals",
-    "stg_shard_assign", "stg_set_profiling", "stg_kernel_count", "stg_kernel_time", "stg_launch_counter", "stg_batch_stats", "stg_stream",
+    "stg_shard_assign", "stg_selftest_chain", "stg_set_profiling", "stg_kernel_count", "stg_kernel_time", "stg_launch_counter", "stg_batch_stats", "stg_stream",
 ]
 
 
@@ -118,6 +118,7 @@ def load_library() -> C.CDLL:
     L.stg_asm_array_info.argtypes = [vp, C.c_int, c_i64p, C.POINTER(C.c_int32)]
     L.stg_fetch_asm_array.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
     L.stg_rewind.argtypes = [vp, vp]
+    L.stg_selftest_chain.argtypes = [vp, C.c_int64, C.POINTER(C.c_uint32), c_f32p, c_f32p, c_f32p, C.c_int, c_f32p]
     L.stg_reduce_totals.argtypes = [vp, vp, vp]
     L.stg_shard_assign.argtypes = [C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
                                    C.POINTER(C.c_int32), c_f64p]
@@ -266,6 +267,16 @@ class Engine:
         sel = np.concatenate([np.arange(int(cap_off[i]), int(cap_off[i]) + int(cnt[i])) for i in range(n)]) if n else np.zeros(0, int)
         sel = sel.astype(np.int64)
         return off, pos[sel], ab[sel], st[sel]
+
+    def selftest_chain(self, off, x, s0, plain=False, want_ms=False):
+        """Ordered float32 sums of the CSR lists (stg_selftest_chain): the kernels' integer form of the addition chain."""
+        off = np.ascontiguousarray(off, dtype=np.uint32); x = np.ascontiguousarray(x, dtype=np.float32)
+        s0 = np.ascontiguousarray(s0, dtype=np.float32)
+        out = np.zeros(s0.size, np.float32)
+        ms = C.c_float(0.0)
+        self._ck(self.L.stg_selftest_chain(self.ctx, s0.size, off.ctypes.data_as(C.POINTER(C.c_uint32)), x.ctypes.data_as(c_f32p),
+                                           s0.ctypes.data_as(c_f32p), out.ctypes.data_as(c_f32p), int(plain), C.byref(ms)))
+        return (out, ms.value) if want_ms else out
 
     # ---- rows a8 + a9 -------------------------------------------------------------------------------------
     def build_groups(self, batch: DeviceBatch):
