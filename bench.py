@@ -313,13 +313,16 @@ def main():
                 cov_host = None
                 config["e2e_bpcov"] = f"not copied back (pinned allocation failed: {ex})"
         d2h = [0]
+        strand_bundles = [0]
 
         from concurrent.futures import ThreadPoolExecutor
         uploader = ThreadPoolExecutor(1)   # stg_upload of batch i+1 (validation + H2D on the copy-in stream) beside batch i
 
+        lane_floats = (cov_host.numel() // 3) if cov_host is not None else 0
+
         def start_cov_copy(b):
-            if cov_host is not None:
-                eng.fetch_bpcov_all_begin(b, cov_host.data_ptr())   # copy-out stream: overlaps the group / assembly stages
+            if cov_host is not None:   # lane 1 of every bundle, on the copy-out stream: overlaps the group / assembly stages
+                eng.fetch_bpcov_lane_begin(b, 1, cov_host.data_ptr() + 4 * lane_floats)
 
         phases = {}
 
@@ -338,8 +341,17 @@ def main():
             nbytes = sum(x.nbytes for x in p.values()) + sum(x.nbytes for x in n.values()) + nf.nbytes + fl.nbytes
             t = tick("fetch_predictions", t)
             if cov_host is not None:
+                # the strand lanes, for the bundles whose predictions make printResults read them (rlink.cpp:18453-18459)
+                need = eng.strand_lane_bundles(b)
+                off, _, _ = b.layout()
+                lens = arrays["b_end"].astype(np.int64) - arrays["b_start"].astype(np.int64) + 3
+                for bb in need:
+                    for ln in (0, 2):
+                        eng.fetch_bpcov_bundle_lane(b, int(bb), ln, cov_host.data_ptr() + 4 * (ln * lane_floats + int(off[bb])))
+                    nbytes += 8 * int(lens[bb])
+                strand_bundles[0] = int(need.size)
                 eng.fetch_wait(b)
-                nbytes += cov_host.numel() * 4
+                nbytes += lane_floats * 4
             t = tick("wait_bpcov_copy", t)
             d2h[0] = nbytes
             b.free()
@@ -378,11 +390,14 @@ def main():
                "single_batch_ms": 1e3 * single,
                "host_phases_ms_per_step": {k: 1e3 * v / n_e2e for k, v in phases.items()},
                "bpcov_copied_back": cov_host is not None,
+               "bpcov_lanes": "lane 1 of every bundle + lanes 0 / 2 of the %d bundles holding a single-exon prediction with a strand "
+                              "(the only place the reference's printResults reads them: rlink.cpp:18453-18459, :18524-18531)" % strand_bundles[0],
                "timing": "host wall clock around n batches, each: stg_upload (validation + H2D of every input array from pinned "
                          "memory, on the copy-in stream) + stg_run + stg_build_groups + stg_neutral_predictions + stg_assemble + D2H of "
                          "BundleData::pred (neutral and graph predictions with exons), num_fragments, frag_len and — unless "
-                         "--e2e-no-bpcov — the whole of bpcov into pinned host memory (the reference's printResults, which stays on "
-                         "the host, reads it; the copy runs on the copy-out stream from the end of the coverage stage) + "
+                         "--e2e-no-bpcov — bpcov into pinned host memory: strand lane 1 of every bundle (the reference's printResults, which "
+                         "stays on the host, reads it; the copy runs on the copy-out stream from the end of the coverage stage) and "
+                         "lanes 0 / 2 of the bundles whose predictions make printResults read them + "
                          "stg_free_batch.  The upload of batch i+1 is issued while batch i computes, as the bundle queue of the "
                          "host does; every H2D and D2H byte of the n batches is inside the timed region.  single_batch_ms is one "
                          "batch alone (nothing to overlap its upload with).  Max over ranks"}

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define STG_ABI_VERSION 4 /* 2: stg_build_groups, stg_neutral_predictions, stg_find_trims and the groups array fetch */
+#define STG_ABI_VERSION 5 /* 2: stg_build_groups, stg_neutral_predictions, stg_find_trims and the groups array fetch */
 #define STG_BSIZE 10000 /* rlink.cpp:11 — block size of the blocked prefix sums in bpcov */
 
 enum {
@@ -175,7 +175,9 @@ int stg_trim(stg_ctx* ctx);                            /* release the pooled dev
 
 /* Outputs of the coverage / junction-support stage (count_good_junctions, rlink.cpp:16656-17136).
  * bpcov layout in HBM: for bundle b, lane s in {0:-, 1:all, 2:+}, index i in [0, len_b) with
- * len_b = end-start+3 (rlink.cpp:16875): element cov_off[b] + s*stride[b] + i  (float32).             */
+ * len_b = end-start+3 (rlink.cpp:16875): element cov_off[b] + s*stride[b] + i  (float32).  Since ABI 5 the strand lanes
+ * are batch-wide: stride[b] = total_floats / 3 for every bundle, i.e. lane 1 of all bundles is ONE contiguous block —
+ * the part of bpcov the host needs back in full (stg_fetch_bpcov_lane_begin).                            */
 int stg_cov_layout(const stg_dbatch* batch, int64_t* cov_off /*[n_bundles]*/, int64_t* stride /*[n_bundles]*/,
                    int64_t* total_floats);
 int stg_fetch_bpcov(stg_ctx* ctx, const stg_dbatch* batch, int64_t bundle, float* out /*[3*len_b], lane-major*/);
@@ -185,6 +187,14 @@ int stg_fetch_bpcov_all(stg_ctx* ctx, const stg_dbatch* batch, float* out /*[tot
  * writes bpcov.  `out` (pinned, or the copy is staged) is complete after stg_fetch_wait; stg_free_batch and a second
  * stg_run of the batch wait for it too. */
 int stg_fetch_bpcov_all_begin(stg_ctx* ctx, stg_dbatch* batch, float* out /*[total_floats]*/);
+/* One strand lane of every bundle (total_floats / 3 floats; bundle b at cov_off[b]) on the copy-out stream, like
+ * stg_fetch_bpcov_all_begin.  After infer_transcripts the reference reads lane 1 everywhere (get_cov(1, ...) in
+ * print_predcluster) and lanes 0 / 2 only in the strand check of single-exon predictions that carry a strand
+ * (rlink.cpp:18453-18459, :18524-18531): a host copies lane 1 in full and the strand lanes of the bundles
+ * stg_strand_lane_bundles names (after stg_assemble), one bundle at a time. */
+int stg_fetch_bpcov_lane_begin(stg_ctx* ctx, stg_dbatch* batch, int lane, float* out /*[total_floats / 3]*/);
+int stg_fetch_bpcov_bundle_lane(stg_ctx* ctx, const stg_dbatch* batch, int64_t bundle, int lane, float* out /*[len_b]*/);
+int stg_strand_lane_bundles(stg_ctx* ctx, const stg_dbatch* batch, int64_t cap, int64_t* bundles /*[cap]*/, int64_t* n);
 int stg_fetch_wait(stg_ctx* ctx, stg_dbatch* batch);
 const float* stg_device_bpcov(const stg_dbatch* batch); /* device pointer (for consumers that stay on the GPU) */
 /* CJunction::nreads_good / leftsupport / rightsupport after the stage; each [n_juncs] */
@@ -334,6 +344,11 @@ typedef struct stg_bundle_result {
   const uint32_t* p_exon_off;                  /* [n_pred+1] */
   const uint32_t *e_start, *e_end;             /* CPrediction::exons */
   const float* e_cov;                          /* CPrediction::exoncov */
+  /* ---- ABI 5 ---- */
+  int32_t strand_lanes;    /* out: 1 if lanes 0 and 2 of `bpcov` were filled.  Always with assemble == 0.  With assemble != 0 lane 1
+                            * ([len, 2*len)) is always filled and the strand lanes only for a bundle that holds a single-exon prediction
+                            * carrying a strand: the one place the reference reads them after infer_transcripts (the strand check of
+                            * print_predcluster, rlink.cpp:18453-18459 and :18524-18531); otherwise they are left untouched. */
 } stg_bundle_result;
 int stg_infer_transcripts(stg_ctx* ctx, const stg_bundle_view* view, stg_bundle_result* result);
 /* The same for n bundles in ONE device batch (what a host does that collects the bundles of its worker threads, or of its

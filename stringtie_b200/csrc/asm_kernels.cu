@@ -100,8 +100,8 @@ __device__ __forceinline__ void make_graph_src(const DevBatchView& v, const Grou
   const int s = A.g_s[gi];
   L = lane_base(g, b, 2 * s);
   k = L.base + (size_t)A.g_k[gi];
-  const float* base = v.bpcov + 3 * (size_t)v.b_gbase[b];
-  const uint32_t stride = v.b_stride[b];
+  const float* base = v.bpcov + v.b_gbase[b];
+  const size_t stride = v.cov_pitch;
   G.s = s; G.refstart = (uint32_t)v.b_start[b]; G.covlen = v.b_len[b];
   G.c_all = base + stride; G.c_opp = base + (size_t)(2 - 2 * s) * stride;
   G.bn_start = g.bn_start + L.base; G.bn_end = g.bn_end + L.base; G.bn_next = g.bn_next + L.base;

@@ -1007,7 +1007,7 @@ __global__ void __launch_bounds__(STG_TILE_WARPS * 32, 1) cov_tile_kernel(DevBat
     const uint32_t stride = __shfl_sync(FULL, recw, 4), npos = __shfl_sync(FULL, recw, 5);
     const uint32_t tile_id = __shfl_sync(FULL, recw, 6), wait_tile = __shfl_sync(FULL, recw, 7);
     const uint32_t to_reset = (STG_BSIZE - i0 % STG_BSIZE) % STG_BSIZE;  // in-tile position where idx % BSIZE == 0
-    float* out = v.bpcov + 3 * (size_t)gbase + i0;
+    float* out = v.bpcov + (size_t)gbase + i0;           // strand lane s of the batch starts at s * cov_pitch
     const uint32_t n4 = min((uint32_t)TW, stride - i0) / 4;              // float4 per lane incl. the zero padding
 
     const bool deep = (nev_raw & 0x80000000u) != 0u;     // difference array precomputed by deep_deposit_kernel
@@ -1044,7 +1044,7 @@ __global__ void __launch_bounds__(STG_TILE_WARPS * 32, 1) cov_tile_kernel(DevBat
       for (int s = 0; s < 3; s++) {
         const uint32_t fm = __shfl_sync(FULL, fillmask, s);
         const float4* src = reinterpret_cast<const float4*>(d + s * TWS);
-        float4* dst = reinterpret_cast<float4*>(out + (size_t)s * stride);
+        float4* dst = reinterpret_cast<float4*>(out + (size_t)s * v.cov_pitch);
         for (uint32_t q = lane; q < n4; q += 32) {
           float4 x;
           if ((fm >> (q >> 3)) & 1u) { const float f = fills[s * TNW + (q >> 3)]; x = make_float4(f, f, f, f); }
@@ -1224,7 +1224,7 @@ __global__ void __launch_bounds__(256) cov_fill_kernel(DevBatchView v) {
     const uint32_t stride = __shfl_sync(FULL, recw, 4), npos = __shfl_sync(FULL, recw, 5);
     const uint32_t tile_id = __shfl_sync(FULL, recw, 6), wait_tile = __shfl_sync(FULL, recw, 7);
     const uint32_t to_reset = (STG_BSIZE - i0 % STG_BSIZE) % STG_BSIZE;  // in-tile position where idx % BSIZE == 0
-    float* out = v.bpcov + 3 * (size_t)gbase + i0;
+    float* out = v.bpcov + (size_t)gbase + i0;
     const uint32_t n4 = min((uint32_t)TW, stride - i0) / 4;              // float4 per lane incl. the zero padding
     // state before the first position: from the nearest earlier sub-tile with events, advanced over the gap
     float c = 0.f, bs = 0.f;
@@ -1249,7 +1249,7 @@ __global__ void __launch_bounds__(256) cov_fill_kernel(DevBatchView v) {
 #pragma unroll
       for (int s = 0; s < 3; s++) {
         const float bv = s == 0 ? b0 : (s == 1 ? b1 : b2);
-        float* dst = out + (size_t)s * stride;
+        float* dst = out + (size_t)s * v.cov_pitch;
         if (bv == 0.f || lim == 0u) {
           if (lane == 0) bulk_store(dst, zero_row, n4 * 16u);
         } else {
@@ -1272,7 +1272,7 @@ __global__ void __launch_bounds__(256) cov_fill_kernel(DevBatchView v) {
       for (int s = 0; s < 3; s++) {
         const float cs = __shfl_sync(FULL, c, s);
         float bss = __shfl_sync(FULL, bs, s);
-        float* dl = out + (size_t)s * stride;
+        float* dl = out + (size_t)s * v.cov_pitch;
         if (to_reset < npos) {
           fill_run(dl, 0, to_reset, cs, bss, lane);
           bss = 0.f;
@@ -1343,11 +1343,10 @@ __global__ void query_cov_kernel(DevBatchView v, int64_t n, const int32_t* __res
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int32_t b = bundle[i];
-  const float* base = v.bpcov + 3 * (size_t)v.b_gbase[b];
-  const uint32_t stride = v.b_stride[b];
+  const float* base = v.bpcov + v.b_gbase[b];
   const int s = lane[i];
-  if (!sign) out[i] = dev_get_cov(base + (size_t)s * stride, start[i], end[i]);
-  else out[i] = dev_get_cov_sign(base + stride, base + (size_t)(2 - s) * stride, start[i], end[i]);
+  if (!sign) out[i] = dev_get_cov(base + (size_t)s * v.cov_pitch, start[i], end[i]);
+  else out[i] = dev_get_cov_sign(base + v.cov_pitch, base + (size_t)(2 - s) * v.cov_pitch, start[i], end[i]);
 }
 
 cudaError_t launch_query_cov(const DevBatchView& v, int64_t n, const int32_t* bundle, const int8_t* lane,
@@ -1363,7 +1362,7 @@ __global__ void cov_totals_kernel(DevBatchView v) {
   if (i >= v.n_bundles * 3) return;
   const int64_t b = i / 3;
   const int s = (int)(i % 3);
-  const float* base = v.bpcov + 3 * (size_t)v.b_gbase[b] + (size_t)s * v.b_stride[b];
+  const float* base = v.bpcov + (size_t)s * v.cov_pitch + v.b_gbase[b];
   v.b_cov_total[i] = dev_get_cov(base, 0u, v.b_len[b] - 2u);
 }
 

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(32 * GROUPS_WARPS, MINB) groups_walk_kernel(De
   S.curr.fill(-1); S.startg.fill(-1);
   S.junctionsupport = prm.junctionsupport; S.bundledist = g.bundledist;
   S.refstart = v.b_start[b]; S.len = v.b_len[b];
-  S.c1 = v.bpcov + 3 * (size_t)v.b_gbase[b] + v.b_stride[b];
+  S.c1 = v.bpcov + v.cov_pitch + v.b_gbase[b];
   S.prm = prm; S.err = 0;
   if (gcap == 0 || gcap > 0x7fffffffu) { if (!tid) atomicOr(v.err_flag, STG_GERR_GROUPS); return; }
   bool in_smem = true;
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel
   S.curr.fill(-1); S.startg.fill(-1);
   S.junctionsupport = prm.junctionsupport; S.bundledist = g.bundledist;
   S.refstart = v.b_start[b]; S.len = v.b_len[b];
-  S.c1 = v.bpcov + 3 * (size_t)v.b_gbase[b] + v.b_stride[b];
+  S.c1 = v.bpcov + v.cov_pitch + v.b_gbase[b];
   S.prm = prm; S.err = 0;
   ClusterCtl* ctl = (ClusterCtl*)g.cl_ctl + cid;
   FastRec* R = g.cl_rec + (size_t)cid * CLUSTER_WINDOW;

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(32 * JUNC_WARPS) junc_pass_kernel(DevBatchView
   if (n == 0) return;
   const int64_t refstart = v.b_start[b];
   const int64_t len = v.b_len[b];
-  const float* __restrict__ c1 = v.bpcov + 3 * (size_t)v.b_gbase[b] + v.b_stride[b];   // lane 1
+  const float* __restrict__ c1 = v.bpcov + v.cov_pitch + v.b_gbase[b];   // lane 1
   JView J;
   J.start = v.j_start + j0; J.end = v.j_end + j0; J.strand = v.jp_strand + j0; J.guide_match = v.j_guide_match + j0;
   J.nreads = v.jp_nreads + j0; J.nreads_good = v.jp_nreads_good + j0; J.left = v.jp_left + j0; J.right = v.jp_right + j0;

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(128) neutral_preds_kernel(DevBatchView v, Grou
   if (b >= v.n_bundles) return;
   const uint32_t r0 = nv.reg_off[b], nr = nv.reg_cnt[b];
   const int64_t refstart = v.b_start[b];
-  const float* __restrict__ c1 = v.bpcov + 3 * (size_t)v.b_gbase[b] + v.b_stride[b];
+  const float* __restrict__ c1 = v.bpcov + v.cov_pitch + v.b_gbase[b];
   const size_t out0 = (size_t)nv.cap_off[r0] + r0;
   uint32_t np = 0;
   int geneno = 0, t = 1;

@@ -126,8 +126,8 @@ struct stg_builder {
 struct stg_dbatch {
   DevBatchView v;
   std::vector<PoolBlock> allocs;   // every device block this batch holds (returned to the context pool on free)
-  std::vector<int64_t> h_cov_off;  // [n_bundles] float offset of lane 0 of bundle b (= 3*gbase)
-  std::vector<int64_t> h_stride;   // [n_bundles]
+  std::vector<int64_t> h_cov_off;  // [n_bundles] float offset of lane 0 of bundle b (= gbase)
+  std::vector<int64_t> h_stride;   // [n_bundles] distance between the strand lanes of bundle b (= total_pos: the lanes are batch-wide)
   std::vector<uint32_t> h_len;
   std::vector<int32_t> h_start;    // [n_bundles] BundleData::start
   int64_t ivl_capacity = 0;     // intervals the interval / event / chunk arrays can hold
@@ -571,7 +571,7 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
     const uint64_t s = (l + STG_LANE_ALIGN - 1) / STG_LANE_ALIGN * STG_LANE_ALIGN;
     if (l >= 0x7fffffffull) { delete d; return fail(ctx, STG_ERANGE, "bundle span too large"); }
     len[b] = (uint32_t)l; stride[b] = (uint32_t)s; gbase[b] = (uint32_t)g; tile_off[b] = (uint32_t)t;
-    d->h_cov_off[b] = (int64_t)(3 * g); d->h_stride[b] = (int64_t)s; d->h_len[b] = (uint32_t)l; d->h_start[b] = h->b_start[b];
+    d->h_cov_off[b] = (int64_t)g; d->h_stride[b] = 0; d->h_len[b] = (uint32_t)l; d->h_start[b] = h->b_start[b];
     d->sum_len += (int64_t)l;
     d->h_nreads.push_back(h->b_read_off[b + 1] - h->b_read_off[b]);
     g += s; t += (l + STG_TILE_W - 1) / STG_TILE_W;
@@ -579,6 +579,8 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
   }
   gbase[nb] = (uint32_t)g; tile_off[nb] = (uint32_t)t;
   v.total_pos = (int64_t)g; v.n_tiles = (int64_t)t;
+  v.cov_pitch = (size_t)g;
+  for (int64_t b = 0; b < nb; b++) d->h_stride[b] = (int64_t)g;
   // rounds of the tile schedule (tile_plan_kernel): at least the sub-tile count of the longest bundle
   {
     uint32_t max_nt = 1;
@@ -802,6 +804,53 @@ int stg_fetch_bpcov_all_begin(stg_ctx* ctx, stg_dbatch* d, float* out) {
   CK(ctx, cudaStreamWaitEvent(ctx->out_stream, d->ev_cov, 0));
   d->out_pending = true;
   CK(ctx, copy_chunked(out, d->v.bpcov, sizeof(float) * 3 * (size_t)d->v.total_pos, cudaMemcpyDeviceToHost, ctx->out_stream));
+  return STG_OK;
+}
+
+int stg_fetch_bpcov_lane_begin(stg_ctx* ctx, stg_dbatch* d, int lane, float* out) {
+  if (!ctx || !d || !out || lane < 0 || lane > 2) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_lane_begin: bad argument");
+  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_lane_begin: batch has not been run");
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaStreamWaitEvent(ctx->out_stream, d->ev_cov, 0));
+  d->out_pending = true;
+  CK(ctx, copy_chunked(out, d->v.bpcov + (size_t)lane * d->v.cov_pitch, sizeof(float) * (size_t)d->v.total_pos, cudaMemcpyDeviceToHost, ctx->out_stream));
+  return STG_OK;
+}
+
+int stg_fetch_bpcov_bundle_lane(stg_ctx* ctx, const stg_dbatch* d, int64_t b, int lane, float* out) {
+  if (!ctx || !d || !out || b < 0 || b >= d->v.n_bundles || lane < 0 || lane > 2)
+    return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_bundle_lane: bad argument");
+  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_bundle_lane: batch has not been run");
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaMemcpyAsync(out, d->v.bpcov + (size_t)lane * d->v.cov_pitch + d->h_cov_off[b], sizeof(float) * (size_t)d->h_len[b],
+                          cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return STG_OK;
+}
+
+// Bundles whose strand lanes (bpcov[0], bpcov[2]) the reference's printResults reads: the only place is the strand check of
+// a single-exon prediction that carries a strand (rlink.cpp:18453-18459 and :18524-18531); every other use of bpcov after
+// infer_transcripts goes to lane 1.
+int stg_strand_lane_bundles(stg_ctx* ctx, const stg_dbatch* d, int64_t cap, int64_t* bundles, int64_t* n_out) {
+  if (!ctx || !d || !n_out || cap < 0 || (cap && !bundles)) return fail(ctx, STG_EINVAL, "stg_strand_lane_bundles: bad argument");
+  if (!d->assembled) return fail(ctx, STG_EINVAL, "stg_strand_lane_bundles: batch has not been assembled");
+  const int64_t nb = d->v.n_bundles, np = d->av.n_pred;
+  *n_out = 0;
+  if (np == 0) return STG_OK;
+  std::vector<uint32_t> poff(nb + 1), xo(np + 1);
+  std::vector<int8_t> st(np);
+  int rc = stg_fetch_asm_array(ctx, d, STG_AA_PRED_OFF, 0, nb + 1, poff.data());
+  if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_STRAND, 0, np, st.data());
+  if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_EXON_OFF, 0, np + 1, xo.data());
+  if (rc) return rc;
+  int64_t k = 0;
+  for (int64_t b = 0; b < nb; b++) {
+    bool need = false;
+    for (uint32_t q = poff[b]; q < poff[b + 1] && !need; q++) need = xo[q + 1] - xo[q] == 1 && st[q] != '.';
+    if (need) { if (k < cap) bundles[k] = b; k++; }
+  }
+  *n_out = k;
+  if (k > cap) return fail(ctx, STG_ERANGE, "stg_strand_lane_bundles: more bundles than the caller's array holds");
   return STG_OK;
 }
 
@@ -1562,13 +1611,23 @@ int stg_infer_transcripts_batch(stg_ctx* ctx, int64_t n, const stg_bundle_view* 
   if (n == 0) return STG_OK;
   if (!(rc = stg_builder_packed(b, &pb)) && !(rc = stg_upload(ctx, &pb, &d)) && !(rc = stg_run(ctx, d))) {
     // bpcov and the junction support of every bundle that asked for them: the copies are queued together, one wait
-    for (int64_t i = 0; i < n && !rc; i++)
+    // (a bundle that goes on to the assembly gets lane 1 now and its strand lanes only if a prediction will make the host
+    // read them: stg_strand_lane_bundles)
+    for (int64_t i = 0; i < n && !rc; i++) {
+      results[i].strand_lanes = 0;
       if (results[i].bpcov) {
         const size_t len = d->h_len[i];
-        if (cudaMemcpy2DAsync(results[i].bpcov, len * sizeof(float), d->v.bpcov + d->h_cov_off[i], (size_t)d->h_stride[i] * sizeof(float),
-                              len * sizeof(float), 3, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-          rc = fail(ctx, STG_ECUDA, "stg_infer_transcripts_batch: copy of bpcov failed");
+        cudaError_t ce;
+        if (results[i].assemble)
+          ce = cudaMemcpyAsync(results[i].bpcov + len, d->v.bpcov + d->v.cov_pitch + d->h_cov_off[i], len * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        else {
+          ce = cudaMemcpy2DAsync(results[i].bpcov, len * sizeof(float), d->v.bpcov + d->h_cov_off[i], (size_t)d->h_stride[i] * sizeof(float),
+                                 len * sizeof(float), 3, cudaMemcpyDeviceToHost, ctx->stream);
+          results[i].strand_lanes = 1;
+        }
+        if (ce != cudaSuccess) rc = fail(ctx, STG_ECUDA, "stg_infer_transcripts_batch: copy of bpcov failed");
       }
+    }
     if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, STG_ECUDA, "stg_infer_transcripts_batch: stream failed");
     OneBundleOut& o = ctx->one_out;
     if (!rc && pb.n_juncs) {
@@ -1642,7 +1701,19 @@ int stg_infer_transcripts_batch(stg_ctx* ctx, int64_t n, const stg_bundle_view* 
           r.p_start = o.p_start.data() + p0; r.p_end = o.p_end.data() + p0; r.p_cov = o.p_cov.data() + p0; r.p_tlen = o.p_tlen.data() + p0;
           r.p_geneno = o.p_geneno.data() + p0; r.p_strand = o.p_strand.data() + p0; r.p_exon_off = o.p_exon_off.data() + x0;
           r.e_start = o.e_start.data() + e0; r.e_end = o.e_end.data() + e0; r.e_cov = o.e_cov.data() + e0;
+          // the strand lanes of bpcov, where the reference's printResults will look at them (rlink.cpp:18453-18459, :18524-18531)
+          bool need = false;
+          for (uint32_t q = poff[i]; q < poff[i + 1] && !need; q++) need = xo[q + 1] - xo[q] == 1 && gst[q] != '.';
+          if (need && r.bpcov) {
+            const size_t len = d->h_len[i];
+            if (cudaMemcpyAsync(r.bpcov, d->v.bpcov + d->h_cov_off[i], len * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaMemcpyAsync(r.bpcov + 2 * len, d->v.bpcov + 2 * d->v.cov_pitch + d->h_cov_off[i], len * sizeof(float), cudaMemcpyDeviceToHost,
+                                ctx->stream) != cudaSuccess)
+              rc = fail(ctx, STG_ECUDA, "stg_infer_transcripts_batch: copy of bpcov failed");
+            r.strand_lanes = 1;
+          }
         }
+        if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, STG_ECUDA, "stg_infer_transcripts_batch: stream failed");
       }
     }
   }

@@ -89,7 +89,8 @@ struct DevBatchView {
                                //             sub-tile with events; all-ones until published (bundle-major tile id)
   uint32_t* tile_ticket;       // [6] work counters: cov_tile_kernel, deep_deposit_kernel, deep_long_kernel, scan blocks, very long lists
   // outputs
-  float* bpcov;                // [3*total_pos]: bundle b lane s index i at 3*b_gbase[b] + s*b_stride[b] + i
+  float* bpcov;                // [3*total_pos], lane-major over the whole batch: bundle b lane s index i at s*cov_pitch + b_gbase[b] + i
+  size_t cov_pitch;            // = total_pos: strand lane 1 of every bundle is ONE contiguous block (the part the host reads back)
   double *j_nreads_good, *j_leftsupport, *j_rightsupport;  // [n_juncs]
   double* b_cov_total;         // [n_bundles*3]
   // junction pass of build_graphs (row a7): CJunction fields after rlink.cpp:14385-14809, one per junction row

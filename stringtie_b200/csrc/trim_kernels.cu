@@ -23,8 +23,8 @@ __global__ void __launch_bounds__(256) find_trims_kernel(DevBatchView v, int64_t
   if (w >= n) return;
   const int32_t b = bundle[w];
   const int sno = sno_in[w];
-  const float* __restrict__ base = v.bpcov + 3 * (size_t)v.b_gbase[b];
-  const uint32_t stride = v.b_stride[b];
+  const float* __restrict__ base = v.bpcov + v.b_gbase[b];
+  const size_t stride = v.cov_pitch;
   const uint32_t cnt = find_trims_warp(base + stride, base + (size_t)(2 - sno) * stride, (uint32_t)v.b_start[b], start_in[w], end_in[w],
                                        o_pos + cap_off[w], o_ab + cap_off[w], o_st + cap_off[w], cap_off[w + 1] - cap_off[w]);
   if ((threadIdx.x & 31) == 0) o_cnt[w] = cnt;

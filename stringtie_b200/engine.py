@@ -22,7 +22,8 @@ EXPORTS = [
     "stg_params_default", "stg_init", "stg_shutdown", "stg_last_error", "stg_abi_version", "stg_builder_create",
     "stg_builder_add", "stg_builder_packed", "stg_builder_reset", "stg_builder_destroy", "stg_upload", "stg_run",
     "stg_sync", "stg_free_batch", "stg_trim", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
-    "stg_upload_wait", "stg_fetch_bpcov_all_begin", "stg_fetch_wait",
+    "stg_upload_wait", "stg_fetch_bpcov_all_begin", "stg_fetch_wait", "stg_fetch_bpcov_lane_begin", "stg_fetch_bpcov_bundle_lane",
+    "stg_strand_lane_bundles",
     "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_trims_capacity", "stg_find_trims", "stg_infer_transcripts", "stg_infer_transcripts_batch",
     "stg_build_groups", "stg_groups_array_info", "stg_fetch_groups_array", "stg_neutral_predictions",
     "stg_assemble", "stg_asm_array_info", "stg_fetch_asm_array", "stg_rewind", "stg_reduce_totals",
@@ -94,6 +95,9 @@ def load_library() -> C.CDLL:
     L.stg_fetch_bpcov.argtypes = [vp, vp, C.c_int64, c_f32p]
     L.stg_fetch_bpcov_all.argtypes = [vp, vp, c_f32p]
     L.stg_fetch_bpcov_all_begin.argtypes = [vp, vp, c_f32p]
+    L.stg_fetch_bpcov_lane_begin.argtypes = [vp, vp, C.c_int, c_f32p]
+    L.stg_fetch_bpcov_bundle_lane.argtypes = [vp, vp, C.c_int64, C.c_int, c_f32p]
+    L.stg_strand_lane_bundles.argtypes = [vp, vp, C.c_int64, c_i64p, c_i64p]
     L.stg_fetch_wait.argtypes = [vp, vp]
     L.stg_upload_wait.argtypes = [vp, vp]
     L.stg_device_bpcov.argtypes = [vp]
@@ -350,6 +354,20 @@ class Engine:
         """bpcov of every bundle into caller memory (pinned memory makes it one DMA)."""
         self._ck(self.L.stg_fetch_bpcov_all(self.ctx, batch.handle, C.cast(C.c_void_p(host_ptr), c_f32p)))
 
+    def fetch_bpcov_lane_begin(self, batch: DeviceBatch, lane: int, host_ptr: int) -> None:
+        """One strand lane of every bundle (total_floats / 3 floats) on the copy-out stream (stg_fetch_bpcov_lane_begin)."""
+        self._ck(self.L.stg_fetch_bpcov_lane_begin(self.ctx, batch.handle, lane, C.cast(C.c_void_p(host_ptr), c_f32p)))
+
+    def fetch_bpcov_bundle_lane(self, batch: DeviceBatch, bundle: int, lane: int, host_ptr: int) -> None:
+        self._ck(self.L.stg_fetch_bpcov_bundle_lane(self.ctx, batch.handle, bundle, lane, C.cast(C.c_void_p(host_ptr), c_f32p)))
+
+    def strand_lane_bundles(self, batch: DeviceBatch) -> np.ndarray:
+        """Bundles whose bpcov lanes 0 / 2 the reference's printResults reads (stg_strand_lane_bundles)."""
+        out = np.zeros(max(1, batch.n_bundles), dtype=np.int64)
+        n = C.c_int64(0)
+        self._ck(self.L.stg_strand_lane_bundles(self.ctx, batch.handle, out.size, ptr(out), C.byref(n)))
+        return out[:n.value].copy()
+
     def fetch_bpcov_all_begin(self, batch: DeviceBatch, host_ptr: int) -> None:
         """Start the same copy on the copy-out stream (overlaps the group / assembly stages); fetch_wait completes it."""
         self._ck(self.L.stg_fetch_bpcov_all_begin(self.ctx, batch.handle, C.cast(C.c_void_p(host_ptr), c_f32p)))
@@ -424,7 +442,7 @@ class Engine:
             keep.append(k)
             views[i] = view
             length = view.end - view.start + 3
-            cov = np.empty(3 * length, dtype=np.float32)
+            cov = np.zeros(3 * length, dtype=np.float32)
             covs.append((cov, length))
             results[i] = StgBundleResult(ptr(cov), None, None, None)
             results[i].assemble = 1
@@ -438,15 +456,16 @@ class Engine:
                     "tlen": cp(res.p_tlen, m, np.int32), "geneno": cp(res.p_geneno, m, np.int32), "strand": cp(res.p_strand, m, np.int8),
                     "exon_off": cp(res.p_exon_off, m + 1, np.uint32) if m else np.zeros(1, dtype=np.uint32),
                     "e_start": cp(res.e_start, ne, np.uint32), "e_end": cp(res.e_end, ne, np.uint32), "e_cov": cp(res.e_cov, ne, np.float32)}
-            out.append((covs[i][0].reshape(3, covs[i][1]), pred, res.num_fragments, res.frag_len))
+            out.append((covs[i][0].reshape(3, covs[i][1]), pred, res.num_fragments, res.frag_len, bool(res.strand_lanes)))
         return out
 
     def infer_transcripts_full(self, arrays: Dict[str, np.ndarray], b: int = 0):
         """The whole of `infer_transcripts(BundleData*)` (rlink.h:380) for bundle b: returns (bpcov, predictions dict,
-        num_fragments, frag_len); predictions = BundleData::pred in the reference's order."""
+        num_fragments, frag_len, strand_lanes); predictions = BundleData::pred in the reference's order; lanes 0 and 2 of
+        bpcov are filled only if strand_lanes (a single-exon prediction with a strand makes printResults read them)."""
         view, keep = bundle_view(arrays, b)
         length = view.end - view.start + 3
-        cov = np.empty(3 * length, dtype=np.float32)
+        cov = np.zeros(3 * length, dtype=np.float32)
         good = np.zeros(view.n_juncs, dtype=np.float64)
         left = np.zeros(view.n_juncs, dtype=np.float64)
         right = np.zeros(view.n_juncs, dtype=np.float64)
@@ -459,4 +478,4 @@ class Engine:
                 "tlen": cp(res.p_tlen, n, np.int32), "geneno": cp(res.p_geneno, n, np.int32), "strand": cp(res.p_strand, n, np.int8),
                 "exon_off": cp(res.p_exon_off, n + 1, np.uint32) if n else np.zeros(1, dtype=np.uint32),
                 "e_start": cp(res.e_start, ne, np.uint32), "e_end": cp(res.e_end, ne, np.uint32), "e_cov": cp(res.e_cov, ne, np.float32)}
-        return cov.reshape(3, length), pred, res.num_fragments, res.frag_len
+        return cov.reshape(3, length), pred, res.num_fragments, res.frag_len, bool(res.strand_lanes)

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"libstgpu.so does not export {n}"
     assert sorted(engine.EXPORTS) == names
-    assert L.stg_abi_version() == 4
+    assert L.stg_abi_version() == 5
 
 
 def test_params_default_match_reference_defaults():

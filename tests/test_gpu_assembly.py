@@ -102,7 +102,7 @@ def test_one_bundle_drop_in_returns_the_reference_prediction_list(engine):
     from stringtie_b200.stgb import input_view
     a = input_view(g)
     for b in (0, 3, 7, 11, int(g["b_start"].size) - 1):
-        cov, pred, nfrag, flen = engine.infer_transcripts_full(a, b)
+        cov, pred, nfrag, flen, strand_lanes = engine.infer_transcripts_full(a, b)
         r0, r1 = int(g["f_pred_off"][b]), int(g["f_pred_off"][b + 1])
         assert np.array_equal(pred["start"], g["p_start"][r0:r1]) and np.array_equal(pred["end"], g["p_end"][r0:r1])
         assert np.array_equal(pred["cov"].view(np.uint64), g["p_cov"][r0:r1].view(np.uint64))
@@ -114,7 +114,14 @@ def test_one_bundle_drop_in_returns_the_reference_prediction_list(engine):
         assert np.array_equal(pred["exon_off"] - pred["exon_off"][0], g["p_exon_off"][r0:r1 + 1] - g["p_exon_off"][r0])
         assert nfrag == g["f_num_fragments"][b] and flen == g["f_frag_len"][b]
         c0, c1 = int(g["s1_cov_off"][b]), int(g["s1_cov_off"][b + 1])
-        assert np.array_equal(cov.reshape(-1).view(np.uint32), g["s1_cov"][c0:c1].view(np.uint32))
+        ref_cov = g["s1_cov"][c0:c1].reshape(3, -1)
+        assert np.array_equal(cov[1].view(np.uint32), ref_cov[1].view(np.uint32))
+        # lanes 0 / 2 come back exactly where the reference's printResults reads them: a single-exon prediction with a strand
+        # (rlink.cpp:18453-18459, :18524-18531)
+        nex = np.diff(pred["exon_off"].astype(np.int64))
+        assert strand_lanes == bool(((nex == 1) & (pred["strand"] != ord("."))).any())
+        if strand_lanes:
+            assert np.array_equal(cov.view(np.uint32), ref_cov.view(np.uint32))
 
 
 def test_batched_drop_in_equals_one_bundle_calls(engine):
@@ -125,10 +132,10 @@ def test_batched_drop_in_equals_one_bundle_calls(engine):
     a = input_view(g)
     pick = [0, 3, 4, 7, 11, int(g["b_start"].size) - 1]
     got = engine.infer_transcripts_batch(a, pick)
-    assert sum(p["start"].size for _, p, _, _ in got) > 10
-    for (cov, pred, nfrag, flen), b in zip(got, pick):
-        cov1, pred1, nfrag1, flen1 = engine.infer_transcripts_full(a, b)
-        assert np.array_equal(cov.view(np.uint32), cov1.view(np.uint32))
+    assert sum(p["start"].size for _, p, _, _, _ in got) > 10
+    for (cov, pred, nfrag, flen, sl), b in zip(got, pick):
+        cov1, pred1, nfrag1, flen1, sl1 = engine.infer_transcripts_full(a, b)
+        assert sl == sl1 and np.array_equal(cov.view(np.uint32), cov1.view(np.uint32))
         assert nfrag == nfrag1 and flen == flen1
         for k in pred1:
             assert np.array_equal(pred[k].view(np.uint8), pred1[k].view(np.uint8)), (b, k)
