@@ -343,12 +343,8 @@ def main():
             if cov_host is not None:
                 # the strand lanes, for the bundles whose predictions make printResults read them (rlink.cpp:18453-18459)
                 need = eng.strand_lane_bundles(b)
-                off, _, _ = b.layout()
-                lens = arrays["b_end"].astype(np.int64) - arrays["b_start"].astype(np.int64) + 3
-                for bb in need:
-                    for ln in (0, 2):
-                        eng.fetch_bpcov_bundle_lane(b, int(bb), ln, cov_host.data_ptr() + 4 * (ln * lane_floats + int(off[bb])))
-                    nbytes += 8 * int(lens[bb])
+                eng.fetch_bpcov_strand_lanes_begin(b, need, cov_host.data_ptr())
+                nbytes += 8 * int((arrays["b_end"][need].astype(np.int64) - arrays["b_start"][need].astype(np.int64) + 3).sum())
                 strand_bundles[0] = int(need.size)
                 eng.fetch_wait(b)
                 nbytes += lane_floats * 4
@@ -376,10 +372,12 @@ def main():
         n_e2e = max(1, min(args.steps, 5))
         barrier()
         phases.clear()
+        pool0 = eng.pool_stats()
         t0 = time.perf_counter()
         e2e_pass(n_e2e)
         barrier()
         wall = (time.perf_counter() - t0) / n_e2e
+        pool1 = eng.pool_stats()
         uploader.shutdown()
         if dist is not None:
             t = torch.tensor([wall, single], dtype=torch.float64, device="cuda")
@@ -390,6 +388,9 @@ def main():
                "single_batch_ms": 1e3 * single,
                "host_phases_ms_per_step": {k: 1e3 * v / n_e2e for k, v in phases.items()},
                "bpcov_copied_back": cov_host is not None,
+               "device_pool": {"cudaMalloc_calls_in_timed_region": pool1["cudaMalloc_calls"] - pool0["cudaMalloc_calls"],
+                               "cudaFree_calls_in_timed_region": pool1["cudaFree_calls"] - pool0["cudaFree_calls"],
+                               "pool_flushes_in_timed_region": pool1["pool_flushes"] - pool0["pool_flushes"], "pool_bytes": pool1["pool_bytes"]},
                "bpcov_lanes": "lane 1 of every bundle + lanes 0 / 2 of the %d bundles holding a single-exon prediction with a strand "
                               "(the only place the reference's printResults reads them: rlink.cpp:18453-18459, :18524-18531)" % strand_bundles[0],
                "timing": "host wall clock around n batches, each: stg_upload (validation + H2D of every input array from pinned "

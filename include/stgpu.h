@@ -195,6 +195,9 @@ int stg_fetch_bpcov_all_begin(stg_ctx* ctx, stg_dbatch* batch, float* out /*[tot
 int stg_fetch_bpcov_lane_begin(stg_ctx* ctx, stg_dbatch* batch, int lane, float* out /*[total_floats / 3]*/);
 int stg_fetch_bpcov_bundle_lane(stg_ctx* ctx, const stg_dbatch* batch, int64_t bundle, int lane, float* out /*[len_b]*/);
 int stg_strand_lane_bundles(stg_ctx* ctx, const stg_dbatch* batch, int64_t cap, int64_t* bundles /*[cap]*/, int64_t* n);
+/* Lanes 0 and 2 of the listed bundles into a host buffer of total_floats laid out like stg_fetch_bpcov_all's (copy-out stream;
+ * complete after stg_fetch_wait). */
+int stg_fetch_bpcov_strand_lanes_begin(stg_ctx* ctx, stg_dbatch* batch, int64_t n, const int64_t* bundles, float* out /*[total_floats]*/);
 int stg_fetch_wait(stg_ctx* ctx, stg_dbatch* batch);
 const float* stg_device_bpcov(const stg_dbatch* batch); /* device pointer (for consumers that stay on the GPU) */
 /* CJunction::nreads_good / leftsupport / rightsupport after the stage; each [n_juncs] */
@@ -372,6 +375,10 @@ int stg_shard_assign(int64_t n_bundles, const uint32_t* b_read_off /*[n+1]*/, co
 int stg_selftest_chain(stg_ctx* ctx, int64_t n, const uint32_t* off /*[n+1]*/, const float* x, const float* s0 /*[n]*/,
                        float* out /*[n]*/, int plain, float* kernel_ms);
 
+/* Device-memory pool of the context: out[5] = {cudaMalloc calls, bytes they asked for, cudaFree calls of blocks the bounded pool
+ * refused, times the whole pool was dropped to make room, bytes parked now}.  cudaMalloc / cudaFree synchronise the device:
+ * a host that streams batches wants these counters to stand still. */
+int stg_pool_stats(stg_ctx* ctx, int64_t* out /*[5]*/);
 int stg_set_profiling(stg_ctx* ctx, int enabled);
 int stg_kernel_count(const stg_ctx* ctx);                       /* kernels launched by the last stg_run */
 int stg_kernel_time(stg_ctx* ctx, int i, const char** name, float* ms); /* after stg_sync */

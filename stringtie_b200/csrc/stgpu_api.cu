@@ -44,6 +44,8 @@ struct stg_ctx {
   std::vector<StagePending> stage_pending;
   int64_t cluster_reads = 0;           // bundles with at least this many reads are walked by a cluster of CTAs (row x1)
   cudaStream_t in_stream = nullptr;    // H2D copies of stg_upload (a batch can be uploaded while the previous one computes)
+  size_t pool_limit = (size_t)160 << 30;   // set from the device's memory size in stg_init
+  int64_t n_malloc = 0, malloc_bytes = 0, n_free = 0, n_pool_flush = 0;   // cudaMalloc / cudaFree calls behind the pool (stg_pool_stats)
   cudaStream_t out_stream = nullptr;   // D2H of bpcov started by stg_fetch_bpcov_all_begin (overlaps rows a8-a15)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
   std::string error;
@@ -193,9 +195,11 @@ int dev_alloc(stg_ctx* ctx, stg_dbatch* d, T** out, int64_t count) {
   void* p = pool_take(ctx, bytes, &got);
   if (!p) {
     cudaError_t e = cudaMalloc(&p, bytes);
+    ctx->n_malloc++; ctx->malloc_bytes += (int64_t)bytes;
     if (e != cudaSuccess) {   // make room: drop everything parked in the pool and retry once
       cudaGetLastError();
       pool_release_all(ctx);
+      ctx->n_pool_flush++;
       e = cudaMalloc(&p, bytes);
     }
     if (e != cudaSuccess) return fail(ctx, STG_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
@@ -289,7 +293,10 @@ void free_batch_allocs(stg_ctx* ctx, stg_dbatch* d) {
   if (ctx) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     for (auto& b : d->allocs) {
-      if (ctx->pool_bytes + b.bytes > ((size_t)96 << 30)) { cudaFree(b.p); continue; }   // keep the pool bounded
+      // no bound of its own: a C2 batch takes ~52 GB and a streaming host has two in flight plus one parked; when the device
+      // runs out, dev_alloc drops the whole pool once and retries (cudaFree / cudaMalloc synchronise the device, so the pool
+      // must not churn in the steady state: stg_pool_stats)
+      if (ctx->pool_bytes + b.bytes > ctx->pool_limit) { cudaFree(b.p); ctx->n_free++; continue; }
       ctx->pool_free.push_back(b); ctx->pool_bytes += b.bytes;
     }
   } else {
@@ -425,6 +432,7 @@ int stg_init(const stg_params* params, int device, stg_ctx** out) {
   ctx->cluster_reads = getenv("STGPU_CLUSTER_READS") ? atoll(getenv("STGPU_CLUSTER_READS")) : groups_cluster_reads();
   if (ctx->cluster_reads < 1) ctx->cluster_reads = 1;
   ICK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  { size_t fr = 0, tot = 0; if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && tot) ctx->pool_limit = tot - tot / 16; }
   ICK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
   ICK(cudaStreamCreateWithFlags(&ctx->aux3_stream, cudaStreamNonBlocking));
   ctx->stage_cap = (size_t)16 << 20;
@@ -828,6 +836,24 @@ int stg_fetch_bpcov_bundle_lane(stg_ctx* ctx, const stg_dbatch* d, int64_t b, in
   return STG_OK;
 }
 
+// Lanes 0 and 2 of the listed bundles into a host buffer laid out like the device's (lane s of bundle b at s * total_floats / 3 +
+// cov_off[b]), queued on the copy-out stream: complete after stg_fetch_wait.
+int stg_fetch_bpcov_strand_lanes_begin(stg_ctx* ctx, stg_dbatch* d, int64_t n, const int64_t* bundles, float* out) {
+  if (!ctx || !d || n < 0 || (n && (!bundles || !out))) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_strand_lanes_begin: bad argument");
+  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_strand_lanes_begin: batch has not been run");
+  for (int64_t i = 0; i < n; i++)
+    if (bundles[i] < 0 || bundles[i] >= d->v.n_bundles) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_strand_lanes_begin: bad bundle");
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaStreamWaitEvent(ctx->out_stream, d->ev_cov, 0));
+  d->out_pending = true;
+  for (int64_t i = 0; i < n; i++)
+    for (int lane = 0; lane < 3; lane += 2) {
+      const size_t o = (size_t)lane * d->v.cov_pitch + (size_t)d->h_cov_off[bundles[i]];
+      CK(ctx, cudaMemcpyAsync(out + o, d->v.bpcov + o, sizeof(float) * (size_t)d->h_len[bundles[i]], cudaMemcpyDeviceToHost, ctx->out_stream));
+    }
+  return STG_OK;
+}
+
 // Bundles whose strand lanes (bpcov[0], bpcov[2]) the reference's printResults reads: the only place is the strand check of
 // a single-exon prediction that carries a strand (rlink.cpp:18453-18459 and :18524-18531); every other use of bpcov after
 // infer_transcripts goes to lane 1.
@@ -851,6 +877,13 @@ int stg_strand_lane_bundles(stg_ctx* ctx, const stg_dbatch* d, int64_t cap, int6
   }
   *n_out = k;
   if (k > cap) return fail(ctx, STG_ERANGE, "stg_strand_lane_bundles: more bundles than the caller's array holds");
+  return STG_OK;
+}
+
+int stg_pool_stats(stg_ctx* ctx, int64_t* out) {
+  if (!ctx || !out) return fail(ctx, STG_EINVAL, "stg_pool_stats: null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  out[0] = ctx->n_malloc; out[1] = ctx->malloc_bytes; out[2] = ctx->n_free; out[3] = ctx->n_pool_flush; out[4] = (int64_t)ctx->pool_bytes;
   return STG_OK;
 }
 

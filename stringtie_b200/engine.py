@@ -23,11 +23,11 @@ EXPORTS = [
     "stg_builder_add", "stg_builder_packed", "stg_builder_reset", "stg_builder_destroy", "stg_upload", "stg_run",
     "stg_sync", "stg_free_batch", "stg_trim", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
     "stg_upload_wait", "stg_fetch_bpcov_all_begin", "stg_fetch_wait", "stg_fetch_bpcov_lane_begin", "stg_fetch_bpcov_bundle_lane",
-    "stg_strand_lane_bundles",
+    "stg_strand_lane_bundles", "stg_fetch_bpcov_strand_lanes_begin",
     "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_trims_capacity", "stg_find_trims", "stg_infer_transcripts", "stg_infer_transcripts_batch",
     "stg_build_groups", "stg_groups_array_info", "stg_fetch_groups_array", "stg_neutral_predictions",
     "stg_assemble", "stg_asm_array_info", "stg_fetch_asm_array", "stg_rewind", "stg_reduce_totals",
-    "stg_shard_assign", "stg_selftest_chain", "stg_set_profiling", "stg_kernel_count", "stg_kernel_time", "stg_launch_counter", "stg_batch_stats", "stg_stream",
+    "stg_shard_assign", "stg_selftest_chain", "stg_pool_stats", "stg_set_profiling", "stg_kernel_count", "stg_kernel_time", "stg_launch_counter", "stg_batch_stats", "stg_stream",
 ]
 
 
@@ -98,6 +98,7 @@ def load_library() -> C.CDLL:
     L.stg_fetch_bpcov_lane_begin.argtypes = [vp, vp, C.c_int, c_f32p]
     L.stg_fetch_bpcov_bundle_lane.argtypes = [vp, vp, C.c_int64, C.c_int, c_f32p]
     L.stg_strand_lane_bundles.argtypes = [vp, vp, C.c_int64, c_i64p, c_i64p]
+    L.stg_fetch_bpcov_strand_lanes_begin.argtypes = [vp, vp, C.c_int64, c_i64p, c_f32p]
     L.stg_fetch_wait.argtypes = [vp, vp]
     L.stg_upload_wait.argtypes = [vp, vp]
     L.stg_device_bpcov.argtypes = [vp]
@@ -122,6 +123,7 @@ def load_library() -> C.CDLL:
     L.stg_asm_array_info.argtypes = [vp, C.c_int, c_i64p, C.POINTER(C.c_int32)]
     L.stg_fetch_asm_array.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
     L.stg_rewind.argtypes = [vp, vp]
+    L.stg_pool_stats.argtypes = [vp, c_i64p]
     L.stg_selftest_chain.argtypes = [vp, C.c_int64, C.POINTER(C.c_uint32), c_f32p, c_f32p, c_f32p, C.c_int, c_f32p]
     L.stg_reduce_totals.argtypes = [vp, vp, vp]
     L.stg_shard_assign.argtypes = [C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
@@ -272,6 +274,12 @@ class Engine:
         sel = sel.astype(np.int64)
         return off, pos[sel], ab[sel], st[sel]
 
+    def pool_stats(self) -> Dict[str, int]:
+        out = np.zeros(5, dtype=np.int64)
+        self._ck(self.L.stg_pool_stats(self.ctx, ptr(out)))
+        return {"cudaMalloc_calls": int(out[0]), "cudaMalloc_bytes": int(out[1]), "cudaFree_calls": int(out[2]), "pool_flushes": int(out[3]),
+                "pool_bytes": int(out[4])}
+
     def selftest_chain(self, off, x, s0, plain=False, want_ms=False):
         """Ordered float32 sums of the CSR lists (stg_selftest_chain): the kernels' integer form of the addition chain."""
         off = np.ascontiguousarray(off, dtype=np.uint32); x = np.ascontiguousarray(x, dtype=np.float32)
@@ -360,6 +368,11 @@ class Engine:
 
     def fetch_bpcov_bundle_lane(self, batch: DeviceBatch, bundle: int, lane: int, host_ptr: int) -> None:
         self._ck(self.L.stg_fetch_bpcov_bundle_lane(self.ctx, batch.handle, bundle, lane, C.cast(C.c_void_p(host_ptr), c_f32p)))
+
+    def fetch_bpcov_strand_lanes_begin(self, batch: DeviceBatch, bundles: np.ndarray, host_ptr: int) -> None:
+        """Lanes 0 / 2 of the listed bundles into a buffer laid out like fetch_bpcov_all's (copy-out stream; fetch_wait completes it)."""
+        bundles = np.ascontiguousarray(bundles, dtype=np.int64)
+        self._ck(self.L.stg_fetch_bpcov_strand_lanes_begin(self.ctx, batch.handle, bundles.size, ptr(bundles), C.cast(C.c_void_p(host_ptr), c_f32p)))
 
     def strand_lane_bundles(self, batch: DeviceBatch) -> np.ndarray:
         """Bundles whose bpcov lanes 0 / 2 the reference's printResults reads (stg_strand_lane_bundles)."""

@@ -139,3 +139,37 @@ def test_batched_drop_in_equals_one_bundle_calls(engine):
         assert nfrag == nfrag1 and flen == flen1
         for k in pred1:
             assert np.array_equal(pred[k].view(np.uint8), pred1[k].view(np.uint8)), (b, k)
+
+
+def test_lane_fetches_return_what_the_host_reads(engine):
+    """The end-to-end path of a batch consumer: lane 1 of every bundle in one copy (stg_fetch_bpcov_lane_begin) and lanes 0 / 2 of
+    the bundles stg_strand_lane_bundles names, against the full copy (stg_fetch_bpcov_all); the named bundles are exactly those
+    holding a single-exon prediction with a strand (rlink.cpp:18453-18459, :18524-18531)."""
+    import ctypes as C
+    a = synth.make_batch(n_bundles=300, reads_per_bundle=900, seed=21)
+    batch = engine.upload(a)
+    engine.run(batch)
+    full = engine.fetch_bpcov_all(batch)
+    off, stride, tot = batch.layout()
+    assert (stride == tot // 3).all()
+    engine.build_groups(batch); engine.neutral_predictions_only(batch); engine.assemble(batch)
+    got = np.zeros(tot, dtype=np.float32)
+    engine.fetch_bpcov_lane_begin(batch, 1, got.ctypes.data + 4 * (tot // 3))
+    need = engine.strand_lane_bundles(batch)
+    engine.fetch_bpcov_strand_lanes_begin(batch, need, got.ctypes.data)
+    engine.fetch_wait(batch)
+    pitch = tot // 3
+    assert np.array_equal(got[pitch:2 * pitch].view(np.uint32), full[pitch:2 * pitch].view(np.uint32))
+    lens = a["b_end"].astype(np.int64) - a["b_start"].astype(np.int64) + 3
+    for b in need:
+        for ln in (0, 2):
+            o = ln * pitch + int(off[b])
+            assert np.array_equal(got[o:o + lens[b]].view(np.uint32), full[o:o + lens[b]].view(np.uint32))
+    one = np.zeros(int(lens[0]), dtype=np.float32)
+    engine.fetch_bpcov_bundle_lane(batch, 0, 2, one.ctypes.data)
+    assert np.array_equal(one.view(np.uint32), full[2 * pitch + int(off[0]): 2 * pitch + int(off[0]) + int(lens[0])].view(np.uint32))
+    pr = engine.fetch_predictions(batch)
+    nex = np.diff(pr["exon_off"].astype(np.int64))
+    bundle_of = np.repeat(np.arange(pr["off"].size - 1), np.diff(pr["off"].astype(np.int64)))
+    assert np.array_equal(np.sort(need), np.unique(bundle_of[(nex == 1) & (pr["strand"] != ord("."))]))
+    batch.free()
