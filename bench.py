@@ -303,26 +303,50 @@ def main():
         parr = {k: v.numpy() for k, v in pinned.items()}
         pb, keep = make_packed(parr)
         cov_host = None
+        pk = None
+        host_threads = max(1, min(32, (os.cpu_count() or 4) - 3))   # the host's worker threads, less the ones that drive the GPU and the upload
         if not args.e2e_no_bpcov:
             try:   # BundleData::bpcov of every bundle comes back too: the reference's printResults reads it on the host
                 b0 = eng.upload_packed(pb, keep)
+                eng.run(b0)
                 cov_floats = eng.cov_total_floats(b0)
+                nt, nraw = eng.pack_bpcov(b0)
                 b0.free()
-                cov_host = torch.empty(cov_floats, dtype=torch.float32).pin_memory()
+                cov_host = torch.empty(cov_floats, dtype=torch.float32)   # where the host's worker threads unpack to
+                cap = nraw + nraw // 8 + 64
+                pk = [{"desc": torch.empty(3 * nt, dtype=torch.int32).pin_memory(), "val": torch.empty(3 * nt, dtype=torch.float32).pin_memory(),
+                       "raw": torch.empty(cap * 512, dtype=torch.float32).pin_memory(), "cap": cap} for _ in range(2)]
             except Exception as ex:
                 cov_host = None
-                config["e2e_bpcov"] = f"not copied back (pinned allocation failed: {ex})"
+                config["e2e_bpcov"] = f"not copied back (host allocation failed: {ex})"
         d2h = [0]
-        strand_bundles = [0]
+        pk_stats = {}
 
         from concurrent.futures import ThreadPoolExecutor
         uploader = ThreadPoolExecutor(1)   # stg_upload of batch i+1 (validation + H2D on the copy-in stream) beside batch i
+        unpackers = ThreadPoolExecutor(host_threads)   # the host's worker threads: bpcov of their bundles out of the packed form
+        pending = []                       # (batch, futures): unpacking of an earlier batch that may still run
 
-        lane_floats = (cov_host.numel() // 3) if cov_host is not None else 0
+        def finish_pending(keep_last=0):
+            while len(pending) > keep_last:
+                pb_, futs = pending.pop(0)
+                for f in futs:
+                    f.result()
+                pb_.free()
+
+        seq = [0]
 
         def start_cov_copy(b):
-            if cov_host is not None:   # lane 1 of every bundle, on the copy-out stream: overlaps the group / assembly stages
-                eng.fetch_bpcov_lane_begin(b, 1, cov_host.data_ptr() + 4 * lane_floats)
+            if cov_host is None:
+                return
+            k = seq[0] % 2
+            # the buffers of set k were last used two batches ago: that unpacking must be over
+            finish_pending(keep_last=1)
+            nt_, nraw_ = eng.pack_bpcov(b)      # on the device, right behind the coverage stage
+            if nraw_ > pk[k]["cap"]:
+                raise SystemExit("bench.py: packed bpcov outgrew its host buffer")
+            pk_stats.update({"sub_tile_lanes": 3 * nt_, "lanes_sent_in_full": nraw_})
+            eng.fetch_bpcov_packed_begin(b, pk[k]["desc"].data_ptr(), pk[k]["val"].data_ptr(), pk[k]["raw"].data_ptr())   # copy-out stream
 
         phases = {}
 
@@ -341,16 +365,20 @@ def main():
             nbytes = sum(x.nbytes for x in p.values()) + sum(x.nbytes for x in n.values()) + nf.nbytes + fl.nbytes
             t = tick("fetch_predictions", t)
             if cov_host is not None:
-                # the strand lanes, for the bundles whose predictions make printResults read them (rlink.cpp:18453-18459)
-                need = eng.strand_lane_bundles(b)
-                eng.fetch_bpcov_strand_lanes_begin(b, need, cov_host.data_ptr())
-                nbytes += 8 * int((arrays["b_end"][need].astype(np.int64) - arrays["b_start"][need].astype(np.int64) + 3).sum())
-                strand_bundles[0] = int(need.size)
+                k = seq[0] % 2
                 eng.fetch_wait(b)
-                nbytes += lane_floats * 4
-            t = tick("wait_bpcov_copy", t)
+                nbytes += pk[k]["desc"].numel() * 4 + pk[k]["val"].numel() * 4 + pk_stats["lanes_sent_in_full"] * 512 * 4
+                t = tick("wait_bpcov_copy", t)
+                eng.release_device(b)      # device memory back to the pool; the handle keeps the layout tables for the unpacking
+                nb_ = b.n_bundles
+                step = (nb_ + 4 * host_threads - 1) // (4 * host_threads)
+                futs = [unpackers.submit(eng.unpack_bpcov, b, lo, min(nb_, lo + step), pk[k]["desc"].data_ptr(), pk[k]["val"].data_ptr(),
+                                         pk[k]["raw"].data_ptr(), cov_host.data_ptr()) for lo in range(0, nb_, step)]
+                pending.append((b, futs))
+                seq[0] += 1
+            else:
+                b.free()
             d2h[0] = nbytes
-            b.free()
             tick("free", t)
 
         def e2e_pass(n):
@@ -362,6 +390,9 @@ def main():
                 if i + 1 < n:
                     fut = uploader.submit(eng.upload_packed, pb, keep)
                 consume(b)
+            t = time.perf_counter()
+            finish_pending()           # the last batch's bpcov is unpacked inside the timed region too
+            tick("wait_last_unpack", t)
 
         e2e_pass(max(1, min(args.warmup, 2)))
         barrier()
@@ -378,7 +409,7 @@ def main():
         barrier()
         wall = (time.perf_counter() - t0) / n_e2e
         pool1 = eng.pool_stats()
-        uploader.shutdown()
+        uploader.shutdown(); unpackers.shutdown()
         if dist is not None:
             t = torch.tensor([wall, single], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -391,14 +422,14 @@ def main():
                "device_pool": {"cudaMalloc_calls_in_timed_region": pool1["cudaMalloc_calls"] - pool0["cudaMalloc_calls"],
                                "cudaFree_calls_in_timed_region": pool1["cudaFree_calls"] - pool0["cudaFree_calls"],
                                "pool_flushes_in_timed_region": pool1["pool_flushes"] - pool0["pool_flushes"], "pool_bytes": pool1["pool_bytes"]},
-               "bpcov_lanes": "lane 1 of every bundle + lanes 0 / 2 of the %d bundles holding a single-exon prediction with a strand "
-                              "(the only place the reference's printResults reads them: rlink.cpp:18453-18459, :18524-18531)" % strand_bundles[0],
+               "bpcov_packed": dict(pk_stats, host_threads_unpacking=host_threads) if cov_host is not None else None,
                "timing": "host wall clock around n batches, each: stg_upload (validation + H2D of every input array from pinned "
                          "memory, on the copy-in stream) + stg_run + stg_build_groups + stg_neutral_predictions + stg_assemble + D2H of "
                          "BundleData::pred (neutral and graph predictions with exons), num_fragments, frag_len and — unless "
-                         "--e2e-no-bpcov — bpcov into pinned host memory: strand lane 1 of every bundle (the reference's printResults, which "
-                         "stays on the host, reads it; the copy runs on the copy-out stream from the end of the coverage stage) and "
-                         "lanes 0 / 2 of the bundles whose predictions make printResults read them + "
+                         "--e2e-no-bpcov — ALL of bpcov (the reference's printResults, which stays on the host, reads the three lanes): packed on "
+                         "the device behind the coverage stage (a sub-tile lane that repeats one value travels as that value: "
+                         "stg_pack_bpcov), copied on the copy-out stream into pinned memory and unpacked into the bundles' arrays by "
+                         "the host's worker threads (stg_unpack_bpcov) while the next batch computes + "
                          "stg_free_batch.  The upload of batch i+1 is issued while batch i computes, as the bundle queue of the "
                          "host does; every H2D and D2H byte of the n batches is inside the timed region.  single_batch_ms is one "
                          "batch alone (nothing to overlap its upload with).  Max over ranks"}

@@ -77,7 +77,7 @@ struct Request {
   std::vector<int32_t> rjunc, pair_idx;
   std::vector<double> j_nreads, j_nm, j_mm;
   int len = 0, geneno = 0;
-  bool done = false, strand_lanes = false;
+  bool done = false;
 };
 
 void flatten(BundleData* bundle, Request& q, stg_bundle_view& v) {
@@ -162,7 +162,6 @@ void run_batch(std::vector<std::pair<Request*, stg_bundle_view> >& batch) {
     }
     q.bundle->num_fragments += r.num_fragments;         // rlink.cpp:15105-15116 (both start at 0 for a fresh bundle)
     q.bundle->frag_len += r.frag_len;
-    q.strand_lanes = r.strand_lanes != 0;
   }
 }
 }  // namespace
@@ -197,12 +196,9 @@ int infer_transcripts(BundleData* bundle) {
     }
     g_inside--;
   }
-  // BundleData::bpcov, bundle.h:329.  printResults reads lane 1 everywhere and the strand lanes only in the strand check of a
-  // single-exon prediction with a strand (rlink.cpp:18453-18459, :18524-18531): the library sends them for those bundles only
-  // (stg_bundle_result::strand_lanes); otherwise they keep the zeros Resize() gives them, as sized as the reference's.
-  for (int s = 0; s < 3; s++) {
+  for (int s = 0; s < 3; s++) {                        // BundleData::bpcov, bundle.h:329 (printResults reads all three lanes)
     bundle->bpcov[s].Resize(q.len);
-    if (s == 1 || q.strand_lanes) memcpy(&bundle->bpcov[s][0], &q.cov[(size_t)s * q.len], (size_t)q.len * sizeof(float));
+    memcpy(&bundle->bpcov[s][0], &q.cov[(size_t)s * q.len], (size_t)q.len * sizeof(float));
   }
   return q.geneno;
 }

@@ -171,13 +171,15 @@ int stg_upload_wait(stg_ctx* ctx, stg_dbatch* batch);
 int stg_run(stg_ctx* ctx, stg_dbatch* batch);
 int stg_sync(stg_ctx* ctx);
 int stg_free_batch(stg_ctx* ctx, stg_dbatch* batch);   /* device blocks go back to the context's pool for reuse */
+/* Device memory of the batch back to the pool while the handle stays valid for stg_unpack_bpcov (a host that unpacks bpcov on its
+ * worker threads while the next batch computes); stg_free_batch ends the handle. */
+int stg_release_device(stg_ctx* ctx, stg_dbatch* batch);
 int stg_trim(stg_ctx* ctx);                            /* release the pooled device memory (cudaFree) */
 
 /* Outputs of the coverage / junction-support stage (count_good_junctions, rlink.cpp:16656-17136).
  * bpcov layout in HBM: for bundle b, lane s in {0:-, 1:all, 2:+}, index i in [0, len_b) with
  * len_b = end-start+3 (rlink.cpp:16875): element cov_off[b] + s*stride[b] + i  (float32).  Since ABI 5 the strand lanes
- * are batch-wide: stride[b] = total_floats / 3 for every bundle, i.e. lane 1 of all bundles is ONE contiguous block —
- * the part of bpcov the host needs back in full (stg_fetch_bpcov_lane_begin).                            */
+ * are batch-wide: stride[b] = total_floats / 3 for every bundle, i.e. a lane of all bundles is ONE contiguous block.   */
 int stg_cov_layout(const stg_dbatch* batch, int64_t* cov_off /*[n_bundles]*/, int64_t* stride /*[n_bundles]*/,
                    int64_t* total_floats);
 int stg_fetch_bpcov(stg_ctx* ctx, const stg_dbatch* batch, int64_t bundle, float* out /*[3*len_b], lane-major*/);
@@ -188,16 +190,22 @@ int stg_fetch_bpcov_all(stg_ctx* ctx, const stg_dbatch* batch, float* out /*[tot
  * stg_run of the batch wait for it too. */
 int stg_fetch_bpcov_all_begin(stg_ctx* ctx, stg_dbatch* batch, float* out /*[total_floats]*/);
 /* One strand lane of every bundle (total_floats / 3 floats; bundle b at cov_off[b]) on the copy-out stream, like
- * stg_fetch_bpcov_all_begin.  After infer_transcripts the reference reads lane 1 everywhere (get_cov(1, ...) in
- * print_predcluster) and lanes 0 / 2 only in the strand check of single-exon predictions that carry a strand
- * (rlink.cpp:18453-18459, :18524-18531): a host copies lane 1 in full and the strand lanes of the bundles
- * stg_strand_lane_bundles names (after stg_assemble), one bundle at a time. */
+ * stg_fetch_bpcov_all_begin; and one lane of one bundle, synchronously.  (The reference's printResults needs all three lanes:
+ * lane 1 nearly everywhere, lanes 0 / 2 in the strand check of single-exon predictions, rlink.cpp:18453-18459, and in the gene
+ * coverage pass, :20232-20236.) */
 int stg_fetch_bpcov_lane_begin(stg_ctx* ctx, stg_dbatch* batch, int lane, float* out /*[total_floats / 3]*/);
 int stg_fetch_bpcov_bundle_lane(stg_ctx* ctx, const stg_dbatch* batch, int64_t bundle, int lane, float* out /*[len_b]*/);
-int stg_strand_lane_bundles(stg_ctx* ctx, const stg_dbatch* batch, int64_t cap, int64_t* bundles /*[cap]*/, int64_t* n);
-/* Lanes 0 and 2 of the listed bundles into a host buffer of total_floats laid out like stg_fetch_bpcov_all's (copy-out stream;
- * complete after stg_fetch_wait). */
-int stg_fetch_bpcov_strand_lanes_begin(stg_ctx* ctx, stg_dbatch* batch, int64_t n, const int64_t* bundles, float* out /*[total_floats]*/);
+/* bpcov packed for the trip to the host.  A strand lane of a 512-position sub-tile that repeats one value (no event in it: the
+ * gaps between loci, introns — four fifths of a short-read batch) travels as that value, the others as their 512 floats in one
+ * dense buffer.  stg_pack_bpcov (after stg_run; synchronous: it returns the sizes) builds the packed form on the device:
+ * n_tiles sub-tiles in the batch, n_raw lanes that travel in full.  stg_fetch_bpcov_packed_begin copies it on the copy-out
+ * stream (complete after stg_fetch_wait): desc and val [3 * n_tiles], raw [n_raw * 512].  stg_unpack_bpcov (host only, any
+ * thread) writes bpcov of the bundles [b0, b1) into a buffer laid out like stg_fetch_bpcov_all's, bit for bit what that
+ * call returns for them: a fill or a copy per sub-tile lane. */
+int stg_pack_bpcov(stg_ctx* ctx, stg_dbatch* batch, int64_t* n_tiles, int64_t* n_raw);
+int stg_fetch_bpcov_packed_begin(stg_ctx* ctx, stg_dbatch* batch, uint32_t* desc, float* val, float* raw);
+int stg_unpack_bpcov(const stg_dbatch* batch, int64_t b0, int64_t b1, const uint32_t* desc, const float* val, const float* raw,
+                     float* out /*[total_floats]*/);
 int stg_fetch_wait(stg_ctx* ctx, stg_dbatch* batch);
 const float* stg_device_bpcov(const stg_dbatch* batch); /* device pointer (for consumers that stay on the GPU) */
 /* CJunction::nreads_good / leftsupport / rightsupport after the stage; each [n_juncs] */
@@ -347,11 +355,6 @@ typedef struct stg_bundle_result {
   const uint32_t* p_exon_off;                  /* [n_pred+1] */
   const uint32_t *e_start, *e_end;             /* CPrediction::exons */
   const float* e_cov;                          /* CPrediction::exoncov */
-  /* ---- ABI 5 ---- */
-  int32_t strand_lanes;    /* out: 1 if lanes 0 and 2 of `bpcov` were filled.  Always with assemble == 0.  With assemble != 0 lane 1
-                            * ([len, 2*len)) is always filled and the strand lanes only for a bundle that holds a single-exon prediction
-                            * carrying a strand: the one place the reference reads them after infer_transcripts (the strand check of
-                            * print_predcluster, rlink.cpp:18453-18459 and :18524-18531); otherwise they are left untouched. */
 } stg_bundle_result;
 int stg_infer_transcripts(stg_ctx* ctx, const stg_bundle_view* view, stg_bundle_result* result);
 /* The same for n bundles in ONE device batch (what a host does that collects the bundles of its worker threads, or of its

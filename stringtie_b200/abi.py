@@ -61,7 +61,7 @@ class StgBundleResult(C.Structure):
                 ("frag_len", C.c_double), ("p_start", C.POINTER(C.c_int32)), ("p_end", C.POINTER(C.c_int32)), ("p_cov", c_f64p),
                 ("p_tlen", C.POINTER(C.c_int32)), ("p_geneno", C.POINTER(C.c_int32)), ("p_strand", C.POINTER(C.c_int8)),
                 ("p_exon_off", C.POINTER(C.c_uint32)), ("e_start", C.POINTER(C.c_uint32)), ("e_end", C.POINTER(C.c_uint32)),
-                ("e_cov", c_f32p), ("strand_lanes", C.c_int32)]
+                ("e_cov", c_f32p)]
 
 
 def ptr(a: np.ndarray):

@@ -1356,6 +1356,71 @@ cudaError_t launch_query_cov(const DevBatchView& v, int64_t n, const int32_t* bu
   return cudaGetLastError();
 }
 
+// --------------------------------------------------------------------------------------------------------------
+// K11b: bpcov for the trip to the host.  The host needs all of bpcov (printResults, rlink.cpp:18402-20260, reads the three
+// lanes), but most of it says nothing: four fifths of the sub-tiles saw no event and repeat ONE value per strand lane (the
+// block sum at a standstill between loci and inside introns).  A strand lane of a sub-tile either travels as that value or
+// as its 512 floats, gathered into one dense buffer: cov_pack_flag marks the lanes that change inside the sub-tile, a scan
+// numbers them, cov_pack_gather copies them; stg_unpack_bpcov lays the bundle's arrays out again on the host (a fill or
+// a copy per sub-tile lane: what the host adaptor's copy into BundleData::bpcov costs anyway).
+// --------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cov_pack_flag_kernel(DevBatchView v, uint32_t* __restrict__ flag, float* __restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per sub-tile (plan record)
+  if (w >= v.n_tiles) return;
+  uint32_t recw = 0;
+  if (lane < 8) recw = __ldg(reinterpret_cast<const uint32_t*>(v.tile_plan + w) + lane);
+  const uint32_t gbase = __shfl_sync(FULL, recw, 0), i0 = __shfl_sync(FULL, recw, 1);
+  const uint32_t npos = __shfl_sync(FULL, recw, 5), tile_id = __shfl_sync(FULL, recw, 6);
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(v.bpcov + (size_t)s * v.cov_pitch + gbase + i0);
+    const uint32_t x0 = __ldg(p);
+    bool same = true;
+    for (uint32_t q = lane; q * 4 < npos; q += 32) {
+      const uint4 y = __ldg(reinterpret_cast<const uint4*>(p) + q);
+      const uint32_t k = q * 4;
+      same = same && y.x == x0 && (k + 1 >= npos || y.y == x0) && (k + 2 >= npos || y.z == x0) && (k + 3 >= npos || y.w == x0);
+    }
+    same = __all_sync(FULL, same);
+    if (lane == 0) { flag[(size_t)s * v.n_tiles + tile_id] = same ? 0u : 1u; val[(size_t)s * v.n_tiles + tile_id] = __uint_as_float(x0); }
+  }
+}
+
+// slot[i] = exclusive prefix of the flags (slot[3 * n_tiles] = lanes that travel in full); desc[i] = slot or 0xffffffff
+__global__ void __launch_bounds__(256) cov_pack_gather_kernel(DevBatchView v, const uint32_t* __restrict__ slot, uint32_t* __restrict__ desc,
+                                                              float* __restrict__ raw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= v.n_tiles) return;
+  uint32_t recw = 0;
+  if (lane < 8) recw = __ldg(reinterpret_cast<const uint32_t*>(v.tile_plan + w) + lane);
+  const uint32_t gbase = __shfl_sync(FULL, recw, 0), i0 = __shfl_sync(FULL, recw, 1);
+  const uint32_t npos = __shfl_sync(FULL, recw, 5), tile_id = __shfl_sync(FULL, recw, 6);
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+    const size_t i = (size_t)s * v.n_tiles + tile_id;
+    const uint32_t a = __ldg(slot + i), z = __ldg(slot + i + 1);
+    if (lane == 0) desc[i] = z != a ? a : 0xffffffffu;
+    if (z == a) continue;
+    const uint4* p = reinterpret_cast<const uint4*>(v.bpcov + (size_t)s * v.cov_pitch + gbase + i0);
+    uint4* o = reinterpret_cast<uint4*>(raw + (size_t)a * STG_TILE_W);
+    for (uint32_t q = lane; q * 4 < npos; q += 32) __stcs(o + q, __ldcs(p + q));
+  }
+}
+
+cudaError_t launch_cov_pack_flag(const DevBatchView& v, uint32_t* flag, float* val, cudaStream_t st) {
+  if (v.n_tiles == 0) return cudaSuccess;
+  cov_pack_flag_kernel<<<(unsigned)((v.n_tiles * 32 + 255) / 256), 256, 0, st>>>(v, flag, val);
+  return cudaGetLastError();
+}
+cudaError_t launch_cov_pack_gather(const DevBatchView& v, const uint32_t* slot, uint32_t* desc, float* raw, cudaStream_t st) {
+  if (v.n_tiles == 0) return cudaSuccess;
+  cov_pack_gather_kernel<<<(unsigned)((v.n_tiles * 32 + 255) / 256), 256, 0, st>>>(v, slot, desc, raw);
+  return cudaGetLastError();
+}
+
+
 // per (bundle, lane): get_cov(s, 0, len-2) — the summed clamped coverage of the whole bundle
 __global__ void cov_totals_kernel(DevBatchView v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -356,9 +356,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ uint32_t cluster_cta_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 
-__global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel(DevBatchView v, GroupsView g, JuncParams prm,
-                                                                                  uint32_t order_base) {
-  const uint32_t cid = blockIdx.x / CLUSTER_CTAS;                 // which oversized bundle
+// one oversized bundle (order[order_base + cid]) walked by the calling cluster
+__device__ void cluster_walk_bundle(const DevBatchView& v, const GroupsView& g, const JuncParams& prm, uint32_t order_base, uint32_t cid) {
   const uint32_t crank = cluster_cta_rank();
   const uint32_t b = g.order[order_base + cid];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -633,6 +632,25 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel
       g.b_startgroup[3 * b] = S.startg.a; g.b_startgroup[3 * b + 1] = S.startg.b; g.b_startgroup[3 * b + 2] = S.startg.c;
     }
   }
+  __syncwarp();   // the boss's warp leaves together: the caller goes on to an aligned cluster barrier
+}
+
+// Persistent clusters: as many as the GPU holds at once (launch_groups_walk), each drawing the next oversized bundle (longest
+// first) from a ticket.  A cluster that had to be scheduled in the middle of the stage would wait for 8 SMs of one GPC to be
+// free at the same moment, which the small CTAs of the other walk kernels hardly ever allow; a resident one just goes on.
+__global__ void __launch_bounds__(CLUSTER_THREADS, 1) groups_walk_cluster_kernel(DevBatchView v, GroupsView g, JuncParams prm,
+                                                                                  uint32_t order_base, uint32_t n_cluster) {
+  const uint32_t slot = blockIdx.x / CLUSTER_CTAS;                // this cluster
+  volatile uint32_t* mine = g.cl_ticket + 1 + slot;
+  for (;;) {
+    if (cluster_cta_rank() == 0 && threadIdx.x == 0) *mine = atomicAdd(g.cl_ticket, 1u);
+    __syncwarp();
+    cluster_sync_all();
+    const uint32_t cid = *mine;
+    cluster_sync_all();          // everyone has it before the slot is written again
+    if (cid >= n_cluster) break;
+    cluster_walk_bundle(v, g, prm, order_base, cid);
+  }
 }
 
 // compaction of the colour tables, one thread per colour of the batch: its bundle is found by bisection of the prefix b_ncol
@@ -751,11 +769,20 @@ cudaError_t launch_groups_walk(const DevBatchView& v, const GroupsView& g, const
     if ((e = cudaStreamWaitEvent(aux3, fork, 0)) == cudaSuccess) {
       forked_aux3 = true;
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)(n_cluster * CLUSTER_CTAS)); cfg.blockDim = dim3(CLUSTER_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = aux3;
+      cfg.gridDim = dim3((unsigned)CLUSTER_CTAS); cfg.blockDim = dim3(CLUSTER_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = aux3;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CLUSTER_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      e = cudaLaunchKernelEx(&cfg, groups_walk_cluster_kernel, v, g, p, 0u);
+      static int resident = 0;   // clusters the device holds at once (they are persistent: see the kernel)
+      if (!resident) {
+        int nc = 0;
+        cfg.gridDim = dim3((unsigned)(64 * CLUSTER_CTAS));
+        if (cudaOccupancyMaxActiveClusters(&nc, groups_walk_cluster_kernel, &cfg) != cudaSuccess || nc < 1) { cudaGetLastError(); nc = 8; }
+        resident = nc;
+      }
+      const int64_t nclu = n_cluster < resident ? n_cluster : resident;
+      cfg.gridDim = dim3((unsigned)(nclu * CLUSTER_CTAS));
+      e = cudaLaunchKernelEx(&cfg, groups_walk_cluster_kernel, v, g, p, 0u, (uint32_t)n_cluster);
     }
   }
   if (e == cudaSuccess && n_deep > n_cluster) {   // the deep bundles next to the shallow mass

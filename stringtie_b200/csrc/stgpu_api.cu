@@ -1,5 +1,8 @@
 // stgpu_api.cu — host side of libstgpu: the C ABI of include/stgpu.h, the bundle batcher, HBM layout planning,
 // kernel sequencing and result fetch.  No CPU compute path exists here: without a CUDA device stg_init fails.
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include "stgpu_internal.h"
 #include "asm_device.cuh"
 #include <algorithm>
@@ -131,6 +134,11 @@ struct stg_dbatch {
   std::vector<int64_t> h_cov_off;  // [n_bundles] float offset of lane 0 of bundle b (= gbase)
   std::vector<int64_t> h_stride;   // [n_bundles] distance between the strand lanes of bundle b (= total_pos: the lanes are batch-wide)
   std::vector<uint32_t> h_len;
+  std::vector<uint32_t> h_tile_off;   // [n_bundles + 1] first sub-tile of every bundle
+  uint32_t* pk_desc = nullptr; float* pk_val = nullptr; float* pk_raw = nullptr;   // packed bpcov (stg_pack_bpcov)
+  int64_t pk_nraw = -1, pk_raw_cap = 0;
+  size_t pk_mark = 0;                  // allocs.size() when the packed form was first allocated
+  bool released = false;               // stg_release_device: no device memory behind the handle any more
   std::vector<int32_t> h_start;    // [n_bundles] BundleData::start
   int64_t ivl_capacity = 0;     // intervals the interval / event / chunk arrays can hold
   int64_t cell_capacity = 0;    // counter cells of the binning matrix
@@ -586,6 +594,7 @@ int stg_upload(stg_ctx* ctx, const stg_packed_batch* h, stg_dbatch** out) {
     if (g >= 0xffffffffull || t >= 0xffffffffull) { delete d; return fail(ctx, STG_ERANGE, "batch spans more than 2^32 positions; split it"); }
   }
   gbase[nb] = (uint32_t)g; tile_off[nb] = (uint32_t)t;
+  d->h_tile_off = tile_off;
   v.total_pos = (int64_t)g; v.n_tiles = (int64_t)t;
   v.cov_pitch = (size_t)g;
   for (int64_t b = 0; b < nb; b++) d->h_stride[b] = (int64_t)g;
@@ -660,9 +669,24 @@ int stg_free_batch(stg_ctx* ctx, stg_dbatch* d) {
   return STG_OK;
 }
 
+// The device memory of a batch goes back to the pool; the handle stays valid for stg_unpack_bpcov (host-side layout tables)
+// until stg_free_batch.
+int stg_release_device(stg_ctx* ctx, stg_dbatch* d) {
+  if (!ctx || !d) return fail(ctx, STG_EINVAL, "stg_release_device: null argument");
+  cudaSetDevice(ctx->device);
+  if (d->ev_uploaded) cudaEventSynchronize(d->ev_uploaded);
+  cudaStreamSynchronize(ctx->stream);
+  if (d->out_pending) { cudaStreamSynchronize(ctx->out_stream); d->out_pending = false; }
+  free_batch_allocs(ctx, d);
+  d->ran = false; d->groups_built = false; d->neutral_done = false; d->assembled = false; d->released = true;
+  d->pk_desc = nullptr; d->pk_val = nullptr; d->pk_raw = nullptr; d->pk_raw_cap = 0; d->pk_nraw = -1;
+  return STG_OK;
+}
+
 // ---- run: the kernel sequence of the stage -----------------------------------------------------------------
 int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   if (!ctx || !d) return fail(ctx, STG_EINVAL, "stg_run: null argument");
+  if (d->released) return fail(ctx, STG_EINVAL, "stg_run: the batch's device memory has been released");
   CK(ctx, cudaSetDevice(ctx->device));
   DevBatchView& v = d->v;
   cudaStream_t st = ctx->stream;
@@ -836,47 +860,100 @@ int stg_fetch_bpcov_bundle_lane(stg_ctx* ctx, const stg_dbatch* d, int64_t b, in
   return STG_OK;
 }
 
-// Lanes 0 and 2 of the listed bundles into a host buffer laid out like the device's (lane s of bundle b at s * total_floats / 3 +
-// cov_off[b]), queued on the copy-out stream: complete after stg_fetch_wait.
-int stg_fetch_bpcov_strand_lanes_begin(stg_ctx* ctx, stg_dbatch* d, int64_t n, const int64_t* bundles, float* out) {
-  if (!ctx || !d || n < 0 || (n && (!bundles || !out))) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_strand_lanes_begin: bad argument");
-  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_strand_lanes_begin: batch has not been run");
-  for (int64_t i = 0; i < n; i++)
-    if (bundles[i] < 0 || bundles[i] >= d->v.n_bundles) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_strand_lanes_begin: bad bundle");
+// bpcov packed for the trip to the host (kernels K11b, cov_kernels.cu)
+int stg_pack_bpcov(stg_ctx* ctx, stg_dbatch* d, int64_t* n_tiles, int64_t* n_raw) {
+  if (!ctx || !d) return fail(ctx, STG_EINVAL, "stg_pack_bpcov: null argument");
+  if (!d->ran) return fail(ctx, STG_EINVAL, "stg_pack_bpcov: batch has not been run");
   CK(ctx, cudaSetDevice(ctx->device));
-  CK(ctx, cudaStreamWaitEvent(ctx->out_stream, d->ev_cov, 0));
-  d->out_pending = true;
-  for (int64_t i = 0; i < n; i++)
-    for (int lane = 0; lane < 3; lane += 2) {
-      const size_t o = (size_t)lane * d->v.cov_pitch + (size_t)d->h_cov_off[bundles[i]];
-      CK(ctx, cudaMemcpyAsync(out + o, d->v.bpcov + o, sizeof(float) * (size_t)d->h_len[bundles[i]], cudaMemcpyDeviceToHost, ctx->out_stream));
-    }
+  cudaStream_t st = ctx->stream;
+  const DevBatchView& v = d->v;
+  const int64_t nt3 = 3 * v.n_tiles;
+  if (n_tiles) *n_tiles = v.n_tiles;
+  if (n_raw) *n_raw = 0;
+  d->pk_nraw = 0;
+  if (nt3 == 0) return STG_OK;
+  StageScope stage_scope(ctx);
+  int rc = STG_OK;
+  stg_dbatch tmp;
+  struct Release { stg_ctx* c; stg_dbatch* t; ~Release() { cudaStreamSynchronize(c->stream); free_batch_allocs(c, t); } } release{ctx, &tmp};
+  uint32_t *slot = nullptr, *ticket = nullptr; unsigned long long* state = nullptr;
+  if ((rc = dev_alloc(ctx, &tmp, &slot, nt3 + 1 + 16)) || (rc = dev_alloc(ctx, &tmp, &ticket, 1)) || (rc = dev_alloc(ctx, &tmp, &state, nt3 / 4096 + 4))) return rc;
+  if (!d->pk_desc) d->pk_mark = d->allocs.size();
+  if (!d->pk_desc && ((rc = dev_alloc(ctx, d, &d->pk_desc, nt3)) || (rc = dev_alloc(ctx, d, &d->pk_val, nt3)))) return rc;
+  uint32_t total = 0;
+  {
+    Scope s(ctx, "cov_pack_flag+scan", 2);
+    CK(ctx, cudaMemsetAsync(slot + nt3, 0, sizeof(uint32_t), st));
+    CK(ctx, launch_cov_pack_flag(v, slot, d->pk_val, st));
+    CK(ctx, launch_scan_exclusive_add(slot, nt3 + 1, state, ticket, st));
+  }
+  CK(ctx, small_d2h(ctx, &total, slot + nt3, 4, st));
+  CK(ctx, small_sync(ctx, st));
+  if ((int64_t)total > d->pk_raw_cap) {
+    const int64_t cap = (int64_t)total + (int64_t)total / 8 + 64;
+    if ((rc = dev_alloc(ctx, d, &d->pk_raw, cap * STG_TILE_W))) return rc;
+    d->pk_raw_cap = cap;
+  }
+  {
+    Scope s(ctx, "cov_pack_gather", 1);
+    CK(ctx, launch_cov_pack_gather(v, slot, d->pk_desc, d->pk_raw, st));
+  }
+  CK(ctx, cudaEventRecord(d->ev_cov, st));   // the copy-out stream waits for this event
+  d->pk_nraw = total;
+  if (n_raw) *n_raw = total;
   return STG_OK;
 }
 
-// Bundles whose strand lanes (bpcov[0], bpcov[2]) the reference's printResults reads: the only place is the strand check of
-// a single-exon prediction that carries a strand (rlink.cpp:18453-18459 and :18524-18531); every other use of bpcov after
-// infer_transcripts goes to lane 1.
-int stg_strand_lane_bundles(stg_ctx* ctx, const stg_dbatch* d, int64_t cap, int64_t* bundles, int64_t* n_out) {
-  if (!ctx || !d || !n_out || cap < 0 || (cap && !bundles)) return fail(ctx, STG_EINVAL, "stg_strand_lane_bundles: bad argument");
-  if (!d->assembled) return fail(ctx, STG_EINVAL, "stg_strand_lane_bundles: batch has not been assembled");
-  const int64_t nb = d->v.n_bundles, np = d->av.n_pred;
-  *n_out = 0;
-  if (np == 0) return STG_OK;
-  std::vector<uint32_t> poff(nb + 1), xo(np + 1);
-  std::vector<int8_t> st(np);
-  int rc = stg_fetch_asm_array(ctx, d, STG_AA_PRED_OFF, 0, nb + 1, poff.data());
-  if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_STRAND, 0, np, st.data());
-  if (!rc) rc = stg_fetch_asm_array(ctx, d, STG_AA_P_EXON_OFF, 0, np + 1, xo.data());
-  if (rc) return rc;
-  int64_t k = 0;
-  for (int64_t b = 0; b < nb; b++) {
-    bool need = false;
-    for (uint32_t q = poff[b]; q < poff[b + 1] && !need; q++) need = xo[q + 1] - xo[q] == 1 && st[q] != '.';
-    if (need) { if (k < cap) bundles[k] = b; k++; }
+int stg_fetch_bpcov_packed_begin(stg_ctx* ctx, stg_dbatch* d, uint32_t* desc, float* val, float* raw) {
+  if (!ctx || !d || !desc || !val) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_packed_begin: bad argument");
+  if (d->pk_nraw < 0) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_packed_begin: stg_pack_bpcov has not run on this batch");
+  if (d->pk_nraw && !raw) return fail(ctx, STG_EINVAL, "stg_fetch_bpcov_packed_begin: bad argument");
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaStreamWaitEvent(ctx->out_stream, d->ev_cov, 0));
+  d->out_pending = true;
+  const size_t nt3 = 3 * (size_t)d->v.n_tiles;
+  if (nt3) {
+    CK(ctx, copy_chunked(desc, d->pk_desc, sizeof(uint32_t) * nt3, cudaMemcpyDeviceToHost, ctx->out_stream));
+    CK(ctx, copy_chunked(val, d->pk_val, sizeof(float) * nt3, cudaMemcpyDeviceToHost, ctx->out_stream));
   }
-  *n_out = k;
-  if (k > cap) return fail(ctx, STG_ERANGE, "stg_strand_lane_bundles: more bundles than the caller's array holds");
+  if (d->pk_nraw) CK(ctx, copy_chunked(raw, d->pk_raw, sizeof(float) * (size_t)d->pk_nraw * STG_TILE_W, cudaMemcpyDeviceToHost, ctx->out_stream));
+  return STG_OK;
+}
+
+// host only: BundleData::bpcov of bundles [b0, b1) from the packed form, laid out like stg_fetch_bpcov_all's buffer
+int stg_unpack_bpcov(const stg_dbatch* d, int64_t b0, int64_t b1, const uint32_t* desc, const float* val, const float* raw, float* out) {
+  if (!d || !desc || !val || !out || b0 < 0 || b1 > d->v.n_bundles || b0 > b1) return fail(nullptr, STG_EINVAL, "stg_unpack_bpcov: bad argument");
+  const size_t nt = (size_t)d->v.n_tiles, pitch = (size_t)d->v.total_pos;
+  for (int64_t b = b0; b < b1; b++) {
+    const uint32_t t0 = d->h_tile_off[b], t1 = d->h_tile_off[b + 1], len = d->h_len[b];
+    for (int s = 0; s < 3; s++) {
+      float* o = out + (size_t)s * pitch + (size_t)d->h_cov_off[b];
+      for (uint32_t t = t0; t < t1; t++) {
+        const uint32_t p0 = (t - t0) * STG_TILE_W, n = len - p0 < STG_TILE_W ? len - p0 : STG_TILE_W;
+        const uint32_t ds = desc[s * nt + t];
+        // the arrays are written once and read much later (printResults): streaming stores, no read-for-ownership traffic
+        if (ds == 0xffffffffu) {
+          const float x = val[s * nt + t];
+          uint32_t i = 0;
+#if defined(__SSE2__)
+          if ((((uintptr_t)(o + p0)) & 15u) == 0) { const __m128 x4 = _mm_set1_ps(x); for (; i + 4 <= n; i += 4) _mm_stream_ps(o + p0 + i, x4); }
+#endif
+          for (; i < n; i++) o[p0 + i] = x;
+        } else {
+          if (!raw) return fail(nullptr, STG_EINVAL, "stg_unpack_bpcov: bad argument");
+          const float* r = raw + (size_t)ds * STG_TILE_W;
+          uint32_t i = 0;
+#if defined(__SSE2__)
+          if (((((uintptr_t)(o + p0)) | (uintptr_t)r) & 15u) == 0) for (; i + 4 <= n; i += 4) _mm_stream_ps(o + p0 + i, _mm_load_ps(r + i));
+#endif
+          for (; i < n; i++) o[p0 + i] = r[i];
+        }
+      }
+    }
+  }
+#if defined(__SSE2__)
+  _mm_sfence();
+#endif
   return STG_OK;
 }
 
@@ -1157,6 +1234,8 @@ int stg_build_groups(stg_ctx* ctx, stg_dbatch* d) {
     TEMP(rec_raw, (int64_t)groups_cluster_rec_bytes() * std::max<int64_t>(n_cluster, 1));
     g.cl_ctl = (void*)ctl_raw; g.cl_rec = (FastRec*)(void*)rec_raw;
     TEMP(g.cl_claim, std::max<int64_t>(vr, 1));
+    TEMP(g.cl_ticket, 1 + 256);
+    CK(ctx, cudaMemsetAsync(g.cl_ticket, 0, sizeof(uint32_t) * 257, st));
     CK(ctx, cudaMemsetAsync(g.cl_claim, 0x7f, sizeof(int32_t) * (size_t)std::max<int64_t>(vr, 1), st));
   }
   { Scope s(ctx, "groups_walk", 3);
@@ -1367,6 +1446,7 @@ int stg_rewind(stg_ctx* ctx, stg_dbatch* d) {
     for (size_t i = d->stage_mark; i < d->allocs.size(); i++) { ctx->pool_free.push_back(d->allocs[i]); ctx->pool_bytes += d->allocs[i].bytes; }
   }
   d->allocs.resize(d->stage_mark);
+  if (d->pk_desc && d->pk_mark >= d->stage_mark) { d->pk_desc = nullptr; d->pk_val = nullptr; d->pk_raw = nullptr; d->pk_raw_cap = 0; d->pk_nraw = -1; }
   d->groups_built = false; d->neutral_done = false; d->assembled = false;
   return STG_OK;
 }
@@ -1644,23 +1724,15 @@ int stg_infer_transcripts_batch(stg_ctx* ctx, int64_t n, const stg_bundle_view* 
   if (n == 0) return STG_OK;
   if (!(rc = stg_builder_packed(b, &pb)) && !(rc = stg_upload(ctx, &pb, &d)) && !(rc = stg_run(ctx, d))) {
     // bpcov and the junction support of every bundle that asked for them: the copies are queued together, one wait
-    // (a bundle that goes on to the assembly gets lane 1 now and its strand lanes only if a prediction will make the host
-    // read them: stg_strand_lane_bundles)
-    for (int64_t i = 0; i < n && !rc; i++) {
-      results[i].strand_lanes = 0;
+    // (all three strand lanes: the reference's printResults reads lane 1 nearly everywhere, but its gene-coverage pass sums every
+    // lane over the exons of every gene, rlink.cpp:20232-20236)
+    for (int64_t i = 0; i < n && !rc; i++)
       if (results[i].bpcov) {
         const size_t len = d->h_len[i];
-        cudaError_t ce;
-        if (results[i].assemble)
-          ce = cudaMemcpyAsync(results[i].bpcov + len, d->v.bpcov + d->v.cov_pitch + d->h_cov_off[i], len * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-        else {
-          ce = cudaMemcpy2DAsync(results[i].bpcov, len * sizeof(float), d->v.bpcov + d->h_cov_off[i], (size_t)d->h_stride[i] * sizeof(float),
-                                 len * sizeof(float), 3, cudaMemcpyDeviceToHost, ctx->stream);
-          results[i].strand_lanes = 1;
-        }
-        if (ce != cudaSuccess) rc = fail(ctx, STG_ECUDA, "stg_infer_transcripts_batch: copy of bpcov failed");
+        if (cudaMemcpy2DAsync(results[i].bpcov, len * sizeof(float), d->v.bpcov + d->h_cov_off[i], (size_t)d->h_stride[i] * sizeof(float),
+                              len * sizeof(float), 3, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+          rc = fail(ctx, STG_ECUDA, "stg_infer_transcripts_batch: copy of bpcov failed");
       }
-    }
     if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, STG_ECUDA, "stg_infer_transcripts_batch: stream failed");
     OneBundleOut& o = ctx->one_out;
     if (!rc && pb.n_juncs) {
@@ -1734,19 +1806,7 @@ int stg_infer_transcripts_batch(stg_ctx* ctx, int64_t n, const stg_bundle_view* 
           r.p_start = o.p_start.data() + p0; r.p_end = o.p_end.data() + p0; r.p_cov = o.p_cov.data() + p0; r.p_tlen = o.p_tlen.data() + p0;
           r.p_geneno = o.p_geneno.data() + p0; r.p_strand = o.p_strand.data() + p0; r.p_exon_off = o.p_exon_off.data() + x0;
           r.e_start = o.e_start.data() + e0; r.e_end = o.e_end.data() + e0; r.e_cov = o.e_cov.data() + e0;
-          // the strand lanes of bpcov, where the reference's printResults will look at them (rlink.cpp:18453-18459, :18524-18531)
-          bool need = false;
-          for (uint32_t q = poff[i]; q < poff[i + 1] && !need; q++) need = xo[q + 1] - xo[q] == 1 && gst[q] != '.';
-          if (need && r.bpcov) {
-            const size_t len = d->h_len[i];
-            if (cudaMemcpyAsync(r.bpcov, d->v.bpcov + d->h_cov_off[i], len * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-                cudaMemcpyAsync(r.bpcov + 2 * len, d->v.bpcov + 2 * d->v.cov_pitch + d->h_cov_off[i], len * sizeof(float), cudaMemcpyDeviceToHost,
-                                ctx->stream) != cudaSuccess)
-              rc = fail(ctx, STG_ECUDA, "stg_infer_transcripts_batch: copy of bpcov failed");
-            r.strand_lanes = 1;
-          }
         }
-        if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, STG_ECUDA, "stg_infer_transcripts_batch: stream failed");
       }
     }
   }

@@ -115,6 +115,7 @@ struct GroupsView {
   int32_t *jt_perm, *jt_inv;   // [n_juncs + n_introns] bundle b at b_junc_off[b] + intron base of b
   // very deep bundles (order[0 .. n_vdeep)): log of the ordered part of every simple read; read r of the i-th at vlog_off[i] + r
   const uint32_t* vlog_off; int32_t* vlog_grp; float2 *vlog_val, *vlog_sorted; double *vlog_fl, *vlog_nf;
+  uint32_t* cl_ticket;   // [1 + clusters]: next oversized bundle, and the one every resident cluster is walking
   void* cl_ctl; struct FastRec* cl_rec; int32_t* cl_claim;   // oversized bundles (order[0 .. n_cluster)): control block, window records, claims
   // sparse groups / colours / readgroup
   uint32_t *g_start, *g_end; int32_t *g_color, *g_next, *g_merge, *g_grid; float *g_cov, *g_multi; int8_t* g_alive;
@@ -241,6 +242,8 @@ cudaError_t launch_bin_columns(const DevBatchView& v, cudaStream_t st);     // +
 cudaError_t launch_bin_scatter(const DevBatchView& v, cudaStream_t st);
 cudaError_t launch_junc_anchor(const DevBatchView& v, const KernelParams& p, cudaStream_t st);
 cudaError_t launch_tile_plan(const DevBatchView& v, cudaStream_t st);
+cudaError_t launch_cov_pack_flag(const DevBatchView& v, uint32_t* flag, float* val, cudaStream_t st);
+cudaError_t launch_cov_pack_gather(const DevBatchView& v, const uint32_t* slot, uint32_t* desc, float* raw, cudaStream_t st);
 cudaError_t launch_chain_selftest(int64_t n, const uint32_t* off, const float* x, const float* s0, float* out, int plain, cudaStream_t st);
 cudaError_t launch_deep_deposit(const DevBatchView& v, int num_sms, cudaStream_t st);
 cudaError_t launch_cov_tiles(const DevBatchView& v, int num_sms, cudaStream_t st);

@@ -23,7 +23,7 @@ EXPORTS = [
     "stg_builder_add", "stg_builder_packed", "stg_builder_reset", "stg_builder_destroy", "stg_upload", "stg_run",
     "stg_sync", "stg_free_batch", "stg_trim", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
     "stg_upload_wait", "stg_fetch_bpcov_all_begin", "stg_fetch_wait", "stg_fetch_bpcov_lane_begin", "stg_fetch_bpcov_bundle_lane",
-    "stg_strand_lane_bundles", "stg_fetch_bpcov_strand_lanes_begin",
+    "stg_pack_bpcov", "stg_fetch_bpcov_packed_begin", "stg_unpack_bpcov", "stg_release_device",
     "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_trims_capacity", "stg_find_trims", "stg_infer_transcripts", "stg_infer_transcripts_batch",
     "stg_build_groups", "stg_groups_array_info", "stg_fetch_groups_array", "stg_neutral_predictions",
     "stg_assemble", "stg_asm_array_info", "stg_fetch_asm_array", "stg_rewind", "stg_reduce_totals",
@@ -97,8 +97,10 @@ def load_library() -> C.CDLL:
     L.stg_fetch_bpcov_all_begin.argtypes = [vp, vp, c_f32p]
     L.stg_fetch_bpcov_lane_begin.argtypes = [vp, vp, C.c_int, c_f32p]
     L.stg_fetch_bpcov_bundle_lane.argtypes = [vp, vp, C.c_int64, C.c_int, c_f32p]
-    L.stg_strand_lane_bundles.argtypes = [vp, vp, C.c_int64, c_i64p, c_i64p]
-    L.stg_fetch_bpcov_strand_lanes_begin.argtypes = [vp, vp, C.c_int64, c_i64p, c_f32p]
+    L.stg_pack_bpcov.argtypes = [vp, vp, c_i64p, c_i64p]
+    L.stg_release_device.argtypes = [vp, vp]
+    L.stg_fetch_bpcov_packed_begin.argtypes = [vp, vp, C.POINTER(C.c_uint32), c_f32p, c_f32p]
+    L.stg_unpack_bpcov.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(C.c_uint32), c_f32p, c_f32p, c_f32p]
     L.stg_fetch_wait.argtypes = [vp, vp]
     L.stg_upload_wait.argtypes = [vp, vp]
     L.stg_device_bpcov.argtypes = [vp]
@@ -369,17 +371,26 @@ class Engine:
     def fetch_bpcov_bundle_lane(self, batch: DeviceBatch, bundle: int, lane: int, host_ptr: int) -> None:
         self._ck(self.L.stg_fetch_bpcov_bundle_lane(self.ctx, batch.handle, bundle, lane, C.cast(C.c_void_p(host_ptr), c_f32p)))
 
-    def fetch_bpcov_strand_lanes_begin(self, batch: DeviceBatch, bundles: np.ndarray, host_ptr: int) -> None:
-        """Lanes 0 / 2 of the listed bundles into a buffer laid out like fetch_bpcov_all's (copy-out stream; fetch_wait completes it)."""
-        bundles = np.ascontiguousarray(bundles, dtype=np.int64)
-        self._ck(self.L.stg_fetch_bpcov_strand_lanes_begin(self.ctx, batch.handle, bundles.size, ptr(bundles), C.cast(C.c_void_p(host_ptr), c_f32p)))
+    def release_device(self, batch: DeviceBatch) -> None:
+        """Device memory of the batch back to the pool; the handle stays good for unpack_bpcov until batch.free()."""
+        self._ck(self.L.stg_release_device(self.ctx, batch.handle))
 
-    def strand_lane_bundles(self, batch: DeviceBatch) -> np.ndarray:
-        """Bundles whose bpcov lanes 0 / 2 the reference's printResults reads (stg_strand_lane_bundles)."""
-        out = np.zeros(max(1, batch.n_bundles), dtype=np.int64)
-        n = C.c_int64(0)
-        self._ck(self.L.stg_strand_lane_bundles(self.ctx, batch.handle, out.size, ptr(out), C.byref(n)))
-        return out[:n.value].copy()
+    def pack_bpcov(self, batch: DeviceBatch):
+        """bpcov packed on the device for the trip to the host (stg_pack_bpcov): returns (n_tiles, n_raw)."""
+        nt, nr = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.stg_pack_bpcov(self.ctx, batch.handle, C.byref(nt), C.byref(nr)))
+        return int(nt.value), int(nr.value)
+
+    def fetch_bpcov_packed_begin(self, batch: DeviceBatch, desc_ptr: int, val_ptr: int, raw_ptr: int) -> None:
+        cast = lambda p, t: C.cast(C.c_void_p(p), t)
+        self._ck(self.L.stg_fetch_bpcov_packed_begin(self.ctx, batch.handle, cast(desc_ptr, C.POINTER(C.c_uint32)), cast(val_ptr, c_f32p),
+                                                     cast(raw_ptr, c_f32p)))
+
+    def unpack_bpcov(self, batch: DeviceBatch, b0: int, b1: int, desc_ptr: int, val_ptr: int, raw_ptr: int, out_ptr: int) -> None:
+        """Host side: bpcov of the bundles [b0, b1) from the packed form into a buffer laid out like fetch_bpcov_all's."""
+        cast = lambda p, t: C.cast(C.c_void_p(p), t)
+        self._ck(self.L.stg_unpack_bpcov(batch.handle, b0, b1, cast(desc_ptr, C.POINTER(C.c_uint32)), cast(val_ptr, c_f32p), cast(raw_ptr, c_f32p),
+                                         cast(out_ptr, c_f32p)))
 
     def fetch_bpcov_all_begin(self, batch: DeviceBatch, host_ptr: int) -> None:
         """Start the same copy on the copy-out stream (overlaps the group / assembly stages); fetch_wait completes it."""
@@ -469,13 +480,12 @@ class Engine:
                     "tlen": cp(res.p_tlen, m, np.int32), "geneno": cp(res.p_geneno, m, np.int32), "strand": cp(res.p_strand, m, np.int8),
                     "exon_off": cp(res.p_exon_off, m + 1, np.uint32) if m else np.zeros(1, dtype=np.uint32),
                     "e_start": cp(res.e_start, ne, np.uint32), "e_end": cp(res.e_end, ne, np.uint32), "e_cov": cp(res.e_cov, ne, np.float32)}
-            out.append((covs[i][0].reshape(3, covs[i][1]), pred, res.num_fragments, res.frag_len, bool(res.strand_lanes)))
+            out.append((covs[i][0].reshape(3, covs[i][1]), pred, res.num_fragments, res.frag_len))
         return out
 
     def infer_transcripts_full(self, arrays: Dict[str, np.ndarray], b: int = 0):
         """The whole of `infer_transcripts(BundleData*)` (rlink.h:380) for bundle b: returns (bpcov, predictions dict,
-        num_fragments, frag_len, strand_lanes); predictions = BundleData::pred in the reference's order; lanes 0 and 2 of
-        bpcov are filled only if strand_lanes (a single-exon prediction with a strand makes printResults read them)."""
+        num_fragments, frag_len); predictions = BundleData::pred in the reference's order."""
         view, keep = bundle_view(arrays, b)
         length = view.end - view.start + 3
         cov = np.zeros(3 * length, dtype=np.float32)
@@ -491,4 +501,4 @@ class Engine:
                 "tlen": cp(res.p_tlen, n, np.int32), "geneno": cp(res.p_geneno, n, np.int32), "strand": cp(res.p_strand, n, np.int8),
                 "exon_off": cp(res.p_exon_off, n + 1, np.uint32) if n else np.zeros(1, dtype=np.uint32),
                 "e_start": cp(res.e_start, ne, np.uint32), "e_end": cp(res.e_end, ne, np.uint32), "e_cov": cp(res.e_cov, ne, np.float32)}
-        return cov.reshape(3, length), pred, res.num_fragments, res.frag_len, bool(res.strand_lanes)
+        return cov.reshape(3, length), pred, res.num_fragments, res.frag_len
