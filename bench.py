@@ -304,7 +304,8 @@ def main():
         pb, keep = make_packed(parr)
         cov_host = None
         pk = None
-        host_threads = max(1, min(32, (os.cpu_count() or 4) - 3))   # the host's worker threads, less the ones that drive the GPU and the upload
+        # the host's worker threads: this rank's share of the cores, less the two that drive the GPU and the upload
+        host_threads = max(1, min(32, (os.cpu_count() or 4) // max(1, world) - 2))
         if not args.e2e_no_bpcov:
             try:   # BundleData::bpcov of every bundle comes back too: the reference's printResults reads it on the host
                 b0 = eng.upload_packed(pb, keep)

@@ -91,3 +91,16 @@ def test_builder_rejects_bad_view():
     assert L.stg_builder_add(bld, C.byref(v)) == -1
     assert b"bad view" in L.stg_last_error(None)
     L.stg_builder_destroy(bld)
+
+
+def test_sass_has_no_contracted_multiply_add_and_uses_bulk_stores():
+    """tools/sass_check.py on the built library: every FFMA / DFMA belongs to a division / square-root expansion (the build is
+    -fmad=false: a contracted product-sum would change bits against the reference), and cov_fill stores its flat rows with
+    cp.async.bulk (UBLKCP in SASS)."""
+    import subprocess, sys, shutil
+    if shutil.which("cuobjdump") is None:
+        import pytest
+        pytest.skip("cuobjdump not on PATH")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_check.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "cov_fill_kernel" in r.stdout.split("bulk copies (UBLKCP):")[1].splitlines()[0]
