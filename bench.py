@@ -304,8 +304,11 @@ def main():
         pb, keep = make_packed(parr)
         cov_host = None
         pk = None
-        # the host's worker threads: this rank's share of the cores, less the two that drive the GPU and the upload
-        host_threads = max(1, min(32, (os.cpu_count() or 4) // max(1, world) - 2))
+        max_len = 0
+        # the host's worker threads: this rank's share of the cores, less the ones that drive the GPU and the upload
+        host_threads = max(1, min(6, (os.cpu_count() or 4) // max(1, world) - 3))
+        if os.environ.get("STGPU_BENCH_UNPACK_THREADS"):
+            host_threads = max(1, int(os.environ["STGPU_BENCH_UNPACK_THREADS"]))
         if not args.e2e_no_bpcov:
             try:   # BundleData::bpcov of every bundle comes back too: the reference's printResults reads it on the host
                 b0 = eng.upload_packed(pb, keep)
@@ -313,7 +316,8 @@ def main():
                 cov_floats = eng.cov_total_floats(b0)
                 nt, nraw = eng.pack_bpcov(b0)
                 b0.free()
-                cov_host = torch.empty(cov_floats, dtype=torch.float32)   # where the host's worker threads unpack to
+                cov_host = True   # (bpcov comes back; the workers unpack it bundle by bundle into their own arrays)
+                max_len = int((arrays["b_end"].astype(np.int64) - arrays["b_start"].astype(np.int64) + 3).max())
                 cap = nraw + nraw // 8 + 64
                 pk = [{"desc": torch.empty(3 * nt, dtype=torch.int32).pin_memory(), "val": torch.empty(3 * nt, dtype=torch.float32).pin_memory(),
                        "raw": torch.empty(cap * 512, dtype=torch.float32).pin_memory(), "cap": cap} for _ in range(2)]
@@ -373,8 +377,11 @@ def main():
                 eng.release_device(b)      # device memory back to the pool; the handle keeps the layout tables for the unpacking
                 nb_ = b.n_bundles
                 step = (nb_ + 4 * host_threads - 1) // (4 * host_threads)
-                futs = [unpackers.submit(eng.unpack_bpcov, b, lo, min(nb_, lo + step), pk[k]["desc"].data_ptr(), pk[k]["val"].data_ptr(),
-                                         pk[k]["raw"].data_ptr(), cov_host.data_ptr()) for lo in range(0, nb_, step)]
+                def unpack_share(lo, hi, k=k, b=b):
+                    # a worker thread: BundleData::bpcov of its bundles, one after the other, in its own (reused) arrays
+                    return eng.unpack_bpcov_stream(b, lo, hi, pk[k]["desc"].data_ptr(), pk[k]["val"].data_ptr(), pk[k]["raw"].data_ptr(),
+                                                   np.empty(3 * max_len, dtype=np.float32))
+                futs = [unpackers.submit(unpack_share, lo, min(nb_, lo + step)) for lo in range(0, nb_, step)]
                 pending.append((b, futs))
                 seq[0] += 1
             else:
@@ -429,8 +436,9 @@ def main():
                          "BundleData::pred (neutral and graph predictions with exons), num_fragments, frag_len and — unless "
                          "--e2e-no-bpcov — ALL of bpcov (the reference's printResults, which stays on the host, reads the three lanes): packed on "
                          "the device behind the coverage stage (a sub-tile lane that repeats one value travels as that value: "
-                         "stg_pack_bpcov), copied on the copy-out stream into pinned memory and unpacked into the bundles' arrays by "
-                         "the host's worker threads (stg_unpack_bpcov) while the next batch computes + "
+                         "stg_pack_bpcov), copied on the copy-out stream into pinned memory and unpacked by the host's worker threads, "
+                         "every bundle into the thread's own reused arrays as the reference's workers hold BundleData::bpcov "
+                         "(stg_unpack_bpcov_stream), while the next batch computes + "
                          "stg_free_batch.  The upload of batch i+1 is issued while batch i computes, as the bundle queue of the "
                          "host does; every H2D and D2H byte of the n batches is inside the timed region.  single_batch_ms is one "
                          "batch alone (nothing to overlap its upload with).  Max over ranks"}

@@ -206,6 +206,13 @@ int stg_pack_bpcov(stg_ctx* ctx, stg_dbatch* batch, int64_t* n_tiles, int64_t* n
 int stg_fetch_bpcov_packed_begin(stg_ctx* ctx, stg_dbatch* batch, uint32_t* desc, float* val, float* raw);
 int stg_unpack_bpcov(const stg_dbatch* batch, int64_t b0, int64_t b1, const uint32_t* desc, const float* val, const float* raw,
                      float* out /*[total_floats]*/);
+/* One bundle into its own arrays (lane-major, [3 * len_b]: BundleData::bpcov as stg_fetch_bpcov returns it): the call of a host
+ * adaptor's worker thread; and the same for a worker's share [b0, b1) of a batch, bundle after bundle into ONE set of working
+ * arrays (the reference reuses its BundleData from bundle to bundle, bundle.h:398-405), with a checksum of what was written. */
+int stg_unpack_bpcov_bundle(const stg_dbatch* batch, int64_t bundle, const uint32_t* desc, const float* val, const float* raw,
+                            float* out /*[3 * len_b]*/);
+int stg_unpack_bpcov_stream(const stg_dbatch* batch, int64_t b0, int64_t b1, const uint32_t* desc, const float* val, const float* raw,
+                            float* work, int64_t work_floats, double* check);
 int stg_fetch_wait(stg_ctx* ctx, stg_dbatch* batch);
 const float* stg_device_bpcov(const stg_dbatch* batch); /* device pointer (for consumers that stay on the GPU) */
 /* CJunction::nreads_good / leftsupport / rightsupport after the stage; each [n_juncs] */

@@ -921,39 +921,79 @@ int stg_fetch_bpcov_packed_begin(stg_ctx* ctx, stg_dbatch* d, uint32_t* desc, fl
 }
 
 // host only: BundleData::bpcov of bundles [b0, b1) from the packed form, laid out like stg_fetch_bpcov_all's buffer
-int stg_unpack_bpcov(const stg_dbatch* d, int64_t b0, int64_t b1, const uint32_t* desc, const float* val, const float* raw, float* out) {
-  if (!d || !desc || !val || !out || b0 < 0 || b1 > d->v.n_bundles || b0 > b1) return fail(nullptr, STG_EINVAL, "stg_unpack_bpcov: bad argument");
-  const size_t nt = (size_t)d->v.n_tiles, pitch = (size_t)d->v.total_pos;
-  for (int64_t b = b0; b < b1; b++) {
-    const uint32_t t0 = d->h_tile_off[b], t1 = d->h_tile_off[b + 1], len = d->h_len[b];
-    for (int s = 0; s < 3; s++) {
-      float* o = out + (size_t)s * pitch + (size_t)d->h_cov_off[b];
-      for (uint32_t t = t0; t < t1; t++) {
-        const uint32_t p0 = (t - t0) * STG_TILE_W, n = len - p0 < STG_TILE_W ? len - p0 : STG_TILE_W;
-        const uint32_t ds = desc[s * nt + t];
-        // the arrays are written once and read much later (printResults): streaming stores, no read-for-ownership traffic
-        if (ds == 0xffffffffu) {
-          const float x = val[s * nt + t];
-          uint32_t i = 0;
+} // extern "C"
+namespace {
+// one strand lane of one bundle out of the packed form; STREAM: the destination is written once and read much later
+// (streaming stores, no read-for-ownership traffic), else it is the caller's working array (plain stores: it stays in cache)
+template <bool STREAM>
+inline bool unpack_lane(const stg_dbatch* d, int64_t b, int s, const uint32_t* desc, const float* val, const float* raw, float* o) {
+  const size_t nt = (size_t)d->v.n_tiles;
+  const uint32_t t0 = d->h_tile_off[b], t1 = d->h_tile_off[b + 1], len = d->h_len[b];
+  for (uint32_t t = t0; t < t1; t++) {
+    const uint32_t p0 = (t - t0) * STG_TILE_W, n = len - p0 < STG_TILE_W ? len - p0 : STG_TILE_W;
+    const uint32_t ds = desc[s * nt + t];
+    uint32_t i = 0;
+    if (ds == 0xffffffffu) {
+      const float x = val[s * nt + t];
 #if defined(__SSE2__)
-          if ((((uintptr_t)(o + p0)) & 15u) == 0) { const __m128 x4 = _mm_set1_ps(x); for (; i + 4 <= n; i += 4) _mm_stream_ps(o + p0 + i, x4); }
-#endif
-          for (; i < n; i++) o[p0 + i] = x;
-        } else {
-          if (!raw) return fail(nullptr, STG_EINVAL, "stg_unpack_bpcov: bad argument");
-          const float* r = raw + (size_t)ds * STG_TILE_W;
-          uint32_t i = 0;
-#if defined(__SSE2__)
-          if (((((uintptr_t)(o + p0)) | (uintptr_t)r) & 15u) == 0) for (; i + 4 <= n; i += 4) _mm_stream_ps(o + p0 + i, _mm_load_ps(r + i));
-#endif
-          for (; i < n; i++) o[p0 + i] = r[i];
-        }
+      {
+        const __m128 x4 = _mm_set1_ps(x);
+        if (STREAM && (((uintptr_t)(o + p0)) & 15u) == 0) for (; i + 4 <= n; i += 4) _mm_stream_ps(o + p0 + i, x4);
+        else for (; i + 4 <= n; i += 4) _mm_storeu_ps(o + p0 + i, x4);
       }
+#endif
+      for (; i < n; i++) o[p0 + i] = x;
+    } else {
+      if (!raw) return false;
+      const float* r = raw + (size_t)ds * STG_TILE_W;
+#if defined(__SSE2__)
+      if (STREAM && ((((uintptr_t)(o + p0)) | (uintptr_t)r) & 15u) == 0) for (; i + 4 <= n; i += 4) _mm_stream_ps(o + p0 + i, _mm_load_ps(r + i));
+#endif
+      if (i == 0) memcpy(o + p0, r, sizeof(float) * n);
+      else for (; i < n; i++) o[p0 + i] = r[i];
     }
   }
+  return true;
+}
+}  // namespace
+extern "C" {
+
+int stg_unpack_bpcov(const stg_dbatch* d, int64_t b0, int64_t b1, const uint32_t* desc, const float* val, const float* raw, float* out) {
+  if (!d || !desc || !val || !out || b0 < 0 || b1 > d->v.n_bundles || b0 > b1) return fail(nullptr, STG_EINVAL, "stg_unpack_bpcov: bad argument");
+  const size_t pitch = (size_t)d->v.total_pos;
+  for (int64_t b = b0; b < b1; b++)
+    for (int s = 0; s < 3; s++)
+      if (!unpack_lane<true>(d, b, s, desc, val, raw, out + (size_t)s * pitch + (size_t)d->h_cov_off[b]))
+        return fail(nullptr, STG_EINVAL, "stg_unpack_bpcov: bad argument");
 #if defined(__SSE2__)
   _mm_sfence();
 #endif
+  return STG_OK;
+}
+
+int stg_unpack_bpcov_bundle(const stg_dbatch* d, int64_t b, const uint32_t* desc, const float* val, const float* raw, float* out) {
+  if (!d || !desc || !val || !out || b < 0 || b >= d->v.n_bundles) return fail(nullptr, STG_EINVAL, "stg_unpack_bpcov_bundle: bad argument");
+  for (int s = 0; s < 3; s++)
+    if (!unpack_lane<false>(d, b, s, desc, val, raw, out + (size_t)s * d->h_len[b])) return fail(nullptr, STG_EINVAL, "stg_unpack_bpcov_bundle: bad argument");
+  return STG_OK;
+}
+
+// What ONE worker thread of the host does with its share of a batch: bundle after bundle, BundleData::bpcov of the bundle into
+// the thread's own arrays (`work`, reused from bundle to bundle as the reference reuses its BundleData: bundle.h:398-405), where
+// printResults would read it.  `check` (may be NULL) receives the sum over the bundles of the last lane-1 element, so that the
+// work cannot be skipped.
+int stg_unpack_bpcov_stream(const stg_dbatch* d, int64_t b0, int64_t b1, const uint32_t* desc, const float* val, const float* raw,
+                            float* work, int64_t work_floats, double* check) {
+  if (!d || !desc || !val || !work || b0 < 0 || b1 > d->v.n_bundles || b0 > b1) return fail(nullptr, STG_EINVAL, "stg_unpack_bpcov_stream: bad argument");
+  double acc = 0;
+  for (int64_t b = b0; b < b1; b++) {
+    const size_t len = d->h_len[b];
+    if ((int64_t)(3 * len) > work_floats) return fail(nullptr, STG_ERANGE, "stg_unpack_bpcov_stream: a bundle is longer than the working arrays");
+    for (int s = 0; s < 3; s++)
+      if (!unpack_lane<false>(d, b, s, desc, val, raw, work + (size_t)s * len)) return fail(nullptr, STG_EINVAL, "stg_unpack_bpcov_stream: bad argument");
+    acc += work[2 * len - 1];
+  }
+  if (check) *check = acc;
   return STG_OK;
 }
 

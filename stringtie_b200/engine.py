@@ -23,7 +23,7 @@ EXPORTS = [
     "stg_builder_add", "stg_builder_packed", "stg_builder_reset", "stg_builder_destroy", "stg_upload", "stg_run",
     "stg_sync", "stg_free_batch", "stg_trim", "stg_cov_layout", "stg_fetch_bpcov", "stg_fetch_bpcov_all", "stg_device_bpcov",
     "stg_upload_wait", "stg_fetch_bpcov_all_begin", "stg_fetch_wait", "stg_fetch_bpcov_lane_begin", "stg_fetch_bpcov_bundle_lane",
-    "stg_pack_bpcov", "stg_fetch_bpcov_packed_begin", "stg_unpack_bpcov", "stg_release_device",
+    "stg_pack_bpcov", "stg_fetch_bpcov_packed_begin", "stg_unpack_bpcov", "stg_unpack_bpcov_bundle", "stg_unpack_bpcov_stream", "stg_release_device",
     "stg_fetch_junction_support", "stg_fetch_junction_pass", "stg_fetch_cov_totals", "stg_query_cov", "stg_trims_capacity", "stg_find_trims", "stg_infer_transcripts", "stg_infer_transcripts_batch",
     "stg_build_groups", "stg_groups_array_info", "stg_fetch_groups_array", "stg_neutral_predictions",
     "stg_assemble", "stg_asm_array_info", "stg_fetch_asm_array", "stg_rewind", "stg_reduce_totals",
@@ -99,6 +99,8 @@ def load_library() -> C.CDLL:
     L.stg_fetch_bpcov_bundle_lane.argtypes = [vp, vp, C.c_int64, C.c_int, c_f32p]
     L.stg_pack_bpcov.argtypes = [vp, vp, c_i64p, c_i64p]
     L.stg_release_device.argtypes = [vp, vp]
+    L.stg_unpack_bpcov_bundle.argtypes = [vp, C.c_int64, C.POINTER(C.c_uint32), c_f32p, c_f32p, c_f32p]
+    L.stg_unpack_bpcov_stream.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(C.c_uint32), c_f32p, c_f32p, c_f32p, C.c_int64, c_f64p]
     L.stg_fetch_bpcov_packed_begin.argtypes = [vp, vp, C.POINTER(C.c_uint32), c_f32p, c_f32p]
     L.stg_unpack_bpcov.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(C.c_uint32), c_f32p, c_f32p, c_f32p]
     L.stg_fetch_wait.argtypes = [vp, vp]
@@ -391,6 +393,20 @@ class Engine:
         cast = lambda p, t: C.cast(C.c_void_p(p), t)
         self._ck(self.L.stg_unpack_bpcov(batch.handle, b0, b1, cast(desc_ptr, C.POINTER(C.c_uint32)), cast(val_ptr, c_f32p), cast(raw_ptr, c_f32p),
                                          cast(out_ptr, c_f32p)))
+
+    def unpack_bpcov_bundle(self, batch: DeviceBatch, b: int, length: int, desc: np.ndarray, val: np.ndarray, raw: np.ndarray) -> np.ndarray:
+        """BundleData::bpcov of bundle b ([3, length], length = end - start + 3) out of the packed form (stg_unpack_bpcov_bundle)."""
+        out = np.zeros(3 * int(length), dtype=np.float32)
+        self._ck(self.L.stg_unpack_bpcov_bundle(batch.handle, b, desc.ctypes.data_as(C.POINTER(C.c_uint32)), ptr(val), ptr(raw), ptr(out)))
+        return out.reshape(3, -1)
+
+    def unpack_bpcov_stream(self, batch: DeviceBatch, b0: int, b1: int, desc_ptr: int, val_ptr: int, raw_ptr: int, work: np.ndarray) -> float:
+        """A worker thread's share [b0, b1) of a batch, bundle after bundle into its own working arrays (stg_unpack_bpcov_stream)."""
+        cast = lambda p, t: C.cast(C.c_void_p(p), t)
+        chk = C.c_double(0.0)
+        self._ck(self.L.stg_unpack_bpcov_stream(batch.handle, b0, b1, cast(desc_ptr, C.POINTER(C.c_uint32)), cast(val_ptr, c_f32p), cast(raw_ptr, c_f32p),
+                                                ptr(work), work.size, C.byref(chk)))
+        return chk.value
 
     def fetch_bpcov_all_begin(self, batch: DeviceBatch, host_ptr: int) -> None:
         """Start the same copy on the copy-out stream (overlaps the group / assembly stages); fetch_wait completes it."""

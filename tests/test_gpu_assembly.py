@@ -157,4 +157,14 @@ def test_packed_bpcov_unpacks_to_the_full_copy(engine):
             for s in range(3):
                 o = int(off[b]) + s * int(stride[b])
                 assert np.array_equal(got[o:o + lens[b]].view(np.uint32), full[o:o + lens[b]].view(np.uint32)), (b, s)
+        # the per-bundle form a host adaptor's worker calls, and a worker's share of the batch through one set of working arrays
+        for b in (0, nb // 3, nb - 1):
+            one = engine.unpack_bpcov_bundle(batch, b, int(lens[b]), desc, val, raw)
+            for s in range(3):
+                o = int(off[b]) + s * int(stride[b])
+                assert np.array_equal(one[s].view(np.uint32), full[o:o + lens[b]].view(np.uint32))
+        work = np.zeros(3 * int(lens.max()), np.float32)
+        chk = engine.unpack_bpcov_stream(batch, 0, nb, desc.ctypes.data, val.ctypes.data, raw.ctypes.data, work)
+        want = sum(float(full[int(off[b]) + int(stride[b]) + int(lens[b]) - 1]) for b in range(nb))
+        assert chk == want
         batch.free()
