@@ -235,13 +235,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    stage_wall = {}
+
     def all_stages(b, after_run=None):
+        t0 = time.perf_counter()
         eng.run(b, sync=False)
+        t1 = time.perf_counter()
         if after_run is not None:
             after_run(b)
+        t2 = time.perf_counter()
         eng.build_groups(b)
+        t3 = time.perf_counter()
         eng.neutral_predictions_only(b)
         eng.assemble(b)
+        t4 = time.perf_counter()
+        for k, v in (("run_issue", t1 - t0), ("pack_bpcov", t2 - t1), ("build_groups", t3 - t2), ("neutral+assemble", t4 - t3)):
+            stage_wall[k] = stage_wall.get(k, 0.0) + v
         if dist is not None:
             # the path's only collective (stringtie.cpp:1490-1497): the global totals of the FPKM / TPM pass, reduced on the
             # device and all-reduced from there — no host round trip
@@ -410,7 +419,7 @@ def main():
         single = time.perf_counter() - t0
         n_e2e = max(1, min(args.steps, 5))
         barrier()
-        phases.clear()
+        phases.clear(); stage_wall.clear()
         pool0 = eng.pool_stats()
         t0 = time.perf_counter()
         e2e_pass(n_e2e)
@@ -426,6 +435,7 @@ def main():
                "d2h_bytes_per_step": d2h[0], "ms_per_step": 1e3 * wall, "steps": n_e2e,
                "single_batch_ms": 1e3 * single,
                "host_phases_ms_per_step": {k: 1e3 * v / n_e2e for k, v in phases.items()},
+               "stages_host_wall_ms_per_step": {k: 1e3 * v / n_e2e for k, v in stage_wall.items()},
                "bpcov_copied_back": cov_host is not None,
                "device_pool": {"cudaMalloc_calls_in_timed_region": pool1["cudaMalloc_calls"] - pool0["cudaMalloc_calls"],
                                "cudaFree_calls_in_timed_region": pool1["cudaFree_calls"] - pool0["cudaFree_calls"],
@@ -460,7 +470,7 @@ def main():
     alg_cov = 24.0 * L + 13.0 * S + 8.0 * J       # DESIGN.md §6 / SURVEY.md §8d: algorithmic bytes of the coverage stage
     traffic = None
     try:  # DRAM bytes of the bpcov kernels from the committed ncu --set full capture (valid for the default workload shape)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r4_traffic.json")))
         traffic = float(tj["traffic_bytes_per_pass"])
     except Exception:
         pass
