@@ -237,7 +237,7 @@ def main():
 
     stage_wall = {}
 
-    def all_stages(b, after_run=None):
+    def all_stages(b, after_run=None, after_groups=None):
         t0 = time.perf_counter()
         eng.run(b, sync=False)
         t1 = time.perf_counter()
@@ -246,6 +246,8 @@ def main():
         t2 = time.perf_counter()
         eng.build_groups(b)
         t3 = time.perf_counter()
+        if after_groups is not None:
+            after_groups()
         eng.neutral_predictions_only(b)
         eng.assemble(b)
         t4 = time.perf_counter()
@@ -360,7 +362,15 @@ def main():
             if nraw_ > pk[k]["cap"]:
                 raise SystemExit("bench.py: packed bpcov outgrew its host buffer")
             pk_stats.update({"sub_tile_lanes": 3 * nt_, "lanes_sent_in_full": nraw_})
-            eng.fetch_bpcov_packed_begin(b, pk[k]["desc"].data_ptr(), pk[k]["val"].data_ptr(), pk[k]["raw"].data_ptr())   # copy-out stream
+            if os.environ.get("STGPU_BENCH_D2H_EARLY") == "1":   # (experiment knob: the copy beside the group stage costs its walk kernels 40 ms)
+                eng.fetch_bpcov_packed_begin(b, pk[k]["desc"].data_ptr(), pk[k]["val"].data_ptr(), pk[k]["raw"].data_ptr())
+
+        def start_cov_copy_late(b):
+            # the packed bpcov leaves on the copy-out stream beside the assembly stages, not beside the read loop of rows a8 + a9: its
+            # latency-bound walk kernels lose a third of their speed to a concurrent device-to-host copy (measured: 173 against 121 ms)
+            if cov_host is not None and os.environ.get("STGPU_BENCH_D2H_EARLY") != "1":
+                k = seq[0] % 2
+                eng.fetch_bpcov_packed_begin(b, pk[k]["desc"].data_ptr(), pk[k]["val"].data_ptr(), pk[k]["raw"].data_ptr())
 
         phases = {}
 
@@ -369,10 +379,18 @@ def main():
             phases[name] = phases.get(name, 0.0) + (t - t0)
             return t
 
-        def consume(b):
+        def consume(b, after_groups=None):
             t = time.perf_counter()
-            all_stages(b, after_run=start_cov_copy)
+            def behind_groups():
+                start_cov_copy_late(b)
+                if after_groups is not None:
+                    after_groups()
+            all_stages(b, after_run=start_cov_copy, after_groups=behind_groups)
             t = tick("stages", t)
+            if e2e_prof:
+                eng.sync()
+                for name, ms in eng.kernel_times():
+                    e2e_kernel.setdefault(name, []).append(ms)
             p = eng.fetch_predictions(b)
             n = eng.fetch_neutral(b)
             nf = eng.fetch_groups_array(b, "NUM_FRAGMENTS"); fl = eng.fetch_groups_array(b, "FRAG_LEN")
@@ -390,7 +408,7 @@ def main():
                     # a worker thread: BundleData::bpcov of its bundles, one after the other, in its own (reused) arrays
                     return eng.unpack_bpcov_stream(b, lo, hi, pk[k]["desc"].data_ptr(), pk[k]["val"].data_ptr(), pk[k]["raw"].data_ptr(),
                                                    np.empty(3 * max_len, dtype=np.float32))
-                futs = [unpackers.submit(unpack_share, lo, min(nb_, lo + step)) for lo in range(0, nb_, step)]
+                futs = [unpackers.submit(unpack_share, lo, min(nb_, lo + step)) for lo in range(0, nb_, step)] if os.environ.get("STGPU_BENCH_SKIP_UNPACK") != "1" else []
                 pending.append((b, futs))
                 seq[0] += 1
             else:
@@ -398,15 +416,26 @@ def main():
             d2h[0] = nbytes
             tick("free", t)
 
+        e2e_prof = os.environ.get("STGPU_BENCH_E2E_PROFILE") == "1"   # experiment: device time of every stage inside the e2e passes
+        e2e_kernel = {}
+        if e2e_prof:
+            eng.set_profiling(True)
+        late_upload = os.environ.get("STGPU_BENCH_LATE_UPLOAD") == "1"   # experiment: upload of batch i+1 only behind the group stage of batch i
+
         def e2e_pass(n):
             fut = uploader.submit(eng.upload_packed, pb, keep)
             for i in range(n):
                 t = time.perf_counter()
                 b = fut.result()
                 tick("wait_upload_issue", t)
-                if i + 1 < n:
-                    fut = uploader.submit(eng.upload_packed, pb, keep)
-                consume(b)
+                nxt = {}
+                def submit_next():
+                    nxt["fut"] = uploader.submit(eng.upload_packed, pb, keep)
+                if i + 1 < n and not late_upload:
+                    submit_next()
+                consume(b, after_groups=submit_next if (i + 1 < n and late_upload) else None)
+                if "fut" in nxt:
+                    fut = nxt["fut"]
             t = time.perf_counter()
             finish_pending()           # the last batch's bpcov is unpacked inside the timed region too
             tick("wait_last_unpack", t)
@@ -436,6 +465,7 @@ def main():
                "single_batch_ms": 1e3 * single,
                "host_phases_ms_per_step": {k: 1e3 * v / n_e2e for k, v in phases.items()},
                "stages_host_wall_ms_per_step": {k: 1e3 * v / n_e2e for k, v in stage_wall.items()},
+               "device_ms_inside_e2e": {k: statistics.mean(v[-n_e2e:]) for k, v in e2e_kernel.items()} if e2e_prof else None,
                "bpcov_copied_back": cov_host is not None,
                "device_pool": {"cudaMalloc_calls_in_timed_region": pool1["cudaMalloc_calls"] - pool0["cudaMalloc_calls"],
                                "cudaFree_calls_in_timed_region": pool1["cudaFree_calls"] - pool0["cudaFree_calls"],
