@@ -168,3 +168,33 @@ def test_packed_bpcov_unpacks_to_the_full_copy(engine):
         want = sum(float(full[int(off[b]) + int(stride[b]) + int(lens[b]) - 1]) for b in range(nb))
         assert chk == want
         batch.free()
+
+
+def test_release_device_keeps_the_handle_for_unpacking(engine):
+    """stg_release_device: the device memory of a batch goes back to the pool (no cudaFree), the handle still unpacks bpcov, and the
+    stages refuse to run on it."""
+    a = synth.make_batch(n_bundles=40, reads_per_bundle=500, seed=3)
+    batch = engine.upload(a)
+    engine.run(batch)
+    full = engine.fetch_bpcov_all(batch)
+    nt, nraw = engine.pack_bpcov(batch)
+    desc = np.zeros(3 * nt, np.uint32); val = np.zeros(3 * nt, np.float32); raw = np.zeros(max(1, nraw) * 512, np.float32)
+    engine.fetch_bpcov_packed_begin(batch, desc.ctypes.data, val.ctypes.data, raw.ctypes.data)
+    engine.fetch_wait(batch)
+    before = engine.pool_stats()
+    engine.release_device(batch)
+    after = engine.pool_stats()
+    assert after["pool_bytes"] > before["pool_bytes"] and after["cudaFree_calls"] == before["cudaFree_calls"]
+    off, stride, tot = batch.layout()
+    lens = a["b_end"].astype(np.int64) - a["b_start"].astype(np.int64) + 3
+    one = engine.unpack_bpcov_bundle(batch, 7, int(lens[7]), desc, val, raw)
+    for s in range(3):
+        o = int(off[7]) + s * int(stride[7])
+        assert np.array_equal(one[s].view(np.uint32), full[o:o + lens[7]].view(np.uint32))
+    with pytest.raises(Exception):
+        engine.run(batch)
+    batch.free()
+    # a second batch of the same shape is served from the pool
+    m0 = engine.pool_stats()["cudaMalloc_calls"]
+    b2 = engine.upload(a); engine.run(b2); b2.free()
+    assert engine.pool_stats()["cudaMalloc_calls"] == m0
