@@ -514,7 +514,16 @@ STG_HD int tf_cmp(const TfG& f, int a, int b) {
 // GPVec::qSort (gclib/GVec.hh:896-920): Hoare partition around the middle element, not stable; comparators return 0 on
 // ties, so the permutation it leaves is part of the result (SURVEY.md §7 hard part 3).  The two halves are independent,
 // so an explicit stack (smaller half first) gives the same permutation as the reference's recursion.
+// The sort keys travel WITH the list (klo / khi / kab [position], swapped together with it) instead of being looked up
+// through the slot: the two scans of a partition then read consecutive words (one cache line per 32 steps) where the
+// indirect form paid two dependent loads from L2 per comparison — the sort of the largest graph was the tail of asm_flow.
+// The three key arrays are koff / klen / ab of the final list, which is only written after the sort.
 STG_HDN inline void tf_sort_ref(const TfG& f, int32_t* list, int n) {
+  uint32_t* klo = f.koff; uint32_t* khi = f.klen; float* kab = f.ab;
+  for (int t = 0; t < n; t++) {
+    const int sl = list[t];
+    klo[t] = (uint32_t)f.skey[sl]; khi[t] = (uint32_t)(f.skey[sl] >> 32); kab[t] = f.w_ab[sl];
+  }
   int stack[2 * 48];
   int sp = 0;
   if (n < 2) return;
@@ -522,11 +531,25 @@ STG_HDN inline void tf_sort_ref(const TfG& f, int32_t* list, int n) {
   while (sp) {
     const int R = stack[--sp], L = stack[--sp];
     int I = L, J = R;
-    const int P = list[L + ((R - L) >> 1)];
+    const int M = L + ((R - L) >> 1);
+    const unsigned long long pk = ((unsigned long long)khi[M] << 32) | klo[M];   // the pivot ELEMENT's keys (trCmp: larger keys first)
+    const float pa = kab[M];
     do {
-      while (tf_cmp(f, list[I], P) < 0) I++;
-      while (tf_cmp(f, list[J], P) > 0) J--;
-      if (I <= J) { const int t = list[I]; list[I] = list[J]; list[J] = t; I++; J--; }
+      for (;;) {    // while (trCmp(list[I], P) < 0) I++
+        const unsigned long long k = ((unsigned long long)khi[I] << 32) | klo[I];
+        if (k > pk || (k == pk && kab[I] > pa)) I++; else break;
+      }
+      for (;;) {    // while (trCmp(list[J], P) > 0) J--
+        const unsigned long long k = ((unsigned long long)khi[J] << 32) | klo[J];
+        if (k < pk || (k == pk && kab[J] < pa)) J--; else break;
+      }
+      if (I <= J) {
+        const int t = list[I]; list[I] = list[J]; list[J] = t;
+        const uint32_t a = klo[I]; klo[I] = klo[J]; klo[J] = a;
+        const uint32_t b = khi[I]; khi[I] = khi[J]; khi[J] = b;
+        const float c = kab[I]; kab[I] = kab[J]; kab[J] = c;
+        I++; J--;
+      }
     } while (I <= J);
     const bool left = L < J, right = I < R;
     if (left && right) {
@@ -760,6 +783,7 @@ struct FlowScratch {             // per graph
   uint8_t* prev_edge;            // [edges] prevpath's edge bits
   int32_t* node2path;            // [gno]
   float *capl, *capr, *suml, *sumr, *nodeflux;   // [gno + 1], indexed by position on the path
+  int dbg_iters;                 // paths tried (STGPU_ASM_DEBUG)
 };
 
 struct PredOut {                 // predictions of the whole batch, appended as they are stored (any order across graphs)
@@ -1203,7 +1227,9 @@ STG_HDN inline int find_transcripts_warp(const Graph& g, TfG& f, FlowScratch& S,
   float maxcov = 0.f;
   const int istr_words = (f.nt + 63) >> 6;
   int guard = 0;
+  S.dbg_iters = 0;
   while (S.nodecov[maxi] >= 1.f && !*err) {
+    S.dbg_iters++;
     // a fresh path
     for (int w = lane; w < nwn; w += WP_N) S.pathpat[w] = 0ull;
     for (int w = lane; w < istr_words; w += WP_N) S.istr[w] = 0ull;

@@ -372,6 +372,7 @@ __global__ void __launch_bounds__(256) asm_flow_order_kernel(AsmView A, uint32_t
   if (gi < A.n_graphs) order[atomicAdd(&bins[flow_bin(flow_work(A, gi))], 1u)] = (uint32_t)gi;
 }
 
+__device__ int g_asm_debug = 0;   // STGPU_ASM_DEBUG: the graphs that keep a warp of asm_flow longest
 __device__ void asm_flow_graph(const DevBatchView& v, const AsmView& A, const AsmParams& P, const int64_t gi) {
   const int lane = threadIdx.x & 31;
   const Graph gr = A.graphs[gi];
@@ -389,8 +390,10 @@ __device__ void asm_flow_graph(const DevBatchView& v, const AsmView& A, const As
   f.order = A.f_order + t0; f.w_koff = A.f_wkoff + t0; f.w_klen = A.f_wklen + t0; f.w_ab = A.f_wab + t0; f.skey = A.f_skey + t0;
   f.e_cov = A.f_ecov + A.x_edge[gi];
   uint32_t err = 0;
+  const long long tp0 = g_asm_debug ? clock64() : 0;
   const int nt = process_transfrags_warp(gr, f, &err);
   f.nt = nt;
+  const long long tp1 = g_asm_debug ? clock64() : 0;
   FlowScratch S;
   S.nodecov = A.s_nodecov + nb; S.path = A.s_path + nb; S.npath = 0; S.succ = A.s_succ + nb;
   S.pathpat = A.s_pathpat + nb;          // nwn <= gno words
@@ -403,6 +406,9 @@ __device__ void asm_flow_graph(const DevBatchView& v, const AsmView& A, const As
   out.p_exon0 = A.pp_exon0; out.p_nex = A.pp_nex; out.e_start = A.pe_start; out.e_end = A.pe_end; out.e_cov = A.pe_cov;
   int ns = 0;
   if (!err) ns = find_transcripts_warp(gr, f, S, P, out, (int)gi, A.s_exs + nb, A.s_exe + nb, A.s_exc + nb, &err);
+  if (g_asm_debug && lane == 0 && clock64() - tp0 > 8000000)
+    printf("asm_flow graph %lld: %d nodes, %d transfrags, %d paths tried, %d stored | Mcycles: process_transfrags %.1f find_transcripts %.1f\n", (long long)gi,
+           gr.gno, nt, S.dbg_iters, ns, (tp1 - tp0) * 1e-6, (clock64() - tp1) * 1e-6);
   if (lane == 0) { A.g_npred[gi] = (uint32_t)ns; if (err) atomicOr(v.err_flag, err); }
   if (gi == 0 && lane == 0) A.g_npred[A.n_graphs] = 0;
 }
@@ -540,6 +546,7 @@ cudaError_t launch_asm_flow(const DevBatchView& v, const AsmView& A, const AsmPa
   return cudaGetLastError();
 }
 size_t asm_flow_bins_words() { return FLOW_BINS + 1; }
+void asm_set_debug(int on) { cudaMemcpyToSymbol(g_asm_debug, &on, sizeof(int)); }
 cudaError_t launch_asm_geneno(const DevBatchView& v, const AsmView& A, const int32_t* b_geneno, cudaStream_t st) {
   asm_geneno_kernel<<<blocks(v.n_bundles + 1, 256), 256, 0, st>>>(v, A, b_geneno);
   return cudaGetLastError();

@@ -1665,6 +1665,7 @@ int stg_assemble(stg_ctx* ctx, stg_dbatch* d) {
   { Scope s(ctx, "asm_gather", 1); CK(ctx, launch_asm_gather(v, A, st)); }
   uint32_t *flow_bins = nullptr, *flow_order = nullptr;
   TEMP(flow_bins, (int64_t)asm_flow_bins_words()); TEMP(flow_order, G);
+  { static int dbg = -1; if (dbg < 0) { dbg = getenv("STGPU_ASM_DEBUG") ? 1 : 0; asm_set_debug(dbg); } }
   { Scope s(ctx, "asm_flow", 4); CK(ctx, launch_asm_flow(v, A, P, flow_bins, flow_order, ctx->num_sms, st)); }
   uint32_t ctr[2] = {0, 0};
   CK(ctx, small_d2h(ctx, ctr, A.p_counters, 8, st));

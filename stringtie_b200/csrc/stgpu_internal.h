@@ -286,6 +286,7 @@ cudaError_t launch_asm_gather(const DevBatchView& v, const AsmView& A, cudaStrea
 cudaError_t launch_asm_flow(const DevBatchView& v, const AsmView& A, const AsmParams& P, uint32_t* bins, uint32_t* order, int num_sms,
                             cudaStream_t st);
 size_t asm_flow_bins_words();
+void asm_set_debug(int on);
 cudaError_t launch_asm_geneno(const DevBatchView& v, const AsmView& A, const int32_t* b_geneno, cudaStream_t st);
 cudaError_t launch_asm_pred_scatter(const AsmView& A, uint32_t npool, cudaStream_t st);
 cudaError_t launch_asm_exon_scatter(const AsmView& A, uint32_t npool, cudaStream_t st);
