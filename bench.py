@@ -309,6 +309,11 @@ def main():
     # ---- end-to-end through the C ABI from pinned host buffers ------------------------------------------------
     e2e = None
     if not args.skip_e2e:
+        # this process drives the GPU from Python beside its uploader / unpacking threads: a thread that comes back from a C call
+        # waits for the interpreter lock up to the switch interval (5 ms by default) — keep that out of the measurement
+        sys.setswitchinterval(float(os.environ.get("STGPU_BENCH_SWITCH_INTERVAL", "1e-4")))
+        import gc
+        gc.collect(); gc.freeze(); gc.disable()   # no collector pauses inside the timed passes either
         from stringtie_b200.stgb import INPUT_FIELDS
         pinned = {k: torch.from_numpy(np.ascontiguousarray(arrays[k])).pin_memory() for k in INPUT_FIELDS}
         parr = {k: v.numpy() for k, v in pinned.items()}
@@ -446,7 +451,9 @@ def main():
         e2e_pass(1)
         barrier()
         single = time.perf_counter() - t0
-        n_e2e = max(1, min(args.steps, 5))
+        # (the first batch of a pass waits ~90 ms for its own upload and the last one's unpacking has nothing to hide behind: with
+        # few batches this fill and drain is a fifth of the measurement, so the timed pass is 2 x steps batches, at most 10)
+        n_e2e = max(1, min(2 * args.steps, 10))
         barrier()
         phases.clear(); stage_wall.clear()
         pool0 = eng.pool_stats()

@@ -687,12 +687,17 @@ int stg_release_device(stg_ctx* ctx, stg_dbatch* d) {
 int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   if (!ctx || !d) return fail(ctx, STG_EINVAL, "stg_run: null argument");
   if (d->released) return fail(ctx, STG_EINVAL, "stg_run: the batch's device memory has been released");
+  static const bool run_dbg = getenv("STGPU_RUN_DEBUG") != nullptr;   // host clock at the stage's sync points
+  struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
   CK(ctx, cudaSetDevice(ctx->device));
   DevBatchView& v = d->v;
   cudaStream_t st = ctx->stream;
   StageScope stage_scope(ctx);   // an early return leaves no staged read-back behind
+  auto mark = [&](const char* what) { if (run_dbg) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); fprintf(stderr, "stg_run: %-28s %8.3f ms\n", what, 1e3 * (double)(t.tv_sec - ts0.tv_sec) + 1e-6 * (double)(t.tv_nsec - ts0.tv_nsec)); } };
   // the caller's host arrays are free again once this returns; a pending D2H of bpcov must not see the rewrite
+  mark("device set");
   CK(ctx, cudaEventSynchronize(d->ev_uploaded));
+  mark("upload waited for");
   if (d->out_pending) { CK(ctx, cudaStreamSynchronize(ctx->out_stream)); d->out_pending = false; }
   ctx->timed.clear();
   ctx->event_used = 0;
@@ -715,7 +720,9 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
     uint32_t err = 0;
     CK(ctx, small_d2h(ctx, &n_ivl, v.r_ivl_cnt + v.n_reads, sizeof(uint32_t), st));
     CK(ctx, small_d2h(ctx, &err, v.err_flag, sizeof(uint32_t), st));
+    mark("count + scan enqueued");
     CK(ctx, small_sync(ctx, st));
+    mark("interval count read back");
     if (err) {
       std::string what;
       if (err & 1u) what += " r_seg_off runs backwards or past n_segs;";
@@ -748,6 +755,7 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
     }
     d->ivl_capacity = cap;
   }
+  mark("interval buffers allocated");
   { Scope s(ctx, "expand_write", 1); CK(ctx, launch_expand_write(v, st)); }
   { Scope s(ctx, "chunk_hull+scans", 10); CK(ctx, launch_chunk_hull(v, st)); }
   // second read-back: the size of the (chunk x tile) counter matrix
@@ -755,6 +763,7 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   if (v.n_chunks) {
     CK(ctx, small_d2h(ctx, &n_cells, v.ch_row_off + v.n_chunks, sizeof(uint32_t), st));
     CK(ctx, small_sync(ctx, st));
+    mark("cell count read back");
   }
   v.n_cells = n_cells;
   if ((int64_t)n_cells > d->cell_capacity) {
@@ -773,12 +782,14 @@ int stg_run(stg_ctx* ctx, stg_dbatch* d) {
   { Scope s(ctx, "cov_fill", 1); CK(ctx, launch_cov_fill(v, ctx->num_sms, st)); }
   CK(ctx, cudaEventRecord(d->ev_cov, st));   // bpcov is final from here on (nothing later writes it)
   { Scope s(ctx, "cov_totals", 1); CK(ctx, launch_cov_totals(v, st)); }
+  mark("tile kernels enqueued");
   {
     JuncParams jp{ctx->params.junctionsupport, ctx->params.sserror, ctx->params.junctionthr, ctx->params.eonly};
     Scope s(ctx, "junction_pass", 1);
     CK(ctx, launch_junc_pass(v, jp, st));
   }
   d->ran = true;
+  mark("junction pass enqueued");
   return STG_OK;
 }
 

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -218,7 +219,14 @@ class Engine:
         return DeviceBatch(self, h.value, keep, int(pb.n_bundles), int(pb.n_juncs))
 
     def run(self, batch: DeviceBatch, sync: bool = True):
-        self._ck(self.L.stg_run(self.ctx, batch.handle))
+        if os.environ.get("STGPU_RUN_DEBUG"):
+            import time
+            t0 = time.perf_counter()
+            rc = self.L.stg_run(self.ctx, batch.handle)
+            print("Engine.run: stg_run took %.3f ms of Python's clock" % (1e3 * (time.perf_counter() - t0)), file=sys.stderr)
+            self._ck(rc)
+        else:
+            self._ck(self.L.stg_run(self.ctx, batch.handle))
         if sync:
             self.sync()
 
