@@ -321,8 +321,8 @@ def main():
         cov_host = None
         pk = None
         max_len = 0
-        # the host's worker threads: this rank's share of the cores, less the ones that drive the GPU and the upload
-        host_threads = max(1, min(6, (os.cpu_count() or 4) // max(1, world) - 3))
+        # the host's worker threads: this rank's share of the cores, less the one that drives the GPU (at most 6: more only get in its way)
+        host_threads = max(1, min(6, (os.cpu_count() or 4) // max(1, world) - 1))
         if os.environ.get("STGPU_BENCH_UNPACK_THREADS"):
             host_threads = max(1, int(os.environ["STGPU_BENCH_UNPACK_THREADS"]))
         if not args.e2e_no_bpcov:
