@@ -56,6 +56,13 @@ def build_workload(parts: int, part_bundles: int, rank: int):
     from stringtie_b200 import synth
     paths = [os.path.join(tempfile.gettempdir(), f"stg_c2_part_{part_bundles}_{SEED + 1000 * rank + i}.npz") for i in range(parts)]
     todo = [(part_bundles, SEED + 1000 * rank + i, p) for i, p in enumerate(paths) if not os.path.exists(p)]
+    if todo and rank == 0 and int(os.environ.get("LOCAL_RANK", "0")) != 0:
+        # every rank of a multi-rank run assembles the SAME workload (seed of rank 0): local rank 0 generates the parts (atomic
+        # rename), the others wait for the files instead of generating them again
+        t_wait = time.time()
+        while any(not os.path.exists(p) for p in paths) and time.time() - t_wait < 900:
+            time.sleep(0.5)
+        todo = [(part_bundles, SEED + i, p) for i, p in enumerate(paths) if not os.path.exists(p)]
     if todo:
         import multiprocessing as mp
         nproc = max(1, min(len(todo), (os.cpu_count() or 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
@@ -164,7 +171,7 @@ def main():
     workload_name = (f"C2 synthetic short-read: {args.parts} x {args.part_bundles} independently drawn loci "
                      f"(~{args.parts * args.part_bundles * READS_PER_BUNDLE / 1e6:.0f} M alignments, 2x150 PE, de novo)")
     config = {"workload": workload_name,
-              "per_gpu": ("one full workload per rank, seeds differ by rank (weak scaling)" if args.scaling == "weak" else
+              "per_gpu": ("every rank assembles the same full C2 workload: equal work per GPU (weak scaling)" if args.scaling == "weak" else
                           "ONE workload split across the ranks by stg_shard_assign (strong scaling)"),
               "l2": "inputs_larger_than_L2",
               "stages": ["a1-a5 coverage + junction support (count_good_junctions)", "a7 junction pass + good_junc",
@@ -197,7 +204,10 @@ def main():
 
     # ---------------- our arm ----------------------------------------------------------------------------------
     # the workload first (worker processes are forked: no CUDA context may exist yet)
-    base, arrays = build_workload(args.parts, args.part_bundles, rank if args.scaling == "weak" else 0)
+    # weak scaling: every rank assembles the same C2 workload (equal work per GPU: the stage's time is the latency of its deepest
+    # bundle, and independently drawn workloads differ by 2x in that — measured 231 against 439 ms for two seeds —, which the
+    # all-reduce of the totals would turn into the step time of every rank); strong scaling splits that one workload
+    base, arrays = build_workload(args.parts, args.part_bundles, 0)
     import torch
     from stringtie_b200 import synth
     from stringtie_b200.abi import make_packed
