@@ -65,7 +65,7 @@ def build_workload(parts: int, part_bundles: int, rank: int):
         todo = [(part_bundles, SEED + i, p) for i, p in enumerate(paths) if not os.path.exists(p)]
     if todo:
         import multiprocessing as mp
-        nproc = max(1, min(len(todo), (os.cpu_count() or 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+        nproc = max(1, min(len(todo), os.cpu_count() or 2))   # (the other local ranks wait for these files)
         with mp.get_context("fork").Pool(nproc) as pool:
             pool.map(_make_part, todo)
     loaded = []
