@@ -4,7 +4,7 @@
 // tools/asm_hostcheck.py), starting from the reference's OWN state after the bundles were formed (a9 / a9b arrays), so
 // that the graph / transfrag / flow code can be debugged on a CPU-only box against the reference's stage dumps.
 // Writes what it computed as a10_* / a11_* / a12_* / hp_* arrays for tools/asm_hostcheck.py to compare.
-//   nvcc -std=c++17 -O1 -Xcompiler -ffp-contract=off -o tools/_build/asm_hostcheck tools/asm_hostcheck.cu
+//   nvcc -std=c++17 -O1 -gencode arch=compute_100a,code=sm_100a -Xcompiler -ffp-contract=off -o tools/_build/asm_hostcheck tools/asm_hostcheck.cu
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
