@@ -164,7 +164,10 @@ int stg_builder_destroy(stg_builder* b);
  *             then the arrays must stay valid until stg_upload_wait, stg_run or stg_free_batch of that batch returns.
  *             The copy-in stream is separate from the compute stream: batch i+1 may be uploaded (from another host
  *             thread, or before the stage calls of batch i) while batch i computes.
- * stg_run:    wait for the batch's upload, enqueue every kernel of the stages listed at the top of this file.
+ * stg_run:    wait for the batch's upload, enqueue every kernel of the stages listed at the top of this file.  The call
+ *             blocks the host twice for a 4-byte read-back that sizes its buffers (interval count, cell count: ~6 ms into a
+ *             20 ms stage on a 10^8-alignment batch) and returns with the tile kernels and the junction pass still in flight;
+ *             stg_build_groups / stg_assemble likewise read a few counts back between their kernels.
  * stg_sync:   wait for the context stream.                                                            */
 int stg_upload(stg_ctx* ctx, const stg_packed_batch* host, stg_dbatch** out);
 int stg_upload_wait(stg_ctx* ctx, stg_dbatch* batch);
