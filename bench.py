@@ -535,7 +535,7 @@ def main():
                                     "bound": "latency of the deepest bundle (one CTA / warp walks it in read order): not an HBM-bound kernel"}}
 
     cpu_baseline = None
-    if not args.skip_cpu_baseline:
+    if not args.skip_cpu_baseline and world == 1:   # the CPU baseline is reported at N = 1 only (the reference arm covers every N)
         cpu_baseline = reference_hot(base, 2000, os.cpu_count() or 1, 2, stages=("--full", "--a7", "--a9b", "--a11"))
 
     line = {"metric": METRIC, "value": job_reads / (ms_step * 1e-3), "unit": "reads/s", "n_gpus": world,
