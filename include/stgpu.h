@@ -20,8 +20,16 @@
  *   a7  junction pass of build_graphs, good_junc -> stg_run(), kernel junc_pass; stg_fetch_junction_pass()
  *   a8  per-read junction repair, un-pairing     -> stg_build_groups(), kernel groups_walk
  *   a9  groups, colours, bundles / bundlenodes   -> stg_build_groups(), kernels groups_walk / groups_colour
- *   a10 (part) find_all_trims                    -> stg_find_trims(), kernel find_trims
- *   a19 (part) neutral single-exon predictions   -> stg_neutral_predictions(), kernels neutral_* + find_trims
+ *   a10 create_graph (+ find_all_trims)          -> stg_assemble(), kernels asm_sweep / asm_finish; stg_find_trims()
+ *   a11 read -> transfrag, update_abundance      -> stg_assemble(), kernels asm_frag_*, tf_*, nodecov_*
+ *   a12 process_transfrags                       -> stg_assemble(), kernel asm_flow
+ *   a13-a15 find_transcripts / push_max_flow /
+ *       store_transcript                         -> stg_assemble(), kernel asm_flow; BundleData::pred via stg_fetch_asm_array()
+ *   a19 (de novo part) neutral single-exon preds -> stg_neutral_predictions(), kernels neutral_* + find_trims
+ *   x1  oversized bundles                        -> stg_build_groups() (thread-block clusters), stg_assemble() (CTA-wide ordered sums)
+ *   b   int infer_transcripts(BundleData*)       -> stg_infer_transcripts(), stg_infer_transcripts_batch()
+ * Refused with STG_EUNSUPPORTED (no CPU path behind them): guides / -e (a17), long reads / --mix (a6, a16), nascent (a18),
+ * --viral, --ptf, splice-consensus filtering from the genome sequence; printResults (a20) stays on the host.
  */
 #ifndef STGPU_H_
 #define STGPU_H_
@@ -32,7 +40,7 @@
 extern "C" {
 #endif
 
-#define STG_ABI_VERSION 5 /* 2: stg_build_groups, stg_neutral_predictions, stg_find_trims and the groups array fetch */
+#define STG_ABI_VERSION 5 /* 2: groups; 3: stg_assemble, predictions; 4: copy-in / copy-out streams; 5: bpcov lane-major + packed, pool stats */
 #define STG_BSIZE 10000 /* rlink.cpp:11 — block size of the blocked prefix sums in bpcov */
 
 enum {
